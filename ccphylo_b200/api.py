@@ -1,0 +1,287 @@
+"""ctypes binding of the C-ABI in include/ccphylo_gpu.h.
+
+This is the host-side mirror used by the tests and the bench.  It adds no
+arithmetic of its own: every result comes from the CUDA library, and loading
+fails loudly when the library is missing (there is no CPU fallback).
+
+Reference interface mirrored: ``fsaCmpThreadOut`` (fsacmpthrd.h:49) with its
+two workers ``cmpairFsaThrd`` (pair mode, fsacmpthrd.c:261) and ``cmpFsaThrd``
+(shared-mask mode, fsacmpthrd.c:108).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libccphylo_gpu.so")
+
+ELEM_DTYPE = {8: np.float64, 4: np.float32, 2: np.uint16, 1: np.uint8}
+KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA = 0, 1, 2
+
+EXPORTS = [
+    "ccg_strerror", "ccg_last_error", "ccg_init", "ccg_destroy", "ccg_set_stream", "ccg_set_kernel", "ccg_sync",
+    "ccg_set_partition", "ccg_tile_edge", "ccg_partition_cells", "ccg_partition_tiles", "ccg_set_problem", "ccg_put_global_mask", "ccg_put_samples_packed",
+    "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
+    "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
+    "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms",
+]
+
+
+class CcgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ccphylo_gpu error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libccphylo_gpu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the CUDA library is the only implementation; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i, u, d, ll = C.c_void_p, C.c_int, C.c_uint, C.c_double, C.c_longlong
+    L.ccg_strerror.restype = C.c_char_p
+    L.ccg_strerror.argtypes = [i]
+    L.ccg_last_error.restype = C.c_char_p
+    L.ccg_last_error.argtypes = [vp]
+    L.ccg_init.argtypes = [C.POINTER(vp), i]
+    L.ccg_destroy.restype = None
+    L.ccg_destroy.argtypes = [vp]
+    L.ccg_set_stream.argtypes = [vp, vp]
+    L.ccg_set_kernel.argtypes = [vp, i]
+    L.ccg_sync.argtypes = [vp]
+    L.ccg_set_partition.argtypes = [vp, i, i]
+    L.ccg_tile_edge.restype = i
+    L.ccg_tile_edge.argtypes = []
+    L.ccg_partition_cells.restype = ll
+    L.ccg_partition_cells.argtypes = [i, i, i]
+    L.ccg_partition_tiles.restype = ll
+    L.ccg_partition_tiles.argtypes = [i, i, i, vp, vp, ll]
+    L.ccg_set_problem.argtypes = [vp, i, i, i]
+    L.ccg_put_global_mask.argtypes = [vp, vp]
+    L.ccg_put_samples_packed.argtypes = [vp, i, i, vp, vp]
+    L.ccg_put_samples_packed_dev.argtypes = [vp, i, i, vp, vp, C.c_long]
+    L.ccg_put_sample_codes.argtypes = [vp, i, vp]
+    L.ccg_get_inc_counts.argtypes = [vp, vp]
+    L.ccg_run_pair.argtypes = [vp, vp, u, u, d, i, d, vp, vp, C.POINTER(i)]
+    L.ccg_run_global.argtypes = [vp, vp, u, i, d, vp, C.POINTER(i), C.POINTER(u)]
+    L.ccg_run_pair_dev.argtypes = [vp, vp, u, u, d, i, d, vp, vp, C.POINTER(i)]
+    L.ccg_run_global_dev.argtypes = [vp, vp, u, i, d, vp, C.POINTER(i), C.POINTER(u)]
+    L.ccg_get_raw_counts.argtypes = [vp, vp, vp]
+    L.ccg_fsa_cmp_thread_out.argtypes = [vp, i, vp, vp, i, d, i, i, vp, vp, vp, u, u, d, u, C.POINTER(i), C.POINTER(u)]
+    L.ccg_host_alloc.restype = vp
+    L.ccg_host_alloc.argtypes = [C.c_size_t]
+    L.ccg_host_free.restype = None
+    L.ccg_host_free.argtypes = [vp]
+    L.ccg_launch_count.restype = ll
+    L.ccg_launch_count.argtypes = [vp]
+    L.ccg_last_kernel.restype = C.c_char_p
+    L.ccg_last_kernel.argtypes = [vp]
+    L.ccg_last_compare_ms.restype = C.c_float
+    L.ccg_last_compare_ms.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def partition_cells(n, rank, world):
+    """Cells of the n-sample lower triangle owned by `rank` of `world` (host only, no device needed)."""
+    return load().ccg_partition_cells(n, rank, world)
+
+
+def partition_tiles(n, rank, world):
+    """(ti, tj) tiles owned by `rank` of `world` (host only, no device needed)."""
+    L = load()
+    k = L.ccg_partition_tiles(n, rank, world, None, None, 0)
+    ti = np.zeros(max(k, 1), dtype=np.int32)
+    tj = np.zeros(max(k, 1), dtype=np.int32)
+    L.ccg_partition_tiles(n, rank, world, ti.ctypes.data, tj.ctypes.data, k)
+    return list(zip(ti[:k].tolist(), tj[:k].tolist()))
+
+
+def words(length):
+    return (length >> 5) + (1 if length & 31 else 0)
+
+
+def cells(dn):
+    return dn * (dn - 1) // 2 if dn > 1 else 0
+
+
+def _row_ptrs(arr2d, skip=None):
+    """Array of row pointers into a C-contiguous 2-D numpy array (NULL where skip[i])."""
+    n = arr2d.shape[0]
+    ptrs = (C.c_void_p * max(n, 1))()
+    base, stride = arr2d.ctypes.data, arr2d.strides[0]
+    for k in range(n):
+        ptrs[k] = None if (skip is not None and skip[k]) else base + k * stride
+    return ptrs
+
+
+class Context:
+    """One GPU context (one per process / GPU), wrapping ``ccg_ctx``."""
+
+    def __init__(self, device=-1):
+        self._L = load()
+        self._h = C.c_void_p()
+        rc = self._L.ccg_init(C.byref(self._h), device)
+        if rc:
+            raise CcgError(rc, self._L.ccg_last_error(None).decode())
+        self.n = self.len = 0
+        self.pair = True
+
+    def _ck(self, rc):
+        if rc:
+            msg = self._L.ccg_last_error(self._h).decode() or self._L.ccg_strerror(rc).decode()
+            raise CcgError(rc, msg)
+
+    def close(self):
+        if self._h:
+            self._L.ccg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- configuration ----
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self._L.ccg_set_stream(self._h, cuda_stream_ptr))
+
+    def set_kernel(self, kernel):
+        self._ck(self._L.ccg_set_kernel(self._h, kernel))
+
+    def set_partition(self, rank, world):
+        self._ck(self._L.ccg_set_partition(self._h, rank, world))
+
+    def sync(self):
+        self._ck(self._L.ccg_sync(self._h))
+
+    def set_problem(self, n, length, pair=True):
+        self._ck(self._L.ccg_set_problem(self._h, n, length, 1 if pair else 0))
+        self.n, self.len, self.pair = n, length, pair
+
+    # ---- uploads ----
+    def put_global_mask(self, mask):
+        mask = np.ascontiguousarray(mask, dtype=np.uint32)
+        assert mask.size >= words(self.len)
+        self._ck(self._L.ccg_put_global_mask(self._h, mask.ctypes.data))
+
+    def put_samples_packed(self, seqs, masks=None, first=0, skip=None):
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint64)
+        sp = _row_ptrs(seqs, skip)
+        mp = None
+        if masks is not None:
+            masks = np.ascontiguousarray(masks, dtype=np.uint32)
+            mp = _row_ptrs(masks, skip)
+        self._ck(self._L.ccg_put_samples_packed(self._h, first, seqs.shape[0], sp, mp))
+
+    def put_samples_packed_dev(self, d_seqs_ptr, d_masks_ptr, count, wstride, first=0):
+        self._ck(self._L.ccg_put_samples_packed_dev(self._h, first, count, d_seqs_ptr, d_masks_ptr, wstride))
+
+    def put_sample_codes(self, idx, codes):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        assert codes.size == self.len
+        self._ck(self._L.ccg_put_sample_codes(self._h, idx, codes.ctypes.data))
+
+    def inc_counts(self):
+        out = np.zeros(max(self.n, 1), dtype=np.uint32)
+        self._ck(self._L.ccg_get_inc_counts(self._h, out.ctypes.data))
+        return out[:self.n]
+
+    # ---- runs ----
+    def run_pair(self, include=None, norm=0, min_length=1, min_cov=0.5, elem_size=8, byte_scale=1.0, want_n=True):
+        dt = ELEM_DTYPE[elem_size]
+        D = np.zeros(max(cells(self.n), 1), dtype=dt)
+        N = np.zeros(max(cells(self.n), 1), dtype=dt) if want_n else None
+        inc = None if include is None else np.ascontiguousarray(include, dtype=np.uint8)
+        dn = C.c_int(0)
+        self._ck(self._L.ccg_run_pair(self._h, None if inc is None else inc.ctypes.data, norm, min_length, min_cov,
+                                      elem_size, byte_scale, D.ctypes.data, N.ctypes.data if want_n else None,
+                                      C.byref(dn)))
+        k = cells(dn.value)
+        return D[:k], (N[:k] if want_n else None), dn.value
+
+    def run_global(self, include=None, norm=0, elem_size=8, byte_scale=1.0):
+        D = np.zeros(max(cells(self.n), 1), dtype=ELEM_DTYPE[elem_size])
+        inc = None if include is None else np.ascontiguousarray(include, dtype=np.uint8)
+        dn, ginc = C.c_int(0), C.c_uint(0)
+        self._ck(self._L.ccg_run_global(self._h, None if inc is None else inc.ctypes.data, norm, elem_size,
+                                        byte_scale, D.ctypes.data, C.byref(dn), C.byref(ginc)))
+        return D[:cells(dn.value)], dn.value, ginc.value
+
+    def run_pair_dev(self, d_D_ptr, d_N_ptr, include=None, norm=0, min_length=1, min_cov=0.5, elem_size=8,
+                     byte_scale=1.0):
+        inc = None if include is None else np.ascontiguousarray(include, dtype=np.uint8)
+        dn = C.c_int(0)
+        self._ck(self._L.ccg_run_pair_dev(self._h, None if inc is None else inc.ctypes.data, norm, min_length,
+                                          min_cov, elem_size, byte_scale, d_D_ptr, d_N_ptr, C.byref(dn)))
+        return dn.value
+
+    def run_global_dev(self, d_D_ptr, include=None, norm=0, elem_size=8, byte_scale=1.0):
+        inc = None if include is None else np.ascontiguousarray(include, dtype=np.uint8)
+        dn, ginc = C.c_int(0), C.c_uint(0)
+        self._ck(self._L.ccg_run_global_dev(self._h, None if inc is None else inc.ctypes.data, norm, elem_size,
+                                            byte_scale, d_D_ptr, C.byref(dn), C.byref(ginc)))
+        return dn.value, ginc.value
+
+    def raw_counts(self, dn):
+        mism = np.zeros(max(cells(dn), 1), dtype=np.uint32)
+        ninc = np.zeros(max(cells(dn), 1), dtype=np.uint32)
+        self._ck(self._L.ccg_get_raw_counts(self._h, mism.ctypes.data, ninc.ctypes.data))
+        return mism[:cells(dn)], ninc[:cells(dn)]
+
+    # ---- introspection ----
+    @property
+    def launches(self):
+        return self._L.ccg_launch_count(self._h)
+
+    @property
+    def last_kernel(self):
+        return self._L.ccg_last_kernel(self._h).decode()
+
+    def last_compare_ms(self):
+        return self._L.ccg_last_compare_ms(self._h)
+
+
+def fsa_cmp_thread_out(seqs, include, includes, length, pair=True, norm=0, min_length=1, min_cov=0.5, proxi=0,
+                       elem_size=8, byte_scale=1.0, want_n=True, ctx=None):
+    """Drop-in for the reference's ``fsaCmpThreadOut`` call (cdist.c:181/184).
+
+    seqs (n, W) u64 and includes (n, W) u32 -- or (1, W) in shared-mask mode --
+    are HOST arrays in the reference's packed formats; include is (n,) u8.
+    Returns (D, N, Dn, global_inc): packed lower-triangular cells over the
+    included samples.
+    """
+    L = load()
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint64)
+    includes = np.ascontiguousarray(includes, dtype=np.uint32)
+    n = seqs.shape[0]
+    include = np.ascontiguousarray(include, dtype=np.uint8)
+    dt = ELEM_DTYPE[elem_size]
+    D = np.zeros(max(cells(n), 1), dtype=dt)
+    N = np.zeros(max(cells(n), 1), dtype=dt) if (want_n and pair) else None
+    sp = _row_ptrs(seqs)
+    if pair:
+        mp = _row_ptrs(includes)
+    else:
+        mp = (C.c_void_p * max(n, 1))()
+        for k in range(max(n, 1)):
+            mp[k] = includes.ctypes.data
+    dn, ginc = C.c_int(0), C.c_uint(0)
+    rc = L.ccg_fsa_cmp_thread_out(ctx._h if ctx else None, 1 if pair else 0, D.ctypes.data,
+                                  N.ctypes.data if N is not None else None, elem_size, byte_scale, n, length, sp,
+                                  include.ctypes.data, mp, norm, min_length, min_cov, proxi, C.byref(dn),
+                                  C.byref(ginc))
+    if rc:
+        msg = L.ccg_last_error(ctx._h if ctx else None).decode() or L.ccg_strerror(rc).decode()
+        raise CcgError(rc, msg)
+    k = cells(dn.value)
+    return D[:k], (N[:k] if N is not None else None), dn.value, ginc.value

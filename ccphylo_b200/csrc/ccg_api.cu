@@ -1,0 +1,594 @@
+/*
+ * ccg_api.cu -- the C-ABI of include/ccphylo_gpu.h: context, device sample
+ * store, uploads, and the run entry points that replace the reference's
+ * fsaCmpThreadOut fan-out (fsacmpthrd.c:76) and its two workers
+ * cmpairFsaThrd (:261) / cmpFsaThrd (:108).
+ *
+ * Host logic only; the arithmetic lives in k_encode.cu / k_pairdist_*.cu.
+ * No CPU fallback: every failure is reported to the caller.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ccg_internal.h"
+
+static char g_init_err[512] = "";
+
+static void set_err(ccg_ctx *ctx, const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(ctx ? ctx->err : g_init_err, 512, fmt, ap);
+	va_end(ap);
+}
+
+#define CK(ctx, call)                                                                              \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                                  \
+		if(e__ != cudaSuccess) {                                                                   \
+			set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+			return CCG_ERR_CUDA;                                                                   \
+		}                                                                                          \
+	} while(0)
+
+extern "C" const char *ccg_strerror(int code) {
+	switch(code) {
+		case CCG_OK: return "ok";
+		case CCG_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+		case CCG_ERR_CUDA: return "CUDA call failed";
+		case CCG_ERR_ARG: return "invalid argument or call order";
+		case CCG_ERR_NOMEM: return "out of memory";
+		case CCG_ERR_UNSUPPORTED: return "unsupported on the GPU path";
+		default: return "unknown error";
+	}
+}
+
+extern "C" const char *ccg_last_error(const ccg_ctx *ctx) { return ctx ? ctx->err : g_init_err; }
+
+extern "C" int ccg_init(ccg_ctx **out, int device) {
+	int count = 0;
+	if(!out) return CCG_ERR_ARG;
+	*out = 0;
+	if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+		set_err(0, "no CUDA device visible: %s", cudaGetErrorString(cudaGetLastError()));
+		return CCG_ERR_NO_DEVICE;
+	}
+	if(device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;
+	if(device >= count) {
+		set_err(0, "device %d requested, %d visible", device, count);
+		return CCG_ERR_NO_DEVICE;
+	}
+	cudaDeviceProp prop;
+	if(cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+		set_err(0, "device %d is compute capability %d.%d; this library is built for sm_100a only", device, prop.major,
+		        prop.minor);
+		return CCG_ERR_NO_DEVICE;
+	}
+	ccg_ctx *ctx = (ccg_ctx *) calloc(1, sizeof(ccg_ctx));
+	if(!ctx) return CCG_ERR_NOMEM;
+	ctx->device = device;
+	ctx->sm_count = prop.multiProcessorCount;
+	ctx->world = 1;
+	if(cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+	   cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+		set_err(0, "context set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+		free(ctx);
+		return CCG_ERR_CUDA;
+	}
+	ctx->stream = ctx->own_stream;
+	*out = ctx;
+	return CCG_OK;
+}
+
+static void free_problem(ccg_ctx *ctx) {
+	cudaFree(ctx->d_planes); ctx->d_planes = 0;
+	cudaFree(ctx->d_gmask); ctx->d_gmask = 0;
+	cudaFree(ctx->d_inc); ctx->d_inc = 0;
+	cudaFree(ctx->d_rank); ctx->d_rank = 0;
+	free(ctx->present); ctx->present = 0;
+	free(ctx->h_rank); ctx->h_rank = 0;
+	ctx->tmap_valid = 0;
+	ctx->n = ctx->len = 0;
+	ctx->last_Dn = 0;
+	ctx->last_ntiles_local = 0;
+}
+
+extern "C" void ccg_destroy(ccg_ctx *ctx) {
+	if(!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	free_problem(ctx);
+	cudaFree(ctx->d_stage);
+	cudaFree(ctx->d_acc);
+	cudaFree(ctx->d_tickets);
+	cudaFree(ctx->d_out_D);
+	cudaFree(ctx->d_out_N);
+	cudaEventDestroy(ctx->ev0);
+	cudaEventDestroy(ctx->ev1);
+	cudaStreamDestroy(ctx->own_stream);
+	free(ctx);
+}
+
+extern "C" int ccg_set_stream(ccg_ctx *ctx, void *cuda_stream) {
+	if(!ctx) return CCG_ERR_ARG;
+	ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+	return CCG_OK;
+}
+
+extern "C" int ccg_set_kernel(ccg_ctx *ctx, int kernel) {
+	if(!ctx || kernel < CCG_KERNEL_AUTO || kernel > CCG_KERNEL_UMMA) return CCG_ERR_ARG;
+	ctx->kernel_choice = kernel;
+	return CCG_OK;
+}
+
+extern "C" int ccg_sync(ccg_ctx *ctx) {
+	if(!ctx) return CCG_ERR_ARG;
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return CCG_OK;
+}
+
+extern "C" int ccg_set_partition(ccg_ctx *ctx, int rank, int world) {
+	if(!ctx || world < 1 || rank < 0 || rank >= world) return CCG_ERR_ARG;
+	ctx->rank = rank;
+	ctx->world = world;
+	return CCG_OK;
+}
+
+static int tile_of(long long t, int *ti, int *tj) {
+	int i = (int) ((sqrt(8.0 * (double) t + 1.0) - 1.0) * 0.5);
+	while((long long) (i + 1) * (i + 2) / 2 <= t) ++i;
+	while((long long) i * (i + 1) / 2 > t) --i;
+	*ti = i;
+	*tj = (int) (t - (long long) i * (i + 1) / 2);
+	return 0;
+}
+
+extern "C" int ccg_tile_edge(void) { return CCG_TILE; }
+
+extern "C" long long ccg_partition_tiles(int n, int rank, int world, int *ti_out, int *tj_out, long long cap) {
+	if(n < 1 || world < 1 || rank < 0 || rank >= world) return 0;
+	int rows = (n + CCG_TILE - 1) / CCG_TILE;
+	long long total = ccg_tiles_total(rows), k = 0;
+	for(long long t = rank; t < total; t += world, ++k) {
+		if(k < cap && ti_out && tj_out) tile_of(t, ti_out + k, tj_out + k);
+	}
+	return k;
+}
+
+extern "C" long long ccg_partition_cells(int n, int rank, int world) {
+	if(n < 2 || world < 1 || rank < 0 || rank >= world) return 0;
+	int rows = (n + CCG_TILE - 1) / CCG_TILE;
+	long long total = ccg_tiles_total(rows), cells = 0;
+	for(long long t = rank; t < total; t += world) {
+		int ti, tj;
+		tile_of(t, &ti, &tj);
+		int hi = n - ti * CCG_TILE; if(hi > CCG_TILE) hi = CCG_TILE;
+		int wj = n - tj * CCG_TILE; if(wj > CCG_TILE) wj = CCG_TILE;
+		if(ti == tj) cells += (long long) hi * (hi - 1) / 2;
+		else cells += (long long) hi * wj;
+	}
+	return cells;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_planes_tmap(ccg_ctx *ctx) {
+	void *fn = 0;
+	cudaDriverEntryPointQueryResult qres;
+	CK(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+	if(!fn || qres != cudaDriverEntryPointSuccess) {
+		set_err(ctx, "cuTensorMapEncodeTiled not available from the driver");
+		return CCG_ERR_CUDA;
+	}
+	cuuint64_t gdim[4] = {CCG_CHUNK_WORDS, (cuuint64_t) ctx->n_pad, (cuuint64_t) ctx->nplanes, (cuuint64_t) ctx->chunks};
+	cuuint64_t gstride[3] = {16, (cuuint64_t) 16 * ctx->n_pad, (cuuint64_t) 16 * ctx->n_pad * ctx->nplanes};
+	cuuint32_t box[4] = {CCG_CHUNK_WORDS, CCG_TILE, (cuuint32_t) ctx->nplanes, (cuuint32_t) ccg_popc_kc()};
+	cuuint32_t estr[4] = {1, 1, 1, 1};
+	CUresult r = ((EncodeTiledFn) fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, ctx->d_planes, gdim, gstride, box,
+	                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+	                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(r != CUDA_SUCCESS) {
+		set_err(ctx, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
+		return CCG_ERR_CUDA;
+	}
+	ctx->tmap_valid = 1;
+	return CCG_OK;
+}
+
+extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
+	if(!ctx || n < 0 || len < 0) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	free_problem(ctx);
+	ctx->n = n;
+	ctx->len = len;
+	ctx->pair_mode = pair_mode ? 1 : 0;
+	ctx->nplanes = pair_mode ? 3 : 2;
+	ctx->words = (len >> 5) + ((len & 31) ? 1 : 0);
+	ctx->chunks = (ctx->words + CCG_CHUNK_WORDS - 1) / CCG_CHUNK_WORDS;
+	ctx->n_pad = ((n + CCG_TILE - 1) / CCG_TILE) * CCG_TILE;
+	if(ctx->n_pad == 0) ctx->n_pad = CCG_TILE;
+	if(ctx->chunks == 0) ctx->chunks = 1;
+	ctx->planes_bytes = (size_t) ctx->chunks * ctx->nplanes * ctx->n_pad * 16;
+	if(cudaMalloc(&ctx->d_planes, ctx->planes_bytes) != cudaSuccess) {
+		set_err(ctx, "cudaMalloc of %zu bytes for the sample store failed: %s", ctx->planes_bytes,
+		        cudaGetErrorString(cudaGetLastError()));
+		ctx->d_planes = 0;
+		return CCG_ERR_NOMEM;
+	}
+	CK(ctx, cudaMemsetAsync(ctx->d_planes, 0, ctx->planes_bytes, ctx->stream));
+	CK(ctx, cudaMalloc(&ctx->d_inc, (size_t) ctx->n_pad * sizeof(unsigned)));
+	CK(ctx, cudaMemsetAsync(ctx->d_inc, 0, (size_t) ctx->n_pad * sizeof(unsigned), ctx->stream));
+	CK(ctx, cudaMalloc(&ctx->d_rank, (size_t) ctx->n_pad * sizeof(int)));
+	if(!pair_mode) {
+		CK(ctx, cudaMalloc(&ctx->d_gmask, (size_t) (ctx->words + 1) * sizeof(uint32_t)));
+		CK(ctx, cudaMemsetAsync(ctx->d_gmask, 0, (size_t) (ctx->words + 1) * sizeof(uint32_t), ctx->stream));
+	}
+	ctx->present = (unsigned char *) calloc((size_t) ctx->n_pad, 1);
+	ctx->h_rank = (int *) malloc((size_t) ctx->n_pad * sizeof(int));
+	if(!ctx->present || !ctx->h_rank) return CCG_ERR_NOMEM;
+	ctx->global_inc = 0;
+	return make_planes_tmap(ctx);
+}
+
+static int ensure_stage(ccg_ctx *ctx, size_t bytes) {
+	if(ctx->stage_bytes >= bytes) return CCG_OK;
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_stage);
+	ctx->d_stage = 0;
+	ctx->stage_bytes = 0;
+	if(cudaMalloc(&ctx->d_stage, bytes) != cudaSuccess) {
+		set_err(ctx, "cudaMalloc of %zu staging bytes failed", bytes);
+		return CCG_ERR_NOMEM;
+	}
+	ctx->stage_bytes = bytes;
+	return CCG_OK;
+}
+
+extern "C" int ccg_put_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
+	if(!ctx || !ctx->d_planes || ctx->pair_mode || !mask) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaMemcpyAsync(ctx->d_gmask, mask, (size_t) ctx->words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+	unsigned inc = 0;
+	for(int w = 0; w < ctx->words; ++w) inc += (unsigned) __builtin_popcount(mask[w]);
+	ctx->global_inc = inc;      /* getNpos(*includes, len), fsacmpthrd.c:164 */
+	return CCG_OK;
+}
+
+extern "C" int ccg_put_samples_packed(ccg_ctx *ctx, int first, int count, const uint64_t *const *seqs,
+                                      const uint32_t *const *includes) {
+	if(!ctx || !ctx->d_planes || first < 0 || count < 0 || first + count > ctx->n || !seqs) return CCG_ERR_ARG;
+	if(ctx->pair_mode && !includes) return CCG_ERR_ARG;
+	if(count == 0 || ctx->words == 0) return CCG_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	const size_t W = (size_t) ctx->words;
+	const size_t row_bytes = W * (ctx->pair_mode ? 12 : 8);
+	size_t batch = ((size_t) 256 << 20) / row_bytes;
+	if(batch < 1) batch = 1;
+	if(batch > (size_t) count) batch = (size_t) count;
+	int rc = ensure_stage(ctx, batch * row_bytes + 64);
+	if(rc) return rc;
+	uint64_t *d_seq = (uint64_t *) ctx->d_stage;
+	uint32_t *d_msk = ctx->pair_mode ? (uint32_t *) (d_seq + batch * W) : 0;
+
+	int k = 0;
+	while(k < count) {
+		/* run of consecutive present rows, at most one staging batch */
+		if(!seqs[k] || (ctx->pair_mode && !includes[k])) { ++k; continue; }
+		int run = 0;
+		while(k + run < count && (size_t) run < batch && seqs[k + run] && (!ctx->pair_mode || includes[k + run])) {
+			CK(ctx, cudaMemcpyAsync(d_seq + (size_t) run * W, seqs[k + run], W * 8, cudaMemcpyHostToDevice, ctx->stream));
+			if(ctx->pair_mode)
+				CK(ctx, cudaMemcpyAsync(d_msk + (size_t) run * W, includes[k + run], W * 4, cudaMemcpyHostToDevice, ctx->stream));
+			ctx->present[first + k + run] = 1;
+			++run;
+		}
+		CK(ctx, ccg_launch_repack(ctx, first + k, run, d_seq, d_msk, (long) W));
+		k += run;
+	}
+	return CCG_OK;
+}
+
+extern "C" int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count, const uint64_t *d_seqs,
+                                          const uint32_t *d_masks, long wstride) {
+	if(!ctx || !ctx->d_planes || first < 0 || count < 0 || first + count > ctx->n || !d_seqs || wstride < ctx->words)
+		return CCG_ERR_ARG;
+	if(ctx->pair_mode && !d_masks) return CCG_ERR_ARG;
+	if(count == 0) return CCG_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, ccg_launch_repack(ctx, first, count, d_seqs, ctx->pair_mode ? d_masks : 0, wstride));
+	memset(ctx->present + first, 1, (size_t) count);
+	return CCG_OK;
+}
+
+extern "C" int ccg_put_sample_codes(ccg_ctx *ctx, int idx, const unsigned char *codes) {
+	if(!ctx || !ctx->d_planes || !ctx->pair_mode || idx < 0 || idx >= ctx->n || !codes) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	size_t stride = ((size_t) ctx->len + 15) & ~(size_t) 15;
+	if(stride == 0) stride = 16;
+	int rc = ensure_stage(ctx, stride + 64);
+	if(rc) return rc;
+	CK(ctx, cudaMemcpyAsync(ctx->d_stage, codes, (size_t) ctx->len, cudaMemcpyHostToDevice, ctx->stream));
+	CK(ctx, ccg_launch_encode_codes(ctx, idx, 1, (const unsigned char *) ctx->d_stage, (long) stride));
+	ctx->present[idx] = 1;
+	return CCG_OK;
+}
+
+extern "C" int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out) {
+	if(!ctx || !ctx->d_inc || !out) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaMemcpyAsync(out, ctx->d_inc, (size_t) ctx->n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return CCG_OK;
+}
+
+/* choose the K split: fill whole waves of resident CTAs as evenly as possible */
+static void choose_ksplit(const ccg_ctx *ctx, long long ntiles, int kc, int *ksplit, int *cps) {
+	const long long slots = 2LL * ctx->sm_count;
+	const int iters_total = (ctx->chunks + kc - 1) / kc;
+	int best = 1;
+	double best_util = -1.0;
+	for(int k = 1; k <= 64; ++k) {
+		if(k > 1 && iters_total / k < 8) break;
+		long long items = ntiles * k;
+		long long waves = (items + slots - 1) / slots;
+		double util = (double) items / (double) (waves * slots);
+		if(util > best_util + 0.02) { best_util = util; best = k; }
+		if(items >= 8 * slots) break;
+	}
+	int per = (iters_total + best - 1) / best;
+	*ksplit = best;
+	*cps = per * kc;
+	/* drop slices that would start past the end */
+	while(*ksplit > 1 && (long long) (*ksplit - 1) * (*cps) >= ctx->chunks) --*ksplit;
+}
+
+static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
+                      double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn_out) {
+	if(!ctx || !ctx->d_planes) return CCG_ERR_ARG;
+	if(elem_size != 8 && elem_size != 4 && elem_size != 2 && elem_size != 1) return CCG_ERR_ARG;
+	if((mode == 0) != (ctx->pair_mode == 1)) {
+		set_err(ctx, "run mode does not match ccg_set_problem(pair_mode=%d)", ctx->pair_mode);
+		return CCG_ERR_ARG;
+	}
+	if(ctx->kernel_choice == CCG_KERNEL_UMMA) {
+		set_err(ctx, "tcgen05 kernel not built into this library yet");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	CK(ctx, cudaSetDevice(ctx->device));
+
+	/* compaction map: included samples in input order (fsacmpthrd.c:305-329) */
+	int Dn = 0;
+	for(int i = 0; i < ctx->n_pad; ++i) {
+		int inc = i < ctx->n && ctx->present[i] && (!include || include[i]);
+		ctx->h_rank[i] = inc ? Dn++ : -1;
+	}
+	ctx->last_Dn = Dn;
+	if(Dn_out) *Dn_out = Dn;
+	ctx->last_ntiles_local = 0;
+	if(Dn < 2) return CCG_OK;
+	CK(ctx, cudaMemcpyAsync(ctx->d_rank, ctx->h_rank, (size_t) ctx->n_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+
+	PopcParams p;
+	memset(&p, 0, sizeof(p));
+	const int tile_rows = ctx->n_pad / CCG_TILE;
+	const long long total = ccg_tiles_total(tile_rows);
+	const long long local = ccg_tiles_local(total, ctx->rank, ctx->world);
+	p.n_pad = ctx->n_pad;
+	p.chunks = ctx->chunks;
+	p.rank = ctx->rank;
+	p.world = ctx->world;
+	p.ntiles_local = (int) local;
+	choose_ksplit(ctx, local > 0 ? local : 1, ccg_popc_kc(), &p.ksplit, &p.chunks_per_split);
+	ctx->last_ntiles_local = (int) local;
+	if(local == 0) return CCG_OK;
+
+	size_t acc_bytes = (size_t) local * 2 * CCG_TILE * CCG_TILE * sizeof(uint32_t);
+	if(ctx->acc_bytes < acc_bytes) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_acc);
+		ctx->d_acc = 0;
+		ctx->acc_bytes = 0;
+		if(cudaMalloc(&ctx->d_acc, acc_bytes) != cudaSuccess) {
+			set_err(ctx, "cudaMalloc of %zu accumulator bytes failed", acc_bytes);
+			return CCG_ERR_NOMEM;
+		}
+		ctx->acc_bytes = acc_bytes;
+	}
+	if(ctx->tickets_count < (size_t) local) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_tickets);
+		ctx->d_tickets = 0;
+		CK(ctx, cudaMalloc(&ctx->d_tickets, (size_t) local * sizeof(unsigned)));
+		ctx->tickets_count = (size_t) local;
+	}
+	if(p.ksplit > 1) {
+		CK(ctx, cudaMemsetAsync(ctx->d_acc, 0, acc_bytes, ctx->stream));
+		CK(ctx, cudaMemsetAsync(ctx->d_tickets, 0, (size_t) local * sizeof(unsigned), ctx->stream));
+	}
+	p.acc = ctx->d_acc;
+	p.tickets = ctx->d_tickets;
+
+	p.ep.mode = mode;
+	p.ep.elem_size = elem_size;
+	p.ep.norm = norm;
+	p.ep.byteScale = byteScale;
+	p.ep.D = d_D;
+	p.ep.N = mode == 0 ? d_N : 0;
+	p.ep.rank = ctx->d_rank;
+	if(mode == 0) {
+		/* fsacmpthrd.c:292: minLength = minLength < minCov * len ? minCov * len : minLength */
+		if(minLength < minCov * ctx->len) minLength = (unsigned) (minCov * ctx->len);
+		p.ep.minLength = minLength;
+		p.ep.nFactor = 1.0;
+	} else {
+		/* fsacmpthrd.c:171-176 */
+		double nFactor = 1.0;
+		if(norm) { nFactor = norm; nFactor /= (int) ctx->global_inc; }
+		p.ep.nFactor = nFactor;
+	}
+
+	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	CK(ctx, ccg_launch_popc(ctx, p));
+	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	ctx->ev_valid = 1;
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_popc<%d> ksplit=%d", ctx->nplanes, p.ksplit);
+	return CCG_OK;
+}
+
+static int run_to_host(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
+                       double minCov, int elem_size, double byteScale, void *D, void *N, int *Dn_out) {
+	if(!ctx || !D) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	/* worst case Dn = n */
+	size_t max_cells = ctx->n > 1 ? (size_t) ctx->n * (ctx->n - 1) / 2 : 0;
+	size_t bytes = max_cells * 8;
+	if(ctx->out_bytes < bytes || !ctx->d_out_D) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_out_D); ctx->d_out_D = 0;
+		cudaFree(ctx->d_out_N); ctx->d_out_N = 0;
+		ctx->out_bytes = 0;
+		if(bytes) {
+			if(cudaMalloc(&ctx->d_out_D, bytes) != cudaSuccess || cudaMalloc(&ctx->d_out_N, bytes) != cudaSuccess) {
+				set_err(ctx, "cudaMalloc of 2 x %zu result bytes failed", bytes);
+				return CCG_ERR_NOMEM;
+			}
+		}
+		ctx->out_bytes = bytes;
+	}
+	int Dn = 0;
+	if(ctx->world > 1 && bytes) {
+		/* cells owned by other ranks read back as zero */
+		CK(ctx, cudaMemsetAsync(ctx->d_out_D, 0, bytes, ctx->stream));
+		CK(ctx, cudaMemsetAsync(ctx->d_out_N, 0, bytes, ctx->stream));
+	}
+	int rc = run_common(ctx, mode, include, norm, minLength, minCov, elem_size, byteScale, ctx->d_out_D,
+	                    N ? ctx->d_out_N : 0, &Dn);
+	if(rc) return rc;
+	if(Dn_out) *Dn_out = Dn;
+	if(Dn > 1) {
+		size_t cells = (size_t) Dn * (Dn - 1) / 2;
+		CK(ctx, cudaMemcpyAsync(D, ctx->d_out_D, cells * elem_size, cudaMemcpyDeviceToHost, ctx->stream));
+		if(N) CK(ctx, cudaMemcpyAsync(N, ctx->d_out_N, cells * elem_size, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return CCG_OK;
+}
+
+extern "C" int ccg_run_pair(ccg_ctx *ctx, const unsigned char *include, unsigned norm, unsigned minLength, double minCov,
+                            int elem_size, double byteScale, void *D, void *N, int *Dn) {
+	return run_to_host(ctx, 0, include, norm, minLength, minCov, elem_size, byteScale, D, N, Dn);
+}
+
+extern "C" int ccg_run_global(ccg_ctx *ctx, const unsigned char *include, unsigned norm, int elem_size, double byteScale,
+                              void *D, int *Dn, unsigned *global_inc) {
+	if(ctx && global_inc) *global_inc = ctx->global_inc;
+	return run_to_host(ctx, 1, include, norm, 0, 0.0, elem_size, byteScale, D, 0, Dn);
+}
+
+extern "C" int ccg_run_pair_dev(ccg_ctx *ctx, const unsigned char *include, unsigned norm, unsigned minLength,
+                                double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn) {
+	if(!d_D) return CCG_ERR_ARG;
+	return run_common(ctx, 0, include, norm, minLength, minCov, elem_size, byteScale, d_D, d_N, Dn);
+}
+
+extern "C" int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include, unsigned norm, int elem_size,
+                                  double byteScale, void *d_D, int *Dn, unsigned *global_inc) {
+	if(!d_D) return CCG_ERR_ARG;
+	if(ctx && global_inc) *global_inc = ctx->global_inc;
+	return run_common(ctx, 1, include, norm, 0, 0.0, elem_size, byteScale, d_D, 0, Dn);
+}
+
+extern "C" int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc) {
+	if(!ctx || !ctx->d_planes) return CCG_ERR_ARG;
+	int Dn = ctx->last_Dn;
+	if(Dn < 2) return CCG_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	size_t cells = (size_t) Dn * (Dn - 1) / 2;
+	uint32_t *d_m = 0, *d_n = 0;
+	CK(ctx, cudaMalloc(&d_m, cells * 4));
+	if(cudaMalloc(&d_n, cells * 4) != cudaSuccess) { cudaFree(d_m); return CCG_ERR_NOMEM; }
+	cudaMemsetAsync(d_m, 0, cells * 4, ctx->stream);
+	cudaMemsetAsync(d_n, 0, cells * 4, ctx->stream);
+	cudaError_t e = ccg_launch_gather_raw(ctx, Dn, d_m, d_n);
+	if(e == cudaSuccess && mism) e = cudaMemcpyAsync(mism, d_m, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
+	if(e == cudaSuccess && ninc) e = cudaMemcpyAsync(ninc, d_n, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
+	if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d_m);
+	cudaFree(d_n);
+	if(e != cudaSuccess) {
+		set_err(ctx, "raw count gather failed: %s", cudaGetErrorString(e));
+		return CCG_ERR_CUDA;
+	}
+	return CCG_OK;
+}
+
+extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, int elem_size, double byteScale, int n,
+                                      int len, const uint64_t *const *seqs, const unsigned char *include,
+                                      const uint32_t *const *includes, unsigned norm, unsigned minLength, double minCov,
+                                      unsigned proxi, int *Dn, unsigned *global_inc) {
+	if(proxi) {
+		set_err(ctx, "proximity masking (-P %u) is not implemented on the GPU path", proxi);
+		return CCG_ERR_UNSUPPORTED;
+	}
+	if(!seqs || !includes || n < 0) return CCG_ERR_ARG;
+	ccg_ctx *own = 0;
+	int rc;
+	if(!ctx) {
+		rc = ccg_init(&own, -1);
+		if(rc) return rc;
+		ctx = own;
+	}
+	rc = ccg_set_problem(ctx, n, len, pair);
+	if(!rc && !pair) rc = ccg_put_global_mask(ctx, includes[0]);
+	if(!rc) {
+		/* excluded samples are never uploaded: NULL row = empty slot */
+		const uint64_t **srow = (const uint64_t **) malloc((size_t) (n ? n : 1) * sizeof(*srow));
+		const uint32_t **mrow = (const uint32_t **) malloc((size_t) (n ? n : 1) * sizeof(*mrow));
+		if(!srow || !mrow) rc = CCG_ERR_NOMEM;
+		else {
+			for(int i = 0; i < n; ++i) {
+				int inc = !include || include[i];
+				srow[i] = inc ? seqs[i] : 0;
+				mrow[i] = inc ? (pair ? includes[i] : includes[0]) : 0;
+			}
+			rc = ccg_put_samples_packed(ctx, 0, n, srow, pair ? mrow : 0);
+		}
+		free(srow);
+		free(mrow);
+	}
+	if(!rc) {
+		if(pair) rc = ccg_run_pair(ctx, include, norm, minLength, minCov, elem_size, byteScale, D, N, Dn);
+		else rc = ccg_run_global(ctx, include, norm, elem_size, byteScale, D, Dn, global_inc);
+	}
+	if(own) {
+		if(rc) snprintf(g_init_err, sizeof(g_init_err), "%s", own->err);
+		ccg_destroy(own);
+	}
+	return rc;
+}
+
+extern "C" void *ccg_host_alloc(size_t bytes) {
+	void *p = 0;
+	if(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return 0;
+	return p;
+}
+
+extern "C" void ccg_host_free(void *p) {
+	if(p) cudaFreeHost(p);
+}
+
+extern "C" long long ccg_launch_count(const ccg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" const char *ccg_last_kernel(const ccg_ctx *ctx) { return ctx ? ctx->last_kernel : ""; }
+
+extern "C" float ccg_last_compare_ms(ccg_ctx *ctx) {
+	float ms = -1.0f;
+	if(!ctx || !ctx->ev_valid) return ms;
+	if(cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;
+	if(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0f;
+	return ms;
+}

@@ -1,0 +1,185 @@
+/*
+ * k_encode.cu -- K1: build the device-resident bit-plane sample store.
+ *
+ * Replaces, per sample, the reference's host-side preparation for the compare
+ * loop: qseq2nibble (qseqs.c:60-88), initIncPos (fsacmp.c:164-179),
+ * getIncPos(seq, seq, 0) (fsacmp.c:181-238) and getNpos (fsacmp.c:487-503).
+ *
+ * Roofline: HBM streaming.  Algorithmic bytes per 32-base word and sample:
+ * repack reads 8 B (u64 codes) + 4 B (u32 mask) and writes 12 B of planes;
+ * encode_codes reads 32 B of codes and writes 12 B.
+ */
+#include "ccg_internal.h"
+
+/* keep the even bits of x (bit 2k -> bit k) */
+__device__ __forceinline__ uint32_t compress_even(uint64_t x) {
+	x &= 0x5555555555555555ull;
+	x = (x | (x >> 1)) & 0x3333333333333333ull;
+	x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+	x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+	x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+	x = (x | (x >> 16));
+	return (uint32_t) x;
+}
+
+__device__ __forceinline__ void store_chunk(uint32_t *planes, int n_pad, int nplanes, long long chunk, int slot,
+                                            const uint32_t h[4], const uint32_t l[4], const uint32_t m[4]) {
+	uint4 *base = reinterpret_cast<uint4 *>(planes);
+	size_t row = (size_t) chunk * nplanes;
+	base[(row + 0) * n_pad + slot] = make_uint4(h[0], h[1], h[2], h[3]);
+	base[(row + 1) * n_pad + slot] = make_uint4(l[0], l[1], l[2], l[3]);
+	if(nplanes == 3) base[(row + 2) * n_pad + slot] = make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+/* Reference packed format -> planes.  One thread per (chunk, sample), sample
+ * fastest so the 16-byte plane stores of a warp are contiguous. */
+__global__ void __launch_bounds__(256)
+k_repack_packed(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks, int words, int first, int count,
+                const uint64_t *__restrict__ seqs, const uint32_t *__restrict__ masks,
+                const uint32_t *__restrict__ gmask, long wstride) {
+	long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	long long total = (long long) chunks * count;
+	if(gid >= total) return;
+	int s = (int) (gid % count);
+	long long c = gid / count;
+	uint32_t h[4], l[4], m[4];
+#pragma unroll
+	for(int q = 0; q < 4; ++q) {
+		long long w = c * 4 + q;
+		if(w < words) {
+			uint64_t x = seqs[(size_t) s * wstride + w];
+			uint32_t mk = masks ? masks[(size_t) s * wstride + w] : gmask[w];
+			m[q] = mk;
+			h[q] = compress_even(x >> 1) & mk;
+			l[q] = compress_even(x) & mk;
+		} else {
+			h[q] = l[q] = m[q] = 0;
+		}
+	}
+	store_chunk(planes, n_pad, nplanes, c, first + s, h, l, m);
+}
+
+/* getNpos of each uploaded mask row (fsacmp.c:487): one block per sample. */
+__global__ void __launch_bounds__(256)
+k_mask_count(const uint32_t *__restrict__ masks, long wstride, int words, int first, unsigned *__restrict__ inc) {
+	__shared__ unsigned warp_sums[8];
+	const uint32_t *row = masks + (size_t) blockIdx.x * wstride;
+	unsigned acc = 0;
+	for(int w = threadIdx.x; w < words; w += blockDim.x) acc += __popc(row[w]);
+#pragma unroll
+	for(int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		unsigned t = 0;
+		for(int i = 0; i < (int) (blockDim.x >> 5); ++i) t += warp_sums[i];
+		inc[first + blockIdx.x] = t;
+	}
+}
+
+/* Translated codes (0..3 base, anything else unknown) -> planes + inc count.
+ * One thread per (chunk, sample): 128 codes in, three 16-byte plane words out. */
+__global__ void __launch_bounds__(256)
+k_encode_codes(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks, int len, int first, int count,
+               const unsigned char *__restrict__ codes, long stride, unsigned *__restrict__ inc) {
+	long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	long long total = (long long) chunks * count;
+	if(gid >= total) return;
+	int s = (int) (gid % count);
+	long long c = gid / count;
+	const unsigned char *row = codes + (size_t) s * stride;
+	uint32_t h[4], l[4], m[4];
+	unsigned known = 0;
+#pragma unroll
+	for(int q = 0; q < 4; ++q) {
+		long long p0 = c * CCG_CHUNK_BASES + q * 32;
+		uint32_t hh = 0, ll = 0, mm = 0;
+		if(p0 + 32 <= len) {
+			/* stride and row base are 16-byte aligned by the staging allocator */
+			const uint4 *v = reinterpret_cast<const uint4 *>(row + p0);
+			uint4 a = v[0], b = v[1];
+			uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+			for(int k = 0; k < 32; ++k) {
+				uint32_t code = (wv[k >> 2] >> (8 * (k & 3))) & 0xFF;
+				uint32_t kn = code < 4 ? 1u : 0u;
+				mm |= kn << (31 - k);
+				hh |= (kn & (code >> 1)) << (31 - k);
+				ll |= (kn & code) << (31 - k);
+			}
+		} else {
+			for(int k = 0; k < 32; ++k) {
+				long long p = p0 + k;
+				uint32_t code = p < len ? row[p] : 4;
+				uint32_t kn = code < 4 ? 1u : 0u;
+				mm |= kn << (31 - k);
+				hh |= (kn & (code >> 1)) << (31 - k);
+				ll |= (kn & code) << (31 - k);
+			}
+		}
+		h[q] = hh; l[q] = ll; m[q] = mm;
+		known += __popc(mm);
+	}
+	store_chunk(planes, n_pad, nplanes, c, first + s, h, l, m);
+	if(known) atomicAdd(inc + first + s, known);
+}
+
+/* tile-major raw counts -> packed lower triangle over included samples */
+__global__ void __launch_bounds__(256)
+k_gather_raw(const uint32_t *__restrict__ acc, int ntiles_local, int rank_id, int world, const int *__restrict__ rank,
+             uint32_t *__restrict__ mism, uint32_t *__restrict__ ninc) {
+	int lt = blockIdx.x;
+	if(lt >= ntiles_local) return;
+	long long t = (long long) lt * world + rank_id;
+	int ti = (int) ((sqrt(8.0 * (double) t + 1.0) - 1.0) * 0.5);
+	while((long long) (ti + 1) * (ti + 2) / 2 <= t) ++ti;
+	while((long long) ti * (ti + 1) / 2 > t) --ti;
+	int tj = (int) (t - (long long) ti * (ti + 1) / 2);
+	const uint32_t *a = acc + (size_t) lt * 2 * CCG_TILE * CCG_TILE;
+	for(int e = threadIdx.x; e < CCG_TILE * CCG_TILE; e += blockDim.x) {
+		int i = ti * CCG_TILE + e / CCG_TILE;
+		int j = tj * CCG_TILE + e % CCG_TILE;
+		if(i <= j) continue;
+		int r = rank[i], c = rank[j];
+		if(r < 0 || c < 0) continue;
+		long long cell = (long long) r * (r - 1) / 2 + c;
+		if(mism) mism[cell] = a[e];
+		if(ninc) ninc[cell] = a[CCG_TILE * CCG_TILE + e];
+	}
+}
+
+cudaError_t ccg_launch_repack(ccg_ctx *ctx, int first, int count, const uint64_t *d_seqs, const uint32_t *d_masks,
+                              long wstride) {
+	long long total = (long long) ctx->chunks * count;
+	if(total == 0) return cudaSuccess;
+	unsigned blocks = (unsigned) ((total + 255) / 256);
+	k_repack_packed<<<blocks, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks, ctx->words,
+	                                                  first, count, d_seqs, d_masks, ctx->d_gmask, wstride);
+	ctx->launches++;
+	if(d_masks) {
+		k_mask_count<<<count, 256, 0, ctx->stream>>>(d_masks, wstride, ctx->words, first, ctx->d_inc);
+		ctx->launches++;
+	}
+	return cudaGetLastError();
+}
+
+cudaError_t ccg_launch_encode_codes(ccg_ctx *ctx, int first, int count, const unsigned char *d_codes, long stride) {
+	long long total = (long long) ctx->chunks * count;
+	if(total == 0) return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(ctx->d_inc + first, 0, (size_t) count * sizeof(unsigned), ctx->stream);
+	if(e != cudaSuccess) return e;
+	unsigned blocks = (unsigned) ((total + 255) / 256);
+	k_encode_codes<<<blocks, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks, ctx->len,
+	                                                 first, count, d_codes, stride, ctx->d_inc);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t ccg_launch_gather_raw(ccg_ctx *ctx, int Dn, uint32_t *d_mism, uint32_t *d_ninc) {
+	(void) Dn;
+	if(ctx->last_ntiles_local <= 0) return cudaSuccess;
+	k_gather_raw<<<ctx->last_ntiles_local, 256, 0, ctx->stream>>>(ctx->d_acc, ctx->last_ntiles_local, ctx->rank,
+	                                                              ctx->world, ctx->d_rank, d_mism, d_ninc);
+	ctx->launches++;
+	return cudaGetLastError();
+}

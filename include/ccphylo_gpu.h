@@ -1,0 +1,183 @@
+/*
+ * ccphylo_gpu.h -- C-ABI of the B200 (sm_100a) implementation of ccphylo's
+ * `dist` hot path: the all-vs-all pairwise nucleotide distance matrix D and
+ * the inclusion-count matrix N over KMA consensus alignments.
+ *
+ * This is the drop-in boundary.  The reference has no FFI; its seam is the
+ * fan-out call
+ *
+ *     fsaCmpThreadOut(tnum, &cmpairFsaThrd | &cmpFsaThrd, D, N, n, len, seqs,
+ *                     include, includes, norm, minLength, minCov, ...)
+ *                                  reference fsacmpthrd.h:49, fsacmpthrd.c:76
+ *
+ * called at cdist.c:181,184 (multi-file) and cdist.c:351,354 (MSA).  Every
+ * entry point below cites the reference interface it replaces (paths relative
+ * to the reference tree).  Plain C types only; all buffers are caller-owned.
+ * There is no CPU fallback: when no sm_100 device is usable every call
+ * returns an error and the caller must stop.
+ *
+ * Data formats at the boundary (exactly the reference's in-memory formats):
+ *   seqs[i]      ceil(len/32) x u64, 32 bases per word, base p in bits
+ *                63-2(p%32)..62-2(p%32), unknown packed as 00, tail
+ *                left-aligned                      (qseqs.c:60 qseq2nibble)
+ *   includes[i]  ceil(len/32) x u32, base p <-> bit 31-(p%32); bits >= len
+ *                clear                    (fsacmp.c:164 initIncPos, :181 getIncPos)
+ *   include[i]   0 = sample excluded (compacted out of D and N)
+ *   D, N         packed strict lower triangle over the INCLUDED samples in
+ *                input order, row-major, row r at r(r-1)/2, cells of
+ *                elem_size bytes: 8 double | 4 float | 2 u16 | 1 u8
+ *                                                (matrix.c:32 ltdMatrixInit)
+ */
+#ifndef CCPHYLO_GPU_H
+#define CCPHYLO_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ccg_ctx ccg_ctx;
+
+enum {
+	CCG_OK = 0,
+	CCG_ERR_NO_DEVICE = 1,   /* no CUDA device / not sm_100: there is no CPU fallback */
+	CCG_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed: see ccg_last_error */
+	CCG_ERR_ARG = 3,         /* invalid argument or call order */
+	CCG_ERR_NOMEM = 4,       /* host or device allocation failed */
+	CCG_ERR_UNSUPPORTED = 5  /* e.g. proxi > 0 (-P), handled on the host in the reference */
+};
+
+/* kernel selection for ccg_set_kernel */
+enum {
+	CCG_KERNEL_AUTO = 0,
+	CCG_KERNEL_POPC = 1,     /* bit-sliced LOP3+POPC path on the INT pipe */
+	CCG_KERNEL_UMMA = 2      /* int8 contraction on tcgen05 tensor cores */
+};
+
+const char *ccg_strerror(int code);
+/* last detailed message of this context (or of the failed ccg_init when ctx is NULL) */
+const char *ccg_last_error(const ccg_ctx *ctx);
+
+/* Create a context on CUDA device `device` (-1 = the current device).  Replaces
+ * the thread fan-out set-up of fsaCmpThreadOut (fsacmpthrd.c:76-96). */
+int ccg_init(ccg_ctx **ctx, int device);
+void ccg_destroy(ccg_ctx *ctx);
+
+/* Launch everything on the caller's cudaStream_t (NULL = the context's own
+ * stream).  Lets a host that already owns a stream order and time the work. */
+int ccg_set_stream(ccg_ctx *ctx, void *cuda_stream);
+int ccg_set_kernel(ccg_ctx *ctx, int kernel);
+/* Block until all work queued by this context has finished. */
+int ccg_sync(ccg_ctx *ctx);
+
+/* This context computes only the lower-triangular tile blocks dealt to `rank`
+ * of `world` (one process per GPU, no data-path collective).  Cells of other
+ * ranks are left untouched in D / N.  Default rank 0 of 1. */
+int ccg_set_partition(ccg_ctx *ctx, int rank, int world);
+/* Pure host helpers (no device needed) describing that deal: the lower
+ * triangle is cut into 64x64 sample tiles, tile (ti, tj<=ti) has index
+ * t = ti(ti+1)/2 + tj and belongs to rank t % world.
+ * ccg_partition_cells: number of (r,c) cells of an n-sample matrix owned by
+ * `rank`.  ccg_partition_tiles: writes up to `cap` owned tiles to ti[] / tj[]
+ * and returns how many the rank owns. */
+int ccg_tile_edge(void);
+long long ccg_partition_cells(int n, int rank, int world);
+long long ccg_partition_tiles(int n, int rank, int world, int *ti, int *tj, long long cap);
+
+/* Declare the sample set: n sample slots of len bases.  pair_mode != 0 is
+ * `-f` bit 2 (per-pair inclusion, cmpairFsaThrd); 0 is the shared-mask mode
+ * (cmpFsaThrd).  Allocates the device-resident sample store. */
+int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode);
+
+/* Shared-mask mode only: the global mask includes[0] (cdist.c:101-112), must
+ * be set before the samples are put.  Host pointer. */
+int ccg_put_global_mask(ccg_ctx *ctx, const uint32_t *mask);
+
+/* Upload samples [first, first+count) in the reference's packed format from
+ * HOST memory; seqs[k] / includes[k] are row pointers exactly as the
+ * reference holds them (dist.c:143-154).  includes may be NULL in
+ * shared-mask mode.  A NULL row pointer leaves that slot empty (excluded). */
+int ccg_put_samples_packed(ccg_ctx *ctx, int first, int count,
+                           const uint64_t *const *seqs,
+                           const uint32_t *const *includes);
+
+/* Same, from DEVICE memory already holding count x wstride words
+ * (row-major).  d_masks may be NULL in shared-mask mode. */
+int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count,
+                               const uint64_t *d_seqs, const uint32_t *d_masks,
+                               long wstride);
+
+/* Upload one sample as translated codes 0..4 (len bytes, host); the device
+ * performs qseq2nibble (qseqs.c:60), initIncPos + getIncPos(seq, seq, 0)
+ * (fsacmp.c:164,181) and getNpos (:487).  Pair mode only. */
+int ccg_put_sample_codes(ccg_ctx *ctx, int idx, const unsigned char *codes);
+
+/* Per-slot included-position counts (getNpos of each sample's own mask,
+ * fsacmp.c:487; cdist.c:91).  out has n entries. */
+int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out);
+
+/* Pair mode: replaces fsaCmpThreadOut(tnum, &cmpairFsaThrd, ...)
+ * (cdist.c:181, fsacmpthrd.c:261-480).  include has n flags (NULL = all
+ * uploaded slots).  minLength is re-maxed with minCov*len as fsacmpthrd.c:292
+ * does.  D and N (N may be NULL) are HOST buffers of Dn(Dn-1)/2 cells of
+ * elem_size bytes; byteScale is the reference's global ByteScale
+ * (bytescale.c:22) used for elem_size 2 and 1.  *Dn receives the number of
+ * included samples (D->n). */
+int ccg_run_pair(ccg_ctx *ctx, const unsigned char *include, unsigned norm,
+                 unsigned minLength, double minCov, int elem_size,
+                 double byteScale, void *D, void *N, int *Dn);
+
+/* Shared-mask mode: replaces fsaCmpThreadOut(tnum, &cmpFsaThrd, ...)
+ * (cdist.c:184, fsacmpthrd.c:108-259).  *global_inc receives getNpos of the
+ * global mask (the caller prints the "# inc / len bases included" line,
+ * fsacmpthrd.c:165).  Only included samples are compared (the reference's
+ * own pair selection is wrong when a sample is excluded, fsacmpthrd.c:194). */
+int ccg_run_global(ccg_ctx *ctx, const unsigned char *include, unsigned norm,
+                   int elem_size, double byteScale, void *D, int *Dn,
+                   unsigned *global_inc);
+
+/* Device-resident variants: D / N are DEVICE buffers, nothing is copied to
+ * the host and the call only enqueues work on the context's stream. */
+int ccg_run_pair_dev(ccg_ctx *ctx, const unsigned char *include, unsigned norm,
+                     unsigned minLength, double minCov, int elem_size,
+                     double byteScale, void *d_D, void *d_N, int *Dn);
+int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include,
+                       unsigned norm, int elem_size, double byteScale,
+                       void *d_D, int *Dn, unsigned *global_inc);
+
+/* Raw integer results of the last pair-mode run for included samples:
+ * mismatch counts and inclusion counts as u32, same packed layout.  HOST
+ * buffers; either may be NULL. */
+int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc);
+
+/* One-call drop-in with the argument list of fsaCmpThreadOut
+ * (fsacmpthrd.h:49): pair != 0 selects cmpairFsaThrd, else cmpFsaThrd.
+ * Host row pointers in, host matrices out.  proxi must be 0
+ * (CCG_ERR_UNSUPPORTED otherwise).  ctx may be NULL (a temporary context on
+ * the current device is used). */
+int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N,
+                           int elem_size, double byteScale, int n, int len,
+                           const uint64_t *const *seqs,
+                           const unsigned char *include,
+                           const uint32_t *const *includes, unsigned norm,
+                           unsigned minLength, double minCov, unsigned proxi,
+                           int *Dn, unsigned *global_inc);
+
+/* Pinned host memory for sample rows / result matrices (faster H2D / D2H). */
+void *ccg_host_alloc(size_t bytes);
+void ccg_host_free(void *p);
+
+/* Introspection for tests and the bench: kernel launches issued by this
+ * context so far, and the name of the compare kernel used by the last run. */
+long long ccg_launch_count(const ccg_ctx *ctx);
+const char *ccg_last_kernel(const ccg_ctx *ctx);
+/* device time (ms, CUDA events on the context's stream) of the compare kernel
+ * of the last run; < 0 if unavailable */
+float ccg_last_compare_ms(ccg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

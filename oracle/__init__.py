@@ -1,0 +1,215 @@
+"""ctypes bindings for the CPU oracle (liboracle.so) and, when built, the
+unmodified reference (oracle/_ref/libccphylo_ref.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py -- never by ccphylo_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "liboracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libccphylo_ref.so")
+REF_BIN = os.path.join(_HERE, "_ref", "ccphylo")
+
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+
+ELEM_DTYPE = {8: np.float64, 4: np.float32, 2: np.uint16, 1: np.uint8}
+
+
+def build(ref=True):
+    """Compile the checker (and the reference when /root/reference exists)."""
+    subprocess.run(["make", "-s", "-C", _HERE] + ([] if ref else ["liboracle.so"]), check=True)
+
+
+def words(length):
+    return (length >> 5) + (1 if length & 31 else 0)
+
+
+def cells(dn):
+    return dn * (dn - 1) // 2 if dn > 1 else 0
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        L = C.CDLL(ORACLE_SO)
+        L.orc_translate.restype = C.c_long
+        L.orc_translate.argtypes = [_u8p, C.c_long, C.c_uint, _u8p]
+        L.orc_pack.restype = C.c_int
+        L.orc_pack.argtypes = [_u8p, C.c_int, _u64p]
+        L.orc_known_mask.restype = C.c_int
+        L.orc_known_mask.argtypes = [_u8p, C.c_int, _u32p]
+        L.orc_and_known.restype = None
+        L.orc_and_known.argtypes = [_u32p, _u8p, _u8p, C.c_int]
+        L.orc_mask_count.restype = C.c_int
+        L.orc_mask_count.argtypes = [_u32p, C.c_int]
+        L.orc_raw_pair_matrix.restype = None
+        L.orc_raw_pair_matrix.argtypes = [C.c_int, C.c_int, _u64p, _u32p, C.c_long, _u32p, _u32p, C.c_int]
+        L.orc_fsa_cmp_pair.restype = C.c_int
+        L.orc_fsa_cmp_pair.argtypes = [C.c_int, C.c_int, _u64p, C.c_long, _u8p, _u32p, C.c_uint, C.c_uint,
+                                       C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_fsa_cmp_global.restype = C.c_int
+        L.orc_fsa_cmp_global.argtypes = [C.c_int, C.c_int, _u64p, C.c_long, _u8p, _u32p, C.c_uint, C.c_int,
+                                         C.c_double, C.c_void_p, C.POINTER(C.c_uint)]
+        _lib = L
+    return _lib
+
+
+# ----------------------------------------------------------------------------
+# oracle (our restatement)
+# ----------------------------------------------------------------------------
+def translate(data: bytes, flag=1):
+    buf = np.frombuffer(data, dtype=np.uint8)
+    buf = np.ascontiguousarray(buf)
+    codes = np.empty(max(len(buf), 1), dtype=np.uint8)
+    n = lib().orc_translate(buf if len(buf) else np.zeros(1, np.uint8), len(buf), flag, codes)
+    return codes[:n].copy()
+
+
+def pack(codes):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    W = words(len(codes))
+    seq = np.zeros(max(W, 1), dtype=np.uint64)
+    unknown = lib().orc_pack(codes if len(codes) else np.zeros(1, np.uint8), len(codes), seq)
+    return seq[:W], unknown
+
+
+def known_mask(codes):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    W = words(len(codes))
+    mask = np.zeros(max(W, 1), dtype=np.uint32)
+    inc = lib().orc_known_mask(codes if len(codes) else np.zeros(1, np.uint8), len(codes), mask)
+    return mask[:W], inc
+
+
+def encode_samples(codes2d):
+    """codes2d: (n, L) u8 codes -> (seqs (n,W) u64, masks (n,W) u32, inc (n,) i32)."""
+    n, L = codes2d.shape
+    W = words(L)
+    seqs = np.zeros((n, W), dtype=np.uint64)
+    masks = np.zeros((n, W), dtype=np.uint32)
+    inc = np.zeros(n, dtype=np.int32)
+    for i in range(n):
+        seqs[i], _ = pack(codes2d[i])
+        masks[i], inc[i] = known_mask(codes2d[i])
+    return seqs, masks, inc
+
+
+def global_mask(codes2d, include):
+    """cdist.c:86-112 accumulation: first included sample is `ref`."""
+    n, L = codes2d.shape
+    inc_idx = [i for i in range(n) if include[i]]
+    ref = np.ascontiguousarray(codes2d[inc_idx[0]])
+    mask, _ = known_mask(ref)
+    mask = mask.copy()
+    for i in inc_idx[1:]:
+        lib().orc_and_known(mask, np.ascontiguousarray(codes2d[i]), ref, L)
+    return mask
+
+
+def raw_pair_matrix(seqs, masks, length, nthreads=8):
+    n, W = seqs.shape
+    mism = np.zeros(max(cells(n), 1), dtype=np.uint32)
+    ninc = np.zeros(max(cells(n), 1), dtype=np.uint32)
+    lib().orc_raw_pair_matrix(n, length, seqs, masks, W, mism, ninc, nthreads)
+    return mism[:cells(n)], ninc[:cells(n)]
+
+
+def fsa_cmp_pair(seqs, masks, include, length, norm=0, min_length=1, min_cov=0.5, elem_size=8, byte_scale=1.0,
+                 want_n=True):
+    n, W = seqs.shape
+    include = np.ascontiguousarray(include, dtype=np.uint8)
+    dt = ELEM_DTYPE[elem_size]
+    D = np.zeros(max(cells(n), 1), dtype=dt)
+    N = np.zeros(max(cells(n), 1), dtype=dt)
+    dn = lib().orc_fsa_cmp_pair(n, length, np.ascontiguousarray(seqs), W, include, np.ascontiguousarray(masks),
+                                norm, min_length, min_cov, elem_size, byte_scale, D.ctypes.data,
+                                N.ctypes.data if want_n else None)
+    return D[:cells(dn)], (N[:cells(dn)] if want_n else None), dn
+
+
+def fsa_cmp_global(seqs, mask, include, length, norm=0, elem_size=8, byte_scale=1.0):
+    n, W = seqs.shape
+    include = np.ascontiguousarray(include, dtype=np.uint8)
+    D = np.zeros(max(cells(n), 1), dtype=ELEM_DTYPE[elem_size])
+    ginc = C.c_uint(0)
+    dn = lib().orc_fsa_cmp_global(n, length, np.ascontiguousarray(seqs), W, include,
+                                  np.ascontiguousarray(mask), norm, elem_size, byte_scale, D.ctypes.data,
+                                  C.byref(ginc))
+    return D[:cells(dn)], dn, ginc.value
+
+
+# ----------------------------------------------------------------------------
+# the unmodified reference (oracle/_ref), when present
+# ----------------------------------------------------------------------------
+_ref = None
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        R = C.CDLL(REF_SO)
+        R.refshim_encode.restype = C.c_long
+        R.refshim_encode.argtypes = [_u8p, C.c_long, C.c_uint, C.c_uint, _u8p, _u64p, _u32p,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        R.refshim_and_known.restype = None
+        R.refshim_and_known.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint]
+        R.refshim_pair.restype = C.c_uint64
+        R.refshim_pair.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint]
+        R.refshim_fsa_cmp.restype = C.c_int
+        R.refshim_fsa_cmp.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _u64p, C.c_long, _u8p, _u32p,
+                                      C.c_uint, C.c_uint, C.c_double, C.c_uint, C.c_int, C.c_double,
+                                      C.c_void_p, C.c_void_p]
+        _ref = R
+    return _ref
+
+
+def ref_encode(data: bytes, flag=1, proxi=0):
+    buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8))
+    nb = len(buf)
+    codes = np.zeros(nb + 1, dtype=np.uint8)
+    W = nb // 32 + 2
+    seq = np.zeros(W, dtype=np.uint64)
+    mask = np.zeros(W, dtype=np.uint32)
+    unk, inc = C.c_int(0), C.c_int(0)
+    L = ref().refshim_encode(buf if nb else np.zeros(1, np.uint8), nb, flag, proxi, codes, seq, mask,
+                             C.byref(unk), C.byref(inc))
+    return codes[:L].copy(), seq[:words(L)].copy(), mask[:words(L)].copy(), unk.value, inc.value
+
+
+def ref_fsa_cmp(seqs, masks, include, length, pair=True, tnum=1, norm=0, min_length=1, min_cov=0.5, proxi=0,
+                elem_size=8, byte_scale=1.0, want_n=True):
+    n, W = seqs.shape
+    include = np.ascontiguousarray(include, dtype=np.uint8).copy()
+    dt = ELEM_DTYPE[elem_size]
+    D = np.zeros(max(cells(n), 1), dtype=dt)
+    N = np.zeros(max(cells(n), 1), dtype=dt)
+    masks = np.ascontiguousarray(masks)
+    # the reference scratch-reads one word past ceil(len/32) when len%32==0 (fsacmpthrd.c:336 sizes len/32+1)
+    seqs_p = np.zeros((n, W + 1), dtype=np.uint64)
+    seqs_p[:, :W] = seqs
+    if pair:
+        masks_p = np.zeros((n, W + 1), dtype=np.uint32)
+        masks_p[:, :W] = masks
+    else:
+        masks_p = np.zeros((1, W + 1), dtype=np.uint32)
+        masks_p[0, :W] = masks.reshape(-1)[:W]
+    dn = ref().refshim_fsa_cmp(tnum, 1 if pair else 0, n, length, seqs_p, W + 1, include, masks_p, norm,
+                               min_length, min_cov, proxi, elem_size, byte_scale, D.ctypes.data,
+                               N.ctypes.data if (want_n and pair) else None)
+    return D[:cells(dn)], (N[:cells(dn)] if (want_n and pair) else None), dn

@@ -1,0 +1,309 @@
+/*
+ * fsa_oracle.c -- CPU restatement of ccphylo's `dist` FASTA hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see fsa_oracle.h).  Parity pinned by execution
+ * against the unmodified reference built into oracle/_ref/.
+ *
+ * Written from the behavioural description of the reference (SURVEY.md
+ * App. A), popcount based, with none of the reference's bit-serial loops.
+ */
+#include "fsa_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ */
+/* byte -> code table                      (reference fsacmp.c:32-91)  */
+/* ------------------------------------------------------------------ */
+void orc_code_table(unsigned flag, unsigned char table[256]) {
+	static const char unknown_upper[] = "N-RYSWKMBDHVX";
+	static const char unknown_lower[] = "ryswkmbdhvx";
+	const char *p;
+	int low = (flag & 8) ? 1 : 0;
+
+	memset(table, 32, 256);
+	table['A'] = 0; table['C'] = 1; table['G'] = 2; table['T'] = 3; table['U'] = 3;
+	for(p = unknown_upper; *p; ++p) table[(unsigned char) *p] = 4;
+	for(p = unknown_lower; *p; ++p) table[(unsigned char) *p] = 4;
+	/* lower case = "insignificant" calls: unknown unless flag bit 8 */
+	table['a'] = low ? 0 : 4;
+	table['c'] = low ? 1 : 4;
+	table['g'] = low ? 2 : 4;
+	table['t'] = low ? 3 : 4;
+	table['u'] = low ? 3 : 4;
+	table['n'] = 4;
+}
+
+/* (reference seqparse.c:195-248) */
+long orc_translate(const unsigned char *bytes, long nbytes, unsigned flag,
+                   unsigned char *codes) {
+	unsigned char table[256];
+	long i, len = 0;
+
+	orc_code_table(flag, table);
+	for(i = 0; i < nbytes; ++i) {
+		unsigned char c = table[bytes[i]];
+		if(c < 32) codes[len++] = c;
+	}
+	return len;
+}
+
+/* (reference qseqs.c:60-88) */
+int orc_pack(const unsigned char *codes, int len, uint64_t *words) {
+	int p, unknown = 0, W = orc_words(len);
+
+	memset(words, 0, (size_t) W * sizeof(uint64_t));
+	for(p = 0; p < len; ++p) {
+		unsigned c = codes[p];
+		if(c == 4) {
+			++unknown;
+		} else {
+			words[p >> 5] |= (uint64_t) (c & 3) << (62 - 2 * (p & 31));
+		}
+	}
+	return unknown;
+}
+
+/* (reference fsacmp.c:164-179, :181-238 with proxi == 0, :487-503) */
+int orc_known_mask(const unsigned char *codes, int len, uint32_t *mask) {
+	int p, inc = 0, W = orc_words(len);
+
+	memset(mask, 0, (size_t) W * sizeof(uint32_t));
+	for(p = 0; p < len; ++p) {
+		if(codes[p] != 4) {
+			mask[p >> 5] |= 1u << (31 - (p & 31));
+			++inc;
+		}
+	}
+	return inc;
+}
+
+/* (reference fsacmp.c:181-238 with proxi == 0, seq != ref) */
+void orc_and_known(uint32_t *mask, const unsigned char *seq_codes,
+                   const unsigned char *ref_codes, int len) {
+	int p;
+
+	for(p = 0; p < len; ++p) {
+		if(seq_codes[p] == 4 || ref_codes[p] == 4) {
+			mask[p >> 5] &= ~(1u << (31 - (p & 31)));
+		}
+	}
+}
+
+/* (reference fsacmp.c:487-503) */
+int orc_mask_count(const uint32_t *mask, int len) {
+	int w, inc = 0, W = orc_words(len);
+
+	for(w = 0; w < W; ++w) inc += __builtin_popcount(mask[w]);
+	return inc;
+}
+
+/* Spread the 32 mask bits to the even bit of each 2-bit lane. */
+static inline uint64_t spread32(uint32_t m) {
+	uint64_t x = m;
+	x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+	x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+	x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+	x = (x | (x << 2)) & 0x3333333333333333ull;
+	x = (x | (x << 1)) & 0x5555555555555555ull;
+	return x;
+}
+
+/* number of 2-bit lanes that differ between a and b, restricted to the lanes
+ * whose mask bit is set (mask bit k <-> lane bits 2k+1:2k). */
+static inline uint32_t lane_mism(uint64_t a, uint64_t b, uint32_t m) {
+	uint64_t x = a ^ b;
+	uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;
+	return (uint32_t) __builtin_popcountll(d & spread32(m));
+}
+
+/* (reference fsacmp.c:355-389 maskProxi with proxi == 0, :587-633 fsacmpair) */
+void orc_pair_counts(const uint64_t *seq_i, const uint64_t *seq_j,
+                     const uint32_t *inc_i, const uint32_t *inc_j, int len,
+                     uint32_t *mism, uint32_t *ninc) {
+	int w, W = orc_words(len);
+	uint32_t d = 0, n = 0;
+
+	for(w = 0; w < W; ++w) {
+		uint32_t m = inc_i[w] & inc_j[w];
+		n += (uint32_t) __builtin_popcount(m);
+		d += lane_mism(seq_i[w], seq_j[w], m);
+	}
+	*mism = d;
+	*ninc = n;
+}
+
+/* (reference fsacmp.c:552-585) */
+uint32_t orc_masked_mism(const uint64_t *seq_i, const uint64_t *seq_j,
+                         const uint32_t *mask, int len) {
+	int w, W = orc_words(len);
+	uint32_t d = 0;
+
+	for(w = 0; w < W; ++w) d += lane_mism(seq_i[w], seq_j[w], mask[w]);
+	return d;
+}
+
+/* ------------------------------------------------------------------ */
+/* raw all-vs-all integer matrices (test helper, threaded over rows)   */
+/* ------------------------------------------------------------------ */
+typedef struct {
+	int n, len, tid, nthreads;
+	long wstride;
+	const uint64_t *seqs;
+	const uint32_t *masks;
+	uint32_t *mism, *ninc;
+} RawJob;
+
+static void *raw_worker(void *arg) {
+	RawJob *job = arg;
+	int i, j;
+
+	/* interleave rows so each thread gets a similar number of cells */
+	for(i = 1 + job->tid; i < job->n; i += job->nthreads) {
+		size_t row = (size_t) i * (i - 1) / 2;
+		for(j = 0; j < i; ++j) {
+			orc_pair_counts(job->seqs + i * job->wstride, job->seqs + j * job->wstride,
+			                job->masks + i * job->wstride, job->masks + j * job->wstride,
+			                job->len, job->mism + row + j, job->ninc + row + j);
+		}
+	}
+	return 0;
+}
+
+void orc_raw_pair_matrix(int n, int len, const uint64_t *seqs,
+                         const uint32_t *masks, long wstride,
+                         uint32_t *mism, uint32_t *ninc, int nthreads) {
+	pthread_t ids[256];
+	RawJob jobs[256];
+	int t;
+
+	if(nthreads < 1) nthreads = 1;
+	if(nthreads > 256) nthreads = 256;
+	for(t = 0; t < nthreads; ++t) {
+		jobs[t] = (RawJob){n, len, t, nthreads, wstride, seqs, masks, mism, ninc};
+		if(t && pthread_create(ids + t, 0, raw_worker, jobs + t)) {
+			raw_worker(jobs + t);
+			ids[t] = 0;
+		}
+	}
+	raw_worker(jobs);
+	for(t = 1; t < nthreads; ++t) {
+		if(ids[t]) pthread_join(ids[t], 0);
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* epilogues                                                           */
+/* ------------------------------------------------------------------ */
+
+/* double -> integer cell as gcc/x86-64 does it for the reference's
+ * `unsigned short = double` / `unsigned char = double` stores: a truncating
+ * 32-bit cvttsd2si whose low bits are kept. */
+static inline int32_t trunc_i32(double x) {
+	if(!(x > -2147483649.0 && x < 2147483648.0)) return INT32_MIN;
+	return (int32_t) x;
+}
+
+/* (reference fsacmpthrd.c:419-475; bytescale.h:22 dtouc) */
+void orc_pair_cell(uint32_t mism, uint32_t inc, unsigned norm,
+                   unsigned minLength, int elem_size, double byteScale,
+                   void *Dcell, void *Ncell) {
+	uint64_t scaled = (uint64_t) mism * norm;
+	int ok = minLength <= inc;
+
+	if(elem_size == 8) {
+		double d;
+		if(!ok) d = -1.0;
+		else if(norm) { d = (double) scaled; d /= inc; }
+		else d = (double) mism;
+		*(double *) Dcell = d;
+		if(Ncell) *(double *) Ncell = (double) inc;
+	} else if(elem_size == 4) {
+		float f;
+		if(!ok) f = -1.0f;
+		else if(norm) { f = (float) scaled; f /= inc; }
+		else f = (float) mism;
+		*(float *) Dcell = f;
+		if(Ncell) *(float *) Ncell = (float) inc;
+	} else {
+		double d, nn;
+		if(!ok) d = -1.0 * byteScale + 0;
+		else if(norm) d = ((double) scaled * byteScale + 0.5) / inc;
+		else d = (double) (uint64_t) mism * byteScale + 0.5;
+		nn = inc * byteScale + 0.5;
+		if(elem_size == 2) {
+			*(uint16_t *) Dcell = (uint16_t) trunc_i32(d);
+			if(Ncell) *(uint16_t *) Ncell = (uint16_t) trunc_i32(nn);
+		} else {
+			*(uint8_t *) Dcell = (uint8_t) trunc_i32(d);
+			if(Ncell) *(uint8_t *) Ncell = (uint8_t) trunc_i32(nn);
+		}
+	}
+}
+
+static int compact_included(int n, const unsigned char *include, int *idx) {
+	int i, Dn = 0;
+	for(i = 0; i < n; ++i) {
+		if(include[i]) idx[Dn++] = i;
+	}
+	return Dn;
+}
+
+/* (reference fsacmpthrd.c:261-480) */
+int orc_fsa_cmp_pair(int n, int len, const uint64_t *seqs, long wstride,
+                     const unsigned char *include, const uint32_t *masks,
+                     unsigned norm, unsigned minLength, double minCov,
+                     int elem_size, double byteScale, void *D, void *N) {
+	int *idx = malloc((size_t) (n > 0 ? n : 1) * sizeof(int));
+	int Dn = compact_included(n, include, idx), r, c;
+	size_t cell = 0;
+
+	/* fsacmpthrd.c:292: threshold re-derived from minCov, truncating */
+	if(minLength < minCov * len) minLength = (unsigned) (minCov * len);
+
+	for(r = 1; r < Dn; ++r) {
+		for(c = 0; c < r; ++c, ++cell) {
+			uint32_t mism, inc;
+			int i = idx[r], j = idx[c];
+			orc_pair_counts(seqs + i * wstride, seqs + j * wstride,
+			                masks + i * wstride, masks + j * wstride, len, &mism, &inc);
+			orc_pair_cell(mism, inc, norm, minLength, elem_size, byteScale,
+			              (char *) D + cell * elem_size,
+			              N ? (char *) N + cell * elem_size : 0);
+		}
+	}
+	free(idx);
+	return Dn;
+}
+
+/* (reference fsacmpthrd.c:108-259; intended pair selection) */
+int orc_fsa_cmp_global(int n, int len, const uint64_t *seqs, long wstride,
+                       const unsigned char *include, const uint32_t *mask,
+                       unsigned norm, int elem_size, double byteScale,
+                       void *D, unsigned *global_inc) {
+	int *idx = malloc((size_t) (n > 0 ? n : 1) * sizeof(int));
+	int Dn = compact_included(n, include, idx), r, c;
+	int inc = orc_mask_count(mask, len);
+	double nFactor;
+	size_t cell = 0;
+
+	if(global_inc) *global_inc = (unsigned) inc;
+	/* fsacmpthrd.c:171-176 */
+	if(norm) { nFactor = norm; nFactor /= inc; }
+	else nFactor = 1.0;
+
+	for(r = 1; r < Dn; ++r) {
+		for(c = 0; c < r; ++c, ++cell) {
+			uint64_t dist = orc_masked_mism(seqs + idx[r] * wstride, seqs + idx[c] * wstride, mask, len);
+			double v = nFactor * dist;          /* fsacmpthrd.c:247-255 */
+			char *cellp = (char *) D + cell * elem_size;
+			if(elem_size == 8) *(double *) cellp = v;
+			else if(elem_size == 4) *(float *) cellp = (float) v;
+			else if(elem_size == 2) *(uint16_t *) cellp = (uint16_t) trunc_i32(v * byteScale + 0.5);
+			else *(uint8_t *) cellp = (uint8_t) trunc_i32(v * byteScale + 0.5);
+		}
+	}
+	free(idx);
+	return Dn;
+}

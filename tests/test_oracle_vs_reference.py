@@ -1,0 +1,109 @@
+"""Pin the CPU oracle against the UNMODIFIED reference called in-process through
+oracle/_ref/libccphylo_ref.so (reference objects + oracle/ref_shim.c): the real
+get2BitTable / qseq2nibble / initIncPos / getIncPos / getNpos / maskProxi / fsacmpair and
+the real fsaCmpThreadOut fan-out with cmpairFsaThrd / cmpFsaThrd.  Bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from ccphylo_b200 import synth
+
+pytestmark = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+ALPHABET = np.frombuffer(b"ACGTUNacgtun-RYSWKMBDHVXryswkmbdhvx\n\r *0Zz", dtype=np.uint8)
+
+
+@pytest.mark.parametrize("flag", [1, 3, 9, 11])
+@pytest.mark.parametrize("length", [0, 1, 31, 32, 33, 64, 95, 1000, 4097])
+def test_encode_matches_reference(built, flag, length):
+    rng = np.random.default_rng(1000 * flag + length)
+    data = ALPHABET[rng.integers(0, len(ALPHABET), size=length)].tobytes()
+    codes_r, seq_r, mask_r, unk_r, inc_r = oracle.ref_encode(data, flag=flag)
+    codes = oracle.translate(data, flag)
+    assert np.array_equal(codes, codes_r)
+    seq, unk = oracle.pack(codes)
+    mask, inc = oracle.known_mask(codes)
+    assert unk == unk_r and inc == inc_r
+    assert np.array_equal(seq, seq_r)
+    assert np.array_equal(mask, mask_r)
+
+
+def _random_set(n, length, seed, all_n=()):
+    codes = synth.make_codes(n, length, seed=seed, snp=0.03, nrun=0.08, lower=0.02, gap=0.01)
+    for k in all_n:
+        codes[k, :] = 4
+    return codes
+
+
+@pytest.mark.parametrize("elem,scale", [(8, 1.0), (4, 1.0), (2, 10.0), (2, 100.0), (1, 0.01), (1, 1.0)])
+@pytest.mark.parametrize("norm", [0, 1000, 1000000])
+def test_pair_mode_matches_reference(built, elem, scale, norm):
+    n, length = 13, 2085
+    codes = _random_set(n, length, seed=elem * 7 + norm % 13, all_n=(0, 5))
+    seqs, masks, inc = oracle.encode_samples(codes)
+    min_len = int(0.5 * length)
+    include = (inc >= min_len).astype(np.uint8)
+    for tnum in (1, 3):
+        Dr, Nr, dnr = oracle.ref_fsa_cmp(seqs, masks, include, length, pair=True, tnum=tnum, norm=norm,
+                                         min_length=min_len, min_cov=0.5, elem_size=elem, byte_scale=scale)
+        Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=norm, min_length=min_len, min_cov=0.5,
+                                          elem_size=elem, byte_scale=scale)
+        assert dnr == dno == n - 2
+        assert np.array_equal(Dr.view(np.uint8), Do.view(np.uint8))
+        assert np.array_equal(Nr.view(np.uint8), No.view(np.uint8))
+
+
+def test_pair_gate_minus_one(built):
+    """Pairs whose joint inclusion falls below the gate get -1 in D and keep their count in N."""
+    n, length = 6, 640
+    codes = _random_set(n, length, seed=5)
+    codes[1, :300] = 4
+    codes[2, 250:] = 4          # 1 & 2 overlap in 0 known positions... 250..300 unknown in both
+    seqs, masks, inc = oracle.encode_samples(codes)
+    include = np.ones(n, dtype=np.uint8)
+    for elem, scale in ((8, 1.0), (4, 1.0), (2, 10.0), (1, 0.1)):
+        Dr, Nr, dnr = oracle.ref_fsa_cmp(seqs, masks, include, length, pair=True, norm=100, min_length=200,
+                                         min_cov=0.0, elem_size=elem, byte_scale=scale)
+        Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=100, min_length=200, min_cov=0.0,
+                                          elem_size=elem, byte_scale=scale)
+        assert dnr == dno == n
+        assert np.array_equal(Dr.view(np.uint8), Do.view(np.uint8))
+        assert np.array_equal(Nr.view(np.uint8), No.view(np.uint8))
+    D8, _, _ = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=100, min_length=200, min_cov=0.0)
+    assert (D8 == -1.0).any()
+
+
+@pytest.mark.parametrize("elem,scale", [(8, 1.0), (4, 1.0), (2, 10.0), (1, 0.5)])
+@pytest.mark.parametrize("norm", [0, 1000])
+def test_global_mode_matches_reference_without_exclusions(built, elem, scale, norm):
+    n, length = 11, 3333
+    codes = _random_set(n, length, seed=17 + elem)
+    seqs, _, _ = oracle.encode_samples(codes)
+    include = np.ones(n, dtype=np.uint8)
+    gmask = oracle.global_mask(codes, include)
+    for tnum in (1, 4):
+        Dr, _, dnr = oracle.ref_fsa_cmp(seqs, gmask, include, length, pair=False, tnum=tnum, norm=norm,
+                                        elem_size=elem, byte_scale=scale)
+        Do, dno, ginc = oracle.fsa_cmp_global(seqs, gmask, include, length, norm=norm, elem_size=elem,
+                                              byte_scale=scale)
+        assert dnr == dno == n
+        assert ginc == oracle.lib().orc_mask_count(gmask, length)
+        assert np.array_equal(Dr.view(np.uint8), Do.view(np.uint8))
+
+
+def test_global_mask_accumulation_matches_reference(built):
+    n, length = 7, 1999
+    codes = _random_set(n, length, seed=99)
+    include = np.ones(n, dtype=np.uint8)
+    g = oracle.global_mask(codes, include)
+    R = oracle.ref()
+    W = oracle.words(length)
+    gr = np.zeros(W + 1, dtype=np.uint32)
+    R.refshim_init_mask.argtypes = [np.ctypeslib.ndpointer(np.uint32), __import__("ctypes").c_int]
+    R.refshim_init_mask.restype = None
+    R.refshim_init_mask(gr, length)
+    ref0 = np.ascontiguousarray(codes[0]).copy()
+    R.refshim_and_known(gr, ref0.copy(), ref0.copy(), length, 0)
+    for i in range(1, n):
+        R.refshim_and_known(gr, np.ascontiguousarray(codes[i]).copy(), ref0.copy(), length, 0)
+    assert np.array_equal(g, gr[:W])
