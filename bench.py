@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- pairwise base comparisons/s of the `ccphylo dist` hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch of synthetic KMA-consensus samples:
+encode (reference packed words -> device bit planes) + all-vs-all compare + fused epilogue
+(packed lower-triangular D and N as doubles).  Workload at N=1: BASELINE.json configs[1]
+(1,000 samples x 5 Mbp, pair mode, -n); for N>1 the lower-triangular 64x64 tile blocks are
+dealt to the ranks (no data-path collective) and the sample count grows with sqrt(N) so the
+pairs per GPU stay fixed ("weak").
+
+`value`  : inputs resident in HBM (reference packed format) when the timed region starts.
+`e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers
+           (pinned rows in, host matrices out; H2D + D2H inside the timed region).
+`--impl reference`: the UNMODIFIED reference's fsaCmpThreadOut (oracle/_ref, all host
+           threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "pairwise base comparisons/sec"
+UNIT = "base-cmp/s"
+LENGTH = 5_000_000
+BASE_SAMPLES = 1000
+OPS_PER_BASECMP = 8          # int8 ops of the K=4L tetrahedral+mask contraction
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def samples_for(world, base):
+    n = int(round(base * math.sqrt(world)))
+    return max(64, (n // 64) * 64) if world > 1 else n
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (profiling guide recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference's hot path on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_reference_rate(seqs, masks, length, cores, budget_s, steps=1, warmup=0):
+    """Runs the reference (oracle/_ref) -- or the oracle port if the reference .so is absent --
+    on the first n_s samples, n_s sized so one step is about budget_s seconds.
+    Returns (rate, kind, sample description, seconds per step, D, N)."""
+    import oracle
+
+    kind = "reference" if oracle.have_ref() else "port"
+    n_all = seqs.shape[0]
+
+    def run(ns, tnum):
+        inc = np.ones(ns, dtype=np.uint8)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            D, N, dn = oracle.ref_fsa_cmp(seqs[:ns], masks[:ns], inc, length, pair=True, tnum=tnum, min_length=1,
+                                          min_cov=0.5)
+        else:
+            D, N, dn = oracle.fsa_cmp_pair(seqs[:ns], masks[:ns], inc, length, min_length=1, min_cov=0.5)
+        return time.perf_counter() - t0, D, N
+
+    threads = cores if kind == "reference" else 1
+    probe = min(n_all, max(8, int(math.sqrt(2 * threads * 4)) + 1))
+    t_probe, _, _ = run(probe, threads)
+    rate = probe * (probe - 1) / 2 * length / max(t_probe, 1e-9)
+    pairs = budget_s * rate / length
+    ns = int(min(n_all, max(probe, (1 + math.sqrt(1 + 8 * pairs)) / 2)))
+    times = []
+    D = N = None
+    for k in range(warmup + steps):
+        t, D, N = run(ns, threads)
+        if k >= warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    value = ns * (ns - 1) / 2 * length / sec
+    what = (f"first {ns} of the workload's samples x {length} bp, pair mode, "
+            f"{'fsaCmpThreadOut(cmpairFsaThrd) -t ' + str(threads) if kind == 'reference' else 'oracle port, 1 thread'}")
+    return value, kind, what, sec, threads, ns, D, N
+
+
+def make_host_workload(n, length, seed):
+    """Synthetic workload on the host (numpy) for the reference arm when no GPU generated it."""
+    import oracle
+    from ccphylo_b200 import synth
+
+    codes = synth.make_codes(n, length, seed=seed)
+    return oracle.encode_samples(codes)[:2]
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = samples_for(world, args.samples)
+    # the bounded sample never needs more than a few hundred samples: generate just those
+    ns_cap = min(n, 64 + 8 * cores)
+    seqs, masks = make_host_workload(ns_cap, args.length, seed=2)
+    value, kind, what, sec, threads, ns, _, _ = cpu_reference_rate(seqs, masks, args.length, cores, args.cpu_budget,
+                                                                   steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 words / u32 counters (scalar bit loops)", "data": "synthetic",
+        "config": {"workload": f"{n} samples x {args.length} bp all-vs-all D+N (pair mode, -f 3 -n), "
+                               f"bounded sample: {what}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": what},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=int, default=BASE_SAMPLES, help="samples at N=1 (grows with sqrt(N))")
+    ap.add_argument("--length", type=int, default=LENGTH)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "umma"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work per reference step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}")
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    if args.warmup < 3:
+        log("note: fewer than 3 warm-up steps requested; using 3")
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+
+    from ccphylo_b200 import api, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    n, length = samples_for(world, args.samples), args.length
+    W = api.words(length)
+    t_gen = time.time()
+    seqs_t, masks_t = synth.make_packed_torch(n, length, seed=2, device=dev)
+    torch.cuda.synchronize()
+    log(f"[rank {rank}] generated {n} x {length} bp in {time.time() - t_gen:.1f}s")
+
+    ctx = api.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_kernel({"auto": api.KERNEL_AUTO, "popc": api.KERNEL_POPC, "umma": api.KERNEL_UMMA}[args.kernel])
+    ctx.set_partition(rank, world)
+    ctx.set_problem(n, length, pair=True)
+    ncell = api.cells(n)
+    d_D = torch.zeros(ncell, dtype=torch.float64, device=dev)
+    d_N = torch.zeros(ncell, dtype=torch.float64, device=dev)
+    my_cells = api.partition_cells(n, rank, world)
+    total_basecmp = float(ncell) * length
+
+    def step():
+        ctx.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
+        ctx.run_pair_dev(d_D.data_ptr(), d_N.data_ptr(), norm=0, min_length=1, min_cov=0.5, elem_size=8)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        # per-launch device time of the compare kernel: CUDA events recorded by the library on
+        # the same stream around that launch (read after the region, see below)
+    ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms_total = ev0.elapsed_time(ev1)
+    kms.append(ctx.last_compare_ms())
+    clocks = sampler.stop(t0, t1)
+    launches = ctx.launches - launches0
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    value = total_basecmp / (ms_step * 1e-3)
+
+    # ---- dominant kernel: average launch duration measured live (library events on this stream) ----
+    kern_ms = []
+    for _ in range(3):
+        step()
+        torch.cuda.synchronize()
+        kern_ms.append(ctx.last_compare_ms())
+    kern_ms = float(np.mean(kern_ms))
+    peaks, peaks_src = measured_peaks()
+    int8_peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    my_basecmp = float(my_cells) * length
+    achieved = OPS_PER_BASECMP * my_basecmp / (kern_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)",
+        "frac": achieved / int8_peak, "traffic": None, "kernel": ctx.last_kernel,
+        "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step,
+        "peak_source": f"2 x bf16_tflops_sustained of {peaks_src} MEASURED_PEAKS.json (int8 = 2x bf16 rate)",
+        "algorithmic": f"{OPS_PER_BASECMP} int8 ops per pairwise base comparison (K=4L contraction)",
+    }
+
+    # ---- parity spot check (outside the timed region): a few cells against the oracle ----
+    parity = None
+    cpu_baseline = None
+    if rank == 0:
+        import oracle
+        ns = min(n, 64)
+        hs = seqs_t[:ns].cpu().numpy().view(np.uint64)
+        hm = masks_t[:ns].cpu().numpy().view(np.uint32)
+        Do, No, _ = oracle.fsa_cmp_pair(hs, hm, np.ones(ns, np.uint8), length)
+        Dg = d_D[:api.cells(ns)].cpu().numpy()
+        Ng = d_N[:api.cells(ns)].cpu().numpy()
+        if world == 1:
+            parity = bool(np.array_equal(Dg, Do) and np.array_equal(Ng, No))
+        else:                                   # rank 0 owns only some of these cells
+            own = Ng != 0
+            parity = bool(np.array_equal(Dg[own], Do[own]) and np.array_equal(Ng[own], No[own]))
+        if not parity:
+            raise SystemExit("bench.py: GPU result differs from the oracle -- number withheld")
+
+    # ---- e2e: host buffers through the reference-facing C-ABI call ----
+    e2e = None
+    if not args.no_e2e:
+        L = api.load()
+        import ctypes as C
+        row_s, row_m = W * 8, W * 4
+        hs_ptr = L.ccg_host_alloc(n * row_s)
+        hm_ptr = L.ccg_host_alloc(n * row_m)
+        hD_ptr = L.ccg_host_alloc(max(ncell, 1) * 8)
+        hN_ptr = L.ccg_host_alloc(max(ncell, 1) * 8)
+        if not (hs_ptr and hm_ptr and hD_ptr and hN_ptr):
+            raise SystemExit("bench.py: pinned host allocation failed")
+        hs = np.ctypeslib.as_array(C.cast(hs_ptr, C.POINTER(C.c_uint64)), shape=(n, W))
+        hm = np.ctypeslib.as_array(C.cast(hm_ptr, C.POINTER(C.c_uint32)), shape=(n, W))
+        hs_t = torch.from_numpy(hs.view(np.int64))
+        hm_t = torch.from_numpy(hm.view(np.int32))
+        hs_t.copy_(seqs_t.cpu())
+        hm_t.copy_(masks_t.cpu())
+        sp = (C.c_void_p * n)(*[hs_ptr + k * row_s for k in range(n)])
+        mp = (C.c_void_p * n)(*[hm_ptr + k * row_m for k in range(n)])
+        include = np.ones(n, dtype=np.uint8)
+        dn, ginc = C.c_int(0), C.c_uint(0)
+
+        def e2e_step():
+            rc = L.ccg_fsa_cmp_thread_out(ctx._h, 1, hD_ptr, hN_ptr, 8, 1.0, n, length, sp, include.ctypes.data, mp,
+                                          0, 1, 0.5, 0, C.byref(dn), C.byref(ginc))
+            if rc:
+                raise SystemExit("ccg_fsa_cmp_thread_out failed: " + L.ccg_last_error(ctx._h).decode())
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e_steps = max(2, min(args.steps, 5))
+        ev0.record(stream)
+        for _ in range(e_steps):
+            e2e_step()
+        ev1.record(stream)
+        barrier()
+        e_ms = ev0.elapsed_time(ev1) / e_steps
+        if world > 1:
+            tt = torch.tensor([e_ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_ms = float(tt.item())
+        hD = np.ctypeslib.as_array(C.cast(hD_ptr, C.POINTER(C.c_double)), shape=(max(ncell, 1),))
+        if rank == 0 and world == 1 and not np.array_equal(hD[:ncell], d_D.cpu().numpy()):
+            raise SystemExit("bench.py: host-path result differs from the device-path result")
+        e2e = {"value": total_basecmp / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(n * (row_s + row_m)) * world,
+               "d2h_bytes_per_step": int(2 * ncell * 8) * world, "steps": e_steps,
+               "call": "ccg_fsa_cmp_thread_out(ctx, pair=1, host rows in pinned memory, host D/N out)"}
+        for p in (hs_ptr, hm_ptr, hD_ptr, hN_ptr):
+            L.ccg_host_free(p)
+
+    # ---- cpu baseline: the unmodified reference on this box's host cores (rank 0, N=1 only) ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        ns_cap = min(n, 64 + 8 * cores)
+        hs = seqs_t[:ns_cap].cpu().numpy().view(np.uint64)
+        hm = masks_t[:ns_cap].cpu().numpy().view(np.uint32)
+        v, kind, what, sec, threads, ns, Dc, Nc = cpu_reference_rate(hs, hm, length, cores, args.cpu_budget)
+        same = bool(np.array_equal(Dc, d_D[:api.cells(ns)].cpu().numpy())
+                    and np.array_equal(Nc, d_N[:api.cells(ns)].cpu().numpy()))
+        if not same:
+            raise SystemExit("bench.py: reference CPU result differs from the GPU result")
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": what,
+                        "seconds": sec, "matches_gpu_bit_exact": same}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 bit-planes (LOP3+POPC), u32 counters, f64 epilogue",
+            "data": "synthetic",
+            "config": {"workload": f"{n} samples x {length} bp all-vs-all distance + inclusion matrix "
+                                   f"(pair mode, -f 3 -n), BASELINE configs[1] scaled by sqrt(N) samples",
+                       "samples": n, "length": length, "pairs": ncell,
+                       "partition": f"lower-triangular 64x64 tile blocks dealt to {world} rank(s), no collective",
+                       "l2": "inputs (%.2f GB of planes) larger than the 126 MB L2; no explicit flush" %
+                             (n * W * 12 / 1e9),
+                       "step": "encode (packed words -> bit planes) + compare + fused epilogue"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches), "parity_vs_oracle": parity,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

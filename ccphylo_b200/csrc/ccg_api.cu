@@ -202,6 +202,25 @@ static int make_planes_tmap(ccg_ctx *ctx) {
 extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	if(!ctx || n < 0 || len < 0) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
+	{
+		/* same geometry as the resident store: keep the allocation.  Stale planes of
+		 * slots that are not uploaded again are harmless -- a slot that is absent or
+		 * excluded gets rank -1 and none of its cells is ever written. */
+		const int words = (len >> 5) + ((len & 31) ? 1 : 0);
+		int chunks = (words + CCG_CHUNK_WORDS - 1) / CCG_CHUNK_WORDS;
+		int n_pad = ((n + CCG_TILE - 1) / CCG_TILE) * CCG_TILE;
+		if(n_pad == 0) n_pad = CCG_TILE;
+		if(chunks == 0) chunks = 1;
+		if(ctx->d_planes && ctx->tmap_valid && ctx->words == words && ctx->chunks == chunks && ctx->n_pad == n_pad &&
+		   ctx->pair_mode == (pair_mode ? 1 : 0) && ctx->len == len) {
+			ctx->n = n;
+			memset(ctx->present, 0, (size_t) ctx->n_pad);
+			ctx->global_inc = 0;
+			ctx->last_Dn = 0;
+			ctx->last_ntiles_local = 0;
+			return CCG_OK;
+		}
+	}
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	free_problem(ctx);
 	ctx->n = n;

@@ -1,0 +1,58 @@
+"""N>1 host-side logic on CPU: world_size-2 gloo ranks deal the lower-triangular tile blocks
+between them with no overlap and no gap (the path has no data-path collective; the only
+collective here is the test's own checksum)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ccphylo_b200 import api
+
+    T = api.load().ccg_tile_edge()
+    rows = (n + T - 1) // T
+    owner = torch.zeros(rows * (rows + 1) // 2, dtype=torch.int64)
+    for ti, tj in api.partition_tiles(n, rank, world):
+        owner[ti * (ti + 1) // 2 + tj] += 1
+    cells = torch.tensor([api.partition_cells(n, rank, world)], dtype=torch.int64)
+    dist.all_reduce(owner)
+    dist.all_reduce(cells)
+    if rank == 0:
+        out.put((owner.tolist(), int(cells.item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1000, 1408])
+def test_two_ranks_cover_the_triangle_exactly_once(built, n):
+    import bench
+    from ccphylo_b200 import api
+
+    assert bench.samples_for(1, 1000) == 1000 and bench.samples_for(2, 1000) == 1408
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    owner, cells = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(v == 1 for v in owner)
+    assert cells == api.cells(n)
