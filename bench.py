@@ -229,7 +229,10 @@ def main():
     log(f"[rank {rank}] generated {n} x {length} bp in {time.time() - t_gen:.1f}s")
 
     ctx = api.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on it and the torch events below see the work
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     ctx.set_kernel({"auto": api.KERNEL_AUTO, "popc": api.KERNEL_POPC, "umma": api.KERNEL_UMMA}[args.kernel])
     ctx.set_partition(rank, world)

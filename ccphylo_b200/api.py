@@ -21,7 +21,8 @@ KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA = 0, 1, 2
 
 EXPORTS = [
     "ccg_strerror", "ccg_last_error", "ccg_init", "ccg_destroy", "ccg_set_stream", "ccg_set_kernel", "ccg_sync",
-    "ccg_set_partition", "ccg_tile_edge", "ccg_partition_cells", "ccg_partition_tiles", "ccg_set_problem", "ccg_put_global_mask", "ccg_put_samples_packed",
+    "ccg_set_partition", "ccg_tile_rows", "ccg_tile_cols", "ccg_partition_cells", "ccg_partition_tiles",
+    "ccg_set_scratch_limit", "ccg_set_problem", "ccg_put_global_mask", "ccg_put_samples_packed",
     "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms",
@@ -58,8 +59,11 @@ def load():
     L.ccg_set_kernel.argtypes = [vp, i]
     L.ccg_sync.argtypes = [vp]
     L.ccg_set_partition.argtypes = [vp, i, i]
-    L.ccg_tile_edge.restype = i
-    L.ccg_tile_edge.argtypes = []
+    L.ccg_tile_rows.restype = i
+    L.ccg_tile_rows.argtypes = []
+    L.ccg_tile_cols.restype = i
+    L.ccg_tile_cols.argtypes = []
+    L.ccg_set_scratch_limit.argtypes = [vp, C.c_size_t]
     L.ccg_partition_cells.restype = ll
     L.ccg_partition_cells.argtypes = [i, i, i]
     L.ccg_partition_tiles.restype = ll
@@ -96,7 +100,7 @@ def partition_cells(n, rank, world):
 
 
 def partition_tiles(n, rank, world):
-    """(ti, tj) tiles owned by `rank` of `world` (host only, no device needed)."""
+    """(tm, tn) macro tiles owned by `rank` of `world` (host only, no device needed)."""
     L = load()
     k = L.ccg_partition_tiles(n, rank, world, None, None, 0)
     ti = np.zeros(max(k, 1), dtype=np.int32)
@@ -160,6 +164,9 @@ class Context:
 
     def set_partition(self, rank, world):
         self._ck(self._L.ccg_set_partition(self._h, rank, world))
+
+    def set_scratch_limit(self, nbytes):
+        self._ck(self._L.ccg_set_scratch_limit(self._h, nbytes))
 
     def sync(self):
         self._ck(self._L.ccg_sync(self._h))

@@ -87,12 +87,14 @@ static void free_problem(ccg_ctx *ctx) {
 	cudaFree(ctx->d_gmask); ctx->d_gmask = 0;
 	cudaFree(ctx->d_inc); ctx->d_inc = 0;
 	cudaFree(ctx->d_rank); ctx->d_rank = 0;
+	cudaFree(ctx->d_X); ctx->d_X = 0; ctx->x_bytes = 0;
+	cudaFree(ctx->d_C); ctx->d_C = 0; ctx->c_bytes = 0;
 	free(ctx->present); ctx->present = 0;
 	free(ctx->h_rank); ctx->h_rank = 0;
 	ctx->tmap_valid = 0;
 	ctx->n = ctx->len = 0;
 	ctx->last_Dn = 0;
-	ctx->last_ntiles_local = 0;
+	ctx->last_ntiles = 0;
 }
 
 extern "C" void ccg_destroy(ccg_ctx *ctx) {
@@ -103,6 +105,7 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	cudaFree(ctx->d_stage);
 	cudaFree(ctx->d_acc);
 	cudaFree(ctx->d_tickets);
+	cudaFree(ctx->d_tiles);
 	cudaFree(ctx->d_out_D);
 	cudaFree(ctx->d_out_N);
 	cudaEventDestroy(ctx->ev0);
@@ -123,6 +126,12 @@ extern "C" int ccg_set_kernel(ccg_ctx *ctx, int kernel) {
 	return CCG_OK;
 }
 
+extern "C" int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes) {
+	if(!ctx) return CCG_ERR_ARG;
+	ctx->x_budget = bytes;
+	return CCG_OK;
+}
+
 extern "C" int ccg_sync(ccg_ctx *ctx) {
 	if(!ctx) return CCG_ERR_ARG;
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -136,39 +145,45 @@ extern "C" int ccg_set_partition(ccg_ctx *ctx, int rank, int world) {
 	return CCG_OK;
 }
 
-static int tile_of(long long t, int *ti, int *tj) {
-	int i = (int) ((sqrt(8.0 * (double) t + 1.0) - 1.0) * 0.5);
-	while((long long) (i + 1) * (i + 2) / 2 <= t) ++i;
-	while((long long) i * (i + 1) / 2 > t) --i;
-	*ti = i;
-	*tj = (int) (t - (long long) i * (i + 1) / 2);
-	return 0;
+/* ---- the macro-tile deal (pure host arithmetic) ---- */
+extern "C" int ccg_tile_rows(void) { return CCG_UMMA_BM; }
+extern "C" int ccg_tile_cols(void) { return CCG_UMMA_BN; }
+
+/* visits the macro tiles (tm, tn) of an n-sample triangle owned by rank, in id order */
+template <class F>
+static long long for_each_macro_tile(int n, int rank, int world, F f) {
+	if(n < 2 || world < 1 || rank < 0 || rank >= world) return 0;
+	const int TM = (n + CCG_UMMA_BM - 1) / CCG_UMMA_BM;
+	long long id = 0, owned = 0;
+	for(int tm = 0; tm < TM; ++tm) {
+		for(int tn = 0; 2 * tn <= tm; ++tn, ++id) {
+			if(id % world != rank) continue;
+			f(tm, tn);
+			++owned;
+		}
+	}
+	return owned;
 }
 
-extern "C" int ccg_tile_edge(void) { return CCG_TILE; }
-
-extern "C" long long ccg_partition_tiles(int n, int rank, int world, int *ti_out, int *tj_out, long long cap) {
-	if(n < 1 || world < 1 || rank < 0 || rank >= world) return 0;
-	int rows = (n + CCG_TILE - 1) / CCG_TILE;
-	long long total = ccg_tiles_total(rows), k = 0;
-	for(long long t = rank; t < total; t += world, ++k) {
-		if(k < cap && ti_out && tj_out) tile_of(t, ti_out + k, tj_out + k);
-	}
-	return k;
+extern "C" long long ccg_partition_tiles(int n, int rank, int world, int *tm_out, int *tn_out, long long cap) {
+	long long k = 0;
+	return for_each_macro_tile(n, rank, world, [&](int tm, int tn) {
+		if(k < cap && tm_out && tn_out) { tm_out[k] = tm; tn_out[k] = tn; }
+		++k;
+	});
 }
 
 extern "C" long long ccg_partition_cells(int n, int rank, int world) {
-	if(n < 2 || world < 1 || rank < 0 || rank >= world) return 0;
-	int rows = (n + CCG_TILE - 1) / CCG_TILE;
-	long long total = ccg_tiles_total(rows), cells = 0;
-	for(long long t = rank; t < total; t += world) {
-		int ti, tj;
-		tile_of(t, &ti, &tj);
-		int hi = n - ti * CCG_TILE; if(hi > CCG_TILE) hi = CCG_TILE;
-		int wj = n - tj * CCG_TILE; if(wj > CCG_TILE) wj = CCG_TILE;
-		if(ti == tj) cells += (long long) hi * (hi - 1) / 2;
-		else cells += (long long) hi * wj;
-	}
+	long long cells = 0;
+	for_each_macro_tile(n, rank, world, [&](int tm, int tn) {
+		const int i0 = tm * CCG_UMMA_BM, i1 = i0 + CCG_UMMA_BM < n ? i0 + CCG_UMMA_BM : n;
+		const int j0 = tn * CCG_UMMA_BN;
+		for(int i = i0; i < i1; ++i) {
+			int j1 = j0 + CCG_UMMA_BN;
+			if(j1 > i) j1 = i;
+			if(j1 > j0) cells += j1 - j0;
+		}
+	});
 	return cells;
 }
 
@@ -176,7 +191,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_planes_tmap(ccg_ctx *ctx) {
+static int get_encoder(ccg_ctx *ctx, EncodeTiledFn *out) {
 	void *fn = 0;
 	cudaDriverEntryPointQueryResult qres;
 	CK(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -184,42 +199,67 @@ static int make_planes_tmap(ccg_ctx *ctx) {
 		set_err(ctx, "cuTensorMapEncodeTiled not available from the driver");
 		return CCG_ERR_CUDA;
 	}
+	*out = (EncodeTiledFn) fn;
+	return CCG_OK;
+}
+
+static int make_planes_tmap(ccg_ctx *ctx) {
+	EncodeTiledFn enc;
+	int rc = get_encoder(ctx, &enc);
+	if(rc) return rc;
 	cuuint64_t gdim[4] = {CCG_CHUNK_WORDS, (cuuint64_t) ctx->n_pad, (cuuint64_t) ctx->nplanes, (cuuint64_t) ctx->chunks};
 	cuuint64_t gstride[3] = {16, (cuuint64_t) 16 * ctx->n_pad, (cuuint64_t) 16 * ctx->n_pad * ctx->nplanes};
 	cuuint32_t box[4] = {CCG_CHUNK_WORDS, CCG_TILE, (cuuint32_t) ctx->nplanes, (cuuint32_t) ccg_popc_kc()};
 	cuuint32_t estr[4] = {1, 1, 1, 1};
-	CUresult r = ((EncodeTiledFn) fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, ctx->d_planes, gdim, gstride, box,
-	                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-	                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	CUresult r = enc(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, ctx->d_planes, gdim, gstride, box, estr,
+	                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if(r != CUDA_SUCCESS) {
-		set_err(ctx, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
+		set_err(ctx, "cuTensorMapEncodeTiled(planes) failed with CUresult %d", (int) r);
 		return CCG_ERR_CUDA;
 	}
 	ctx->tmap_valid = 1;
 	return CCG_OK;
 }
 
+/* operand panel X[n_pad][x_chunks*512] int8, 128-byte swizzled boxes of 128 rows */
+static int make_x_tmap(ccg_ctx *ctx) {
+	EncodeTiledFn enc;
+	int rc = get_encoder(ctx, &enc);
+	if(rc) return rc;
+	cuuint64_t gdim[2] = {(cuuint64_t) ctx->x_pitch, (cuuint64_t) ctx->n_pad};
+	cuuint64_t gstride[1] = {(cuuint64_t) ctx->x_pitch};
+	cuuint32_t box[2] = {128, 128};
+	cuuint32_t estr[2] = {1, 1};
+	CUresult r = enc(&ctx->tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->d_X, gdim, gstride, box, estr,
+	                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(r != CUDA_SUCCESS) {
+		set_err(ctx, "cuTensorMapEncodeTiled(X) failed with CUresult %d", (int) r);
+		return CCG_ERR_CUDA;
+	}
+	return CCG_OK;
+}
+
 extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	if(!ctx || n < 0 || len < 0) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
-	{
-		/* same geometry as the resident store: keep the allocation.  Stale planes of
-		 * slots that are not uploaded again are harmless -- a slot that is absent or
-		 * excluded gets rank -1 and none of its cells is ever written. */
-		const int words = (len >> 5) + ((len & 31) ? 1 : 0);
-		int chunks = (words + CCG_CHUNK_WORDS - 1) / CCG_CHUNK_WORDS;
-		int n_pad = ((n + CCG_TILE - 1) / CCG_TILE) * CCG_TILE;
-		if(n_pad == 0) n_pad = CCG_TILE;
-		if(chunks == 0) chunks = 1;
-		if(ctx->d_planes && ctx->tmap_valid && ctx->words == words && ctx->chunks == chunks && ctx->n_pad == n_pad &&
-		   ctx->pair_mode == (pair_mode ? 1 : 0) && ctx->len == len) {
-			ctx->n = n;
-			memset(ctx->present, 0, (size_t) ctx->n_pad);
-			ctx->global_inc = 0;
-			ctx->last_Dn = 0;
-			ctx->last_ntiles_local = 0;
-			return CCG_OK;
-		}
+	const int words = (len >> 5) + ((len & 31) ? 1 : 0);
+	int chunks = (words + CCG_CHUNK_WORDS - 1) / CCG_CHUNK_WORDS;
+	int n_pad = ((n + CCG_SLOT_PAD - 1) / CCG_SLOT_PAD) * CCG_SLOT_PAD;
+	if(n_pad == 0) n_pad = CCG_SLOT_PAD;
+	if(chunks == 0) chunks = 1;
+	/* same geometry as the resident store: keep the allocations.  Stale planes of slots
+	 * that are not uploaded again are harmless -- a slot that is absent or excluded gets
+	 * rank -1 and none of its cells is ever written. */
+	if(ctx->d_planes && ctx->tmap_valid && ctx->words == words && ctx->chunks == chunks && ctx->n_pad == n_pad &&
+	   ctx->pair_mode == (pair_mode ? 1 : 0) && ctx->len == len) {
+		ctx->n = n;
+		memset(ctx->present, 0, (size_t) ctx->n_pad);
+		ctx->global_inc = 0;
+		ctx->last_Dn = 0;
+		ctx->last_ntiles = 0;
+		return CCG_OK;
 	}
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	free_problem(ctx);
@@ -227,11 +267,9 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	ctx->len = len;
 	ctx->pair_mode = pair_mode ? 1 : 0;
 	ctx->nplanes = pair_mode ? 3 : 2;
-	ctx->words = (len >> 5) + ((len & 31) ? 1 : 0);
-	ctx->chunks = (ctx->words + CCG_CHUNK_WORDS - 1) / CCG_CHUNK_WORDS;
-	ctx->n_pad = ((n + CCG_TILE - 1) / CCG_TILE) * CCG_TILE;
-	if(ctx->n_pad == 0) ctx->n_pad = CCG_TILE;
-	if(ctx->chunks == 0) ctx->chunks = 1;
+	ctx->words = words;
+	ctx->chunks = chunks;
+	ctx->n_pad = n_pad;
 	ctx->planes_bytes = (size_t) ctx->chunks * ctx->nplanes * ctx->n_pad * 16;
 	if(cudaMalloc(&ctx->d_planes, ctx->planes_bytes) != cudaSuccess) {
 		set_err(ctx, "cudaMalloc of %zu bytes for the sample store failed: %s", ctx->planes_bytes,
@@ -346,67 +384,72 @@ extern "C" int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out) {
 }
 
 /* choose the K split: fill whole waves of resident CTAs as evenly as possible */
-static void choose_ksplit(const ccg_ctx *ctx, long long ntiles, int kc, int *ksplit, int *cps) {
-	const long long slots = 2LL * ctx->sm_count;
-	const int iters_total = (ctx->chunks + kc - 1) / kc;
+static int choose_split(long long slots, long long ntiles, int iters_total, int min_iters, int max_split) {
 	int best = 1;
 	double best_util = -1.0;
-	for(int k = 1; k <= 64; ++k) {
-		if(k > 1 && iters_total / k < 8) break;
+	for(int k = 1; k <= max_split; ++k) {
+		if(k > 1 && iters_total / k < min_iters) break;
 		long long items = ntiles * k;
 		long long waves = (items + slots - 1) / slots;
 		double util = (double) items / (double) (waves * slots);
 		if(util > best_util + 0.02) { best_util = util; best = k; }
 		if(items >= 8 * slots) break;
 	}
-	int per = (iters_total + best - 1) / best;
-	*ksplit = best;
-	*cps = per * kc;
-	/* drop slices that would start past the end */
-	while(*ksplit > 1 && (long long) (*ksplit - 1) * (*cps) >= ctx->chunks) --*ksplit;
+	return best;
 }
 
-static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
-                      double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn_out) {
-	if(!ctx || !ctx->d_planes) return CCG_ERR_ARG;
-	if(elem_size != 8 && elem_size != 4 && elem_size != 2 && elem_size != 1) return CCG_ERR_ARG;
-	if((mode == 0) != (ctx->pair_mode == 1)) {
-		set_err(ctx, "run mode does not match ccg_set_problem(pair_mode=%d)", ctx->pair_mode);
-		return CCG_ERR_ARG;
+static int ensure_tiles(ccg_ctx *ctx, const int2 *host, size_t count) {
+	if(ctx->tiles_cap < count) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_tiles);
+		ctx->d_tiles = 0;
+		ctx->tiles_cap = 0;
+		CK(ctx, cudaMalloc(&ctx->d_tiles, count * sizeof(int2)));
+		ctx->tiles_cap = count;
 	}
-	if(ctx->kernel_choice == CCG_KERNEL_UMMA) {
-		set_err(ctx, "tcgen05 kernel not built into this library yet");
-		return CCG_ERR_UNSUPPORTED;
-	}
-	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaMemcpyAsync(ctx->d_tiles, host, count * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+	/* the host list is freed by the caller right after this returns */
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return CCG_OK;
+}
 
-	/* compaction map: included samples in input order (fsacmpthrd.c:305-329) */
-	int Dn = 0;
-	for(int i = 0; i < ctx->n_pad; ++i) {
-		int inc = i < ctx->n && ctx->present[i] && (!include || include[i]);
-		ctx->h_rank[i] = inc ? Dn++ : -1;
-	}
-	ctx->last_Dn = Dn;
-	if(Dn_out) *Dn_out = Dn;
-	ctx->last_ntiles_local = 0;
-	if(Dn < 2) return CCG_OK;
-	CK(ctx, cudaMemcpyAsync(ctx->d_rank, ctx->h_rank, (size_t) ctx->n_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
+	/* 64x64 tiles of the macro tiles this rank owns */
+	const int n = ctx->n;
+	size_t cap = 0;
+	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int, int) { cap += (CCG_UMMA_BM / CCG_TILE) * (CCG_UMMA_BN / CCG_TILE); });
+	int2 *host = (int2 *) malloc((cap ? cap : 1) * sizeof(int2));
+	if(!host) return CCG_ERR_NOMEM;
+	size_t cnt = 0;
+	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int tm, int tn) {
+		for(int a = 0; a < CCG_UMMA_BM / CCG_TILE; ++a)
+			for(int b = 0; b < CCG_UMMA_BN / CCG_TILE; ++b) {
+				int ti = tm * (CCG_UMMA_BM / CCG_TILE) + a, tj = tn * (CCG_UMMA_BN / CCG_TILE) + b;
+				if(tj > ti || ti * CCG_TILE >= n || tj * CCG_TILE >= n) continue;
+				host[cnt].x = ti;
+				host[cnt].y = tj;
+				++cnt;
+			}
+	});
+	ctx->last_ntiles = (int) cnt;
+	ctx->last_kernel_kind = CCG_KERNEL_POPC;
+	if(cnt == 0) { free(host); return CCG_OK; }
+	int rc = ensure_tiles(ctx, host, cnt);
+	free(host);
+	if(rc) return rc;
 
 	PopcParams p;
 	memset(&p, 0, sizeof(p));
-	const int tile_rows = ctx->n_pad / CCG_TILE;
-	const long long total = ccg_tiles_total(tile_rows);
-	const long long local = ccg_tiles_local(total, ctx->rank, ctx->world);
-	p.n_pad = ctx->n_pad;
+	const int kc = ccg_popc_kc();
+	const int iters_total = (ctx->chunks + kc - 1) / kc;
 	p.chunks = ctx->chunks;
-	p.rank = ctx->rank;
-	p.world = ctx->world;
-	p.ntiles_local = (int) local;
-	choose_ksplit(ctx, local > 0 ? local : 1, ccg_popc_kc(), &p.ksplit, &p.chunks_per_split);
-	ctx->last_ntiles_local = (int) local;
-	if(local == 0) return CCG_OK;
+	p.ntiles = (int) cnt;
+	p.tiles = ctx->d_tiles;
+	p.ksplit = choose_split(2LL * ctx->sm_count, (long long) cnt, iters_total, 8, 64);
+	p.chunks_per_split = ((iters_total + p.ksplit - 1) / p.ksplit) * kc;
+	while(p.ksplit > 1 && (long long) (p.ksplit - 1) * p.chunks_per_split >= ctx->chunks) --p.ksplit;
 
-	size_t acc_bytes = (size_t) local * 2 * CCG_TILE * CCG_TILE * sizeof(uint32_t);
+	size_t acc_bytes = cnt * 2 * CCG_TILE * CCG_TILE * sizeof(uint32_t);
 	if(ctx->acc_bytes < acc_bytes) {
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
 		cudaFree(ctx->d_acc);
@@ -418,45 +461,171 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 		}
 		ctx->acc_bytes = acc_bytes;
 	}
-	if(ctx->tickets_count < (size_t) local) {
+	if(ctx->tickets_count < cnt) {
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
 		cudaFree(ctx->d_tickets);
 		ctx->d_tickets = 0;
-		CK(ctx, cudaMalloc(&ctx->d_tickets, (size_t) local * sizeof(unsigned)));
-		ctx->tickets_count = (size_t) local;
+		CK(ctx, cudaMalloc(&ctx->d_tickets, cnt * sizeof(unsigned)));
+		ctx->tickets_count = cnt;
 	}
 	if(p.ksplit > 1) {
 		CK(ctx, cudaMemsetAsync(ctx->d_acc, 0, acc_bytes, ctx->stream));
-		CK(ctx, cudaMemsetAsync(ctx->d_tickets, 0, (size_t) local * sizeof(unsigned), ctx->stream));
+		CK(ctx, cudaMemsetAsync(ctx->d_tickets, 0, cnt * sizeof(unsigned), ctx->stream));
 	}
 	p.acc = ctx->d_acc;
 	p.tickets = ctx->d_tickets;
-
-	p.ep.mode = mode;
-	p.ep.elem_size = elem_size;
-	p.ep.norm = norm;
-	p.ep.byteScale = byteScale;
-	p.ep.D = d_D;
-	p.ep.N = mode == 0 ? d_N : 0;
-	p.ep.rank = ctx->d_rank;
-	if(mode == 0) {
-		/* fsacmpthrd.c:292: minLength = minLength < minCov * len ? minCov * len : minLength */
-		if(minLength < minCov * ctx->len) minLength = (unsigned) (minCov * ctx->len);
-		p.ep.minLength = minLength;
-		p.ep.nFactor = 1.0;
-	} else {
-		/* fsacmpthrd.c:171-176 */
-		double nFactor = 1.0;
-		if(norm) { nFactor = norm; nFactor /= (int) ctx->global_inc; }
-		p.ep.nFactor = nFactor;
-	}
-
+	p.ep = ep;
 	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	CK(ctx, ccg_launch_popc(ctx, p));
 	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 	ctx->ev_valid = 1;
-	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_popc<%d> ksplit=%d", ctx->nplanes, p.ksplit);
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_popc<%d> tiles=%d ksplit=%d", ctx->nplanes,
+	         p.ntiles, p.ksplit);
 	return CCG_OK;
+}
+
+static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
+	const int n = ctx->n;
+	size_t cap = 0;
+	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int, int) { ++cap; });
+	int2 *host = (int2 *) malloc((cap ? cap : 1) * sizeof(int2));
+	if(!host) return CCG_ERR_NOMEM;
+	size_t cnt = 0;
+	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int tm, int tn) {
+		host[cnt].x = tm;
+		host[cnt].y = tn;
+		++cnt;
+	});
+	ctx->last_ntiles = (int) cnt;
+	ctx->last_kernel_kind = CCG_KERNEL_UMMA;
+	if(cnt == 0) { free(host); return CCG_OK; }
+	int rc = ensure_tiles(ctx, host, cnt);
+	free(host);
+	if(rc) return rc;
+
+	/* dense int32 accumulators S and I */
+	size_t c_bytes = (size_t) 2 * ctx->n_pad * ctx->n_pad * sizeof(int);
+	if(ctx->c_bytes < c_bytes) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_C);
+		ctx->d_C = 0;
+		ctx->c_bytes = 0;
+		if(cudaMalloc(&ctx->d_C, c_bytes) != cudaSuccess) {
+			set_err(ctx, "cudaMalloc of %zu bytes for the int32 accumulators failed", c_bytes);
+			return CCG_ERR_NOMEM;
+		}
+		ctx->c_bytes = c_bytes;
+	}
+	CK(ctx, cudaMemsetAsync(ctx->d_C, 0, c_bytes, ctx->stream));
+
+	/* operand panel: as many chunks per slab as the scratch budget allows */
+	size_t free_b = 0, total_b = 0;
+	CK(ctx, cudaMemGetInfo(&free_b, &total_b));
+	size_t budget = ctx->x_budget ? ctx->x_budget : (size_t) 48 << 30;
+	size_t avail = free_b + ctx->x_bytes;
+	if(budget > avail - avail / 8) budget = avail - avail / 8;
+	long long slab = (long long) (budget / ((size_t) ctx->n_pad * 512));
+	if(slab > ctx->chunks) slab = ctx->chunks;
+	if(slab < 1) {
+		set_err(ctx, "not enough device memory for one chunk of the operand panel (%d slots)", ctx->n_pad);
+		return CCG_ERR_NOMEM;
+	}
+	/* equal slabs */
+	const int nslabs = (int) ((ctx->chunks + slab - 1) / slab);
+	slab = (ctx->chunks + nslabs - 1) / nslabs;
+	size_t x_pitch = (size_t) slab * 512;
+	size_t x_bytes = x_pitch * ctx->n_pad;
+	if(ctx->x_bytes < x_bytes || ctx->x_chunks != (int) slab) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_X);
+		ctx->d_X = 0;
+		ctx->x_bytes = 0;
+		if(cudaMalloc(&ctx->d_X, x_bytes) != cudaSuccess) {
+			set_err(ctx, "cudaMalloc of %zu bytes for the operand panel failed", x_bytes);
+			return CCG_ERR_NOMEM;
+		}
+		ctx->x_bytes = x_bytes;
+		ctx->x_chunks = (int) slab;
+		ctx->x_pitch = x_pitch;
+		rc = make_x_tmap(ctx);
+		if(rc) return rc;
+	}
+
+	UmmaParams p;
+	memset(&p, 0, sizeof(p));
+	p.ntiles = (int) cnt;
+	p.tiles = ctx->d_tiles;
+	p.C_S = ctx->d_C;
+	p.C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
+	p.ldc = ctx->n_pad;
+	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	for(int s = 0; s < nslabs; ++s) {
+		const int chunk0 = (int) (s * slab);
+		int nch = ctx->chunks - chunk0;
+		if(nch > slab) nch = (int) slab;
+		p.slab_chunks = nch;
+		p.kslices = choose_split((long long) ctx->sm_count, (long long) cnt, nch, 16, 512);
+		p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
+		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nch) --p.kslices;
+		CK(ctx, ccg_launch_expand(ctx, chunk0, nch));
+		CK(ctx, ccg_launch_umma(ctx, p));
+	}
+	/* shared-mask mode: every position of every chunk counts as included in the raw product */
+	const int i_const = ctx->chunks * CCG_CHUNK_BASES;
+	CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, i_const));
+	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	ctx->ev_valid = 1;
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_umma tiles=%d kslices=%d slabs=%d", p.ntiles,
+	         p.kslices, nslabs);
+	return CCG_OK;
+}
+
+static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
+                      double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn_out) {
+	if(!ctx || !ctx->d_planes) return CCG_ERR_ARG;
+	if(elem_size != 8 && elem_size != 4 && elem_size != 2 && elem_size != 1) return CCG_ERR_ARG;
+	if((mode == 0) != (ctx->pair_mode == 1)) {
+		set_err(ctx, "run mode does not match ccg_set_problem(pair_mode=%d)", ctx->pair_mode);
+		return CCG_ERR_ARG;
+	}
+	CK(ctx, cudaSetDevice(ctx->device));
+
+	/* compaction map: included samples in input order (fsacmpthrd.c:305-329) */
+	int Dn = 0;
+	for(int i = 0; i < ctx->n_pad; ++i) {
+		int inc = i < ctx->n && ctx->present[i] && (!include || include[i]);
+		ctx->h_rank[i] = inc ? Dn++ : -1;
+	}
+	ctx->last_Dn = Dn;
+	if(Dn_out) *Dn_out = Dn;
+	ctx->last_ntiles = 0;
+	if(Dn < 2) return CCG_OK;
+	CK(ctx, cudaMemcpyAsync(ctx->d_rank, ctx->h_rank, (size_t) ctx->n_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+
+	EpilogueParams ep;
+	memset(&ep, 0, sizeof(ep));
+	ep.mode = mode;
+	ep.elem_size = elem_size;
+	ep.norm = norm;
+	ep.byteScale = byteScale;
+	ep.D = d_D;
+	ep.N = mode == 0 ? d_N : 0;
+	ep.rank = ctx->d_rank;
+	if(mode == 0) {
+		/* fsacmpthrd.c:292: minLength = minLength < minCov * len ? minCov * len : minLength */
+		if(minLength < minCov * ctx->len) minLength = (unsigned) (minCov * ctx->len);
+		ep.minLength = minLength;
+		ep.nFactor = 1.0;
+	} else {
+		/* fsacmpthrd.c:171-176 */
+		double nFactor = 1.0;
+		if(norm) { nFactor = norm; nFactor /= (int) ctx->global_inc; }
+		ep.nFactor = nFactor;
+	}
+	/* AUTO: the tensor-core kernel wins once there is enough work to fill the machine */
+	int kind = ctx->kernel_choice;
+	if(kind == CCG_KERNEL_AUTO) kind = CCG_KERNEL_POPC;
+	return kind == CCG_KERNEL_UMMA ? run_umma(ctx, ep) : run_popc(ctx, ep);
 }
 
 static int run_to_host(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
@@ -533,7 +702,9 @@ extern "C" int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc) 
 	if(cudaMalloc(&d_n, cells * 4) != cudaSuccess) { cudaFree(d_m); return CCG_ERR_NOMEM; }
 	cudaMemsetAsync(d_m, 0, cells * 4, ctx->stream);
 	cudaMemsetAsync(d_n, 0, cells * 4, ctx->stream);
-	cudaError_t e = ccg_launch_gather_raw(ctx, Dn, d_m, d_n);
+	cudaError_t e;
+	if(ctx->last_kernel_kind == CCG_KERNEL_UMMA) e = ccg_launch_gather_raw_dense(ctx, ctx->chunks * CCG_CHUNK_BASES, d_m, d_n);
+	else e = ccg_launch_gather_raw(ctx, d_m, d_n);
 	if(e == cudaSuccess && mism) e = cudaMemcpyAsync(mism, d_m, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
 	if(e == cudaSuccess && ninc) e = cudaMemcpyAsync(ninc, d_n, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
 	if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -9,14 +9,18 @@
  *   plane  = 0: high bit of the 2-bit code, 1: low bit, 2: inclusion mask
  *            (pair mode: 3 planes; shared-mask mode: 2 planes, the global mask
  *             is folded into the code planes at encode time)
- *   slot   = sample index, padded to a multiple of CCG_TILE
+ *   slot   = sample index, padded to a multiple of CCG_SLOT_PAD
  *   bit 31-(p%32) of word (p/32)%4 <-> base p (the reference's mask bit order,
  *   fsacmp.c:164).  Code bits of masked positions are cleared, so a plane word
  *   of an absent / padded slot is all-zero and contributes nothing.
  *
- * One (chunk, plane) row of CCG_TILE slots is 1 KiB contiguous, every thread
- * access is a 128-bit vector, and a [KC chunks][planes][CCG_TILE slots][4]
- * box is a single TMA tile.
+ * One (chunk, plane) row of 64 slots is 1 KiB contiguous, every thread access
+ * is a 128-bit vector, and a [KC chunks][planes][64 slots][4] box is a single
+ * TMA tile.
+ *
+ * Work partition (both compare kernels): the lower triangle is cut into macro
+ * tiles of CCG_UMMA_BM rows x CCG_UMMA_BN columns, enumerated row-major over
+ * (tm, tn <= tm/2); macro tile id % world == rank is owned by `rank`.
  */
 #ifndef CCG_INTERNAL_H
 #define CCG_INTERNAL_H
@@ -30,6 +34,9 @@
 #define CCG_TILE 64          /* samples per tile edge (popc kernel) */
 #define CCG_CHUNK_WORDS 4    /* u32 words per plane per chunk */
 #define CCG_CHUNK_BASES 128
+#define CCG_UMMA_BM 128      /* macro tile rows    (tcgen05 M, TMEM lanes) */
+#define CCG_UMMA_BN 256      /* macro tile columns (tcgen05 N) */
+#define CCG_SLOT_PAD 256     /* slots are padded to a multiple of this */
 
 struct EpilogueParams {
 	int mode;              /* 0 pair (fsacmpthrd.c:419-475), 1 global (fsacmpthrd.c:247-255) */
@@ -44,15 +51,24 @@ struct EpilogueParams {
 };
 
 struct PopcParams {
-	int n_pad;             /* slots (multiple of CCG_TILE) */
 	int chunks;            /* ceil(words/4) */
 	int ksplit;            /* K slices per tile */
 	int chunks_per_split;  /* multiple of KC */
-	int ntiles_local;      /* tiles owned by this rank */
-	int rank, world;       /* tile t is owned by rank t % world */
-	uint32_t *acc;         /* [ntiles_local][2][TILE*TILE] raw mism / ninc */
-	unsigned *tickets;     /* [ntiles_local] */
+	int ntiles;            /* 64x64 tiles owned by this rank */
+	const int2 *tiles;     /* device: (ti, tj) */
+	uint32_t *acc;         /* [ntiles][2][TILE*TILE] raw mism / ninc */
+	unsigned *tickets;     /* [ntiles] */
 	EpilogueParams ep;
+};
+
+struct UmmaParams {
+	int ntiles;            /* macro tiles owned by this rank */
+	const int2 *tiles;     /* device: (tm, tn) */
+	int kslices;           /* K slices per tile within the slab */
+	int chunks_per_slice;
+	int slab_chunks;       /* chunks resident in X */
+	int *C_S, *C_I;        /* dense [n_pad][ldc] int32 accumulators */
+	int ldc;
 };
 
 struct ccg_ctx {
@@ -77,21 +93,33 @@ struct ccg_ctx {
 	int *d_rank;               /* [n_pad] */
 	int *h_rank;               /* host mirror of the last run */
 	int last_Dn;
-	uint32_t *d_acc;
+	int2 *d_tiles;             /* tile list of the last run */
+	size_t tiles_cap;
+	int last_ntiles;
+	int last_kernel_kind;      /* CCG_KERNEL_POPC / CCG_KERNEL_UMMA of the last run */
+	uint32_t *d_acc;           /* popc: tile-major raw counts */
 	size_t acc_bytes;
 	unsigned *d_tickets;
 	size_t tickets_count;
-	int last_ntiles_local;
 	void *d_out_D, *d_out_N;   /* device result buffers for the host-output API */
 	size_t out_bytes;
 
+	/* tensor-core path */
+	int8_t *d_X;               /* operand panel [n_pad][x_chunks][4][128] */
+	size_t x_bytes, x_pitch;
+	int x_chunks;              /* chunks per slab */
+	int *d_C;                  /* 2 x [n_pad][n_pad] int32 */
+	size_t c_bytes;
+	size_t x_budget;           /* max bytes for d_X (0 = default) */
+
 	CUtensorMap tmap;          /* planes as a 4-D tensor */
+	CUtensorMap tmap_x;        /* operand panel as a 2-D tensor */
 	int tmap_valid;
 
 	cudaEvent_t ev0, ev1;
 	int ev_valid;
 	long long launches;
-	char last_kernel[64];
+	char last_kernel[96];
 	char err[512];
 };
 
@@ -102,18 +130,16 @@ cudaError_t ccg_launch_repack(ccg_ctx *ctx, int first, int count, const uint64_t
                               const uint32_t *d_masks, long wstride);
 cudaError_t ccg_launch_encode_codes(ccg_ctx *ctx, int first, int count, const unsigned char *d_codes,
                                     long stride);
-cudaError_t ccg_launch_gather_raw(ccg_ctx *ctx, int Dn, uint32_t *d_mism, uint32_t *d_ninc);
+cudaError_t ccg_launch_gather_raw(ccg_ctx *ctx, uint32_t *d_mism, uint32_t *d_ninc);
 
 /* k_pairdist_popc.cu */
 cudaError_t ccg_launch_popc(ccg_ctx *ctx, const PopcParams &p);
 int ccg_popc_kc(void);
 
-/* tile bookkeeping shared by host and device */
-static inline __host__ __device__ long long ccg_tiles_total(int ntile_rows) {
-	return (long long) ntile_rows * (ntile_rows + 1) / 2;
-}
-static inline __host__ __device__ long long ccg_tiles_local(long long total, int rank, int world) {
-	return total > rank ? (total - rank + world - 1) / world : 0;
-}
+/* k_pairdist_umma.cu */
+cudaError_t ccg_launch_expand(ccg_ctx *ctx, int chunk0, int nchunks);
+cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
+cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);
+cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc);
 
 #endif

@@ -126,15 +126,11 @@ k_encode_codes(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks
 
 /* tile-major raw counts -> packed lower triangle over included samples */
 __global__ void __launch_bounds__(256)
-k_gather_raw(const uint32_t *__restrict__ acc, int ntiles_local, int rank_id, int world, const int *__restrict__ rank,
+k_gather_raw(const uint32_t *__restrict__ acc, int ntiles, const int2 *__restrict__ tiles, const int *__restrict__ rank,
              uint32_t *__restrict__ mism, uint32_t *__restrict__ ninc) {
 	int lt = blockIdx.x;
-	if(lt >= ntiles_local) return;
-	long long t = (long long) lt * world + rank_id;
-	int ti = (int) ((sqrt(8.0 * (double) t + 1.0) - 1.0) * 0.5);
-	while((long long) (ti + 1) * (ti + 2) / 2 <= t) ++ti;
-	while((long long) ti * (ti + 1) / 2 > t) --ti;
-	int tj = (int) (t - (long long) ti * (ti + 1) / 2);
+	if(lt >= ntiles) return;
+	const int ti = tiles[lt].x, tj = tiles[lt].y;
 	const uint32_t *a = acc + (size_t) lt * 2 * CCG_TILE * CCG_TILE;
 	for(int e = threadIdx.x; e < CCG_TILE * CCG_TILE; e += blockDim.x) {
 		int i = ti * CCG_TILE + e / CCG_TILE;
@@ -175,11 +171,10 @@ cudaError_t ccg_launch_encode_codes(ccg_ctx *ctx, int first, int count, const un
 	return cudaGetLastError();
 }
 
-cudaError_t ccg_launch_gather_raw(ccg_ctx *ctx, int Dn, uint32_t *d_mism, uint32_t *d_ninc) {
-	(void) Dn;
-	if(ctx->last_ntiles_local <= 0) return cudaSuccess;
-	k_gather_raw<<<ctx->last_ntiles_local, 256, 0, ctx->stream>>>(ctx->d_acc, ctx->last_ntiles_local, ctx->rank,
-	                                                              ctx->world, ctx->d_rank, d_mism, d_ninc);
+cudaError_t ccg_launch_gather_raw(ccg_ctx *ctx, uint32_t *d_mism, uint32_t *d_ninc) {
+	if(ctx->last_ntiles <= 0) return cudaSuccess;
+	k_gather_raw<<<ctx->last_ntiles, 256, 0, ctx->stream>>>(ctx->d_acc, ctx->last_ntiles, ctx->d_tiles, ctx->d_rank,
+	                                                        d_mism, d_ninc);
 	ctx->launches++;
 	return cudaGetLastError();
 }

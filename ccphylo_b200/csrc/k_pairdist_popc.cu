@@ -59,9 +59,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, unsigned parity) {
 
 /* bounded wait: a lost TMA completion traps instead of hanging the GPU */
 __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
+	if(mbar_try_wait(bar, parity)) return;
+	const long long t0 = clock64();
 	unsigned spins = 0;
 	while(!mbar_try_wait(bar, parity)) {
-		if(++spins > (1u << 24)) __trap();
+		/* watchdog: ~2 s at 2 GHz, far beyond any legitimate wait in these kernels */
+		if((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
 	}
 }
 
@@ -93,13 +96,9 @@ k_pairdist_popc(const __grid_constant__ CUtensorMap tmap, const PopcParams p) {
 
 	/* work item -> (local tile, K slice); K slices outermost so co-resident
 	 * CTAs walk the same chunk range and share it through L2 */
-	const int lt = blockIdx.x % p.ntiles_local;
-	const int ks = blockIdx.x / p.ntiles_local;
-	const long long t = (long long) lt * p.world + p.rank;
-	int ti = (int) ((sqrt(8.0 * (double) t + 1.0) - 1.0) * 0.5);
-	while((long long) (ti + 1) * (ti + 2) / 2 <= t) ++ti;
-	while((long long) ti * (ti + 1) / 2 > t) --ti;
-	const int tj = (int) (t - (long long) ti * (ti + 1) / 2);
+	const int lt = blockIdx.x % p.ntiles;
+	const int ks = blockIdx.x / p.ntiles;
+	const int ti = p.tiles[lt].x, tj = p.tiles[lt].y;
 
 	const int c_begin = ks * p.chunks_per_split;
 	int span = p.chunks - c_begin;
@@ -227,7 +226,7 @@ cudaError_t launch(ccg_ctx *ctx, const PopcParams &p) {
 	constexpr int smem = STAGES * 2 * KC * NPL * T * 16 + STAGES * 8 + 128;
 	cudaError_t e = cudaFuncSetAttribute(k_pairdist_popc<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if(e != cudaSuccess) return e;
-	const long long items = (long long) p.ntiles_local * p.ksplit;
+	const long long items = (long long) p.ntiles * p.ksplit;
 	if(items <= 0) return cudaSuccess;
 	k_pairdist_popc<NPL><<<(unsigned) items, THREADS, smem, ctx->stream>>>(ctx->tmap, p);
 	ctx->launches++;

@@ -1,0 +1,348 @@
+/*
+ * k_pairdist_umma.cu -- K2a: the all-vs-all compare as an int8 contraction on
+ * the tcgen05 tensor cores (int32 accumulation in TMEM), plus the operand
+ * expansion and the finalising epilogue.
+ *
+ * Replaces the same reference code as K2b: maskProxi (proxi == 0)
+ * fsacmp.c:355-389, fsacmpair fsacmp.c:587-633, fsacmp fsacmp.c:552-585 and
+ * the pair loop + epilogue of cmpairFsaThrd / cmpFsaThrd
+ * (fsacmpthrd.c:261-480 / :108-259).
+ *
+ * Algebra.  Per base every sample gets three
+ * "tetrahedral" int8 channels and one mask channel:
+ *     A=(+1,+1,+1) C=(+1,-1,-1) G=(-1,+1,-1) T=(-1,-1,+1)  unknown=(0,0,0), m = known ? 1 : 0
+ * Over the three code channels  S(i,j) = sum t_i.t_j = 3*match - mismatch  on
+ * jointly known positions, over the mask channel  I(i,j) = sum m_i*m_j = the
+ * inclusion count.  Hence   mismatch = (3*I - S) / 4   exactly, in int32
+ * (|S|, I <= 3L < 2^31).  K = 4L bytes: 8 int8 ops per pairwise base comparison.
+ *
+ * Operand panel X (HBM, built by k_expand from the bit planes):
+ *     X[slot][chunk][channel 0..3][128 bases]  int8   (K-major rows)
+ * one 128-byte channel row = one SWIZZLE_128B row = one pipeline stage.
+ *
+ * GEMM work item = (tile of 128 rows x 256 columns of the lower triangle,
+ * K slice of chunks).  Warp 0 lane 0 issues TMA (A: 128x128 B, B: 2 x 128x128 B
+ * per stage, 4 stages); warp 1 lane 0 issues tcgen05.mma kind::i8 M=128 N=256
+ * K=32 (4 per stage) into two TMEM accumulators (S: channels 0-2, I: channel 3);
+ * warps 2-5 drain TMEM with tcgen05.ld and RED.ADD the int32 partials into the
+ * dense C buffers (split-K is exact for integers).  k_finalize applies
+ * (3I-S)/4 and the reference epilogue.
+ */
+#include "ccg_internal.h"
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr int BM = CCG_UMMA_BM;      /* 128 rows  (A tile, TMEM lanes) */
+constexpr int BN = CCG_UMMA_BN;      /* 256 cols  (B tile, TMEM columns per accumulator) */
+constexpr int BK = 128;              /* K bytes per stage = one channel row of a chunk */
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK;
+constexpr int B_BYTES = BN * BK;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+/* instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) @4,
+ * a/b_format signed int8 (1) @7/@10, K-major A and B, n_dim = N>>3 @17, m_dim = M>>4 @24 */
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, unsigned parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	return ok != 0;
+}
+/* bounded wait: a lost completion traps (reported as a CUDA error) instead of hanging the GPU */
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
+	if(mbar_try_wait(bar, parity)) return;
+	const long long t0 = clock64();
+	unsigned spins = 0;
+	while(!mbar_try_wait(bar, parity)) {
+		/* watchdog: ~2 s at 2 GHz, far beyond any legitimate wait in these kernels */
+		if((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+	}
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+	    ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+/* K-major SWIZZLE_128B shared-memory matrix descriptor (SmemDescriptor in
+ * cute/arch/mma_sm100_desc.hpp): start>>4 @0, LBO=1 @16 (ignored for swizzled K-major),
+ * SBO = 1024 B (8 rows x 128 B) >> 4 @32, version 1 @46, layout SWIZZLE_128B (2) @61 */
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+	return (uint64_t) ((saddr & 0x3FFFFu) >> 4) | ((uint64_t) 1 << 16) | ((uint64_t) (1024 >> 4) << 32) |
+	       ((uint64_t) 1 << 46) | ((uint64_t) 2 << 61);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+	    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+	    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+	      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+	      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+	      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+	    : "r"(taddr) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+/* ------------------------------------------------------------------ */
+/* operand expansion: bit planes -> int8 panel                         */
+/* ------------------------------------------------------------------ */
+/* 4 plane bits (bit j <-> base j of the group) -> 4 bytes of 0/1 */
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+/* One warp per (slot, chunk): lane = channel*8 + segment of 16 bases; the warp
+ * writes the 512 contiguous bytes X[slot][chunk][0..3][0..127]. */
+__global__ void __launch_bounds__(256)
+k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slots, int chunk0, int nchunks,
+         int8_t *__restrict__ X, size_t row_pitch) {
+	const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if(warp >= (long long) slots * nchunks) return;
+	const int slot = (int) (warp % slots);
+	const int cl = (int) (warp / slots);           /* chunk within the slab */
+	const int ch = lane >> 3, seg = lane & 7;
+	const int q = seg >> 1, half = seg & 1;
+	const size_t prow = (size_t) (chunk0 + cl) * nplanes;
+	const uint32_t *ph = planes + ((prow + 0) * n_pad + slot) * 4;
+	const uint32_t *pl = planes + ((prow + 1) * n_pad + slot) * 4;
+	uint32_t h = ph[q], l = pl[q], m;
+	if(nplanes == 3) m = planes[((prow + 2) * n_pad + slot) * 4 + q];
+	else m = 0xFFFFFFFFu;                          /* shared-mask mode: planes are pre-masked, see below */
+	/* base k of the word <-> bit 31-k; reverse so base k <-> bit k, then take this lane's 16 bases */
+	h = (__brev(h) >> (16 * half)) & 0xFFFFu;
+	l = (__brev(l) >> (16 * half)) & 0xFFFFu;
+	m = (__brev(m) >> (16 * half)) & 0xFFFFu;
+	/* sign bit of the channel: 0 -> h, 1 -> l, 2 -> h^l; channel 3 is the mask itself */
+	const uint32_t neg = ch == 0 ? h : ch == 1 ? l : ch == 2 ? (h ^ l) : 0u;
+	uint32_t out[4];
+#pragma unroll
+	for(int g = 0; g < 4; ++g) {
+		const uint32_t ones = spread4((m >> (4 * g)) & 0xFu);                 /* 0x01 where known */
+		const uint32_t minus = spread4(((neg & m) >> (4 * g)) & 0xFu);        /* 0x01 where the value is -1 */
+		out[g] = ones | (minus * 0xFEu);                                       /* +1 = 0x01, -1 = 0xFF, 0 */
+	}
+	uint4 *dst = reinterpret_cast<uint4 *>(X + (size_t) slot * row_pitch + (size_t) cl * 512 + ch * 128 + seg * 16);
+	*dst = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+/* ------------------------------------------------------------------ */
+/* the GEMM                                                            */
+/* ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(THREADS, 1)
+k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t raw = smem_u32(smem_raw);
+	const uint32_t base = (raw + 1023u) & ~1023u;                /* SWIZZLE_128B tiles need 1024-byte alignment */
+	const uint32_t bar_full = base + STAGES * STAGE_BYTES;       /* STAGES x 8 B */
+	const uint32_t bar_empty = bar_full + 8 * STAGES;            /* STAGES x 8 B */
+	const uint32_t bar_accum = bar_empty + 8 * STAGES;           /* 8 B */
+	const uint32_t tmem_slot = bar_accum + 8;                    /* 4 B */
+	volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int tile = blockIdx.x % p.ntiles;
+	const int ks = blockIdx.x / p.ntiles;
+	const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
+	const int c_begin = ks * p.chunks_per_slice;
+	int nchunk = p.slab_chunks - c_begin;
+	if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
+	if(nchunk < 0) nchunk = 0;
+	const int nkb = nchunk * 4;                                   /* k-blocks: 4 channel rows per chunk */
+
+	if(threadIdx.x == 0) {
+		for(int s = 0; s < STAGES; ++s) {
+			mbar_init(bar_full + 8 * s, 1);
+			mbar_init(bar_empty + 8 * s, 1);
+		}
+		mbar_init(bar_accum, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	if(warp == 2) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem = *tmem_slot_ptr;
+
+	if(warp == 0) {
+		/* ===== TMA producer ===== */
+		if(lane == 0) {
+			for(int kb = 0; kb < nkb; ++kb) {
+				const int s = kb % STAGES;
+				if(kb >= STAGES) mbar_wait(bar_empty + 8 * s, ((kb / STAGES) - 1) & 1);
+				const uint32_t dst = base + s * STAGE_BYTES;
+				const uint32_t bar = bar_full + 8 * s;
+				const int kcoord = (c_begin * 4 + kb) * BK;
+				mbar_expect_tx(bar, STAGE_BYTES);
+				tma_load_2d(dst, &tmap, bar, kcoord, tm * BM);
+				tma_load_2d(dst + A_BYTES, &tmap, bar, kcoord, tn * BN);
+				tma_load_2d(dst + A_BYTES + 128 * BK, &tmap, bar, kcoord, tn * BN + 128);
+			}
+		}
+	} else if(warp == 1) {
+		/* ===== MMA issuer ===== */
+		if(lane == 0) {
+			uint32_t usedS = 0, usedI = 0;
+			for(int kb = 0; kb < nkb; ++kb) {
+				const int s = kb % STAGES;
+				mbar_wait(bar_full + 8 * s, (kb / STAGES) & 1);
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				const uint32_t a0 = base + s * STAGE_BYTES;
+				const uint64_t adesc = make_desc(a0);
+				const uint64_t bdesc = make_desc(a0 + A_BYTES);
+				const bool is_mask = (kb & 3) == 3;
+				const uint32_t d = tmem + (is_mask ? BN : 0);
+#pragma unroll
+				for(int k = 0; k < BK / 32; ++k) {
+					const uint32_t acc = is_mask ? usedI : usedS;
+					/* advancing K by 32 bytes inside the 128-byte swizzle row: +2 in the (addr>>4) field */
+					umma_i8(d, adesc + 2 * k, bdesc + 2 * k, acc);
+					if(is_mask) usedI = 1; else usedS = 1;
+				}
+				umma_commit(bar_empty + 8 * s);        /* frees the stage once these MMAs have read it */
+			}
+			umma_commit(bar_accum);                     /* accumulators complete */
+		}
+	} else {
+		/* ===== epilogue: TMEM -> registers -> RED.ADD into C ===== */
+		const int quarter = warp & 3;                   /* a warp may only touch TMEM lanes 32*(warp%4).. */
+		const int row = tm * BM + quarter * 32 + lane;
+		if(nkb > 0) {
+			mbar_wait(bar_accum, 0);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			int *cS = p.C_S + (size_t) row * p.ldc + tn * BN;
+			int *cI = p.C_I + (size_t) row * p.ldc + tn * BN;
+			const int jlim = row - tn * BN;              /* only columns j < row are ever read back */
+#pragma unroll 1
+			for(int cb = 0; cb < BN / 32; ++cb) {
+				if(__all_sync(0xffffffffu, cb * 32 >= jlim)) break;
+				uint32_t r[32];
+				tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + cb * 32, r);
+#pragma unroll
+				for(int e = 0; e < 32; ++e)
+					if(cb * 32 + e < jlim && r[e]) atomicAdd(cS + cb * 32 + e, (int) r[e]);
+				tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + BN + cb * 32, r);
+#pragma unroll
+				for(int e = 0; e < 32; ++e)
+					if(cb * 32 + e < jlim && r[e]) atomicAdd(cI + cb * 32 + e, (int) r[e]);
+			}
+		}
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if(warp == 2) {
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+	}
+}
+
+/* mismatch = (3I - S)/4, then the reference epilogue.  Pair mode: I comes from the mask
+ * channel.  Shared-mask mode: the planes are pre-masked and expanded with m = 1 everywhere,
+ * so every masked / padded position is an (A, A) match and I is the constant i_const =
+ * chunks * 128 (then 3*i_const - S = 4 * mismatch as well). */
+__global__ void __launch_bounds__(256)
+k_finalize_umma(const int *__restrict__ C_S, const int *__restrict__ C_I, int ldc, int n, int pair_mode, int i_const,
+                const int2 *__restrict__ tiles, int ntiles, EpilogueParams ep) {
+	const int tile = blockIdx.x;
+	if(tile >= ntiles) return;
+	const int tm = tiles[tile].x, tn = tiles[tile].y;
+	for(int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
+		const int i = tm * BM + e / BN;
+		const int j = tn * BN + e % BN;
+		if(i >= n || j >= i) continue;
+		const int S = C_S[(size_t) i * ldc + j];
+		const int I = pair_mode ? C_I[(size_t) i * ldc + j] : i_const;
+		const unsigned mism = (unsigned) ((3 * (long long) I - S) >> 2);
+		ccg_write_cell(ep, i, j, mism, (unsigned) I);
+	}
+}
+
+/* raw integer counts of the last run -> packed lower triangle over included samples */
+__global__ void __launch_bounds__(256)
+k_gather_raw_dense(const int *__restrict__ C_S, const int *__restrict__ C_I, int ldc, int n, int pair_mode, int i_const,
+                   const int2 *__restrict__ tiles, int ntiles, const int *__restrict__ rank,
+                   uint32_t *__restrict__ mism, uint32_t *__restrict__ ninc) {
+	const int tile = blockIdx.x;
+	if(tile >= ntiles) return;
+	const int tm = tiles[tile].x, tn = tiles[tile].y;
+	for(int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
+		const int i = tm * BM + e / BN;
+		const int j = tn * BN + e % BN;
+		if(i >= n || j >= i) continue;
+		const int r = rank[i], c = rank[j];
+		if(r < 0 || c < 0) continue;
+		const long long cell = (long long) r * (r - 1) / 2 + c;
+		const int S = C_S[(size_t) i * ldc + j];
+		const int I = pair_mode ? C_I[(size_t) i * ldc + j] : i_const;
+		if(mism) mism[cell] = (unsigned) ((3 * (long long) I - S) >> 2);
+		if(ninc) ninc[cell] = (unsigned) I;
+	}
+}
+
+} // namespace
+
+cudaError_t ccg_launch_expand(ccg_ctx *ctx, int chunk0, int nchunks) {
+	const int slots = ctx->n_pad;
+	const long long warps = (long long) slots * nchunks;
+	if(warps <= 0) return cudaSuccess;
+	const unsigned blocks = (unsigned) ((warps * 32 + 255) / 256);
+	k_expand<<<blocks, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, slots, chunk0, nchunks, ctx->d_X,
+	                                           ctx->x_pitch);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p) {
+	constexpr int smem = STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1) + 16 + 1024;
+	cudaError_t e = cudaFuncSetAttribute(k_pairdist_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if(e != cudaSuccess) return e;
+	const long long items = (long long) p.ntiles * p.kslices;
+	if(items <= 0) return cudaSuccess;
+	k_pairdist_umma<<<(unsigned) items, THREADS, smem, ctx->stream>>>(ctx->tmap_x, p);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const) {
+	if(p.ntiles <= 0) return cudaSuccess;
+	k_finalize_umma<<<p.ntiles, 256, 0, ctx->stream>>>(p.C_S, p.C_I, p.ldc, ctx->n, ctx->pair_mode, i_const, p.tiles,
+	                                                   p.ntiles, ep);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc) {
+	if(ctx->last_ntiles <= 0) return cudaSuccess;
+	int *C_S = ctx->d_C;
+	int *C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
+	k_gather_raw_dense<<<ctx->last_ntiles, 256, 0, ctx->stream>>>(C_S, C_I, ctx->n_pad, ctx->n, ctx->pair_mode, i_const,
+	                                                              ctx->d_tiles, ctx->last_ntiles, ctx->d_rank, d_mism,
+	                                                              d_ninc);
+	ctx->launches++;
+	return cudaGetLastError();
+}

@@ -74,17 +74,24 @@ int ccg_sync(ccg_ctx *ctx);
 
 /* This context computes only the lower-triangular tile blocks dealt to `rank`
  * of `world` (one process per GPU, no data-path collective).  Cells of other
- * ranks are left untouched in D / N.  Default rank 0 of 1. */
+ * ranks are left untouched in device outputs and read back as zero in host
+ * outputs.  Default rank 0 of 1. */
 int ccg_set_partition(ccg_ctx *ctx, int rank, int world);
 /* Pure host helpers (no device needed) describing that deal: the lower
- * triangle is cut into 64x64 sample tiles, tile (ti, tj<=ti) has index
- * t = ti(ti+1)/2 + tj and belongs to rank t % world.
+ * triangle is cut into macro tiles of ccg_tile_rows() x ccg_tile_cols()
+ * samples, enumerated row-major over (tm, tn <= tm/2); the tile with index id
+ * belongs to rank id % world.
  * ccg_partition_cells: number of (r,c) cells of an n-sample matrix owned by
- * `rank`.  ccg_partition_tiles: writes up to `cap` owned tiles to ti[] / tj[]
+ * `rank`.  ccg_partition_tiles: writes up to `cap` owned tiles to tm[] / tn[]
  * and returns how many the rank owns. */
-int ccg_tile_edge(void);
+int ccg_tile_rows(void);
+int ccg_tile_cols(void);
 long long ccg_partition_cells(int n, int rank, int world);
-long long ccg_partition_tiles(int n, int rank, int world, int *ti, int *tj, long long cap);
+long long ccg_partition_tiles(int n, int rank, int world, int *tm, int *tn, long long cap);
+
+/* Upper bound in bytes for the tensor-core kernel's int8 operand panel (the
+ * K axis is processed in slabs that fit); 0 = default (48 GiB or what is free). */
+int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes);
 
 /* Declare the sample set: n sample slots of len bases.  pair_mode != 0 is
  * `-f` bit 2 (per-pair inclusion, cmpairFsaThrd); 0 is the shared-mask mode

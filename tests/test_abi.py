@@ -58,11 +58,14 @@ def test_product_never_imports_the_oracle():
 def test_partition_helpers_are_host_only(built):
     from ccphylo_b200 import api
 
-    T = api.load().ccg_tile_edge()
-    for n in (1, 2, 63, 64, 65, 1000, 2816):
+    L = api.load()
+    BM, BN = L.ccg_tile_rows(), L.ccg_tile_cols()
+    assert (BM, BN) == (128, 256)
+    for n in (1, 2, 63, 64, 65, 129, 1000, 2816):
+        rows = (n + BM - 1) // BM
+        expect = [(tm, tn) for tm in range(rows) for tn in range(tm // 2 + 1)] if n >= 2 else []
         for world in (1, 2, 3, 8):
             cells = [api.partition_cells(n, r, world) for r in range(world)]
             assert sum(cells) == api.cells(n)
             tiles = [t for r in range(world) for t in api.partition_tiles(n, r, world)]
-            rows = (n + T - 1) // T
-            assert sorted(tiles) == [(i, j) for i in range(rows) for j in range(i + 1)]
+            assert sorted(tiles) == expect

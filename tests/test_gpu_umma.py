@@ -1,0 +1,161 @@
+"""GPU parity of the tensor-core path (tcgen05 int8 contraction, CCG_KERNEL_UMMA): same
+bit-exact bar as the LOP3+POPC path -- integer counts, every cell type, shared-mask mode,
+the rank partition, and multi-slab K processing -- against the CPU oracle and against the
+POPC kernel on the device."""
+import numpy as np
+import pytest
+
+import helpers
+import oracle
+from ccphylo_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def _set(n, length, seed, **kw):
+    kw.setdefault("snp", 0.02)
+    kw.setdefault("nrun", 0.05)
+    codes = synth.make_codes(n, length, seed=seed, **kw)
+    seqs, masks, inc = oracle.encode_samples(codes)
+    return codes, seqs, masks, inc
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = api.Context()
+    c.set_kernel(api.KERNEL_UMMA)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n,length", [(2, 1), (3, 31), (5, 128), (64, 129), (129, 1000), (257, 4099), (300, 20000 + 17),
+                                      (513, 3000)])
+def test_umma_raw_counts_bit_exact(ctx, n, length):
+    codes, seqs, masks, inc = _set(n, length, seed=n * 31 + length)
+    ctx.set_problem(n, length, pair=True)
+    ctx.put_samples_packed(seqs, masks)
+    D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
+    assert dn == n
+    assert "k_pairdist_umma" in ctx.last_kernel
+    mism, ninc = ctx.raw_counts(dn)
+    mo, no = oracle.raw_pair_matrix(seqs, masks, length)
+    assert np.array_equal(ninc, no)
+    assert np.array_equal(mism, mo)
+    assert np.array_equal(N, no.astype(np.float64))
+    assert np.array_equal(D, mo.astype(np.float64))
+
+
+@pytest.mark.parametrize("elem,scale", [(8, 1.0), (4, 1.0), (2, 10.0), (1, 0.01)])
+@pytest.mark.parametrize("norm", [0, 1000000])
+def test_umma_pair_epilogue_with_exclusions(ctx, elem, scale, norm):
+    n, length = 140, 3001
+    codes, seqs, masks, inc = _set(n, length, seed=elem + norm % 97)
+    codes[7, :] = 4
+    codes[130, : length - 100] = 4
+    seqs, masks, inc = oracle.encode_samples(codes)
+    min_len = int(0.5 * length)
+    include = (inc >= min_len).astype(np.uint8)
+    D, N, dn, _ = api.fsa_cmp_thread_out(seqs, include, masks, length, pair=True, norm=norm, min_length=min_len,
+                                         min_cov=0.5, elem_size=elem, byte_scale=scale, ctx=ctx)
+    Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=norm, min_length=min_len, min_cov=0.5,
+                                      elem_size=elem, byte_scale=scale)
+    assert dn == dno == n - 2
+    assert np.array_equal(_bits(D), _bits(Do))
+    assert np.array_equal(_bits(N), _bits(No))
+
+
+@pytest.mark.parametrize("norm", [0, 1000])
+def test_umma_global_mode(ctx, norm):
+    n, length = 150, 5003
+    codes, seqs, masks, inc = _set(n, length, seed=23, nrun=0.002)
+    include = np.ones(n, dtype=np.uint8)
+    include[[3, 129]] = 0
+    gmask = oracle.global_mask(codes, include)
+    D, _, dn, ginc = api.fsa_cmp_thread_out(seqs, include, gmask.reshape(1, -1), length, pair=False, norm=norm, ctx=ctx)
+    Do, dno, ginco = oracle.fsa_cmp_global(seqs, gmask, include, length, norm=norm)
+    assert dn == dno == n - 2 and ginc == ginco and ginc > length // 4
+    assert np.array_equal(_bits(D), _bits(Do))
+    assert float(D.max()) > 0
+
+
+POOL, CASES = helpers.golden_cases()
+SOME = [c for c in CASES if c["name"].startswith(("c1_", "c6_", "rand_L129", "rand_L777"))]
+
+
+@pytest.mark.parametrize("case", SOME, ids=[c["name"] for c in SOME])
+def test_umma_golden_text(ctx, case):
+    def backend(prep):
+        o = prep["opts"]
+        return api.fsa_cmp_thread_out(prep["seqs"], prep["include"], prep["masks"] if prep["pair"] else prep["gmask"],
+                                      prep["L"], pair=prep["pair"], norm=o["norm"], min_length=prep["min_len"],
+                                      min_cov=o["min_cov"], elem_size=o["elem"], byte_scale=o["scale"], ctx=ctx)
+
+    phy, num, err = helpers.replay(case, POOL, backend)
+    assert err == case["stderr"] and phy == case["phy"] and num == case["num"]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_umma_partition(ctx, world):
+    n, length = 600, 2048 + 5
+    codes, seqs, masks, inc = _set(n, length, seed=world)
+    mo, no = oracle.raw_pair_matrix(seqs, masks, length)
+    ctx.set_problem(n, length, pair=True)
+    ctx.put_samples_packed(seqs, masks)
+    total_D = np.zeros(api.cells(n))
+    total_N = np.zeros(api.cells(n))
+    try:
+        for r in range(world):
+            ctx.set_partition(r, world)
+            D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
+            assert np.count_nonzero(N) == api.partition_cells(n, r, world)
+            assert not np.any((total_N != 0) & (N != 0))
+            total_D += D
+            total_N += N
+    finally:
+        ctx.set_partition(0, 1)
+    assert np.array_equal(total_N, no.astype(np.float64)) and np.array_equal(total_D, mo.astype(np.float64))
+
+
+def test_umma_multi_slab_and_kslices(ctx):
+    """Tiny scratch budget forces several K slabs; long K forces several K slices per tile."""
+    n, length = 200, 300000 + 77
+    codes, seqs, masks, inc = _set(n, length, seed=4242, snp=0.001, nrun=0.01)
+    ctx.set_problem(n, length, pair=True)
+    ctx.put_samples_packed(seqs, masks)
+    mo, no = oracle.raw_pair_matrix(seqs, masks, length)
+    try:
+        ctx.set_scratch_limit(256 * 512 * 700)          # 700 chunks per slab -> 4 slabs
+        D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
+        assert "slabs=4" in ctx.last_kernel, ctx.last_kernel
+        mism, ninc = ctx.raw_counts(dn)
+        assert np.array_equal(mism, mo) and np.array_equal(ninc, no)
+    finally:
+        ctx.set_scratch_limit(0)
+    D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
+    assert "slabs=1" in ctx.last_kernel and "kslices=1 " not in ctx.last_kernel + " "
+    mism, ninc = ctx.raw_counts(dn)
+    assert np.array_equal(mism, mo) and np.array_equal(ninc, no)
+
+
+def test_umma_equals_popc_on_device(built):
+    import torch
+
+    n, length = 700, 400_000
+    seqs_t, masks_t = synth.make_packed_torch(n, length, seed=5, device="cuda")
+    torch.cuda.synchronize()
+    out = {}
+    for kind in (api.KERNEL_POPC, api.KERNEL_UMMA):
+        with api.Context() as c:
+            c.set_kernel(kind)
+            c.set_problem(n, length, pair=True)
+            c.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
+            D, N, dn = c.run_pair(norm=1000000)
+            out[kind] = (D, N, c.raw_counts(dn))
+    a, b = out[api.KERNEL_POPC], out[api.KERNEL_UMMA]
+    assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
+    assert np.array_equal(_bits(a[0]), _bits(b[0])) and np.array_equal(_bits(a[1]), _bits(b[1]))
+    assert a[2][0].max() > 0

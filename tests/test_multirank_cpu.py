@@ -24,11 +24,15 @@ def _worker(rank, world, port, n, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from ccphylo_b200 import api
 
-    T = api.load().ccg_tile_edge()
-    rows = (n + T - 1) // T
-    owner = torch.zeros(rows * (rows + 1) // 2, dtype=torch.int64)
-    for ti, tj in api.partition_tiles(n, rank, world):
-        owner[ti * (ti + 1) // 2 + tj] += 1
+    BM = api.load().ccg_tile_rows()
+    rows = (n + BM - 1) // BM
+    ids = {}
+    for tm in range(rows):
+        for tn in range(tm // 2 + 1):
+            ids[(tm, tn)] = len(ids)
+    owner = torch.zeros(len(ids), dtype=torch.int64)
+    for t in api.partition_tiles(n, rank, world):
+        owner[ids[t]] += 1
     cells = torch.tensor([api.partition_cells(n, rank, world)], dtype=torch.int64)
     dist.all_reduce(owner)
     dist.all_reduce(cells)
