@@ -25,7 +25,7 @@ EXPORTS = [
     "ccg_set_scratch_limit", "ccg_set_problem", "ccg_put_global_mask", "ccg_put_samples_packed",
     "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
-    "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms",
+    "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
 ]
 
 
@@ -90,6 +90,8 @@ def load():
     L.ccg_last_kernel.argtypes = [vp]
     L.ccg_last_compare_ms.restype = C.c_float
     L.ccg_last_compare_ms.argtypes = [vp]
+    L.ccg_last_phase_ms.restype = C.c_float
+    L.ccg_last_phase_ms.argtypes = [vp, i]
     _lib = L
     return L
 
@@ -256,6 +258,9 @@ class Context:
 
     def last_compare_ms(self):
         return self._L.ccg_last_compare_ms(self._h)
+
+    def last_phase_ms(self, phase):
+        return self._L.ccg_last_phase_ms(self._h, phase)
 
 
 def fsa_cmp_thread_out(seqs, include, includes, length, pair=True, norm=0, min_length=1, min_cov=0.5, proxi=0,

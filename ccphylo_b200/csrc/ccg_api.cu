@@ -77,6 +77,7 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 		free(ctx);
 		return CCG_ERR_CUDA;
 	}
+	for(int k = 0; k < 4; ++k) cudaEventCreate(&ctx->ev_phase[k]);
 	ctx->stream = ctx->own_stream;
 	*out = ctx;
 	return CCG_OK;
@@ -110,6 +111,7 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	cudaFree(ctx->d_out_N);
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
+	for(int k = 0; k < 4; ++k) cudaEventDestroy(ctx->ev_phase[k]);
 	cudaStreamDestroy(ctx->own_stream);
 	free(ctx);
 }
@@ -128,6 +130,13 @@ extern "C" int ccg_set_kernel(ccg_ctx *ctx, int kernel) {
 
 extern "C" int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes) {
 	if(!ctx) return CCG_ERR_ARG;
+	if(ctx->x_budget != bytes && ctx->d_X) {
+		/* re-size the operand panel on the next run */
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_X);
+		ctx->d_X = 0;
+		ctx->x_bytes = 0;
+	}
 	ctx->x_budget = bytes;
 	return CCG_OK;
 }
@@ -222,13 +231,15 @@ static int make_planes_tmap(ccg_ctx *ctx) {
 	return CCG_OK;
 }
 
-/* operand panel X[n_pad][x_chunks*512] int8, 128-byte swizzled boxes of 128 rows */
+/* operand panel X (see k_pairdist_umma.cu), 128-byte swizzled boxes of 128 rows */
 static int make_x_tmap(ccg_ctx *ctx) {
 	EncodeTiledFn enc;
 	int rc = get_encoder(ctx, &enc);
 	if(rc) return rc;
-	cuuint64_t gdim[2] = {(cuuint64_t) ctx->x_pitch, (cuuint64_t) ctx->n_pad};
-	cuuint64_t gstride[1] = {(cuuint64_t) ctx->x_pitch};
+	/* tile-blocked panel seen as a flat [n_pad * k-blocks][128 B] matrix: a 128-row box is one
+	 * contiguous 16 KiB (row block, k-block) tile */
+	cuuint64_t gdim[2] = {128, (cuuint64_t) (ctx->x_bytes / 128)};
+	cuuint64_t gstride[1] = {128};
 	cuuint32_t box[2] = {128, 128};
 	cuuint32_t estr[2] = {1, 1};
 	CUresult r = enc(&ctx->tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->d_X, gdim, gstride, box, estr,
@@ -518,38 +529,34 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	}
 	CK(ctx, cudaMemsetAsync(ctx->d_C, 0, c_bytes, ctx->stream));
 
-	/* operand panel: as many chunks per slab as the scratch budget allows */
-	size_t free_b = 0, total_b = 0;
-	CK(ctx, cudaMemGetInfo(&free_b, &total_b));
-	size_t budget = ctx->x_budget ? ctx->x_budget : (size_t) 48 << 30;
-	size_t avail = free_b + ctx->x_bytes;
-	if(budget > avail - avail / 8) budget = avail - avail / 8;
-	long long slab = (long long) (budget / ((size_t) ctx->n_pad * 512));
-	if(slab > ctx->chunks) slab = ctx->chunks;
-	if(slab < 1) {
-		set_err(ctx, "not enough device memory for one chunk of the operand panel (%d slots)", ctx->n_pad);
-		return CCG_ERR_NOMEM;
-	}
-	/* equal slabs */
-	const int nslabs = (int) ((ctx->chunks + slab - 1) / slab);
-	slab = (ctx->chunks + nslabs - 1) / nslabs;
-	size_t x_pitch = (size_t) slab * 512;
-	size_t x_bytes = x_pitch * ctx->n_pad;
-	if(ctx->x_bytes < x_bytes || ctx->x_chunks != (int) slab) {
-		CK(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(ctx->d_X);
-		ctx->d_X = 0;
-		ctx->x_bytes = 0;
+	/* operand panel: as many chunks per slab as the scratch budget allows; sized once per
+	 * problem geometry (cudaMemGetInfo / cudaMalloc are far too slow for the per-run path) */
+	if(!ctx->d_X) {
+		size_t free_b = 0, total_b = 0;
+		CK(ctx, cudaMemGetInfo(&free_b, &total_b));
+		size_t budget = ctx->x_budget ? ctx->x_budget : (size_t) 48 << 30;
+		if(budget > free_b - free_b / 8) budget = free_b - free_b / 8;
+		long long fit = (long long) (budget / ((size_t) ctx->n_pad * 512));
+		if(fit > ctx->chunks) fit = ctx->chunks;
+		if(fit < 1) {
+			set_err(ctx, "not enough device memory for one chunk of the operand panel (%d slots)", ctx->n_pad);
+			return CCG_ERR_NOMEM;
+		}
+		const int want_slabs = (int) ((ctx->chunks + fit - 1) / fit);
+		fit = (ctx->chunks + want_slabs - 1) / want_slabs;          /* equal slabs */
+		size_t x_bytes = (size_t) fit * 512 * ctx->n_pad;
 		if(cudaMalloc(&ctx->d_X, x_bytes) != cudaSuccess) {
+			ctx->d_X = 0;
 			set_err(ctx, "cudaMalloc of %zu bytes for the operand panel failed", x_bytes);
 			return CCG_ERR_NOMEM;
 		}
 		ctx->x_bytes = x_bytes;
-		ctx->x_chunks = (int) slab;
-		ctx->x_pitch = x_pitch;
+		ctx->x_chunks = (int) fit;
 		rc = make_x_tmap(ctx);
 		if(rc) return rc;
 	}
+	const long long slab = ctx->x_chunks;
+	const int nslabs = (int) ((ctx->chunks + slab - 1) / slab);
 
 	UmmaParams p;
 	memset(&p, 0, sizeof(p));
@@ -567,9 +574,14 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		p.kslices = choose_split((long long) ctx->sm_count, (long long) cnt, nch, 16, 512);
 		p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
 		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nch) --p.kslices;
+		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[0], ctx->stream));
 		CK(ctx, ccg_launch_expand(ctx, chunk0, nch));
+		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->stream));
+		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[2], ctx->stream));
 		CK(ctx, ccg_launch_umma(ctx, p));
+		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[3], ctx->stream));
 	}
+	ctx->phase_valid = 1;
 	/* shared-mask mode: every position of every chunk counts as included in the raw product */
 	const int i_const = ctx->chunks * CCG_CHUNK_BASES;
 	CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, i_const));
@@ -623,8 +635,11 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 		ep.nFactor = nFactor;
 	}
 	/* AUTO: the tensor-core kernel wins once there is enough work to fill the machine */
+	/* measured on B200 (profiles/): the tensor kernel runs the contraction ~5x faster than the
+	 * XU-pipe-bound POPC kernel but pays a fixed operand-expansion pass; small problems stay on POPC */
 	int kind = ctx->kernel_choice;
-	if(kind == CCG_KERNEL_AUTO) kind = CCG_KERNEL_POPC;
+	if(kind == CCG_KERNEL_AUTO)
+		kind = (Dn >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
 	return kind == CCG_KERNEL_UMMA ? run_umma(ctx, ep) : run_popc(ctx, ep);
 }
 
@@ -774,6 +789,14 @@ extern "C" void ccg_host_free(void *p) {
 
 extern "C" long long ccg_launch_count(const ccg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" const char *ccg_last_kernel(const ccg_ctx *ctx) { return ctx ? ctx->last_kernel : ""; }
+
+extern "C" float ccg_last_phase_ms(ccg_ctx *ctx, int phase) {
+	float ms = -1.0f;
+	if(!ctx || !ctx->phase_valid || phase < 0 || phase > 1 || ctx->last_kernel_kind != CCG_KERNEL_UMMA) return ms;
+	if(cudaEventSynchronize(ctx->ev_phase[2 * phase + 1]) != cudaSuccess) return -1.0f;
+	if(cudaEventElapsedTime(&ms, ctx->ev_phase[2 * phase], ctx->ev_phase[2 * phase + 1]) != cudaSuccess) return -1.0f;
+	return ms;
+}
 
 extern "C" float ccg_last_compare_ms(ccg_ctx *ctx) {
 	float ms = -1.0f;

@@ -118,6 +118,8 @@ struct ccg_ctx {
 
 	cudaEvent_t ev0, ev1;
 	int ev_valid;
+	cudaEvent_t ev_phase[4];   /* tensor-core path, first slab: expand begin/end, GEMM begin/end */
+	int phase_valid;
 	long long launches;
 	char last_kernel[96];
 	char err[512];

@@ -117,7 +117,7 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x0020
  * writes the 512 contiguous bytes X[slot][chunk][0..3][0..127]. */
 __global__ void __launch_bounds__(256)
 k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slots, int chunk0, int nchunks,
-         int8_t *__restrict__ X, size_t row_pitch) {
+         int8_t *__restrict__ X, size_t nkb) {
 	const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if(warp >= (long long) slots * nchunks) return;
@@ -144,7 +144,10 @@ k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slots,
 		const uint32_t minus = spread4(((neg & m) >> (4 * g)) & 0xFu);        /* 0x01 where the value is -1 */
 		out[g] = ones | (minus * 0xFEu);                                       /* +1 = 0x01, -1 = 0xFF, 0 */
 	}
-	uint4 *dst = reinterpret_cast<uint4 *>(X + (size_t) slot * row_pitch + (size_t) cl * 512 + ch * 128 + seg * 16);
+	/* tile-blocked panel: X[slot/128][k-block][slot%128][128 B], k-block = chunk*4 + channel, so the
+	 * 128 rows x 128 B box a TMA load fetches is 16 KiB contiguous */
+	const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) cl * 4 + ch) * 128 + (slot & 127);
+	uint4 *dst = reinterpret_cast<uint4 *>(X + tile_row * 128 + seg * 16);
 	*dst = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
@@ -198,11 +201,13 @@ k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 				if(kb >= STAGES) mbar_wait(bar_empty + 8 * s, ((kb / STAGES) - 1) & 1);
 				const uint32_t dst = base + s * STAGE_BYTES;
 				const uint32_t bar = bar_full + 8 * s;
-				const int kcoord = (c_begin * 4 + kb) * BK;
+				/* row coordinate of the 128-row box of row block rb, k-block kabs in the blocked panel */
+				const int kabs = c_begin * 4 + kb;
+				const int nkb_slab = p.slab_chunks * 4;
 				mbar_expect_tx(bar, STAGE_BYTES);
-				tma_load_2d(dst, &tmap, bar, kcoord, tm * BM);
-				tma_load_2d(dst + A_BYTES, &tmap, bar, kcoord, tn * BN);
-				tma_load_2d(dst + A_BYTES + 128 * BK, &tmap, bar, kcoord, tn * BN + 128);
+				tma_load_2d(dst, &tmap, bar, 0, (tm * nkb_slab + kabs) * 128);
+				tma_load_2d(dst + A_BYTES, &tmap, bar, 0, ((2 * tn) * nkb_slab + kabs) * 128);
+				tma_load_2d(dst + A_BYTES + 128 * BK, &tmap, bar, 0, ((2 * tn + 1) * nkb_slab + kabs) * 128);
 			}
 		}
 	} else if(warp == 1) {
@@ -312,7 +317,7 @@ cudaError_t ccg_launch_expand(ccg_ctx *ctx, int chunk0, int nchunks) {
 	if(warps <= 0) return cudaSuccess;
 	const unsigned blocks = (unsigned) ((warps * 32 + 255) / 256);
 	k_expand<<<blocks, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, slots, chunk0, nchunks, ctx->d_X,
-	                                           ctx->x_pitch);
+	                                           (size_t) nchunks * 4);
 	ctx->launches++;
 	return cudaGetLastError();
 }

@@ -183,6 +183,9 @@ const char *ccg_last_kernel(const ccg_ctx *ctx);
 /* device time (ms, CUDA events on the context's stream) of the compare kernel
  * of the last run; < 0 if unavailable */
 float ccg_last_compare_ms(ccg_ctx *ctx);
+/* tensor-core path only: device time (ms) of the first K slab's operand
+ * expansion (phase 0) or int8 GEMM launch (phase 1); < 0 if unavailable */
+float ccg_last_phase_ms(ccg_ctx *ctx, int phase);
 
 #ifdef __cplusplus
 }
