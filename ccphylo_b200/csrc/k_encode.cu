@@ -6,7 +6,8 @@
  * getIncPos(seq, seq, 0) (fsacmp.c:181-238) and getNpos (fsacmp.c:487-503).
  *
  * Roofline: HBM streaming.  Algorithmic bytes per 32-base word and sample:
- * repack reads 8 B (u64 codes) + 4 B (u32 mask) and writes 12 B of planes;
+ * repack reads 8 B (u64 codes) + 4 B (u32 mask) and writes 12 B of planes
+ * (coalesced both ways through a shared-memory transpose);
  * encode_codes reads 32 B of codes and writes 12 B.
  */
 #include "ccg_internal.h"
@@ -31,49 +32,58 @@ __device__ __forceinline__ void store_chunk(uint32_t *planes, int n_pad, int npl
 	if(nplanes == 3) base[(row + 2) * n_pad + slot] = make_uint4(m[0], m[1], m[2], m[3]);
 }
 
-/* Reference packed format -> planes.  One thread per (chunk, sample), sample
- * fastest so the 16-byte plane stores of a warp are contiguous. */
+/* Reference packed format -> planes, plus getNpos of every mask row (fsacmp.c:487).
+ * A block transposes a tile of 32 samples x 16 chunks through shared memory: the reads
+ * walk each sample row contiguously (half-warp = one sample, lane = chunk: 32 B of codes +
+ * 16 B of mask per lane), the writes walk each (chunk, plane) row contiguously (lane =
+ * sample: 16 B per lane). */
 __global__ void __launch_bounds__(256)
 k_repack_packed(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks, int words, int first, int count,
                 const uint64_t *__restrict__ seqs, const uint32_t *__restrict__ masks,
-                const uint32_t *__restrict__ gmask, long wstride) {
-	long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	long long total = (long long) chunks * count;
-	if(gid >= total) return;
-	int s = (int) (gid % count);
-	long long c = gid / count;
-	uint32_t h[4], l[4], m[4];
+                const uint32_t *__restrict__ gmask, long wstride, unsigned *__restrict__ inc) {
+	__shared__ uint4 tile[3][16][33];                  /* [plane][chunk][sample], padded against bank conflicts */
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int cl = lane & 15;
+	const long long c0 = (long long) blockIdx.x * 16;
+	const int s0 = blockIdx.y * 32;
+
+	for(int si = warp * 2 + (lane >> 4); si < 32; si += 16) {
+		const int s = s0 + si;
+		const long long c = c0 + cl;
+		uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0};
+		unsigned known = 0;
+		if(s < count && c < chunks) {
+			const uint64_t *srow = seqs + (size_t) s * wstride;
+			const uint32_t *mrow = masks ? masks + (size_t) s * wstride : gmask;
 #pragma unroll
-	for(int q = 0; q < 4; ++q) {
-		long long w = c * 4 + q;
-		if(w < words) {
-			uint64_t x = seqs[(size_t) s * wstride + w];
-			uint32_t mk = masks ? masks[(size_t) s * wstride + w] : gmask[w];
-			m[q] = mk;
-			h[q] = compress_even(x >> 1) & mk;
-			l[q] = compress_even(x) & mk;
-		} else {
-			h[q] = l[q] = m[q] = 0;
+			for(int q = 0; q < 4; ++q) {
+				const long long w = c * 4 + q;
+				if(w < words) {
+					const uint64_t x = __ldg(srow + w);
+					const uint32_t mk = __ldg(mrow + w);
+					m[q] = mk;
+					h[q] = compress_even(x >> 1) & mk;
+					l[q] = compress_even(x) & mk;
+					known += __popc(mk);
+				}
+			}
+		}
+		tile[0][cl][si] = make_uint4(h[0], h[1], h[2], h[3]);
+		tile[1][cl][si] = make_uint4(l[0], l[1], l[2], l[3]);
+		if(nplanes == 3) tile[2][cl][si] = make_uint4(m[0], m[1], m[2], m[3]);
+		if(masks) {
+#pragma unroll
+			for(int o = 8; o; o >>= 1) known += __shfl_xor_sync(0xffffffffu, known, o);   /* within the half-warp */
+			if(cl == 0 && s < count && known) atomicAdd(inc + first + s, known);
 		}
 	}
-	store_chunk(planes, n_pad, nplanes, c, first + s, h, l, m);
-}
-
-/* getNpos of each uploaded mask row (fsacmp.c:487): one block per sample. */
-__global__ void __launch_bounds__(256)
-k_mask_count(const uint32_t *__restrict__ masks, long wstride, int words, int first, unsigned *__restrict__ inc) {
-	__shared__ unsigned warp_sums[8];
-	const uint32_t *row = masks + (size_t) blockIdx.x * wstride;
-	unsigned acc = 0;
-	for(int w = threadIdx.x; w < words; w += blockDim.x) acc += __popc(row[w]);
-#pragma unroll
-	for(int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-	if((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
 	__syncthreads();
-	if(threadIdx.x == 0) {
-		unsigned t = 0;
-		for(int i = 0; i < (int) (blockDim.x >> 5); ++i) t += warp_sums[i];
-		inc[first + blockIdx.x] = t;
+	uint4 *out = reinterpret_cast<uint4 *>(planes);
+	for(int r = warp; r < 16 * nplanes; r += 8) {
+		const int ci = r / nplanes, pl = r % nplanes;
+		const long long c = c0 + ci;
+		const int s = s0 + lane;
+		if(c < chunks && s < count) out[((size_t) c * nplanes + pl) * n_pad + first + s] = tile[pl][ci][lane];
 	}
 }
 
@@ -146,16 +156,15 @@ k_gather_raw(const uint32_t *__restrict__ acc, int ntiles, const int2 *__restric
 
 cudaError_t ccg_launch_repack(ccg_ctx *ctx, int first, int count, const uint64_t *d_seqs, const uint32_t *d_masks,
                               long wstride) {
-	long long total = (long long) ctx->chunks * count;
-	if(total == 0) return cudaSuccess;
-	unsigned blocks = (unsigned) ((total + 255) / 256);
-	k_repack_packed<<<blocks, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks, ctx->words,
-	                                                  first, count, d_seqs, d_masks, ctx->d_gmask, wstride);
-	ctx->launches++;
+	if(count <= 0) return cudaSuccess;
 	if(d_masks) {
-		k_mask_count<<<count, 256, 0, ctx->stream>>>(d_masks, wstride, ctx->words, first, ctx->d_inc);
-		ctx->launches++;
+		cudaError_t e = cudaMemsetAsync(ctx->d_inc + first, 0, (size_t) count * sizeof(unsigned), ctx->stream);
+		if(e != cudaSuccess) return e;
 	}
+	dim3 grid((unsigned) ((ctx->chunks + 15) / 16), (unsigned) ((count + 31) / 32));
+	k_repack_packed<<<grid, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks, ctx->words, first,
+	                                                count, d_seqs, d_masks, ctx->d_gmask, wstride, ctx->d_inc);
+	ctx->launches++;
 	return cudaGetLastError();
 }
 

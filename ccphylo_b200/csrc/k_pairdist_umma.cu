@@ -113,42 +113,49 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 /* 4 plane bits (bit j <-> base j of the group) -> 4 bytes of 0/1 */
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
-/* One warp per (slot, chunk): lane = channel*8 + segment of 16 bases; the warp
- * writes the 512 contiguous bytes X[slot][chunk][0..3][0..127]. */
+/* One thread per (slot, chunk, segment of 16 bases): it produces the 16 bytes of all four
+ * channels, so the known-mask spread and the plane loads are shared.  A warp covers 4
+ * consecutive slots x 8 segments and every store instruction writes 4 x 128 contiguous bytes.
+ * The code planes are already ANDed with the mask (k_encode), so h, l and h^l are zero
+ * wherever the base is unknown. */
 __global__ void __launch_bounds__(256)
 k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slots, int chunk0, int nchunks,
          int8_t *__restrict__ X, size_t nkb) {
-	const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int lane = threadIdx.x & 31;
-	if(warp >= (long long) slots * nchunks) return;
-	const int slot = (int) (warp % slots);
-	const int cl = (int) (warp / slots);           /* chunk within the slab */
-	const int ch = lane >> 3, seg = lane & 7;
+	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const long long item = gid >> 3;
+	if(item >= (long long) slots * nchunks) return;
+	const int seg = (int) (gid & 7);
+	const int slot = (int) (item % slots);
+	const int cl = (int) (item / slots);           /* chunk within the slab */
 	const int q = seg >> 1, half = seg & 1;
 	const size_t prow = (size_t) (chunk0 + cl) * nplanes;
-	const uint32_t *ph = planes + ((prow + 0) * n_pad + slot) * 4;
-	const uint32_t *pl = planes + ((prow + 1) * n_pad + slot) * 4;
-	uint32_t h = ph[q], l = pl[q], m;
-	if(nplanes == 3) m = planes[((prow + 2) * n_pad + slot) * 4 + q];
-	else m = 0xFFFFFFFFu;                          /* shared-mask mode: planes are pre-masked, see below */
-	/* base k of the word <-> bit 31-k; reverse so base k <-> bit k, then take this lane's 16 bases */
-	h = (__brev(h) >> (16 * half)) & 0xFFFFu;
-	l = (__brev(l) >> (16 * half)) & 0xFFFFu;
-	m = (__brev(m) >> (16 * half)) & 0xFFFFu;
-	/* sign bit of the channel: 0 -> h, 1 -> l, 2 -> h^l; channel 3 is the mask itself */
-	const uint32_t neg = ch == 0 ? h : ch == 1 ? l : ch == 2 ? (h ^ l) : 0u;
-	uint32_t out[4];
+	uint32_t h = planes[((prow + 0) * n_pad + slot) * 4 + q];
+	uint32_t l = planes[((prow + 1) * n_pad + slot) * 4 + q];
+	uint32_t m = nplanes == 3 ? planes[((prow + 2) * n_pad + slot) * 4 + q] : 0xFFFFFFFFu;
+	/* base k of the word <-> bit 31-k; reverse so base k <-> bit k, then take this thread's 16 bases */
+	h = __brev(h) >> (16 * half);
+	l = __brev(l) >> (16 * half);
+	m = __brev(m) >> (16 * half);
+	uint32_t c0[4], c1[4], c2[4], c3[4];
 #pragma unroll
 	for(int g = 0; g < 4; ++g) {
-		const uint32_t ones = spread4((m >> (4 * g)) & 0xFu);                 /* 0x01 where known */
-		const uint32_t minus = spread4(((neg & m) >> (4 * g)) & 0xFu);        /* 0x01 where the value is -1 */
-		out[g] = ones | (minus * 0xFEu);                                       /* +1 = 0x01, -1 = 0xFF, 0 */
+		const uint32_t ones = spread4((m >> (4 * g)) & 0xFu);     /* 0x01 where known */
+		const uint32_t sh = spread4((h >> (4 * g)) & 0xFu);       /* 0x01 where channel 0 is -1 */
+		const uint32_t sl = spread4((l >> (4 * g)) & 0xFu);       /* 0x01 where channel 1 is -1 */
+		const uint32_t sx = sh ^ sl;                              /* 0x01 where channel 2 is -1 */
+		c0[g] = sh * 0xFEu + ones;                                /* +1 = 0x01, -1 = 0xFF, unknown = 0 */
+		c1[g] = sl * 0xFEu + ones;
+		c2[g] = sx * 0xFEu + ones;
+		c3[g] = ones;
 	}
 	/* tile-blocked panel: X[slot/128][k-block][slot%128][128 B], k-block = chunk*4 + channel, so the
 	 * 128 rows x 128 B box a TMA load fetches is 16 KiB contiguous */
-	const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) cl * 4 + ch) * 128 + (slot & 127);
+	const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) cl * 4) * 128 + (slot & 127);
 	uint4 *dst = reinterpret_cast<uint4 *>(X + tile_row * 128 + seg * 16);
-	*dst = make_uint4(out[0], out[1], out[2], out[3]);
+	dst[0 * 1024] = make_uint4(c0[0], c0[1], c0[2], c0[3]);       /* channel rows are 128 x 128 B = 1024 uint4 apart */
+	dst[1 * 1024] = make_uint4(c1[0], c1[1], c1[2], c1[3]);
+	dst[2 * 1024] = make_uint4(c2[0], c2[1], c2[2], c2[3]);
+	dst[3 * 1024] = make_uint4(c3[0], c3[1], c3[2], c3[3]);
 }
 
 /* ------------------------------------------------------------------ */
@@ -313,9 +320,9 @@ k_gather_raw_dense(const int *__restrict__ C_S, const int *__restrict__ C_I, int
 
 cudaError_t ccg_launch_expand(ccg_ctx *ctx, int chunk0, int nchunks) {
 	const int slots = ctx->n_pad;
-	const long long warps = (long long) slots * nchunks;
-	if(warps <= 0) return cudaSuccess;
-	const unsigned blocks = (unsigned) ((warps * 32 + 255) / 256);
+	const long long items = (long long) slots * nchunks;
+	if(items <= 0) return cudaSuccess;
+	const unsigned blocks = (unsigned) ((items * 8 + 255) / 256);
 	k_expand<<<blocks, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, slots, chunk0, nchunks, ctx->d_X,
 	                                           (size_t) nchunks * 4);
 	ctx->launches++;
