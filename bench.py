@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples", type=int, default=BASE_SAMPLES, help="samples at N=1 (grows with sqrt(N))")
     ap.add_argument("--length", type=int, default=LENGTH)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "umma"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "umma", "fused"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -234,8 +234,9 @@ def main():
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
-    use_umma = args.kernel in ("auto", "umma")          # AUTO resolves to the tensor kernel at bench sizes
-    ctx.set_kernel(api.KERNEL_UMMA if use_umma else api.KERNEL_POPC)
+    use_umma = args.kernel in ("auto", "umma", "fused")   # AUTO resolves to a tensor kernel at bench sizes
+    ctx.set_kernel({"auto": api.KERNEL_AUTO, "popc": api.KERNEL_POPC, "umma": api.KERNEL_UMMA,
+                    "fused": api.KERNEL_FUSED}[args.kernel])
     ctx.set_partition(rank, world)
     ctx.set_problem(n, length, pair=True)
     ncell = api.cells(n)
@@ -293,7 +294,8 @@ def main():
         torch.cuda.synchronize()
         compare_ms.append(ctx.last_compare_ms())
         if use_umma:
-            expand_ms.append(ctx.last_phase_ms(0))
+            if ctx.last_phase_ms(0) >= 0:
+                expand_ms.append(ctx.last_phase_ms(0))
             kern_ms.append(ctx.last_phase_ms(1))
         else:
             kern_ms.append(ctx.last_compare_ms())

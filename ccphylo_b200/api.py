@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libccphylo_gpu.so")
 
 ELEM_DTYPE = {8: np.float64, 4: np.float32, 2: np.uint16, 1: np.uint8}
-KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA = 0, 1, 2
+KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_FUSED = 0, 1, 2, 3
 
 EXPORTS = [
     "ccg_strerror", "ccg_last_error", "ccg_init", "ccg_destroy", "ccg_set_stream", "ccg_set_kernel", "ccg_sync",

@@ -123,7 +123,7 @@ extern "C" int ccg_set_stream(ccg_ctx *ctx, void *cuda_stream) {
 }
 
 extern "C" int ccg_set_kernel(ccg_ctx *ctx, int kernel) {
-	if(!ctx || kernel < CCG_KERNEL_AUTO || kernel > CCG_KERNEL_UMMA) return CCG_ERR_ARG;
+	if(!ctx || kernel < CCG_KERNEL_AUTO || kernel > CCG_KERNEL_FUSED) return CCG_ERR_ARG;
 	ctx->kernel_choice = kernel;
 	return CCG_OK;
 }
@@ -225,6 +225,14 @@ static int make_planes_tmap(ccg_ctx *ctx) {
 	                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if(r != CUDA_SUCCESS) {
 		set_err(ctx, "cuTensorMapEncodeTiled(planes) failed with CUresult %d", (int) r);
+		return CCG_ERR_CUDA;
+	}
+	cuuint32_t box_pl[4] = {CCG_CHUNK_WORDS, 128, (cuuint32_t) ctx->nplanes, 1};
+	r = enc(&ctx->tmap_pl, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, ctx->d_planes, gdim, gstride, box_pl, estr,
+	        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(r != CUDA_SUCCESS) {
+		set_err(ctx, "cuTensorMapEncodeTiled(planes, fused box) failed with CUresult %d", (int) r);
 		return CCG_ERR_CUDA;
 	}
 	ctx->tmap_valid = 1;
@@ -592,6 +600,63 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	return CCG_OK;
 }
 
+/* tensor path with the operand expansion fused into the GEMM: no panel, no slabs */
+static int run_fused(ccg_ctx *ctx, const EpilogueParams &ep) {
+	const int n = ctx->n;
+	size_t cap = 0;
+	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int, int) { ++cap; });
+	int2 *host = (int2 *) malloc((cap ? cap : 1) * sizeof(int2));
+	if(!host) return CCG_ERR_NOMEM;
+	size_t cnt = 0;
+	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int tm, int tn) {
+		host[cnt].x = tm;
+		host[cnt].y = tn;
+		++cnt;
+	});
+	ctx->last_ntiles = (int) cnt;
+	ctx->last_kernel_kind = CCG_KERNEL_FUSED;
+	if(cnt == 0) { free(host); return CCG_OK; }
+	int rc = ensure_tiles(ctx, host, cnt);
+	free(host);
+	if(rc) return rc;
+
+	size_t c_bytes = (size_t) 2 * ctx->n_pad * ctx->n_pad * sizeof(int);
+	if(ctx->c_bytes < c_bytes) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_C);
+		ctx->d_C = 0;
+		ctx->c_bytes = 0;
+		if(cudaMalloc(&ctx->d_C, c_bytes) != cudaSuccess) {
+			set_err(ctx, "cudaMalloc of %zu bytes for the int32 accumulators failed", c_bytes);
+			return CCG_ERR_NOMEM;
+		}
+		ctx->c_bytes = c_bytes;
+	}
+	CK(ctx, cudaMemsetAsync(ctx->d_C, 0, c_bytes, ctx->stream));
+
+	UmmaParams p;
+	memset(&p, 0, sizeof(p));
+	p.ntiles = (int) cnt;
+	p.tiles = ctx->d_tiles;
+	p.C_S = ctx->d_C;
+	p.C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
+	p.ldc = ctx->n_pad;
+	p.slab_chunks = ctx->chunks;
+	p.kslices = choose_split((long long) ctx->sm_count, (long long) cnt, ctx->chunks, 16, 1024);
+	p.chunks_per_slice = (ctx->chunks + p.kslices - 1) / p.kslices;
+	while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= ctx->chunks) --p.kslices;
+	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev_phase[2], ctx->stream));
+	CK(ctx, ccg_launch_fused(ctx, p));
+	CK(ctx, cudaEventRecord(ctx->ev_phase[3], ctx->stream));
+	ctx->phase_valid = 1;
+	CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, ctx->chunks * CCG_CHUNK_BASES));
+	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	ctx->ev_valid = 1;
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_fused tiles=%d kslices=%d", p.ntiles, p.kslices);
+	return CCG_OK;
+}
+
 static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
                       double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn_out) {
 	if(!ctx || !ctx->d_planes) return CCG_ERR_ARG;
@@ -640,6 +705,7 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	int kind = ctx->kernel_choice;
 	if(kind == CCG_KERNEL_AUTO)
 		kind = (Dn >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
+	if(kind == CCG_KERNEL_FUSED) return run_fused(ctx, ep);
 	return kind == CCG_KERNEL_UMMA ? run_umma(ctx, ep) : run_popc(ctx, ep);
 }
 
@@ -718,7 +784,7 @@ extern "C" int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc) 
 	cudaMemsetAsync(d_m, 0, cells * 4, ctx->stream);
 	cudaMemsetAsync(d_n, 0, cells * 4, ctx->stream);
 	cudaError_t e;
-	if(ctx->last_kernel_kind == CCG_KERNEL_UMMA) e = ccg_launch_gather_raw_dense(ctx, ctx->chunks * CCG_CHUNK_BASES, d_m, d_n);
+	if(ctx->last_kernel_kind == CCG_KERNEL_UMMA || ctx->last_kernel_kind == CCG_KERNEL_FUSED) e = ccg_launch_gather_raw_dense(ctx, ctx->chunks * CCG_CHUNK_BASES, d_m, d_n);
 	else e = ccg_launch_gather_raw(ctx, d_m, d_n);
 	if(e == cudaSuccess && mism) e = cudaMemcpyAsync(mism, d_m, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
 	if(e == cudaSuccess && ninc) e = cudaMemcpyAsync(ninc, d_n, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -792,7 +858,8 @@ extern "C" const char *ccg_last_kernel(const ccg_ctx *ctx) { return ctx ? ctx->l
 
 extern "C" float ccg_last_phase_ms(ccg_ctx *ctx, int phase) {
 	float ms = -1.0f;
-	if(!ctx || !ctx->phase_valid || phase < 0 || phase > 1 || ctx->last_kernel_kind != CCG_KERNEL_UMMA) return ms;
+	if(!ctx || !ctx->phase_valid || phase < 0 || phase > 1) return ms;
+	if(ctx->last_kernel_kind == CCG_KERNEL_POPC || (ctx->last_kernel_kind == CCG_KERNEL_FUSED && phase == 0)) return ms;
 	if(cudaEventSynchronize(ctx->ev_phase[2 * phase + 1]) != cudaSuccess) return -1.0f;
 	if(cudaEventElapsedTime(&ms, ctx->ev_phase[2 * phase], ctx->ev_phase[2 * phase + 1]) != cudaSuccess) return -1.0f;
 	return ms;

@@ -112,7 +112,8 @@ struct ccg_ctx {
 	size_t c_bytes;
 	size_t x_budget;           /* max bytes for d_X (0 = default) */
 
-	CUtensorMap tmap;          /* planes as a 4-D tensor */
+	CUtensorMap tmap;          /* planes as a 4-D tensor, box [4 chunks][planes][64 slots][4] (POPC kernel) */
+	CUtensorMap tmap_pl;       /* same tensor, box [1 chunk][planes][128 slots][4] (fused tensor kernel) */
 	CUtensorMap tmap_x;        /* operand panel as a 2-D tensor */
 	int tmap_valid;
 
@@ -143,5 +144,8 @@ cudaError_t ccg_launch_expand(ccg_ctx *ctx, int chunk0, int nchunks);
 cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
 cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);
 cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc);
+
+/* k_pairdist_fused.cu */
+cudaError_t ccg_launch_fused(ccg_ctx *ctx, const UmmaParams &p);
 
 #endif

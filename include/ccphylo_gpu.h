@@ -53,7 +53,8 @@ enum {
 enum {
 	CCG_KERNEL_AUTO = 0,
 	CCG_KERNEL_POPC = 1,     /* bit-sliced LOP3+POPC path on the INT pipe */
-	CCG_KERNEL_UMMA = 2      /* int8 contraction on tcgen05 tensor cores */
+	CCG_KERNEL_UMMA = 2,     /* int8 contraction on tcgen05 tensor cores, operands expanded to an HBM panel */
+	CCG_KERNEL_FUSED = 3     /* same contraction, operands expanded from the bit planes inside the CTA */
 };
 
 const char *ccg_strerror(int code);

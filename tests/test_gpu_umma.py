@@ -24,10 +24,14 @@ def _set(n, length, seed, **kw):
     return codes, seqs, masks, inc
 
 
-@pytest.fixture(scope="module")
-def ctx(built):
+KNAME = {api.KERNEL_UMMA: "k_pairdist_umma", api.KERNEL_FUSED: "k_pairdist_fused"}
+
+
+@pytest.fixture(scope="module", params=[api.KERNEL_UMMA, api.KERNEL_FUSED], ids=["umma", "fused"])
+def ctx(built, request):
     c = api.Context()
-    c.set_kernel(api.KERNEL_UMMA)
+    c.set_kernel(request.param)
+    c.kind = request.param
     yield c
     c.close()
 
@@ -40,7 +44,7 @@ def test_umma_raw_counts_bit_exact(ctx, n, length):
     ctx.put_samples_packed(seqs, masks)
     D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
     assert dn == n
-    assert "k_pairdist_umma" in ctx.last_kernel
+    assert KNAME[ctx.kind] in ctx.last_kernel
     mism, ninc = ctx.raw_counts(dn)
     mo, no = oracle.raw_pair_matrix(seqs, masks, length)
     assert np.array_equal(ninc, no)
@@ -127,16 +131,17 @@ def test_umma_multi_slab_and_kslices(ctx):
     ctx.set_problem(n, length, pair=True)
     ctx.put_samples_packed(seqs, masks)
     mo, no = oracle.raw_pair_matrix(seqs, masks, length)
-    try:
-        ctx.set_scratch_limit(256 * 512 * 700)          # 700 chunks per slab -> 4 slabs
-        D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
-        assert "slabs=4" in ctx.last_kernel, ctx.last_kernel
-        mism, ninc = ctx.raw_counts(dn)
-        assert np.array_equal(mism, mo) and np.array_equal(ninc, no)
-    finally:
-        ctx.set_scratch_limit(0)
+    if ctx.kind == api.KERNEL_UMMA:
+        try:
+            ctx.set_scratch_limit(256 * 512 * 700)          # 700 chunks per slab -> 4 slabs
+            D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
+            assert "slabs=4" in ctx.last_kernel, ctx.last_kernel
+            mism, ninc = ctx.raw_counts(dn)
+            assert np.array_equal(mism, mo) and np.array_equal(ninc, no)
+        finally:
+            ctx.set_scratch_limit(0)
     D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
-    assert "slabs=1" in ctx.last_kernel and "kslices=1 " not in ctx.last_kernel + " "
+    assert "kslices=1 " not in ctx.last_kernel + " "
     mism, ninc = ctx.raw_counts(dn)
     assert np.array_equal(mism, mo) and np.array_equal(ninc, no)
 
@@ -148,14 +153,16 @@ def test_umma_equals_popc_on_device(built):
     seqs_t, masks_t = synth.make_packed_torch(n, length, seed=5, device="cuda")
     torch.cuda.synchronize()
     out = {}
-    for kind in (api.KERNEL_POPC, api.KERNEL_UMMA):
+    for kind in (api.KERNEL_POPC, api.KERNEL_UMMA, api.KERNEL_FUSED):
         with api.Context() as c:
             c.set_kernel(kind)
             c.set_problem(n, length, pair=True)
             c.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
             D, N, dn = c.run_pair(norm=1000000)
             out[kind] = (D, N, c.raw_counts(dn))
-    a, b = out[api.KERNEL_POPC], out[api.KERNEL_UMMA]
-    assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
-    assert np.array_equal(_bits(a[0]), _bits(b[0])) and np.array_equal(_bits(a[1]), _bits(b[1]))
+    a = out[api.KERNEL_POPC]
+    for kind in (api.KERNEL_UMMA, api.KERNEL_FUSED):
+        b = out[kind]
+        assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
+        assert np.array_equal(_bits(a[0]), _bits(b[0])) and np.array_equal(_bits(a[1]), _bits(b[1]))
     assert a[2][0].max() > 0
