@@ -13,9 +13,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "ccg_internal.h"
 
 static char g_init_err[512] = "";
+static void update_need(ccg_ctx *ctx);
 
 static void set_err(ccg_ctx *ctx, const char *fmt, ...) {
 	va_list ap;
@@ -78,6 +82,12 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 		return CCG_ERR_CUDA;
 	}
 	for(int k = 0; k < 4; ++k) cudaEventCreate(&ctx->ev_phase[k]);
+	cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+	for(int k = 0; k < 2; ++k) {
+		cudaEventCreateWithFlags(&ctx->ev_x[k], cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&ctx->ev_g[k], cudaEventDisableTiming);
+	}
 	ctx->stream = ctx->own_stream;
 	*out = ctx;
 	return CCG_OK;
@@ -91,6 +101,8 @@ static void free_problem(ccg_ctx *ctx) {
 	cudaFree(ctx->d_X); ctx->d_X = 0; ctx->x_bytes = 0;
 	cudaFree(ctx->d_C); ctx->d_C = 0; ctx->c_bytes = 0;
 	free(ctx->present); ctx->present = 0;
+	free(ctx->need); ctx->need = 0;
+	free(ctx->have); ctx->have = 0;
 	free(ctx->h_rank); ctx->h_rank = 0;
 	ctx->tmap_valid = 0;
 	ctx->n = ctx->len = 0;
@@ -112,6 +124,10 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	for(int k = 0; k < 4; ++k) cudaEventDestroy(ctx->ev_phase[k]);
+	cudaEventDestroy(ctx->ev_fork);
+	for(int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_x[k]); cudaEventDestroy(ctx->ev_g[k]); }
+	cudaStreamSynchronize(ctx->aux_stream);
+	cudaStreamDestroy(ctx->aux_stream);
 	cudaStreamDestroy(ctx->own_stream);
 	free(ctx);
 }
@@ -136,6 +152,7 @@ extern "C" int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes) {
 		cudaFree(ctx->d_X);
 		ctx->d_X = 0;
 		ctx->x_bytes = 0;
+		ctx->x_chunks = 0;
 	}
 	ctx->x_budget = bytes;
 	return CCG_OK;
@@ -151,6 +168,7 @@ extern "C" int ccg_set_partition(ccg_ctx *ctx, int rank, int world) {
 	if(!ctx || world < 1 || rank < 0 || rank >= world) return CCG_ERR_ARG;
 	ctx->rank = rank;
 	ctx->world = world;
+	update_need(ctx);
 	return CCG_OK;
 }
 
@@ -158,20 +176,61 @@ extern "C" int ccg_set_partition(ccg_ctx *ctx, int rank, int world) {
 extern "C" int ccg_tile_rows(void) { return CCG_UMMA_BM; }
 extern "C" int ccg_tile_cols(void) { return CCG_UMMA_BN; }
 
-/* visits the macro tiles (tm, tn) of an n-sample triangle owned by rank, in id order */
+/* The deal: macro tiles (tm, tn <= tm/2) are ordered along a Z-order (Morton) curve over
+ * (256-row band, 256-column panel) and cut into `world` contiguous runs of equal length.  A
+ * run is a compact 2-D region, so a rank touches only O(sqrt(tiles)) row blocks: that is what
+ * keeps the per-rank encode / expansion work from being replicated on every GPU. */
+static inline unsigned long long spread_bits(unsigned x) {
+	unsigned long long v = x;
+	v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+	v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+	v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+	v = (v | (v << 2)) & 0x3333333333333333ull;
+	v = (v | (v << 1)) & 0x5555555555555555ull;
+	return v;
+}
+
+struct MacroTile {
+	unsigned long long key;
+	int tm, tn;
+};
+
+static void macro_tiles_sorted(int n, std::vector<MacroTile> &out) {
+	const int TM = (n + CCG_UMMA_BM - 1) / CCG_UMMA_BM;
+	out.clear();
+	for(int tm = 0; tm < TM; ++tm)
+		for(int tn = 0; 2 * tn <= tm; ++tn) {
+			MacroTile t;
+			t.key = ((((spread_bits((unsigned) (tm >> 1)) << 1) | spread_bits((unsigned) tn))) << 1) | (unsigned) (tm & 1);
+			t.tm = tm;
+			t.tn = tn;
+			out.push_back(t);
+		}
+	std::sort(out.begin(), out.end(), [](const MacroTile &a, const MacroTile &b) { return a.key < b.key; });
+}
+
+/* visits the macro tiles (tm, tn) of an n-sample triangle owned by rank, in curve order */
 template <class F>
 static long long for_each_macro_tile(int n, int rank, int world, F f) {
 	if(n < 2 || world < 1 || rank < 0 || rank >= world) return 0;
-	const int TM = (n + CCG_UMMA_BM - 1) / CCG_UMMA_BM;
-	long long id = 0, owned = 0;
-	for(int tm = 0; tm < TM; ++tm) {
-		for(int tn = 0; 2 * tn <= tm; ++tn, ++id) {
-			if(id % world != rank) continue;
-			f(tm, tn);
-			++owned;
-		}
-	}
-	return owned;
+	std::vector<MacroTile> t;
+	macro_tiles_sorted(n, t);
+	const long long T = (long long) t.size();
+	const long long lo = T * rank / world, hi = T * (rank + 1) / world;
+	for(long long k = lo; k < hi; ++k) f(t[(size_t) k].tm, t[(size_t) k].tn);
+	return hi - lo;
+}
+
+/* row blocks (128 slots) the owned macro tiles read: A rows tm, B rows 2tn and 2tn+1 */
+static void update_need(ccg_ctx *ctx) {
+	if(!ctx->need) return;
+	const int nblocks = ctx->n_pad / 128;
+	memset(ctx->need, 0, (size_t) nblocks);
+	for_each_macro_tile(ctx->n, ctx->rank, ctx->world, [&](int tm, int tn) {
+		if(tm < nblocks) ctx->need[tm] = 1;
+		if(2 * tn < nblocks) ctx->need[2 * tn] = 1;
+		if(2 * tn + 1 < nblocks) ctx->need[2 * tn + 1] = 1;
+	});
 }
 
 extern "C" long long ccg_partition_tiles(int n, int rank, int world, int *tm_out, int *tn_out, long long cap) {
@@ -275,6 +334,8 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	   ctx->pair_mode == (pair_mode ? 1 : 0) && ctx->len == len) {
 		ctx->n = n;
 		memset(ctx->present, 0, (size_t) ctx->n_pad);
+		memset(ctx->have, 0, (size_t) ctx->n_pad / 128);
+		update_need(ctx);
 		ctx->global_inc = 0;
 		ctx->last_Dn = 0;
 		ctx->last_ntiles = 0;
@@ -305,8 +366,11 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 		CK(ctx, cudaMemsetAsync(ctx->d_gmask, 0, (size_t) (ctx->words + 1) * sizeof(uint32_t), ctx->stream));
 	}
 	ctx->present = (unsigned char *) calloc((size_t) ctx->n_pad, 1);
+	ctx->need = (unsigned char *) calloc((size_t) ctx->n_pad / 128, 1);
+	ctx->have = (unsigned char *) calloc((size_t) ctx->n_pad / 128, 1);
 	ctx->h_rank = (int *) malloc((size_t) ctx->n_pad * sizeof(int));
-	if(!ctx->present || !ctx->h_rank) return CCG_ERR_NOMEM;
+	if(!ctx->present || !ctx->h_rank || !ctx->need || !ctx->have) return CCG_ERR_NOMEM;
+	update_need(ctx);
 	ctx->global_inc = 0;
 	return make_planes_tmap(ctx);
 }
@@ -353,10 +417,14 @@ extern "C" int ccg_put_samples_packed(ccg_ctx *ctx, int first, int count, const 
 
 	int k = 0;
 	while(k < count) {
-		/* run of consecutive present rows, at most one staging batch */
+		/* run of consecutive present rows, at most one staging batch; rows of row blocks that no
+		 * macro tile of this rank reads are registered but not uploaded */
 		if(!seqs[k] || (ctx->pair_mode && !includes[k])) { ++k; continue; }
+		if(!ctx->need[(first + k) >> 7]) { ctx->present[first + k] = 1; ++k; continue; }
 		int run = 0;
-		while(k + run < count && (size_t) run < batch && seqs[k + run] && (!ctx->pair_mode || includes[k + run])) {
+		while(k + run < count && (size_t) run < batch && seqs[k + run] && (!ctx->pair_mode || includes[k + run]) &&
+		      ctx->need[(first + k + run) >> 7]) {
+			ctx->have[(first + k + run) >> 7] = 1;
 			CK(ctx, cudaMemcpyAsync(d_seq + (size_t) run * W, seqs[k + run], W * 8, cudaMemcpyHostToDevice, ctx->stream));
 			if(ctx->pair_mode)
 				CK(ctx, cudaMemcpyAsync(d_msk + (size_t) run * W, includes[k + run], W * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -376,8 +444,21 @@ extern "C" int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count, co
 	if(ctx->pair_mode && !d_masks) return CCG_ERR_ARG;
 	if(count == 0) return CCG_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
-	CK(ctx, ccg_launch_repack(ctx, first, count, d_seqs, ctx->pair_mode ? d_masks : 0, wstride));
 	memset(ctx->present + first, 1, (size_t) count);
+	/* runs of row blocks this rank's macro tiles read */
+	int k = 0;
+	while(k < count) {
+		if(!ctx->need[(first + k) >> 7]) { k = (((first + k) >> 7) + 1) * 128 - first; continue; }
+		int e = k;
+		while(e < count && ctx->need[(first + e) >> 7]) {
+			ctx->have[(first + e) >> 7] = 1;
+			e = (((first + e) >> 7) + 1) * 128 - first;
+		}
+		if(e > count) e = count;
+		CK(ctx, ccg_launch_repack(ctx, first + k, e - k, d_seqs + (size_t) k * wstride,
+		                          ctx->pair_mode ? d_masks + (size_t) k * wstride : 0, wstride));
+		k = e;
+	}
 	return CCG_OK;
 }
 
@@ -391,6 +472,7 @@ extern "C" int ccg_put_sample_codes(ccg_ctx *ctx, int idx, const unsigned char *
 	CK(ctx, cudaMemcpyAsync(ctx->d_stage, codes, (size_t) ctx->len, cudaMemcpyHostToDevice, ctx->stream));
 	CK(ctx, ccg_launch_encode_codes(ctx, idx, 1, (const unsigned char *) ctx->d_stage, (long) stride));
 	ctx->present[idx] = 1;
+	ctx->have[idx >> 7] = 1;
 	return CCG_OK;
 }
 
@@ -537,22 +619,27 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	}
 	CK(ctx, cudaMemsetAsync(ctx->d_C, 0, c_bytes, ctx->stream));
 
-	/* operand panel: as many chunks per slab as the scratch budget allows; sized once per
-	 * problem geometry (cudaMemGetInfo / cudaMalloc are far too slow for the per-run path) */
+	/* operand panel: the K axis is cut into slabs; two slab buffers so that the expansion of
+	 * slab s+1 (aux stream, HBM-write bound) runs under the GEMM of slab s (tensor bound).
+	 * Sized once per problem geometry (cudaMemGetInfo / cudaMalloc are far too slow per run). */
 	if(!ctx->d_X) {
 		size_t free_b = 0, total_b = 0;
 		CK(ctx, cudaMemGetInfo(&free_b, &total_b));
 		size_t budget = ctx->x_budget ? ctx->x_budget : (size_t) 48 << 30;
 		if(budget > free_b - free_b / 8) budget = free_b - free_b / 8;
-		long long fit = (long long) (budget / ((size_t) ctx->n_pad * 512));
+		const size_t per_chunk = (size_t) ctx->n_pad * 512;
+		long long fit = (long long) (budget / (2 * per_chunk));
 		if(fit > ctx->chunks) fit = ctx->chunks;
 		if(fit < 1) {
-			set_err(ctx, "not enough device memory for one chunk of the operand panel (%d slots)", ctx->n_pad);
+			set_err(ctx, "not enough device memory for the operand panel (%d slots)", ctx->n_pad);
 			return CCG_ERR_NOMEM;
 		}
-		const int want_slabs = (int) ((ctx->chunks + fit - 1) / fit);
-		fit = (ctx->chunks + want_slabs - 1) / want_slabs;          /* equal slabs */
-		size_t x_bytes = (size_t) fit * 512 * ctx->n_pad;
+		int want_slabs = (int) ((ctx->chunks + fit - 1) / fit);
+		if(ctx->chunks >= 2048 && want_slabs < 8) want_slabs = 8;      /* enough slabs to hide the first expansion */
+		fit = (ctx->chunks + want_slabs - 1) / want_slabs;              /* equal slabs */
+		const int nbuf = want_slabs > 1 ? 2 : 1;
+		ctx->x_buf_bytes = (size_t) fit * per_chunk;
+		size_t x_bytes = ctx->x_buf_bytes * nbuf;
 		if(cudaMalloc(&ctx->d_X, x_bytes) != cudaSuccess) {
 			ctx->d_X = 0;
 			set_err(ctx, "cudaMalloc of %zu bytes for the operand panel failed", x_bytes);
@@ -574,21 +661,30 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	p.C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
 	p.ldc = ctx->n_pad;
 	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+	CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+	CK(ctx, cudaEventRecord(ctx->ev_phase[0], ctx->aux_stream));
 	for(int s = 0; s < nslabs; ++s) {
+		const int b = s & 1;
 		const int chunk0 = (int) (s * slab);
 		int nch = ctx->chunks - chunk0;
 		if(nch > slab) nch = (int) slab;
 		p.slab_chunks = nch;
+		p.row_base = (int) (b * (ctx->x_buf_bytes / 128));
 		p.kslices = choose_split((long long) ctx->sm_count, (long long) cnt, nch, 16, 512);
 		p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
 		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nch) --p.kslices;
-		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[0], ctx->stream));
-		CK(ctx, ccg_launch_expand(ctx, chunk0, nch));
-		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->stream));
+		/* buffer b is free once the GEMM of slab s-2 has read it */
+		if(s >= 2) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b], 0));
+		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + b * ctx->x_buf_bytes, chunk0, nch));
+		CK(ctx, cudaEventRecord(ctx->ev_x[b], ctx->aux_stream));
+		if(s == nslabs - 1) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->aux_stream));
+		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x[b], 0));
 		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[2], ctx->stream));
 		CK(ctx, ccg_launch_umma(ctx, p));
-		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[3], ctx->stream));
+		CK(ctx, cudaEventRecord(ctx->ev_g[b], ctx->stream));
 	}
+	CK(ctx, cudaEventRecord(ctx->ev_phase[3], ctx->stream));
 	ctx->phase_valid = 1;
 	/* shared-mask mode: every position of every chunk counts as included in the raw product */
 	const int i_const = ctx->chunks * CCG_CHUNK_BASES;
@@ -677,6 +773,15 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	if(Dn_out) *Dn_out = Dn;
 	ctx->last_ntiles = 0;
 	if(Dn < 2) return CCG_OK;
+	for(int b = 0; b < ctx->n_pad / 128; ++b) {
+		if(!ctx->need[b] || ctx->have[b]) continue;
+		for(int i = b * 128; i < (b + 1) * 128; ++i)
+			if(ctx->h_rank[i] >= 0) {
+				set_err(ctx, "row block %d is needed by rank %d/%d but was not uploaded: call ccg_set_partition before "
+				        "the ccg_put_* calls", b, ctx->rank, ctx->world);
+				return CCG_ERR_ARG;
+			}
+	}
 	CK(ctx, cudaMemcpyAsync(ctx->d_rank, ctx->h_rank, (size_t) ctx->n_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 
 	EpilogueParams ep;

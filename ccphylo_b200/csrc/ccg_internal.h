@@ -69,12 +69,15 @@ struct UmmaParams {
 	int slab_chunks;       /* chunks resident in X */
 	int *C_S, *C_I;        /* dense [n_pad][ldc] int32 accumulators */
 	int ldc;
+	int row_base;          /* first 128-byte row of this slab's buffer inside the panel allocation */
 };
 
 struct ccg_ctx {
 	int device;
 	int sm_count;
 	cudaStream_t own_stream, stream;
+	cudaStream_t aux_stream;   /* operand expansion of slab s+1 runs here, under the GEMM of slab s */
+	cudaEvent_t ev_fork, ev_x[2], ev_g[2];
 	int kernel_choice;
 	int rank, world;
 
@@ -85,7 +88,9 @@ struct ccg_ctx {
 	uint32_t *d_gmask;         /* shared-mask mode: [words] */
 	unsigned global_inc;
 	unsigned *d_inc;           /* [n_pad] per-slot included counts */
-	unsigned char *present;    /* host [n]: slot uploaded */
+	unsigned char *present;    /* host [n_pad]: slot holds a sample of the current problem */
+	unsigned char *need;       /* host [n_pad/128]: row block touched by a macro tile this rank owns */
+	unsigned char *have;       /* host [n_pad/128]: row block whose present slots were really uploaded */
 
 	void *d_stage;             /* staging for host rows */
 	size_t stage_bytes;
@@ -105,8 +110,9 @@ struct ccg_ctx {
 	size_t out_bytes;
 
 	/* tensor-core path */
-	int8_t *d_X;               /* operand panel [n_pad][x_chunks][4][128] */
-	size_t x_bytes, x_pitch;
+	int8_t *d_X;               /* operand panel: 2 slab buffers of [n_pad/128][x_chunks*4][128][128 B] */
+	size_t x_bytes;            /* whole allocation */
+	size_t x_buf_bytes;        /* one slab buffer */
 	int x_chunks;              /* chunks per slab */
 	int *d_C;                  /* 2 x [n_pad][n_pad] int32 */
 	size_t c_bytes;
@@ -140,7 +146,7 @@ cudaError_t ccg_launch_popc(ccg_ctx *ctx, const PopcParams &p);
 int ccg_popc_kc(void);
 
 /* k_pairdist_umma.cu */
-cudaError_t ccg_launch_expand(ccg_ctx *ctx, int chunk0, int nchunks);
+cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks);
 cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
 cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);
 cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc);

@@ -119,13 +119,13 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x0020
  * The code planes are already ANDed with the mask (k_encode), so h, l and h^l are zero
  * wherever the base is unknown. */
 __global__ void __launch_bounds__(256)
-k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slots, int chunk0, int nchunks,
+k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slot0, int slots, int chunk0, int nchunks,
          int8_t *__restrict__ X, size_t nkb) {
 	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
 	const long long item = gid >> 3;
 	if(item >= (long long) slots * nchunks) return;
 	const int seg = (int) (gid & 7);
-	const int slot = (int) (item % slots);
+	const int slot = slot0 + (int) (item % slots);
 	const int cl = (int) (item / slots);           /* chunk within the slab */
 	const int q = seg >> 1, half = seg & 1;
 	const size_t prow = (size_t) (chunk0 + cl) * nplanes;
@@ -212,9 +212,9 @@ k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 				const int kabs = c_begin * 4 + kb;
 				const int nkb_slab = p.slab_chunks * 4;
 				mbar_expect_tx(bar, STAGE_BYTES);
-				tma_load_2d(dst, &tmap, bar, 0, (tm * nkb_slab + kabs) * 128);
-				tma_load_2d(dst + A_BYTES, &tmap, bar, 0, ((2 * tn) * nkb_slab + kabs) * 128);
-				tma_load_2d(dst + A_BYTES + 128 * BK, &tmap, bar, 0, ((2 * tn + 1) * nkb_slab + kabs) * 128);
+				tma_load_2d(dst, &tmap, bar, 0, p.row_base + (tm * nkb_slab + kabs) * 128);
+				tma_load_2d(dst + A_BYTES, &tmap, bar, 0, p.row_base + ((2 * tn) * nkb_slab + kabs) * 128);
+				tma_load_2d(dst + A_BYTES + 128 * BK, &tmap, bar, 0, p.row_base + ((2 * tn + 1) * nkb_slab + kabs) * 128);
 			}
 		}
 	} else if(warp == 1) {
@@ -318,14 +318,24 @@ k_gather_raw_dense(const int *__restrict__ C_S, const int *__restrict__ C_I, int
 
 } // namespace
 
-cudaError_t ccg_launch_expand(ccg_ctx *ctx, int chunk0, int nchunks) {
-	const int slots = ctx->n_pad;
-	const long long items = (long long) slots * nchunks;
-	if(items <= 0) return cudaSuccess;
-	const unsigned blocks = (unsigned) ((items * 8 + 255) / 256);
-	k_expand<<<blocks, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, slots, chunk0, nchunks, ctx->d_X,
-	                                           (size_t) nchunks * 4);
-	ctx->launches++;
+/* expands the row blocks this rank needs (runs of consecutive needed 128-slot blocks) */
+cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks) {
+	const int nblocks = ctx->n_pad / 128;
+	int b = 0;
+	while(b < nblocks) {
+		if(!ctx->need[b]) { ++b; continue; }
+		int e = b;
+		while(e < nblocks && ctx->need[e]) ++e;
+		const int slot0 = b * 128, slots = (e - b) * 128;
+		const long long items = (long long) slots * nchunks;
+		if(items > 0) {
+			const unsigned blocks = (unsigned) ((items * 8 + 255) / 256);
+			k_expand<<<blocks, 256, 0, stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, slot0, slots, chunk0, nchunks, X,
+			                                      (size_t) nchunks * 4);
+			ctx->launches++;
+		}
+		b = e;
+	}
 	return cudaGetLastError();
 }
 

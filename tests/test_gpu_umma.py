@@ -133,9 +133,9 @@ def test_umma_multi_slab_and_kslices(ctx):
     mo, no = oracle.raw_pair_matrix(seqs, masks, length)
     if ctx.kind == api.KERNEL_UMMA:
         try:
-            ctx.set_scratch_limit(256 * 512 * 700)          # 700 chunks per slab -> 4 slabs
+            ctx.set_scratch_limit(2 * 256 * 512 * 350)      # two 350-chunk slab buffers -> 8 slabs
             D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
-            assert "slabs=4" in ctx.last_kernel, ctx.last_kernel
+            assert "slabs=8" in ctx.last_kernel, ctx.last_kernel
             mism, ninc = ctx.raw_counts(dn)
             assert np.array_equal(mism, mo) and np.array_equal(ninc, no)
         finally:
@@ -166,3 +166,41 @@ def test_umma_equals_popc_on_device(built):
         assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
         assert np.array_equal(_bits(a[0]), _bits(b[0])) and np.array_equal(_bits(a[1]), _bits(b[1]))
     assert a[2][0].max() > 0
+
+
+@pytest.mark.parametrize("kind", [api.KERNEL_POPC, api.KERNEL_UMMA], ids=["popc", "umma"])
+def test_partition_set_before_upload_only_touches_needed_rows(built, kind):
+    """One process per GPU sets its partition FIRST: rows that none of its macro tiles reads are
+    registered (they still count in the compaction) but never uploaded / expanded."""
+    n, length, world = 900, 4096 + 31, 4
+    codes, seqs, masks, inc = _set(n, length, seed=77)
+    include = np.ones(n, dtype=np.uint8)
+    include[[5, 400]] = 0
+    Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=1000, min_length=0, min_cov=0.0)
+    total_D = np.zeros(api.cells(dno))
+    total_N = np.zeros(api.cells(dno))
+    for r in range(world):
+        with api.Context() as c:
+            c.set_kernel(kind)
+            c.set_partition(r, world)
+            c.set_problem(n, length, pair=True)
+            c.put_samples_packed(seqs, masks)
+            D, N, dn = c.run_pair(include=include, norm=1000, min_length=0, min_cov=0.0)
+            assert dn == dno
+            assert not np.any((total_N != 0) & (N != 0))
+            total_D += D
+            total_N += N
+    assert np.array_equal(total_N, No) and np.array_equal(total_D, Do)
+
+
+def test_partition_change_after_upload_is_refused(built):
+    n, length = 900, 2048
+    codes, seqs, masks, inc = _set(n, length, seed=78)
+    with api.Context() as c:
+        c.set_partition(3, 4)
+        c.set_problem(n, length, pair=True)
+        c.put_samples_packed(seqs, masks)
+        c.set_partition(0, 1)
+        with pytest.raises(api.CcgError) as e:
+            c.run_pair()
+        assert e.value.code == 3 and "ccg_set_partition before" in str(e.value)
