@@ -628,14 +628,20 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		size_t budget = ctx->x_budget ? ctx->x_budget : (size_t) 48 << 30;
 		if(budget > free_b - free_b / 8) budget = free_b - free_b / 8;
 		const size_t per_chunk = (size_t) ctx->n_pad * 512;
-		long long fit = (long long) (budget / (2 * per_chunk));
-		if(fit > ctx->chunks) fit = ctx->chunks;
-		if(fit < 1) {
-			set_err(ctx, "not enough device memory for the operand panel (%d slots)", ctx->n_pad);
-			return CCG_ERR_NOMEM;
+		long long fit = (long long) (budget / per_chunk);        /* chunks one buffer could hold */
+		int want_slabs = 1;
+		if(fit < ctx->chunks) {
+			fit = (long long) (budget / (2 * per_chunk));         /* two buffers */
+			if(fit < 1) {
+				set_err(ctx, "not enough device memory for the operand panel (%d slots)", ctx->n_pad);
+				return CCG_ERR_NOMEM;
+			}
+			want_slabs = (int) ((ctx->chunks + fit - 1) / fit);
 		}
-		int want_slabs = (int) ((ctx->chunks + fit - 1) / fit);
-		if(ctx->chunks >= 2048 && want_slabs < 8) want_slabs = 8;      /* enough slabs to hide the first expansion */
+		/* measured (profiles/): running the expansion under the GEMM does not pay on one GPU (both
+		 * are limited by HBM traffic and issue slots: 13.2 ms overlapped vs 12.3 ms back to back at
+		 * 1000 x 5 Mbp), so the panel is cut only when it does not fit; then the two buffers keep
+		 * the tensor pipe busy while the next slab is produced */
 		fit = (ctx->chunks + want_slabs - 1) / want_slabs;              /* equal slabs */
 		const int nbuf = want_slabs > 1 ? 2 : 1;
 		ctx->x_buf_bytes = (size_t) fit * per_chunk;
@@ -676,7 +682,7 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nch) --p.kslices;
 		/* buffer b is free once the GEMM of slab s-2 has read it */
 		if(s >= 2) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b], 0));
-		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + b * ctx->x_buf_bytes, chunk0, nch));
+		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + b * ctx->x_buf_bytes, chunk0, nch, nslabs > 1));
 		CK(ctx, cudaEventRecord(ctx->ev_x[b], ctx->aux_stream));
 		if(s == nslabs - 1) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->aux_stream));
 		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x[b], 0));

@@ -146,7 +146,7 @@ cudaError_t ccg_launch_popc(ccg_ctx *ctx, const PopcParams &p);
 int ccg_popc_kc(void);
 
 /* k_pairdist_umma.cu */
-cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks);
+cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks, int bounded);
 cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
 cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);
 cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc);

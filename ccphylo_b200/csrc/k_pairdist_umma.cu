@@ -121,41 +121,45 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x0020
 __global__ void __launch_bounds__(256)
 k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slot0, int slots, int chunk0, int nchunks,
          int8_t *__restrict__ X, size_t nkb) {
-	const long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	const long long item = gid >> 3;
-	if(item >= (long long) slots * nchunks) return;
-	const int seg = (int) (gid & 7);
-	const int slot = slot0 + (int) (item % slots);
-	const int cl = (int) (item / slots);           /* chunk within the slab */
-	const int q = seg >> 1, half = seg & 1;
-	const size_t prow = (size_t) (chunk0 + cl) * nplanes;
-	uint32_t h = planes[((prow + 0) * n_pad + slot) * 4 + q];
-	uint32_t l = planes[((prow + 1) * n_pad + slot) * 4 + q];
-	uint32_t m = nplanes == 3 ? planes[((prow + 2) * n_pad + slot) * 4 + q] : 0xFFFFFFFFu;
-	/* base k of the word <-> bit 31-k; reverse so base k <-> bit k, then take this thread's 16 bases */
-	h = __brev(h) >> (16 * half);
-	l = __brev(l) >> (16 * half);
-	m = __brev(m) >> (16 * half);
-	uint32_t c0[4], c1[4], c2[4], c3[4];
+	/* bounded persistent grid (grid-stride): leaves thread slots on every SM for the GEMM CTAs of the
+	 * previous slab, which run concurrently on the main stream */
+	const long long total = (long long) slots * nchunks * 8;
+	for(long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+	    gid += (long long) gridDim.x * blockDim.x) {
+		const long long item = gid >> 3;
+		const int seg = (int) (gid & 7);
+		const int slot = slot0 + (int) (item % slots);
+		const int cl = (int) (item / slots);           /* chunk within the slab */
+		const int q = seg >> 1, half = seg & 1;
+		const size_t prow = (size_t) (chunk0 + cl) * nplanes;
+		uint32_t h = planes[((prow + 0) * n_pad + slot) * 4 + q];
+		uint32_t l = planes[((prow + 1) * n_pad + slot) * 4 + q];
+		uint32_t m = nplanes == 3 ? planes[((prow + 2) * n_pad + slot) * 4 + q] : 0xFFFFFFFFu;
+		/* base k of the word <-> bit 31-k; reverse so base k <-> bit k, then take this thread's 16 bases */
+		h = __brev(h) >> (16 * half);
+		l = __brev(l) >> (16 * half);
+		m = __brev(m) >> (16 * half);
+		uint32_t c0[4], c1[4], c2[4], c3[4];
 #pragma unroll
-	for(int g = 0; g < 4; ++g) {
-		const uint32_t ones = spread4((m >> (4 * g)) & 0xFu);     /* 0x01 where known */
-		const uint32_t sh = spread4((h >> (4 * g)) & 0xFu);       /* 0x01 where channel 0 is -1 */
-		const uint32_t sl = spread4((l >> (4 * g)) & 0xFu);       /* 0x01 where channel 1 is -1 */
-		const uint32_t sx = sh ^ sl;                              /* 0x01 where channel 2 is -1 */
-		c0[g] = sh * 0xFEu + ones;                                /* +1 = 0x01, -1 = 0xFF, unknown = 0 */
-		c1[g] = sl * 0xFEu + ones;
-		c2[g] = sx * 0xFEu + ones;
-		c3[g] = ones;
+		for(int g = 0; g < 4; ++g) {
+			const uint32_t ones = spread4((m >> (4 * g)) & 0xFu);     /* 0x01 where known */
+			const uint32_t sh = spread4((h >> (4 * g)) & 0xFu);       /* 0x01 where channel 0 is -1 */
+			const uint32_t sl = spread4((l >> (4 * g)) & 0xFu);       /* 0x01 where channel 1 is -1 */
+			const uint32_t sx = sh ^ sl;                              /* 0x01 where channel 2 is -1 */
+			c0[g] = sh * 0xFEu + ones;                                /* +1 = 0x01, -1 = 0xFF, unknown = 0 */
+			c1[g] = sl * 0xFEu + ones;
+			c2[g] = sx * 0xFEu + ones;
+			c3[g] = ones;
+		}
+		/* tile-blocked panel: X[slot/128][k-block][slot%128][128 B], k-block = chunk*4 + channel, so the
+		 * 128 rows x 128 B box a TMA load fetches is 16 KiB contiguous */
+		const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) cl * 4) * 128 + (slot & 127);
+		uint4 *dst = reinterpret_cast<uint4 *>(X + tile_row * 128 + seg * 16);
+		dst[0 * 1024] = make_uint4(c0[0], c0[1], c0[2], c0[3]);   /* channel rows are 128 x 128 B = 1024 uint4 apart */
+		dst[1 * 1024] = make_uint4(c1[0], c1[1], c1[2], c1[3]);
+		dst[2 * 1024] = make_uint4(c2[0], c2[1], c2[2], c2[3]);
+		dst[3 * 1024] = make_uint4(c3[0], c3[1], c3[2], c3[3]);
 	}
-	/* tile-blocked panel: X[slot/128][k-block][slot%128][128 B], k-block = chunk*4 + channel, so the
-	 * 128 rows x 128 B box a TMA load fetches is 16 KiB contiguous */
-	const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) cl * 4) * 128 + (slot & 127);
-	uint4 *dst = reinterpret_cast<uint4 *>(X + tile_row * 128 + seg * 16);
-	dst[0 * 1024] = make_uint4(c0[0], c0[1], c0[2], c0[3]);       /* channel rows are 128 x 128 B = 1024 uint4 apart */
-	dst[1 * 1024] = make_uint4(c1[0], c1[1], c1[2], c1[3]);
-	dst[2 * 1024] = make_uint4(c2[0], c2[1], c2[2], c2[3]);
-	dst[3 * 1024] = make_uint4(c3[0], c3[1], c3[2], c3[3]);
 }
 
 /* ------------------------------------------------------------------ */
@@ -319,7 +323,7 @@ k_gather_raw_dense(const int *__restrict__ C_S, const int *__restrict__ C_I, int
 } // namespace
 
 /* expands the row blocks this rank needs (runs of consecutive needed 128-slot blocks) */
-cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks) {
+cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks, int bounded) {
 	const int nblocks = ctx->n_pad / 128;
 	int b = 0;
 	while(b < nblocks) {
@@ -329,8 +333,10 @@ cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int 
 		const int slot0 = b * 128, slots = (e - b) * 128;
 		const long long items = (long long) slots * nchunks;
 		if(items > 0) {
-			const unsigned blocks = (unsigned) ((items * 8 + 255) / 256);
-			k_expand<<<blocks, 256, 0, stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, slot0, slots, chunk0, nchunks, X,
+			long long blocks = (items * 8 + 255) / 256;
+			/* when a GEMM of the previous slab runs concurrently, leave it room on every SM */
+			if(bounded && blocks > 6LL * ctx->sm_count) blocks = 6LL * ctx->sm_count;
+			k_expand<<<(unsigned) blocks, 256, 0, stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, slot0, slots, chunk0, nchunks, X,
 			                                      (size_t) nchunks * 4);
 			ctx->launches++;
 		}
