@@ -219,6 +219,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout: keep it to one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     n, length = samples_for(world, args.samples), args.length

@@ -177,9 +177,9 @@ extern "C" int ccg_tile_rows(void) { return CCG_UMMA_BM; }
 extern "C" int ccg_tile_cols(void) { return CCG_UMMA_BN; }
 
 /* The deal: macro tiles (tm, tn <= tm/2) are ordered along a Z-order (Morton) curve over
- * (256-row band, 256-column panel) and cut into `world` contiguous runs of equal length.  A
- * run is a compact 2-D region, so a rank touches only O(sqrt(tiles)) row blocks: that is what
- * keeps the per-rank encode / expansion work from being replicated on every GPU. */
+ * (256-row band, 256-column panel) and cut into `world` contiguous runs of equal estimated
+ * cost.  A run is a compact 2-D region, so a rank touches only O(sqrt(tiles)) row blocks: that
+ * is what keeps the per-rank encode / expansion work from being replicated on every GPU. */
 static inline unsigned long long spread_bits(unsigned x) {
 	unsigned long long v = x;
 	v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
@@ -209,14 +209,68 @@ static void macro_tiles_sorted(int n, std::vector<MacroTile> &out) {
 	std::sort(out.begin(), out.end(), [](const MacroTile &a, const MacroTile &b) { return a.key < b.key; });
 }
 
+/* Cost of giving one rank the curve segment [lo, hi): its macro tiles (GEMM time) plus the row
+ * blocks they read (encode + expansion time of those 128 samples).  Measured on B200 at 5 Mbp:
+ * 0.39 ms per tile, 0.58 ms per row block -> 1.5 tiles per block. */
+static const double kRowBlockCost = 1.5;
+
+/* greedy walk along the curve: how many segments of cost <= cap are needed; optionally records cuts */
+static int segments_for_cap(const std::vector<MacroTile> &t, int nblocks, double cap, std::vector<long long> *cuts) {
+	std::vector<int> stamp((size_t) nblocks + 2, -1);
+	int seg = 0;
+	double cost = 0.0;
+	if(cuts) { cuts->clear(); cuts->push_back(0); }
+	for(size_t k = 0; k < t.size(); ++k) {
+		const int blk[3] = {t[k].tm, 2 * t[k].tn, 2 * t[k].tn + 1};
+		double add = 1.0;
+		for(int q = 0; q < 3; ++q)
+			if(blk[q] < nblocks && stamp[(size_t) blk[q]] != seg) add += kRowBlockCost;
+		if(cost > 0.0 && cost + add > cap) {
+			++seg;
+			cost = 0.0;
+			if(cuts) cuts->push_back((long long) k);
+			add = 1.0;
+			for(int q = 0; q < 3; ++q)
+				if(blk[q] < nblocks) add += kRowBlockCost;
+			/* blocks shared inside this tile are counted once below */
+			if(blk[1] == blk[0] || blk[2] == blk[0]) add -= kRowBlockCost;
+		}
+		for(int q = 0; q < 3; ++q)
+			if(blk[q] < nblocks) stamp[(size_t) blk[q]] = seg;
+		cost += add;
+	}
+	if(cuts) cuts->push_back((long long) t.size());
+	return seg + 1;
+}
+
+/* cut points of the curve for `world` ranks: smallest per-rank cost cap that needs <= world segments */
+static void balanced_cuts(const std::vector<MacroTile> &t, int n, int world, std::vector<long long> &cuts) {
+	const int nblocks = (n + 127) / 128;
+	if(world <= 1 || t.size() <= 1) {
+		cuts.assign(1, 0);
+		cuts.push_back((long long) t.size());
+		while((int) cuts.size() < world + 1) cuts.push_back((long long) t.size());
+		return;
+	}
+	double lo = 1.0, hi = (double) t.size() + kRowBlockCost * nblocks + 1.0;
+	for(int it = 0; it < 48; ++it) {
+		const double mid = 0.5 * (lo + hi);
+		if(segments_for_cap(t, nblocks, mid, 0) <= world) hi = mid;
+		else lo = mid;
+	}
+	segments_for_cap(t, nblocks, hi, &cuts);
+	while((int) cuts.size() < world + 1) cuts.push_back((long long) t.size());
+}
+
 /* visits the macro tiles (tm, tn) of an n-sample triangle owned by rank, in curve order */
 template <class F>
 static long long for_each_macro_tile(int n, int rank, int world, F f) {
 	if(n < 2 || world < 1 || rank < 0 || rank >= world) return 0;
 	std::vector<MacroTile> t;
+	std::vector<long long> cuts;
 	macro_tiles_sorted(n, t);
-	const long long T = (long long) t.size();
-	const long long lo = T * rank / world, hi = T * (rank + 1) / world;
+	balanced_cuts(t, n, world, cuts);
+	const long long lo = cuts[(size_t) rank], hi = cuts[(size_t) rank + 1];
 	for(long long k = lo; k < hi; ++k) f(t[(size_t) k].tm, t[(size_t) k].tn);
 	return hi - lo;
 }
