@@ -43,6 +43,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Library chatter (e.g. NCCL's version banner) goes to fd 1; the contract is ONE JSON line on stdout.
+# Keep the real stdout aside, point fd 1 at stderr, and write the result line to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def samples_for(world, base):
     n = int(round(base * math.sqrt(world)))
     return max(64, (n // 64) * 64) if world > 1 else n
@@ -174,7 +184,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -219,8 +229,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout: keep it to one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     n, length = samples_for(world, args.samples), args.length
@@ -425,7 +433,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "parity_vs_oracle": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

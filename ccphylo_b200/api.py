@@ -22,7 +22,8 @@ KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_FUSED = 0, 1, 2, 3
 EXPORTS = [
     "ccg_strerror", "ccg_last_error", "ccg_init", "ccg_destroy", "ccg_set_stream", "ccg_set_kernel", "ccg_sync",
     "ccg_set_partition", "ccg_tile_rows", "ccg_tile_cols", "ccg_partition_cells", "ccg_partition_tiles",
-    "ccg_set_scratch_limit", "ccg_set_problem", "ccg_put_global_mask", "ccg_put_samples_packed",
+    "ccg_set_scratch_limit", "ccg_set_problem", "ccg_put_global_mask", "ccg_apply_global_mask",
+    "ccg_put_samples_packed",
     "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
@@ -70,6 +71,7 @@ def load():
     L.ccg_partition_tiles.argtypes = [i, i, i, vp, vp, ll]
     L.ccg_set_problem.argtypes = [vp, i, i, i]
     L.ccg_put_global_mask.argtypes = [vp, vp]
+    L.ccg_apply_global_mask.argtypes = [vp, vp]
     L.ccg_put_samples_packed.argtypes = [vp, i, i, vp, vp]
     L.ccg_put_samples_packed_dev.argtypes = [vp, i, i, vp, vp, C.c_long]
     L.ccg_put_sample_codes.argtypes = [vp, i, vp]
@@ -182,6 +184,11 @@ class Context:
         mask = np.ascontiguousarray(mask, dtype=np.uint32)
         assert mask.size >= words(self.len)
         self._ck(self._L.ccg_put_global_mask(self._h, mask.ctypes.data))
+
+    def apply_global_mask(self, mask):
+        mask = np.ascontiguousarray(mask, dtype=np.uint32)
+        assert mask.size >= words(self.len)
+        self._ck(self._L.ccg_apply_global_mask(self._h, mask.ctypes.data))
 
     def put_samples_packed(self, seqs, masks=None, first=0, skip=None):
         seqs = np.ascontiguousarray(seqs, dtype=np.uint64)

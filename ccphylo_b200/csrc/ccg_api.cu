@@ -391,6 +391,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 		memset(ctx->have, 0, (size_t) ctx->n_pad / 128);
 		update_need(ctx);
 		ctx->global_inc = 0;
+		ctx->global_applied = 0;
 		ctx->last_Dn = 0;
 		ctx->last_ntiles = 0;
 		return CCG_OK;
@@ -425,6 +426,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	ctx->h_rank = (int *) malloc((size_t) ctx->n_pad * sizeof(int));
 	if(!ctx->present || !ctx->h_rank || !ctx->need || !ctx->have) return CCG_ERR_NOMEM;
 	update_need(ctx);
+	ctx->global_applied = 0;
 	ctx->global_inc = 0;
 	return make_planes_tmap(ctx);
 }
@@ -450,6 +452,19 @@ extern "C" int ccg_put_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
 	unsigned inc = 0;
 	for(int w = 0; w < ctx->words; ++w) inc += (unsigned) __builtin_popcount(mask[w]);
 	ctx->global_inc = inc;      /* getNpos(*includes, len), fsacmpthrd.c:164 */
+	return CCG_OK;
+}
+
+extern "C" int ccg_apply_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
+	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !mask) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	if(!ctx->d_gmask) CK(ctx, cudaMalloc(&ctx->d_gmask, (size_t) (ctx->words + 1) * sizeof(uint32_t)));
+	CK(ctx, cudaMemcpyAsync(ctx->d_gmask, mask, (size_t) ctx->words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+	unsigned inc = 0;
+	for(int w = 0; w < ctx->words; ++w) inc += (unsigned) __builtin_popcount(mask[w]);
+	ctx->global_inc = inc;
+	CK(ctx, ccg_launch_apply_global_mask(ctx));
+	ctx->global_applied = 1;
 	return CCG_OK;
 }
 
@@ -679,7 +694,8 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	if(!ctx->d_X) {
 		size_t free_b = 0, total_b = 0;
 		CK(ctx, cudaMemGetInfo(&free_b, &total_b));
-		size_t budget = ctx->x_budget ? ctx->x_budget : (size_t) 48 << 30;
+		/* default: up to 70 % of what is free (the planes, accumulators and outputs are already allocated) */
+		size_t budget = ctx->x_budget ? ctx->x_budget : free_b / 10 * 7;
 		if(budget > free_b - free_b / 8) budget = free_b - free_b / 8;
 		const size_t per_chunk = (size_t) ctx->n_pad * 512;
 		long long fit = (long long) (budget / per_chunk);        /* chunks one buffer could hold */
@@ -817,7 +833,7 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
                       double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn_out) {
 	if(!ctx || !ctx->d_planes) return CCG_ERR_ARG;
 	if(elem_size != 8 && elem_size != 4 && elem_size != 2 && elem_size != 1) return CCG_ERR_ARG;
-	if((mode == 0) != (ctx->pair_mode == 1)) {
+	if((mode == 0) != (ctx->pair_mode == 1) && !(mode == 1 && ctx->pair_mode && ctx->global_applied)) {
 		set_err(ctx, "run mode does not match ccg_set_problem(pair_mode=%d)", ctx->pair_mode);
 		return CCG_ERR_ARG;
 	}

@@ -87,6 +87,7 @@ struct ccg_ctx {
 	size_t planes_bytes;
 	uint32_t *d_gmask;         /* shared-mask mode: [words] */
 	unsigned global_inc;
+	int global_applied;        /* pair-mode store whose planes were ANDed with a global mask */
 	unsigned *d_inc;           /* [n_pad] per-slot included counts */
 	unsigned char *present;    /* host [n_pad]: slot holds a sample of the current problem */
 	unsigned char *need;       /* host [n_pad/128]: row block touched by a macro tile this rank owns */
@@ -140,6 +141,7 @@ cudaError_t ccg_launch_repack(ccg_ctx *ctx, int first, int count, const uint64_t
 cudaError_t ccg_launch_encode_codes(ccg_ctx *ctx, int first, int count, const unsigned char *d_codes,
                                     long stride);
 cudaError_t ccg_launch_gather_raw(ccg_ctx *ctx, uint32_t *d_mism, uint32_t *d_ninc);
+cudaError_t ccg_launch_apply_global_mask(ccg_ctx *ctx);
 
 /* k_pairdist_popc.cu */
 cudaError_t ccg_launch_popc(ccg_ctx *ctx, const PopcParams &p);

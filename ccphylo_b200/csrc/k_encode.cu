@@ -134,6 +134,32 @@ k_encode_codes(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks
 	if(known) atomicAdd(inc + first + s, known);
 }
 
+/* Shared-mask mode on a pair-mode store (cdist.c:101-112 followed by cmpFsaThrd): every plane
+ * word of every slot is ANDed with the global mask G, so the per-pair mask m_i & m_j equals G
+ * and the pair kernels count exactly the reference's shared-mask mismatches. */
+__global__ void __launch_bounds__(256)
+k_apply_global_mask(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks, int words,
+                    const uint32_t *__restrict__ gmask) {
+	const long long total = (long long) chunks * nplanes * n_pad;
+	uint4 *v = reinterpret_cast<uint4 *>(planes);
+	for(long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
+		const long long c = e / ((long long) nplanes * n_pad);
+		uint32_t g[4];
+#pragma unroll
+		for(int q = 0; q < 4; ++q) g[q] = (c * 4 + q < words) ? gmask[c * 4 + q] : 0u;
+		uint4 x = v[e];
+		x.x &= g[0]; x.y &= g[1]; x.z &= g[2]; x.w &= g[3];
+		v[e] = x;
+	}
+}
+
+cudaError_t ccg_launch_apply_global_mask(ccg_ctx *ctx) {
+	k_apply_global_mask<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks,
+	                                                                   ctx->words, ctx->d_gmask);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
 /* tile-major raw counts -> packed lower triangle over included samples */
 __global__ void __launch_bounds__(256)
 k_gather_raw(const uint32_t *__restrict__ acc, int ntiles, const int2 *__restrict__ tiles, const int *__restrict__ rank,

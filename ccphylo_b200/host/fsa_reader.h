@@ -1,0 +1,40 @@
+/*
+ * fsa_reader.h -- buffered (gzip-transparent) file reader and KMA consensus FASTA parsing
+ * for the `dist` driver.  Behavioural counterpart of the reference's filebuff.c:52
+ * (openAndDetermine), seqparse.c:128 (FileBuffgetFsaHeader), :195 (FileBuffgetFsaSeq) and :28
+ * (FileBuffgetFsa), and of the byte -> code table of fsacmp.c:32 (get2BitTable).
+ */
+#ifndef FSA_READER_H
+#define FSA_READER_H
+
+#include <stddef.h>
+
+typedef struct FsaReader FsaReader;
+
+/* growable byte buffer */
+typedef struct {
+	unsigned char *data;
+	size_t len, cap;
+} ByteBuf;
+
+void bytebuf_init(ByteBuf *b, size_t cap);
+void bytebuf_free(ByteBuf *b);
+
+/* byte -> code table: 0..3 bases, 4 unknown, 32 = not a sequence byte (dropped).
+ * flag bit 8 makes lower-case acgtu count as bases (fsacmp.c:32-91). */
+void fsa_code_table(unsigned flag, unsigned char table[256]);
+
+/* opens a plain or gzip file ("-" = stdin); NULL on failure (errno set) */
+FsaReader *fsa_open(const char *path);
+void fsa_close(FsaReader *r);
+/* first byte of the (decompressed) stream without consuming it, or -1 (filebuff.c:26 fileExist) */
+int fsa_peek(FsaReader *r);
+
+/* advance to the next '>' and read the header line (without '>', trailing white space
+ * stripped) into header; 0 at end of file (seqparse.c:128) */
+int fsa_next_header(FsaReader *r, ByteBuf *header);
+/* translate the sequence up to the next '>' or end of file, keeping codes < 32; returns 0
+ * only if the stream was already exhausted (seqparse.c:195) */
+int fsa_read_codes(FsaReader *r, const unsigned char table[256], ByteBuf *codes);
+
+#endif

@@ -91,7 +91,7 @@ long long ccg_partition_cells(int n, int rank, int world);
 long long ccg_partition_tiles(int n, int rank, int world, int *tm, int *tn, long long cap);
 
 /* Upper bound in bytes for the tensor-core kernel's int8 operand panel (the
- * K axis is processed in slabs that fit); 0 = default (48 GiB or what is free). */
+ * K axis is processed in slabs that fit); 0 = default (70 % of the free device memory). */
 int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes);
 
 /* Declare the sample set: n sample slots of len bases.  pair_mode != 0 is
@@ -102,6 +102,12 @@ int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode);
 /* Shared-mask mode only: the global mask includes[0] (cdist.c:101-112), must
  * be set before the samples are put.  Host pointer. */
 int ccg_put_global_mask(ccg_ctx *ctx, const uint32_t *mask);
+
+/* Shared-mask mode for a store declared with pair_mode != 0 and already filled: ANDs every
+ * sample with the global mask (host pointer, ceil(len/32) words).  For callers that stream
+ * samples to the device before the global mask is complete (cdist.c:86-112 builds it while
+ * loading).  Afterwards ccg_run_global[_dev] may be used on this store. */
+int ccg_apply_global_mask(ccg_ctx *ctx, const uint32_t *mask);
 
 /* Upload samples [first, first+count) in the reference's packed format from
  * HOST memory; seqs[k] / includes[k] are row pointers exactly as the
