@@ -6,10 +6,12 @@
 
 A step = one pass of the hot path over one batch of synthetic KMA-consensus samples:
 encode (reference packed words -> device bit planes) + all-vs-all compare + fused epilogue
-(packed lower-triangular D and N as doubles).  Workload at N=1: BASELINE.json configs[1]
-(1,000 samples x 5 Mbp, pair mode, -n); for N>1 the lower-triangular 64x64 tile blocks are
-dealt to the ranks (no data-path collective) and the sample count grows with sqrt(N) so the
-pairs per GPU stay fixed ("weak").
+(packed lower-triangular D and N as doubles).  Workload: the configuration BASELINE.json's
+metric is quoted on -- 10,000 samples x 5 Mbp, pair mode, -n (configs[2]; it fits one B200:
+19 GB of bit planes, the int8 operand panel is processed in K slabs).  The job is the same
+at every N ("strong"): the lower-triangular macro tiles are cut into N contiguous runs of a
+Z-order curve, one per rank, with no data-path collective.  `--scaling weak` instead grows
+the sample count with sqrt(N) so the pairs per GPU stay fixed.
 
 `value`  : inputs resident in HBM (reference packed format) when the timed region starts.
 `e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers
@@ -35,7 +37,7 @@ import numpy as np  # noqa: E402
 METRIC = "pairwise base comparisons/sec"
 UNIT = "base-cmp/s"
 LENGTH = 5_000_000
-BASE_SAMPLES = 1000
+BASE_SAMPLES = 10000
 OPS_PER_BASECMP = 8          # int8 ops of the K=4L tetrahedral+mask contraction
 
 
@@ -53,9 +55,11 @@ def emit(line):
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
-def samples_for(world, base):
+def samples_for(world, base, scaling="strong"):
+    if scaling == "strong" or world == 1:
+        return base
     n = int(round(base * math.sqrt(world)))
-    return max(64, (n // 64) * 64) if world > 1 else n
+    return max(64, (n // 64) * 64)
 
 
 def measured_peaks():
@@ -168,7 +172,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = samples_for(world, args.samples)
+    n = samples_for(world, args.samples, args.scaling)
     # the bounded sample never needs more than a few hundred samples: generate just those
     ns_cap = min(n, 64 + 8 * cores)
     seqs, masks = make_host_workload(ns_cap, args.length, seed=2)
@@ -176,7 +180,7 @@ def reference_arm(args, rank, world):
                                                                    steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u64 words / u32 counters (scalar bit loops)", "data": "synthetic",
         "config": {"workload": f"{n} samples x {args.length} bp all-vs-all D+N (pair mode, -f 3 -n), "
                                f"bounded sample: {what}"},
@@ -196,7 +200,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--samples", type=int, default=BASE_SAMPLES, help="samples at N=1 (grows with sqrt(N))")
+    ap.add_argument("--samples", type=int, default=BASE_SAMPLES, help="samples (at N=1 when --scaling weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--length", type=int, default=LENGTH)
     ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "umma", "fused"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work per reference step")
@@ -231,7 +236,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    n, length = samples_for(world, args.samples), args.length
+    n, length = samples_for(world, args.samples, args.scaling), args.length
     W = api.words(length)
     t_gen = time.time()
     seqs_t, masks_t = synth.make_packed_torch(n, length, seed=2, device=dev)
@@ -364,8 +369,9 @@ def main():
         hm = np.ctypeslib.as_array(C.cast(hm_ptr, C.POINTER(C.c_uint32)), shape=(n, W))
         hs_t = torch.from_numpy(hs.view(np.int64))
         hm_t = torch.from_numpy(hm.view(np.int32))
-        hs_t.copy_(seqs_t.cpu())
-        hm_t.copy_(masks_t.cpu())
+        hs_t.copy_(seqs_t)                      # device -> pinned host, no pageable intermediate
+        hm_t.copy_(masks_t)
+        torch.cuda.synchronize()
         sp = (C.c_void_p * n)(*[hs_ptr + k * row_s for k in range(n)])
         mp = (C.c_void_p * n)(*[hm_ptr + k * row_m for k in range(n)])
         include = np.ones(n, dtype=np.uint8)
@@ -418,15 +424,18 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None,
             "dtype": ("int8 operands, int32 accumulate (tcgen05 kind::i8), f64 epilogue" if use_umma
                       else "u32 bit-planes (LOP3+POPC), u32 counters, f64 epilogue"),
             "data": "synthetic",
             "config": {"workload": f"{n} samples x {length} bp all-vs-all distance + inclusion matrix "
-                                   f"(pair mode, -f 3 -n), BASELINE configs[1] scaled by sqrt(N) samples",
+                                   f"(pair mode, -f 3 -n), " + ("BASELINE configs[2], the metric's own configuration, same job at every N"
+                                                             if args.scaling == "strong" else
+                                                             "sample count grown with sqrt(N)"),
                        "samples": n, "length": length, "pairs": ncell,
-                       "partition": f"lower-triangular 64x64 tile blocks dealt to {world} rank(s), no collective",
+                       "partition": f"lower-triangular 128x256 macro tiles, Z-order curve cut into {world} cost-balanced run(s), "
+                                    f"no collective",
                        "l2": "inputs (%.2f GB of planes) larger than the 126 MB L2; no explicit flush" %
                              (n * W * 12 / 1e9),
                        "step": "encode (packed words -> bit planes) + compare + fused epilogue"},

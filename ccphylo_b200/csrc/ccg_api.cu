@@ -89,6 +89,9 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 		cudaEventCreateWithFlags(&ctx->ev_g[k], cudaEventDisableTiming);
 	}
 	ctx->stream = ctx->own_stream;
+	/* tuning knobs for experiments (scripts/one_step.py); unset in normal use */
+	if(getenv("CCG_KSLICES")) ctx->dbg_kslices = atoi(getenv("CCG_KSLICES"));
+	if(getenv("CCG_EXPAND_SERIAL")) ctx->dbg_serial = atoi(getenv("CCG_EXPAND_SERIAL"));
 	*out = ctx;
 	return CCG_OK;
 }
@@ -749,10 +752,15 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		p.row_base = (int) (b * (ctx->x_buf_bytes / 128));
 		p.kslices = choose_split((long long) ctx->sm_count, (long long) cnt, nch, 16, 512);
 		p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
+		if(ctx->dbg_kslices > 0) {
+			p.kslices = ctx->dbg_kslices;
+			p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
+		}
 		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nch) --p.kslices;
 		/* buffer b is free once the GEMM of slab s-2 has read it */
 		if(s >= 2) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b], 0));
-		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + b * ctx->x_buf_bytes, chunk0, nch, nslabs > 1));
+		if(ctx->dbg_serial && s >= 1) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b ^ 1], 0));
+		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + b * ctx->x_buf_bytes, chunk0, nch, nslabs > 1 && !ctx->dbg_serial));
 		CK(ctx, cudaEventRecord(ctx->ev_x[b], ctx->aux_stream));
 		if(s == nslabs - 1) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->aux_stream));
 		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x[b], 0));

@@ -80,6 +80,7 @@ struct ccg_ctx {
 	cudaEvent_t ev_fork, ev_x[2], ev_g[2];
 	int kernel_choice;
 	int rank, world;
+	int dbg_kslices, dbg_serial;   /* CCG_KSLICES / CCG_EXPAND_SERIAL environment overrides (experiments only) */
 
 	int n, len, pair_mode;
 	int words, chunks, n_pad, nplanes;

@@ -120,6 +120,26 @@ def test_global_mode(ctx, elem, scale, norm):
     assert float(D.max()) > 0
 
 
+@pytest.mark.parametrize("kernel", [api.KERNEL_POPC, api.KERNEL_UMMA], ids=["popc", "umma"])
+def test_global_mask_applied_to_a_pair_store(built, kernel):
+    """ccg_apply_global_mask: samples streamed into a pair-mode store first (the dist driver's
+    load loop, cdist.c:55-168), the shared mask ANDed in afterwards, then cmpFsaThrd semantics."""
+    n, length = 140, 4000 + 21
+    codes, seqs, masks, inc = _set(n, length, seed=77, nrun=0.003)
+    include = np.ones(n, dtype=np.uint8)
+    gmask = oracle.global_mask(codes, include)
+    with api.Context() as c:
+        c.set_kernel(kernel)
+        c.set_problem(n, length, pair=True)
+        c.put_samples_packed(seqs, masks)
+        c.apply_global_mask(gmask)
+        D, dn, ginc = c.run_global(include, norm=1000)
+    Do, dno, ginco = oracle.fsa_cmp_global(seqs, gmask, include, length, norm=1000)
+    assert dn == dno == n and ginc == ginco
+    assert np.array_equal(_bits(D), _bits(Do))
+    assert float(D.max()) > 0
+
+
 def test_codes_upload_matches_packed_upload(ctx):
     """Device-side qseq2nibble + initIncPos + getIncPos + getNpos (ccg_put_sample_codes)."""
     n, length = 66, 1000 + 29

@@ -47,7 +47,8 @@ def test_two_ranks_cover_the_triangle_exactly_once(built, n):
     import bench
     from ccphylo_b200 import api
 
-    assert bench.samples_for(1, 1000) == 1000 and bench.samples_for(2, 1000) == 1408
+    assert bench.samples_for(1, 1000) == 1000 and bench.samples_for(2, 1000) == 1000
+    assert bench.samples_for(2, 1000, "weak") == 1408
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
