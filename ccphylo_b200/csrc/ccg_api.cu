@@ -84,14 +84,27 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 	for(int k = 0; k < 4; ++k) cudaEventCreate(&ctx->ev_phase[k]);
 	cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
 	cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->ev_launch, cudaEventDisableTiming);
 	for(int k = 0; k < 2; ++k) {
 		cudaEventCreateWithFlags(&ctx->ev_x[k], cudaEventDisableTiming);
 		cudaEventCreateWithFlags(&ctx->ev_g[k], cudaEventDisableTiming);
 	}
 	ctx->stream = ctx->own_stream;
+	{
+		/* stream memory operations: let the aux stream wait until the GEMM CTAs are resident */
+		void *fn = 0;
+		cudaDriverEntryPointQueryResult qres;
+		if(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+		   qres == cudaDriverEntryPointSuccess && !getenv("CCG_NOGATE"))
+			ctx->fn_wait_value = fn;
+		else cudaGetLastError();
+		if(cudaMalloc(&ctx->d_resident, sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); ctx->d_resident = 0; }
+	}
 	/* tuning knobs for experiments (scripts/one_step.py); unset in normal use */
 	if(getenv("CCG_KSLICES")) ctx->dbg_kslices = atoi(getenv("CCG_KSLICES"));
 	if(getenv("CCG_EXPAND_SERIAL")) ctx->dbg_serial = atoi(getenv("CCG_EXPAND_SERIAL"));
+	if(getenv("CCG_NOLOCK")) ctx->dbg_nolock = atoi(getenv("CCG_NOLOCK"));
+	if(getenv("CCG_UMMA1")) ctx->dbg_umma1 = atoi(getenv("CCG_UMMA1"));
 	*out = ctx;
 	return CCG_OK;
 }
@@ -122,12 +135,15 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	cudaFree(ctx->d_acc);
 	cudaFree(ctx->d_tickets);
 	cudaFree(ctx->d_tiles);
+	cudaFree(ctx->d_sync);
+	cudaFree(ctx->d_resident);
 	cudaFree(ctx->d_out_D);
 	cudaFree(ctx->d_out_N);
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	for(int k = 0; k < 4; ++k) cudaEventDestroy(ctx->ev_phase[k]);
 	cudaEventDestroy(ctx->ev_fork);
+	cudaEventDestroy(ctx->ev_launch);
 	for(int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_x[k]); cudaEventDestroy(ctx->ev_g[k]); }
 	cudaStreamSynchronize(ctx->aux_stream);
 	cudaStreamDestroy(ctx->aux_stream);
@@ -179,8 +195,8 @@ extern "C" int ccg_set_partition(ccg_ctx *ctx, int rank, int world) {
 extern "C" int ccg_tile_rows(void) { return CCG_UMMA_BM; }
 extern "C" int ccg_tile_cols(void) { return CCG_UMMA_BN; }
 
-/* The deal: macro tiles (tm, tn <= tm/2) are ordered along a Z-order (Morton) curve over
- * (256-row band, 256-column panel) and cut into `world` contiguous runs of equal estimated
+/* The deal: macro tiles (tm, tn <= tm) of 256 x 256 samples are ordered along a Z-order (Morton)
+ * curve and cut into `world` contiguous runs of equal estimated
  * cost.  A run is a compact 2-D region, so a rank touches only O(sqrt(tiles)) row blocks: that
  * is what keeps the per-rank encode / expansion work from being replicated on every GPU. */
 static inline unsigned long long spread_bits(unsigned x) {
@@ -202,9 +218,9 @@ static void macro_tiles_sorted(int n, std::vector<MacroTile> &out) {
 	const int TM = (n + CCG_UMMA_BM - 1) / CCG_UMMA_BM;
 	out.clear();
 	for(int tm = 0; tm < TM; ++tm)
-		for(int tn = 0; 2 * tn <= tm; ++tn) {
+		for(int tn = 0; tn <= tm; ++tn) {
 			MacroTile t;
-			t.key = ((((spread_bits((unsigned) (tm >> 1)) << 1) | spread_bits((unsigned) tn))) << 1) | (unsigned) (tm & 1);
+			t.key = (spread_bits((unsigned) tm) << 1) | spread_bits((unsigned) tn);
 			t.tm = tm;
 			t.tn = tn;
 			out.push_back(t);
@@ -214,8 +230,8 @@ static void macro_tiles_sorted(int n, std::vector<MacroTile> &out) {
 
 /* Cost of giving one rank the curve segment [lo, hi): its macro tiles (GEMM time) plus the row
  * blocks they read (encode + expansion time of those 128 samples).  Measured on B200 at 5 Mbp:
- * 0.39 ms per tile, 0.58 ms per row block -> 1.5 tiles per block. */
-static const double kRowBlockCost = 1.5;
+ * 0.78 ms per 256 x 256 tile, 0.58 ms per row block -> 0.75 tiles per block. */
+static const double kRowBlockCost = 0.75;
 
 /* greedy walk along the curve: how many segments of cost <= cap are needed; optionally records cuts */
 static int segments_for_cap(const std::vector<MacroTile> &t, int nblocks, double cap, std::vector<long long> *cuts) {
@@ -224,21 +240,20 @@ static int segments_for_cap(const std::vector<MacroTile> &t, int nblocks, double
 	double cost = 0.0;
 	if(cuts) { cuts->clear(); cuts->push_back(0); }
 	for(size_t k = 0; k < t.size(); ++k) {
-		const int blk[3] = {t[k].tm, 2 * t[k].tn, 2 * t[k].tn + 1};
+		const int blk[4] = {2 * t[k].tm, 2 * t[k].tm + 1, 2 * t[k].tn, 2 * t[k].tn + 1};
+		const int nb = t[k].tm == t[k].tn ? 2 : 4;              /* a diagonal tile reads two blocks */
 		double add = 1.0;
-		for(int q = 0; q < 3; ++q)
+		for(int q = 0; q < nb; ++q)
 			if(blk[q] < nblocks && stamp[(size_t) blk[q]] != seg) add += kRowBlockCost;
 		if(cost > 0.0 && cost + add > cap) {
 			++seg;
 			cost = 0.0;
 			if(cuts) cuts->push_back((long long) k);
 			add = 1.0;
-			for(int q = 0; q < 3; ++q)
+			for(int q = 0; q < nb; ++q)
 				if(blk[q] < nblocks) add += kRowBlockCost;
-			/* blocks shared inside this tile are counted once below */
-			if(blk[1] == blk[0] || blk[2] == blk[0]) add -= kRowBlockCost;
 		}
-		for(int q = 0; q < 3; ++q)
+		for(int q = 0; q < nb; ++q)
 			if(blk[q] < nblocks) stamp[(size_t) blk[q]] = seg;
 		cost += add;
 	}
@@ -278,15 +293,15 @@ static long long for_each_macro_tile(int n, int rank, int world, F f) {
 	return hi - lo;
 }
 
-/* row blocks (128 slots) the owned macro tiles read: A rows tm, B rows 2tn and 2tn+1 */
+/* row blocks (128 slots) the owned macro tiles read: A rows 2tm, 2tm+1, B rows 2tn, 2tn+1 */
 static void update_need(ccg_ctx *ctx) {
 	if(!ctx->need) return;
 	const int nblocks = ctx->n_pad / 128;
 	memset(ctx->need, 0, (size_t) nblocks);
 	for_each_macro_tile(ctx->n, ctx->rank, ctx->world, [&](int tm, int tn) {
-		if(tm < nblocks) ctx->need[tm] = 1;
-		if(2 * tn < nblocks) ctx->need[2 * tn] = 1;
-		if(2 * tn + 1 < nblocks) ctx->need[2 * tn + 1] = 1;
+		const int blk[4] = {2 * tm, 2 * tm + 1, 2 * tn, 2 * tn + 1};
+		for(int q = 0; q < 4; ++q)
+			if(blk[q] < nblocks) ctx->need[blk[q]] = 1;
 	});
 }
 
@@ -657,24 +672,36 @@ static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
 	return CCG_OK;
 }
 
-static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
-	const int n = ctx->n;
+/* uploads this rank's macro tiles to d_tiles[0, cnt) and, behind them, their 128-row halves
+ * (2tm, tn), (2tm+1, tn) for the kernels that work on 128 x 256 tiles: d_tiles[cnt, 3 cnt) */
+static int upload_macro_tiles(ccg_ctx *ctx, size_t *cnt_out) {
 	size_t cap = 0;
-	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int, int) { ++cap; });
-	int2 *host = (int2 *) malloc((cap ? cap : 1) * sizeof(int2));
+	for_each_macro_tile(ctx->n, ctx->rank, ctx->world, [&](int, int) { ++cap; });
+	int2 *host = (int2 *) malloc((cap ? 3 * cap : 1) * sizeof(int2));
 	if(!host) return CCG_ERR_NOMEM;
 	size_t cnt = 0;
-	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int tm, int tn) {
+	for_each_macro_tile(ctx->n, ctx->rank, ctx->world, [&](int tm, int tn) {
 		host[cnt].x = tm;
 		host[cnt].y = tn;
+		host[cap + 2 * cnt].x = 2 * tm;
+		host[cap + 2 * cnt].y = tn;
+		host[cap + 2 * cnt + 1].x = 2 * tm + 1;
+		host[cap + 2 * cnt + 1].y = tn;
 		++cnt;
 	});
+	*cnt_out = cnt;
+	int rc = cnt ? ensure_tiles(ctx, host, 3 * cnt) : CCG_OK;
+	free(host);
+	return rc;
+}
+
+static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
+	size_t cnt = 0;
+	int rc = upload_macro_tiles(ctx, &cnt);
+	if(rc) return rc;
 	ctx->last_ntiles = (int) cnt;
 	ctx->last_kernel_kind = CCG_KERNEL_UMMA;
-	if(cnt == 0) { free(host); return CCG_OK; }
-	int rc = ensure_tiles(ctx, host, cnt);
-	free(host);
-	if(rc) return rc;
+	if(cnt == 0) return CCG_OK;
 
 	/* dense int32 accumulators S and I */
 	size_t c_bytes = (size_t) 2 * ctx->n_pad * ctx->n_pad * sizeof(int);
@@ -740,6 +767,14 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	p.C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
 	p.ldc = ctx->n_pad;
 	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	/* The expansion of slab s+1 runs beside the GEMM of slab s.  It must not start before every
+	 * (persistent) GEMM CTA holds its SM, or expansion blocks can fill an SM and keep a GEMM CTA
+	 * out for milliseconds while all others wait for it in lock-step: the GEMM CTAs count
+	 * themselves in d_resident (monotonic over the run) and the aux stream waits for the count. */
+	const bool gate = ctx->fn_wait_value && ctx->d_resident && nslabs > 1;
+	if(gate) CK(ctx, cudaMemsetAsync(ctx->d_resident, 0, sizeof(unsigned), ctx->stream));
+	p.resident = gate ? ctx->d_resident : 0;
+	unsigned resident_target = 0;
 	CK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
 	CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
 	CK(ctx, cudaEventRecord(ctx->ev_phase[0], ctx->aux_stream));
@@ -750,7 +785,12 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		if(nch > slab) nch = (int) slab;
 		p.slab_chunks = nch;
 		p.row_base = (int) (b * (ctx->x_buf_bytes / 128));
-		p.kslices = choose_split((long long) ctx->sm_count, (long long) cnt, nch, 16, 512);
+		if(ctx->dbg_umma1) {
+			p.single = 1;
+			p.ntiles = (int) (2 * cnt);
+			p.tiles = ctx->d_tiles + cnt;
+		}
+		p.kslices = choose_split((long long) (p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx)), (long long) p.ntiles, nch, 16, 512);
 		p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
 		if(ctx->dbg_kslices > 0) {
 			p.kslices = ctx->dbg_kslices;
@@ -760,45 +800,49 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		/* buffer b is free once the GEMM of slab s-2 has read it */
 		if(s >= 2) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b], 0));
 		if(ctx->dbg_serial && s >= 1) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b ^ 1], 0));
+		if(gate && s >= 1) {
+			typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+			/* ev_launch: the GEMM of slab s-1 has been handed to the device queue */
+			CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_launch, 0));
+			CUresult r = ((WaitValueFn) ctx->fn_wait_value)((CUstream) ctx->aux_stream, (CUdeviceptr) ctx->d_resident,
+			                                                resident_target, CU_STREAM_WAIT_VALUE_GEQ);
+			if(r != CUDA_SUCCESS) {
+				set_err(ctx, "cuStreamWaitValue32 failed with CUresult %d", (int) r);
+				return CCG_ERR_CUDA;
+			}
+		}
 		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + b * ctx->x_buf_bytes, chunk0, nch, nslabs > 1 && !ctx->dbg_serial));
 		CK(ctx, cudaEventRecord(ctx->ev_x[b], ctx->aux_stream));
 		if(s == nslabs - 1) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->aux_stream));
 		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x[b], 0));
 		if(s == 0) CK(ctx, cudaEventRecord(ctx->ev_phase[2], ctx->stream));
+		if(gate) CK(ctx, cudaEventRecord(ctx->ev_launch, ctx->stream));     /* everything before the GEMM of slab s */
 		CK(ctx, ccg_launch_umma(ctx, p));
+		resident_target += (unsigned) ctx->last_gemm_ctas;
 		CK(ctx, cudaEventRecord(ctx->ev_g[b], ctx->stream));
 	}
 	CK(ctx, cudaEventRecord(ctx->ev_phase[3], ctx->stream));
 	ctx->phase_valid = 1;
 	/* shared-mask mode: every position of every chunk counts as included in the raw product */
 	const int i_const = ctx->chunks * CCG_CHUNK_BASES;
+	p.ntiles = (int) cnt;
+	p.tiles = ctx->d_tiles;
 	CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, i_const));
 	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 	ctx->ev_valid = 1;
-	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_umma tiles=%d kslices=%d slabs=%d", p.ntiles,
-	         p.kslices, nslabs);
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_umma%s tiles=%d kslices=%d slabs=%d",
+	         ctx->dbg_umma1 ? "" : "2", p.ntiles, p.kslices, nslabs);
 	return CCG_OK;
 }
 
 /* tensor path with the operand expansion fused into the GEMM: no panel, no slabs */
 static int run_fused(ccg_ctx *ctx, const EpilogueParams &ep) {
-	const int n = ctx->n;
-	size_t cap = 0;
-	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int, int) { ++cap; });
-	int2 *host = (int2 *) malloc((cap ? cap : 1) * sizeof(int2));
-	if(!host) return CCG_ERR_NOMEM;
 	size_t cnt = 0;
-	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int tm, int tn) {
-		host[cnt].x = tm;
-		host[cnt].y = tn;
-		++cnt;
-	});
+	int rc = upload_macro_tiles(ctx, &cnt);
+	if(rc) return rc;
 	ctx->last_ntiles = (int) cnt;
 	ctx->last_kernel_kind = CCG_KERNEL_FUSED;
-	if(cnt == 0) { free(host); return CCG_OK; }
-	int rc = ensure_tiles(ctx, host, cnt);
-	free(host);
-	if(rc) return rc;
+	if(cnt == 0) return CCG_OK;
 
 	size_t c_bytes = (size_t) 2 * ctx->n_pad * ctx->n_pad * sizeof(int);
 	if(ctx->c_bytes < c_bytes) {
@@ -822,7 +866,10 @@ static int run_fused(ccg_ctx *ctx, const EpilogueParams &ep) {
 	p.C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
 	p.ldc = ctx->n_pad;
 	p.slab_chunks = ctx->chunks;
-	p.kslices = choose_split((long long) ctx->sm_count, (long long) cnt, ctx->chunks, 16, 1024);
+	/* the fused kernel works on the 128 x 256 halves of the macro tiles */
+	p.ntiles = (int) (2 * cnt);
+	p.tiles = ctx->d_tiles + cnt;
+	p.kslices = choose_split((long long) ctx->sm_count, (long long) p.ntiles, ctx->chunks, 16, 1024);
 	p.chunks_per_slice = (ctx->chunks + p.kslices - 1) / p.kslices;
 	while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= ctx->chunks) --p.kslices;
 	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -830,6 +877,8 @@ static int run_fused(ccg_ctx *ctx, const EpilogueParams &ep) {
 	CK(ctx, ccg_launch_fused(ctx, p));
 	CK(ctx, cudaEventRecord(ctx->ev_phase[3], ctx->stream));
 	ctx->phase_valid = 1;
+	p.ntiles = (int) cnt;
+	p.tiles = ctx->d_tiles;
 	CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, ctx->chunks * CCG_CHUNK_BASES));
 	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 	ctx->ev_valid = 1;

@@ -18,9 +18,9 @@
  * is a 128-bit vector, and a [KC chunks][planes][64 slots][4] box is a single
  * TMA tile.
  *
- * Work partition (both compare kernels): the lower triangle is cut into macro
- * tiles of CCG_UMMA_BM rows x CCG_UMMA_BN columns, enumerated row-major over
- * (tm, tn <= tm/2); macro tile id % world == rank is owned by `rank`.
+ * Work partition (all compare kernels): the lower triangle is cut into macro
+ * tiles of CCG_UMMA_BM rows x CCG_UMMA_BN columns (tm, tn <= tm), ordered along
+ * a Z-order curve that is cut into `world` contiguous cost-balanced runs.
  */
 #ifndef CCG_INTERNAL_H
 #define CCG_INTERNAL_H
@@ -34,7 +34,7 @@
 #define CCG_TILE 64          /* samples per tile edge (popc kernel) */
 #define CCG_CHUNK_WORDS 4    /* u32 words per plane per chunk */
 #define CCG_CHUNK_BASES 128
-#define CCG_UMMA_BM 128      /* macro tile rows    (tcgen05 M, TMEM lanes) */
+#define CCG_UMMA_BM 256      /* macro tile rows    (tcgen05 M = 256 over a CTA pair: 2 x 128 TMEM lanes) */
 #define CCG_UMMA_BN 256      /* macro tile columns (tcgen05 N) */
 #define CCG_SLOT_PAD 256     /* slots are padded to a multiple of this */
 
@@ -70,6 +70,10 @@ struct UmmaParams {
 	int *C_S, *C_I;        /* dense [n_pad][ldc] int32 accumulators */
 	int ldc;
 	int row_base;          /* first 128-byte row of this slab's buffer inside the panel allocation */
+	unsigned *sync;        /* lock-step epoch counters [rounds][epochs_per_item] (zeroed), or NULL */
+	int epochs_per_item;
+	unsigned *resident;    /* every CTA adds 1 once it holds its SM (gates the overlapped expansion), or NULL */
+	int single;            /* tiles are 128 x 256 and run on the single-CTA kernel (CCG_UMMA1=1, experiments) */
 };
 
 struct ccg_ctx {
@@ -77,10 +81,10 @@ struct ccg_ctx {
 	int sm_count;
 	cudaStream_t own_stream, stream;
 	cudaStream_t aux_stream;   /* operand expansion of slab s+1 runs here, under the GEMM of slab s */
-	cudaEvent_t ev_fork, ev_x[2], ev_g[2];
+	cudaEvent_t ev_fork, ev_launch, ev_x[2], ev_g[2];
 	int kernel_choice;
 	int rank, world;
-	int dbg_kslices, dbg_serial;   /* CCG_KSLICES / CCG_EXPAND_SERIAL environment overrides (experiments only) */
+	int dbg_kslices, dbg_serial, dbg_nolock, dbg_umma1;   /* CCG_KSLICES / CCG_EXPAND_SERIAL / CCG_NOLOCK / CCG_UMMA1 overrides (experiments only) */
 
 	int n, len, pair_mode;
 	int words, chunks, n_pad, nplanes;
@@ -119,6 +123,12 @@ struct ccg_ctx {
 	int *d_C;                  /* 2 x [n_pad][n_pad] int32 */
 	size_t c_bytes;
 	size_t x_budget;           /* max bytes for d_X (0 = default) */
+	int last_gemm_ctas;        /* CTAs of the last GEMM launch */
+	unsigned *d_resident;      /* running count of GEMM CTAs that became resident during this run */
+	void *fn_wait_value;       /* cuStreamWaitValue32, or NULL when stream memory operations are unavailable */
+	int max_pairs;             /* CTA pairs of k_pairdist_umma2 that can be resident at once (0 = not queried) */
+	unsigned *d_sync;          /* lock-step epoch counters of the persistent GEMM */
+	size_t sync_cap;
 
 	CUtensorMap tmap;          /* planes as a 4-D tensor, box [4 chunks][planes][64 slots][4] (POPC kernel) */
 	CUtensorMap tmap_pl;       /* same tensor, box [1 chunk][planes][128 slots][4] (fused tensor kernel) */
@@ -151,6 +161,7 @@ int ccg_popc_kc(void);
 /* k_pairdist_umma.cu */
 cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks, int bounded);
 cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
+int ccg_umma_pair_slots(ccg_ctx *ctx);
 cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);
 cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc);
 

@@ -28,7 +28,7 @@
 
 namespace {
 
-constexpr int BM = CCG_UMMA_BM;
+constexpr int BM = 128;              /* this kernel works on 128 x 256 halves of the macro tiles */
 constexpr int BN = CCG_UMMA_BN;
 constexpr int BK = 128;
 constexpr int OP_STAGES = 3;

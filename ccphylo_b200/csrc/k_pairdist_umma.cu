@@ -21,19 +21,23 @@
  * one 128-byte channel row = one SWIZZLE_128B row = one pipeline stage.
  *
  * GEMM work item = (tile of 128 rows x 256 columns of the lower triangle,
- * K slice of chunks).  Warp 0 lane 0 issues TMA (A: 128x128 B, B: 2 x 128x128 B
+ * K slice of chunks); the kernel is persistent (one CTA per SM looping over items) and the CTAs
+ * of a round are throttled into lock-step so that shared operand rows are served by L2.  Warp 0 lane 0 issues TMA (A: 128x128 B, B: 2 x 128x128 B
  * per stage, 4 stages); warp 1 lane 0 issues tcgen05.mma kind::i8 M=128 N=256
  * K=32 (4 per stage) into two TMEM accumulators (S: channels 0-2, I: channel 3);
  * warps 2-5 drain TMEM with tcgen05.ld and RED.ADD the int32 partials into the
  * dense C buffers (split-K is exact for integers).  k_finalize applies
  * (3I-S)/4 and the reference epilogue.
  */
+#include <string.h>
+
 #include "ccg_internal.h"
 #include "epilogue.cuh"
 
 namespace {
 
-constexpr int BM = CCG_UMMA_BM;      /* 128 rows  (A tile, TMEM lanes) */
+constexpr int BMT = CCG_UMMA_BM;     /* 256 rows of a macro tile = one CTA pair (2 x 128 TMEM lanes) */
+constexpr int BM = 128;              /* rows per CTA (A tile, TMEM lanes) */
 constexpr int BN = CCG_UMMA_BN;      /* 256 cols  (B tile, TMEM columns per accumulator) */
 constexpr int BK = 128;              /* K bytes per stage = one channel row of a chunk */
 constexpr int STAGES = 4;
@@ -155,16 +159,45 @@ k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slot0,
 		 * 128 rows x 128 B box a TMA load fetches is 16 KiB contiguous */
 		const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) cl * 4) * 128 + (slot & 127);
 		uint4 *dst = reinterpret_cast<uint4 *>(X + tile_row * 128 + seg * 16);
-		dst[0 * 1024] = make_uint4(c0[0], c0[1], c0[2], c0[3]);   /* channel rows are 128 x 128 B = 1024 uint4 apart */
-		dst[1 * 1024] = make_uint4(c1[0], c1[1], c1[2], c1[3]);
-		dst[2 * 1024] = make_uint4(c2[0], c2[1], c2[2], c2[3]);
-		dst[3 * 1024] = make_uint4(c3[0], c3[1], c3[2], c3[3]);
+		/* channel rows are 128 x 128 B = 1024 uint4 apart; streaming stores: the panel is far larger
+		 * than L2 and must not evict the working set of a GEMM running beside this kernel */
+		__stcs(dst + 0 * 1024, make_uint4(c0[0], c0[1], c0[2], c0[3]));
+		__stcs(dst + 1 * 1024, make_uint4(c1[0], c1[1], c1[2], c1[3]));
+		__stcs(dst + 2 * 1024, make_uint4(c2[0], c2[1], c2[2], c2[3]));
+		__stcs(dst + 3 * 1024, make_uint4(c3[0], c3[1], c3[2], c3[3]));
 	}
 }
 
 /* ------------------------------------------------------------------ */
 /* the GEMM                                                            */
 /* ------------------------------------------------------------------ */
+/* Lock-step throttle.  The CTAs of one round work on neighbouring tiles of the Z-order curve and
+ * read the same operand row blocks; that reuse only reaches L2 (instead of HBM) while they are at
+ * nearly the same K position.  Left alone they drift apart -- at 10,000 x 5 Mbp the panel was read
+ * 33 times from HBM and the kernel ran at the HBM roof (profiles/r01_umma_10k_dram_bound.csv).
+ * Every LOCK_E stages a producer announces the epoch it enters and waits (bounded) until every
+ * CTA of the round has entered epoch - LOCK_LAG.  The wait is a throttle, not a correctness
+ * barrier: on time-out the CTA simply proceeds. */
+constexpr int LOCK_E = 8;
+constexpr int LOCK_LAG = 2;
+
+__device__ __forceinline__ void lockstep_arrive(unsigned *sync, long long g) { atomicAdd(sync + g, 1u); }
+/* returns false on time-out (some CTA of the round is far behind or not resident): the caller then
+ * runs LOCK_BACKOFF epochs unthrottled before it waits again */
+constexpr int LOCK_BACKOFF = 64;
+__device__ __forceinline__ bool lockstep_wait(const unsigned *sync, long long g, unsigned expected) {
+	const volatile unsigned *c = sync + g;
+	if(*c >= expected) return true;
+	const long long t0 = clock64();
+	while(*c < expected) {
+		if(clock64() - t0 > 200000LL) return false;     /* ~0.1 ms */
+	}
+	return true;
+}
+
+/* Persistent: gridDim.x CTAs (one per SM); CTA b handles work items b, b + grid, b + 2 grid, ...
+ * Work item w = (tile w % ntiles, K slice w / ntiles), so the items of one round are consecutive
+ * tiles of the curve on the same K range. */
 __global__ void __launch_bounds__(THREADS, 1)
 k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 	extern __shared__ uint8_t smem_raw[];
@@ -172,19 +205,15 @@ k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 	const uint32_t base = (raw + 1023u) & ~1023u;                /* SWIZZLE_128B tiles need 1024-byte alignment */
 	const uint32_t bar_full = base + STAGES * STAGE_BYTES;       /* STAGES x 8 B */
 	const uint32_t bar_empty = bar_full + 8 * STAGES;            /* STAGES x 8 B */
-	const uint32_t bar_accum = bar_empty + 8 * STAGES;           /* 8 B */
-	const uint32_t tmem_slot = bar_accum + 8;                    /* 4 B */
+	const uint32_t bar_accum = bar_empty + 8 * STAGES;           /* 8 B: accumulators of the item complete */
+	const uint32_t bar_tfree = bar_accum + 8;                    /* 8 B: TMEM drained, next item may accumulate */
+	const uint32_t tmem_slot = bar_tfree + 8;                    /* 4 B */
 	volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int tile = blockIdx.x % p.ntiles;
-	const int ks = blockIdx.x / p.ntiles;
-	const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
-	const int c_begin = ks * p.chunks_per_slice;
-	int nchunk = p.slab_chunks - c_begin;
-	if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
-	if(nchunk < 0) nchunk = 0;
-	const int nkb = nchunk * 4;                                   /* k-blocks: 4 channel rows per chunk */
+	const int G = (int) gridDim.x;
+	const int items = p.ntiles * p.kslices;
+	const int nkb_slab = p.slab_chunks * 4;
 
 	if(threadIdx.x == 0) {
 		for(int s = 0; s < STAGES; ++s) {
@@ -192,6 +221,7 @@ k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 			mbar_init(bar_empty + 8 * s, 1);
 		}
 		mbar_init(bar_accum, 1);
+		mbar_init(bar_tfree, 4);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
@@ -203,77 +233,326 @@ k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 	__syncthreads();
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 	const uint32_t tmem = *tmem_slot_ptr;
+	if(threadIdx.x == 0 && p.resident) atomicAdd(p.resident, 1u);    /* this CTA holds its SM: see run_umma */
 
 	if(warp == 0) {
 		/* ===== TMA producer ===== */
 		if(lane == 0) {
-			for(int kb = 0; kb < nkb; ++kb) {
-				const int s = kb % STAGES;
-				if(kb >= STAGES) mbar_wait(bar_empty + 8 * s, ((kb / STAGES) - 1) & 1);
-				const uint32_t dst = base + s * STAGE_BYTES;
-				const uint32_t bar = bar_full + 8 * s;
-				/* row coordinate of the 128-row box of row block rb, k-block kabs in the blocked panel */
-				const int kabs = c_begin * 4 + kb;
-				const int nkb_slab = p.slab_chunks * 4;
-				mbar_expect_tx(bar, STAGE_BYTES);
-				tma_load_2d(dst, &tmap, bar, 0, p.row_base + (tm * nkb_slab + kabs) * 128);
-				tma_load_2d(dst + A_BYTES, &tmap, bar, 0, p.row_base + ((2 * tn) * nkb_slab + kabs) * 128);
-				tma_load_2d(dst + A_BYTES + 128 * BK, &tmap, bar, 0, p.row_base + ((2 * tn + 1) * nkb_slab + kabs) * 128);
+			unsigned it = 0;                                      /* stages issued so far, over all items */
+			int round = 0;
+			int lock_skip = 0;
+			for(int w = blockIdx.x; w < items; w += G, ++round) {
+				const int tile = w % p.ntiles, ks = w / p.ntiles;
+				const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
+				const int c_begin = ks * p.chunks_per_slice;
+				int nchunk = p.slab_chunks - c_begin;
+				if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
+				if(nchunk < 0) nchunk = 0;
+				const int nkb = nchunk * 4;                       /* k-blocks: 4 channel rows per chunk */
+				const long long g0 = (long long) round * p.epochs_per_item;
+				for(int kb = 0; kb < nkb; ++kb, ++it) {
+					if(p.sync && (kb % LOCK_E) == 0) {
+						const long long g = g0 + kb / LOCK_E;
+						lockstep_arrive(p.sync, g);
+						if(lock_skip > 0) --lock_skip;
+						else if(g >= LOCK_LAG) {
+							const long long gw = g - LOCK_LAG;
+							const int rw = (int) (gw / p.epochs_per_item);
+							const int left = items - rw * G;
+							if(!lockstep_wait(p.sync, gw, (unsigned) (left < G ? left : G))) lock_skip = LOCK_BACKOFF;
+						}
+					}
+					const int s = it % STAGES;
+					if(it >= STAGES) mbar_wait(bar_empty + 8 * s, ((it / STAGES) - 1) & 1);
+					const uint32_t dst = base + s * STAGE_BYTES;
+					const uint32_t bar = bar_full + 8 * s;
+					/* row coordinate of the 128-row box of row block rb, k-block kabs in the blocked panel */
+					const int kabs = c_begin * 4 + kb;
+					mbar_expect_tx(bar, STAGE_BYTES);
+					tma_load_2d(dst, &tmap, bar, 0, p.row_base + (tm * nkb_slab + kabs) * 128);
+					tma_load_2d(dst + A_BYTES, &tmap, bar, 0, p.row_base + ((2 * tn) * nkb_slab + kabs) * 128);
+					tma_load_2d(dst + A_BYTES + 128 * BK, &tmap, bar, 0, p.row_base + ((2 * tn + 1) * nkb_slab + kabs) * 128);
+				}
+				/* a short (last) K slice still counts in every epoch of its round */
+				if(p.sync)
+					for(int e = (nkb + LOCK_E - 1) / LOCK_E; e < p.epochs_per_item; ++e) lockstep_arrive(p.sync, g0 + e);
 			}
 		}
 	} else if(warp == 1) {
 		/* ===== MMA issuer ===== */
 		if(lane == 0) {
-			uint32_t usedS = 0, usedI = 0;
-			for(int kb = 0; kb < nkb; ++kb) {
-				const int s = kb % STAGES;
-				mbar_wait(bar_full + 8 * s, (kb / STAGES) & 1);
-				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				const uint32_t a0 = base + s * STAGE_BYTES;
-				const uint64_t adesc = make_desc(a0);
-				const uint64_t bdesc = make_desc(a0 + A_BYTES);
-				const bool is_mask = (kb & 3) == 3;
-				const uint32_t d = tmem + (is_mask ? BN : 0);
-#pragma unroll
-				for(int k = 0; k < BK / 32; ++k) {
-					const uint32_t acc = is_mask ? usedI : usedS;
-					/* advancing K by 32 bytes inside the 128-byte swizzle row: +2 in the (addr>>4) field */
-					umma_i8(d, adesc + 2 * k, bdesc + 2 * k, acc);
-					if(is_mask) usedI = 1; else usedS = 1;
+			unsigned it = 0;
+			int round = 0;
+			for(int w = blockIdx.x; w < items; w += G, ++round) {
+				const int ks = w / p.ntiles;
+				const int c_begin = ks * p.chunks_per_slice;
+				int nchunk = p.slab_chunks - c_begin;
+				if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
+				if(nchunk < 0) nchunk = 0;
+				const int nkb = nchunk * 4;
+				if(round > 0) {
+					mbar_wait(bar_tfree, (round - 1) & 1);           /* the previous item's accumulators were read */
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				}
-				umma_commit(bar_empty + 8 * s);        /* frees the stage once these MMAs have read it */
+				uint32_t usedS = 0, usedI = 0;
+				for(int kb = 0; kb < nkb; ++kb, ++it) {
+					const int s = it % STAGES;
+					mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t a0 = base + s * STAGE_BYTES;
+					const uint64_t adesc = make_desc(a0);
+					const uint64_t bdesc = make_desc(a0 + A_BYTES);
+					const bool is_mask = (kb & 3) == 3;
+					const uint32_t d = tmem + (is_mask ? BN : 0);
+#pragma unroll
+					for(int k = 0; k < BK / 32; ++k) {
+						const uint32_t acc = is_mask ? usedI : usedS;
+						/* advancing K by 32 bytes inside the 128-byte swizzle row: +2 in the (addr>>4) field */
+						umma_i8(d, adesc + 2 * k, bdesc + 2 * k, acc);
+						if(is_mask) usedI = 1; else usedS = 1;
+					}
+					umma_commit(bar_empty + 8 * s);        /* frees the stage once these MMAs have read it */
+				}
+				umma_commit(bar_accum);                     /* accumulators of this item complete */
 			}
-			umma_commit(bar_accum);                     /* accumulators complete */
 		}
 	} else {
 		/* ===== epilogue: TMEM -> registers -> RED.ADD into C ===== */
 		const int quarter = warp & 3;                   /* a warp may only touch TMEM lanes 32*(warp%4).. */
-		const int row = tm * BM + quarter * 32 + lane;
-		if(nkb > 0) {
-			mbar_wait(bar_accum, 0);
+		int round = 0;
+		for(int w = blockIdx.x; w < items; w += G, ++round) {
+			const int tile = w % p.ntiles, ks = w / p.ntiles;
+			const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
+			const int nleft = p.slab_chunks - ks * p.chunks_per_slice;
+			const int row = tm * BM + quarter * 32 + lane;
+			mbar_wait(bar_accum, round & 1);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-			int *cS = p.C_S + (size_t) row * p.ldc + tn * BN;
-			int *cI = p.C_I + (size_t) row * p.ldc + tn * BN;
-			const int jlim = row - tn * BN;              /* only columns j < row are ever read back */
+			if(nleft > 0) {
+				int *cS = p.C_S + (size_t) row * p.ldc + tn * BN;
+				int *cI = p.C_I + (size_t) row * p.ldc + tn * BN;
+				const int jlim = row - tn * BN;              /* only columns j < row are ever read back */
 #pragma unroll 1
-			for(int cb = 0; cb < BN / 32; ++cb) {
-				if(__all_sync(0xffffffffu, cb * 32 >= jlim)) break;
-				uint32_t r[32];
-				tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + cb * 32, r);
+				for(int cb = 0; cb < BN / 32; ++cb) {
+					if(__all_sync(0xffffffffu, cb * 32 >= jlim)) break;
+					uint32_t r[32];
+					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + cb * 32, r);
 #pragma unroll
-				for(int e = 0; e < 32; ++e)
-					if(cb * 32 + e < jlim && r[e]) atomicAdd(cS + cb * 32 + e, (int) r[e]);
-				tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + BN + cb * 32, r);
+					for(int e = 0; e < 32; ++e)
+						if(cb * 32 + e < jlim && r[e]) atomicAdd(cS + cb * 32 + e, (int) r[e]);
+					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + BN + cb * 32, r);
 #pragma unroll
-				for(int e = 0; e < 32; ++e)
-					if(cb * 32 + e < jlim && r[e]) atomicAdd(cI + cb * 32 + e, (int) r[e]);
+					for(int e = 0; e < 32; ++e)
+						if(cb * 32 + e < jlim && r[e]) atomicAdd(cI + cb * 32 + e, (int) r[e]);
+				}
 			}
+			/* all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32) */
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+			__syncwarp();
+			if(lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree) : "memory");
 		}
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
 	if(warp == 2) {
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+	}
+}
+
+/* ------------------------------------------------------------------ */
+/* the GEMM on CTA pairs (cta_group::2)                                */
+/* ------------------------------------------------------------------ */
+/* A cluster of two CTAs (one TPC) owns a 256 x 256 macro tile: tcgen05.mma.cta_group::2 with
+ * M = 256, N = 256.  CTA r of the pair stages A rows [128 r, 128 r + 128) and B columns
+ * [128 r, 128 r + 128) of the tile -- 32 KiB per stage instead of 48 KiB, so six stages fit and
+ * each SM needs one third less L2 bandwidth for the same tensor work (the single-CTA kernel
+ * above was limited by bytes in flight: 72-84 % tensor-pipe activity).  Both CTAs issue TMA,
+ * all loads of a stage complete on the leader's full barrier; the leader (cluster rank 0)
+ * issues the MMAs and its commits arrive on both CTAs' empty / accumulator barriers. */
+constexpr int STAGES2 = 6;
+constexpr int B2_BYTES = 128 * BK;
+constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;              /* per CTA */
+constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (256 >> 4) << 24);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                   /* shared::cluster address of the even CTA of the pair */
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+	    ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+	    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+	             ::"r"(bar), "h"((uint16_t) 3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t raw = smem_u32(smem_raw);
+	const uint32_t base = (raw + 1023u) & ~1023u;
+	const uint32_t bar_full = base + STAGES2 * STAGE2_BYTES;     /* used on the leader only */
+	const uint32_t bar_empty = bar_full + 8 * STAGES2;
+	const uint32_t bar_accum = bar_empty + 8 * STAGES2;
+	const uint32_t bar_tfree = bar_accum + 8;                    /* used on the leader only: 8 epilogue warps */
+	const uint32_t tmem_slot = bar_tfree + 8;
+	volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t cta_rank;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+	const int G = (int) (gridDim.x >> 1);                        /* clusters */
+	const int cid = (int) (blockIdx.x >> 1);
+	const int items = p.ntiles * p.kslices;
+	const int nkb_slab = p.slab_chunks * 4;
+
+	if(threadIdx.x == 0) {
+		for(int s = 0; s < STAGES2; ++s) {
+			mbar_init(bar_full + 8 * s, 1);
+			mbar_init(bar_empty + 8 * s, 1);
+		}
+		mbar_init(bar_accum, 1);
+		mbar_init(bar_tfree, 8);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	if(warp == 2) {
+		asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	cluster_sync_all();                                          /* both CTAs' barriers and TMEM are ready */
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem = *tmem_slot_ptr;
+	if(threadIdx.x == 0 && p.resident) atomicAdd(p.resident, 1u);
+
+	if(warp == 0) {
+		/* ===== TMA producer (both CTAs) ===== */
+		if(lane == 0) {
+			unsigned it = 0;
+			int round = 0;
+			int lock_skip = 0;
+			for(int w = cid; w < items; w += G, ++round) {
+				const int tile = w % p.ntiles, ks = w / p.ntiles;
+				const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
+				const int c_begin = ks * p.chunks_per_slice;
+				int nchunk = p.slab_chunks - c_begin;
+				if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
+				if(nchunk < 0) nchunk = 0;
+				const int nkb = nchunk * 4;
+				const long long g0 = (long long) round * p.epochs_per_item;
+				const int rbA = 2 * tm + (int) cta_rank, rbB = 2 * tn + (int) cta_rank;
+				for(int kb = 0; kb < nkb; ++kb, ++it) {
+					if(p.sync && cta_rank == 0 && (kb % LOCK_E) == 0) {
+						const long long g = g0 + kb / LOCK_E;
+						lockstep_arrive(p.sync, g);
+						if(lock_skip > 0) --lock_skip;
+						else if(g >= LOCK_LAG) {
+							const long long gw = g - LOCK_LAG;
+							const int rw = (int) (gw / p.epochs_per_item);
+							const int left = items - rw * G;
+							if(!lockstep_wait(p.sync, gw, (unsigned) (left < G ? left : G))) lock_skip = LOCK_BACKOFF;
+						}
+					}
+					const int s = it % STAGES2;
+					if(it >= STAGES2) mbar_wait(bar_empty + 8 * s, ((it / STAGES2) - 1) & 1);
+					const uint32_t dst = base + s * STAGE2_BYTES;
+					const uint32_t bar = (bar_full + 8 * s) & PEER_MASK;      /* the leader's barrier */
+					const int kabs = c_begin * 4 + kb;
+					if(cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE2_BYTES);
+					tma_load_2d_pair(dst, &tmap, bar, 0, p.row_base + (rbA * nkb_slab + kabs) * 128);
+					tma_load_2d_pair(dst + A_BYTES, &tmap, bar, 0, p.row_base + (rbB * nkb_slab + kabs) * 128);
+				}
+				if(p.sync && cta_rank == 0)
+					for(int e = (nkb + LOCK_E - 1) / LOCK_E; e < p.epochs_per_item; ++e) lockstep_arrive(p.sync, g0 + e);
+			}
+		}
+	} else if(warp == 1) {
+		/* ===== MMA issuer (leader CTA only) ===== */
+		if(lane == 0 && cta_rank == 0) {
+			unsigned it = 0;
+			int round = 0;
+			for(int w = cid; w < items; w += G, ++round) {
+				const int ks = w / p.ntiles;
+				const int c_begin = ks * p.chunks_per_slice;
+				int nchunk = p.slab_chunks - c_begin;
+				if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
+				if(nchunk < 0) nchunk = 0;
+				const int nkb = nchunk * 4;
+				if(round > 0) {
+					mbar_wait(bar_tfree, (round - 1) & 1);
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				}
+				uint32_t usedS = 0, usedI = 0;
+				for(int kb = 0; kb < nkb; ++kb, ++it) {
+					const int s = it % STAGES2;
+					mbar_wait(bar_full + 8 * s, (it / STAGES2) & 1);
+					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+					const uint32_t a0 = base + s * STAGE2_BYTES;
+					const uint64_t adesc = make_desc(a0);
+					const uint64_t bdesc = make_desc(a0 + A_BYTES);
+					const bool is_mask = (kb & 3) == 3;
+					const uint32_t d = tmem + (is_mask ? BN : 0);
+#pragma unroll
+					for(int k = 0; k < BK / 32; ++k) {
+						const uint32_t acc = is_mask ? usedI : usedS;
+						umma2_i8(d, adesc + 2 * k, bdesc + 2 * k, acc);
+						if(is_mask) usedI = 1; else usedS = 1;
+					}
+					umma2_commit(bar_empty + 8 * s);       /* frees the stage in both CTAs */
+				}
+				umma2_commit(bar_accum);                    /* both CTAs' epilogues may read their TMEM half */
+			}
+		}
+	} else {
+		/* ===== epilogue (both CTAs): TMEM -> registers -> RED.ADD into C ===== */
+		const int quarter = warp & 3;
+		uint32_t leader_tfree;
+		asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(leader_tfree) : "r"(bar_tfree));
+		int round = 0;
+		for(int w = cid; w < items; w += G, ++round) {
+			const int tile = w % p.ntiles, ks = w / p.ntiles;
+			const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
+			const int nleft = p.slab_chunks - ks * p.chunks_per_slice;
+			const int row = tm * BMT + (int) cta_rank * 128 + quarter * 32 + lane;
+			mbar_wait(bar_accum, round & 1);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			if(nleft > 0) {
+				int *cS = p.C_S + (size_t) row * p.ldc + tn * BN;
+				int *cI = p.C_I + (size_t) row * p.ldc + tn * BN;
+				const int jlim = row - tn * BN;
+#pragma unroll 1
+				for(int cb = 0; cb < BN / 32; ++cb) {
+					if(__all_sync(0xffffffffu, cb * 32 >= jlim)) break;
+					uint32_t r[32];
+					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + cb * 32, r);
+#pragma unroll
+					for(int e = 0; e < 32; ++e)
+						if(cb * 32 + e < jlim && r[e]) atomicAdd(cS + cb * 32 + e, (int) r[e]);
+					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + BN + cb * 32, r);
+#pragma unroll
+					for(int e = 0; e < 32; ++e)
+						if(cb * 32 + e < jlim && r[e]) atomicAdd(cI + cb * 32 + e, (int) r[e]);
+				}
+			}
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+			__syncwarp();
+			if(lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_tfree) : "memory");
+		}
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	cluster_sync_all();                                          /* the peer's smem / barriers stay alive until both are done */
+	if(warp == 2) {
+		asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 	}
 }
 
@@ -287,8 +566,8 @@ k_finalize_umma(const int *__restrict__ C_S, const int *__restrict__ C_I, int ld
 	const int tile = blockIdx.x;
 	if(tile >= ntiles) return;
 	const int tm = tiles[tile].x, tn = tiles[tile].y;
-	for(int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
-		const int i = tm * BM + e / BN;
+	for(int e = threadIdx.x; e < BMT * BN; e += blockDim.x) {
+		const int i = tm * BMT + e / BN;
 		const int j = tn * BN + e % BN;
 		if(i >= n || j >= i) continue;
 		const int S = C_S[(size_t) i * ldc + j];
@@ -306,8 +585,8 @@ k_gather_raw_dense(const int *__restrict__ C_S, const int *__restrict__ C_I, int
 	const int tile = blockIdx.x;
 	if(tile >= ntiles) return;
 	const int tm = tiles[tile].x, tn = tiles[tile].y;
-	for(int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
-		const int i = tm * BM + e / BN;
+	for(int e = threadIdx.x; e < BMT * BN; e += blockDim.x) {
+		const int i = tm * BMT + e / BN;
 		const int j = tn * BN + e % BN;
 		if(i >= n || j >= i) continue;
 		const int r = rank[i], c = rank[j];
@@ -345,13 +624,66 @@ cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int 
 	return cudaGetLastError();
 }
 
-cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p) {
-	constexpr int smem = STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1) + 16 + 1024;
-	cudaError_t e = cudaFuncSetAttribute(k_pairdist_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+/* CTA pairs of k_pairdist_umma2 that can be resident at once (a pair needs both SMs of a TPC) */
+int ccg_umma_pair_slots(ccg_ctx *ctx) {
+	constexpr int smem2 = STAGES2 * STAGE2_BYTES + 8 * (2 * STAGES2 + 2) + 16 + 1024;
+	if(!ctx->max_pairs) {
+		cudaFuncSetAttribute(k_pairdist_umma2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3((unsigned) (2 * (ctx->sm_count / 2)));
+		cfg.blockDim = dim3(THREADS);
+		cfg.dynamicSmemBytes = smem2;
+		cudaLaunchAttribute attr;
+		attr.id = cudaLaunchAttributeClusterDimension;
+		attr.val.clusterDim.x = 2;
+		attr.val.clusterDim.y = 1;
+		attr.val.clusterDim.z = 1;
+		cfg.attrs = &attr;
+		cfg.numAttrs = 1;
+		int nclusters = 0;
+		if(cudaOccupancyMaxActiveClusters(&nclusters, k_pairdist_umma2, &cfg) != cudaSuccess || nclusters < 1) {
+			cudaGetLastError();
+			nclusters = ctx->sm_count / 2;
+		}
+		ctx->max_pairs = nclusters < ctx->sm_count / 2 ? nclusters : ctx->sm_count / 2;
+	}
+	return ctx->max_pairs;
+}
+
+/* p.tiles: 256 x 256 macro tiles for the CTA-pair kernel; 128 x 256 tiles (p.single != 0) for the
+ * single-CTA kernel */
+cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p_in) {
+	constexpr int smem1 = STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2) + 16 + 1024;
+	constexpr int smem2 = STAGES2 * STAGE2_BYTES + 8 * (2 * STAGES2 + 2) + 16 + 1024;
+	cudaError_t e = cudaFuncSetAttribute(k_pairdist_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
 	if(e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(k_pairdist_umma2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+	if(e != cudaSuccess) return e;
+	UmmaParams p = p_in;
 	const long long items = (long long) p.ntiles * p.kslices;
 	if(items <= 0) return cudaSuccess;
-	k_pairdist_umma<<<(unsigned) items, THREADS, smem, ctx->stream>>>(ctx->tmap_x, p);
+	const int slots = p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx);   /* CTAs or CTA pairs */
+	const int grid = items < slots ? (int) items : slots;
+	/* lock-step counters: one per (round, epoch of LOCK_E stages) */
+	const long long rounds = (items + grid - 1) / grid;
+	p.epochs_per_item = (p.chunks_per_slice * 4 + LOCK_E - 1) / LOCK_E;
+	const size_t need = (size_t) rounds * p.epochs_per_item + 1;
+	p.sync = 0;
+	if(!ctx->dbg_nolock && grid > 1 && need <= ((size_t) 64 << 20)) {
+		if(ctx->sync_cap < need) {
+			if((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;
+			cudaFree(ctx->d_sync);
+			ctx->d_sync = 0;
+			ctx->sync_cap = 0;
+			if((e = cudaMalloc(&ctx->d_sync, need * sizeof(unsigned))) != cudaSuccess) return e;
+			ctx->sync_cap = need;
+		}
+		if((e = cudaMemsetAsync(ctx->d_sync, 0, need * sizeof(unsigned), ctx->stream)) != cudaSuccess) return e;
+		p.sync = ctx->d_sync;
+	}
+	ctx->last_gemm_ctas = p.single ? grid : 2 * grid;
+	if(p.single) k_pairdist_umma<<<(unsigned) grid, THREADS, smem1, ctx->stream>>>(ctx->tmap_x, p);
+	else k_pairdist_umma2<<<(unsigned) (2 * grid), THREADS, smem2, ctx->stream>>>(ctx->tmap_x, p);
 	ctx->launches++;
 	return cudaGetLastError();
 }

@@ -60,10 +60,10 @@ def test_partition_helpers_are_host_only(built):
 
     L = api.load()
     BM, BN = L.ccg_tile_rows(), L.ccg_tile_cols()
-    assert (BM, BN) == (128, 256)
+    assert (BM, BN) == (256, 256)
     for n in (1, 2, 63, 64, 65, 129, 1000, 2816):
         rows = (n + BM - 1) // BM
-        expect = [(tm, tn) for tm in range(rows) for tn in range(tm // 2 + 1)] if n >= 2 else []
+        expect = [(tm, tn) for tm in range(rows) for tn in range(tm + 1)] if n >= 2 else []
         for world in (1, 2, 3, 8):
             cells = [api.partition_cells(n, r, world) for r in range(world)]
             assert sum(cells) == api.cells(n)

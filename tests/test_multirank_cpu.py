@@ -28,7 +28,7 @@ def _worker(rank, world, port, n, out):
     rows = (n + BM - 1) // BM
     ids = {}
     for tm in range(rows):
-        for tn in range(tm // 2 + 1):
+        for tn in range(tm + 1):
             ids[(tm, tn)] = len(ids)
     owner = torch.zeros(len(ids), dtype=torch.int64)
     for t in api.partition_tiles(n, rank, world):
