@@ -27,6 +27,7 @@ EXPORTS = [
     "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
+    "ccg_measure_i8_peak",
 ]
 
 
@@ -94,6 +95,8 @@ def load():
     L.ccg_last_compare_ms.argtypes = [vp]
     L.ccg_last_phase_ms.restype = C.c_float
     L.ccg_last_phase_ms.argtypes = [vp, i]
+    L.ccg_measure_i8_peak.restype = C.c_double
+    L.ccg_measure_i8_peak.argtypes = [vp, C.c_double]
     _lib = L
     return L
 
@@ -268,6 +271,10 @@ class Context:
 
     def last_phase_ms(self, phase):
         return self._L.ccg_last_phase_ms(self._h, phase)
+
+    def measure_i8_peak(self, target_ms=20.0):
+        """int8 TOP/s of a loads-free tcgen05 kind::i8 loop on every CTA pair (roofline denominator)."""
+        return self._L.ccg_measure_i8_peak(self._h, target_ms)
 
 
 def fsa_cmp_thread_out(seqs, include, includes, length, pair=True, norm=0, min_length=1, min_cov=0.5, proxi=0,

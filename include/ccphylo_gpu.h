@@ -194,6 +194,12 @@ float ccg_last_compare_ms(ccg_ctx *ctx);
  * expansion (phase 0) or int8 GEMM launch (phase 1); < 0 if unavailable */
 float ccg_last_phase_ms(ccg_ctx *ctx, int phase);
 
+/* Roofline denominator for the tensor-core kernel: runs a loads-free loop of the kernel's own
+ * MMA shape (tcgen05 kind::i8, cta_group::2, 256 x 256 x 32, operands static in shared memory)
+ * on every CTA pair for about target_ms and returns the rate in int8 TOP/s (2 ops per MAC);
+ * < 0 on failure.  A few ms measures the burst rate, a second the power-capped sustained one. */
+double ccg_measure_i8_peak(ccg_ctx *ctx, double target_ms);
+
 #ifdef __cplusplus
 }
 #endif
