@@ -22,7 +22,7 @@ KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_FUSED = 0, 1, 2, 3
 EXPORTS = [
     "ccg_strerror", "ccg_last_error", "ccg_init", "ccg_destroy", "ccg_set_stream", "ccg_set_kernel", "ccg_sync",
     "ccg_set_partition", "ccg_tile_rows", "ccg_tile_cols", "ccg_partition_cells", "ccg_partition_tiles",
-    "ccg_set_scratch_limit", "ccg_set_problem", "ccg_put_global_mask", "ccg_apply_global_mask",
+    "ccg_set_scratch_limit", "ccg_set_problem", "ccg_put_global_mask", "ccg_apply_global_mask", "ccg_build_global_mask",
     "ccg_put_samples_packed",
     "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
@@ -73,6 +73,7 @@ def load():
     L.ccg_set_problem.argtypes = [vp, i, i, i]
     L.ccg_put_global_mask.argtypes = [vp, vp]
     L.ccg_apply_global_mask.argtypes = [vp, vp]
+    L.ccg_build_global_mask.argtypes = [vp, vp, vp]
     L.ccg_put_samples_packed.argtypes = [vp, i, i, vp, vp]
     L.ccg_put_samples_packed_dev.argtypes = [vp, i, i, vp, vp, C.c_long]
     L.ccg_put_sample_codes.argtypes = [vp, i, vp]
@@ -193,6 +194,12 @@ class Context:
         assert mask.size >= words(self.len)
         self._ck(self._L.ccg_apply_global_mask(self._h, mask.ctypes.data))
 
+    def build_global_mask(self, include=None):
+        inc = None if include is None else np.ascontiguousarray(include, dtype=np.uint8)
+        g = C.c_uint(0)
+        self._ck(self._L.ccg_build_global_mask(self._h, None if inc is None else inc.ctypes.data, C.byref(g)))
+        return g.value
+
     def put_samples_packed(self, seqs, masks=None, first=0, skip=None):
         seqs = np.ascontiguousarray(seqs, dtype=np.uint64)
         sp = _row_ptrs(seqs, skip)
@@ -278,13 +285,15 @@ class Context:
 
 
 def fsa_cmp_thread_out(seqs, include, includes, length, pair=True, norm=0, min_length=1, min_cov=0.5, proxi=0,
-                       elem_size=8, byte_scale=1.0, want_n=True, ctx=None):
+                       elem_size=8, byte_scale=1.0, want_n=True, ctx=None, rows=None):
     """Drop-in for the reference's ``fsaCmpThreadOut`` call (cdist.c:181/184).
 
     seqs (n, W) u64 and includes (n, W) u32 -- or (1, W) in shared-mask mode --
     are HOST arrays in the reference's packed formats; include is (n,) u8.
     Returns (D, N, Dn, global_inc): packed lower-triangular cells over the
-    included samples.
+    included samples.  rows = (list of per-sample u64 arrays, list of per-sample
+    u32 arrays) passes separately allocated rows, as the reference holds them
+    (dist.c:143-154), instead of the rows of the 2-D arrays.
     """
     L = load()
     seqs = np.ascontiguousarray(seqs, dtype=np.uint64)
@@ -295,8 +304,14 @@ def fsa_cmp_thread_out(seqs, include, includes, length, pair=True, norm=0, min_l
     D = np.zeros(max(cells(n), 1), dtype=dt)
     N = np.zeros(max(cells(n), 1), dtype=dt) if (want_n and pair) else None
     sp = _row_ptrs(seqs)
+    if rows is not None:
+        for k in range(n):
+            sp[k] = rows[0][k].ctypes.data
     if pair:
         mp = _row_ptrs(includes)
+        if rows is not None:
+            for k in range(n):
+                mp[k] = rows[1][k].ctypes.data
     else:
         mp = (C.c_void_p * max(n, 1))()
         for k in range(max(n, 1)):
@@ -309,5 +324,7 @@ def fsa_cmp_thread_out(seqs, include, includes, length, pair=True, norm=0, min_l
     if rc:
         msg = L.ccg_last_error(ctx._h if ctx else None).decode() or L.ccg_strerror(rc).decode()
         raise CcgError(rc, msg)
+    if ctx is not None:
+        ctx.n, ctx.len, ctx.pair = n, length, bool(pair)     # the call declared this problem on ctx
     k = cells(dn.value)
     return D[:k], (N[:k] if N is not None else None), dn.value, ginc.value

@@ -83,6 +83,11 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 	}
 	for(int k = 0; k < 4; ++k) cudaEventCreate(&ctx->ev_phase[k]);
 	cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+	for(int k = 0; k < 2; ++k) {
+		cudaStreamCreateWithFlags(&ctx->copy_stream[k], cudaStreamNonBlocking);
+		cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming);
+	}
+	cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&ctx->ev_launch, cudaEventDisableTiming);
 	for(int k = 0; k < 2; ++k) {
@@ -105,6 +110,9 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 	if(getenv("CCG_EXPAND_SERIAL")) ctx->dbg_serial = atoi(getenv("CCG_EXPAND_SERIAL"));
 	if(getenv("CCG_NOLOCK")) ctx->dbg_nolock = atoi(getenv("CCG_NOLOCK"));
 	if(getenv("CCG_UMMA1")) ctx->dbg_umma1 = atoi(getenv("CCG_UMMA1"));
+	if(getenv("CCG_FEED_SLABS")) ctx->dbg_feed_slabs = atoi(getenv("CCG_FEED_SLABS"));
+	/* host rows are streamed K slab by K slab from this alignment length on (0 = never) */
+	ctx->stream_min_chunks = getenv("CCG_STREAM_MIN_CHUNKS") ? atoi(getenv("CCG_STREAM_MIN_CHUNKS")) : 4096;
 	*out = ctx;
 	return CCG_OK;
 }
@@ -147,6 +155,13 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	for(int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_x[k]); cudaEventDestroy(ctx->ev_g[k]); }
 	cudaStreamSynchronize(ctx->aux_stream);
 	cudaStreamDestroy(ctx->aux_stream);
+	for(int k = 0; k < 2; ++k) {
+		cudaStreamSynchronize(ctx->copy_stream[k]);
+		cudaStreamDestroy(ctx->copy_stream[k]);
+		cudaEventDestroy(ctx->ev_up[k]);
+		cudaFree(ctx->d_stage2[k]);
+	}
+	cudaEventDestroy(ctx->ev_main);
 	cudaStreamDestroy(ctx->own_stream);
 	free(ctx);
 }
@@ -486,6 +501,40 @@ extern "C" int ccg_apply_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
 	return CCG_OK;
 }
 
+extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include, unsigned *global_inc) {
+	if(!ctx || !ctx->d_planes || !ctx->pair_mode) return CCG_ERR_ARG;
+	if(ctx->world > 1) {
+		set_err(ctx, "ccg_build_global_mask needs every sample on this device (partitioned contexts hold only their row blocks)");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	CK(ctx, cudaSetDevice(ctx->device));
+	if(!ctx->d_gmask) CK(ctx, cudaMalloc(&ctx->d_gmask, (size_t) (ctx->words + 1) * sizeof(uint32_t)));
+	unsigned char *h_use = (unsigned char *) calloc((size_t) ctx->n_pad, 1);
+	if(!h_use) return CCG_ERR_NOMEM;
+	for(int i = 0; i < ctx->n; ++i) h_use[i] = ctx->present[i] && (!include || include[i]);
+	int rc = ensure_stage(ctx, (size_t) ctx->n_pad + 64);
+	if(rc) { free(h_use); return rc; }
+	unsigned char *d_use = (unsigned char *) ctx->d_stage;
+	unsigned *d_cnt = (unsigned *) (d_use + (((size_t) ctx->n_pad + 15) & ~(size_t) 15));
+	cudaError_t e = cudaMemcpyAsync(d_use, h_use, (size_t) ctx->n_pad, cudaMemcpyHostToDevice, ctx->stream);
+	if(e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned), ctx->stream);
+	if(e == cudaSuccess) e = cudaMemsetAsync(ctx->d_gmask, 0, (size_t) (ctx->words + 1) * sizeof(uint32_t), ctx->stream);
+	if(e == cudaSuccess) e = ccg_launch_build_global_mask(ctx, d_use, d_cnt);
+	unsigned inc = 0;
+	if(e == cudaSuccess) e = cudaMemcpyAsync(&inc, d_cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+	if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	free(h_use);
+	if(e != cudaSuccess) {
+		set_err(ctx, "building the global mask failed: %s", cudaGetErrorString(e));
+		return CCG_ERR_CUDA;
+	}
+	ctx->global_inc = inc;
+	if(global_inc) *global_inc = inc;
+	CK(ctx, ccg_launch_apply_global_mask(ctx));
+	ctx->global_applied = 1;
+	return CCG_OK;
+}
+
 extern "C" int ccg_put_samples_packed(ccg_ctx *ctx, int first, int count, const uint64_t *const *seqs,
                                       const uint32_t *const *includes) {
 	if(!ctx || !ctx->d_planes || first < 0 || count < 0 || first + count > ctx->n || !seqs) return CCG_ERR_ARG;
@@ -672,6 +721,77 @@ static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
 	return CCG_OK;
 }
 
+/* ---- K-slab streaming of host rows ----
+ * Uploads the words of chunks [chunk0, chunk0 + nch) of every needed row (copy stream) and
+ * repacks them into the plane store; ev_up fires when the slab's planes are complete.  Rows at
+ * a uniform distance (one host allocation) go as 2-D copies, others row by row. */
+static int feed_slab(ccg_ctx *ctx, int chunk0, int nch) {
+	const int w0 = chunk0 * CCG_CHUNK_WORDS;
+	int nw = nch * CCG_CHUNK_WORDS;
+	if(nw > ctx->words - w0) nw = ctx->words - w0;
+	if(nw > 0) {
+		const int pair = ctx->feed_masks != 0;
+		const size_t pw = ((size_t) nw + 3) & ~(size_t) 3;          /* staging pitch in words: vector loads in k_repack_direct */
+		const size_t row_bytes = pw * (pair ? 12 : 8);
+		size_t batch = ((size_t) 256 << 20) / row_bytes;
+		if(batch < 32) batch = 32;
+		if(batch > (size_t) ctx->n) batch = (size_t) ctx->n;
+		const size_t bytes = batch * row_bytes + 64;
+		/* two copy streams with a staging buffer each, used in turn: the copy engines work in parallel */
+		for(int q = 0; q < 2; ++q) {
+			if(ctx->stage2_bytes[q] >= bytes) continue;
+			CK(ctx, cudaStreamSynchronize(ctx->copy_stream[q]));
+			cudaFree(ctx->d_stage2[q]);
+			ctx->d_stage2[q] = 0;
+			ctx->stage2_bytes[q] = 0;
+			if(cudaMalloc(&ctx->d_stage2[q], bytes) != cudaSuccess) {
+				set_err(ctx, "cudaMalloc of %zu staging bytes failed", bytes);
+				return CCG_ERR_NOMEM;
+			}
+			ctx->stage2_bytes[q] = bytes;
+		}
+		const uint64_t *const *seqs = ctx->feed_seqs;
+		const uint32_t *const *masks = ctx->feed_masks;
+		int k = 0, q = 0;
+		while(k < ctx->n) {
+			if(!seqs[k] || (pair && !masks[k]) || !ctx->need[k >> 7]) { ++k; continue; }
+			/* run of consecutive present, needed rows */
+			int run = 1;
+			while(k + run < ctx->n && (size_t) run < batch && seqs[k + run] && (!pair || masks[k + run]) && ctx->need[(k + run) >> 7]) ++run;
+			/* uniform row distance inside the run? */
+			bool uniform = run > 1;
+			const ptrdiff_t ds = run > 1 ? (const char *) seqs[k + 1] - (const char *) seqs[k] : 0;
+			const ptrdiff_t dm = (run > 1 && pair) ? (const char *) masks[k + 1] - (const char *) masks[k] : 0;
+			for(int r = 1; uniform && r + 1 < run; ++r) {
+				if((const char *) seqs[k + r + 1] - (const char *) seqs[k + r] != ds) uniform = false;
+				if(pair && (const char *) masks[k + r + 1] - (const char *) masks[k + r] != dm) uniform = false;
+			}
+			if(uniform && (ds < (ptrdiff_t) ((size_t) nw * 8) || (pair && dm < (ptrdiff_t) ((size_t) nw * 4)))) uniform = false;
+			cudaStream_t cs = ctx->copy_stream[q];
+			uint64_t *d_seq = (uint64_t *) ctx->d_stage2[q];
+			uint32_t *d_msk = pair ? (uint32_t *) (d_seq + batch * pw) : 0;
+			if(uniform) {
+				CK(ctx, cudaMemcpy2DAsync(d_seq, pw * 8, seqs[k] + w0, (size_t) ds, (size_t) nw * 8, (size_t) run,
+				                          cudaMemcpyHostToDevice, cs));
+				if(pair)
+					CK(ctx, cudaMemcpy2DAsync(d_msk, pw * 4, masks[k] + w0, (size_t) dm, (size_t) nw * 4, (size_t) run,
+					                          cudaMemcpyHostToDevice, cs));
+			} else {
+				for(int r = 0; r < run; ++r) {
+					CK(ctx, cudaMemcpyAsync(d_seq + (size_t) r * pw, seqs[k + r] + w0, (size_t) nw * 8, cudaMemcpyHostToDevice, cs));
+					if(pair)
+						CK(ctx, cudaMemcpyAsync(d_msk + (size_t) r * pw, masks[k + r] + w0, (size_t) nw * 4, cudaMemcpyHostToDevice, cs));
+				}
+			}
+			CK(ctx, ccg_launch_repack_direct(ctx, cs, k, run, d_seq, d_msk, (long) pw, chunk0, nch));
+			k += run;
+			q ^= 1;
+		}
+	}
+	for(int q = 0; q < 2; ++q) CK(ctx, cudaEventRecord(ctx->ev_up[q], ctx->copy_stream[q]));
+	return CCG_OK;
+}
+
 /* uploads this rank's macro tiles to d_tiles[0, cnt) and, behind them, their 128-row halves
  * (2tm, tn), (2tm+1, tn) for the kernels that work on 128 x 256 tiles: d_tiles[cnt, 3 cnt) */
 static int upload_macro_tiles(ccg_ctx *ctx, size_t *cnt_out) {
@@ -756,8 +876,29 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		rc = make_x_tmap(ctx);
 		if(rc) return rc;
 	}
-	const long long slab = ctx->x_chunks;
+	long long slab = ctx->x_chunks;
+	if(ctx->feed_seqs) {
+		/* host rows are streamed slab by slab: shorter slabs shorten the pipeline fill (the first
+		 * slab's upload is the only one not hidden behind a GEMM) */
+		const int feed_slabs = ctx->dbg_feed_slabs > 0 ? ctx->dbg_feed_slabs : 16;
+		long long want = (ctx->chunks + feed_slabs - 1) / feed_slabs;
+		if(want < ctx->stream_min_chunks / 2) want = ctx->stream_min_chunks / 2;
+		if(want < 16) want = 16;
+		const long long cap = ctx->x_bytes >= 2 * ctx->x_buf_bytes ? ctx->x_chunks : ctx->x_chunks / 2;
+		if(want < slab && cap >= 1) slab = want < cap ? want : cap;
+	}
 	const int nslabs = (int) ((ctx->chunks + slab - 1) / slab);
+	/* two slab buffers: the allocation's two halves, or -- when the whole panel fits in a single
+	 * buffer and shorter slabs are streamed -- that buffer cut in two */
+	const size_t per_chunk_b = (size_t) ctx->n_pad * 512;
+	size_t buf_off[2] = {0, ctx->x_buf_bytes};
+	if(ctx->x_bytes < 2 * ctx->x_buf_bytes) {
+		buf_off[1] = ((size_t) ctx->x_chunks / 2) * per_chunk_b;
+		if(nslabs > 1 && (size_t) slab * per_chunk_b > buf_off[1]) {
+			set_err(ctx, "internal: slab of %lld chunks does not fit half of the operand panel", slab);
+			return CCG_ERR_ARG;
+		}
+	}
 
 	UmmaParams p;
 	memset(&p, 0, sizeof(p));
@@ -771,6 +912,10 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	 * (persistent) GEMM CTA holds its SM, or expansion blocks can fill an SM and keep a GEMM CTA
 	 * out for milliseconds while all others wait for it in lock-step: the GEMM CTAs count
 	 * themselves in d_resident (monotonic over the run) and the aux stream waits for the count. */
+	if(ctx->feed_seqs) {
+		CK(ctx, cudaEventRecord(ctx->ev_main, ctx->stream));
+		for(int q = 0; q < 2; ++q) CK(ctx, cudaStreamWaitEvent(ctx->copy_stream[q], ctx->ev_main, 0));
+	}
 	const bool gate = ctx->fn_wait_value && ctx->d_resident && nslabs > 1;
 	if(gate) CK(ctx, cudaMemsetAsync(ctx->d_resident, 0, sizeof(unsigned), ctx->stream));
 	p.resident = gate ? ctx->d_resident : 0;
@@ -784,7 +929,7 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		int nch = ctx->chunks - chunk0;
 		if(nch > slab) nch = (int) slab;
 		p.slab_chunks = nch;
-		p.row_base = (int) (b * (ctx->x_buf_bytes / 128));
+		p.row_base = (int) (buf_off[b] / 128);
 		if(ctx->dbg_umma1) {
 			p.single = 1;
 			p.ntiles = (int) (2 * cnt);
@@ -797,6 +942,11 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 			p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
 		}
 		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nch) --p.kslices;
+		if(ctx->feed_seqs) {
+			rc = feed_slab(ctx, chunk0, nch);
+			if(rc) return rc;
+			for(int q = 0; q < 2; ++q) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_up[q], 0));
+		}
 		/* buffer b is free once the GEMM of slab s-2 has read it */
 		if(s >= 2) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b], 0));
 		if(ctx->dbg_serial && s >= 1) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b ^ 1], 0));
@@ -811,7 +961,7 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 				return CCG_ERR_CUDA;
 			}
 		}
-		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + b * ctx->x_buf_bytes, chunk0, nch, nslabs > 1 && !ctx->dbg_serial));
+		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + buf_off[b], chunk0, nch, nslabs > 1 && !ctx->dbg_serial));
 		CK(ctx, cudaEventRecord(ctx->ev_x[b], ctx->aux_stream));
 		if(s == nslabs - 1) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->aux_stream));
 		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x[b], 0));
@@ -943,6 +1093,7 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	int kind = ctx->kernel_choice;
 	if(kind == CCG_KERNEL_AUTO)
 		kind = (Dn >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
+	if(ctx->feed_seqs) kind = CCG_KERNEL_UMMA;      /* the caller streams host rows into the tensor path's K slabs */
 	if(kind == CCG_KERNEL_FUSED) return run_fused(ctx, ep);
 	return kind == CCG_KERNEL_UMMA ? run_umma(ctx, ep) : run_popc(ctx, ep);
 }
@@ -1054,26 +1205,56 @@ extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, 
 	}
 	rc = ccg_set_problem(ctx, n, len, pair);
 	if(!rc && !pair) rc = ccg_put_global_mask(ctx, includes[0]);
+	const uint64_t **srow = 0;
+	const uint32_t **mrow = 0;
 	if(!rc) {
 		/* excluded samples are never uploaded: NULL row = empty slot */
-		const uint64_t **srow = (const uint64_t **) malloc((size_t) (n ? n : 1) * sizeof(*srow));
-		const uint32_t **mrow = (const uint32_t **) malloc((size_t) (n ? n : 1) * sizeof(*mrow));
+		srow = (const uint64_t **) malloc((size_t) (n ? n : 1) * sizeof(*srow));
+		mrow = (const uint32_t **) malloc((size_t) (n ? n : 1) * sizeof(*mrow));
 		if(!srow || !mrow) rc = CCG_ERR_NOMEM;
-		else {
+	}
+	int streamed = 0;
+	if(!rc) {
+		int ninc = 0;
+		for(int i = 0; i < n; ++i) {
+			int inc = (!include || include[i]) && seqs[i] && (pair ? includes[i] != 0 : 1);
+			srow[i] = inc ? seqs[i] : 0;
+			mrow[i] = inc ? (pair ? includes[i] : includes[0]) : 0;
+			ninc += inc;
+		}
+		/* tensor path on a long alignment: stream the rows K slab by K slab inside the run, so that
+		 * the PCIe upload of slab s+1 hides behind the GEMM of slab s (run_umma / feed_slab) */
+		int kind = ctx->kernel_choice;
+		if(kind == CCG_KERNEL_AUTO) kind = (ninc >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
+		if(kind == CCG_KERNEL_UMMA && ctx->stream_min_chunks > 0 && ctx->chunks >= ctx->stream_min_chunks) {
 			for(int i = 0; i < n; ++i) {
-				int inc = !include || include[i];
-				srow[i] = inc ? seqs[i] : 0;
-				mrow[i] = inc ? (pair ? includes[i] : includes[0]) : 0;
+				if(!srow[i]) continue;
+				ctx->present[i] = 1;
+				if(ctx->need[i >> 7]) ctx->have[i >> 7] = 1;
 			}
+			if(cudaMemsetAsync(ctx->d_inc, 0, (size_t) ctx->n_pad * sizeof(unsigned), ctx->stream) != cudaSuccess) {
+				set_err(ctx, "cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+				rc = CCG_ERR_CUDA;
+			}
+			ctx->feed_seqs = srow;
+			ctx->feed_masks = pair ? mrow : 0;
+			streamed = 1;
+		} else {
 			rc = ccg_put_samples_packed(ctx, 0, n, srow, pair ? mrow : 0);
 		}
-		free(srow);
-		free(mrow);
 	}
 	if(!rc) {
 		if(pair) rc = ccg_run_pair(ctx, include, norm, minLength, minCov, elem_size, byteScale, D, N, Dn);
 		else rc = ccg_run_global(ctx, include, norm, elem_size, byteScale, D, Dn, global_inc);
 	}
+	if(streamed) {
+		/* the run has synchronised the main stream, which waited for every slab's upload */
+		for(int q = 0; q < 2; ++q) cudaStreamSynchronize(ctx->copy_stream[q]);
+		ctx->feed_seqs = 0;
+		ctx->feed_masks = 0;
+	}
+	free(srow);
+	free(mrow);
 	if(own) {
 		if(rc) snprintf(g_init_err, sizeof(g_init_err), "%s", own->err);
 		ccg_destroy(own);

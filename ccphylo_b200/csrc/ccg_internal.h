@@ -101,6 +101,17 @@ struct ccg_ctx {
 	void *d_stage;             /* staging for host rows */
 	size_t stage_bytes;
 
+	/* K-slab streaming of host rows (ccg_fsa_cmp_thread_out on the tensor path): the rows of slab
+	 * s+1 cross PCIe on copy_stream while the GEMM of slab s runs */
+	int stream_min_chunks;                 /* stream when the alignment has at least this many chunks (0 = never) */
+	int dbg_feed_slabs;                    /* CCG_FEED_SLABS override (experiments) */
+	cudaStream_t copy_stream[2];
+	cudaEvent_t ev_up[2], ev_main;
+	const uint64_t *const *feed_seqs;      /* host row pointers, or NULL when nothing is being streamed */
+	const uint32_t *const *feed_masks;     /* NULL in shared-mask mode */
+	void *d_stage2[2];                     /* the streaming path's own staging buffers, one per copy stream */
+	size_t stage2_bytes[2];
+
 	int *d_rank;               /* [n_pad] */
 	int *h_rank;               /* host mirror of the last run */
 	int last_Dn;
@@ -149,10 +160,15 @@ struct ccg_ctx {
 /* k_encode.cu */
 cudaError_t ccg_launch_repack(ccg_ctx *ctx, int first, int count, const uint64_t *d_seqs,
                               const uint32_t *d_masks, long wstride);
+cudaError_t ccg_launch_repack_range(ccg_ctx *ctx, cudaStream_t stream, int first, int count, const uint64_t *d_seqs,
+                                    const uint32_t *d_masks, long wstride, int chunk0, int nch);
+cudaError_t ccg_launch_repack_direct(ccg_ctx *ctx, cudaStream_t stream, int first, int count, const uint64_t *d_seqs,
+                                     const uint32_t *d_masks, long wstride, int chunk0, int nch);
 cudaError_t ccg_launch_encode_codes(ccg_ctx *ctx, int first, int count, const unsigned char *d_codes,
                                     long stride);
 cudaError_t ccg_launch_gather_raw(ccg_ctx *ctx, uint32_t *d_mism, uint32_t *d_ninc);
 cudaError_t ccg_launch_apply_global_mask(ccg_ctx *ctx);
+cudaError_t ccg_launch_build_global_mask(ccg_ctx *ctx, const unsigned char *d_use, unsigned *d_inc);
 
 /* k_pairdist_popc.cu */
 cudaError_t ccg_launch_popc(ccg_ctx *ctx, const PopcParams &p);

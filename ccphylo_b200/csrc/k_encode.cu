@@ -37,8 +37,10 @@ __device__ __forceinline__ void store_chunk(uint32_t *planes, int n_pad, int npl
  * walk each sample row contiguously (half-warp = one sample, lane = chunk: 32 B of codes +
  * 16 B of mask per lane), the writes walk each (chunk, plane) row contiguously (lane =
  * sample: 16 B per lane). */
+/* The rows may hold only the words of chunks [chunk0, chunk0 + nch) (K-slab streaming of host
+ * rows, see feed_slab in ccg_api.cu): seqs / masks rows then start at word 4 * chunk0. */
 __global__ void __launch_bounds__(256)
-k_repack_packed(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks, int words, int first, int count,
+k_repack_packed(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunk0, int nch, int words, int first, int count,
                 const uint64_t *__restrict__ seqs, const uint32_t *__restrict__ masks,
                 const uint32_t *__restrict__ gmask, long wstride, unsigned *__restrict__ inc) {
 	__shared__ uint4 tile[3][16][33];                  /* [plane][chunk][sample], padded against bank conflicts */
@@ -52,13 +54,13 @@ k_repack_packed(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunk
 		const long long c = c0 + cl;
 		uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0};
 		unsigned known = 0;
-		if(s < count && c < chunks) {
+		if(s < count && c < nch) {
 			const uint64_t *srow = seqs + (size_t) s * wstride;
-			const uint32_t *mrow = masks ? masks + (size_t) s * wstride : gmask;
+			const uint32_t *mrow = masks ? masks + (size_t) s * wstride : gmask + (size_t) chunk0 * 4;
 #pragma unroll
 			for(int q = 0; q < 4; ++q) {
-				const long long w = c * 4 + q;
-				if(w < words) {
+				const long long w = c * 4 + q;                    /* word within the rows; absolute word = 4 chunk0 + w */
+				if((long long) chunk0 * 4 + w < words) {
 					const uint64_t x = __ldg(srow + w);
 					const uint32_t mk = __ldg(mrow + w);
 					m[q] = mk;
@@ -83,8 +85,63 @@ k_repack_packed(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunk
 		const int ci = r / nplanes, pl = r % nplanes;
 		const long long c = c0 + ci;
 		const int s = s0 + lane;
-		if(c < chunks && s < count) out[((size_t) c * nplanes + pl) * n_pad + first + s] = tile[pl][ci][lane];
+		if(c < nch && s < count) out[((size_t) (chunk0 + c) * nplanes + pl) * n_pad + first + s] = tile[pl][ci][lane];
 	}
+}
+
+/* Same conversion without shared memory, for the K-slab streaming path (feed_slab): it runs on
+ * a copy stream BESIDE the persistent tensor kernel, which leaves ~30 KiB of shared memory per
+ * SM -- the transposing kernel above would get one block per SM and stall the uploads behind
+ * it.  Lane = sample: every lane streams its own row (one 32-byte sector of codes + 16 bytes of
+ * mask per chunk) and the 32 lanes of a warp write 512 contiguous bytes per (chunk, plane).
+ * Rows hold the words of chunks [chunk0, chunk0 + nch) at a pitch of wstride words (a multiple
+ * of 4); nvalid = number of valid words per row. */
+constexpr int REPACK_CPT = 8;      /* chunks per thread */
+__global__ void __launch_bounds__(256)
+k_repack_direct(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunk0, int nch, int nvalid, int first, int count,
+                const uint64_t *__restrict__ seqs, const uint32_t *__restrict__ masks, const uint32_t *__restrict__ gmask,
+                long wstride, unsigned *__restrict__ inc) {
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int s = blockIdx.y * 32 + lane;
+	const int cbeg = (blockIdx.x * 8 + warp) * REPACK_CPT;
+	if(s >= count || cbeg >= nch) return;
+	const uint64_t *srow = seqs + (size_t) s * wstride;
+	const uint32_t *mrow = masks ? masks + (size_t) s * wstride : gmask + (size_t) chunk0 * 4;
+	uint4 *out = reinterpret_cast<uint4 *>(planes);
+	unsigned known = 0;
+	const int cend = cbeg + REPACK_CPT < nch ? cbeg + REPACK_CPT : nch;
+#pragma unroll 4
+	for(int c = cbeg; c < cend; ++c) {
+		uint64_t x[4] = {0, 0, 0, 0};
+		uint32_t mk[4] = {0, 0, 0, 0};
+		if(c * 4 + 4 <= nvalid) {
+			const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(srow + c * 4));
+			const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(srow + c * 4 + 2));
+			x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+			if(masks) {
+				const uint4 m4 = __ldg(reinterpret_cast<const uint4 *>(mrow + c * 4));
+				mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+			} else {
+#pragma unroll
+				for(int q = 0; q < 4; ++q) mk[q] = __ldg(mrow + c * 4 + q);
+			}
+		} else {
+			for(int q = 0; q < 4; ++q)
+				if(c * 4 + q < nvalid) { x[q] = __ldg(srow + c * 4 + q); mk[q] = __ldg(mrow + c * 4 + q); }
+		}
+		uint32_t h[4], l[4];
+#pragma unroll
+		for(int q = 0; q < 4; ++q) {
+			h[q] = compress_even(x[q] >> 1) & mk[q];
+			l[q] = compress_even(x[q]) & mk[q];
+			known += __popc(mk[q]);
+		}
+		const size_t row = (size_t) (chunk0 + c) * nplanes;
+		out[(row + 0) * n_pad + first + s] = make_uint4(h[0], h[1], h[2], h[3]);
+		out[(row + 1) * n_pad + first + s] = make_uint4(l[0], l[1], l[2], l[3]);
+		if(nplanes == 3) out[(row + 2) * n_pad + first + s] = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+	}
+	if(masks && known) atomicAdd(inc + first + s, known);
 }
 
 /* Translated codes (0..3 base, anything else unknown) -> planes + inc count.
@@ -153,6 +210,45 @@ k_apply_global_mask(uint32_t *__restrict__ planes, int n_pad, int nplanes, int c
 	}
 }
 
+/* Global mask = AND of the inclusion masks of all included samples (cdist.c:101-112: every
+ * included sample clears the positions it does not know).  One warp per chunk: the mask plane
+ * row of a chunk is n_pad x 16 contiguous bytes; lanes stride over the slots. */
+__global__ void __launch_bounds__(256)
+k_build_global_mask(const uint32_t *__restrict__ planes, int n_pad, int chunks, int words, const unsigned char *__restrict__ use,
+                    uint32_t *__restrict__ gmask, unsigned *__restrict__ inc) {
+	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if(warp >= chunks) return;
+	const uint4 *row = reinterpret_cast<const uint4 *>(planes) + ((size_t) warp * 3 + 2) * n_pad;
+	uint4 g = make_uint4(~0u, ~0u, ~0u, ~0u);
+	for(int s = lane; s < n_pad; s += 32) {
+		if(!use[s]) continue;
+		const uint4 m = row[s];
+		g.x &= m.x; g.y &= m.y; g.z &= m.z; g.w &= m.w;
+	}
+#pragma unroll
+	for(int o = 16; o; o >>= 1) {
+		g.x &= __shfl_xor_sync(0xffffffffu, g.x, o);
+		g.y &= __shfl_xor_sync(0xffffffffu, g.y, o);
+		g.z &= __shfl_xor_sync(0xffffffffu, g.z, o);
+		g.w &= __shfl_xor_sync(0xffffffffu, g.w, o);
+	}
+	if(lane == 0) {
+		const uint32_t w[4] = {g.x, g.y, g.z, g.w};
+		unsigned known = 0;
+		for(int q = 0; q < 4; ++q)
+			if(warp * 4 + q < words) { gmask[warp * 4 + q] = w[q]; known += __popc(w[q]); }
+		if(known) atomicAdd(inc, known);
+	}
+}
+
+cudaError_t ccg_launch_build_global_mask(ccg_ctx *ctx, const unsigned char *d_use, unsigned *d_inc) {
+	const long long threads = (long long) ctx->chunks * 32;
+	k_build_global_mask<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks, ctx->words,
+	                                                                                d_use, ctx->d_gmask, d_inc);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
 cudaError_t ccg_launch_apply_global_mask(ccg_ctx *ctx) {
 	k_apply_global_mask<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks,
 	                                                                   ctx->words, ctx->d_gmask);
@@ -187,9 +283,30 @@ cudaError_t ccg_launch_repack(ccg_ctx *ctx, int first, int count, const uint64_t
 		cudaError_t e = cudaMemsetAsync(ctx->d_inc + first, 0, (size_t) count * sizeof(unsigned), ctx->stream);
 		if(e != cudaSuccess) return e;
 	}
-	dim3 grid((unsigned) ((ctx->chunks + 15) / 16), (unsigned) ((count + 31) / 32));
-	k_repack_packed<<<grid, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks, ctx->words, first,
-	                                                count, d_seqs, d_masks, ctx->d_gmask, wstride, ctx->d_inc);
+	return ccg_launch_repack_range(ctx, ctx->stream, first, count, d_seqs, d_masks, wstride, 0, ctx->chunks);
+}
+
+/* rows hold the words of chunks [chunk0, chunk0 + nch) only; the per-sample counts accumulate
+ * (the caller zeroes d_inc once before the first range) */
+/* shared-memory-free variant for work that runs beside the tensor kernel; wstride must be a multiple of 4 */
+cudaError_t ccg_launch_repack_direct(ccg_ctx *ctx, cudaStream_t stream, int first, int count, const uint64_t *d_seqs,
+                                     const uint32_t *d_masks, long wstride, int chunk0, int nch) {
+	if(count <= 0 || nch <= 0) return cudaSuccess;
+	int nvalid = ctx->words - chunk0 * CCG_CHUNK_WORDS;
+	if(nvalid > nch * CCG_CHUNK_WORDS) nvalid = nch * CCG_CHUNK_WORDS;
+	dim3 grid((unsigned) ((nch + 8 * REPACK_CPT - 1) / (8 * REPACK_CPT)), (unsigned) ((count + 31) / 32));
+	k_repack_direct<<<grid, 256, 0, stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, chunk0, nch, nvalid, first, count, d_seqs,
+	                                         d_masks, ctx->d_gmask, wstride, ctx->d_inc);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t ccg_launch_repack_range(ccg_ctx *ctx, cudaStream_t stream, int first, int count, const uint64_t *d_seqs,
+                                    const uint32_t *d_masks, long wstride, int chunk0, int nch) {
+	if(count <= 0 || nch <= 0) return cudaSuccess;
+	dim3 grid((unsigned) ((nch + 15) / 16), (unsigned) ((count + 31) / 32));
+	k_repack_packed<<<grid, 256, 0, stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, chunk0, nch, ctx->words, first, count,
+	                                         d_seqs, d_masks, ctx->d_gmask, wstride, ctx->d_inc);
 	ctx->launches++;
 	return cudaGetLastError();
 }

@@ -109,6 +109,11 @@ int ccg_put_global_mask(ccg_ctx *ctx, const uint32_t *mask);
  * loading).  Afterwards ccg_run_global[_dev] may be used on this store. */
 int ccg_apply_global_mask(ccg_ctx *ctx, const uint32_t *mask);
 
+/* Same, with the global mask built on the device: the AND of the inclusion masks of all
+ * uploaded samples with include[i] != 0 (NULL = all), which is what cdist.c:86-112 accumulates
+ * in includes[0] while loading.  *global_inc receives its getNpos (fsacmpthrd.c:164). */
+int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include, unsigned *global_inc);
+
 /* Upload samples [first, first+count) in the reference's packed format from
  * HOST memory; seqs[k] / includes[k] are row pointers exactly as the
  * reference holds them (dist.c:143-154).  includes may be NULL in

@@ -134,6 +134,12 @@ def test_global_mask_applied_to_a_pair_store(built, kernel):
         c.put_samples_packed(seqs, masks)
         c.apply_global_mask(gmask)
         D, dn, ginc = c.run_global(include, norm=1000)
+        # and with the mask built on the device from the uploaded samples' own masks
+        c.set_problem(n, length, pair=True)
+        c.put_samples_packed(seqs, masks)
+        assert c.build_global_mask(include) == int(sum(bin(int(w)).count("1") for w in gmask))
+        D2, dn2, ginc2 = c.run_global(include, norm=1000)
+        assert dn2 == dn and ginc2 == ginc and np.array_equal(_bits(D2), _bits(D))
     Do, dno, ginco = oracle.fsa_cmp_global(seqs, gmask, include, length, norm=1000)
     assert dn == dno == n and ginc == ginco
     assert np.array_equal(_bits(D), _bits(Do))

@@ -204,3 +204,39 @@ def test_partition_change_after_upload_is_refused(built):
         with pytest.raises(api.CcgError) as e:
             c.run_pair()
         assert e.value.code == 3 and "ccg_set_partition before" in str(e.value)
+
+
+@pytest.mark.parametrize("pair", [True, False], ids=["pair", "shared-mask"])
+@pytest.mark.parametrize("contiguous", [True, False], ids=["2d-copies", "row-copies"])
+def test_streamed_host_rows_match_resident_upload(built, monkeypatch, pair, contiguous):
+    """ccg_fsa_cmp_thread_out on the tensor path streams the host rows K slab by K slab (upload of
+    slab s+1 under the GEMM of slab s); results must equal the oracle bit for bit, for rows in one
+    allocation (2-D copies) and for separately allocated rows (row-by-row copies)."""
+    monkeypatch.setenv("CCG_STREAM_MIN_CHUNKS", "32")
+    n, length = 260, 128 * 150 + 77
+    codes, seqs, masks, inc = _set(n, length, seed=5, nrun=0.004 if not pair else 0.05)
+    include = np.ones(n, dtype=np.uint8)
+    include[[7, 200]] = 0
+    rows = None
+    if not contiguous:
+        # every row in its own buffer, so the row pointers are at irregular distances
+        rs = [np.array(seqs[k], dtype=np.uint64, copy=True) for k in range(n)]
+        rm = [np.array(masks[k], dtype=np.uint32, copy=True) for k in range(n)]
+        rows = (rs, rm)
+    with api.Context() as c:
+        c.set_kernel(api.KERNEL_UMMA)
+        if pair:
+            D, N, dn, _ = api.fsa_cmp_thread_out(seqs, include, masks, length, pair=True, norm=1000, ctx=c, rows=rows)
+            Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=1000)
+            assert dn == dno == n - 2
+            assert np.array_equal(_bits(N), _bits(No))
+            assert np.array_equal(_bits(D), _bits(Do))
+            assert np.array_equal(c.inc_counts()[include == 1], inc[include == 1])
+        else:
+            gmask = oracle.global_mask(codes, include)
+            D, _, dn, ginc = api.fsa_cmp_thread_out(seqs, include, gmask.reshape(1, -1), length, pair=False, norm=1000,
+                                                    ctx=c, rows=rows)
+            Do, dno, ginco = oracle.fsa_cmp_global(seqs, gmask, include, length, norm=1000)
+            assert dn == dno == n - 2 and ginc == ginco
+            assert np.array_equal(_bits(D), _bits(Do))
+        assert "slabs=" in c.last_kernel and int(c.last_kernel.split("slabs=")[1]) > 1
