@@ -27,8 +27,22 @@ EXPORTS = [
     "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
-    "ccg_measure_i8_peak",
+    "ccg_measure_i8_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
 ]
+
+MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "ln", "nl1", "nl2",
+               "nlinf", "nln"]          # CCG_MAT_* ids, include/ccphylo_gpu.h
+
+
+def mat_method(name):
+    """'-d' name -> (CCG_MAT_* id, order), same precedence as the dist driver (dist.c:738-786)."""
+    if name in MAT_METHODS and name not in ("ln", "nln"):
+        return MAT_METHODS.index(name), 0
+    if name.startswith("l"):
+        return MAT_METHODS.index("ln"), int(name[1:])
+    if name.startswith("nl"):
+        return MAT_METHODS.index("nln"), int(name[2:])
+    raise ValueError(name)
 
 
 class CcgError(RuntimeError):
@@ -96,6 +110,10 @@ def load():
     L.ccg_last_compare_ms.argtypes = [vp]
     L.ccg_last_phase_ms.restype = C.c_float
     L.ccg_last_phase_ms.argtypes = [vp, i]
+    L.ccg_mat_set_problem.argtypes = [vp, i, i]
+    L.ccg_mat_put_sample.argtypes = [vp, i, vp, vp, i]
+    L.ccg_mat_run.argtypes = [vp, vp, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, i, C.c_double,
+                              vp, vp, vp, vp]
     L.ccg_measure_i8_peak.restype = C.c_double
     L.ccg_measure_i8_peak.argtypes = [vp, C.c_double]
     _lib = L
@@ -263,6 +281,35 @@ class Context:
         ninc = np.zeros(max(cells(dn), 1), dtype=np.uint32)
         self._ck(self._L.ccg_get_raw_counts(self._h, mism.ctypes.data, ninc.ctypes.data))
         return mism[:cells(dn)], ninc[:cells(dn)]
+
+    # ---- count-matrix (.mat) path ----
+    def mat_set_problem(self, n, max_len):
+        self._ck(self._L.ccg_mat_set_problem(self._h, n, max_len))
+        self.mat_n = n
+
+    def mat_put_sample(self, idx, counts6, totals=None):
+        counts6 = np.ascontiguousarray(counts6, dtype=np.uint16).reshape(-1, 6)
+        tp = None
+        if totals is not None:
+            totals = np.ascontiguousarray(totals, dtype=np.uint32)
+            tp = totals.ctypes.data
+        self._ck(self._L.ccg_mat_put_sample(self._h, idx, counts6.ctypes.data, tp, counts6.shape[0]))
+
+    def mat_run(self, include=None, method="cos", alpha=0.05, norm=0, min_depth=15, min_length=1, min_cov=0.5,
+                elem_size=8, byte_scale=1.0):
+        mid, order = mat_method(method)
+        n = self.mat_n
+        dt = ELEM_DTYPE[elem_size]
+        D = np.zeros(max(cells(n), 1), dtype=dt)
+        N = np.zeros(max(cells(n), 1), dtype=dt)
+        rows = np.zeros(max(cells(n), 1), dtype=np.uint32)
+        inc = None if include is None else np.ascontiguousarray(include, dtype=np.uint8)
+        dn = C.c_int(0)
+        self._ck(self._L.ccg_mat_run(self._h, None if inc is None else inc.ctypes.data, mid, order, alpha, norm, min_depth,
+                                     min_length, min_cov, elem_size, byte_scale, D.ctypes.data, N.ctypes.data,
+                                     C.byref(dn), rows.ctypes.data))
+        k = cells(dn.value)
+        return D[:k], N[:k], dn.value, rows[:k]
 
     # ---- introspection ----
     @property

@@ -139,6 +139,7 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	free_problem(ctx);
+	ccg_mat_free(ctx);
 	cudaFree(ctx->d_stage);
 	cudaFree(ctx->d_acc);
 	cudaFree(ctx->d_tickets);

@@ -146,6 +146,17 @@ struct ccg_ctx {
 	CUtensorMap tmap_x;        /* operand panel as a 2-D tensor */
 	int tmap_valid;
 
+	/* count-matrix (.mat) path, k_matdist.cu */
+	void *mat_counts;          /* [mat_npad][mat_lpad] 16-byte records */
+	int *mat_lens, *mat_hlens; /* device / host: rows per slot */
+	int *mat_rank;
+	int mat_n, mat_npad;
+	long long mat_lpad;
+	void *mat_stage;           /* pinned staging for one sample */
+	double *mat_part_dist;
+	unsigned *mat_part_rows, *mat_rows;
+	size_t mat_part_cap;
+
 	cudaEvent_t ev0, ev1;
 	int ev_valid;
 	cudaEvent_t ev_phase[4];   /* tensor-core path, first slab: expand begin/end, GEMM begin/end */
@@ -180,6 +191,9 @@ cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
 int ccg_umma_pair_slots(ccg_ctx *ctx);
 cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);
 cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc);
+
+/* k_matdist.cu */
+void ccg_mat_free(ccg_ctx *ctx);
 
 /* k_pairdist_fused.cu */
 cudaError_t ccg_launch_fused(ccg_ctx *ctx, const UmmaParams &p);

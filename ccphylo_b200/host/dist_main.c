@@ -1,0 +1,545 @@
+/*
+ * dist_main.c -- `ccphylo-b200 dist`: the host side of the reference's `ccphylo dist`
+ * (dist.c:473 main_dist, dist.c:42 makeMatrix, cdist.c:36 ltdFsaMatrix_get, cdist.c:196
+ * ltdMsaMatrix_get) in front of the CUDA library.  Same options, same Phylip / .num text, same
+ * stderr lines, so `ccphylo union | ccphylo-b200 dist | ccphylo tree` keeps working.
+ *
+ * What is different by design (B200-first):
+ *   - input files are parsed by -t host threads in parallel; the translated codes of each
+ *     included sample go straight to the device (ccg_put_sample_codes), which packs them,
+ *     builds the inclusion mask and counts it -- the host keeps O(threads) sequences, not n;
+ *   - the O(n^2 L) comparison and the epilogue run on the GPU (ccg_run_pair / ccg_run_global);
+ *     there is no CPU fallback: without a usable device the program stops with an error;
+ *   - -P (proximity), -V (variant listing), -y (motif masking), -a (row append) are refused.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <errno.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ccphylo_gpu.h"
+#include "cmdline.h"
+#include "dist_opts.h"
+#include "fsa_reader.h"
+#include "ordered_pool.h"
+#include "phy_writer.h"
+
+#define VERSION "0.1.0 (B200 path of ccphylo dist 0.8.5)"
+
+static void die_errno(void) {
+	fprintf(stderr, "Error: %d (%s)\n", errno, strerror(errno));
+	exit(errno ? errno : 1);
+}
+
+static void die_gpu(ccg_ctx *ctx, int rc) {
+	fprintf(stderr, "GPU error: %s (%s)\n", ccg_strerror(rc), ccg_last_error(ctx));
+	exit(rc ? rc : 1);
+}
+
+static FILE *open_out(const char *name) {
+	if(name[0] == '-' && name[1] == 0) return stdout;
+	FILE *f = fopen(name, "wb");
+	if(!f) {
+		fprintf(stderr, "Filename:\t%s\n", name);
+		die_errno();
+	}
+	/* large rows: fewer write calls */
+	setvbuf(f, 0, _IOFBF, 1 << 22);
+	return f;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * result matrices: packed lower triangle in pinned host memory
+ * ------------------------------------------------------------------------------------------ */
+static void *alloc_cells(size_t n, int elem) {
+	size_t cells = n > 1 ? n * (n - 1) / 2 : 1;
+	void *p = ccg_host_alloc(cells * (size_t) elem);
+	if(!p) {
+		fprintf(stderr, "Error: cannot allocate %zu bytes of pinned host memory\n", cells * (size_t) elem);
+		exit(1);
+	}
+	return p;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * multi-file FASTA input: parallel parse, ordered consumption
+ * ------------------------------------------------------------------------------------------ */
+enum { PARSE_OK = 0, PARSE_NOT_FASTA, PARSE_NO_TEMPLATE, PARSE_NO_SEQ, PARSE_OPEN_FAILED };
+
+typedef struct {
+	int status, err;
+	ByteBuf codes;
+	unsigned known;          /* codes < 4 */
+} Parsed;
+
+typedef struct {
+	const DistOpts *o;
+	unsigned char table[256];
+} FsaJob;
+
+static void parse_one(int job, void *state, void *user) {
+	const FsaJob *fj = (const FsaJob *) user;
+	Parsed *r = (Parsed *) state;
+	const char *path = fj->o->filenames[job];
+	ByteBuf header;
+	r->status = PARSE_NO_TEMPLATE;
+	r->known = 0;
+	r->codes.len = 0;
+	FsaReader *fr = fsa_open(path);
+	if(!fr) {
+		r->status = PARSE_OPEN_FAILED;
+		r->err = errno;
+		return;
+	}
+	if(fsa_peek(fr) != '>') {
+		r->status = fsa_peek(fr) < 0 ? PARSE_OPEN_FAILED : PARSE_NOT_FASTA;
+		r->err = 0;
+		fsa_close(fr);
+		return;
+	}
+	bytebuf_init(&header, 256);
+	while(fsa_next_header(fr, &header)) {
+		if(strcmp((const char *) header.data, fj->o->targetTemplate) != 0) continue;
+		if(!fsa_read_codes(fr, fj->table, &r->codes)) r->status = PARSE_NO_SEQ;
+		else {
+			unsigned known = 0;
+			for(size_t k = 0; k < r->codes.len; ++k) known += r->codes.data[k] < 4;
+			r->known = known;
+			r->status = PARSE_OK;
+		}
+		break;
+	}
+	bytebuf_free(&header);
+	fsa_close(fr);
+}
+
+/* shared tail of the two FASTA modes: compare on the device and print (cdist.c:170-192, dist.c:174-180) */
+static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, unsigned minLength, unsigned char *include,
+                             int included, char **names, const char *comment, FILE *outfile, FILE *noutfile, int n_into_out) {
+	const int pair = (o->flag & 2) != 0;
+	const long long cells_all = (long long) n * (n - 1) / 2;
+	if(cells_all < o->threads)
+		fprintf(stderr, "Adjustning number of nodes to %d, to conform with the matrix size.\n", (int) cells_all);
+	if(!included) {
+		fprintf(stderr, "All sequences were trimmed away.\n");
+		return 0;
+	}
+	void *D = alloc_cells((size_t) included, o->elem_size);
+	void *N = (pair && noutfile) ? alloc_cells((size_t) included, o->elem_size) : 0;
+	int Dn = 0, rc;
+	if(pair) {
+		/* minLength was already maxed with minCov * len; the library repeats that (fsacmpthrd.c:292) */
+		rc = ccg_run_pair(ctx, include, o->norm, minLength, o->minCov, o->elem_size, o->byteScale, D, N, &Dn);
+		if(rc) die_gpu(ctx, rc);
+	} else {
+		unsigned ginc = 0;
+		rc = ccg_build_global_mask(ctx, include, &ginc);
+		if(rc) die_gpu(ctx, rc);
+		fprintf(stderr, "# %d / %d bases included in distance matrix.\n", (int) ginc, len);
+		rc = ccg_run_global(ctx, include, o->norm, o->elem_size, o->byteScale, D, &Dn, &ginc);
+		if(rc) die_gpu(ctx, rc);
+	}
+	if(Dn > 1) {
+		phy_write(outfile, D, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision);
+		if(N) phy_write(n_into_out ? outfile : noutfile, N, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision);
+	}
+	ccg_host_free(D);
+	ccg_host_free(N);
+	return Dn;
+}
+
+/* ltdFsaMatrix_get (cdist.c:36-194) */
+static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
+	const int n = (int) o->numFile;
+	FsaJob fj;
+	fj.o = o;
+	fsa_code_table(o->flag, fj.table);
+	int nthreads = o->threads < 1 ? 1 : o->threads;
+	if(nthreads > n) nthreads = n;
+	const int window = nthreads + 2;
+	Parsed *slots = calloc((size_t) window, sizeof(Parsed));
+	if(!slots) die_errno();
+	for(int k = 0; k < window; ++k) bytebuf_init(&slots[k].codes, 1 << 20);
+	OrderedPool *pool = pool_start(n, nthreads, window, slots, sizeof(Parsed), parse_one, &fj);
+	if(!pool) die_errno();
+
+	ccg_ctx *ctx = 0;
+	int rc = ccg_init(&ctx, -1);
+	if(rc) die_gpu(0, rc);
+	unsigned char *include = malloc((size_t) n);
+	if(!include) die_errno();
+	memset(include, 1, (size_t) n);
+	unsigned minLength = o->minLength;
+	int len = 0, have_ref = 0, included = n;
+
+	for(int i = 0; i < n; ++i) {
+		Parsed *r = (Parsed *) pool_take(pool, i);
+		const char *path = o->filenames[i];
+		switch(r->status) {
+			case PARSE_OPEN_FAILED:
+				if(r->err) {
+					errno = r->err;
+					fprintf(stderr, "Filename:\t%s\n", path);
+					die_errno();
+				}
+				fprintf(stderr, "Cannot determine format of file:\t%s\n", path);
+				exit(1);
+			case PARSE_NOT_FASTA:
+				fprintf(stderr, "\"%s\" is not fasta.\n", path);
+				exit(1);
+			case PARSE_NO_TEMPLATE:
+				fprintf(stderr, "Missing template entry (\"%s\") in file:\t%s\n", o->targetTemplate, path);
+				include[i] = 0;
+				--included;
+				break;
+			case PARSE_NO_SEQ:
+				fprintf(stderr, "Missing template sequence (\"%s\") in file:\t%s\n", o->targetTemplate, path);
+				include[i] = 0;
+				--included;
+				break;
+			default: {
+				if(have_ref) {
+					if((int) r->codes.len != len) {
+						fprintf(stderr, "Sequences does not match: %s\n", path);
+						exit(1);
+					}
+				} else {
+					/* until a sample passes, every candidate redefines the alignment length (cdist.c:113-147) */
+					len = (int) r->codes.len;
+					if(minLength < o->minCov * len) minLength = (unsigned) (o->minCov * len);
+				}
+				if(r->known < minLength) {
+					fprintf(stderr, "# Excluded:\t%s\t( %d / %d )\n", path, (int) r->known, len);
+					include[i] = 0;
+					--included;
+				} else {
+					fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", path, (int) r->known, len);
+					if(!have_ref) {
+						have_ref = 1;
+						/* a pair-mode store serves both modes: the shared mask is ANDed in afterwards */
+						rc = ccg_set_problem(ctx, n, len, 1);
+						if(rc) die_gpu(ctx, rc);
+					}
+					if(len > 0) {
+						rc = ccg_put_sample_codes(ctx, i, r->codes.data);
+						if(rc) die_gpu(ctx, rc);
+						/* the staging copy is asynchronous and the ring slot is about to be reused */
+						rc = ccg_sync(ctx);
+						if(rc) die_gpu(ctx, rc);
+					}
+				}
+			}
+		}
+		pool_release(pool, i);
+	}
+	pool_finish(pool);
+	if(!have_ref) included = 0;
+	compare_and_print(o, ctx, n, len, minLength, include, included, o->filenames, o->targetTemplate, outfile, noutfile, 0);
+	ccg_destroy(ctx);
+	for(int k = 0; k < window; ++k) bytebuf_free(&slots[k].codes);
+	free(slots);
+	free(include);
+}
+
+/* ltdMsaMatrix_get (cdist.c:196-390): one multi-FASTA alignment, records are the samples */
+static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
+	const char *path = o->numFile ? o->filenames[0] : "-";
+	unsigned char table[256];
+	fsa_code_table(o->flag, table);
+	const int pair = (o->flag & 2) != 0;
+
+	/* the device store is sized up front: count the records first (a second pass is far cheaper
+	 * than keeping the alignment in host memory) */
+	int nrec = 0;
+	if(strcmp(path, "-") == 0) {
+		fprintf(stderr, "MSA input from stdin is not supported on the GPU path (the alignment is read twice).\n");
+		exit(1);
+	}
+	FsaReader *fr = fsa_open(path);
+	if(!fr) {
+		fprintf(stderr, "Filename:\t%s\n", path);
+		die_errno();
+	}
+	if(fsa_peek(fr) < 0) {
+		fprintf(stderr, "Cannot determine format of file:\t%s\n", path);
+		exit(1);
+	}
+	ByteBuf header, codes;
+	bytebuf_init(&header, 256);
+	bytebuf_init(&codes, 1 << 20);
+	while(fsa_next_header(fr, &header)) ++nrec;
+	fsa_close(fr);
+
+	fr = fsa_open(path);
+	if(!fr) die_errno();
+	ccg_ctx *ctx = 0;
+	int rc = ccg_init(&ctx, -1);
+	if(rc) die_gpu(0, rc);
+	char **names = calloc((size_t) (nrec ? nrec : 1), sizeof(char *));
+	if(!names) die_errno();
+	unsigned minLength = o->minLength;
+	int len = 0, have_ref = 0, n = 0;
+	while(fsa_next_header(fr, &header)) {
+		if(!fsa_read_codes(fr, table, &codes)) break;       /* header at the very end of the file: no record */
+		unsigned known = 0;
+		for(size_t k = 0; k < codes.len; ++k) known += codes.data[k] < 4;
+		const char *name = (const char *) header.data;
+		int keep;
+		if(have_ref) {
+			if((int) codes.len != len) {
+				fprintf(stderr, "Sequences does not match: >%s\n", name);
+				exit(1);
+			}
+			/* shared-mask mode keeps a later record only if it EXCEEDS the threshold (cdist.c:270) */
+			keep = pair ? !(known < minLength) : (minLength < known);
+		} else {
+			len = (int) codes.len;
+			if(minLength < o->minCov * len) minLength = (unsigned) (o->minCov * len);
+			keep = !(known < minLength);
+		}
+		if(!keep) {
+			fprintf(stderr, "# Excluded:\t%s\t( %d / %d )\n", name, (int) known, len);
+			continue;
+		}
+		fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", name, (int) known, len);
+		if(!have_ref) {
+			have_ref = 1;
+			rc = ccg_set_problem(ctx, nrec, len, 1);
+			if(rc) die_gpu(ctx, rc);
+		}
+		names[n] = strdup(name);
+		if(!names[n]) die_errno();
+		if(len > 0) {
+			rc = ccg_put_sample_codes(ctx, n, codes.data);
+			if(rc) die_gpu(ctx, rc);
+			rc = ccg_sync(ctx);
+			if(rc) die_gpu(ctx, rc);
+		}
+		++n;
+	}
+	fsa_close(fr);
+	/* excluded records were dropped: the n kept samples occupy slots 0..n-1 */
+	unsigned char *include = malloc((size_t) (nrec ? nrec : 1));
+	if(!include) die_errno();
+	memset(include, 0, (size_t) (nrec ? nrec : 1));
+	memset(include, 1, (size_t) n);
+	/* the reference prints the N block into the .phy stream, right behind the D block (cdist.c:364-369) */
+	compare_and_print(o, ctx, n, len, minLength, include, n, names, 0, outfile, noutfile, 1);
+	ccg_destroy(ctx);
+	for(int k = 0; k < n; ++k) free(names[k]);
+	free(names);
+	free(include);
+	bytebuf_free(&header);
+	bytebuf_free(&codes);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * makeMatrix (dist.c:42-329)
+ * ------------------------------------------------------------------------------------------ */
+static void make_matrix(DistOpts *o) {
+	FILE *outfile = open_out(o->outputfilename);
+	FILE *noutfile = 0;
+	if(o->noutputfilename) {
+		if(strcmp(o->noutputfilename, o->outputfilename) == 0) noutfile = outfile;
+		else noutfile = open_out(o->noutputfilename);
+	}
+	int informat;
+	if(o->flag & 16) informat = '>';
+	else if(o->numFile) {
+		FsaReader *fr = fsa_open(o->filenames[0]);
+		if(!fr) {
+			fprintf(stderr, "Filename:\t%s\n", o->filenames[0]);
+			die_errno();
+		}
+		informat = fsa_peek(fr);
+		fsa_close(fr);
+		if(informat < 0) {
+			fprintf(stderr, "Cannot determine format of file:\t%s\n", o->filenames[0]);
+			exit(1);
+		}
+	} else informat = '#';                       /* stdin is a union file (dist.c:104) */
+	if(informat != '>') informat = '#';
+
+	if(o->targetTemplate && o->numFile > 1) {
+		if(informat == '>') dist_fasta_files(o, outfile, noutfile);
+		else dist_mat_files(o, outfile, noutfile);
+	} else if(o->numFile < 2 && informat == '#') {
+		dist_mat_union(o, outfile, noutfile);
+	} else if(o->numFile < 2) {
+		dist_fasta_msa(o, outfile, noutfile);
+	} else {
+		fprintf(stderr, "Invalid argument combination.\n");
+		exit(1);
+	}
+	if(outfile != stdout) fclose(outfile);
+	else fflush(stdout);
+	if(noutfile && noutfile != outfile && noutfile != stdout) fclose(noutfile);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * main_dist (dist.c:473-840): options
+ * ------------------------------------------------------------------------------------------ */
+static int help_message(FILE *out) {
+	static const struct { char c; const char *name, *desc, *def; } rows[] = {
+		{'i', "input", "Input file(s)", "stdin"},
+		{'o', "output", "Output file", "stdout"},
+		{'n', "nucleotide_numbers", "Output number of nucleotides included", "False/None"},
+		{'S', "separator", "Separator", "\\t"},
+		{'x', "print_precision", "Floating point print precision", "9"},
+		{'y', "methylation_motifs", "Mask methylation motifs from <file> (not on the GPU path)", "False/None"},
+		{'V', "nucleotide_variations", "Output nucleotide variations (not on the GPU path)", "False/None"},
+		{'r', "reference", "Target reference", "None"},
+		{'a', "add", "Add file to existing matrix (not on the GPU path)", ""},
+		{'E', "min_depth", "Minimum depth", "15"},
+		{'C', "min_cov", "Minimum coverage", "50.0%"},
+		{'L', "min_len", "Minimum overlapping length", "1"},
+		{'W', "normalization_weight", "Normalization weight", "0 / None"},
+		{'P', "proximity", "Minimum proximity between SNPs (only 0 on the GPU path)", "0"},
+		{'f', "flag", "Output flags", "1"},
+		{'F', "flag_help", "Help on option \"-f\"", ""},
+		{'d', "distance", "Distance method", "cos"},
+		{'D', "distance_help", "Help on option \"-d\"", ""},
+		{'l', "significance_lvl", "Minimum lvl. of significance", "0.05"},
+		{'p', "float_precision", "Float precision on distance matrix", "double"},
+		{'s', "short_precision", "Short precision on distance matrix", "double / 1e0"},
+		{'b', "byte_precision", "Byte precision on distance matrix", "double / 1e0"},
+		{'H', "mmap", "Accepted for compatibility (matrices live in pinned host memory)", "False"},
+		{'T', "tmp", "Accepted for compatibility", ""},
+		{'t', "threads", "Number of host threads (file parsing)", "1"},
+		{'h', "help", "Shows this helpmessage", ""},
+	};
+	fprintf(out, "#ccphylo-b200 dist: distances between samples from KMA consensus alignments or count matrices, computed on a B200 GPU.\n");
+	fprintf(out, "#   %-24s\t%-32s\t%s\n", "Options are:", "Desc:", "Default:");
+	for(size_t k = 0; k < sizeof(rows) / sizeof(rows[0]); ++k)
+		fprintf(out, "#    -%c, --%-16s\t%-32s\t%s\n", rows[k].c, rows[k].name, rows[k].desc, rows[k].def);
+	return out == stderr;
+}
+
+static char short_of(const char *longname) {
+	static const struct { const char *name; char c; } map[] = {
+		{"input", 'i'}, {"output", 'o'}, {"nucleotide_numbers", 'n'}, {"separator", 'S'}, {"print_precision", 'x'},
+		{"methylation_motifs", 'y'}, {"nucleotide_variations", 'V'}, {"reference", 'r'}, {"add", 'a'}, {"min_depth", 'E'},
+		{"min_cov", 'C'}, {"min_len", 'L'}, {"normalization_weight", 'W'}, {"proximity", 'P'}, {"flag", 'f'},
+		{"flag_help", 'F'}, {"distance", 'd'}, {"distance_help", 'D'}, {"significance_lvl", 'l'}, {"float_precision", 'p'},
+		{"short_precision", 's'}, {"byte_precision", 'b'}, {"mmap", 'H'}, {"tmp", 'T'}, {"threads", 't'}, {"help", 'h'},
+	};
+	for(size_t k = 0; k < sizeof(map) / sizeof(map[0]); ++k)
+		if(strcmp(map[k].name, longname) == 0) return map[k].c;
+	return 0;
+}
+
+int main_dist(int argc, char **argv) {
+	DistOpts o;
+	memset(&o, 0, sizeof(o));
+	o.precision = 9;
+	o.elem_size = 8;
+	o.byteScale = 1.0;
+	o.flag = 1;
+	o.minDepth = 15;
+	o.minLength = 1;
+	o.threads = 1;
+	o.outputfilename = "-";
+	o.minCov = 0.5;
+	o.alpha = 0.05;
+	o.method = "cos";
+	o.sep = '\t';
+	int flag_help = 0;
+
+	OptScan sc;
+	optscan_init(&sc, argc - 1, argv + 1);
+	char c, longname[64];
+	while(optscan_next(&sc, &c, longname, sizeof(longname))) {
+		char word[80];
+		if(!c) {
+			c = short_of(longname);
+			if(!c) {
+				snprintf(word, sizeof(word), "--%s", longname);
+				die_unknown(word);
+			}
+		}
+		switch(c) {
+			case 'i': o.filenames = optscan_list(&sc, (int *) &o.numFile); break;
+			case 'o': o.outputfilename = optscan_arg(&sc); break;
+			case 'n': o.noutputfilename = optscan_arg(&sc); break;
+			case 'S': o.sep = (char) optscan_char(&sc); break;
+			case 'x': o.precision = (int) optscan_long(&sc); break;
+			case 'y': o.methfilename = optscan_arg(&sc); break;
+			case 'V': o.diffilename = optscan_arg(&sc); break;
+			case 'r': o.targetTemplate = optscan_arg(&sc); break;
+			case 'a': o.addfilename = optscan_arg(&sc); break;
+			case 'E': o.minDepth = (unsigned) optscan_double(&sc); break;
+			case 'C': o.minCov = optscan_double(&sc) / 100; break;
+			case 'L': o.minLength = (unsigned) optscan_long(&sc); break;
+			case 'W': o.norm = (unsigned) optscan_long(&sc); break;
+			case 'P': o.proxi = (unsigned) optscan_long(&sc); break;
+			case 'f': o.flag = (unsigned) optscan_long(&sc); break;
+			case 'F': flag_help = 1; break;
+			case 'd': o.method = optscan_arg(&sc); break;
+			case 'D': o.method = 0; break;
+			case 'l': o.alpha = optscan_double(&sc); break;
+			case 'p': o.elem_size = 4; break;
+			case 's': o.elem_size = 2; o.byteScale = optscan_optional_double(&sc, o.byteScale); break;
+			case 'b': o.elem_size = 1; o.byteScale = optscan_optional_double(&sc, o.byteScale); break;
+			case 'H': break;
+			case 'T': (void) optscan_arg(&sc); break;
+			case 't': o.threads = (int) optscan_long(&sc); break;
+			case 'h': return help_message(stdout);
+			default:
+				snprintf(word, sizeof(word), "-%c", c);
+				die_unknown(word);
+		}
+	}
+	/* trailing words are input files (dist.c:685-689) */
+	if(sc.pos < sc.argc) {
+		if(strcmp(sc.argv[sc.pos], "--") == 0) ++sc.pos;
+		if(sc.pos < sc.argc) {
+			o.filenames = sc.argv + sc.pos;
+			o.numFile = (unsigned) (sc.argc - sc.pos);
+		}
+	}
+	if(o.minCov < 0 || 1 < o.minCov) die_invalid("\"--min_cov\"");
+	if(o.byteScale == 0) die_invalid(o.elem_size == 2 ? "\"--short_precision\"" : "\"--byte_precision\"");
+	if(o.alpha < 0) die_invalid("\"--significance_lvl\"");
+	if(flag_help) {
+		fprintf(stdout, "# Format flags output, add them to combine them.\n#\n"
+		                "#   1:\tRelaxed Phylip\n"
+		                "#   2:\tDistances are pairwise, always true on *.mat files\n"
+		                "#   4:\tInclude template name in phylip file\n"
+		                "#   8:\tInclude insignificant bases in distance calculation, only affects fasta input\n"
+		                "#  16:\tDistances based on fasta input\n"
+		                "#  32:\tDo not include insignificant bases in pruning\n#\n");
+		return 0;
+	}
+	if(!o.method) {
+		dist_mat_method_help(stdout);
+		return 0;
+	}
+	if(dist_mat_parse_method(&o)) die_invalid(o.method_err);
+	if(!o.numFile && o.targetTemplate) o.numFile = 1;
+
+	if(o.addfilename || o.diffilename || o.methfilename || o.proxi) {
+		fprintf(stderr, "%s is not available on the GPU path of dist (use the CPU ccphylo for it).\n",
+		        o.addfilename ? "-a / --add" : o.diffilename ? "-V / --nucleotide_variations" :
+		        o.methfilename ? "-y / --methylation_motifs" : "-P / --proximity");
+		return 1;
+	}
+	make_matrix(&o);
+	return 0;
+}
+
+int main(int argc, char **argv) {
+	if(argc < 2 || strcmp(argv[1], "-h") == 0 || strcmp(argv[1], "--help") == 0) {
+		fprintf(argc < 2 ? stderr : stdout,
+		        "# ccphylo-b200 %s\n# usage: ccphylo-b200 dist [options]   (`ccphylo-b200 dist -h` lists them)\n", VERSION);
+		return argc < 2;
+	}
+	if(strcmp(argv[1], "-v") == 0 || strcmp(argv[1], "--version") == 0) {
+		fprintf(stdout, "ccphylo-b200-%s\n", VERSION);
+		return 0;
+	}
+	if(strcmp(argv[1], "dist") == 0) return main_dist(argc - 1, argv + 1);
+	fprintf(stderr, "Invalid tool specified: %s (this build provides `dist` only)\n", argv[1]);
+	return 1;
+}

@@ -1,0 +1,29 @@
+/* dist_opts.h -- parsed options of `dist` (dist.c:484-506 defaults) shared by the FASTA and .mat drivers */
+#ifndef CCB_DIST_OPTS_H
+#define CCB_DIST_OPTS_H
+
+#include <stdio.h>
+
+typedef struct {
+	unsigned numFile;
+	char **filenames;
+	char *outputfilename, *noutputfilename, *methfilename, *diffilename, *addfilename;
+	char *targetTemplate;
+	char *method;              /* -d */
+	int method_id;             /* CCG_MAT_* */
+	unsigned method_order;     /* n of l<n> / nl<n> */
+	char method_err[32];
+	double minCov, alpha, byteScale;
+	unsigned flag, norm, minDepth, minLength, proxi;
+	int elem_size, precision, threads;
+	char sep;
+} DistOpts;
+
+/* dist_mat.c: KMA .mat count-matrix inputs (ltdmatrixthrd.c:376, ltdmatrix.c:32) */
+void dist_mat_files(const DistOpts *o, FILE *outfile, FILE *noutfile);
+void dist_mat_union(const DistOpts *o, FILE *outfile, FILE *noutfile);
+void dist_mat_method_help(FILE *out);
+/* 0 on success; on failure o->method_err names the option for "Invalid value parsed at ..." */
+int dist_mat_parse_method(DistOpts *o);
+
+#endif

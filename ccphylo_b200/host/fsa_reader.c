@@ -162,3 +162,28 @@ int fsa_read_codes(FsaReader *r, const unsigned char table[256], ByteBuf *codes)
 		if(!refill(r)) return 1;             /* end of file ends the record */
 	}
 }
+
+int fsa_read_line(FsaReader *r, ByteBuf *line) {
+	line->len = 0;
+	if(r->pos == r->avail && !refill(r)) return 0;
+	for(;;) {
+		const unsigned char *p = r->buf + r->pos;
+		const size_t have = r->avail - r->pos;
+		const unsigned char *nl = memchr(p, '\n', have);
+		const size_t take = nl ? (size_t) (nl - p) : have;
+		if(line->cap - line->len < take + 1) {
+			while(line->cap - line->len < take + 1) line->cap <<= 1;
+			line->data = realloc(line->data, line->cap);
+			if(!line->data) {
+				fprintf(stderr, "Error: %d (%s)\n", errno, strerror(errno));
+				exit(errno ? errno : 1);
+			}
+		}
+		memcpy(line->data + line->len, p, take);
+		line->len += take;
+		r->pos += take + (nl ? 1 : 0);
+		if(nl || !refill(r)) break;
+	}
+	line->data[line->len] = 0;
+	return 1;
+}

@@ -37,4 +37,7 @@ int fsa_next_header(FsaReader *r, ByteBuf *header);
  * only if the stream was already exhausted (seqparse.c:195) */
 int fsa_read_codes(FsaReader *r, const unsigned char table[256], ByteBuf *codes);
 
+/* next text line without its '\n' (0-terminated, len excludes the terminator); 0 at end of file */
+int fsa_read_line(FsaReader *r, ByteBuf *line);
+
 #endif

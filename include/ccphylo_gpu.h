@@ -199,6 +199,33 @@ float ccg_last_compare_ms(ccg_ctx *ctx);
  * expansion (phase 0) or int8 GEMM launch (phase 1); < 0 if unavailable */
 float ccg_last_phase_ms(ccg_ctx *ctx, int phase);
 
+/* ---------------------------------------------------------------------------
+ * KMA count-matrix (.mat) inputs: replaces ltdMatrixThrd (ltdmatrixthrd.c:376, called at
+ * dist.c:168) / ltdMatrix_get (ltdmatrix.c:32, dist.c:264) with cmpMats (matcmp.c:448) and the
+ * -d method table of dist.c:738-786.  Every sample's template is uploaded ONCE (the reference
+ * re-reads sample j's file for every cell (i, j)).
+ * ------------------------------------------------------------------------- */
+enum {
+	CCG_MAT_COS = 0, CCG_MAT_Z, CCG_MAT_CHI2, CCG_MAT_NCHI2, CCG_MAT_C, CCG_MAT_NC, CCG_MAT_P, CCG_MAT_NP,
+	CCG_MAT_BC, CCG_MAT_NBC, CCG_MAT_L1, CCG_MAT_L2, CCG_MAT_LINF, CCG_MAT_LN, CCG_MAT_NL1, CCG_MAT_NL2,
+	CCG_MAT_NLINF, CCG_MAT_NLN, CCG_MAT_METHODS
+};
+
+/* n sample slots of at most max_len positions (rows of the template whose reference base is
+ * not '-': insertion rows are dropped by the caller, as stripMat matcmp.c:27 intends). */
+int ccg_mat_set_problem(ccg_ctx *ctx, int n, int max_len);
+/* counts6: len x 6 u16 in the reference's order A, C, G, T, -, N (matparse.c:254-259);
+ * totals: len x u32 row totals, or NULL to sum the six counts.  Host pointers. */
+int ccg_mat_put_sample(ccg_ctx *ctx, int idx, const uint16_t *counts6, const uint32_t *totals, int len);
+/* All pairs of the samples with include[i] != 0 (NULL = all slots).  method is a CCG_MAT_* id,
+ * order the n of l<n> / nl<n>, alpha the -l level of `z`.  D, N (N may be NULL): HOST buffers of
+ * Dn(Dn-1)/2 cells of elem_size bytes; a pair without sufficient overlap (matcmp.c:485) gets
+ * D = -1, N = 0.  rows_inc (may be NULL): u32 rowsInc of every cell, 0 for such pairs, so the
+ * caller can print the reference's "No sufficient overlap" lines. */
+int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha,
+                unsigned norm, unsigned minDepth, unsigned minLength, double minCov, int elem_size,
+                double byteScale, void *D, void *N, int *Dn, uint32_t *rows_inc);
+
 /* Roofline denominator for the tensor-core kernel: runs a loads-free loop of the kernel's own
  * MMA shape (tcgen05 kind::i8, cta_group::2, 256 x 256 x 32, operands static in shared memory)
  * on every CTA pair for about target_ms and returns the rate in int8 TOP/s (2 ops per MAC);

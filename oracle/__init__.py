@@ -62,8 +62,51 @@ def lib():
         L.orc_fsa_cmp_global.restype = C.c_int
         L.orc_fsa_cmp_global.argtypes = [C.c_int, C.c_int, _u64p, C.c_long, _u8p, _u32p, C.c_uint, C.c_int,
                                          C.c_double, C.c_void_p, C.POINTER(C.c_uint)]
+        _u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+        _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+        _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+        L.orc_mat_matrix.restype = C.c_int
+        L.orc_mat_matrix.argtypes = [C.c_int, C.c_uint, C.c_double, C.c_int, C.c_long, _u16p, _u32p, _i32p, _u8p,
+                                     C.c_uint, C.c_uint, C.c_uint, C.c_double, _f64p, _f64p]
         _lib = L
     return _lib
+
+
+# ----------------------------------------------------------------------------
+# count-matrix (.mat) path: mat_oracle.c
+# ----------------------------------------------------------------------------
+MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "ln", "nl1", "nl2",
+               "nlinf", "nln"]
+
+
+def mat_method(name):
+    """'-d' name -> (method id, order) with the reference's precedence (dist.c:738-786)."""
+    if name in MAT_METHODS and name not in ("ln", "nln"):
+        return MAT_METHODS.index(name), 0
+    if name.startswith("l"):
+        return MAT_METHODS.index("ln"), int(name[1:])
+    if name.startswith("nl"):
+        return MAT_METHODS.index("nln"), int(name[2:])
+    raise ValueError(name)
+
+
+def mat_matrix(counts, totals, lens, include=None, method="cos", alpha=0.05, norm=0, min_depth=15, min_length=1,
+               min_cov=0.5):
+    """counts (n, L, 6) u16 [A,C,G,T,-,N], totals (n, L) u32, lens (n,) -> (D, N, Dn) packed doubles
+    over the included samples (cmpMats + ltdMatrixThrd); D = -1 / N = 0 without sufficient overlap."""
+    counts = np.ascontiguousarray(counts, dtype=np.uint16)
+    totals = np.ascontiguousarray(totals, dtype=np.uint32)
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    n, lmax = totals.shape
+    inc = np.ones(n, np.uint8) if include is None else np.ascontiguousarray(include, dtype=np.uint8)
+    mid, order = mat_method(method)
+    D = np.zeros(max(cells(n), 1))
+    N = np.zeros(max(cells(n), 1))
+    dn = lib().orc_mat_matrix(mid, order, alpha, n, lmax, counts, totals, lens, inc, norm, min_depth, min_length,
+                              min_cov, D, N)
+    if dn < 0:
+        raise RuntimeError("a sample fails its own inclusion gate inside a pair (the reference exits there)")
+    return D[:cells(dn)], N[:cells(dn)], dn
 
 
 # ----------------------------------------------------------------------------

@@ -183,3 +183,56 @@ def golden_cases(skip_buggy_global=True):
             continue                      # reference picks wrong pairs here
         out.append(cs)
     return g["pool"], out
+
+
+# ----------------------------------------------------------------------------
+# KMA count matrices (.mat): text <-> arrays, and the reference's gates
+# ----------------------------------------------------------------------------
+def mat_text(template, ref, counts_file_order):
+    """'#template' block: rows ref\tA\tC\tG\tT\tN\t- , blank line at the end."""
+    rows = [f"#{template}"]
+    for b, c in zip(ref, counts_file_order):
+        rows.append(b + "\t" + "\t".join(str(int(x)) for x in c))
+    return "\n".join(rows) + "\n\n"
+
+
+def parse_mat(text, template):
+    """-> (counts (L, 6) u16 in storage order A,C,G,T,-,N; totals (L,) u32) of the template's
+    non-insertion rows, or None if the template is absent."""
+    lines = text.split("\n")
+    try:
+        k = lines.index("#" + template) + 1
+    except ValueError:
+        return None
+    counts, totals = [], []
+    while k < len(lines) and lines[k] and not lines[k].startswith("#"):
+        f = lines[k].split("\t")
+        v = [int(x) for x in f[1:7]]
+        if f[0] != "-":
+            counts.append([v[0], v[1], v[2], v[3], v[5], v[4]])
+            totals.append(sum(v))
+        k += 1
+    return np.array(counts, dtype=np.uint16).reshape(-1, 6), np.array(totals, dtype=np.uint32)
+
+
+def mat_sample_gate(totals, min_depth, min_length, min_cov):
+    """ltdmatrixthrd.c:455-458 / :523-526: is the sample included?"""
+    n_nucs = int((totals >= min_depth).sum())
+    return not (n_nucs < min_length or n_nucs < min_cov * len(totals))
+
+
+def format_phy_cells(names, cells, precision=9, comment=None, flags=1):
+    """printphy (phy.c:59-123) for double cells."""
+    out = []
+    if flags & 4:
+        out.append(f"#{comment}")
+    out.append("%10d" % len(names))
+    k = 0
+    for r, nm in enumerate(names):
+        row = [nm if flags & 1 else "%-10.10s" % nm]
+        for _ in range(r):
+            d = float(cells[k])
+            k += 1
+            row.append("%d" % int(d) if d == int(d) else "%.*f" % (precision, d))
+        out.append("\t".join(row))
+    return "\n".join(out) + "\n"

@@ -1,0 +1,130 @@
+"""The host driver `ccphylo-b200 dist` end to end on the GPU box: the reference binary's golden
+.phy / .num / stderr text must come out byte for byte for FASTA inputs (multi-file, MSA, every
+cell type, shared-mask mode), and within the printed precision for .mat inputs (files, gz, union)."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "ccphylo_b200", "bin", "ccphylo-b200")
+
+POOL, ALL_CASES = helpers.golden_cases()
+# every invocation pays a CUDA context start (~2 s): replay a representative third of the fixture here; the
+# whole fixture goes through the C-ABI in test_gpu_parity.py
+CASES = [c for c in ALL_CASES if c["name"].startswith(("c1_", "c6_", "c7_", "rand_L33_", "rand_L4100_"))]
+
+
+def run(cmd, cwd):
+    p = subprocess.run(cmd, capture_output=True, text=True, cwd=cwd, timeout=300)
+    return p
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_fasta_golden_byte_for_byte(built, tmp_path, case):
+    td = str(tmp_path)
+    seqs = [POOL[k] for k in case["seq_ids"]]
+    if case["msa"]:
+        path = os.path.join(td, "msa.fsa")
+        with open(path, "w") as f:
+            for nm, s in zip(case["names"], seqs):
+                f.write(f">{nm}\n{s}\n")
+        cmd = [BIN, "dist", "-i", path]
+    else:
+        files = []
+        for nm, s in zip(case["names"], seqs):
+            path = os.path.join(td, nm)
+            with open(path, "w") as f:
+                f.write(f">ref\n{s}\n")
+            files.append(path)
+        cmd = [BIN, "dist", "-r", "ref", "-i"] + files
+    phy, num = os.path.join(td, "o.phy"), os.path.join(td, "o.num")
+    p = run(cmd + case["args"] + ["-o", phy, "-n", num, "-t", "3"], td)
+    assert p.returncode == case["returncode"], p.stderr
+    assert open(phy).read() == case["phy"]
+    assert open(num).read() == case["num"]
+    assert p.stderr.replace(td + "/", "") == case["stderr"]
+
+
+def test_fasta_gz_input_stdout_and_long_options(built, tmp_path):
+    case = next(c for c in CASES if c["name"] == "c1_pair_W")
+    td = str(tmp_path)
+    files = []
+    for nm, k in zip(case["names"], case["seq_ids"]):
+        path = os.path.join(td, nm + ".gz")
+        with gzip.open(path, "wt") as f:
+            f.write(">other\nACGT\n>ref\n" + "\n".join(POOL[k][s:s + 10] for s in range(0, len(POOL[k]), 10)) + "\n")
+        files.append(path)
+    p = run([BIN, "dist", "--reference", "ref", "--flag=3", "--normalization_weight", "1000000", "--input"] + files, td)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout == case["phy"].replace("s0\n", "s0.gz\n").replace("s1\t", "s1.gz\t").replace("s2\t", "s2.gz\t").replace("s3\t", "s3.gz\t")
+
+
+def test_refused_options_and_errors(built, tmp_path):
+    td = str(tmp_path)
+    a = os.path.join(td, "a.fsa")
+    with open(a, "w") as f:
+        f.write(">ref\nACGT\n")
+    p = run([BIN, "dist", "-r", "ref", "-i", a, a, "-P", "3"], td)
+    assert p.returncode == 1 and "not available on the GPU path" in p.stderr
+    p = run([BIN, "dist", "-r", "ref", "-i", a, os.path.join(td, "missing.fsa")], td)
+    assert p.returncode != 0
+    p = run([BIN, "dist", "--nope"], td)
+    assert p.returncode == 1 and p.stderr == 'Unknown argument or option: "--nope"\n'
+
+
+G = helpers.load_golden("mat_dist.json")
+
+
+def _cmp_phy(text, ref_text, precision, exact):
+    got, ref = helpers.parse_phy(text), helpers.parse_phy(ref_text)
+    assert len(got) == len(ref)
+    for (gn, gc), (rn, rc) in zip(got, ref):
+        assert gn == rn
+        gc, rc = np.array(gc), np.array(rc)
+        if exact:
+            assert np.array_equal(gc, rc)
+        else:
+            assert np.all(np.abs(gc - rc) <= 1.01 * 10.0 ** (-precision) + 1e-6 * np.abs(rc))
+
+
+MAT_CLI = [c for c in G["cases"] if c["name"] in ("c8_cos", "c8_cos_W", "c8_cos_gz", "c8_cos_f5", "c8_chi2_x3", "rand_cos", "rand_z",
+                                                   "rand_nl3", "rand_cos_W_E30", "rand_bc_t3_gz", "rand_l2_C90",
+                                                   "overlap_fail", "union_cos_f5", "union_chi2")]
+
+
+@pytest.mark.parametrize("case", MAT_CLI, ids=lambda c: c["name"])
+def test_mat_golden(built, tmp_path, case):
+    from test_mat_oracle_golden import mat_args
+    td = str(tmp_path)
+    o = mat_args(case["args"])
+    texts = [G["pool"][k] for k in case["text_ids"]]
+    phy, num = os.path.join(td, "o.phy"), os.path.join(td, "o.num")
+    if case["mode"] == "files":
+        files = []
+        for nm, text in zip(case["names"], texts):
+            path = os.path.join(td, nm + (".gz" if case["gz"] else ""))
+            with (gzip.open(path, "wt") if case["gz"] else open(path, "w")) as f:
+                f.write(text)
+            files.append(path)
+        cmd = [BIN, "dist", "-r", case["template"], "-i"] + files
+    else:
+        for nm, text in zip(case["names"], texts):
+            with gzip.open(os.path.join(td, nm), "wt") as f:
+                f.write(text)
+        upath = os.path.join(td, "in.union")
+        with open(upath, "w") as f:
+            f.write(case["union"].replace("@TD@/", td + "/"))
+        cmd = [BIN, "dist", "-i", upath]
+    p = run(cmd + case["args"] + ["-o", phy, "-n", num], td)
+    assert p.returncode == case["returncode"], p.stderr
+    _cmp_phy(open(phy).read(), case["phy"], o["precision"], exact=False)
+    _cmp_phy(open(num).read(), case["num"], o["precision"], exact=True)
+    assert sorted(p.stderr.replace(td + "/", "").splitlines()) == sorted(case["stderr"].splitlines())
+    # the comment lines of -f 4 come through as well
+    assert [l for l in open(phy).read().splitlines() if l.startswith("#")] == [l for l in case["phy"].splitlines() if l.startswith("#")]

@@ -1,0 +1,129 @@
+"""GPU parity of the count-matrix (.mat) path: k_matdist through the C-ABI (ccg_mat_*) against the
+CPU oracle (oracle/mat_oracle.c, pinned to the reference's golden text) for all 18 -d methods.
+Bar: the inclusion counts N (rowsInc) and the -1 / 0 cells of pairs without sufficient overlap are
+exact; distances are within 1e-6 relative (north star) -- the GPU adds the per-position terms per
+K slice, the reference strictly left to right, and pow / erf differ from glibc in the last ulps."""
+import numpy as np
+import pytest
+
+import helpers
+import oracle
+from ccphylo_b200 import api
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-6
+ALL = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "l3", "nl1", "nl2", "nlinf",
+       "nl3"]
+
+
+def random_counts(n, length, seed, depth=40, low=0.02):
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, size=length)
+    counts = rng.poisson(0.3, size=(n, length, 6)).astype(np.uint16)
+    for i in range(n):
+        call = np.where(rng.random(length) < 0.02, (ref + rng.integers(1, 4, size=length)) % 4, ref)
+        d = rng.poisson(depth, size=length)
+        d = np.where(rng.random(length) < low, rng.integers(0, 6, size=length), d)
+        counts[i, np.arange(length), call] += d.astype(np.uint16)
+    totals = counts.astype(np.uint32).sum(axis=2).astype(np.uint32)
+    return counts, totals
+
+
+def close(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= REL_TOL * np.abs(b) + 1e-12)
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = api.Context()
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("method", ALL)
+def test_all_methods_against_the_oracle(ctx, method):
+    n, length = 37, 2000 + 13
+    counts, totals = random_counts(n, length, seed=ALL.index(method) + 5)
+    lens = np.full(n, length, np.int32)
+    include = np.ones(n, np.uint8)
+    include[[4, 20]] = 0
+    ctx.mat_set_problem(n, length)
+    for i in range(n):
+        ctx.mat_put_sample(i, counts[i], totals[i])
+    for norm in (0, 1000):
+        D, N, dn, rows = ctx.mat_run(include, method=method, norm=norm)
+        Do, No, dno = oracle.mat_matrix(counts, totals, lens, include, method=method, norm=norm)
+        assert dn == dno == n - 2
+        assert np.array_equal(N, No)
+        assert np.array_equal(rows, No.astype(np.uint32))
+        assert close(D, Do), float(np.max(np.abs(D - Do) / np.maximum(np.abs(Do), 1e-300)))
+    assert "k_matdist" in ctx.last_kernel
+
+
+def test_depth_gate_overlap_gate_and_short_samples(ctx):
+    n, length = 18, 900
+    counts, totals = random_counts(n, length, seed=99, low=0.3)
+    lens = np.full(n, length, np.int32)
+    # two samples whose covered halves are disjoint: D = -1, N = 0 for that pair
+    counts[5, : length // 2 + 40] = 0
+    counts[9, length // 2 - 40:] = 0
+    lens[12] = 700                                         # a shorter template instance (rows beyond are absent)
+    counts[12, 700:] = 0
+    totals = counts.astype(np.uint32).sum(axis=2).astype(np.uint32)
+    ctx.mat_set_problem(n, length)
+    for i in range(n):
+        ctx.mat_put_sample(i, counts[i, :lens[i]], totals[i, :lens[i]])
+    for kw in (dict(min_depth=15, min_cov=0.3), dict(min_depth=30, min_cov=0.1, norm=1000000), dict(min_depth=0, min_cov=0.0)):
+        D, N, dn, rows = ctx.mat_run(None, method="cos", **kw)
+        Do, No, dno = oracle.mat_matrix(counts, totals, lens, None, method="cos", **kw)
+        assert dn == dno == n
+        assert np.array_equal(N, No)
+        assert np.array_equal(D == -1.0, Do == -1.0)
+        assert close(D, Do)
+    assert (Do == -1.0).any()
+
+
+@pytest.mark.parametrize("elem,scale", [(4, 1.0), (2, 10.0), (1, 0.1)])
+def test_cell_types(ctx, elem, scale):
+    n, length = 20, 640
+    counts, totals = random_counts(n, length, seed=7)
+    ctx.mat_set_problem(n, length)
+    for i in range(n):
+        ctx.mat_put_sample(i, counts[i], totals[i])
+    D8, N8, dn, _ = ctx.mat_run(None, method="l1")
+    D, N, _, _ = ctx.mat_run(None, method="l1", elem_size=elem, byte_scale=scale)
+    if elem == 4:
+        assert np.array_equal(D, D8.astype(np.float32)) and np.array_equal(N, N8.astype(np.float32))
+    else:
+        # dtouc(value, 0.5) truncated into the cell (bytescale.h:22); l1 distances are integers
+        mask = (1 << (8 * elem)) - 1
+        assert np.array_equal(D.astype(np.int64), (D8 * scale + 0.5).astype(np.int64) & mask)
+        assert np.array_equal(N.astype(np.int64), (N8 * scale + 0.5).astype(np.int64) & mask)
+
+
+G = helpers.load_golden("mat_dist.json")
+FILES = [c for c in G["cases"] if c["mode"] == "files"]
+
+
+@pytest.mark.parametrize("case", FILES, ids=lambda c: c["name"])
+def test_golden_cases_through_the_abi(ctx, case):
+    """The reference's own numbers: parse the fixture's .mat text, gate the samples as
+    ltdMatrixThrd does, run the GPU path, compare with the printed matrices."""
+    from test_mat_oracle_golden import mat_args
+    o = mat_args(case["args"])
+    parsed = [helpers.parse_mat(G["pool"][k], case["template"]) for k in case["text_ids"]]
+    keep = [pm for pm in parsed if pm is not None and helpers.mat_sample_gate(pm[1], o["min_depth"], o["min_length"], o["min_cov"])]
+    lmax = max(len(t) for _, t in keep)
+    ctx.mat_set_problem(len(keep), lmax)
+    for k, (c, t) in enumerate(keep):
+        ctx.mat_put_sample(k, c, t)
+    D, N, dn, _ = ctx.mat_run(None, method=o["method"], norm=o["norm"], min_depth=o["min_depth"], min_length=o["min_length"],
+                              min_cov=o["min_cov"])
+    (names, dref), = helpers.parse_phy(case["phy"])
+    (_, nref), = helpers.parse_phy(case["num"])
+    assert dn == len(names)
+    assert np.array_equal(N, np.array(nref))
+    # the text carries `precision` decimals
+    tol = 0.51 * 10.0 ** (-o["precision"])
+    assert np.all(np.abs(D - np.array(dref)) <= tol + REL_TOL * np.abs(np.array(dref)))
