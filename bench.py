@@ -368,35 +368,65 @@ def main():
         if not parity:
             raise SystemExit("bench.py: GPU result differs from the oracle -- number withheld")
 
-    # ---- e2e: host buffers through the reference-facing C-ABI call ----
+    # ---- e2e: host buffers through the reference-facing C-ABI ----
+    # N = 1: the one-call drop-in ccg_fsa_cmp_thread_out (host row pointers in, host matrices out; the library
+    #        streams the rows K slab by K slab under the GEMM).
+    # N > 1: every rank uploads only ITS shard of the samples (n/N rows: the PCIe links work in parallel instead
+    #        of every rank pulling the rows of its tiles through the same host memory), the packed rows are
+    #        all-gathered over NVLink (NCCL: the one real exchange step of this path), then ccg_put_samples_packed_dev
+    #        + ccg_run_pair with host matrices out.
     e2e = None
     if not args.no_e2e:
         L = api.load()
         import ctypes as C
         row_s, row_m = W * 8, W * 4
-        hs_ptr = L.ccg_host_alloc(n * row_s)
-        hm_ptr = L.ccg_host_alloc(n * row_m)
+        sharded = world > 1 and n % world == 0
+        n_host = n // world if sharded else n
+        r0 = rank * n_host if sharded else 0
+        hs_ptr = L.ccg_host_alloc(n_host * row_s)
+        hm_ptr = L.ccg_host_alloc(n_host * row_m)
         hD_ptr = L.ccg_host_alloc(max(ncell, 1) * 8)
         hN_ptr = L.ccg_host_alloc(max(ncell, 1) * 8)
         if not (hs_ptr and hm_ptr and hD_ptr and hN_ptr):
             raise SystemExit("bench.py: pinned host allocation failed")
-        hs = np.ctypeslib.as_array(C.cast(hs_ptr, C.POINTER(C.c_uint64)), shape=(n, W))
-        hm = np.ctypeslib.as_array(C.cast(hm_ptr, C.POINTER(C.c_uint32)), shape=(n, W))
+        hs = np.ctypeslib.as_array(C.cast(hs_ptr, C.POINTER(C.c_uint64)), shape=(n_host, W))
+        hm = np.ctypeslib.as_array(C.cast(hm_ptr, C.POINTER(C.c_uint32)), shape=(n_host, W))
         hs_t = torch.from_numpy(hs.view(np.int64))
         hm_t = torch.from_numpy(hm.view(np.int32))
-        hs_t.copy_(seqs_t)                      # device -> pinned host, no pageable intermediate
-        hm_t.copy_(masks_t)
+        hs_t.copy_(seqs_t[r0:r0 + n_host])                      # device -> pinned host, no pageable intermediate
+        hm_t.copy_(masks_t[r0:r0 + n_host])
         torch.cuda.synchronize()
-        sp = (C.c_void_p * n)(*[hs_ptr + k * row_s for k in range(n)])
-        mp = (C.c_void_p * n)(*[hm_ptr + k * row_m for k in range(n)])
         include = np.ones(n, dtype=np.uint8)
         dn, ginc = C.c_int(0), C.c_uint(0)
+        if not sharded:
+            sp = (C.c_void_p * n)(*[hs_ptr + k * row_s for k in range(n)])
+            mp = (C.c_void_p * n)(*[hm_ptr + k * row_m for k in range(n)])
 
-        def e2e_step():
-            rc = L.ccg_fsa_cmp_thread_out(ctx._h, 1, hD_ptr, hN_ptr, 8, 1.0, n, length, sp, include.ctypes.data, mp,
-                                          0, 1, 0.5, 0, C.byref(dn), C.byref(ginc))
-            if rc:
-                raise SystemExit("ccg_fsa_cmp_thread_out failed: " + L.ccg_last_error(ctx._h).decode())
+            def e2e_step():
+                rc = L.ccg_fsa_cmp_thread_out(ctx._h, 1, hD_ptr, hN_ptr, 8, 1.0, n, length, sp, include.ctypes.data, mp,
+                                              0, 1, 0.5, 0, C.byref(dn), C.byref(ginc))
+                if rc:
+                    raise SystemExit("ccg_fsa_cmp_thread_out failed: " + L.ccg_last_error(ctx._h).decode())
+            call = "ccg_fsa_cmp_thread_out(ctx, pair=1, host rows in pinned memory, host D/N out)"
+            h2d = int(n * (row_s + row_m))
+        else:
+            # the gather lands in the buffers the device-resident arm used (same contents)
+            seqs_t.zero_()
+            masks_t.zero_()
+
+            def e2e_step():
+                seqs_t[r0:r0 + n_host].copy_(hs_t, non_blocking=True)
+                masks_t[r0:r0 + n_host].copy_(hm_t, non_blocking=True)
+                dist.all_gather_into_tensor(seqs_t, seqs_t[r0:r0 + n_host])
+                dist.all_gather_into_tensor(masks_t, masks_t[r0:r0 + n_host])
+                ctx.set_problem(n, length, pair=True)
+                ctx.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
+                rc = L.ccg_run_pair(ctx._h, include.ctypes.data, 0, 1, 0.5, 8, 1.0, hD_ptr, hN_ptr, C.byref(dn))
+                if rc:
+                    raise SystemExit("ccg_run_pair failed: " + L.ccg_last_error(ctx._h).decode())
+            call = (f"per rank: H2D of its {n_host}-sample shard (pinned rows) -> NCCL all-gather of the packed rows over "
+                    f"NVLink -> ccg_put_samples_packed_dev + ccg_run_pair(host D/N out)")
+            h2d = int(n * (row_s + row_m))                          # summed over the ranks: every row crosses PCIe once
 
         for _ in range(2):
             e2e_step()
@@ -413,12 +443,16 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e_ms = float(tt.item())
         hD = np.ctypeslib.as_array(C.cast(hD_ptr, C.POINTER(C.c_double)), shape=(max(ncell, 1),))
-        if rank == 0 and world == 1 and not np.array_equal(hD[:ncell], d_D.cpu().numpy()):
-            raise SystemExit("bench.py: host-path result differs from the device-path result")
+        hN = np.ctypeslib.as_array(C.cast(hN_ptr, C.POINTER(C.c_double)), shape=(max(ncell, 1),))
+        if rank == 0:
+            # the host-path result must equal the device-path result (rank 0's own cells when partitioned)
+            dD = d_D.cpu().numpy()
+            own = np.ones(ncell, bool) if world == 1 else (hN[:ncell] != 0)
+            if not np.array_equal(hD[:ncell][own], dD[own]) or (world > 1 and not own.any()):
+                raise SystemExit("bench.py: host-path result differs from the device-path result")
         e2e = {"value": total_basecmp / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(n * (row_s + row_m)) * world,
-               "d2h_bytes_per_step": int(2 * ncell * 8) * world, "steps": e_steps,
-               "call": "ccg_fsa_cmp_thread_out(ctx, pair=1, host rows in pinned memory, host D/N out)"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(2 * ncell * 8) * world, "steps": e_steps,
+               "call": call}
         for p in (hs_ptr, hm_ptr, hD_ptr, hN_ptr):
             L.ccg_host_free(p)
 

@@ -21,7 +21,7 @@ KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_FUSED = 0, 1, 2, 3
 
 EXPORTS = [
     "ccg_strerror", "ccg_last_error", "ccg_init", "ccg_destroy", "ccg_set_stream", "ccg_set_kernel", "ccg_sync",
-    "ccg_set_partition", "ccg_tile_rows", "ccg_tile_cols", "ccg_partition_cells", "ccg_partition_tiles",
+    "ccg_set_partition", "ccg_set_tile_window", "ccg_tile_rows", "ccg_tile_cols", "ccg_partition_cells", "ccg_partition_tiles",
     "ccg_set_scratch_limit", "ccg_set_problem", "ccg_put_global_mask", "ccg_apply_global_mask", "ccg_build_global_mask",
     "ccg_put_samples_packed",
     "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
@@ -75,6 +75,7 @@ def load():
     L.ccg_set_kernel.argtypes = [vp, i]
     L.ccg_sync.argtypes = [vp]
     L.ccg_set_partition.argtypes = [vp, i, i]
+    L.ccg_set_tile_window.argtypes = [vp, i, i, i, i]
     L.ccg_tile_rows.restype = i
     L.ccg_tile_rows.argtypes = []
     L.ccg_tile_cols.restype = i
@@ -190,6 +191,10 @@ class Context:
 
     def set_partition(self, rank, world):
         self._ck(self._L.ccg_set_partition(self._h, rank, world))
+
+    def set_tile_window(self, row_lo, row_hi=0, col_lo=0, col_hi=0):
+        """Restrict the run to rows [row_lo, row_hi) x columns [col_lo, col_hi); row_lo < 0 removes the window."""
+        self._ck(self._L.ccg_set_tile_window(self._h, row_lo, row_hi, col_lo, col_hi))
 
     def set_scratch_limit(self, nbytes):
         self._ck(self._L.ccg_set_scratch_limit(self._h, nbytes))

@@ -199,6 +199,22 @@ extern "C" int ccg_sync(ccg_ctx *ctx) {
 	return CCG_OK;
 }
 
+extern "C" int ccg_set_tile_window(ccg_ctx *ctx, int row_lo, int row_hi, int col_lo, int col_hi) {
+	if(!ctx) return CCG_ERR_ARG;
+	if(row_lo < 0) {
+		ctx->win_on = 0;
+	} else {
+		if(row_lo % CCG_UMMA_BM || col_lo % CCG_UMMA_BN || row_hi <= row_lo || col_hi <= col_lo) return CCG_ERR_ARG;
+		ctx->win_on = 1;
+		ctx->win[0] = row_lo / CCG_UMMA_BM;
+		ctx->win[1] = (row_hi + CCG_UMMA_BM - 1) / CCG_UMMA_BM;
+		ctx->win[2] = col_lo / CCG_UMMA_BN;
+		ctx->win[3] = (col_hi + CCG_UMMA_BN - 1) / CCG_UMMA_BN;
+	}
+	update_need(ctx);
+	return CCG_OK;
+}
+
 extern "C" int ccg_set_partition(ccg_ctx *ctx, int rank, int world) {
 	if(!ctx || world < 1 || rank < 0 || rank >= world) return CCG_ERR_ARG;
 	ctx->rank = rank;
@@ -309,12 +325,25 @@ static long long for_each_macro_tile(int n, int rank, int world, F f) {
 	return hi - lo;
 }
 
+/* the macro tiles this context computes: its share of the curve, restricted to the tile window
+ * (ccg_set_tile_window; the sample-shard ring computes one rectangular block per step) */
+template <class F>
+static long long for_each_ctx_tile(const ccg_ctx *ctx, F f) {
+	long long k = 0;
+	for_each_macro_tile(ctx->n, ctx->rank, ctx->world, [&](int tm, int tn) {
+		if(ctx->win_on && (tm < ctx->win[0] || tm >= ctx->win[1] || tn < ctx->win[2] || tn >= ctx->win[3])) return;
+		f(tm, tn);
+		++k;
+	});
+	return k;
+}
+
 /* row blocks (128 slots) the owned macro tiles read: A rows 2tm, 2tm+1, B rows 2tn, 2tn+1 */
 static void update_need(ccg_ctx *ctx) {
 	if(!ctx->need) return;
 	const int nblocks = ctx->n_pad / 128;
 	memset(ctx->need, 0, (size_t) nblocks);
-	for_each_macro_tile(ctx->n, ctx->rank, ctx->world, [&](int tm, int tn) {
+	for_each_ctx_tile(ctx, [&](int tm, int tn) {
 		const int blk[4] = {2 * tm, 2 * tm + 1, 2 * tn, 2 * tn + 1};
 		for(int q = 0; q < 4; ++q)
 			if(blk[q] < nblocks) ctx->need[blk[q]] = 1;
@@ -655,11 +684,11 @@ static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
 	/* 64x64 tiles of the macro tiles this rank owns */
 	const int n = ctx->n;
 	size_t cap = 0;
-	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int, int) { cap += (CCG_UMMA_BM / CCG_TILE) * (CCG_UMMA_BN / CCG_TILE); });
+	for_each_ctx_tile(ctx, [&](int, int) { cap += (CCG_UMMA_BM / CCG_TILE) * (CCG_UMMA_BN / CCG_TILE); });
 	int2 *host = (int2 *) malloc((cap ? cap : 1) * sizeof(int2));
 	if(!host) return CCG_ERR_NOMEM;
 	size_t cnt = 0;
-	for_each_macro_tile(n, ctx->rank, ctx->world, [&](int tm, int tn) {
+	for_each_ctx_tile(ctx, [&](int tm, int tn) {
 		for(int a = 0; a < CCG_UMMA_BM / CCG_TILE; ++a)
 			for(int b = 0; b < CCG_UMMA_BN / CCG_TILE; ++b) {
 				int ti = tm * (CCG_UMMA_BM / CCG_TILE) + a, tj = tn * (CCG_UMMA_BN / CCG_TILE) + b;
@@ -797,11 +826,11 @@ static int feed_slab(ccg_ctx *ctx, int chunk0, int nch) {
  * (2tm, tn), (2tm+1, tn) for the kernels that work on 128 x 256 tiles: d_tiles[cnt, 3 cnt) */
 static int upload_macro_tiles(ccg_ctx *ctx, size_t *cnt_out) {
 	size_t cap = 0;
-	for_each_macro_tile(ctx->n, ctx->rank, ctx->world, [&](int, int) { ++cap; });
+	for_each_ctx_tile(ctx, [&](int, int) { ++cap; });
 	int2 *host = (int2 *) malloc((cap ? 3 * cap : 1) * sizeof(int2));
 	if(!host) return CCG_ERR_NOMEM;
 	size_t cnt = 0;
-	for_each_macro_tile(ctx->n, ctx->rank, ctx->world, [&](int tm, int tn) {
+	for_each_ctx_tile(ctx, [&](int tm, int tn) {
 		host[cnt].x = tm;
 		host[cnt].y = tn;
 		host[cap + 2 * cnt].x = 2 * tm;

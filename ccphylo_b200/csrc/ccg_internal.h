@@ -84,6 +84,7 @@ struct ccg_ctx {
 	cudaEvent_t ev_fork, ev_launch, ev_x[2], ev_g[2];
 	int kernel_choice;
 	int rank, world;
+	int win_on, win[4];            /* macro-tile window [tm_lo, tm_hi) x [tn_lo, tn_hi), ccg_set_tile_window */
 	int dbg_kslices, dbg_serial, dbg_nolock, dbg_umma1;   /* CCG_KSLICES / CCG_EXPAND_SERIAL / CCG_NOLOCK / CCG_UMMA1 overrides (experiments only) */
 
 	int n, len, pair_mode;

@@ -78,6 +78,14 @@ int ccg_sync(ccg_ctx *ctx);
  * ranks are left untouched in device outputs and read back as zero in host
  * outputs.  Default rank 0 of 1. */
 int ccg_set_partition(ccg_ctx *ctx, int rank, int world);
+/* Restrict the run to the cells with row_lo <= i < row_hi and col_lo <= j < col_hi (sample slot
+ * indices; row_lo and col_lo must be multiples of ccg_tile_rows() / ccg_tile_cols(); the window
+ * is widened to whole macro tiles).  row_lo < 0 removes the window.  This is how the
+ * sample-shard ring (sets larger than one GPU's HBM) computes one shard-by-shard block per
+ * step: the resident shard in slots [0, S), the visiting one in [S, 2S), window rows [S, 2S) x
+ * columns [0, S).  Cells outside the window are left untouched. */
+int ccg_set_tile_window(ccg_ctx *ctx, int row_lo, int row_hi, int col_lo, int col_hi);
+
 /* Pure host helpers (no device needed) describing that deal: the lower
  * triangle is cut into macro tiles of ccg_tile_rows() x ccg_tile_cols()
  * samples, enumerated row-major over (tm, tn <= tm/2); the tile with index id

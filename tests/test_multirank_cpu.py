@@ -61,3 +61,54 @@ def test_two_ranks_cover_the_triangle_exactly_once(built, n):
         assert p.exitcode == 0
     assert all(v == 1 for v in owner)
     assert cells == api.cells(n)
+
+
+# ---- sample-shard ring: the schedule and the NCCL-style transport, on gloo with CPU tensors ----
+def _ring_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ccphylo_b200 import ring
+
+    tr = ring.NcclTransport(rank, world)            # the transport only needs torch.distributed P2P
+    cur = torch.full((4,), float(rank))
+    met = []
+    steps = ring.schedule(world)
+    for k, (step, shift, split) in enumerate(steps):
+        nxt = torch.empty(4)
+        works = tr.start([cur], [nxt]) if k + 1 < len(steps) else None
+        met.append((int(cur[0].item()), shift, split, ring.block_rows(rank, int(cur[0].item()), 512, split)))
+        if works is not None:
+            tr.wait(works)
+            cur = nxt
+    out.put((rank, met))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_ring_schedule_visits_every_shard_pair_once(world):
+    from ccphylo_b200 import ring
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rows = {}
+    for g, met in got.items():
+        for visitor, shift, split, (row0, nrows) in met:
+            assert visitor == (g - shift) % world            # the ring delivered the right shard at this step
+            key = (max(g, visitor), min(g, visitor))
+            rows.setdefault(key, []).append((row0, nrows))
+    assert set(rows) == {(hi, lo) for hi in range(world) for lo in range(hi + 1)}
+    for key, parts in rows.items():
+        parts.sort()
+        assert parts[0][0] == 0 and sum(p[1] for p in parts) == 512, (key, parts)
+        assert all(a[0] + a[1] == b[0] for a, b in zip(parts, parts[1:])), (key, parts)
+    assert ring.shard_size(100000, 8) == 12544 and ring.shard_size(1000, 4) == 256
