@@ -113,6 +113,9 @@ class RankState:
         lo_s, lo_m = (self.seqs, self.masks) if lo_is_mine else (other_seqs, other_masks)
         hi_s, hi_m = (other_seqs, other_masks) if lo_is_mine else (self.seqs, self.masks)
         row0, nrows = block_rows(g, h, S, split)
+        if nrows == 0:                                           # the partner's half covers the whole (one macro tile) block
+            empty = self.d_D[:0].view(0, S)
+            return max(g, h), min(g, h), row0, empty, empty, None
         ctx.set_tile_window(S + row0, S + row0 + nrows, 0, S)
         ctx.put_samples_packed_dev(lo_s.data_ptr(), lo_m.data_ptr(), S, lo_s.stride(0), first=0)
         ctx.put_samples_packed_dev(hi_s.data_ptr(), hi_m.data_ptr(), S, hi_s.stride(0), first=S)

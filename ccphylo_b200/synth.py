@@ -78,13 +78,13 @@ def make_packed_torch(n, length, seed, device, snp=SNP_RATE, nrun=NRUN_RATE, sca
     sh_code = (62 - 2 * torch.arange(32, device=device, dtype=torch.int64)).view(1, 32)
     sh_mask = (31 - torch.arange(32, device=device, dtype=torch.int64)).view(1, 32)
     valid = (torch.arange(Lp, device=device) < length)
-    nblk = Lp // NRUN_BLOCK
+    nblk = (Lp + NRUN_BLOCK - 1) // NRUN_BLOCK
     for i in range(n):
         r = torch.rand(Lp, generator=g, device=device)
         code = torch.where(r < snp, (ref + 1 + (r * 3e6).long() % 3) & 3, ref)
         known = (torch.rand(Lp, generator=g, device=device) >= scatter) & valid
         blk = torch.rand(nblk, generator=g, device=device) < nrun
-        known &= ~blk.repeat_interleave(NRUN_BLOCK)
+        known &= ~blk.repeat_interleave(NRUN_BLOCK)[:Lp]
         k64 = known.long()
         seqs[i] = ((code * k64).view(W, 32) << sh_code).sum(dim=1)
         masks[i] = (k64.view(W, 32) << sh_mask).sum(dim=1).to(torch.int32)

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3, 4])
 @pytest.mark.parametrize("kernel", [api.KERNEL_POPC, api.KERNEL_UMMA], ids=["popc", "umma"])
 def test_ring_blocks_assemble_to_the_full_matrix(built, world, kernel):
-    S, length = 256, 128 * 9 + 50
+    S, length = 512 if world % 2 == 0 else 256, 128 * 9 + 50
     n = world * S
     codes = synth.make_codes(n, length, seed=world * 7 + kernel, snp=0.02, nrun=0.05)
     seqs, masks, _ = oracle.encode_samples(codes)
@@ -34,6 +34,8 @@ def test_ring_blocks_assemble_to_the_full_matrix(built, world, kernel):
         def on_block(rank, hi, lo, row0, D, N, dn):
             torch.cuda.synchronize()
             key = (hi, lo, row0, dn)
+            if D.numel() == 0:
+                return
             assert key not in blocks, "a block was computed twice"
             blocks[key] = (D.cpu().numpy().copy(), N.cpu().numpy().copy())
 
