@@ -369,9 +369,9 @@ def main():
             raise SystemExit("bench.py: GPU result differs from the oracle -- number withheld")
 
     # ---- e2e: host buffers through the reference-facing C-ABI ----
-    # N = 1: the one-call drop-in ccg_fsa_cmp_thread_out (host row pointers in, host matrices out; the library
-    #        streams the rows K slab by K slab under the GEMM).
-    # N > 1: every rank uploads only ITS shard of the samples (n/N rows: the PCIe links work in parallel instead
+    # N <= 2: the one-call drop-in ccg_fsa_cmp_thread_out (host row pointers in, host matrices out; the library
+    #        streams the rows its tiles need K slab by K slab under the GEMM).
+    # N >= 4: every rank uploads only ITS shard of the samples (n/N rows: the PCIe links work in parallel instead
     #        of every rank pulling the rows of its tiles through the same host memory), the packed rows are
     #        all-gathered over NVLink (NCCL: the one real exchange step of this path), then ccg_put_samples_packed_dev
     #        + ccg_run_pair with host matrices out.
@@ -380,7 +380,10 @@ def main():
         L = api.load()
         import ctypes as C
         row_s, row_m = W * 8, W * 4
-        sharded = world > 1 and n % world == 0
+        # measured on the 8-GPU box (profiles/): with 2 ranks the per-rank K-slab streaming (upload hidden under
+        # the GEMM) wins (417 vs 522 ms); from 4 ranks on the ranks' tile regions overlap in the rows they need,
+        # the shared host memory becomes the bottleneck (550-577 ms) and the sharded upload + all-gather wins
+        sharded = world >= 4 and n % world == 0
         n_host = n // world if sharded else n
         r0 = rank * n_host if sharded else 0
         hs_ptr = L.ccg_host_alloc(n_host * row_s)
