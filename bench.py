@@ -333,9 +333,20 @@ def main():
     # the contraction only for the tensor kernel's own accounting; the roofline uses the USEFUL
     # pairwise base comparisons (cells of the strict lower triangle) x 8 int8 ops
     achieved = OPS_PER_BASECMP * my_basecmp / (kern_ms * 1e-3) / 1e12
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_umma2_10k_traffic.json")
+    if use_umma and world == 1 and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj["samples"] == n and tj["length"] == length and tj["kernel"] in ctx.last_kernel:
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)",
-        "frac": achieved / int8_peak, "traffic": None, "kernel": ctx.last_kernel,
+        "frac": achieved / int8_peak, "traffic": traffic,
+        "traffic_note": ("DRAM bytes per GEMM launch (ncu); the launch's operand slab is 51 GB, read 5.8x thanks to "
+                         "lock-step L2 sharing (33x before)") if traffic else None,
+        "kernel": ctx.last_kernel,
         "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step,
         "compare_phase_ms": compare_ms,
         "expand_ms": float(np.mean(expand_ms)) if expand_ms else None,
