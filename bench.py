@@ -38,7 +38,7 @@ METRIC = "pairwise base comparisons/sec"
 UNIT = "base-cmp/s"
 LENGTH = 5_000_000
 BASE_SAMPLES = 10000
-OPS_PER_BASECMP = 8          # int8 ops of the K=4L tetrahedral+mask contraction
+OPS_PER_BASECMP = 8          # tensor ops (2 per MAC) of the K=4L tetrahedral+mask contraction
 
 
 def log(*a):
@@ -322,12 +322,21 @@ def main():
     # kernel's MMA shape (tcgen05 kind::i8, cta_group::2, 256x256x32), run about as long as the GEMM phase
     # (sustained) and for a few ms (burst).  MEASURED_PEAKS.json only holds bf16, and 2 x that figure
     # under-states what kind::i8 delivers here (the GEMM itself exceeds it), so it is reported beside.
-    i8_burst = i8_sustained = None
+    i8_burst = i8_sustained = fp4_burst = fp4_sustained = None
+    fp4_inexact = None
+    is_fp4 = "mxf4" in ctx.last_kernel
     if use_umma:
+        sustain_ms = max(50.0, min(kern_ms, 1000.0))
         i8_burst = ctx.measure_i8_peak(10.0)
-        i8_sustained = ctx.measure_i8_peak(max(50.0, min(kern_ms, 1000.0)))
+        i8_sustained = ctx.measure_i8_peak(sustain_ms)
+        fp4_burst, fp4_inexact = ctx.measure_fp4_peak(10.0)
+        fp4_sustained, _ = ctx.measure_fp4_peak(sustain_ms)
         torch.cuda.synchronize()
-    int8_peak = i8_sustained if (i8_sustained and i8_sustained > 0) else int8_2x_bf16
+        if is_fp4 and fp4_inexact != 0:
+            raise SystemExit("bench.py: the kind::mxf4 accumulators are not exact on this device -- number withheld")
+    own_peak = fp4_sustained if is_fp4 else i8_sustained
+    pipe_peak = own_peak if (own_peak and own_peak > 0) else int8_2x_bf16
+    int8_peak = pipe_peak
     my_basecmp = float(my_cells) * length
     # algorithmic work of this rank's launch: every owned macro tile is a full 128 x 256 block of
     # the contraction only for the tensor kernel's own accounting; the roofline uses the USEFUL
@@ -335,28 +344,32 @@ def main():
     achieved = OPS_PER_BASECMP * my_basecmp / (kern_ms * 1e-3) / 1e12
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this workload
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_umma2_10k_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_umma2_mxf4_10k_traffic.json" if "mxf4" in ctx.last_kernel
+                         else "r01_umma2_10k_traffic.json")
     if use_umma and world == 1 and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj["samples"] == n and tj["length"] == length and tj["kernel"] in ctx.last_kernel:
+        if tj["samples"] == n and tj["length"] == length and tj["kernel"] in ctx.last_kernel and \
+                tj.get("operands", "i8") == ("mxf4" if is_fp4 else "i8"):
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8)",
+        "bound": "tensor", "achieved": achieved, "peak": int8_peak,
+        "unit": "TOP/s (e2m1 x e2m1 -> f32, kind::mxf4)" if is_fp4 else "TOP/s (int8)",
         "frac": achieved / int8_peak, "traffic": traffic,
-        "traffic_note": ("DRAM bytes per GEMM launch (ncu); the launch's operand slab is 51 GB, read 5.8x thanks to "
-                         "lock-step L2 sharing (33x before)") if traffic else None,
+        "traffic_note": "DRAM bytes per GEMM launch from the committed ncu --set full capture of this workload" if traffic else None,
         "kernel": ctx.last_kernel,
         "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step,
         "compare_phase_ms": compare_ms,
         "expand_ms": float(np.mean(expand_ms)) if expand_ms else None,
-        "peak_source": ("own loads-free tcgen05 kind::i8 microbenchmark (ccg_measure_i8_peak), sustained: run as long "
-                        "as the GEMM phase, same power cap" if i8_sustained and i8_sustained > 0 else
+        "peak_source": ("own loads-free tcgen05 microbenchmark of the kernel's MMA kind and shape "
+                        "(ccg_measure_fp4_peak / ccg_measure_i8_peak), sustained: run as long as the GEMM phase, same "
+                        "power cap" if own_peak and own_peak > 0 else
                         f"2 x bf16_tflops_sustained of {peaks_src} MEASURED_PEAKS.json"),
+        "peak_fp4_burst": fp4_burst, "peak_fp4_sustained": fp4_sustained, "fp4_inexact_elements_at_1.6e7": fp4_inexact,
         "peak_i8_burst": i8_burst, "peak_i8_sustained": i8_sustained,
         "peak_2x_bf16_sustained": int8_2x_bf16, "frac_of_2x_bf16_sustained": achieved / int8_2x_bf16,
         "peaks_file": peaks_src,
-        "algorithmic": f"{OPS_PER_BASECMP} int8 ops per pairwise base comparison (K=4L contraction), "
+        "algorithmic": f"{OPS_PER_BASECMP} tensor ops (4 MACs) per pairwise base comparison (K=4L contraction), "
                        f"useful cells only (strict lower triangle)",
     }
 
@@ -489,7 +502,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None,
-            "dtype": ("int8 operands, int32 accumulate (tcgen05 kind::i8), f64 epilogue" if use_umma
+            "dtype": (("e2m1 operands (+1/-1/0, exact), f32 accumulate of exact integers (tcgen05 kind::mxf4), int32 "
+                       "split-K sums, f64 epilogue" if is_fp4 else
+                       "int8 operands, int32 accumulate (tcgen05 kind::i8), f64 epilogue") if use_umma
                       else "u32 bit-planes (LOP3+POPC), u32 counters, f64 epilogue"),
             "data": "synthetic",
             "config": {"workload": f"{n} samples x {length} bp all-vs-all distance + inclusion matrix "

@@ -27,7 +27,7 @@ EXPORTS = [
     "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
-    "ccg_measure_i8_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
+    "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
 ]
 
 MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "ln", "nl1", "nl2",
@@ -115,6 +115,8 @@ def load():
     L.ccg_mat_put_sample.argtypes = [vp, i, vp, vp, i]
     L.ccg_mat_run.argtypes = [vp, vp, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, i, C.c_double,
                               vp, vp, vp, vp]
+    L.ccg_measure_fp4_peak.restype = C.c_double
+    L.ccg_measure_fp4_peak.argtypes = [vp, C.c_double, C.c_double, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     L.ccg_measure_i8_peak.restype = C.c_double
     L.ccg_measure_i8_peak.argtypes = [vp, C.c_double]
     _lib = L
@@ -330,6 +332,13 @@ class Context:
 
     def last_phase_ms(self, phase):
         return self._L.ccg_last_phase_ms(self._h, phase)
+
+    def measure_fp4_peak(self, target_ms=20.0, check_sum=1.6e7):
+        """(e2m1 TOP/s of a loads-free tcgen05 kind::mxf4 loop on every CTA pair, accumulator elements that
+        differed from the exact integer after summing +1/-1 products up to about check_sum)."""
+        bad = C.c_longlong(-1)
+        tops = self._L.ccg_measure_fp4_peak(self._h, target_ms, check_sum, C.byref(bad), None)
+        return tops, bad.value
 
     def measure_i8_peak(self, target_ms=20.0):
         """int8 TOP/s of a loads-free tcgen05 kind::i8 loop on every CTA pair (roofline denominator)."""

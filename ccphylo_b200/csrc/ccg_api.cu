@@ -110,6 +110,8 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 	if(getenv("CCG_EXPAND_SERIAL")) ctx->dbg_serial = atoi(getenv("CCG_EXPAND_SERIAL"));
 	if(getenv("CCG_NOLOCK")) ctx->dbg_nolock = atoi(getenv("CCG_NOLOCK"));
 	if(getenv("CCG_UMMA1")) ctx->dbg_umma1 = atoi(getenv("CCG_UMMA1"));
+	if(getenv("CCG_I8")) ctx->use_i8 = atoi(getenv("CCG_I8"));
+	ctx->min_slabs = getenv("CCG_MIN_SLABS") ? atoi(getenv("CCG_MIN_SLABS")) : 0;     /* 0 = automatic */
 	if(getenv("CCG_FEED_SLABS")) ctx->dbg_feed_slabs = atoi(getenv("CCG_FEED_SLABS"));
 	/* host rows are streamed K slab by K slab from this alignment length on (0 = never) */
 	ctx->stream_min_chunks = getenv("CCG_STREAM_MIN_CHUNKS") ? atoi(getenv("CCG_STREAM_MIN_CHUNKS")) : 4096;
@@ -868,6 +870,8 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	}
 	CK(ctx, cudaMemsetAsync(ctx->d_C, 0, c_bytes, ctx->stream));
 
+	/* e2m1 operands on kind::mxf4 (2.27x the kind::i8 pipe rate, exact for these sums) unless CCG_I8=1 */
+	const bool fp4 = !ctx->use_i8 && !ctx->dbg_umma1;
 	/* operand panel: the K axis is cut into slabs; two slab buffers so that the expansion of
 	 * slab s+1 (aux stream, HBM-write bound) runs under the GEMM of slab s (tensor bound).
 	 * Sized once per problem geometry (cudaMemGetInfo / cudaMalloc are far too slow per run). */
@@ -877,7 +881,7 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		/* default: up to 70 % of what is free (the planes, accumulators and outputs are already allocated) */
 		size_t budget = ctx->x_budget ? ctx->x_budget : free_b / 10 * 7;
 		if(budget > free_b - free_b / 8) budget = free_b - free_b / 8;
-		const size_t per_chunk = (size_t) ctx->n_pad * 512;
+		const size_t per_chunk = (size_t) ctx->n_pad * (fp4 ? 256 : 512);
 		long long fit = (long long) (budget / per_chunk);        /* chunks one buffer could hold */
 		int want_slabs = 1;
 		if(fit < ctx->chunks) {
@@ -893,6 +897,7 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		 * 1000 x 5 Mbp), so the panel is cut only when it does not fit; then the two buffers keep
 		 * the tensor pipe busy while the next slab is produced */
 		fit = (ctx->chunks + want_slabs - 1) / want_slabs;              /* equal slabs */
+		if(fp4) fit = (fit + 1) & ~1LL;                                  /* whole chunk pairs */
 		const int nbuf = want_slabs > 1 ? 2 : 1;
 		ctx->x_buf_bytes = (size_t) fit * per_chunk;
 		size_t x_bytes = ctx->x_buf_bytes * nbuf;
@@ -907,6 +912,16 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		if(rc) return rc;
 	}
 	long long slab = ctx->x_chunks;
+	/* a rank of a partitioned run spends a larger share of its step expanding (it reads O(n / sqrt(world)) rows
+	 * for 1 / world of the tiles): cut the K axis so that the expansion of slab s+1 runs under the GEMM of slab s.
+	 * On one GPU the cut does not pay (measured 334 vs 331 ms at 10k, 7.5 vs 6.5 ms at 1k). */
+	const int min_slabs = ctx->min_slabs > 0 ? ctx->min_slabs : (ctx->world > 1 ? 4 : 1);
+	if(!ctx->feed_seqs && min_slabs > 1 && ctx->chunks >= 4096) {
+		long long want = (ctx->chunks + min_slabs - 1) / min_slabs;
+		const long long cap = ctx->x_bytes >= 2 * ctx->x_buf_bytes ? ctx->x_chunks : ctx->x_chunks / 2;
+		if(want < slab && cap >= 1) slab = want < cap ? want : cap;
+		if(fp4 && (slab & 1)) slab = slab > 1 ? slab - 1 : 2;
+	}
 	if(ctx->feed_seqs) {
 		/* host rows are streamed slab by slab: shorter slabs shorten the pipeline fill (the first
 		 * slab's upload is the only one not hidden behind a GEMM) */
@@ -916,14 +931,15 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		if(want < 16) want = 16;
 		const long long cap = ctx->x_bytes >= 2 * ctx->x_buf_bytes ? ctx->x_chunks : ctx->x_chunks / 2;
 		if(want < slab && cap >= 1) slab = want < cap ? want : cap;
+		if(fp4 && (slab & 1)) slab = slab > 1 ? slab - 1 : 2;
 	}
 	const int nslabs = (int) ((ctx->chunks + slab - 1) / slab);
 	/* two slab buffers: the allocation's two halves, or -- when the whole panel fits in a single
 	 * buffer and shorter slabs are streamed -- that buffer cut in two */
-	const size_t per_chunk_b = (size_t) ctx->n_pad * 512;
+	const size_t per_chunk_b = (size_t) ctx->n_pad * (fp4 ? 256 : 512);
 	size_t buf_off[2] = {0, ctx->x_buf_bytes};
 	if(ctx->x_bytes < 2 * ctx->x_buf_bytes) {
-		buf_off[1] = ((size_t) ctx->x_chunks / 2) * per_chunk_b;
+		buf_off[1] = (((size_t) ctx->x_chunks / 2) & ~(size_t) 1) * per_chunk_b;
 		if(nslabs > 1 && (size_t) slab * per_chunk_b > buf_off[1]) {
 			set_err(ctx, "internal: slab of %lld chunks does not fit half of the operand panel", slab);
 			return CCG_ERR_ARG;
@@ -937,6 +953,8 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	p.C_S = ctx->d_C;
 	p.C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
 	p.ldc = ctx->n_pad;
+	p.fp4 = fp4 ? 1 : 0;
+	long long i_const_fp4 = 0;
 	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	/* The expansion of slab s+1 runs beside the GEMM of slab s.  It must not start before every
 	 * (persistent) GEMM CTA holds its SM, or expansion blocks can fill an SM and keep a GEMM CTA
@@ -958,20 +976,25 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		const int chunk0 = (int) (s * slab);
 		int nch = ctx->chunks - chunk0;
 		if(nch > slab) nch = (int) slab;
-		p.slab_chunks = nch;
+		/* K units of this slab: chunks, or chunk pairs for the e2m1 panel (a 128-byte channel row = 256 bases) */
+		const int nu = fp4 ? (nch + 1) / 2 : nch;
+		i_const_fp4 += (long long) nu * 2 * CCG_CHUNK_BASES;
+		p.slab_chunks = nu;
 		p.row_base = (int) (buf_off[b] / 128);
 		if(ctx->dbg_umma1) {
 			p.single = 1;
 			p.ntiles = (int) (2 * cnt);
 			p.tiles = ctx->d_tiles + cnt;
 		}
-		p.kslices = choose_split((long long) (p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx)), (long long) p.ntiles, nch, 16, 512);
-		p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
+		p.kslices = choose_split((long long) (p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx)), (long long) p.ntiles, nu, fp4 ? 8 : 16, 512);
+		/* f32 accumulators: an S item adds at most 3 * 256 per chunk pair and must stay below 2^24 */
+		if(fp4 && (nu + p.kslices - 1) / p.kslices > 20000) p.kslices = (nu + 19999) / 20000;
+		p.chunks_per_slice = (nu + p.kslices - 1) / p.kslices;
 		if(ctx->dbg_kslices > 0) {
 			p.kslices = ctx->dbg_kslices;
-			p.chunks_per_slice = (nch + p.kslices - 1) / p.kslices;
+			p.chunks_per_slice = (nu + p.kslices - 1) / p.kslices;
 		}
-		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nch) --p.kslices;
+		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nu) --p.kslices;
 		if(ctx->feed_seqs) {
 			rc = feed_slab(ctx, chunk0, nch);
 			if(rc) return rc;
@@ -991,7 +1014,8 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 				return CCG_ERR_CUDA;
 			}
 		}
-		CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + buf_off[b], chunk0, nch, nslabs > 1 && !ctx->dbg_serial));
+		if(fp4) CK(ctx, ccg_launch_expand_fp4(ctx, ctx->aux_stream, ctx->d_X + buf_off[b], chunk0, nu, nslabs > 1 && !ctx->dbg_serial));
+		else CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + buf_off[b], chunk0, nch, nslabs > 1 && !ctx->dbg_serial));
 		CK(ctx, cudaEventRecord(ctx->ev_x[b], ctx->aux_stream));
 		if(s == nslabs - 1) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->aux_stream));
 		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x[b], 0));
@@ -1003,15 +1027,16 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	}
 	CK(ctx, cudaEventRecord(ctx->ev_phase[3], ctx->stream));
 	ctx->phase_valid = 1;
-	/* shared-mask mode: every position of every chunk counts as included in the raw product */
-	const int i_const = ctx->chunks * CCG_CHUNK_BASES;
+	/* shared-mask mode: every position of every chunk (pair) counts as included in the raw product */
+	const int i_const = fp4 ? (int) i_const_fp4 : ctx->chunks * CCG_CHUNK_BASES;
+	ctx->last_i_const = i_const;
 	p.ntiles = (int) cnt;
 	p.tiles = ctx->d_tiles;
 	CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, i_const));
 	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 	ctx->ev_valid = 1;
 	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_umma%s tiles=%d kslices=%d slabs=%d",
-	         ctx->dbg_umma1 ? "" : "2", p.ntiles, p.kslices, nslabs);
+	         ctx->dbg_umma1 ? "" : (fp4 ? "2<mxf4>" : "2<i8>"), p.ntiles, p.kslices, nslabs);
 	return CCG_OK;
 }
 
@@ -1059,6 +1084,7 @@ static int run_fused(ccg_ctx *ctx, const EpilogueParams &ep) {
 	ctx->phase_valid = 1;
 	p.ntiles = (int) cnt;
 	p.tiles = ctx->d_tiles;
+	ctx->last_i_const = ctx->chunks * CCG_CHUNK_BASES;
 	CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, ctx->chunks * CCG_CHUNK_BASES));
 	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 	ctx->ev_valid = 1;
@@ -1203,7 +1229,7 @@ extern "C" int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc) 
 	cudaMemsetAsync(d_m, 0, cells * 4, ctx->stream);
 	cudaMemsetAsync(d_n, 0, cells * 4, ctx->stream);
 	cudaError_t e;
-	if(ctx->last_kernel_kind == CCG_KERNEL_UMMA || ctx->last_kernel_kind == CCG_KERNEL_FUSED) e = ccg_launch_gather_raw_dense(ctx, ctx->chunks * CCG_CHUNK_BASES, d_m, d_n);
+	if(ctx->last_kernel_kind == CCG_KERNEL_UMMA || ctx->last_kernel_kind == CCG_KERNEL_FUSED) e = ccg_launch_gather_raw_dense(ctx, ctx->last_i_const, d_m, d_n);
 	else e = ccg_launch_gather_raw(ctx, d_m, d_n);
 	if(e == cudaSuccess && mism) e = cudaMemcpyAsync(mism, d_m, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
 	if(e == cudaSuccess && ninc) e = cudaMemcpyAsync(ninc, d_n, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);

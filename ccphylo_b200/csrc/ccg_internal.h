@@ -73,6 +73,7 @@ struct UmmaParams {
 	unsigned *sync;        /* lock-step epoch counters [rounds][epochs_per_item] (zeroed), or NULL */
 	int epochs_per_item;
 	unsigned *resident;    /* every CTA adds 1 once it holds its SM (gates the overlapped expansion), or NULL */
+	int fp4;               /* e2m1 panel (kind::mxf4): slab_chunks / chunks_per_slice count chunk PAIRS, S and I are separate items */
 	int single;            /* tiles are 128 x 256 and run on the single-CTA kernel (CCG_UMMA1=1, experiments) */
 };
 
@@ -85,6 +86,8 @@ struct ccg_ctx {
 	int kernel_choice;
 	int rank, world;
 	int win_on, win[4];            /* macro-tile window [tm_lo, tm_hi) x [tn_lo, tn_hi), ccg_set_tile_window */
+	int min_slabs;                  /* cut the K axis into at least this many slabs (expansion overlapped with the GEMM) */
+	int use_i8;                     /* CCG_I8=1: int8 operands (kind::i8) instead of the default e2m1 panel (kind::mxf4) */
 	int dbg_kslices, dbg_serial, dbg_nolock, dbg_umma1;   /* CCG_KSLICES / CCG_EXPAND_SERIAL / CCG_NOLOCK / CCG_UMMA1 overrides (experiments only) */
 
 	int n, len, pair_mode;
@@ -119,6 +122,7 @@ struct ccg_ctx {
 	int2 *d_tiles;             /* tile list of the last run */
 	size_t tiles_cap;
 	int last_ntiles;
+	int last_i_const;          /* shared-mask mode: the constant inclusion count of the last tensor-path run */
 	int last_kernel_kind;      /* CCG_KERNEL_POPC / CCG_KERNEL_UMMA of the last run */
 	uint32_t *d_acc;           /* popc: tile-major raw counts */
 	size_t acc_bytes;
@@ -188,6 +192,7 @@ int ccg_popc_kc(void);
 
 /* k_pairdist_umma.cu */
 cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks, int bounded);
+cudaError_t ccg_launch_expand_fp4(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int npairs, int bounded);
 cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
 int ccg_umma_pair_slots(ccg_ctx *ctx);
 cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);

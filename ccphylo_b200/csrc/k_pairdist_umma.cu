@@ -168,6 +168,56 @@ k_expand(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int slot0,
 	}
 }
 
+/* e2m1 variant of the operand panel (kind::mxf4): the same four channels as 4-bit floats, +1 = 0x2,
+ * -1 = 0xA, 0 = 0x0 -- all exact in e2m1 -- two per byte, base k of a row in nibble k.  One 128-byte
+ * channel row now holds a PAIR of chunks (256 bases), so the panel is
+ *     X4[slot/128][chunk pair * 4 + channel][slot%128][128 B]
+ * at 2 bytes per base and sample.  One thread per (slot, chunk, 32-base word): 16 bytes per channel. */
+__device__ __forceinline__ uint32_t spread8(uint32_t x) {      /* bit k of the byte -> bit 4k */
+	x = (x | (x << 12)) & 0x000F000Fu;
+	x = (x | (x << 6)) & 0x03030303u;
+	x = (x | (x << 3)) & 0x11111111u;
+	return x;
+}
+__global__ void __launch_bounds__(256)
+k_expand_fp4(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks_total, int slot0, int slots, int chunk0,
+             int npairs, int8_t *__restrict__ X, size_t nkb) {
+	const long long total = (long long) slots * npairs * 8;           /* 2 chunks x 4 words per pair */
+	for(long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+	    gid += (long long) gridDim.x * blockDim.x) {
+		const long long item = gid >> 3;
+		const int sub = (int) (gid & 7);                                /* chunk of the pair (bit 2), word of the chunk */
+		const int slot = slot0 + (int) (item % slots);
+		const int kp = (int) (item / slots);
+		const int chunk = chunk0 + 2 * kp + (sub >> 2), q = sub & 3;
+		uint32_t h = 0, l = 0, m = nplanes == 3 ? 0u : 0xFFFFFFFFu;
+		if(chunk < chunks_total) {
+			const size_t prow = (size_t) chunk * nplanes;
+			h = planes[((prow + 0) * n_pad + slot) * 4 + q];
+			l = planes[((prow + 1) * n_pad + slot) * 4 + q];
+			if(nplanes == 3) m = planes[((prow + 2) * n_pad + slot) * 4 + q];
+		}
+		h = __brev(h); l = __brev(l); m = __brev(m);                    /* base k of the word <-> bit k */
+		uint32_t c0[4], c1[4], c2[4], c3[4];
+#pragma unroll
+		for(int g = 0; g < 4; ++g) {
+			const uint32_t one = spread8((m >> (8 * g)) & 0xFFu) << 1;    /* 0x2 where known */
+			const uint32_t sh = spread8((h >> (8 * g)) & 0xFFu) << 3;     /* sign bit where channel 0 is -1 */
+			const uint32_t sl = spread8((l >> (8 * g)) & 0xFFu) << 3;
+			c0[g] = one | sh;
+			c1[g] = one | sl;
+			c2[g] = one | (sh ^ sl);
+			c3[g] = one;
+		}
+		const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) kp * 4) * 128 + (slot & 127);
+		uint4 *dst = reinterpret_cast<uint4 *>(X + tile_row * 128 + sub * 16);
+		__stcs(dst + 0 * 1024, make_uint4(c0[0], c0[1], c0[2], c0[3]));
+		__stcs(dst + 1 * 1024, make_uint4(c1[0], c1[1], c1[2], c1[3]));
+		__stcs(dst + 2 * 1024, make_uint4(c2[0], c2[1], c2[2], c2[3]));
+		__stcs(dst + 3 * 1024, make_uint4(c3[0], c3[1], c3[2], c3[3]));
+	}
+}
+
 /* ------------------------------------------------------------------ */
 /* the GEMM                                                            */
 /* ------------------------------------------------------------------ */
@@ -386,6 +436,17 @@ __device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64
 	    "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
 	    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate) : "memory");
 }
+/* kind::mxf4: e2m1 operands, UE8M0 scale vectors (all 1.0, see k_pairdist_umma2<true>), f32 accumulators.
+ * Block-scaled instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptorBlockScaled):
+ * a/b_format E2M1 (1) @7/@10, K-major, n_dim @17, scale_format UE8M0 (1) @23, m_dim @24, K = 64. */
+constexpr uint32_t IDESC_MXF4 = (1u << 7) | (1u << 10) | ((uint32_t) (BN >> 3) << 17) | (1u << 23) | ((uint32_t) (256 >> 4) << 24);
+__device__ __forceinline__ void umma2_mxf4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t sfa, uint32_t sfb) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+	    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_MXF4), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
+}
 __device__ __forceinline__ void umma2_commit(uint32_t bar) {
 	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
 	             ::"r"(bar), "h"((uint16_t) 3) : "memory");
@@ -395,6 +456,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+/* FP4 = true: the same kernel on the e2m1 panel.  The f32 accumulator leaves no room for two 256-column
+ * accumulators plus the scale vectors in the 512 TMEM columns, so S (channels 0-2) and I (mask channel) are
+ * separate work items (first the S items of every K slice, then the I items); p.slab_chunks / p.chunks_per_slice count chunk
+ * PAIRS (one 128-byte channel row = 256 bases).  Exactness: every product is -1, 0 or +1, the pipe adds exact
+ * partial sums into f32 (measured: scripts/fp4_probe.py), so an item is exact while 3 * 256 * pairs < 2^24 --
+ * the host keeps the slices below 20,000 pairs. */
+template <bool FP4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 	extern __shared__ uint8_t smem_raw[];
@@ -412,7 +480,7 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
 	const int G = (int) (gridDim.x >> 1);                        /* clusters */
 	const int cid = (int) (blockIdx.x >> 1);
-	const int items = p.ntiles * p.kslices;
+	const int items = p.ntiles * p.kslices * (FP4 ? 2 : 1);
 	const int nkb_slab = p.slab_chunks * 4;
 
 	if(threadIdx.x == 0) {
@@ -434,6 +502,20 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 	const uint32_t tmem = *tmem_slot_ptr;
 	if(threadIdx.x == 0 && p.resident) atomicAdd(p.resident, 1u);
+	if(FP4) {
+		/* scale vectors: UE8M0 1.0 (0x7F) in every byte of TMEM columns [256, 288) of every lane, whichever
+		 * bytes the scale-factor ids select; written once, shared by all MMAs */
+		if(warp >= 2) {
+			const uint32_t one = 0x7F7F7F7Fu;
+			const uint32_t taddr = tmem + ((uint32_t) ((warp & 3) * 32) << 16) + 256;
+			for(int c = 0; c < 32; c += 8)
+				asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr + c), "r"(one) : "memory");
+			asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+		}
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+		cluster_sync_all();
+		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	}
 
 	if(warp == 0) {
 		/* ===== TMA producer (both CTAs) ===== */
@@ -442,13 +524,14 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 			int round = 0;
 			int lock_skip = 0;
 			for(int w = cid; w < items; w += G, ++round) {
-				const int tile = w % p.ntiles, ks = w / p.ntiles;
+				const int tile = w % p.ntiles, q = w / p.ntiles;
+				const int ks = FP4 ? q % p.kslices : q, which = FP4 ? q / p.kslices : 0;   /* all S items first, then the I items */
 				const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
 				const int c_begin = ks * p.chunks_per_slice;
 				int nchunk = p.slab_chunks - c_begin;
 				if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
 				if(nchunk < 0) nchunk = 0;
-				const int nkb = nchunk * 4;
+				const int nkb = FP4 ? (which ? nchunk : 3 * nchunk) : nchunk * 4;   /* stages of this item */
 				const long long g0 = (long long) round * p.epochs_per_item;
 				const int rbA = 2 * tm + (int) cta_rank, rbB = 2 * tn + (int) cta_rank;
 				for(int kb = 0; kb < nkb; ++kb, ++it) {
@@ -467,7 +550,8 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 					if(it >= STAGES2) mbar_wait(bar_empty + 8 * s, ((it / STAGES2) - 1) & 1);
 					const uint32_t dst = base + s * STAGE2_BYTES;
 					const uint32_t bar = (bar_full + 8 * s) & PEER_MASK;      /* the leader's barrier */
-					const int kabs = c_begin * 4 + kb;
+					/* k-block of this stage inside the slab: 4 per chunk (pair), channel-minor */
+					const int kabs = FP4 ? (which ? (c_begin + kb) * 4 + 3 : (c_begin + kb / 3) * 4 + kb % 3) : c_begin * 4 + kb;
 					if(cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE2_BYTES);
 					tma_load_2d_pair(dst, &tmap, bar, 0, p.row_base + (rbA * nkb_slab + kabs) * 128);
 					tma_load_2d_pair(dst + A_BYTES, &tmap, bar, 0, p.row_base + (rbB * nkb_slab + kabs) * 128);
@@ -482,12 +566,13 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 			unsigned it = 0;
 			int round = 0;
 			for(int w = cid; w < items; w += G, ++round) {
-				const int ks = w / p.ntiles;
+				const int q = w / p.ntiles;
+				const int ks = FP4 ? q % p.kslices : q, which = FP4 ? q / p.kslices : 0;   /* all S items first, then the I items */
 				const int c_begin = ks * p.chunks_per_slice;
 				int nchunk = p.slab_chunks - c_begin;
 				if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
 				if(nchunk < 0) nchunk = 0;
-				const int nkb = nchunk * 4;
+				const int nkb = FP4 ? (which ? nchunk : 3 * nchunk) : nchunk * 4;
 				if(round > 0) {
 					mbar_wait(bar_tfree, (round - 1) & 1);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -500,13 +585,21 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 					const uint32_t a0 = base + s * STAGE2_BYTES;
 					const uint64_t adesc = make_desc(a0);
 					const uint64_t bdesc = make_desc(a0 + A_BYTES);
-					const bool is_mask = (kb & 3) == 3;
-					const uint32_t d = tmem + (is_mask ? BN : 0);
+					if(FP4) {
 #pragma unroll
-					for(int k = 0; k < BK / 32; ++k) {
-						const uint32_t acc = is_mask ? usedI : usedS;
-						umma2_i8(d, adesc + 2 * k, bdesc + 2 * k, acc);
-						if(is_mask) usedI = 1; else usedS = 1;
+						for(int k = 0; k < BK / 32; ++k) {               /* 32 bytes = 64 e2m1 = one MMA K */
+							umma2_mxf4(tmem, adesc + 2 * k, bdesc + 2 * k, usedS, tmem + 256, tmem + 264);
+							usedS = 1;
+						}
+					} else {
+						const bool is_mask = (kb & 3) == 3;
+						const uint32_t d = tmem + (is_mask ? BN : 0);
+#pragma unroll
+						for(int k = 0; k < BK / 32; ++k) {
+							const uint32_t acc = is_mask ? usedI : usedS;
+							umma2_i8(d, adesc + 2 * k, bdesc + 2 * k, acc);
+							if(is_mask) usedI = 1; else usedS = 1;
+						}
 					}
 					umma2_commit(bar_empty + 8 * s);       /* frees the stage in both CTAs */
 				}
@@ -520,7 +613,8 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 		asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(leader_tfree) : "r"(bar_tfree));
 		int round = 0;
 		for(int w = cid; w < items; w += G, ++round) {
-			const int tile = w % p.ntiles, ks = w / p.ntiles;
+			const int tile = w % p.ntiles, q = w / p.ntiles;
+			const int ks = FP4 ? q % p.kslices : q, which = FP4 ? q / p.kslices : 0;   /* all S items first, then the I items */
 			const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
 			const int nleft = p.slab_chunks - ks * p.chunks_per_slice;
 			const int row = tm * BMT + (int) cta_rank * 128 + quarter * 32 + lane;
@@ -535,13 +629,23 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 					if(__all_sync(0xffffffffu, cb * 32 >= jlim)) break;
 					uint32_t r[32];
 					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + cb * 32, r);
+					if(FP4) {
+						/* exact integers in f32 */
+						int *c = which ? cI : cS;
 #pragma unroll
-					for(int e = 0; e < 32; ++e)
-						if(cb * 32 + e < jlim && r[e]) atomicAdd(cS + cb * 32 + e, (int) r[e]);
-					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + BN + cb * 32, r);
+						for(int e = 0; e < 32; ++e) {
+							const int v = __float2int_rn(__uint_as_float(r[e]));
+							if(cb * 32 + e < jlim && v) atomicAdd(c + cb * 32 + e, v);
+						}
+					} else {
 #pragma unroll
-					for(int e = 0; e < 32; ++e)
-						if(cb * 32 + e < jlim && r[e]) atomicAdd(cI + cb * 32 + e, (int) r[e]);
+						for(int e = 0; e < 32; ++e)
+							if(cb * 32 + e < jlim && r[e]) atomicAdd(cS + cb * 32 + e, (int) r[e]);
+						tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + BN + cb * 32, r);
+#pragma unroll
+						for(int e = 0; e < 32; ++e)
+							if(cb * 32 + e < jlim && r[e]) atomicAdd(cI + cb * 32 + e, (int) r[e]);
+					}
 				}
 			}
 			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -602,6 +706,28 @@ k_gather_raw_dense(const int *__restrict__ C_S, const int *__restrict__ C_I, int
 } // namespace
 
 /* expands the row blocks this rank needs (runs of consecutive needed 128-slot blocks) */
+/* e2m1 panel: npairs chunk pairs from chunk0 on (chunks past the end of the alignment expand to zeros) */
+cudaError_t ccg_launch_expand_fp4(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int npairs, int bounded) {
+	const int nblocks = ctx->n_pad / 128;
+	int b = 0;
+	while(b < nblocks) {
+		if(!ctx->need[b]) { ++b; continue; }
+		int e = b;
+		while(e < nblocks && ctx->need[e]) ++e;
+		const int slot0 = b * 128, slots = (e - b) * 128;
+		const long long items = (long long) slots * npairs;
+		if(items > 0) {
+			long long blocks = (items * 8 + 255) / 256;
+			if(bounded && blocks > 6LL * ctx->sm_count) blocks = 6LL * ctx->sm_count;
+			k_expand_fp4<<<(unsigned) blocks, 256, 0, stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks, slot0, slots, chunk0,
+			                                                   npairs, X, (size_t) npairs * 4);
+			ctx->launches++;
+		}
+		b = e;
+	}
+	return cudaGetLastError();
+}
+
 cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks, int bounded) {
 	const int nblocks = ctx->n_pad / 128;
 	int b = 0;
@@ -628,7 +754,7 @@ cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int 
 int ccg_umma_pair_slots(ccg_ctx *ctx) {
 	constexpr int smem2 = STAGES2 * STAGE2_BYTES + 8 * (2 * STAGES2 + 2) + 16 + 1024;
 	if(!ctx->max_pairs) {
-		cudaFuncSetAttribute(k_pairdist_umma2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+		cudaFuncSetAttribute(k_pairdist_umma2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
 		cudaLaunchConfig_t cfg = {};
 		cfg.gridDim = dim3((unsigned) (2 * (ctx->sm_count / 2)));
 		cfg.blockDim = dim3(THREADS);
@@ -641,7 +767,7 @@ int ccg_umma_pair_slots(ccg_ctx *ctx) {
 		cfg.attrs = &attr;
 		cfg.numAttrs = 1;
 		int nclusters = 0;
-		if(cudaOccupancyMaxActiveClusters(&nclusters, k_pairdist_umma2, &cfg) != cudaSuccess || nclusters < 1) {
+		if(cudaOccupancyMaxActiveClusters(&nclusters, k_pairdist_umma2<false>, &cfg) != cudaSuccess || nclusters < 1) {
 			cudaGetLastError();
 			nclusters = ctx->sm_count / 2;
 		}
@@ -657,16 +783,18 @@ cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p_in) {
 	constexpr int smem2 = STAGES2 * STAGE2_BYTES + 8 * (2 * STAGES2 + 2) + 16 + 1024;
 	cudaError_t e = cudaFuncSetAttribute(k_pairdist_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
 	if(e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(k_pairdist_umma2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+	e = cudaFuncSetAttribute(k_pairdist_umma2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+	if(e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(k_pairdist_umma2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
 	if(e != cudaSuccess) return e;
 	UmmaParams p = p_in;
-	const long long items = (long long) p.ntiles * p.kslices;
+	const long long items = (long long) p.ntiles * p.kslices * (p.fp4 ? 2 : 1);
 	if(items <= 0) return cudaSuccess;
 	const int slots = p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx);   /* CTAs or CTA pairs */
 	const int grid = items < slots ? (int) items : slots;
 	/* lock-step counters: one per (round, epoch of LOCK_E stages) */
 	const long long rounds = (items + grid - 1) / grid;
-	p.epochs_per_item = (p.chunks_per_slice * 4 + LOCK_E - 1) / LOCK_E;
+	p.epochs_per_item = (p.chunks_per_slice * (p.fp4 ? 3 : 4) + LOCK_E - 1) / LOCK_E;
 	const size_t need = (size_t) rounds * p.epochs_per_item + 1;
 	p.sync = 0;
 	if(!ctx->dbg_nolock && grid > 1 && need <= ((size_t) 64 << 20)) {
@@ -683,7 +811,8 @@ cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p_in) {
 	}
 	ctx->last_gemm_ctas = p.single ? grid : 2 * grid;
 	if(p.single) k_pairdist_umma<<<(unsigned) grid, THREADS, smem1, ctx->stream>>>(ctx->tmap_x, p);
-	else k_pairdist_umma2<<<(unsigned) (2 * grid), THREADS, smem2, ctx->stream>>>(ctx->tmap_x, p);
+	else if(p.fp4) k_pairdist_umma2<true><<<(unsigned) (2 * grid), THREADS, smem2, ctx->stream>>>(ctx->tmap_x, p);
+	else k_pairdist_umma2<false><<<(unsigned) (2 * grid), THREADS, smem2, ctx->stream>>>(ctx->tmap_x, p);
 	ctx->launches++;
 	return cudaGetLastError();
 }

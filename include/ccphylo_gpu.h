@@ -239,6 +239,11 @@ int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int method, unsigned
  * on every CTA pair for about target_ms and returns the rate in int8 TOP/s (2 ops per MAC);
  * < 0 on failure.  A few ms measures the burst rate, a second the power-capped sustained one. */
 double ccg_measure_i8_peak(ccg_ctx *ctx, double target_ms);
+/* The same for the default operand format: e2m1 on tcgen05 kind::mxf4 (block scales 1.0, f32
+ * accumulators).  Also accumulates +1 / -1 products up to about check_sum (< 2^24) and reports in
+ * *inexact how many accumulator elements then differed from the exact integer (0 is what the
+ * tensor path relies on); info, if not NULL, receives {dot of the test pattern, D[0][0], iterations}. */
+double ccg_measure_fp4_peak(ccg_ctx *ctx, double target_ms, double check_sum, long long *inexact, int *info);
 
 #ifdef __cplusplus
 }

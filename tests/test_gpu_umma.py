@@ -27,11 +27,21 @@ def _set(n, length, seed, **kw):
 KNAME = {api.KERNEL_UMMA: "k_pairdist_umma", api.KERNEL_FUSED: "k_pairdist_fused"}
 
 
-@pytest.fixture(scope="module", params=[api.KERNEL_UMMA, api.KERNEL_FUSED], ids=["umma", "fused"])
+# the tensor path in its three forms: e2m1 operands on kind::mxf4 (the default), int8 operands on kind::i8
+# (CCG_I8=1, read when the context is created), and the fused int8 kernel
+@pytest.fixture(scope="module", params=[(api.KERNEL_UMMA, "0"), (api.KERNEL_UMMA, "1"), (api.KERNEL_FUSED, "0")],
+                ids=["umma-mxf4", "umma-i8", "fused"])
 def ctx(built, request):
-    c = api.Context()
-    c.set_kernel(request.param)
-    c.kind = request.param
+    import os
+    kind, i8 = request.param
+    os.environ["CCG_I8"] = i8
+    try:
+        c = api.Context()
+    finally:
+        del os.environ["CCG_I8"]
+    c.set_kernel(kind)
+    c.kind = kind
+    c.bytes_per_chunk_slot = 512 if (i8 == "1" or kind == api.KERNEL_FUSED) else 256
     yield c
     c.close()
 
@@ -133,7 +143,7 @@ def test_umma_multi_slab_and_kslices(ctx):
     mo, no = oracle.raw_pair_matrix(seqs, masks, length)
     if ctx.kind == api.KERNEL_UMMA:
         try:
-            ctx.set_scratch_limit(2 * 256 * 512 * 350)      # two 350-chunk slab buffers -> 7 slabs of 335
+            ctx.set_scratch_limit(2 * 256 * ctx.bytes_per_chunk_slot * 350)      # two 350-chunk slab buffers -> 7 slabs
             D, N, dn = ctx.run_pair(min_length=0, min_cov=0.0)
             assert "slabs=7" in ctx.last_kernel, ctx.last_kernel
             mism, ninc = ctx.raw_counts(dn)
