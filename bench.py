@@ -176,7 +176,9 @@ def reference_arm(args, rank, world):
     # the bounded sample never needs more than a few hundred samples: generate just those
     ns_cap = min(n, 64 + 8 * cores)
     seqs, masks = make_host_workload(ns_cap, args.length, seed=2)
-    value, kind, what, sec, threads, ns, _, _ = cpu_reference_rate(seqs, masks, args.length, cores, args.cpu_budget,
+    # the whole --steps / --warmup run must end within a few minutes: share about two of them between the steps
+    budget = min(args.cpu_budget, 120.0 / max(1, args.steps + args.warmup))
+    value, kind, what, sec, threads, ns, _, _ = cpu_reference_rate(seqs, masks, args.length, cores, budget,
                                                                    steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -352,6 +354,9 @@ def main():
         if tj["samples"] == n and tj["length"] == length and tj["kernel"] in ctx.last_kernel and \
                 tj.get("operands", "i8") == ("mxf4" if is_fp4 else "i8"):
             traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+            # the capture cut the K axis into more launches than this run: scale to this run's launches per step
+            nslabs_now = int(ctx.last_kernel.split("slabs=")[1]) if "slabs=" in ctx.last_kernel else 1
+            traffic = traffic * tj.get("launches_per_step_in_capture", nslabs_now) / max(nslabs_now, 1)
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": int8_peak,
         "unit": "TOP/s (e2m1 x e2m1 -> f32, kind::mxf4)" if is_fp4 else "TOP/s (int8)",

@@ -422,6 +422,7 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 	if(Dn < 2) return CCG_OK;
 	/* tiles of the lower triangle that hold at least one included pair */
 	std::vector<int2> tiles;
+	long long ordinal = 0;
 	const int T = npad / MT;
 	for(int ti = 0; ti < T; ++ti)
 		for(int tj = 0; tj <= ti; ++tj) {
@@ -430,9 +431,19 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 				any_i |= rank[(size_t) ti * MT + k] >= 0;
 				any_j |= rank[(size_t) tj * MT + k] >= 0;
 			}
-			if(any_i && any_j) tiles.push_back(make_int2(ti, tj));
+			/* one process per GPU: the 16 x 16 tiles are dealt round-robin (ccg_set_partition); cells of other
+			 * ranks read back as zero */
+			if(any_i && any_j && (ctx->world <= 1 || (int) (ordinal++ % ctx->world) == ctx->rank)) tiles.push_back(make_int2(ti, tj));
+			else if(any_i && any_j) { /* another rank's tile */ }
 		}
 	const int ntiles = (int) tiles.size();
+	if(ntiles == 0) {
+		const size_t cells0 = (size_t) Dn * (Dn - 1) / 2;
+		memset(D, 0, cells0 * elem_size);
+		if(N) memset(N, 0, cells0 * elem_size);
+		if(rows_inc) memset(rows_inc, 0, cells0 * 4);
+		return CCG_OK;
+	}
 	/* slices of the position axis: fill the machine a few times over, at least 1024 positions each */
 	const long long stages = ctx->mat_lpad / MP;
 	long long want = (8LL * ctx->sm_count * 4 + ntiles - 1) / ntiles;
@@ -464,6 +475,11 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 	if(e == cudaSuccess) e = cudaMalloc(&d_D, cells * 8);
 	if(e == cudaSuccess && N) e = cudaMalloc(&d_N, cells * 8);
 	if(e == cudaSuccess && rows_inc) e = cudaMalloc(&d_rows, cells * 4);
+	if(e == cudaSuccess && ctx->world > 1) {
+		e = cudaMemsetAsync(d_D, 0, cells * 8, ctx->stream);
+		if(e == cudaSuccess && d_N) e = cudaMemsetAsync(d_N, 0, cells * 8, ctx->stream);
+		if(e == cudaSuccess && d_rows) e = cudaMemsetAsync(d_rows, 0, cells * 4, ctx->stream);
+	}
 	if(e == cudaSuccess) e = cudaMemcpyAsync(d_tiles, tiles.data(), (size_t) ntiles * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);
 	if(e == cudaSuccess) e = cudaMemcpyAsync(ctx->mat_rank, rank.data(), (size_t) npad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
 	if(e == cudaSuccess) e = cudaMemcpyAsync(ctx->mat_lens, ctx->mat_hlens, (size_t) npad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);

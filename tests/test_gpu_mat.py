@@ -127,3 +127,24 @@ def test_golden_cases_through_the_abi(ctx, case):
     # the text carries `precision` decimals
     tol = 0.51 * 10.0 ** (-o["precision"])
     assert np.all(np.abs(D - np.array(dref)) <= tol + REL_TOL * np.abs(np.array(dref)))
+
+
+def test_rank_partition_covers_every_cell_once(built):
+    n, length = 70, 800
+    counts, totals = random_counts(n, length, seed=3)
+    lens = np.full(n, length, np.int32)
+    Do, No, _ = oracle.mat_matrix(counts, totals, lens, None, method="chi2")
+    world = 3
+    Dsum, Nsum, hits = np.zeros_like(Do), np.zeros_like(No), np.zeros_like(No)
+    for r in range(world):
+        with api.Context() as c:
+            c.set_partition(r, world)
+            c.mat_set_problem(n, length)
+            for i in range(n):
+                c.mat_put_sample(i, counts[i], totals[i])
+            D, N, dn, _ = c.mat_run(None, method="chi2")
+            Dsum += D
+            Nsum += N
+            hits += (N != 0)
+    assert np.array_equal(Nsum, No) and hits.max() == 1
+    assert close(Dsum, Do)
