@@ -954,6 +954,7 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	p.C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
 	p.ldc = ctx->n_pad;
 	p.fp4 = fp4 ? 1 : 0;
+	p.no_mask_items = (fp4 && !ctx->pair_mode) ? 1 : 0;   /* two-plane store: k_finalize_umma uses the constant */
 	long long i_const_fp4 = 0;
 	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
 	/* The expansion of slab s+1 runs beside the GEMM of slab s.  It must not start before every

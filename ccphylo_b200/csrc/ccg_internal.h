@@ -73,6 +73,7 @@ struct UmmaParams {
 	unsigned *sync;        /* lock-step epoch counters [rounds][epochs_per_item] (zeroed), or NULL */
 	int epochs_per_item;
 	unsigned *resident;    /* every CTA adds 1 once it holds its SM (gates the overlapped expansion), or NULL */
+	int no_mask_items;     /* e2m1 panel, shared-mask mode: the inclusion count is a constant, no I items */
 	int fp4;               /* e2m1 panel (kind::mxf4): slab_chunks / chunks_per_slice count chunk PAIRS, S and I are separate items */
 	int single;            /* tiles are 128 x 256 and run on the single-CTA kernel (CCG_UMMA1=1, experiments) */
 };

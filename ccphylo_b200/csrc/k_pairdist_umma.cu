@@ -480,7 +480,7 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
 	const int G = (int) (gridDim.x >> 1);                        /* clusters */
 	const int cid = (int) (blockIdx.x >> 1);
-	const int items = p.ntiles * p.kslices * (FP4 ? 2 : 1);
+	const int items = p.ntiles * p.kslices * ((FP4 && !p.no_mask_items) ? 2 : 1);   /* shared-mask mode: I is a constant */
 	const int nkb_slab = p.slab_chunks * 4;
 
 	if(threadIdx.x == 0) {
@@ -788,7 +788,7 @@ cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p_in) {
 	e = cudaFuncSetAttribute(k_pairdist_umma2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
 	if(e != cudaSuccess) return e;
 	UmmaParams p = p_in;
-	const long long items = (long long) p.ntiles * p.kslices * (p.fp4 ? 2 : 1);
+	const long long items = (long long) p.ntiles * p.kslices * ((p.fp4 && !p.no_mask_items) ? 2 : 1);
 	if(items <= 0) return cudaSuccess;
 	const int slots = p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx);   /* CTAs or CTA pairs */
 	const int grid = items < slots ? (int) items : slots;
