@@ -142,8 +142,8 @@ static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, un
 		if(rc) die_gpu(ctx, rc);
 	}
 	if(Dn > 1) {
-		phy_write(outfile, D, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision);
-		if(N) phy_write(n_into_out ? outfile : noutfile, N, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision);
+		phy_write_mt(outfile, D, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision, o->threads);
+		if(N) phy_write_mt(n_into_out ? outfile : noutfile, N, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision, o->threads);
 	}
 	ccg_host_free(D);
 	ccg_host_free(N);

@@ -191,8 +191,8 @@ static void one_template(const DistOpts *o, ccg_ctx *ctx, int n, char **filename
 				if(threaded_msgs) fprintf(stderr, "No sufficient overlap between samples:\t%s\t%s\n", filenames[slot_of[r]], filenames[slot_of[c]]);
 				else fprintf(stderr, "No sufficient overlap between samples:\t%s, %s\n", filenames[slot_of[r]], filenames[slot_of[c]]);
 			}
-	phy_write(outfile, D, o->elem_size, o->byteScale, Dn, filenames, include, target, o->flag, o->precision);
-	if(noutfile) phy_write(noutfile, N, o->elem_size, o->byteScale, Dn, filenames, include, target, o->flag, o->precision);
+	phy_write_mt(outfile, D, o->elem_size, o->byteScale, Dn, filenames, include, target, o->flag, o->precision, o->threads);
+	if(noutfile) phy_write_mt(noutfile, N, o->elem_size, o->byteScale, Dn, filenames, include, target, o->flag, o->precision, o->threads);
 	free(slot_of);
 	free(rows);
 	ccg_host_free(D);

@@ -16,5 +16,8 @@
  * matrix in input order.  cells: dn(dn-1)/2 values of elem_size bytes. */
 void phy_write(FILE *out, const void *cells, int elem_size, double byteScale, int dn, char **names,
                const unsigned char *include, const char *comment, unsigned flags, int precision);
+/* the same text, rows formatted by `threads` host threads (blocks of rows, written in order) */
+void phy_write_mt(FILE *out, const void *cells, int elem_size, double byteScale, int dn, char **names,
+                  const unsigned char *include, const char *comment, unsigned flags, int precision, int threads);
 
 #endif

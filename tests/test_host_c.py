@@ -1,0 +1,44 @@
+"""Host-side C of the driver, on CPU: the threaded Phylip writer prints exactly what a per-cell fprintf loop in the
+reference's format prints (all four cell types, strict and relaxed names, comment line), and the driver's option
+scanner accepts the reference's command-line dialect."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "ccphylo_b200", "host")
+BIN = os.path.join(ROOT, "ccphylo_b200", "bin", "ccphylo-b200")
+
+
+def test_threaded_phylip_writer_matches_per_cell_fprintf(tmp_path):
+    exe = str(tmp_path / "phy_writer_test")
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "phy_writer_test.c"),
+                    os.path.join(HOST, "phy_writer.c"), "-lpthread", "-lm"], check=True)
+    for n in ("9", "1200"):
+        p = subprocess.run([exe, n, str(tmp_path)], capture_output=True, text=True)
+        assert p.returncode == 0 and p.stdout.strip() == "OK", p.stderr
+
+
+def test_option_scanner_dialect(built, tmp_path):
+    def run(*args):
+        return subprocess.run([BIN, "dist"] + list(args), capture_output=True, text=True, cwd=str(tmp_path))
+
+    assert run("-h").stdout.startswith("#ccphylo-b200 dist")
+    assert "Relaxed Phylip" in run("-F").stdout and "Relaxed Phylip" in run("--flag_help").stdout
+    assert "# cos:" in run("-D").stdout
+    assert run("--bogus").stderr == 'Unknown argument or option: "--bogus"\n'
+    assert run("-Z").stderr == 'Unknown argument or option: "-Z"\n'
+    assert run("-x").stderr == "Missing argument at x.\n"
+    assert run("-x", "abc").stderr == "Invalid value parsed at x.\n"
+    assert run("--print_precision=abc").stderr == "Invalid value parsed at print_precision.\n"
+    assert run("-d", "foo").stderr == 'Invalid value parsed at "-d".\n'
+    assert run("-d", "l2x").stderr == 'Invalid value parsed at "-d ln".\n'
+    assert run("-C", "150").stderr == 'Invalid value parsed at "--min_cov".\n'
+    assert run("-s", "0").stderr == 'Invalid value parsed at "--short_precision".\n'
+    # bundled flags, attached values, `-s` without a value before another option: all parse; with two FASTA
+    # files the run then stops at the device (this container has none) or at the refused option
+    a = tmp_path / "a.fsa"
+    a.write_text(">ref\nACGT\n")
+    p = run("-pf3", "-s", "-W", "100", "-rref", "-i", str(a), str(a), "-P", "2")
+    assert p.returncode == 1 and "-P / --proximity is not available on the GPU path" in p.stderr
+    p = run("-r", "ref", "-a", "x", str(a), str(a))
+    assert p.returncode == 1 and "-a / --add" in p.stderr
