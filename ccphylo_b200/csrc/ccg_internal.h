@@ -154,6 +154,7 @@ struct ccg_ctx {
 
 	/* count-matrix (.mat) path, k_matdist.cu */
 	void *mat_counts;          /* [mat_npad][mat_lpad] 16-byte records */
+	void *mat_norms;           /* [mat_npad][mat_lpad] doubles: sqrt of the squared count-vector length (cos) */
 	int *mat_lens, *mat_hlens; /* device / host: rows per slot */
 	int *mat_rank;
 	int mat_n, mat_npad;

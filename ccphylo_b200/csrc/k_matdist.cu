@@ -9,8 +9,9 @@
  * sample's template is parsed once on the host and kept resident in HBM.
  *
  * Device layout: counts[slot][position] = 16-byte record {A, C, G, T, -, N as u16; total as u32}
- * (the order the reference stores them in, matparse.c:254-259), positions zero-padded to a
- * multiple of 64.  Insertion rows (reference base '-') are dropped by the host parser.
+ * (the order the reference stores them in, matparse.c:254-259) plus norms[slot][position] = the
+ * double sqrt(sum of squared counts) that `cos` needs, positions zero-padded to a multiple of 64.
+ * Insertion rows (reference base '-') are dropped by the host parser.
  *
  * Per pair (i > j), over the positions p < len_j of the earlier sample (the one the reference
  * streams):   if(minDepth <= tot_j[p]) { ++nNucs;
@@ -217,12 +218,19 @@ __device__ __forceinline__ double veccmp(const Rec &a, const Rec &b, const MatPa
 	}
 }
 
+/* cos: the two square roots of coscmp depend on one sample each, so they are taken once per sample and
+ * position on the host (ccg_mat_put_sample) instead of once per pair: sqrt(c1) * sqrt(c2) and the division are
+ * the same IEEE operations on the same values, i.e. every per-position term is still bit-identical to the
+ * reference's, at less than half of the FP64 work. */
 template <int M>
 __global__ void __launch_bounds__(MT * MT)
-k_matdist(const uint4 *__restrict__ counts, long long lpad, const int2 *__restrict__ tiles, int ntiles, int nslices,
-          int pos_per_slice, const int *__restrict__ lens, MatParams mp, double *__restrict__ part_dist,
+k_matdist(const uint4 *__restrict__ counts, const double *__restrict__ norms, long long lpad, const int2 *__restrict__ tiles,
+          int ntiles, int nslices, int pos_per_slice, const int *__restrict__ lens, MatParams mp, double *__restrict__ part_dist,
           unsigned *__restrict__ part_rows) {
 	__shared__ uint4 sA[MT][MP + 1], sB[MT][MP + 1];
+	extern __shared__ double s_norm[];                       /* cos only: [2][MT][MP + 1] */
+	double (*nA)[MP + 1] = reinterpret_cast<double (*)[MP + 1]>(s_norm);
+	double (*nB)[MP + 1] = reinterpret_cast<double (*)[MP + 1]>(s_norm + MT * (MP + 1));
 	const int tile = blockIdx.x % ntiles, ks = blockIdx.x / ntiles;
 	const int ti = tiles[tile].x, tj = tiles[tile].y;
 	const int li = threadIdx.x / MT, lj = threadIdx.x % MT;
@@ -240,6 +248,10 @@ k_matdist(const uint4 *__restrict__ counts, long long lpad, const int2 *__restri
 			const int slot = (which ? tj : ti) * MT + r;
 			const uint4 v = counts[(size_t) slot * lpad + p0 + p];
 			if(which) sB[r][p] = v; else sA[r][p] = v;
+			if(M == CCG_MAT_COS) {
+				const double nv = norms[(size_t) slot * lpad + p0 + p];
+				if(which) nB[r][p] = nv; else nA[r][p] = nv;
+			}
 		}
 		__syncthreads();
 		if(sj < si) {
@@ -250,7 +262,19 @@ k_matdist(const uint4 *__restrict__ counts, long long lpad, const int2 *__restri
 				if(mp.minDepth <= (unsigned) b.tot) {
 					const Rec a = unpack(sA[li][p]);
 					if(mp.minDepth <= (unsigned) a.tot) {
-						const double d = veccmp<M>(a, b, mp);
+						double d;
+						if(M == CCG_MAT_COS) {
+							/* coscmp matcmp.c:420 with sqrt(c1), sqrt(c2) precomputed per sample */
+							const double sa = nA[li][p], sb = nB[lj][p];
+							double dot = 0;
+#pragma unroll
+							for(int k = 0; k < 5; ++k) dot += (double) (a.c[k] * b.c[k]);
+							if(sa == 0 || sb == 0) d = -1;
+							else {
+								d = 1 - dot / (sa * sb);
+								d = d < 0 ? 0 : d;
+							}
+						} else d = veccmp<M>(a, b, mp);
 						if(0 <= d) { dist += d; ++rows; }
 					}
 				}
@@ -302,7 +326,8 @@ k_matdist_finalize(const int2 *__restrict__ tiles, int ntiles, int nslices, cons
 	}
 }
 
-typedef void (*MatKernel)(const uint4 *, long long, const int2 *, int, int, int, const int *, MatParams, double *, unsigned *);
+typedef void (*MatKernel)(const uint4 *, const double *, long long, const int2 *, int, int, int, const int *, MatParams, double *,
+                          unsigned *);
 
 MatKernel pick_kernel(int method) {
 	switch(method) {
@@ -341,6 +366,7 @@ MatKernel pick_kernel(int method) {
 
 void ccg_mat_free(ccg_ctx *ctx) {
 	cudaFree(ctx->mat_counts); ctx->mat_counts = 0;
+	cudaFree(ctx->mat_norms); ctx->mat_norms = 0;
 	cudaFree(ctx->mat_lens); ctx->mat_lens = 0;
 	cudaFree(ctx->mat_part_dist); ctx->mat_part_dist = 0;
 	cudaFree(ctx->mat_part_rows); ctx->mat_part_rows = 0;
@@ -371,12 +397,19 @@ extern "C" int ccg_mat_set_problem(ccg_ctx *ctx, int n, int max_len) {
 		return CCG_ERR_NOMEM;
 	}
 	MCK(ctx, cudaMemsetAsync(ctx->mat_counts, 0, bytes, ctx->stream));
+	/* sqrt of the squared count-vector length per sample and position (cos) */
+	if(cudaMalloc(&ctx->mat_norms, bytes / 2) != cudaSuccess) {
+		snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc of %zu bytes for the count-vector norms failed", bytes / 2);
+		ctx->mat_norms = 0;
+		return CCG_ERR_NOMEM;
+	}
+	MCK(ctx, cudaMemsetAsync(ctx->mat_norms, 0, bytes / 2, ctx->stream));
 	MCK(ctx, cudaMalloc(&ctx->mat_lens, (size_t) ctx->mat_npad * sizeof(int)));
 	MCK(ctx, cudaMalloc(&ctx->mat_rank, (size_t) ctx->mat_npad * sizeof(int)));
 	ctx->mat_hlens = (int *) calloc((size_t) ctx->mat_npad, sizeof(int));
 	if(!ctx->mat_hlens) return CCG_ERR_NOMEM;
 	/* pinned staging for one sample */
-	if(cudaHostAlloc(&ctx->mat_stage, (size_t) ctx->mat_lpad * 16, cudaHostAllocDefault) != cudaSuccess) {
+	if(cudaHostAlloc(&ctx->mat_stage, (size_t) ctx->mat_lpad * 24, cudaHostAllocDefault) != cudaSuccess) {
 		ctx->mat_stage = 0;
 		snprintf(ctx->err, sizeof(ctx->err), "cudaHostAlloc of %lld staging bytes failed", ctx->mat_lpad * 16);
 		return CCG_ERR_NOMEM;
@@ -390,16 +423,28 @@ extern "C" int ccg_mat_put_sample(ccg_ctx *ctx, int idx, const uint16_t *counts6
 	/* the staging buffer is reused: wait for the previous upload */
 	MCK(ctx, cudaStreamSynchronize(ctx->stream));
 	uint16_t *st = (uint16_t *) ctx->mat_stage;
+	double *sn = (double *) ((char *) ctx->mat_stage + (size_t) ctx->mat_lpad * 16);
 	for(int p = 0; p < len; ++p) {
 		const uint16_t *c = counts6 + (size_t) p * 6;
 		uint16_t *o = st + (size_t) p * 8;
 		unsigned tot = totals ? totals[p] : (unsigned) c[0] + c[1] + c[2] + c[3] + c[4] + c[5];
 		o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = c[3]; o[4] = c[4]; o[5] = c[5];
 		memcpy(o + 6, &tot, 4);
+		/* coscmp's c1: int products summed in an unsigned long (matcmp.c:426-437) */
+		unsigned long long c1 = 0;
+		for(int k = 0; k < 5; ++k) c1 += (unsigned long long) (long long) ((int) c[k] * (int) c[k]);
+		sn[p] = sqrt((double) c1);
 	}
 	uint4 *dst = (uint4 *) ctx->mat_counts + (size_t) idx * (size_t) ctx->mat_lpad;
-	if(len) MCK(ctx, cudaMemcpyAsync(dst, st, (size_t) len * 16, cudaMemcpyHostToDevice, ctx->stream));
-	if(len < ctx->mat_lpad) MCK(ctx, cudaMemsetAsync(dst + len, 0, (size_t) (ctx->mat_lpad - len) * 16, ctx->stream));
+	double *dstn = (double *) ctx->mat_norms + (size_t) idx * (size_t) ctx->mat_lpad;
+	if(len) {
+		MCK(ctx, cudaMemcpyAsync(dst, st, (size_t) len * 16, cudaMemcpyHostToDevice, ctx->stream));
+		MCK(ctx, cudaMemcpyAsync(dstn, sn, (size_t) len * 8, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	if(len < ctx->mat_lpad) {
+		MCK(ctx, cudaMemsetAsync(dst + len, 0, (size_t) (ctx->mat_lpad - len) * 16, ctx->stream));
+		MCK(ctx, cudaMemsetAsync(dstn + len, 0, (size_t) (ctx->mat_lpad - len) * 8, ctx->stream));
+	}
 	ctx->mat_hlens[idx] = len;
 	return CCG_OK;
 }
@@ -489,7 +534,10 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 		mp.order = order;
 		mp.alpha = alpha;
 		cudaEventRecord(ctx->ev0, ctx->stream);
-		kern<<<(unsigned) ((long long) ntiles * nslices), MT * MT, 0, ctx->stream>>>((const uint4 *) ctx->mat_counts, ctx->mat_lpad, d_tiles,
+		const size_t dyn = method == CCG_MAT_COS ? (size_t) 2 * MT * (MP + 1) * sizeof(double) : 0;
+		if(dyn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
+		kern<<<(unsigned) ((long long) ntiles * nslices), MT * MT, dyn, ctx->stream>>>((const uint4 *) ctx->mat_counts,
+		                                                                              (const double *) ctx->mat_norms, ctx->mat_lpad, d_tiles,
 		                                                                              ntiles, nslices, pos_per_slice, ctx->mat_lens, mp,
 		                                                                              ctx->mat_part_dist, ctx->mat_part_rows);
 		cudaEventRecord(ctx->ev1, ctx->stream);
