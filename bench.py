@@ -445,6 +445,8 @@ def main():
             # the gather lands in the buffers the device-resident arm used (same contents)
             seqs_t.zero_()
             masks_t.zero_()
+            C.memset(hD_ptr, 0, max(ncell, 1) * 8)              # cells of other ranks stay zero
+            C.memset(hN_ptr, 0, max(ncell, 1) * 8)
 
             def e2e_step():
                 seqs_t[r0:r0 + n_host].copy_(hs_t, non_blocking=True)
@@ -453,11 +455,12 @@ def main():
                 dist.all_gather_into_tensor(masks_t, masks_t[r0:r0 + n_host])
                 ctx.set_problem(n, length, pair=True)
                 ctx.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
-                rc = L.ccg_run_pair(ctx._h, include.ctypes.data, 0, 1, 0.5, 8, 1.0, hD_ptr, hN_ptr, C.byref(dn))
-                if rc:
-                    raise SystemExit("ccg_run_pair failed: " + L.ccg_last_error(ctx._h).decode())
+                # the epilogue writes this rank's cells straight into the pinned host matrices (mapped memory):
+                # a rank owns 1/N of the cells, a device-to-host copy of the whole matrix would move N times that
+                ctx.run_pair_dev(hD_ptr, hN_ptr, norm=0, min_length=1, min_cov=0.5, elem_size=8)
+                ctx.sync()
             call = (f"per rank: H2D of its {n_host}-sample shard (pinned rows) -> NCCL all-gather of the packed rows over "
-                    f"NVLink -> ccg_put_samples_packed_dev + ccg_run_pair(host D/N out)")
+                    f"NVLink -> ccg_put_samples_packed_dev + ccg_run_pair_dev writing the rank's cells into pinned host D/N")
             h2d = int(n * (row_s + row_m))                          # summed over the ranks: every row crosses PCIe once
 
         for _ in range(2):
@@ -483,7 +486,8 @@ def main():
             if not np.array_equal(hD[:ncell][own], dD[own]) or (world > 1 and not own.any()):
                 raise SystemExit("bench.py: host-path result differs from the device-path result")
         e2e = {"value": total_basecmp / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(2 * ncell * 8) * world, "steps": e_steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(2 * ncell * 8) * (1 if sharded else world),
+               "steps": e_steps,
                "call": call}
         for p in (hs_ptr, hm_ptr, hD_ptr, hN_ptr):
             L.ccg_host_free(p)

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_every_entry_point_cites_the_reference(built):
     text = open(os.path.join(ROOT, "include", "ccphylo_gpu.h")).read()
     for needle in ("fsacmpthrd.h:49", "fsacmpthrd.c:261", "fsacmpthrd.c:108", "qseqs.c:60", "fsacmp.c:164",
-                   "cdist.c:181", "matrix.c:32"):
+                   "cdist.c:181", "matrix.c:32", "matcmp.c:448", "ltdmatrixthrd.c:376", "dist.c:738"):
         assert needle in text
 
 
@@ -52,7 +52,8 @@ def test_product_never_imports_the_oracle():
     for path in glob.glob(os.path.join(ROOT, "ccphylo_b200", "**", "*"), recursive=True):
         if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
             text = open(path, errors="ignore").read()
-            assert "import oracle" not in text and "liboracle" not in text and "fsa_oracle" not in text, path
+            assert "import oracle" not in text and "liboracle" not in text and "fsa_oracle" not in text \
+                and "mat_oracle" not in text, path
 
 
 def test_partition_helpers_are_host_only(built):
