@@ -51,6 +51,41 @@ def test_fasta_golden_byte_for_byte(built, tmp_path, case):
     assert p.stderr.replace(td + "/", "") == case["stderr"]
 
 
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu")
+BOUND = [c for c in ALL_CASES if c["name"].startswith(("c1_pair", "c1_global", "c1_float", "c1_short_W", "c6_", "c7_",
+                                                       "rand_L129_", "rand_L4100_pair"))]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="oracle/_ref/ccphylo_gpu was not built (needs /root/reference)")
+@pytest.mark.parametrize("case", BOUND, ids=[c["name"] for c in BOUND])
+def test_reference_bound_to_the_gpu_library(built, tmp_path, case):
+    """The drop-in claim, literally: the unmodified reference binary with fsaCmpThreadOut bound to
+    libccphylo_gpu.so through integration/fsacmpgpu.c (oracle/Makefile, target ref_gpu) prints what the
+    original prints."""
+    td = str(tmp_path)
+    seqs = [POOL[k] for k in case["seq_ids"]]
+    if case["msa"]:
+        path = os.path.join(td, "msa.fsa")
+        with open(path, "w") as f:
+            for nm, s in zip(case["names"], seqs):
+                f.write(f">{nm}\n{s}\n")
+        cmd = [REF_GPU, "dist", "-i", path]
+    else:
+        files = []
+        for nm, s in zip(case["names"], seqs):
+            path = os.path.join(td, nm)
+            with open(path, "w") as f:
+                f.write(f">ref\n{s}\n")
+            files.append(path)
+        cmd = [REF_GPU, "dist", "-r", "ref", "-i"] + files
+    phy, num = os.path.join(td, "o.phy"), os.path.join(td, "o.num")
+    p = run(cmd + case["args"] + ["-o", phy, "-n", num], td)
+    assert p.returncode == case["returncode"], p.stderr
+    assert open(phy).read() == case["phy"]
+    assert open(num).read() == case["num"]
+    assert p.stderr.replace(td + "/", "") == case["stderr"]
+
+
 def test_fasta_gz_input_stdout_and_long_options(built, tmp_path):
     case = next(c for c in CASES if c["name"] == "c1_pair_W")
     td = str(tmp_path)

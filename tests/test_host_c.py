@@ -42,3 +42,16 @@ def test_option_scanner_dialect(built, tmp_path):
     assert p.returncode == 1 and "-P / --proximity is not available on the GPU path" in p.stderr
     p = run("-r", "ref", "-a", "x", str(a), str(a))
     assert p.returncode == 1 and "-a / --add" in p.stderr
+
+
+def test_integration_stub_is_the_documented_one_and_compiles(tmp_path):
+    import re
+    import pytest
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```c\n(.*?)```", md, flags=re.S)
+    stub = open(os.path.join(ROOT, "integration", "fsacmpgpu.c")).read()
+    assert any(b == stub for b in blocks), "integration/fsacmpgpu.c and the stub printed in INTEGRATION.md differ"
+    if not os.path.exists("/root/reference/fsacmpthrd.h"):
+        pytest.skip("the reference headers are only present in the authoring container")
+    subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror", "-c", "-I", "/root/reference", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "integration", "fsacmpgpu.c"), "-o", str(tmp_path / "stub.o")], check=True)
