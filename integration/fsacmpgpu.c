@@ -36,6 +36,6 @@ void fsaCmpGpuOut(int tnum, void *(*func)(void *), Matrix *D, Matrix *N, int n, 
 		exit(rc);
 	}
 	D->n = Dn;
-	if(N) N->n = Dn;
+	if(pair && N) N->n = Dn;        /* cmpFsaThrd never touches N: the .num file stays empty (dist.c:177) */
 	if(!pair) fprintf(stderr, "# %u / %d bases included in distance matrix.\n", inc, len); /* fsacmpthrd.c:165 */
 }

@@ -86,6 +86,43 @@ def test_reference_bound_to_the_gpu_library(built, tmp_path, case):
     assert p.stderr.replace(td + "/", "") == case["stderr"]
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ccphylo")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
+def test_config1_64_samples_5mbp_against_the_reference_binary(built, tmp_path):
+    """BASELINE configs[0] at full size: 64 synthetic 5 Mbp KMA consensus files, `dist -r ref -f 3 -n`.  The
+    unmodified reference binary runs on the host cores; this driver and the reference bound to the GPU library
+    must print the same bytes (D, N and the stderr inclusion lines)."""
+    import time
+    from ccphylo_b200 import synth
+    td = str(tmp_path)
+    n, length = 64, 5_000_000
+    rows = synth.make_ascii(n, length, seed=1)
+    files = []
+    for i in range(n):
+        path = os.path.join(td, f"s{i:02d}.fsa")
+        synth.write_fasta(path, rows[i], header="ref", width=60)
+        files.append(path)
+    del rows
+    outs = {}
+    for tag, exe in (("reference", REF_BIN), ("driver", BIN), ("bound", REF_GPU)):
+        if not os.path.exists(exe):
+            continue
+        phy, num = os.path.join(td, tag + ".phy"), os.path.join(td, tag + ".num")
+        t0 = time.perf_counter()
+        p = run([exe, "dist", "-r", "ref", "-f", "3", "-t", str(os.cpu_count() or 1), "-i"] + files + ["-o", phy, "-n", num], td)
+        dt = time.perf_counter() - t0
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[tag] = (open(phy).read(), open(num).read(), p.stderr, dt)
+        print(f"config 1 ({n} x {length} bp) {tag}: {dt:.2f} s wall")
+    assert len(outs["reference"][0]) > 2000
+    for tag in outs:
+        assert outs[tag][0] == outs["reference"][0], tag + ": .phy differs from the reference binary's"
+        assert outs[tag][1] == outs["reference"][1], tag + ": .num differs from the reference binary's"
+        assert outs[tag][2] == outs["reference"][2], tag + ": stderr differs from the reference binary's"
+
+
 def test_fasta_gz_input_stdout_and_long_options(built, tmp_path):
     case = next(c for c in CASES if c["name"] == "c1_pair_W")
     td = str(tmp_path)
