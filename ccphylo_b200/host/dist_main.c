@@ -28,6 +28,17 @@
 
 #define VERSION "0.1.0 (B200 path of ccphylo dist 0.8.5)"
 
+/* CCPHYLO_GPU_STATS=1: phase timings on stderr (off by default: scripts parse the reference's stderr lines) */
+#include <time.h>
+static double now_s(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+static void stat_line(const char *what, double t0) {
+	if(getenv("CCPHYLO_GPU_STATS")) fprintf(stderr, "# gpu-stats\t%s\t%.3f s\n", what, now_s() - t0);
+}
+
 static void die_errno(void) {
 	fprintf(stderr, "Error: %d (%s)\n", errno, strerror(errno));
 	exit(errno ? errno : 1);
@@ -129,6 +140,7 @@ static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, un
 	void *D = alloc_cells((size_t) included, o->elem_size);
 	void *N = (pair && noutfile) ? alloc_cells((size_t) included, o->elem_size) : 0;
 	int Dn = 0, rc;
+	const double t_cmp = now_s();
 	if(pair) {
 		/* minLength was already maxed with minCov * len; the library repeats that (fsacmpthrd.c:292) */
 		rc = ccg_run_pair(ctx, include, o->norm, minLength, o->minCov, o->elem_size, o->byteScale, D, N, &Dn);
@@ -141,6 +153,7 @@ static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, un
 		rc = ccg_run_global(ctx, include, o->norm, o->elem_size, o->byteScale, D, &Dn, &ginc);
 		if(rc) die_gpu(ctx, rc);
 	}
+	stat_line("  compare (device, incl. result copy)", t_cmp);
 	if(Dn > 1) {
 		phy_write_mt(outfile, D, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision, o->threads);
 		if(N) phy_write_mt(n_into_out ? outfile : noutfile, N, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision, o->threads);
@@ -166,8 +179,11 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	if(!pool) die_errno();
 
 	ccg_ctx *ctx = 0;
+	double t0 = now_s();
 	int rc = ccg_init(&ctx, -1);
 	if(rc) die_gpu(0, rc);
+	stat_line("device context", t0);
+	t0 = now_s();
 	unsigned char *include = malloc((size_t) n);
 	if(!include) die_errno();
 	memset(include, 1, (size_t) n);
@@ -235,8 +251,11 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 		pool_release(pool, i);
 	}
 	pool_finish(pool);
+	stat_line("parse + upload", t0);
+	t0 = now_s();
 	if(!have_ref) included = 0;
 	compare_and_print(o, ctx, n, len, minLength, include, included, o->filenames, o->targetTemplate, outfile, noutfile, 0);
+	stat_line("compare + print", t0);
 	ccg_destroy(ctx);
 	for(int k = 0; k < window; ++k) bytebuf_free(&slots[k].codes);
 	free(slots);

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Wall time of the host driver on BASELINE configs[0]/[1]-shaped inputs (n files x 5 Mbp FASTA), with phase timings."""
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ccphylo_b200 import synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+length = int(sys.argv[2]) if len(sys.argv) > 2 else 5_000_000
+with tempfile.TemporaryDirectory() as td:
+    files = []
+    base = synth.make_ascii(min(n, 16), length, seed=1)
+    for i in range(n):
+        path = os.path.join(td, f"s{i:04d}.fsa")
+        synth.write_fasta(path, base[i % len(base)], header="ref", width=60)
+        files.append(path)
+    env = dict(os.environ, CCPHYLO_GPU_STATS="1")
+    for exe in ("ccphylo_b200/bin/ccphylo-b200", "oracle/_ref/ccphylo"):
+        if not os.path.exists(os.path.join(ROOT, exe)) or (n > 256 and "oracle" in exe):
+            continue
+        t0 = time.perf_counter()
+        p = subprocess.run([os.path.join(ROOT, exe), "dist", "-r", "ref", "-f", "3", "-t", str(os.cpu_count()), "-i"] + files +
+                           ["-o", os.path.join(td, "o.phy"), "-n", os.path.join(td, "o.num")], capture_output=True, text=True, env=env)
+        dt = time.perf_counter() - t0
+        print(f"{exe}: rc={p.returncode} {dt:.2f} s wall, n={n}")
+        print("".join(l + "\n" for l in p.stderr.splitlines() if "gpu-stats" in l or "rror" in l), end="")
