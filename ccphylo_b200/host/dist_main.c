@@ -263,15 +263,48 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 }
 
 /* ltdMsaMatrix_get (cdist.c:196-390): one multi-FASTA alignment, records are the samples */
+typedef struct {
+	int status;              /* PARSE_OK | PARSE_NO_SEQ | PARSE_OPEN_FAILED */
+	ByteBuf header, codes;
+	unsigned known;
+} MsaParsed;
+
+typedef struct {
+	const char *path;
+	const long long *offsets;     /* stream offset of every record's '>' */
+	unsigned char table[256];
+} MsaJob;
+
+static void msa_parse_one(int job, void *state, void *user) {
+	const MsaJob *mj = (const MsaJob *) user;
+	MsaParsed *r = (MsaParsed *) state;
+	r->known = 0;
+	r->codes.len = 0;
+	r->status = PARSE_OPEN_FAILED;
+	FsaReader *fr = fsa_open(mj->path);
+	if(!fr) return;
+	if(fsa_seek(fr, mj->offsets[job]) == 0 && fsa_next_header(fr, &r->header)) {
+		if(!fsa_read_codes(fr, mj->table, &r->codes)) r->status = PARSE_NO_SEQ;
+		else {
+			unsigned known = 0;
+			for(size_t k = 0; k < r->codes.len; ++k) known += r->codes.data[k] < 4;
+			r->known = known;
+			r->status = PARSE_OK;
+		}
+	}
+	fsa_close(fr);
+}
+
 static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	const char *path = o->numFile ? o->filenames[0] : "-";
-	unsigned char table[256];
-	fsa_code_table(o->flag, table);
+	MsaJob mj;
+	fsa_code_table(o->flag, mj.table);
 	const int pair = (o->flag & 2) != 0;
 
-	/* the device store is sized up front: count the records first (a second pass is far cheaper
-	 * than keeping the alignment in host memory) */
-	int nrec = 0;
+	/* The device store is sized up front, so the records are counted first (a second pass is far cheaper
+	 * than keeping the alignment in host memory); the same pass notes where every record starts, so that a
+	 * plain (uncompressed) alignment can then be parsed by -t threads in parallel, each seeking to its
+	 * record.  Compressed input is read twice, sequentially. */
 	if(strcmp(path, "-") == 0) {
 		fprintf(stderr, "MSA input from stdin is not supported on the GPU path (the alignment is read twice).\n");
 		exit(1);
@@ -285,14 +318,43 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 		fprintf(stderr, "Cannot determine format of file:\t%s\n", path);
 		exit(1);
 	}
-	ByteBuf header, codes;
+	const int plain = fsa_is_plain(fr);
+	ByteBuf header;
 	bytebuf_init(&header, 256);
-	bytebuf_init(&codes, 1 << 20);
-	while(fsa_next_header(fr, &header)) ++nrec;
+	int nrec = 0, cap = 1024;
+	long long *offsets = malloc((size_t) cap * sizeof(long long)), off = 0;
+	if(!offsets) die_errno();
+	while(fsa_next_header_off(fr, &header, &off)) {
+		if(nrec == cap) {
+			cap <<= 1;
+			offsets = realloc(offsets, (size_t) cap * sizeof(long long));
+			if(!offsets) die_errno();
+		}
+		offsets[nrec++] = off;
+	}
 	fsa_close(fr);
 
-	fr = fsa_open(path);
-	if(!fr) die_errno();
+	int nthreads = o->threads < 1 ? 1 : o->threads;
+	if(nthreads > nrec) nthreads = nrec > 0 ? nrec : 1;
+	const int parallel = plain && nthreads > 1;
+	const int window = parallel ? nthreads + 2 : 1;
+	MsaParsed *slots = calloc((size_t) window, sizeof(MsaParsed));
+	if(!slots) die_errno();
+	for(int k = 0; k < window; ++k) {
+		bytebuf_init(&slots[k].header, 256);
+		bytebuf_init(&slots[k].codes, 1 << 20);
+	}
+	mj.path = path;
+	mj.offsets = offsets;
+	OrderedPool *pool = 0;
+	if(parallel) {
+		pool = pool_start(nrec, nthreads, window, slots, sizeof(MsaParsed), msa_parse_one, &mj);
+		if(!pool) die_errno();
+	} else {
+		fr = fsa_open(path);
+		if(!fr) die_errno();
+	}
+
 	ccg_ctx *ctx = 0;
 	int rc = ccg_init(&ctx, -1);
 	if(rc) die_gpu(0, rc);
@@ -300,45 +362,68 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	if(!names) die_errno();
 	unsigned minLength = o->minLength;
 	int len = 0, have_ref = 0, n = 0;
-	while(fsa_next_header(fr, &header)) {
-		if(!fsa_read_codes(fr, table, &codes)) break;       /* header at the very end of the file: no record */
-		unsigned known = 0;
-		for(size_t k = 0; k < codes.len; ++k) known += codes.data[k] < 4;
-		const char *name = (const char *) header.data;
+	for(int job = 0; job < nrec; ++job) {
+		MsaParsed *r;
+		if(parallel) r = (MsaParsed *) pool_take(pool, job);
+		else {
+			r = &slots[0];
+			r->status = PARSE_OPEN_FAILED;
+			if(fsa_next_header(fr, &r->header)) {
+				if(!fsa_read_codes(fr, mj.table, &r->codes)) r->status = PARSE_NO_SEQ;
+				else {
+					unsigned known = 0;
+					for(size_t k = 0; k < r->codes.len; ++k) known += r->codes.data[k] < 4;
+					r->known = known;
+					r->status = PARSE_OK;
+				}
+			}
+		}
+		if(r->status != PARSE_OK) {
+			/* a header at the very end of the file is no record (seqparse.c:28); anything else is an I/O error */
+			if(r->status == PARSE_OPEN_FAILED) {
+				fprintf(stderr, "Filename:\t%s\n", path);
+				die_errno();
+			}
+			if(parallel) pool_release(pool, job);
+			continue;
+		}
+		const char *name = (const char *) r->header.data;
+		const unsigned known = r->known;
 		int keep;
 		if(have_ref) {
-			if((int) codes.len != len) {
+			if((int) r->codes.len != len) {
 				fprintf(stderr, "Sequences does not match: >%s\n", name);
 				exit(1);
 			}
 			/* shared-mask mode keeps a later record only if it EXCEEDS the threshold (cdist.c:270) */
 			keep = pair ? !(known < minLength) : (minLength < known);
 		} else {
-			len = (int) codes.len;
+			len = (int) r->codes.len;
 			if(minLength < o->minCov * len) minLength = (unsigned) (o->minCov * len);
 			keep = !(known < minLength);
 		}
-		if(!keep) {
-			fprintf(stderr, "# Excluded:\t%s\t( %d / %d )\n", name, (int) known, len);
-			continue;
+		if(!keep) fprintf(stderr, "# Excluded:\t%s\t( %d / %d )\n", name, (int) known, len);
+		else {
+			fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", name, (int) known, len);
+			if(!have_ref) {
+				have_ref = 1;
+				rc = ccg_set_problem(ctx, nrec, len, 1);
+				if(rc) die_gpu(ctx, rc);
+			}
+			names[n] = strdup(name);
+			if(!names[n]) die_errno();
+			if(len > 0) {
+				rc = ccg_put_sample_codes(ctx, n, r->codes.data);
+				if(rc) die_gpu(ctx, rc);
+				rc = ccg_sync(ctx);
+				if(rc) die_gpu(ctx, rc);
+			}
+			++n;
 		}
-		fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", name, (int) known, len);
-		if(!have_ref) {
-			have_ref = 1;
-			rc = ccg_set_problem(ctx, nrec, len, 1);
-			if(rc) die_gpu(ctx, rc);
-		}
-		names[n] = strdup(name);
-		if(!names[n]) die_errno();
-		if(len > 0) {
-			rc = ccg_put_sample_codes(ctx, n, codes.data);
-			if(rc) die_gpu(ctx, rc);
-			rc = ccg_sync(ctx);
-			if(rc) die_gpu(ctx, rc);
-		}
-		++n;
+		if(parallel) pool_release(pool, job);
 	}
-	fsa_close(fr);
+	if(parallel) pool_finish(pool);
+	else fsa_close(fr);
 	/* excluded records were dropped: the n kept samples occupy slots 0..n-1 */
 	unsigned char *include = malloc((size_t) (nrec ? nrec : 1));
 	if(!include) die_errno();
@@ -350,8 +435,13 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	for(int k = 0; k < n; ++k) free(names[k]);
 	free(names);
 	free(include);
+	free(offsets);
+	for(int k = 0; k < window; ++k) {
+		bytebuf_free(&slots[k].header);
+		bytebuf_free(&slots[k].codes);
+	}
+	free(slots);
 	bytebuf_free(&header);
-	bytebuf_free(&codes);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@ struct FsaReader {
 	gzFile gz;
 	unsigned char *buf;
 	size_t pos, avail;
+	long long base;          /* stream offset of buf[0] */
 	int eof;
 };
 
@@ -93,6 +94,7 @@ void fsa_close(FsaReader *r) {
 static int refill(FsaReader *r) {
 	int got;
 	if(r->eof) return 0;
+	r->base += (long long) r->avail;
 	got = gzread(r->gz, r->buf, CHUNK);
 	if(got <= 0) {
 		r->eof = 1;
@@ -104,12 +106,34 @@ static int refill(FsaReader *r) {
 	return 1;
 }
 
+long long fsa_tell(const FsaReader *r) {
+	return r->base + (long long) r->pos;
+}
+
+int fsa_is_plain(FsaReader *r) {
+	/* gzdirect is only meaningful once the header has been looked at */
+	if(r->pos == r->avail && !r->eof) refill(r);
+	return gzdirect(r->gz) ? 1 : 0;
+}
+
+int fsa_seek(FsaReader *r, long long offset) {
+	if(gzseek(r->gz, (z_off_t) offset, SEEK_SET) < 0) return -1;
+	r->base = offset;
+	r->pos = r->avail = 0;
+	r->eof = 0;
+	return 0;
+}
+
 int fsa_peek(FsaReader *r) {
 	if(r->pos == r->avail && !refill(r)) return -1;
 	return r->buf[r->pos];
 }
 
 int fsa_next_header(FsaReader *r, ByteBuf *header) {
+	return fsa_next_header_off(r, header, 0);
+}
+
+int fsa_next_header_off(FsaReader *r, ByteBuf *header, long long *offset) {
 	header->len = 0;
 	/* find the next '>' */
 	for(;;) {
@@ -117,6 +141,7 @@ int fsa_next_header(FsaReader *r, ByteBuf *header) {
 		if(r->pos == r->avail && !refill(r)) return 0;
 		hit = memchr(r->buf + r->pos, '>', r->avail - r->pos);
 		if(hit) {
+			if(offset) *offset = r->base + (long long) (hit - r->buf);
 			r->pos = (size_t) (hit - r->buf) + 1;
 			break;
 		}

@@ -33,9 +33,18 @@ int fsa_peek(FsaReader *r);
 /* advance to the next '>' and read the header line (without '>', trailing white space
  * stripped) into header; 0 at end of file (seqparse.c:128) */
 int fsa_next_header(FsaReader *r, ByteBuf *header);
+/* same; *offset receives the stream offset of the record's '>' */
+int fsa_next_header_off(FsaReader *r, ByteBuf *header, long long *offset);
 /* translate the sequence up to the next '>' or end of file, keeping codes < 32; returns 0
  * only if the stream was already exhausted (seqparse.c:195) */
 int fsa_read_codes(FsaReader *r, const unsigned char table[256], ByteBuf *codes);
+
+/* offset (in the decompressed stream) of the next byte to be read */
+long long fsa_tell(const FsaReader *r);
+/* 1 when the file is not compressed, i.e. fsa_seek is cheap */
+int fsa_is_plain(FsaReader *r);
+/* continue reading at `offset` of the (decompressed) stream; 0 on success */
+int fsa_seek(FsaReader *r, long long offset);
 
 /* next text line without its '\n' (0-terminated, len excludes the terminator); 0 at end of file */
 int fsa_read_line(FsaReader *r, ByteBuf *line);

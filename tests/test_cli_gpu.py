@@ -123,6 +123,39 @@ def test_config1_64_samples_5mbp_against_the_reference_binary(built, tmp_path):
         assert outs[tag][2] == outs["reference"][2], tag + ": stderr differs from the reference binary's"
 
 
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
+@pytest.mark.parametrize("flag", ["3", "1"], ids=["pair", "shared-mask"])
+def test_msa_parallel_and_gz_against_the_reference_binary(built, tmp_path, flag):
+    """MSA input (one multi-FASTA alignment): the plain file is parsed by -t threads seeking to their records,
+    the gz file sequentially; both must print what the reference binary prints (D block, then -- in pair mode --
+    the N block in the same stream, cdist.c:364-369), including an excluded all-N record."""
+    from ccphylo_b200 import synth
+    td = str(tmp_path)
+    n, length = 45, 30000 + 11
+    rows = synth.make_ascii(n, length, seed=9, snp=0.01, nrun=0.02)
+    if flag == "3":
+        rows[7, :] = ord("N")                      # excluded by the coverage gate (shared-mask parity needs no exclusions)
+    plain = os.path.join(td, "aln.fsa")
+    with open(plain, "wb") as f:
+        for i in range(n):
+            f.write(b">sample_%d some description\n" % i)
+            for s0 in range(0, length, 70):
+                f.write(rows[i, s0:s0 + 70].tobytes() + b"\n")
+    gz = plain + ".gz"
+    with open(plain, "rb") as f, gzip.open(gz, "wb") as g:
+        g.write(f.read())
+    ref = run([REF_BIN, "dist", "-i", plain, "-f", flag, "-o", os.path.join(td, "ref.phy"), "-n", os.path.join(td, "ref.num")], td)
+    assert ref.returncode == 0, ref.stderr
+    want = open(os.path.join(td, "ref.phy")).read()
+    assert len(want) > 1000
+    for tag, path, threads in (("plain-t7", plain, "7"), ("plain-t1", plain, "1"), ("gz-t7", gz, "7")):
+        p = run([BIN, "dist", "-i", path, "-f", flag, "-t", threads, "-o", os.path.join(td, tag + ".phy"), "-n",
+                 os.path.join(td, tag + ".num")], td)
+        assert p.returncode == 0, p.stderr
+        assert open(os.path.join(td, tag + ".phy")).read() == want, tag
+        assert p.stderr == ref.stderr, tag
+
+
 def test_fasta_gz_input_stdout_and_long_options(built, tmp_path):
     case = next(c for c in CASES if c["name"] == "c1_pair_W")
     td = str(tmp_path)
