@@ -28,6 +28,7 @@ EXPORTS = [
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
+    "ccg_set_proximity", "ccg_sample_proximity",
 ]
 
 MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "ln", "nl1", "nl2",
@@ -93,6 +94,8 @@ def load():
     L.ccg_put_samples_packed_dev.argtypes = [vp, i, i, vp, vp, C.c_long]
     L.ccg_put_sample_codes.argtypes = [vp, i, vp]
     L.ccg_get_inc_counts.argtypes = [vp, vp]
+    L.ccg_set_proximity.argtypes = [vp, u, i]
+    L.ccg_sample_proximity.argtypes = [vp, i, i, i, vp]
     L.ccg_run_pair.argtypes = [vp, vp, u, u, d, i, d, vp, vp, C.POINTER(i)]
     L.ccg_run_global.argtypes = [vp, vp, u, i, d, vp, C.POINTER(i), C.POINTER(u)]
     L.ccg_run_pair_dev.argtypes = [vp, vp, u, u, d, i, d, vp, vp, C.POINTER(i)]
@@ -204,6 +207,10 @@ class Context:
     def sync(self):
         self._ck(self._L.ccg_sync(self._h))
 
+    def set_proximity(self, proxi, snp_events_only=False):
+        """-P proxi; snp_events_only selects the event definition of -f 8 / -f 32 (dist.c:802-806)."""
+        self._ck(self._L.ccg_set_proximity(self._h, proxi, 1 if snp_events_only else 0))
+
     def set_problem(self, n, length, pair=True):
         self._ck(self._L.ccg_set_problem(self._h, n, length, 1 if pair else 0))
         self.n, self.len, self.pair = n, length, pair
@@ -241,6 +248,13 @@ class Context:
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         assert codes.size == self.len
         self._ck(self._L.ccg_put_sample_codes(self._h, idx, codes.ctypes.data))
+
+    def sample_proximity(self, first=0, count=None, apply=True):
+        """getIncPosPtr(includes[i], seq, seq, proxi) of cdist.c:91 on slots [first, first+count) -> their counts."""
+        count = self.n - first if count is None else count
+        out = np.zeros(max(count, 1), dtype=np.uint32)
+        self._ck(self._L.ccg_sample_proximity(self._h, first, count, 1 if apply else 0, out.ctypes.data))
+        return out[:count]
 
     def inc_counts(self):
         out = np.zeros(max(self.n, 1), dtype=np.uint32)

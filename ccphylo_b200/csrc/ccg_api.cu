@@ -181,6 +181,13 @@ extern "C" int ccg_set_kernel(ccg_ctx *ctx, int kernel) {
 	return CCG_OK;
 }
 
+extern "C" int ccg_set_proximity(ccg_ctx *ctx, unsigned proxi, int snp_events_only) {
+	if(!ctx) return CCG_ERR_ARG;
+	ctx->proxi = proxi;
+	ctx->proxi_snp_only = snp_events_only ? 1 : 0;
+	return CCG_OK;
+}
+
 extern "C" int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes) {
 	if(!ctx) return CCG_ERR_ARG;
 	if(ctx->x_budget != bytes && ctx->d_X) {
@@ -533,6 +540,33 @@ extern "C" int ccg_apply_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
 	return CCG_OK;
 }
 
+/* d_use <- present (and uploaded) slots with include[i] != 0; returns the first such slot in *first (-1 = none) */
+static int stage_use_flags(ccg_ctx *ctx, const unsigned char *include, int lo, int hi, unsigned char **d_use_out,
+                           unsigned **d_aux_out, size_t aux_words, int *first) {
+	unsigned char *h_use = (unsigned char *) calloc((size_t) ctx->n_pad, 1);
+	if(!h_use) return CCG_ERR_NOMEM;
+	*first = -1;
+	for(int i = lo; i < hi; ++i) {
+		h_use[i] = ctx->present[i] && ctx->have[i >> 7] && (!include || include[i]);
+		if(h_use[i] && *first < 0) *first = i;
+	}
+	const size_t use_bytes = ((size_t) ctx->n_pad + 15) & ~(size_t) 15;
+	int rc = ensure_stage(ctx, use_bytes + aux_words * sizeof(unsigned) + 64);
+	if(rc) { free(h_use); return rc; }
+	unsigned char *d_use = (unsigned char *) ctx->d_stage;
+	cudaError_t e = cudaMemcpyAsync(d_use, h_use, (size_t) ctx->n_pad, cudaMemcpyHostToDevice, ctx->stream);
+	if(e == cudaSuccess) e = cudaMemsetAsync(d_use + use_bytes, 0, aux_words * sizeof(unsigned), ctx->stream);
+	/* h_use is pageable: the copy has been staged by the time cudaMemcpyAsync returns */
+	free(h_use);
+	if(e != cudaSuccess) {
+		set_err(ctx, "staging the slot flags failed: %s", cudaGetErrorString(e));
+		return CCG_ERR_CUDA;
+	}
+	*d_use_out = d_use;
+	*d_aux_out = (unsigned *) (d_use + use_bytes);
+	return CCG_OK;
+}
+
 extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include, unsigned *global_inc) {
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode) return CCG_ERR_ARG;
 	if(ctx->world > 1) {
@@ -541,21 +575,24 @@ extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include,
 	}
 	CK(ctx, cudaSetDevice(ctx->device));
 	if(!ctx->d_gmask) CK(ctx, cudaMalloc(&ctx->d_gmask, (size_t) (ctx->words + 1) * sizeof(uint32_t)));
-	unsigned char *h_use = (unsigned char *) calloc((size_t) ctx->n_pad, 1);
-	if(!h_use) return CCG_ERR_NOMEM;
-	for(int i = 0; i < ctx->n; ++i) h_use[i] = ctx->present[i] && (!include || include[i]);
-	int rc = ensure_stage(ctx, (size_t) ctx->n_pad + 64);
-	if(rc) { free(h_use); return rc; }
-	unsigned char *d_use = (unsigned char *) ctx->d_stage;
-	unsigned *d_cnt = (unsigned *) (d_use + (((size_t) ctx->n_pad + 15) & ~(size_t) 15));
-	cudaError_t e = cudaMemcpyAsync(d_use, h_use, (size_t) ctx->n_pad, cudaMemcpyHostToDevice, ctx->stream);
-	if(e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned), ctx->stream);
-	if(e == cudaSuccess) e = cudaMemsetAsync(ctx->d_gmask, 0, (size_t) (ctx->words + 1) * sizeof(uint32_t), ctx->stream);
+	unsigned char *d_use = 0;
+	unsigned *d_cnt = 0;
+	int first = -1;
+	int rc = stage_use_flags(ctx, include, 0, ctx->n, &d_use, &d_cnt, 2, &first);
+	if(rc) return rc;
+	cudaError_t e = cudaMemsetAsync(ctx->d_gmask, 0, (size_t) (ctx->words + 1) * sizeof(uint32_t), ctx->stream);
 	if(e == cudaSuccess) e = ccg_launch_build_global_mask(ctx, d_use, d_cnt);
+	unsigned *d_final = d_cnt;
+	if(e == cudaSuccess && ctx->proxi && first >= 0) {
+		/* -P: every included sample also clears the runs between its close events against the first included
+		 * sample (getIncPosPtr(G, seq, ref, proxi), cdist.c:111; the first sample against itself, :138) */
+		e = ccg_launch_sample_proxi(ctx, 1, first, d_use, 0, 0);
+		if(e == cudaSuccess) e = ccg_launch_count_mask(ctx, d_cnt + 1);
+		d_final = d_cnt + 1;
+	}
 	unsigned inc = 0;
-	if(e == cudaSuccess) e = cudaMemcpyAsync(&inc, d_cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+	if(e == cudaSuccess) e = cudaMemcpyAsync(&inc, d_final, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
 	if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-	free(h_use);
 	if(e != cudaSuccess) {
 		set_err(ctx, "building the global mask failed: %s", cudaGetErrorString(e));
 		return CCG_ERR_CUDA;
@@ -564,6 +601,46 @@ extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include,
 	if(global_inc) *global_inc = inc;
 	CK(ctx, ccg_launch_apply_global_mask(ctx));
 	ctx->global_applied = 1;
+	return CCG_OK;
+}
+
+extern "C" int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int apply, unsigned *inc_out) {
+	if(!ctx || !ctx->d_planes || !ctx->pair_mode || first < 0 || count < 0 || first + count > ctx->n) return CCG_ERR_ARG;
+	if(count == 0) return CCG_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	unsigned *h = (unsigned *) malloc((size_t) count * 2 * sizeof(unsigned));
+	if(!h) return CCG_ERR_NOMEM;
+	unsigned *h_inc = h, *h_clr = h + count;
+	memset(h_clr, 0, (size_t) count * sizeof(unsigned));
+	cudaError_t e = cudaSuccess;
+	/* against itself a sample has no SNPs: only getIncPos (events = unknown positions) clears anything */
+	const int active = ctx->proxi && !ctx->proxi_snp_only && ctx->words > 0;
+	if(active) {
+		unsigned char *d_use = 0;
+		unsigned *d_clr = 0;
+		int first_used = -1;
+		int rc = stage_use_flags(ctx, 0, first, first + count, &d_use, &d_clr, (size_t) ctx->n_pad, &first_used);
+		if(rc) { free(h); return rc; }
+		e = ccg_launch_sample_proxi(ctx, 0, 0, d_use, apply ? 1 : 0, d_clr);
+		if(e == cudaSuccess)
+			e = cudaMemcpyAsync(h_clr, d_clr + first, (size_t) count * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+	}
+	if(e == cudaSuccess)
+		e = cudaMemcpyAsync(h_inc, ctx->d_inc + first, (size_t) count * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+	if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if(e == cudaSuccess) {
+		for(int i = 0; i < count; ++i) h_inc[i] -= h_clr[i];
+		if(inc_out) memcpy(inc_out, h_inc, (size_t) count * sizeof(unsigned));
+		if(apply && active) {
+			e = cudaMemcpyAsync(ctx->d_inc + first, h_inc, (size_t) count * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream);
+			if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		}
+	}
+	free(h);
+	if(e != cudaSuccess) {
+		set_err(ctx, "per-sample proximity masking failed: %s", cudaGetErrorString(e));
+		return CCG_ERR_CUDA;
+	}
 	return CCG_OK;
 }
 
@@ -682,8 +759,8 @@ static int ensure_tiles(ccg_ctx *ctx, const int2 *host, size_t count) {
 	return CCG_OK;
 }
 
-static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
-	/* 64x64 tiles of the macro tiles this rank owns */
+/* the 64x64 tiles of the macro tiles this rank owns -> ctx->d_tiles; *cnt_out = how many */
+static int upload_tiles64(ccg_ctx *ctx, size_t *cnt_out) {
 	const int n = ctx->n;
 	size_t cap = 0;
 	for_each_ctx_tile(ctx, [&](int, int) { cap += (CCG_UMMA_BM / CCG_TILE) * (CCG_UMMA_BN / CCG_TILE); });
@@ -702,10 +779,54 @@ static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
 	});
 	ctx->last_ntiles = (int) cnt;
 	ctx->last_kernel_kind = CCG_KERNEL_POPC;
+	*cnt_out = cnt;
 	if(cnt == 0) { free(host); return CCG_OK; }
 	int rc = ensure_tiles(ctx, host, cnt);
 	free(host);
+	return rc;
+}
+
+static int ensure_acc(ccg_ctx *ctx, size_t acc_bytes) {
+	if(ctx->acc_bytes >= acc_bytes) return CCG_OK;
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_acc);
+	ctx->d_acc = 0;
+	ctx->acc_bytes = 0;
+	if(cudaMalloc(&ctx->d_acc, acc_bytes) != cudaSuccess) {
+		set_err(ctx, "cudaMalloc of %zu accumulator bytes failed", acc_bytes);
+		return CCG_ERR_NOMEM;
+	}
+	ctx->acc_bytes = acc_bytes;
+	return CCG_OK;
+}
+
+/* pair mode with -P: k_pairdist_proxi (the masking is sequential along the alignment: no K split, no tensor path) */
+static int run_proxi(ccg_ctx *ctx, const EpilogueParams &ep) {
+	size_t cnt = 0;
+	int rc = upload_tiles64(ctx, &cnt);
+	if(rc || cnt == 0) return rc;
+	rc = ensure_acc(ctx, cnt * 2 * CCG_TILE * CCG_TILE * sizeof(uint32_t));
 	if(rc) return rc;
+	ProxiParams p;
+	memset(&p, 0, sizeof(p));
+	p.ntiles = (int) cnt;
+	p.tiles = ctx->d_tiles;
+	p.acc = ctx->d_acc;
+	p.ep = ep;
+	/* cells the kernel skips (i <= j, excluded samples) must not hold stale counts for ccg_get_raw_counts */
+	CK(ctx, cudaMemsetAsync(ctx->d_acc, 0, cnt * 2 * CCG_TILE * CCG_TILE * sizeof(uint32_t), ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	CK(ctx, ccg_launch_pair_proxi(ctx, p));
+	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	ctx->ev_valid = 1;
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_proxi tiles=%d proxi=%u", p.ntiles, ctx->proxi);
+	return CCG_OK;
+}
+
+static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
+	size_t cnt = 0;
+	int rc = upload_tiles64(ctx, &cnt);
+	if(rc || cnt == 0) return rc;
 
 	PopcParams p;
 	memset(&p, 0, sizeof(p));
@@ -719,17 +840,8 @@ static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
 	while(p.ksplit > 1 && (long long) (p.ksplit - 1) * p.chunks_per_split >= ctx->chunks) --p.ksplit;
 
 	size_t acc_bytes = cnt * 2 * CCG_TILE * CCG_TILE * sizeof(uint32_t);
-	if(ctx->acc_bytes < acc_bytes) {
-		CK(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(ctx->d_acc);
-		ctx->d_acc = 0;
-		ctx->acc_bytes = 0;
-		if(cudaMalloc(&ctx->d_acc, acc_bytes) != cudaSuccess) {
-			set_err(ctx, "cudaMalloc of %zu accumulator bytes failed", acc_bytes);
-			return CCG_ERR_NOMEM;
-		}
-		ctx->acc_bytes = acc_bytes;
-	}
+	rc = ensure_acc(ctx, acc_bytes);
+	if(rc) return rc;
 	if(ctx->tickets_count < cnt) {
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
 		cudaFree(ctx->d_tickets);
@@ -1147,6 +1259,13 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	/* AUTO: the tensor-core kernel wins once there is enough work to fill the machine */
 	/* measured on B200 (profiles/): the tensor kernel runs the contraction ~5x faster than the
 	 * XU-pipe-bound POPC kernel but pays a fixed operand-expansion pass; small problems stay on POPC */
+	if(mode == 0 && ctx->proxi) {
+		if(ctx->feed_seqs) {
+			set_err(ctx, "internal: host rows cannot be streamed into a run with proximity masking");
+			return CCG_ERR_ARG;
+		}
+		return run_proxi(ctx, ep);
+	}
 	int kind = ctx->kernel_choice;
 	if(kind == CCG_KERNEL_AUTO)
 		kind = (Dn >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
@@ -1248,10 +1367,6 @@ extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, 
                                       int len, const uint64_t *const *seqs, const unsigned char *include,
                                       const uint32_t *const *includes, unsigned norm, unsigned minLength, double minCov,
                                       unsigned proxi, int *Dn, unsigned *global_inc) {
-	if(proxi) {
-		set_err(ctx, "proximity masking (-P %u) is not implemented on the GPU path", proxi);
-		return CCG_ERR_UNSUPPORTED;
-	}
 	if(!seqs || !includes || n < 0) return CCG_ERR_ARG;
 	ccg_ctx *own = 0;
 	int rc;
@@ -1260,6 +1375,10 @@ extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, 
 		if(rc) return rc;
 		ctx = own;
 	}
+	/* -P: the caller's per-sample masks already carry getIncPos' proximity masking (cdist.c:91); what is left
+	 * for the fan-out is maskProxi per pair (fsacmpthrd.c:410).  cmpFsaThrd never looks at proxi. */
+	const unsigned saved_proxi = ctx->proxi;
+	ctx->proxi = pair ? proxi : 0;
 	rc = ccg_set_problem(ctx, n, len, pair);
 	if(!rc && !pair) rc = ccg_put_global_mask(ctx, includes[0]);
 	const uint64_t **srow = 0;
@@ -1283,7 +1402,7 @@ extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, 
 		 * the PCIe upload of slab s+1 hides behind the GEMM of slab s (run_umma / feed_slab) */
 		int kind = ctx->kernel_choice;
 		if(kind == CCG_KERNEL_AUTO) kind = (ninc >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
-		if(kind == CCG_KERNEL_UMMA && ctx->stream_min_chunks > 0 && ctx->chunks >= ctx->stream_min_chunks) {
+		if(kind == CCG_KERNEL_UMMA && !ctx->proxi && ctx->stream_min_chunks > 0 && ctx->chunks >= ctx->stream_min_chunks) {
 			for(int i = 0; i < n; ++i) {
 				if(!srow[i]) continue;
 				ctx->present[i] = 1;
@@ -1312,6 +1431,7 @@ extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, 
 	}
 	free(srow);
 	free(mrow);
+	ctx->proxi = saved_proxi;
 	if(own) {
 		if(rc) snprintf(g_init_err, sizeof(g_init_err), "%s", own->err);
 		ccg_destroy(own);

@@ -61,6 +61,13 @@ struct PopcParams {
 	EpilogueParams ep;
 };
 
+struct ProxiParams {
+	int ntiles;            /* 64x64 tiles owned by this rank */
+	const int2 *tiles;     /* device: (ti, tj) */
+	uint32_t *acc;         /* [ntiles][2][TILE*TILE] mismatches / included under the proximity mask */
+	EpilogueParams ep;
+};
+
 struct UmmaParams {
 	int ntiles;            /* macro tiles owned by this rank */
 	const int2 *tiles;     /* device: (tm, tn) */
@@ -90,6 +97,9 @@ struct ccg_ctx {
 	int min_slabs;                  /* cut the K axis into at least this many slabs (expansion overlapped with the GEMM) */
 	int use_i8;                     /* CCG_I8=1: int8 operands (kind::i8) instead of the default e2m1 panel (kind::mxf4) */
 	int dbg_kslices, dbg_serial, dbg_nolock, dbg_umma1;   /* CCG_KSLICES / CCG_EXPAND_SERIAL / CCG_NOLOCK / CCG_UMMA1 overrides (experiments only) */
+
+	unsigned proxi;                 /* -P: minimum distance between SNPs (0 = no proximity masking), ccg_set_proximity */
+	int proxi_snp_only;             /* events of the per-sample builder: 0 getIncPos, 1 getIncPosInsig / getIncPosInsigPrune */
 
 	int n, len, pair_mode;
 	int words, chunks, n_pad, nplanes;
@@ -199,6 +209,12 @@ cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
 int ccg_umma_pair_slots(ccg_ctx *ctx);
 cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);
 cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc);
+
+/* k_proxi.cu */
+cudaError_t ccg_launch_sample_proxi(ccg_ctx *ctx, int vs_ref, int ref_slot, const unsigned char *d_use, int apply,
+                                    unsigned *d_cleared);
+cudaError_t ccg_launch_count_mask(ccg_ctx *ctx, unsigned *d_count);
+cudaError_t ccg_launch_pair_proxi(ccg_ctx *ctx, const ProxiParams &p);
 
 /* k_matdist.cu */
 void ccg_mat_free(ccg_ctx *ctx);

@@ -10,7 +10,10 @@
  *     builds the inclusion mask and counts it -- the host keeps O(threads) sequences, not n;
  *   - the O(n^2 L) comparison and the epilogue run on the GPU (ccg_run_pair / ccg_run_global);
  *     there is no CPU fallback: without a usable device the program stops with an error;
- *   - -P (proximity), -V (variant listing), -y (motif masking), -a (row append) are refused.
+ *   - -P (proximity) runs on the device too: the per-sample builder right after the upload
+ *     (ccg_sample_proximity), the per-pair maskProxi inside the compare (ccg_run_pair), the
+ *     shared-mask variant in ccg_build_global_mask;
+ *   - -V (variant listing), -y (motif masking), -a (row append) are refused.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -126,6 +129,28 @@ static void parse_one(int job, void *state, void *user) {
 	fsa_close(fr);
 }
 
+/* The count the inclusion test of cdist.c:91-100 / :138-147 looks at, for a candidate whose codes are in r.
+ * Without -P it is the number of known bases, which the parser thread has counted.  With -P and the event
+ * definition of getIncPos (fsacmp.c:181: not -f 8 / -f 32) the bases between two unknown positions at most
+ * proxi apart go as well; the device applies (pair mode) or just counts (the shared-mask reference candidate,
+ * whose ranges ccg_build_global_mask clears later) that on the freshly uploaded sample.
+ * *uploaded tells the caller that slot already holds the sample. */
+static unsigned candidate_count(const DistOpts *o, ccg_ctx *ctx, int slot, const ByteBuf *codes, unsigned known, int len,
+                                int pair, int is_ref_candidate, int *uploaded) {
+	*uploaded = 0;
+	if(!o->proxi || (o->flag & (8 | 32)) || len <= 0) return known;
+	if(!pair && !is_ref_candidate) return known;       /* cdist.c:102: len - unknowns */
+	int rc = ccg_put_sample_codes(ctx, slot, codes->data);
+	if(rc) die_gpu(ctx, rc);
+	rc = ccg_sync(ctx);
+	if(rc) die_gpu(ctx, rc);
+	unsigned inc = 0;
+	rc = ccg_sample_proximity(ctx, slot, 1, pair, &inc);
+	if(rc) die_gpu(ctx, rc);
+	*uploaded = 1;
+	return inc;
+}
+
 /* shared tail of the two FASTA modes: compare on the device and print (cdist.c:170-192, dist.c:174-180) */
 static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, unsigned minLength, unsigned char *include,
                              int included, char **names, const char *comment, FILE *outfile, FILE *noutfile, int n_into_out) {
@@ -189,6 +214,9 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	memset(include, 1, (size_t) n);
 	unsigned minLength = o->minLength;
 	int len = 0, have_ref = 0, included = n;
+	const int pair = (o->flag & 2) != 0;
+	rc = ccg_set_proximity(ctx, o->proxi, (o->flag & (8 | 32)) != 0);
+	if(rc) die_gpu(ctx, rc);
 
 	for(int i = 0; i < n; ++i) {
 		Parsed *r = (Parsed *) pool_take(pool, i);
@@ -225,20 +253,20 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 					/* until a sample passes, every candidate redefines the alignment length (cdist.c:113-147) */
 					len = (int) r->codes.len;
 					if(minLength < o->minCov * len) minLength = (unsigned) (o->minCov * len);
+					/* a pair-mode store serves both modes: the shared mask is ANDed in afterwards */
+					rc = ccg_set_problem(ctx, n, len, 1);
+					if(rc) die_gpu(ctx, rc);
 				}
-				if(r->known < minLength) {
-					fprintf(stderr, "# Excluded:\t%s\t( %d / %d )\n", path, (int) r->known, len);
+				int uploaded = 0;
+				const unsigned inc = candidate_count(o, ctx, i, &r->codes, r->known, len, pair, !have_ref, &uploaded);
+				if(inc < minLength) {
+					fprintf(stderr, "# Excluded:\t%s\t( %d / %d )\n", path, (int) inc, len);
 					include[i] = 0;
 					--included;
 				} else {
-					fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", path, (int) r->known, len);
-					if(!have_ref) {
-						have_ref = 1;
-						/* a pair-mode store serves both modes: the shared mask is ANDed in afterwards */
-						rc = ccg_set_problem(ctx, n, len, 1);
-						if(rc) die_gpu(ctx, rc);
-					}
-					if(len > 0) {
+					fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", path, (int) inc, len);
+					have_ref = 1;
+					if(len > 0 && !uploaded) {
 						rc = ccg_put_sample_codes(ctx, i, r->codes.data);
 						if(rc) die_gpu(ctx, rc);
 						/* the staging copy is asynchronous and the ring slot is about to be reused */
@@ -358,6 +386,8 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	ccg_ctx *ctx = 0;
 	int rc = ccg_init(&ctx, -1);
 	if(rc) die_gpu(0, rc);
+	rc = ccg_set_proximity(ctx, o->proxi, (o->flag & (8 | 32)) != 0);
+	if(rc) die_gpu(ctx, rc);
 	char **names = calloc((size_t) (nrec ? nrec : 1), sizeof(char *));
 	if(!names) die_errno();
 	unsigned minLength = o->minLength;
@@ -388,31 +418,28 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 			continue;
 		}
 		const char *name = (const char *) r->header.data;
-		const unsigned known = r->known;
-		int keep;
 		if(have_ref) {
 			if((int) r->codes.len != len) {
 				fprintf(stderr, "Sequences does not match: >%s\n", name);
 				exit(1);
 			}
-			/* shared-mask mode keeps a later record only if it EXCEEDS the threshold (cdist.c:270) */
-			keep = pair ? !(known < minLength) : (minLength < known);
 		} else {
 			len = (int) r->codes.len;
 			if(minLength < o->minCov * len) minLength = (unsigned) (o->minCov * len);
-			keep = !(known < minLength);
+			rc = ccg_set_problem(ctx, nrec, len, 1);
+			if(rc) die_gpu(ctx, rc);
 		}
+		int uploaded = 0;
+		const unsigned known = candidate_count(o, ctx, n, &r->codes, r->known, len, pair, !have_ref, &uploaded);
+		/* shared-mask mode keeps a later record only if it EXCEEDS the threshold (cdist.c:270) */
+		const int keep = (have_ref && !pair) ? (minLength < known) : !(known < minLength);
 		if(!keep) fprintf(stderr, "# Excluded:\t%s\t( %d / %d )\n", name, (int) known, len);
 		else {
 			fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", name, (int) known, len);
-			if(!have_ref) {
-				have_ref = 1;
-				rc = ccg_set_problem(ctx, nrec, len, 1);
-				if(rc) die_gpu(ctx, rc);
-			}
+			have_ref = 1;
 			names[n] = strdup(name);
 			if(!names[n]) die_errno();
-			if(len > 0) {
+			if(len > 0 && !uploaded) {
 				rc = ccg_put_sample_codes(ctx, n, r->codes.data);
 				if(rc) die_gpu(ctx, rc);
 				rc = ccg_sync(ctx);
@@ -505,7 +532,7 @@ static int help_message(FILE *out) {
 		{'C', "min_cov", "Minimum coverage", "50.0%"},
 		{'L', "min_len", "Minimum overlapping length", "1"},
 		{'W', "normalization_weight", "Normalization weight", "0 / None"},
-		{'P', "proximity", "Minimum proximity between SNPs (only 0 on the GPU path)", "0"},
+		{'P', "proximity", "Minimum proximity between SNPs", "0"},
 		{'f', "flag", "Output flags", "1"},
 		{'F', "flag_help", "Help on option \"-f\"", ""},
 		{'d', "distance", "Distance method", "cos"},
@@ -628,10 +655,9 @@ int main_dist(int argc, char **argv) {
 	if(dist_mat_parse_method(&o)) die_invalid(o.method_err);
 	if(!o.numFile && o.targetTemplate) o.numFile = 1;
 
-	if(o.addfilename || o.diffilename || o.methfilename || o.proxi) {
+	if(o.addfilename || o.diffilename || o.methfilename) {
 		fprintf(stderr, "%s is not available on the GPU path of dist (use the CPU ccphylo for it).\n",
-		        o.addfilename ? "-a / --add" : o.diffilename ? "-V / --nucleotide_variations" :
-		        o.methfilename ? "-y / --methylation_motifs" : "-P / --proximity");
+		        o.addfilename ? "-a / --add" : o.diffilename ? "-V / --nucleotide_variations" : "-y / --methylation_motifs");
 		return 1;
 	}
 	make_matrix(&o);

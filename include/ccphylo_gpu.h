@@ -46,7 +46,7 @@ enum {
 	CCG_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed: see ccg_last_error */
 	CCG_ERR_ARG = 3,         /* invalid argument or call order */
 	CCG_ERR_NOMEM = 4,       /* host or device allocation failed */
-	CCG_ERR_UNSUPPORTED = 5  /* e.g. proxi > 0 (-P), handled on the host in the reference */
+	CCG_ERR_UNSUPPORTED = 5  /* an option combination the device path does not take (e.g. the device-built global mask on a rank partition) */
 };
 
 /* kernel selection for ccg_set_kernel */
@@ -141,6 +141,24 @@ int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count,
  * (fsacmp.c:164,181) and getNpos (:487).  Pair mode only. */
 int ccg_put_sample_codes(ccg_ctx *ctx, int idx, const unsigned char *codes);
 
+/* -P proxi (dist.c:712, "minimum proximity between SNPs"): set before the samples are put.
+ * snp_events_only != 0 selects the event definition of getIncPosInsig / getIncPosInsigPrune
+ * (-f 8 / -f 32, dist.c:802-806: only positions where both sequences are known and differ),
+ * 0 that of getIncPos (fsacmp.c:181: differing or unknown positions).  With proxi > 0
+ *   - ccg_run_pair[_dev] performs maskProxi per pair (fsacmp.c:355-485, fsacmpthrd.c:410)
+ *     before counting, bug-compatible with the reference;
+ *   - ccg_build_global_mask additionally clears, for every included sample, the runs
+ *     between close events against the first included sample (cdist.c:111,138);
+ *   - ccg_sample_proximity applies the per-sample builder (cdist.c:91).
+ * proxi = 0 (the default) switches all of it off. */
+int ccg_set_proximity(ccg_ctx *ctx, unsigned proxi, int snp_events_only);
+
+/* Pair-mode store: getIncPosPtr(includes[i], seq, seq, proxi) (cdist.c:91,138) for the
+ * uploaded slots [first, first+count): positions between two unknown positions at most
+ * proxi apart are removed from the sample's own mask.  apply == 0 only counts.
+ * inc_out[k] (may be NULL) receives getNpos of slot first+k's mask after the masking. */
+int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int apply, unsigned *inc_out);
+
 /* Per-slot included-position counts (getNpos of each sample's own mask,
  * fsacmp.c:487; cdist.c:91).  out has n entries. */
 int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out);
@@ -181,8 +199,9 @@ int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc);
 
 /* One-call drop-in with the argument list of fsaCmpThreadOut
  * (fsacmpthrd.h:49): pair != 0 selects cmpairFsaThrd, else cmpFsaThrd.
- * Host row pointers in, host matrices out.  proxi must be 0
- * (CCG_ERR_UNSUPPORTED otherwise).  ctx may be NULL (a temporary context on
+ * Host row pointers in, host matrices out.  proxi > 0: the
+ * caller's masks already went through getIncPos (cdist.c:91), the call performs
+ * maskProxi per pair (pair mode; cmpFsaThrd ignores proxi).  ctx may be NULL (a temporary context on
  * the current device is used). */
 int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N,
                            int elem_size, double byteScale, int n, int len,

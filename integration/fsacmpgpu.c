@@ -22,7 +22,7 @@ void fsaCmpGpuOut(int tnum, void *(*func)(void *), Matrix *D, Matrix *N, int n, 
 	void *Dcells = cells(D, &elem);
 	void *Ncells = (pair && N) ? cells(N, &elem) : 0;
 
-	if(diffile || proxi) {          /* -V / -P stay on the reference's own CPU code */
+	if(diffile) {                   /* -V (per-pair variant listing) stays on the reference's own CPU code */
 		fsaCmpThreadOut(tnum, func, D, N, n, len, seqs, include, includes, norm, minLength,
 		                minCov, diffile, targetTemplate, ref, filenames, proxi);
 		return;

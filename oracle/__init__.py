@@ -52,6 +52,14 @@ def lib():
         L.orc_known_mask.argtypes = [_u8p, C.c_int, _u32p]
         L.orc_and_known.restype = None
         L.orc_and_known.argtypes = [_u32p, _u8p, _u8p, C.c_int]
+        L.orc_inc_pos.restype = None
+        L.orc_inc_pos.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint, C.c_int]
+        L.orc_pair_counts_proxi.restype = None
+        L.orc_pair_counts_proxi.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint, C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_uint32)]
+        L.orc_fsa_cmp_pair_proxi.restype = C.c_int
+        L.orc_fsa_cmp_pair_proxi.argtypes = [C.c_int, C.c_int, _u64p, C.c_long, _u8p, _u32p, C.c_uint, C.c_uint,
+                                             C.c_double, C.c_uint, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_mask_count.restype = C.c_int
         L.orc_mask_count.argtypes = [_u32p, C.c_int]
         L.orc_raw_pair_matrix.restype = None
@@ -136,8 +144,32 @@ def known_mask(codes):
     return mask[:W], inc
 
 
-def encode_samples(codes2d):
-    """codes2d: (n, L) u8 codes -> (seqs (n,W) u64, masks (n,W) u32, inc (n,) i32)."""
+def variant_of(flag):
+    """-f bits 32 / 8 select getIncPosInsigPrune / getIncPosInsig (dist.c:802-806): events are SNPs only."""
+    return 1 if flag & (32 | 8) else 0
+
+
+def inc_pos(mask, seq_codes, ref_codes, proxi=0, variant=0):
+    """getIncPosPtr(mask, seq, ref, proxi) on an existing mask (in place)."""
+    seq_codes = np.ascontiguousarray(seq_codes, dtype=np.uint8)
+    ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint8)
+    if len(seq_codes):
+        lib().orc_inc_pos(mask, seq_codes, ref_codes, len(seq_codes), proxi, variant)
+    return mask
+
+
+def full_mask(length):
+    """initIncPos (fsacmp.c:164)."""
+    W = words(length)
+    m = np.full(max(W, 1), 0xFFFFFFFF, dtype=np.uint32)
+    if length & 31:
+        m[W - 1] = (0xFFFFFFFF << (32 - (length & 31))) & 0xFFFFFFFF
+    return m[:W]
+
+
+def encode_samples(codes2d, proxi=0, variant=0):
+    """codes2d: (n, L) u8 codes -> (seqs (n,W) u64, masks (n,W) u32, inc (n,) i32); pair mode
+    (cdist.c:88-92: initIncPos, qseq2nibble, getIncPosPtr(seq, seq, proxi), getNpos)."""
     n, L = codes2d.shape
     W = words(L)
     seqs = np.zeros((n, W), dtype=np.uint64)
@@ -145,20 +177,39 @@ def encode_samples(codes2d):
     inc = np.zeros(n, dtype=np.int32)
     for i in range(n):
         seqs[i], _ = pack(codes2d[i])
-        masks[i], inc[i] = known_mask(codes2d[i])
+        if proxi:
+            m = full_mask(L).copy()
+            inc_pos(m, codes2d[i], codes2d[i], proxi, variant)
+            masks[i] = m
+            inc[i] = lib().orc_mask_count(m, L) if W else 0
+        else:
+            masks[i], inc[i] = known_mask(codes2d[i])
     return seqs, masks, inc
 
 
-def global_mask(codes2d, include):
+def global_mask(codes2d, include, proxi=0, variant=0):
     """cdist.c:86-112 accumulation: first included sample is `ref`."""
     n, L = codes2d.shape
     inc_idx = [i for i in range(n) if include[i]]
     ref = np.ascontiguousarray(codes2d[inc_idx[0]])
+    if proxi:
+        mask = full_mask(L).copy()
+        inc_pos(mask, ref, ref, proxi, variant)
+        for i in inc_idx[1:]:
+            inc_pos(mask, codes2d[i], ref, proxi, variant)
+        return mask
     mask, _ = known_mask(ref)
     mask = mask.copy()
     for i in inc_idx[1:]:
         lib().orc_and_known(mask, np.ascontiguousarray(codes2d[i]), ref, L)
     return mask
+
+
+def pair_counts_proxi(seq_i, seq_j, inc_i, inc_j, length, proxi):
+    m, n = C.c_uint32(0), C.c_uint32(0)
+    lib().orc_pair_counts_proxi(np.ascontiguousarray(seq_i), np.ascontiguousarray(seq_j), np.ascontiguousarray(inc_i),
+                                np.ascontiguousarray(inc_j), length, proxi, C.byref(m), C.byref(n))
+    return m.value, n.value
 
 
 def raw_pair_matrix(seqs, masks, length, nthreads=8):
@@ -170,15 +221,15 @@ def raw_pair_matrix(seqs, masks, length, nthreads=8):
 
 
 def fsa_cmp_pair(seqs, masks, include, length, norm=0, min_length=1, min_cov=0.5, elem_size=8, byte_scale=1.0,
-                 want_n=True):
+                 want_n=True, proxi=0):
     n, W = seqs.shape
     include = np.ascontiguousarray(include, dtype=np.uint8)
     dt = ELEM_DTYPE[elem_size]
     D = np.zeros(max(cells(n), 1), dtype=dt)
     N = np.zeros(max(cells(n), 1), dtype=dt)
-    dn = lib().orc_fsa_cmp_pair(n, length, np.ascontiguousarray(seqs), W, include, np.ascontiguousarray(masks),
-                                norm, min_length, min_cov, elem_size, byte_scale, D.ctypes.data,
-                                N.ctypes.data if want_n else None)
+    dn = lib().orc_fsa_cmp_pair_proxi(n, length, np.ascontiguousarray(seqs), W, include, np.ascontiguousarray(masks),
+                                      norm, min_length, min_cov, proxi, elem_size, byte_scale, D.ctypes.data,
+                                      N.ctypes.data if want_n else None)
     return D[:cells(dn)], (N[:cells(dn)] if want_n else None), dn
 
 
@@ -212,6 +263,8 @@ def ref():
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
         R.refshim_and_known.restype = None
         R.refshim_and_known.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint]
+        R.refshim_inc_pos.restype = None
+        R.refshim_inc_pos.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint, C.c_uint]
         R.refshim_pair.restype = C.c_uint64
         R.refshim_pair.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint]
         R.refshim_fsa_cmp.restype = C.c_int
@@ -233,6 +286,27 @@ def ref_encode(data: bytes, flag=1, proxi=0):
     L = ref().refshim_encode(buf if nb else np.zeros(1, np.uint8), nb, flag, proxi, codes, seq, mask,
                              C.byref(unk), C.byref(inc))
     return codes[:L].copy(), seq[:words(L)].copy(), mask[:words(L)].copy(), unk.value, inc.value
+
+
+def ref_inc_pos(mask, seq_codes, ref_codes, proxi=0, flag=1):
+    """the reference's getIncPos / getIncPosInsig / getIncPosInsigPrune (by -f flag) on `mask`, in place"""
+    seq_codes = np.ascontiguousarray(seq_codes, dtype=np.uint8).copy()
+    ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint8).copy()
+    ref().refshim_inc_pos(mask, seq_codes, ref_codes, len(seq_codes), proxi, flag)
+    return mask
+
+
+def ref_pair(seq_i, seq_j, inc_i, inc_j, length, proxi=0):
+    """maskProxi + fsacmpair of the reference -> (mismatches, included)"""
+    W = words(length)
+
+    def pad(a, dt):
+        b = np.zeros(W + 2, dtype=dt)
+        b[:W] = a
+        return b
+    r = ref().refshim_pair(pad(seq_i, np.uint64), pad(seq_j, np.uint64), pad(inc_i, np.uint32), pad(inc_j, np.uint32),
+                           length, proxi)
+    return int(r >> 32), int(r & 0xFFFFFFFF)
 
 
 def ref_fsa_cmp(seqs, masks, include, length, pair=True, tnum=1, norm=0, min_length=1, min_cov=0.5, proxi=0,

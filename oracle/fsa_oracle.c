@@ -145,6 +145,79 @@ uint32_t orc_masked_mism(const uint64_t *seq_i, const uint64_t *seq_j,
 }
 
 /* ------------------------------------------------------------------ */
+/* -P proximity masking                                                */
+/* ------------------------------------------------------------------ */
+static inline void clear_range(uint32_t *mask, long lo, long hi, int len) {
+	long p;
+	if(lo < 0) lo = 0;
+	if(hi >= len) hi = (long) len - 1;   /* positions >= len do not exist (the reference's stores there are out of bounds) */
+	for(p = lo; p <= hi; ++p) mask[p >> 5] &= ~(1u << (31 - (p & 31)));
+}
+
+/* (reference fsacmp.c:181-238 getIncPos, :240-295 getIncPosInsigPrune, :297-353 getIncPosInsig,
+ * selected by -f 32 / -f 8 at dist.c:802-806)
+ * Positions where seq or ref is unknown are cleared.  An "event" is, for getIncPos (variant 0), every
+ * position with seq != ref or seq unknown; for the other two (variant 1) every position where both are
+ * known and differ.  When an event lies at most proxi after the previous event, everything from the
+ * previous event to this one (both inclusive) is cleared; the first event never clears anything (the
+ * reference's range loop compares int -1 as unsigned). */
+void orc_inc_pos(uint32_t *mask, const unsigned char *seq_codes, const unsigned char *ref_codes, int len,
+                 unsigned proxi, int variant) {
+	long p, last = -1;
+
+	for(p = 0; p < len; ++p) {
+		const unsigned c = seq_codes[p], r = ref_codes[p];
+		const int unknown = c == 4 || r == 4;
+		const int event = variant == 0 ? (c != r || c == 4) : (!unknown && c != r);
+		if(unknown) mask[p >> 5] &= ~(1u << (31 - (p & 31)));
+		if(event) {
+			if(last >= 0 && (unsigned long) (p - last) <= proxi) clear_range(mask, last, p, len);
+			last = p;
+		}
+	}
+}
+
+/* (reference fsacmp.c:355-485 maskProxi with proxi > 0, then :587-633 fsacmpair)
+ * inc = inc_i & inc_j; the SNPs of the pair are the included positions whose 2-bit codes differ.  The
+ * reference walks them from the last to the first with a position counter that is one too high, so for
+ * two neighbouring SNPs p < q with q - p <= proxi it clears p+1 .. q+1: q and everything between go, p
+ * stays.  Counts are then taken under the cleared mask. */
+void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j, const uint32_t *inc_i,
+                           const uint32_t *inc_j, int len, unsigned proxi, uint32_t *mism, uint32_t *ninc) {
+	int w, W = orc_words(len);
+	uint32_t *m, d = 0, n = 0;
+	long *snp, ns = 0, k;
+
+	if(!proxi) {
+		orc_pair_counts(seq_i, seq_j, inc_i, inc_j, len, mism, ninc);
+		return;
+	}
+	m = malloc((size_t) (W ? W : 1) * sizeof(uint32_t));
+	snp = malloc((size_t) (len ? len : 1) * sizeof(long));
+	for(w = 0; w < W; ++w) {
+		int b;
+		m[w] = inc_i[w] & inc_j[w];
+		for(b = 0; b < 32; ++b) {
+			if((m[w] >> (31 - b)) & 1) {
+				const unsigned ci = (unsigned) (seq_i[w] >> (62 - 2 * b)) & 3, cj = (unsigned) (seq_j[w] >> (62 - 2 * b)) & 3;
+				if(ci != cj) snp[ns++] = (long) w * 32 + b;
+			}
+		}
+	}
+	for(k = 0; k + 1 < ns; ++k) {
+		if((unsigned long) (snp[k + 1] - snp[k]) <= proxi) clear_range(m, snp[k] + 1, snp[k + 1] + 1, len);
+	}
+	for(w = 0; w < W; ++w) {
+		n += (uint32_t) __builtin_popcount(m[w]);
+		d += lane_mism(seq_i[w], seq_j[w], m[w]);
+	}
+	free(m);
+	free(snp);
+	*mism = d;
+	*ninc = n;
+}
+
+/* ------------------------------------------------------------------ */
 /* raw all-vs-all integer matrices (test helper, threaded over rows)   */
 /* ------------------------------------------------------------------ */
 typedef struct {
@@ -255,6 +328,15 @@ int orc_fsa_cmp_pair(int n, int len, const uint64_t *seqs, long wstride,
                      const unsigned char *include, const uint32_t *masks,
                      unsigned norm, unsigned minLength, double minCov,
                      int elem_size, double byteScale, void *D, void *N) {
+	return orc_fsa_cmp_pair_proxi(n, len, seqs, wstride, include, masks, norm, minLength, minCov, 0, elem_size,
+	                              byteScale, D, N);
+}
+
+/* the same with -P proxi (fsacmpthrd.c:409-410) */
+int orc_fsa_cmp_pair_proxi(int n, int len, const uint64_t *seqs, long wstride,
+                           const unsigned char *include, const uint32_t *masks,
+                           unsigned norm, unsigned minLength, double minCov, unsigned proxi,
+                           int elem_size, double byteScale, void *D, void *N) {
 	int *idx = malloc((size_t) (n > 0 ? n : 1) * sizeof(int));
 	int Dn = compact_included(n, include, idx), r, c;
 	size_t cell = 0;
@@ -266,8 +348,8 @@ int orc_fsa_cmp_pair(int n, int len, const uint64_t *seqs, long wstride,
 		for(c = 0; c < r; ++c, ++cell) {
 			uint32_t mism, inc;
 			int i = idx[r], j = idx[c];
-			orc_pair_counts(seqs + i * wstride, seqs + j * wstride,
-			                masks + i * wstride, masks + j * wstride, len, &mism, &inc);
+			orc_pair_counts_proxi(seqs + i * wstride, seqs + j * wstride,
+			                      masks + i * wstride, masks + j * wstride, len, proxi, &mism, &inc);
 			orc_pair_cell(mism, inc, norm, minLength, elem_size, byteScale,
 			              (char *) D + cell * elem_size,
 			              N ? (char *) N + cell * elem_size : 0);

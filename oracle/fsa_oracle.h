@@ -56,6 +56,17 @@ void orc_pair_counts(const uint64_t *seq_i, const uint64_t *seq_j,
                      const uint32_t *inc_i, const uint32_t *inc_j, int len,
                      uint32_t *mism, uint32_t *ninc);
 
+/* fsacmp.c:181-353 getIncPos (variant 0) / getIncPosInsigPrune, getIncPosInsig (variant 1) with -P
+ * proxi on an existing mask: clears unknown positions and everything between two events at most
+ * proxi apart (see fsa_oracle.c for what counts as an event). */
+void orc_inc_pos(uint32_t *mask, const unsigned char *seq_codes,
+                 const unsigned char *ref_codes, int len, unsigned proxi, int variant);
+
+/* fsacmp.c:355-485 maskProxi with -P proxi + fsacmp.c:587-633 fsacmpair. */
+void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j,
+                           const uint32_t *inc_i, const uint32_t *inc_j, int len,
+                           unsigned proxi, uint32_t *mism, uint32_t *ninc);
+
 /* fsacmp.c:552-585 fsacmp: mismatches under one shared mask. */
 uint32_t orc_masked_mism(const uint64_t *seq_i, const uint64_t *seq_j,
                          const uint32_t *mask, int len);
@@ -79,6 +90,11 @@ int orc_fsa_cmp_pair(int n, int len, const uint64_t *seqs, long wstride,
                      const unsigned char *include, const uint32_t *masks,
                      unsigned norm, unsigned minLength, double minCov,
                      int elem_size, double byteScale, void *D, void *N);
+
+int orc_fsa_cmp_pair_proxi(int n, int len, const uint64_t *seqs, long wstride,
+                           const unsigned char *include, const uint32_t *masks,
+                           unsigned norm, unsigned minLength, double minCov, unsigned proxi,
+                           int elem_size, double byteScale, void *D, void *N);
 
 /* fsacmpthrd.c:108-259 cmpFsaThrd -- global-mask mode.  mask is the single
  * shared mask (includes[0]).  Restates the INTENDED pair selection (included

@@ -58,6 +58,17 @@ void refshim_and_known(uint32_t *mask, unsigned char *seq_codes,
 	getIncPos(mask, &seq, &ref, proxi);
 }
 
+/* The builder -f selects (dist.c:802-806): flag & 32 getIncPosInsigPrune, flag & 8 getIncPosInsig, else getIncPos. */
+void refshim_inc_pos(uint32_t *mask, unsigned char *seq_codes, unsigned char *ref_codes, int len, unsigned proxi,
+                     unsigned flag) {
+	Qseqs seq, ref;
+	seq.size = seq.len = (unsigned) len; seq.seq = seq_codes;
+	ref.size = ref.len = (unsigned) len; ref.seq = ref_codes;
+	if(flag & 32) getIncPosInsigPrune(mask, &seq, &ref, proxi);
+	else if(flag & 8) getIncPosInsig(mask, &seq, &ref, proxi);
+	else getIncPos(mask, &seq, &ref, proxi);
+}
+
 void refshim_init_mask(uint32_t *mask, int len) { initIncPos(mask, len); }
 int refshim_mask_count(uint32_t *mask, int len) { return getNpos(mask, len); }
 

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--scratch-gb", type=float, default=0.0)
+    ap.add_argument("--proxi", type=int, default=0, help="-P: run k_pairdist_proxi instead of the plain compare")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     seqs, masks = synth.make_packed_torch(a.samples, a.length, seed=2, device=dev)
@@ -32,6 +33,7 @@ def main():
                     "fused": api.KERNEL_FUSED}[a.kernel])
     if a.scratch_gb:
         ctx.set_scratch_limit(int(a.scratch_gb * 2 ** 30))
+    ctx.set_proximity(a.proxi)
     ctx.set_problem(a.samples, a.length, pair=True)
     nc = api.cells(a.samples)
     d_D = torch.zeros(nc, dtype=torch.float64, device=dev)
@@ -45,6 +47,7 @@ def main():
         torch.cuda.synchronize()
         print(f"step {k}: {e0.elapsed_time(e1):.2f} ms, compare {ctx.last_compare_ms():.2f} ms, "
               f"gemm phase {ctx.last_phase_ms(1):.2f} ms  [{ctx.last_kernel}] "
+              f"{api.cells(a.samples) * a.length / (ctx.last_compare_ms() * 1e-3):.3e} base-cmp/s (compare)  "
               f"KSLICES={os.environ.get('CCG_KSLICES')} SERIAL={os.environ.get('CCG_EXPAND_SERIAL')}",
               file=sys.stderr, flush=True)
     ctx.close()

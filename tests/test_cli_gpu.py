@@ -156,6 +156,52 @@ def test_msa_parallel_and_gz_against_the_reference_binary(built, tmp_path, flag)
         assert p.stderr == ref.stderr, tag
 
 
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
+@pytest.mark.parametrize("proxi", ["4", "75"])
+@pytest.mark.parametrize("flag", ["3", "1", "11", "9", "35", "33"])
+@pytest.mark.parametrize("msa", [False, True], ids=["files", "msa"])
+def test_proximity_against_the_reference_binary(built, tmp_path, msa, flag, proxi):
+    """-P on the device: the per-sample builder (getIncPos / getIncPosInsig / getIncPosInsigPrune by -f 8 / 32),
+    maskProxi per pair (-f 2) and the shared-mask accumulation print what the reference binary prints -- .phy,
+    .num and the `# Included` counts on stderr -- from this driver and from the reference bound to the library."""
+    from ccphylo_b200 import synth
+    td = str(tmp_path)
+    n, length = 21, 20000 + 7
+    rows = synth.make_ascii(n, length, seed=int(flag) * 100 + int(proxi), snp=0.01, nrun=0.02)
+    rows[:, -1] = ord("A")          # a SNP in the last column makes the reference's maskProxi write out of bounds
+    if int(flag) & 2:
+        rows[5, 50:] = ord("N")     # excluded by the coverage gate (the shared-mask mode mishandles exclusions, App. B #3)
+    if msa:
+        path = os.path.join(td, "aln.fsa")
+        with open(path, "wb") as f:
+            for i in range(n):
+                f.write(b">s%d\n" % i)
+                for s0 in range(0, length, 60):
+                    f.write(rows[i, s0:s0 + 60].tobytes() + b"\n")
+        inputs = ["-i", path]
+    else:
+        files = []
+        for i in range(n):
+            fp = os.path.join(td, f"s{i:02d}.fsa")
+            synth.write_fasta(fp, rows[i], header="ref", width=60)
+            files.append(fp)
+        inputs = ["-r", "ref", "-i"] + files
+    outs = {}
+    for tag, exe in (("reference", REF_BIN), ("driver", BIN), ("bound", REF_GPU)):
+        if not os.path.exists(exe):
+            continue
+        phy, num = os.path.join(td, tag + ".phy"), os.path.join(td, tag + ".num")
+        p = run([exe, "dist", "-f", flag, "-P", proxi, "-W", "1000", "-t", "3", "-o", phy, "-n", num] + inputs, td)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[tag] = (open(phy).read(), open(num).read(), p.stderr)
+    plain = run([REF_BIN, "dist", "-f", flag, "-W", "1000", "-o", os.path.join(td, "plain.phy")] + inputs, td)
+    assert open(os.path.join(td, "plain.phy")).read() != outs["reference"][0], "-P changed nothing: weak inputs"
+    for tag in outs:
+        assert outs[tag][0] == outs["reference"][0], tag + ": .phy differs from the reference binary's"
+        assert outs[tag][1] == outs["reference"][1], tag + ": .num differs from the reference binary's"
+        assert outs[tag][2] == outs["reference"][2], tag + ": stderr differs from the reference binary's"
+
+
 def test_fasta_gz_input_stdout_and_long_options(built, tmp_path):
     case = next(c for c in CASES if c["name"] == "c1_pair_W")
     td = str(tmp_path)
@@ -175,7 +221,7 @@ def test_refused_options_and_errors(built, tmp_path):
     a = os.path.join(td, "a.fsa")
     with open(a, "w") as f:
         f.write(">ref\nACGT\n")
-    p = run([BIN, "dist", "-r", "ref", "-i", a, a, "-P", "3"], td)
+    p = run([BIN, "dist", "-r", "ref", "-i", a, a, "-V", "v.txt"], td)
     assert p.returncode == 1 and "not available on the GPU path" in p.stderr
     p = run([BIN, "dist", "-r", "ref", "-i", a, os.path.join(td, "missing.fsa")], td)
     assert p.returncode != 0

@@ -18,6 +18,19 @@ def test_threaded_phylip_writer_matches_per_cell_fprintf(tmp_path):
         assert p.returncode == 0 and p.stdout.strip() == "OK", p.stderr
 
 
+def test_proximity_arithmetic_of_the_kernels_on_the_host(built, tmp_path):
+    """ccphylo_b200/csrc/proxi_core.h (what k_pairdist_proxi / k_sample_proxi execute per word) compiled for the
+    host and compared with the oracle's maskProxi / getIncPos* restatement"""
+    exe = str(tmp_path / "proxi_core_test")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-I", odir, "-I", os.path.join(ROOT, "ccphylo_b200", "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tests", "csrc", "proxi_core_test.cpp"), "-L", odir, "-loracle",
+                    "-Wl,-rpath," + odir], check=True)
+    for seed in ("1", "2"):
+        p = subprocess.run([exe, seed], capture_output=True, text=True)
+        assert p.returncode == 0 and p.stdout.startswith("OK "), p.stdout + p.stderr
+
+
 def test_option_scanner_dialect(built, tmp_path):
     def run(*args):
         return subprocess.run([BIN, "dist"] + list(args), capture_output=True, text=True, cwd=str(tmp_path))
@@ -38,8 +51,8 @@ def test_option_scanner_dialect(built, tmp_path):
     # files the run then stops at the device (this container has none) or at the refused option
     a = tmp_path / "a.fsa"
     a.write_text(">ref\nACGT\n")
-    p = run("-pf3", "-s", "-W", "100", "-rref", "-i", str(a), str(a), "-P", "2")
-    assert p.returncode == 1 and "-P / --proximity is not available on the GPU path" in p.stderr
+    p = run("-pf3", "-s", "-W", "100", "-rref", "-i", str(a), str(a), "-P", "2", "-y", "m.txt")
+    assert p.returncode == 1 and "-y / --methylation_motifs is not available on the GPU path" in p.stderr
     p = run("-r", "ref", "-a", "x", str(a), str(a))
     assert p.returncode == 1 and "-a / --add" in p.stderr
 

@@ -107,3 +107,68 @@ def test_global_mask_accumulation_matches_reference(built):
     for i in range(1, n):
         R.refshim_and_known(gr, np.ascontiguousarray(codes[i]).copy(), ref0.copy(), length, 0)
     assert np.array_equal(g, gr[:W])
+
+
+# ---------------------------------------------------------------------------------------------
+# -P proximity masking (fsacmp.c:181-485): per-sample builders and the per-pair maskProxi
+# ---------------------------------------------------------------------------------------------
+def _proxi_set(n, length, seed):
+    """clustered SNPs and unknowns so that every proxi has close and distant neighbours; the last column is kept
+    equal and known (a SNP at len-1 makes the reference write past its scratch array, fsacmp.c:395-421)"""
+    codes = synth.make_codes(n, length, seed=seed, snp=0.04, nrun=0.03, lower=0.03, gap=0.01)
+    if length:
+        codes[:, -1] = 2
+    return codes
+
+
+@pytest.mark.parametrize("flag", [1, 8, 32])
+@pytest.mark.parametrize("proxi", [1, 2, 5, 31, 32, 33, 100, 5000])
+def test_per_sample_builders_with_proximity(built, flag, proxi):
+    variant = oracle.variant_of(flag)
+    for length in (1, 31, 32, 64, 97, 1500):
+        codes = _proxi_set(3, length, seed=proxi * 7 + length)
+        # pair mode: seq against itself (cdist.c:91); shared-mask mode: seq against ref on the running mask (:111)
+        for s, r in ((0, 0), (1, 0), (2, 0)):
+            want = oracle.full_mask(length).copy()
+            pad = np.zeros(len(want) + 1, np.uint32)
+            pad[:len(want)] = want
+            oracle.ref_inc_pos(pad, codes[s], codes[r], proxi, flag)
+            got = oracle.full_mask(length).copy()
+            oracle.inc_pos(got, codes[s], codes[r], proxi, variant)
+            assert np.array_equal(got, pad[:len(want)]), (length, s, r)
+            assert pad[len(want)] == 0
+
+
+@pytest.mark.parametrize("proxi", [1, 2, 3, 7, 31, 32, 33, 64, 200, 100000])
+def test_pair_counts_with_proximity(built, proxi):
+    for length in (2, 33, 64, 96, 127, 1000, 3001):
+        codes = _proxi_set(6, length, seed=proxi + length)
+        seqs, masks, _ = oracle.encode_samples(codes, proxi=proxi)
+        some = False
+        for i in range(1, 6):
+            for j in range(i):
+                want = oracle.ref_pair(seqs[i], seqs[j], masks[i], masks[j], length, proxi)
+                got = oracle.pair_counts_proxi(seqs[i], seqs[j], masks[i], masks[j], length, proxi)
+                assert got == want, (length, i, j)
+                plain = oracle.pair_counts_proxi(seqs[i], seqs[j], masks[i], masks[j], length, 0)
+                some |= plain != got
+        assert some or length < 64, "the inputs never triggered proximity masking"
+
+
+@pytest.mark.parametrize("elem,scale", [(8, 1.0), (4, 1.0), (2, 10.0), (1, 0.5)])
+@pytest.mark.parametrize("proxi", [3, 40])
+def test_pair_mode_with_proximity_matches_reference(built, elem, scale, proxi):
+    n, length = 12, 2085
+    codes = _proxi_set(n, length, seed=elem + proxi)
+    codes[4, :] = 4
+    seqs, masks, inc = oracle.encode_samples(codes, proxi=proxi)
+    min_len = int(0.5 * length)
+    include = (inc >= min_len).astype(np.uint8)
+    for tnum in (1, 3):
+        Dr, Nr, dnr = oracle.ref_fsa_cmp(seqs, masks, include, length, pair=True, tnum=tnum, norm=1000,
+                                         min_length=min_len, min_cov=0.5, proxi=proxi, elem_size=elem, byte_scale=scale)
+        Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=1000, min_length=min_len, min_cov=0.5,
+                                          elem_size=elem, byte_scale=scale, proxi=proxi)
+        assert dnr == dno
+        assert np.array_equal(Dr.view(np.uint8), Do.view(np.uint8))
+        assert np.array_equal(Nr.view(np.uint8), No.view(np.uint8))
