@@ -28,7 +28,7 @@ EXPORTS = [
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
-    "ccg_set_proximity", "ccg_sample_proximity",
+    "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row",
 ]
 
 MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "ln", "nl1", "nl2",
@@ -101,6 +101,7 @@ def load():
     L.ccg_run_pair_dev.argtypes = [vp, vp, u, u, d, i, d, vp, vp, C.POINTER(i)]
     L.ccg_run_global_dev.argtypes = [vp, vp, u, i, d, vp, C.POINTER(i), C.POINTER(u)]
     L.ccg_get_raw_counts.argtypes = [vp, vp, vp]
+    L.ccg_run_row.argtypes = [vp, i, u, u, d, vp, vp, C.POINTER(i)]
     L.ccg_fsa_cmp_thread_out.argtypes = [vp, i, vp, vp, i, d, i, i, vp, vp, vp, u, u, d, u, C.POINTER(i), C.POINTER(u)]
     L.ccg_host_alloc.restype = vp
     L.ccg_host_alloc.argtypes = [C.c_size_t]
@@ -118,6 +119,7 @@ def load():
     L.ccg_mat_put_sample.argtypes = [vp, i, vp, vp, i]
     L.ccg_mat_run.argtypes = [vp, vp, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, i, C.c_double,
                               vp, vp, vp, vp]
+    L.ccg_mat_run_row.argtypes = [vp, i, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, vp, vp, vp]
     L.ccg_measure_fp4_peak.restype = C.c_double
     L.ccg_measure_fp4_peak.argtypes = [vp, C.c_double, C.c_double, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     L.ccg_measure_i8_peak.restype = C.c_double
@@ -297,6 +299,15 @@ class Context:
                                             byte_scale, d_D_ptr, C.byref(dn), C.byref(ginc)))
         return dn.value, ginc.value
 
+    def run_row(self, row_slot, norm=0, min_length=1, min_cov=0.5, want_n=True):
+        """cmpFsaRowThrd (fsacmpthrd.c:482): slot row_slot against every uploaded slot below it -> (D, N) doubles."""
+        D = np.zeros(max(row_slot, 1), dtype=np.float64)
+        N = np.zeros(max(row_slot, 1), dtype=np.float64) if want_n else None
+        cols = C.c_int(0)
+        self._ck(self._L.ccg_run_row(self._h, row_slot, norm, min_length, min_cov, D.ctypes.data,
+                                     N.ctypes.data if want_n else None, C.byref(cols)))
+        return D[:cols.value], (N[:cols.value] if want_n else None)
+
     def raw_counts(self, dn):
         mism = np.zeros(max(cells(dn), 1), dtype=np.uint32)
         ninc = np.zeros(max(cells(dn), 1), dtype=np.uint32)
@@ -331,6 +342,16 @@ class Context:
                                      C.byref(dn), rows.ctypes.data))
         k = cells(dn.value)
         return D[:k], N[:k], dn.value, rows[:k]
+
+    def mat_run_row(self, row_slot, method="cos", alpha=0.05, norm=0, min_depth=15, min_length=1, min_cov=0.5):
+        """cmpMatRowThrd (ltdmatrixthrd.c:111): slot row_slot against the slots below it -> (D, N, rows) per column."""
+        mid, order = mat_method(method)
+        D = np.zeros(max(row_slot, 1), dtype=np.float64)
+        N = np.zeros(max(row_slot, 1), dtype=np.float64)
+        rows = np.zeros(max(row_slot, 1), dtype=np.uint32)
+        self._ck(self._L.ccg_mat_run_row(self._h, row_slot, mid, order, alpha, norm, min_depth, min_length, min_cov,
+                                         D.ctypes.data, N.ctypes.data, rows.ctypes.data))
+        return D[:row_slot], N[:row_slot], rows[:row_slot]
 
     # ---- introspection ----
     @property

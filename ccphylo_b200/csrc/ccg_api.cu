@@ -1245,6 +1245,7 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	ep.D = d_D;
 	ep.N = mode == 0 ? d_N : 0;
 	ep.rank = ctx->d_rank;
+	if(ctx->row_slot1) ep.row_plus1 = ctx->h_rank[ctx->row_slot1 - 1] + 1;
 	if(mode == 0) {
 		/* fsacmpthrd.c:292: minLength = minLength < minCov * len ? minCov * len : minLength */
 		if(minLength < minCov * ctx->len) minLength = (unsigned) (minCov * ctx->len);
@@ -1335,6 +1336,62 @@ extern "C" int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include, un
 	if(!d_D) return CCG_ERR_ARG;
 	if(ctx && global_inc) *global_inc = ctx->global_inc;
 	return run_common(ctx, 1, include, norm, 0, 0.0, elem_size, byteScale, d_D, 0, Dn);
+}
+
+/* cmpFsaRowThrd (fsacmpthrd.c:482-580): the row of one sample against every sample uploaded into a lower slot.
+ * The pair kernels run on the macro-tile row that holds the slot; the epilogue keeps that one row. */
+extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned minLength, double minCov, double *D, double *N,
+                           int *cols_out) {
+	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !D || row_slot < 0 || row_slot >= ctx->n || !ctx->present[row_slot])
+		return CCG_ERR_ARG;
+	if(ctx->proxi) {
+		set_err(ctx, "a row against an existing matrix (-a) with proximity masking (-P) is not available on the GPU path");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	if(ctx->world > 1) {
+		set_err(ctx, "ccg_run_row runs on one device");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	CK(ctx, cudaSetDevice(ctx->device));
+	unsigned char *use = (unsigned char *) calloc((size_t) ctx->n, 1);
+	if(!use) return CCG_ERR_NOMEM;
+	int cols = 0;
+	for(int j = 0; j < row_slot; ++j) cols += use[j] = ctx->present[j];
+	use[row_slot] = 1;
+	if(cols_out) *cols_out = cols;
+	if(cols == 0) { free(use); return CCG_OK; }
+	const size_t bytes = (size_t) cols * sizeof(double);
+	if(ctx->out_bytes < bytes || !ctx->d_out_D) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_out_D); ctx->d_out_D = 0;
+		cudaFree(ctx->d_out_N); ctx->d_out_N = 0;
+		ctx->out_bytes = 0;
+		if(cudaMalloc(&ctx->d_out_D, bytes) != cudaSuccess || cudaMalloc(&ctx->d_out_N, bytes) != cudaSuccess) {
+			free(use);
+			set_err(ctx, "cudaMalloc of 2 x %zu result bytes failed", bytes);
+			return CCG_ERR_NOMEM;
+		}
+		ctx->out_bytes = bytes;
+	}
+	const int win_on = ctx->win_on;
+	int win[4];
+	memcpy(win, ctx->win, sizeof(win));
+	int rc = ccg_set_tile_window(ctx, row_slot / CCG_UMMA_BM * CCG_UMMA_BM, row_slot + 1, 0, row_slot > 0 ? row_slot : 1);
+	if(!rc) {
+		int Dn = 0;
+		ctx->row_slot1 = row_slot + 1;
+		rc = run_common(ctx, 0, use, norm, minLength, minCov, 8, 1.0, ctx->d_out_D, ctx->d_out_N, &Dn);
+		ctx->row_slot1 = 0;
+	}
+	ctx->win_on = win_on;
+	memcpy(ctx->win, win, sizeof(win));
+	update_need(ctx);
+	free(use);
+	if(rc) return rc;
+	CK(ctx, cudaMemcpyAsync(D, ctx->d_out_D, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	if(N) CK(ctx, cudaMemcpyAsync(N, ctx->d_out_N, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return CCG_OK;
 }
 
 extern "C" int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc) {

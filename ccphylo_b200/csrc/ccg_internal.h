@@ -48,6 +48,8 @@ struct EpilogueParams {
 	void *D;               /* device, packed over included samples */
 	void *N;               /* device or NULL */
 	const int *rank;       /* slot -> compact index, -1 = excluded */
+	int row_plus1;         /* 0 = the packed triangle.  r + 1: only the cells of compact row r are written, cell = column, and
+	                        * a cell that fails the gate gets N = 0 (cmpFsaRowThrd fsacmpthrd.c:560-570; doubles only) */
 };
 
 struct PopcParams {
@@ -98,6 +100,7 @@ struct ccg_ctx {
 	int use_i8;                     /* CCG_I8=1: int8 operands (kind::i8) instead of the default e2m1 panel (kind::mxf4) */
 	int dbg_kslices, dbg_serial, dbg_nolock, dbg_umma1;   /* CCG_KSLICES / CCG_EXPAND_SERIAL / CCG_NOLOCK / CCG_UMMA1 overrides (experiments only) */
 
+	int row_slot1;                  /* ccg_run_row: 1 + the slot whose row is being computed, 0 otherwise */
 	unsigned proxi;                 /* -P: minimum distance between SNPs (0 = no proximity masking), ccg_set_proximity */
 	int proxi_snp_only;             /* events of the per-sample builder: 0 getIncPos, 1 getIncPosInsig / getIncPosInsigPrune */
 

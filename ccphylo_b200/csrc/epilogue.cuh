@@ -33,9 +33,14 @@ __device__ __forceinline__ void ccg_write_cell(const EpilogueParams &ep, int slo
 	int c = ep.rank[slot_j];
 	if(r < 0 || c < 0) return;
 	long long cell = (long long) r * (r - 1) / 2 + c;
+	if(ep.row_plus1) {
+		if(r + 1 != ep.row_plus1) return;
+		cell = c;
+	}
 
 	if(ep.mode == 0) {
 		bool ok = ep.minLength <= inc;
+		if(ep.row_plus1 && !ok) inc = 0;
 		unsigned long long scaled = (unsigned long long) mism * ep.norm;
 		if(ep.elem_size == 8) {
 			double d;

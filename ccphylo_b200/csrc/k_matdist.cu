@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(MT * MT)
 k_matdist_finalize(const int2 *__restrict__ tiles, int ntiles, int nslices, const double *__restrict__ part_dist,
                    const unsigned *__restrict__ part_rows, const int *__restrict__ lens, const int *__restrict__ rank, int n,
                    unsigned norm, unsigned minLength, double minCov, int elem_size, double byteScale, void *D, void *N,
-                   unsigned *__restrict__ rows_out) {
+                   unsigned *__restrict__ rows_out, int row_slot) {
 	const int tile = blockIdx.x;
 	const int ti = tiles[tile].x, tj = tiles[tile].y;
 	const int si = ti * MT + threadIdx.x / MT, sj = tj * MT + threadIdx.x % MT;
@@ -311,7 +311,9 @@ k_matdist_finalize(const int2 *__restrict__ tiles, int ntiles, int nslices, cons
 	double d, nn;
 	if(!ok) { d = -1.0; nn = 0.0; }
 	else { nn = (double) rows; d = norm ? dist / (double) rows * (double) norm : dist; }
-	const long long cell = (long long) r * (r - 1) / 2 + c;
+	/* row_slot >= 0 (cmpMatRowThrd ltdmatrixthrd.c:111): only that sample's row, cell = column */
+	if(row_slot >= 0 && si != row_slot) return;
+	const long long cell = row_slot >= 0 ? (long long) c : (long long) r * (r - 1) / 2 + c;
 	if(rows_out) rows_out[cell] = ok ? rows : 0u;
 	if(elem_size == 8) {
 		((double *) D)[cell] = d;
@@ -449,9 +451,9 @@ extern "C" int ccg_mat_put_sample(ccg_ctx *ctx, int idx, const uint16_t *counts6
 	return CCG_OK;
 }
 
-extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha, unsigned norm,
-                           unsigned minDepth, unsigned minLength, double minCov, int elem_size, double byteScale, void *D,
-                           void *N, int *Dn_out, uint32_t *rows_inc) {
+static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha, unsigned norm,
+                        unsigned minDepth, unsigned minLength, double minCov, int elem_size, double byteScale, void *D,
+                        void *N, int *Dn_out, uint32_t *rows_inc, int row_slot) {
 	if(!ctx || !ctx->mat_counts || !D) return CCG_ERR_ARG;
 	if(elem_size != 8 && elem_size != 4 && elem_size != 2 && elem_size != 1) return CCG_ERR_ARG;
 	MatKernel kern = pick_kernel(method);
@@ -471,6 +473,7 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 	const int T = npad / MT;
 	for(int ti = 0; ti < T; ++ti)
 		for(int tj = 0; tj <= ti; ++tj) {
+			if(row_slot >= 0 && ti != row_slot / MT) continue;
 			bool any_i = false, any_j = false;
 			for(int k = 0; k < MT; ++k) {
 				any_i |= rank[(size_t) ti * MT + k] >= 0;
@@ -483,7 +486,7 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 		}
 	const int ntiles = (int) tiles.size();
 	if(ntiles == 0) {
-		const size_t cells0 = (size_t) Dn * (Dn - 1) / 2;
+		const size_t cells0 = row_slot >= 0 ? (size_t) Dn - 1 : (size_t) Dn * (Dn - 1) / 2;
 		memset(D, 0, cells0 * elem_size);
 		if(N) memset(N, 0, cells0 * elem_size);
 		if(rows_inc) memset(rows_inc, 0, cells0 * 4);
@@ -512,7 +515,7 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 		ctx->mat_part_cap = part;
 	}
 	int rc = CCG_OK;
-	const size_t cells = (size_t) Dn * (Dn - 1) / 2;
+	const size_t cells = row_slot >= 0 ? (size_t) Dn - 1 : (size_t) Dn * (Dn - 1) / 2;
 	int2 *d_tiles = 0;
 	void *d_D = 0, *d_N = 0;
 	unsigned *d_rows = 0;
@@ -545,7 +548,7 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 		ctx->launches++;
 		k_matdist_finalize<<<ntiles, MT * MT, 0, ctx->stream>>>(d_tiles, ntiles, nslices, ctx->mat_part_dist, ctx->mat_part_rows,
 		                                                       ctx->mat_lens, ctx->mat_rank, n, norm, minLength, minCov, elem_size,
-		                                                       byteScale, d_D, d_N, d_rows);
+		                                                       byteScale, d_D, d_N, d_rows, row_slot);
 		ctx->launches++;
 		e = cudaGetLastError();
 	}
@@ -563,4 +566,24 @@ extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int metho
 	cudaFree(d_N);
 	cudaFree(d_rows);
 	return rc;
+}
+
+extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha, unsigned norm,
+                           unsigned minDepth, unsigned minLength, double minCov, int elem_size, double byteScale, void *D,
+                           void *N, int *Dn_out, uint32_t *rows_inc) {
+	return mat_run_impl(ctx, include, method, order, alpha, norm, minDepth, minLength, minCov, elem_size, byteScale, D, N, Dn_out,
+	                    rows_inc, -1);
+}
+
+/* cmpMatRowThrd (ltdmatrixthrd.c:111-181): the last uploaded sample against all the others */
+extern "C" int ccg_mat_run_row(ccg_ctx *ctx, int row_slot, int method, unsigned order, double alpha, unsigned norm,
+                               unsigned minDepth, unsigned minLength, double minCov, double *D, double *N, uint32_t *rows_inc) {
+	if(!ctx || !ctx->mat_counts || row_slot < 0 || row_slot >= ctx->mat_n) return CCG_ERR_ARG;
+	if(ctx->world > 1) return CCG_ERR_UNSUPPORTED;
+	/* columns are the slots below the row: everything above it stays out */
+	std::vector<unsigned char> use((size_t) ctx->mat_n, 0);
+	for(int i = 0; i <= row_slot; ++i) use[(size_t) i] = 1;
+	int Dn = 0;
+	return mat_run_impl(ctx, use.data(), method, order, alpha, norm, minDepth, minLength, minCov, 8, 1.0, D, N, &Dn, rows_inc,
+	                    row_slot);
 }

@@ -472,6 +472,252 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 }
 
 /* ------------------------------------------------------------------------------------------
+ * -a: one more sample against an existing matrix (add2Matrix dist.c:331-411, ltdFsaRowThrd
+ * fsacmpthrd.c:582-667, printphyUpdate phy.c:201-250)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+	int n;                   /* rows of the existing matrix */
+	char **paths;            /* directory of the first -i argument + the row's name */
+} PhyNames;
+
+/* getSizePhy + getFilenamesPhy (phy.c:509-650): the sample count and the row names of a single-matrix Phylip file */
+static int read_phy_names(const char *phyname, const char *dir, char sep, PhyNames *out) {
+	FILE *f = fopen(phyname, "rb");
+	if(!f) {
+		fprintf(stderr, "Filename:\t%s\n", phyname);
+		die_errno();
+	}
+	ByteBuf text;
+	bytebuf_init(&text, 1 << 16);
+	for(;;) {
+		if(text.cap - text.len < 65536) {
+			text.cap <<= 1;
+			text.data = realloc(text.data, text.cap);
+			if(!text.data) die_errno();
+		}
+		size_t got = fread(text.data + text.len, 1, text.cap - text.len, f);
+		if(!got) break;
+		text.len += got;
+	}
+	fclose(f);
+	const unsigned char *p = text.data, *end = text.data + text.len;
+	if(p < end && *p == '#') {
+		while(p < end && *p != '\n') ++p;
+		if(p < end) ++p;
+	}
+	int n = 0;
+	while(p < end && *p != '\n') {
+		if('0' <= *p && *p <= '9') n = 10 * n + (*p - '0');
+		++p;
+	}
+	if(p < end) ++p;
+	out->n = n;
+	out->paths = calloc((size_t) (n ? n : 1), sizeof(char *));
+	if(!out->paths) die_errno();
+	const size_t dlen = strlen(dir);
+	for(int i = 0; i < n; ++i) {
+		if(p >= end) {
+			fprintf(stderr, "Malformatted phylip file, name on row: %d\n", i + 1);
+			return 0;
+		}
+		const unsigned char *q = p;
+		while(q < end && *q != (unsigned char) sep && *q != '\n') ++q;
+		size_t nl = (size_t) (q - p);
+		while(nl && (p[nl - 1] == ' ' || (p[nl - 1] >= '\t' && p[nl - 1] <= '\r'))) --nl;     /* isspace */
+		char *path = malloc(dlen + nl + 1);
+		if(!path) die_errno();
+		memcpy(path, dir, dlen);
+		memcpy(path + dlen, p, nl);
+		path[dlen + nl] = 0;
+		out->paths[i] = path;
+		while(q < end && *q != '\n') ++q;
+		if(q >= end && i != n - 1) {
+			fprintf(stderr, "Malformatted phylip file, missing newline at row:\t%d\n", i + 1);
+			return 0;
+		}
+		p = q < end ? q + 1 : q;
+	}
+	const int more = p < end;
+	bytebuf_free(&text);
+	if(more) {
+		fprintf(stderr, "Cannot update a multi distance phylip file.\n");
+		return -1;
+	}
+	return 1;
+}
+
+/* printphyUpdate (phy.c:201-250): new count over the first ten bytes, the new row at the end */
+static void phy_append_row(const char *phyname, int n, char *name, const double *row, unsigned flag, int precision) {
+	FILE *f = fopen(phyname, "rb+");
+	if(!f) {
+		fprintf(stderr, "Filename:\t%s\n", phyname);
+		die_errno();
+	}
+	fprintf(f, "%10d", n);
+	fflush(f);
+	fseek(f, 0, SEEK_END);
+	size_t len = strlen(name);
+	if(len && ((name[0] == '"' && name[len - 1] == '"') || (name[0] == '\'' && name[len - 1] == '\''))) {
+		name[len - 1] = 0;
+		++name;
+	}
+	const char *slash = strrchr(name, '/');
+	if(slash) name = (char *) slash + 1;
+	if(flag & 1) fprintf(f, "%s", name);
+	else fprintf(f, "%-10.10s", name);
+	for(int j = 0; j + 1 < n; ++j) {
+		const double d = row[j];
+		if(d == (int) d) fprintf(f, "\t%d", (int) d);
+		else fprintf(f, "\t%.*f", precision, d);
+	}
+	fprintf(f, "\n");
+	fclose(f);
+}
+
+static int add_fasta_row(const DistOpts *o, const PhyNames *phy, double *D, double *N) {
+	const int n = phy->n;
+	FsaJob fj;
+	DistOpts one = *o;
+	char *addname = o->addfilename;
+	one.filenames = &addname;
+	fj.o = &one;
+	fsa_code_table(o->flag, fj.table);
+	Parsed added;
+	memset(&added, 0, sizeof(added));
+	bytebuf_init(&added.codes, 1 << 20);
+	parse_one(0, &added, &fj);
+	if(added.status == PARSE_OPEN_FAILED) {
+		errno = added.err;
+		fprintf(stderr, "Filename:\t%s\n", addname);
+		die_errno();
+	}
+	if(added.status == PARSE_NO_TEMPLATE || added.status == PARSE_NOT_FASTA) {
+		fprintf(stderr, "Missing template entry (\"%s\") in file:\t%s\n", o->targetTemplate, addname);
+		exit(1);
+	}
+	if(added.status == PARSE_NO_SEQ) {
+		fprintf(stderr, "\"%s\" is not fasta.\n", addname);
+		exit(1);
+	}
+	const int len = (int) added.codes.len;
+	unsigned minLength = o->minLength;
+	if(minLength < o->minCov * len) minLength = (unsigned) (o->minCov * len);
+	if(added.known < minLength) {
+		fprintf(stderr, "Template (\"%s\") did not exceed threshold for inclusion:\t%s\n", o->targetTemplate, addname);
+		return 1;
+	}
+	int threads = o->threads < 1 ? 1 : o->threads;
+	if(n < threads) fprintf(stderr, "Adjustning number of nodes to %d, to conform with the matrix size.\n", (threads = n));
+	if(n < 1) return 0;
+
+	ccg_ctx *ctx = 0;
+	int rc = ccg_init(&ctx, -1);
+	if(rc) die_gpu(0, rc);
+	rc = ccg_set_problem(ctx, n + 1, len, 1);
+	if(rc) die_gpu(ctx, rc);
+	if(len > 0) {
+		rc = ccg_put_sample_codes(ctx, n, added.codes.data);
+		if(!rc) rc = ccg_sync(ctx);
+		if(rc) die_gpu(ctx, rc);
+	}
+	/* the samples of the existing matrix, parsed by the host threads, into the slots below */
+	DistOpts old = *o;
+	old.filenames = phy->paths;
+	fj.o = &old;
+	const int window = threads + 2;
+	Parsed *slots = calloc((size_t) window, sizeof(Parsed));
+	if(!slots) die_errno();
+	for(int k = 0; k < window; ++k) bytebuf_init(&slots[k].codes, 1 << 20);
+	OrderedPool *pool = pool_start(n, threads, window, slots, sizeof(Parsed), parse_one, &fj);
+	if(!pool) die_errno();
+	for(int j = 0; j < n; ++j) {
+		Parsed *r = (Parsed *) pool_take(pool, j);
+		if(r->status == PARSE_OPEN_FAILED && r->err) {
+			errno = r->err;
+			fprintf(stderr, "Filename:\t%s\n", phy->paths[j]);
+			die_errno();
+		}
+		if(r->status != PARSE_OK) {
+			/* the reference goes on with whatever its buffers hold (fsacmpthrd.c:538-540) */
+			fprintf(stderr, "Missing template entry (\"%s\") in file:\t%s\n", o->targetTemplate, phy->paths[j]);
+			exit(1);
+		}
+		if((int) r->codes.len != len) {
+			fprintf(stderr, "New sequence does not match the existing sequences.\n");
+			exit(1);
+		}
+		if(len > 0) {
+			rc = ccg_put_sample_codes(ctx, j, r->codes.data);
+			if(!rc) rc = ccg_sync(ctx);
+			if(rc) die_gpu(ctx, rc);
+		}
+		pool_release(pool, j);
+	}
+	pool_finish(pool);
+	for(int k = 0; k < window; ++k) bytebuf_free(&slots[k].codes);
+	free(slots);
+	if(len > 0) {
+		int cols = 0;
+		rc = ccg_run_row(ctx, n, o->norm, minLength, o->minCov, D, N, &cols);
+		if(rc) die_gpu(ctx, rc);
+	} else {
+		for(int j = 0; j < n; ++j) {
+			D[j] = minLength ? -1.0 : 0.0;
+			N[j] = 0.0;
+		}
+	}
+	for(int j = 0; j < n; ++j)
+		if(D[j] == -1.0) fprintf(stderr, "No sufficient overlap with sample:\t%s\n", phy->paths[j]);
+	ccg_destroy(ctx);
+	bytebuf_free(&added.codes);
+	return 0;
+}
+
+static int add_to_matrix(const DistOpts *o) {
+	if(o->proxi) {
+		fprintf(stderr, "-a / --add together with -P / --proximity is not available on the GPU path of dist (use the CPU ccphylo for it).\n");
+		return 1;
+	}
+	/* directory of the first input file: the names of the matrix are looked up there (dist.c:344-356) */
+	char *dir = strdup(o->filenames[0]);
+	if(!dir) die_errno();
+	char *slash = strrchr(dir, '/');
+	if(slash) slash[1] = 0;
+	PhyNames phy;
+	const int ok = read_phy_names(o->outputfilename, dir, o->sep, &phy);
+	free(dir);
+	if(ok == 0) {
+		errno |= 1;
+		die_errno();
+	}
+	if(ok < 0) return 1;
+	FsaReader *fr = fsa_open(o->addfilename);
+	if(!fr) {
+		fprintf(stderr, "Filename:\t%s\n", o->addfilename);
+		die_errno();
+	}
+	const int informat = fsa_peek(fr);
+	fsa_close(fr);
+	const int n = phy.n;
+	double *D = malloc((size_t) (n ? n : 1) * sizeof(double)), *N = malloc((size_t) (n ? n : 1) * sizeof(double));
+	if(!D || !N) die_errno();
+	int failed;
+	if(informat == '>') failed = add_fasta_row(o, &phy, D, N);
+	else failed = dist_mat_add_row(o, n, phy.paths, D, N);
+	if(failed) {
+		fprintf(stderr, "Distance measures failed and thus the matrix was not updated.\n");
+		return 1;
+	}
+	phy_append_row(o->outputfilename, n + 1, o->addfilename, D, o->flag, o->precision);
+	if(o->noutputfilename) phy_append_row(o->noutputfilename, n + 1, o->addfilename, N, o->flag, o->precision);
+	for(int i = 0; i < n; ++i) free(phy.paths[i]);
+	free(phy.paths);
+	free(D);
+	free(N);
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * makeMatrix (dist.c:42-329)
  * ------------------------------------------------------------------------------------------ */
 static void make_matrix(DistOpts *o) {
@@ -527,7 +773,7 @@ static int help_message(FILE *out) {
 		{'y', "methylation_motifs", "Mask methylation motifs from <file> (not on the GPU path)", "False/None"},
 		{'V', "nucleotide_variations", "Output nucleotide variations (not on the GPU path)", "False/None"},
 		{'r', "reference", "Target reference", "None"},
-		{'a', "add", "Add file to existing matrix (not on the GPU path)", ""},
+		{'a', "add", "Add file to existing matrix", ""},
 		{'E', "min_depth", "Minimum depth", "15"},
 		{'C', "min_cov", "Minimum coverage", "50.0%"},
 		{'L', "min_len", "Minimum overlapping length", "1"},
@@ -655,11 +901,12 @@ int main_dist(int argc, char **argv) {
 	if(dist_mat_parse_method(&o)) die_invalid(o.method_err);
 	if(!o.numFile && o.targetTemplate) o.numFile = 1;
 
-	if(o.addfilename || o.diffilename || o.methfilename) {
+	if(o.diffilename || o.methfilename) {
 		fprintf(stderr, "%s is not available on the GPU path of dist (use the CPU ccphylo for it).\n",
-		        o.addfilename ? "-a / --add" : o.diffilename ? "-V / --nucleotide_variations" : "-y / --methylation_motifs");
+		        o.diffilename ? "-V / --nucleotide_variations" : "-y / --methylation_motifs");
 		return 1;
 	}
+	if(o.addfilename && o.filenames) return add_to_matrix(&o);
 	make_matrix(&o);
 	return 0;
 }

@@ -199,6 +199,90 @@ static void one_template(const DistOpts *o, ccg_ctx *ctx, int n, char **filename
 	ccg_host_free(N);
 }
 
+/* ltdRowThrd (ltdmatrixthrd.c:564-611) + cmpMatRowThrd (:111-181) */
+int dist_mat_add_row(const DistOpts *o, int n, char **paths, double *D, double *N) {
+	const char *target = o->targetTemplate;
+	MatSample added;
+	mat_sample_init(&added);
+	errno = 0;
+	int st = mat_load_template(o->addfilename, target, o->minDepth, &added);
+	if(st < 0) {
+		fprintf(stderr, "Filename:\t%s\n", o->addfilename);
+		die_errno();
+	}
+	if(st == 0) {
+		fprintf(stderr, "Malformed matrix in:\t%s\n", o->addfilename);
+		exit(1);
+	}
+	if(added.nNucs < o->minLength || added.nNucs < o->minCov * (double) added.len) {
+		fprintf(stderr, "Template (\"%s\") did not exceed threshold for inclusion:\t%s\n", target, o->addfilename);
+		return 1;
+	}
+	int nthreads = o->threads < 1 ? 1 : o->threads;
+	if(n < nthreads) fprintf(stderr, "Adjustning number of nodes to %d, to conform with the matrix size.\n", (nthreads = n));
+	if(n < 1) return 0;
+	ccg_ctx *ctx = 0;
+	int rc = ccg_init(&ctx, -1);
+	if(rc) die_gpu(0, rc);
+	rc = ccg_mat_set_problem(ctx, n + 1, (int) added.len);
+	if(!rc) rc = ccg_mat_put_sample(ctx, n, added.counts, added.totals, (int) added.len);
+	if(!rc) rc = ccg_sync(ctx);
+	if(rc) die_gpu(ctx, rc);
+
+	MatJob mj = {paths, 0, target, o->minDepth};
+	const int window = nthreads + 2;
+	MatParsed *slots = calloc((size_t) window, sizeof(MatParsed));
+	if(!slots) die_errno();
+	for(int k = 0; k < window; ++k) mat_sample_init(&slots[k].m);
+	OrderedPool *pool = pool_start(n, nthreads, window, slots, sizeof(MatParsed), load_one, &mj);
+	if(!pool) die_errno();
+	/* a column sample with more rows than the new one cannot be compared (cmpMats returns -1, matcmp.c:466) */
+	unsigned char *too_long = calloc((size_t) n, 1);
+	if(!too_long) die_errno();
+	for(int j = 0; j < n; ++j) {
+		MatParsed *r = (MatParsed *) pool_take(pool, j);
+		if(r->status < 0) {
+			if(r->err) errno = r->err;
+			fprintf(stderr, "Filename:\t%s\n", paths[j]);
+			die_errno();
+		}
+		if(r->status == 0 || r->m.nNucs < o->minLength || r->m.nNucs < o->minCov * (double) r->m.len) {
+			/* cmpMats -2 (matcmp.c:455,481): fatal in row mode (ltdmatrixthrd.c:160-162) */
+			fprintf(stderr, "Template (\"%s\") did not exceed threshold for inclusion:\t%s\n", target, paths[j]);
+			exit(1);
+		}
+		size_t len = r->m.len;
+		if(len > added.len) {
+			too_long[j] = 1;
+			len = added.len;
+		}
+		rc = ccg_mat_put_sample(ctx, j, r->m.counts, r->m.totals, (int) len);
+		if(!rc) rc = ccg_sync(ctx);
+		if(rc) die_gpu(ctx, rc);
+		pool_release(pool, j);
+	}
+	pool_finish(pool);
+	for(int k = 0; k < window; ++k) mat_sample_free(&slots[k].m);
+	free(slots);
+	uint32_t *rows = malloc((size_t) n * sizeof(uint32_t));
+	if(!rows) die_errno();
+	rc = ccg_mat_run_row(ctx, n, o->method_id, o->method_order, o->alpha, o->norm, o->minDepth, o->minLength, o->minCov, D, N, rows);
+	if(rc) die_gpu(ctx, rc);
+	for(int j = 0; j < n; ++j) {
+		if(too_long[j]) {
+			D[j] = -1.0;
+			N[j] = 0.0;
+			rows[j] = 0;
+		}
+		if(rows[j] == 0) fprintf(stderr, "No sufficient overlap with sample:\t%s\n", paths[j]);
+	}
+	free(rows);
+	free(too_long);
+	mat_sample_free(&added);
+	ccg_destroy(ctx);
+	return 0;
+}
+
 void dist_mat_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	const int n = (int) o->numFile;
 	ccg_ctx *ctx = 0;

@@ -22,6 +22,9 @@ typedef struct {
 /* dist_mat.c: KMA .mat count-matrix inputs (ltdmatrixthrd.c:376, ltdmatrix.c:32) */
 void dist_mat_files(const DistOpts *o, FILE *outfile, FILE *noutfile);
 void dist_mat_union(const DistOpts *o, FILE *outfile, FILE *noutfile);
+/* -a on .mat input (ltdRowThrd ltdmatrixthrd.c:564): the row of o->addfilename against the n samples in paths;
+ * 0 on success, 1 when the new sample fails its gate */
+int dist_mat_add_row(const DistOpts *o, int n, char **paths, double *D, double *N);
 void dist_mat_method_help(FILE *out);
 /* 0 on success; on failure o->method_err names the option for "Invalid value parsed at ..." */
 int dist_mat_parse_method(DistOpts *o);

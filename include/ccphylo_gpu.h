@@ -192,6 +192,16 @@ int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include,
                        unsigned norm, int elem_size, double byteScale,
                        void *d_D, int *Dn, unsigned *global_inc);
 
+/* One row against an existing matrix (-a): replaces fsaCmpThreadOut(tnum, &cmpFsaRowThrd, ...)
+ * (fsacmpthrd.c:653, worker :482-580).  The new sample sits in slot row_slot of a pair-mode
+ * store, the samples of the existing matrix in the slots below it.  D[k] / N[k] (HOST, doubles as
+ * in the reference; N may be NULL) receive the cell against the k-th uploaded slot below
+ * row_slot: N = positions known in both, D = norm ? mismatches * norm / N : mismatches, and
+ * D = -1, N = 0 where N < max(minLength, minCov * len) (the caller prints the reference's
+ * "No sufficient overlap with sample" line for those).  *cols receives the number of cells. */
+int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned minLength, double minCov,
+                double *D, double *N, int *cols);
+
 /* Raw integer results of the last pair-mode run for included samples:
  * mismatch counts and inclusion counts as u32, same packed layout.  HOST
  * buffers; either may be NULL. */
@@ -252,6 +262,14 @@ int ccg_mat_put_sample(ccg_ctx *ctx, int idx, const uint16_t *counts6, const uin
 int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha,
                 unsigned norm, unsigned minDepth, unsigned minLength, double minCov, int elem_size,
                 double byteScale, void *D, void *N, int *Dn, uint32_t *rows_inc);
+
+/* One row against an existing matrix (-a on .mat input): replaces matCmpThreadOut(tnum,
+ * &cmpMatRowThrd, ...) (ltdmatrixthrd.c:605, worker :111-181).  The new sample sits in slot
+ * row_slot, the samples of the existing matrix in the slots below.  D, N (may be NULL), rows_inc
+ * (may be NULL): HOST buffers of row_slot doubles / u32, same cell rules as ccg_mat_run. */
+int ccg_mat_run_row(ccg_ctx *ctx, int row_slot, int method, unsigned order, double alpha, unsigned norm,
+                    unsigned minDepth, unsigned minLength, double minCov, double *D, double *N,
+                    uint32_t *rows_inc);
 
 /* Roofline denominator for the tensor-core kernel: runs a loads-free loop of the kernel's own
  * MMA shape (tcgen05 kind::i8, cta_group::2, 256 x 256 x 32, operands static in shared memory)

@@ -212,6 +212,24 @@ def pair_counts_proxi(seq_i, seq_j, inc_i, inc_j, length, proxi):
     return m.value, n.value
 
 
+def fsa_cmp_row(seqs, masks, row, length, norm=0, min_length=1, min_cov=0.5):
+    """cmpFsaRowThrd (fsacmpthrd.c:482-580) without -P: sample `row` against samples 0..row-1.  The pair mask is
+    includeadd & known(seq_j) (:545-546, getIncPos with proxi 0), counts by fsacmpair (:555); cell rule :559-569:
+    D = norm ? mism * norm / inc : mism (norm is a double there), D = -1 and N = 0 below the gate."""
+    gate = max(min_length, int(min_cov * length)) if min_length < min_cov * length else min_length
+    D = np.zeros(row, dtype=np.float64)
+    N = np.zeros(row, dtype=np.float64)
+    for j in range(row):
+        m, inc = pair_counts_proxi(seqs[row], seqs[j], masks[row], masks[j], length, 0)
+        if gate <= inc:
+            D[j] = (np.float64(m) * np.float64(norm) / np.float64(inc)) if norm else np.float64(m)
+            N[j] = inc
+        else:
+            D[j] = -1.0
+            N[j] = 0.0
+    return D, N
+
+
 def raw_pair_matrix(seqs, masks, length, nthreads=8):
     n, W = seqs.shape
     mism = np.zeros(max(cells(n), 1), dtype=np.uint32)
