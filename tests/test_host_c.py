@@ -53,8 +53,13 @@ def test_option_scanner_dialect(built, tmp_path):
     a.write_text(">ref\nACGT\n")
     p = run("-pf3", "-s", "-W", "100", "-rref", "-i", str(a), str(a), "-P", "2", "-y", "m.txt")
     assert p.returncode == 1 and "-y / --methylation_motifs is not available on the GPU path" in p.stderr
-    p = run("-r", "ref", "-a", "x", str(a), str(a))
-    assert p.returncode == 1 and "-a / --add" in p.stderr
+    p = run("-r", "ref", "-a", "x", "-P", "3", str(a), str(a))
+    assert p.returncode == 1 and "-a / --add together with -P" in p.stderr
+    # -a reads the existing matrix before it needs the device: a multi-matrix file is refused as the reference does
+    m = tmp_path / "m.phy"
+    m.write_text("%10d\na.fsa\nb.fsa\t1\n%10d\na.fsa\nb.fsa\t2\n" % (2, 2))
+    p = run("-r", "ref", "-a", str(a), "-i", str(a), "-o", str(m))
+    assert p.returncode == 1 and p.stderr == "Cannot update a multi distance phylip file.\n"
 
 
 def test_integration_stub_is_the_documented_one_and_compiles(tmp_path):
