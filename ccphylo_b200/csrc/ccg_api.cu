@@ -464,6 +464,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 		update_need(ctx);
 		ctx->global_inc = 0;
 		ctx->global_applied = 0;
+		ctx->global_pending = 0;
 		ctx->last_Dn = 0;
 		ctx->last_ntiles = 0;
 		return CCG_OK;
@@ -499,6 +500,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	if(!ctx->present || !ctx->h_rank || !ctx->need || !ctx->have) return CCG_ERR_NOMEM;
 	update_need(ctx);
 	ctx->global_applied = 0;
+	ctx->global_pending = 0;
 	ctx->global_inc = 0;
 	return make_planes_tmap(ctx);
 }
@@ -599,8 +601,10 @@ extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include,
 	}
 	ctx->global_inc = inc;
 	if(global_inc) *global_inc = inc;
-	CK(ctx, ccg_launch_apply_global_mask(ctx));
+	/* the planes are ANDed with it by the first shared-mask run (run_common): until then ccg_list_variants can
+	 * still see where two samples differ outside the mask, which decides the reference's position labels */
 	ctx->global_applied = 1;
+	ctx->global_pending = 1;
 	return CCG_OK;
 }
 
@@ -1214,6 +1218,10 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 		return CCG_ERR_ARG;
 	}
 	CK(ctx, cudaSetDevice(ctx->device));
+	if(mode == 1 && ctx->global_pending) {
+		CK(ctx, ccg_launch_apply_global_mask(ctx));
+		ctx->global_pending = 0;
+	}
 
 	/* compaction map: included samples in input order (fsacmpthrd.c:305-329) */
 	int Dn = 0;
@@ -1392,6 +1400,107 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
 	if(N) CK(ctx, cudaMemcpyAsync(N, ctx->d_out_N, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	return CCG_OK;
+}
+
+/* -V: fsacmpairint (fsacmp.c:685) / fsacmprint (:646) for every compared pair, see k_variants.cu */
+extern "C" int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *include, ccg_variant_fn fn, void *user) {
+	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !fn) return CCG_ERR_ARG;
+	if(ctx->proxi || ctx->world > 1) {
+		set_err(ctx, "variant listing (-V) is not available together with %s", ctx->proxi ? "proximity masking (-P)" : "a rank partition");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	if(pair ? ctx->global_applied : !ctx->global_pending) {
+		set_err(ctx, pair ? "variant listing in pair mode needs a store without a global mask"
+		                  : "variant listing in shared-mask mode runs after ccg_build_global_mask and before ccg_run_global");
+		return CCG_ERR_ARG;
+	}
+	CK(ctx, cudaSetDevice(ctx->device));
+	const int n = ctx->n;
+	int *slot_of = (int *) malloc((size_t) (n ? n : 1) * sizeof(int));
+	if(!slot_of) return CCG_ERR_NOMEM;
+	int Dn = 0;
+	for(int i = 0; i < n; ++i)
+		if(ctx->present[i] && ctx->have[i >> 7] && (!include || include[i])) slot_of[Dn++] = i;
+	if(Dn < 2) { free(slot_of); return CCG_OK; }
+	const long long cells = (long long) Dn * (Dn - 1) / 2;
+	const int BATCH = 1 << 18;                       /* cells per count pass */
+	const size_t CAP = (size_t) 1 << 24;             /* entries per write pass (128 MiB) */
+	int *d_slot = 0;
+	unsigned *d_counts = 0, *h_counts = 0;
+	unsigned long long *d_off = 0, *h_off = 0, *d_ent = 0, *h_ent = 0;
+	int rc = CCG_OK;
+	cudaError_t e = cudaMalloc(&d_slot, (size_t) Dn * sizeof(int));
+	if(e == cudaSuccess) e = cudaMalloc(&d_counts, (size_t) BATCH * sizeof(unsigned));
+	if(e == cudaSuccess) e = cudaMalloc(&d_off, (size_t) (BATCH + 1) * sizeof(unsigned long long));
+	if(e == cudaSuccess) e = cudaMalloc(&d_ent, CAP * sizeof(unsigned long long));
+	if(e == cudaSuccess) e = cudaMallocHost(&h_ent, CAP * sizeof(unsigned long long));
+	h_counts = (unsigned *) malloc((size_t) BATCH * sizeof(unsigned));
+	h_off = (unsigned long long *) malloc((size_t) (BATCH + 1) * sizeof(unsigned long long));
+	if(e == cudaSuccess && (!h_counts || !h_off)) rc = CCG_ERR_NOMEM;
+	if(e == cudaSuccess && !rc) e = cudaMemcpyAsync(d_slot, slot_of, (size_t) Dn * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+	for(long long c0 = 0; c0 < cells && e == cudaSuccess && !rc; c0 += BATCH) {
+		const int nb = (int) (cells - c0 < BATCH ? cells - c0 : BATCH);
+		VariantParams p;
+		memset(&p, 0, sizeof(p));
+		p.ncells = nb;
+		p.cell0 = c0;
+		p.slot_of_rank = d_slot;
+		p.counts = d_counts;
+		e = ccg_launch_variants(ctx, p, 0, !pair);
+		if(e == cudaSuccess) e = cudaMemcpyAsync(h_counts, d_counts, (size_t) nb * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+		if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		if(e != cudaSuccess) break;
+		h_off[0] = 0;
+		for(int k = 0; k < nb; ++k) h_off[k + 1] = h_off[k] + h_counts[k];
+		e = cudaMemcpyAsync(d_off, h_off, (size_t) (nb + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream);
+		/* write passes over runs of cells whose lists fit the entry buffer */
+		int k0 = 0;
+		while(k0 < nb && e == cudaSuccess && !rc) {
+			int k1 = k0;
+			while(k1 < nb && h_off[k1 + 1] - h_off[k0] <= CAP) ++k1;
+			if(k1 == k0) {
+				set_err(ctx, "one pair has %u variants: more than the %zu the listing buffer holds", h_counts[k0], CAP);
+				rc = CCG_ERR_NOMEM;
+				break;
+			}
+			const size_t nent = (size_t) (h_off[k1] - h_off[k0]);
+			if(nent) {
+				p.ncells = k1 - k0;
+				p.cell0 = c0 + k0;
+				p.offsets = d_off + k0;
+				p.entries = d_ent;
+				e = ccg_launch_variants(ctx, p, 1, !pair);
+				if(e == cudaSuccess) e = cudaMemcpyAsync(h_ent, d_ent, nent * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+				if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+				if(e != cudaSuccess) break;
+				/* hand the lists out pair by pair, rows ascending, columns ascending: the reference's -t 1 order */
+				long long cell = c0 + k0;
+				long long r = (long long) ((1.0 + sqrt(1.0 + 8.0 * (double) cell)) * 0.5);
+				while(r * (r - 1) / 2 > cell) --r;
+				while((r + 1) * r / 2 <= cell) ++r;
+				long long c = cell - r * (r - 1) / 2;
+				for(int k = k0; k < k1 && !rc; ++k) {
+					if(h_counts[k] && fn(user, slot_of[r], slot_of[c], (const uint64_t *) (h_ent + (h_off[k] - h_off[k0])), h_counts[k]))
+						rc = CCG_ERR_ARG;
+					if(++c == r) { ++r; c = 0; }
+				}
+			}
+			k0 = k1;
+		}
+	}
+	if(e != cudaSuccess) {
+		set_err(ctx, "variant listing failed: %s", cudaGetErrorString(e));
+		rc = CCG_ERR_CUDA;
+	}
+	cudaFree(d_slot);
+	cudaFree(d_counts);
+	cudaFree(d_off);
+	cudaFree(d_ent);
+	cudaFreeHost(h_ent);
+	free(h_counts);
+	free(h_off);
+	free(slot_of);
+	return rc;
 }
 
 extern "C" int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc) {

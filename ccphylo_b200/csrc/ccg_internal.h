@@ -70,6 +70,15 @@ struct ProxiParams {
 	EpilogueParams ep;
 };
 
+struct VariantParams {
+	int ncells;                         /* cells of this batch */
+	long long cell0;                    /* first packed cell (over included samples) */
+	const int *slot_of_rank;            /* device: compact index -> slot */
+	unsigned *counts;                   /* count pass: variants per cell */
+	const unsigned long long *offsets;  /* write pass: running offsets of the batch's cells (offsets[0] = base) */
+	unsigned long long *entries;        /* write pass: label << 4 | code_i << 2 | code_j */
+};
+
 struct UmmaParams {
 	int ntiles;            /* macro tiles owned by this rank */
 	const int2 *tiles;     /* device: (tm, tn) */
@@ -110,7 +119,9 @@ struct ccg_ctx {
 	size_t planes_bytes;
 	uint32_t *d_gmask;         /* shared-mask mode: [words] */
 	unsigned global_inc;
-	int global_applied;        /* pair-mode store whose planes were ANDed with a global mask */
+	int global_applied;        /* pair-mode store with a global mask (ccg_apply_global_mask / ccg_build_global_mask) */
+	int global_pending;        /* ... built on the device but not yet ANDed into the planes (done by the first shared-mask run;
+	                            * ccg_list_variants needs the unmasked code planes) */
 	unsigned *d_inc;           /* [n_pad] per-slot included counts */
 	unsigned char *present;    /* host [n_pad]: slot holds a sample of the current problem */
 	unsigned char *need;       /* host [n_pad/128]: row block touched by a macro tile this rank owns */
@@ -218,6 +229,9 @@ cudaError_t ccg_launch_sample_proxi(ccg_ctx *ctx, int vs_ref, int ref_slot, cons
                                     unsigned *d_cleared);
 cudaError_t ccg_launch_count_mask(ccg_ctx *ctx, unsigned *d_count);
 cudaError_t ccg_launch_pair_proxi(ccg_ctx *ctx, const ProxiParams &p);
+
+/* k_variants.cu */
+cudaError_t ccg_launch_variants(ccg_ctx *ctx, const VariantParams &p, int write, int shared_mask);
 
 /* k_matdist.cu */
 void ccg_mat_free(ccg_ctx *ctx);

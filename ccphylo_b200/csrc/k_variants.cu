@@ -1,0 +1,93 @@
+/*
+ * k_variants.cu -- -V / --nucleotide_variations: the per-pair variant lists the reference prints while it
+ * compares (fsacmpairint fsacmp.c:685-737 in pair mode, fsacmprint :646-683 in shared-mask mode, printDiff
+ * :635-644), extracted on the device from the resident bit planes.
+ *
+ * The list of a pair is ordered along the alignment and its position labels come from a running counter (see
+ * below), so one thread walks one pair from the first to the last word; the parallelism is over pairs.  A batch
+ * is a run of consecutive cells of the packed lower triangle: consecutive cells share their row sample and have
+ * consecutive column samples, so the lanes of a warp read neighbouring 16-byte plane words (the column) and one
+ * broadcast word (the row).  Two passes over a batch: count, (host: prefix sum), write.  HBM-bound on the plane
+ * reads: 2 x 48 B per pair and 128 bases.
+ *
+ * Labels, as the reference produces them (not alignment coordinates): a counter starts at 1; a
+ * word is "walked" when its mask word is non-zero and the two packed words differ anywhere; in a walked word lane
+ * k (counted from the LEAST significant end: base 31 - k of the word, plane / mask bit k) is labelled counter + k
+ * and the counter then advances by (index of the highest set mask bit + 1); any other word advances it by 32.
+ */
+#include "ccg_internal.h"
+
+namespace {
+
+__device__ __forceinline__ void cell_to_pair(long long cell, int &r, int &c) {
+	/* cell = r (r - 1) / 2 + c, 0 <= c < r */
+	long long rr = (long long) ((1.0 + sqrt(1.0 + 8.0 * (double) cell)) * 0.5);
+	while(rr * (rr - 1) / 2 > cell) --rr;
+	while((rr + 1) * rr / 2 <= cell) ++rr;
+	r = (int) rr;
+	c = (int) (cell - rr * (rr - 1) / 2);
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_variants(const uint32_t *__restrict__ planes, int n_pad, int chunks, int words, const uint32_t *__restrict__ gmask,
+           VariantParams p) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= p.ncells) return;
+	int r, c;
+	cell_to_pair(p.cell0 + t, r, c);
+	const int i = p.slot_of_rank[r], j = p.slot_of_rank[c];
+	const uint4 *P = reinterpret_cast<const uint4 *>(planes);
+	unsigned label = 1, count = 0;
+	unsigned long long *out = WRITE ? p.entries + (p.offsets[t] - p.offsets[0]) : 0;
+#pragma unroll 1
+	for(int ch = 0; ch < chunks; ++ch) {
+		const size_t row = (size_t) ch * 3;
+		const uint4 ih = __ldg(P + (row + 0) * n_pad + i), il = __ldg(P + (row + 1) * n_pad + i);
+		const uint4 jh = __ldg(P + (row + 0) * n_pad + j), jl = __ldg(P + (row + 1) * n_pad + j);
+		uint4 m;
+		if(gmask) {
+			const int w0 = ch * CCG_CHUNK_WORDS;
+			m.x = w0 < words ? __ldg(gmask + w0) : 0u;
+			m.y = w0 + 1 < words ? __ldg(gmask + w0 + 1) : 0u;
+			m.z = w0 + 2 < words ? __ldg(gmask + w0 + 2) : 0u;
+			m.w = w0 + 3 < words ? __ldg(gmask + w0 + 3) : 0u;
+		} else {
+			const uint4 im = __ldg(P + (row + 2) * n_pad + i), jm = __ldg(P + (row + 2) * n_pad + j);
+			m = make_uint4(im.x & jm.x, im.y & jm.y, im.z & jm.z, im.w & jm.w);
+		}
+#define CCG_V_WORD(f)                                                                          \
+	{                                                                                          \
+		const uint32_t inc = m.f;                                                              \
+		const uint32_t dh = ih.f ^ jh.f, dl = il.f ^ jl.f;                                     \
+		if(inc && (dh | dl)) {                                                                 \
+			uint32_t snp = (dh | dl) & inc;                                                    \
+			if(WRITE) {                                                                        \
+				while(snp) {                                                                   \
+					const int k = __ffs((int) snp) - 1;                                        \
+					snp &= snp - 1u;                                                           \
+					const unsigned ci = ((ih.f >> k) & 1u) << 1 | ((il.f >> k) & 1u);          \
+					const unsigned cj = ((jh.f >> k) & 1u) << 1 | ((jl.f >> k) & 1u);          \
+					out[count++] = ((unsigned long long) (label + (unsigned) k) << 4) | (ci << 2) | cj; \
+				}                                                                              \
+			} else count += (unsigned) __popc(snp);                                            \
+			label += 32u - (unsigned) __clz((int) inc);                                        \
+		} else label += 32u;                                                                   \
+	}
+		CCG_V_WORD(x) CCG_V_WORD(y) CCG_V_WORD(z) CCG_V_WORD(w)
+#undef CCG_V_WORD
+	}
+	if(!WRITE) p.counts[t] = count;
+}
+
+} // namespace
+
+cudaError_t ccg_launch_variants(ccg_ctx *ctx, const VariantParams &p, int write, int shared_mask) {
+	if(p.ncells <= 0) return cudaSuccess;
+	const unsigned blocks = (unsigned) ((p.ncells + 127) / 128);
+	const uint32_t *g = shared_mask ? ctx->d_gmask : 0;
+	if(write) k_variants<true><<<blocks, 128, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks, ctx->words, g, p);
+	else k_variants<false><<<blocks, 128, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks, ctx->words, g, p);
+	ctx->launches++;
+	return cudaGetLastError();
+}

@@ -13,7 +13,9 @@
  *   - -P (proximity) runs on the device too: the per-sample builder right after the upload
  *     (ccg_sample_proximity), the per-pair maskProxi inside the compare (ccg_run_pair), the
  *     shared-mask variant in ccg_build_global_mask;
- *   - -V (variant listing), -y (motif masking), -a (row append) are refused.
+ *   - -V (variant listing) comes from the device as well (ccg_list_variants, same labels as the reference);
+ *     -a appends one row to an existing matrix (ccg_run_row / ccg_mat_run_row);
+ *   - -y (motif masking) is refused, and so are -V with -P or -a, and -a with -P.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -151,6 +153,18 @@ static unsigned candidate_count(const DistOpts *o, ccg_ctx *ctx, int slot, const
 	return inc;
 }
 
+/* -V: where fsaCmpThreadOut's `diffile` lines go (dist.c:85-95); NULL without -V */
+static FILE *g_diffile = 0;
+
+/* printDiff (fsacmp.c:635-644) for one pair's list from ccg_list_variants */
+static int print_variants(void *user, int sample_i, int sample_j, const uint64_t *variants, size_t count) {
+	FILE *f = (FILE *) user;
+	for(size_t k = 0; k < count; ++k)
+		fprintf(f, "(%d, %d)\t%c%d%c\n", sample_i, sample_j, "ACGT"[(variants[k] >> 2) & 3], (int) (variants[k] >> 4),
+		        "ACGT"[variants[k] & 3]);
+	return 0;
+}
+
 /* shared tail of the two FASTA modes: compare on the device and print (cdist.c:170-192, dist.c:174-180) */
 static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, unsigned minLength, unsigned char *include,
                              int included, char **names, const char *comment, FILE *outfile, FILE *noutfile, int n_into_out) {
@@ -167,6 +181,10 @@ static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, un
 	int Dn = 0, rc;
 	const double t_cmp = now_s();
 	if(pair) {
+		if(g_diffile) {
+			rc = ccg_list_variants(ctx, 1, include, print_variants, g_diffile);
+			if(rc) die_gpu(ctx, rc);
+		}
 		/* minLength was already maxed with minCov * len; the library repeats that (fsacmpthrd.c:292) */
 		rc = ccg_run_pair(ctx, include, o->norm, minLength, o->minCov, o->elem_size, o->byteScale, D, N, &Dn);
 		if(rc) die_gpu(ctx, rc);
@@ -175,6 +193,10 @@ static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, un
 		rc = ccg_build_global_mask(ctx, include, &ginc);
 		if(rc) die_gpu(ctx, rc);
 		fprintf(stderr, "# %d / %d bases included in distance matrix.\n", (int) ginc, len);
+		if(g_diffile) {
+			rc = ccg_list_variants(ctx, 0, include, print_variants, g_diffile);
+			if(rc) die_gpu(ctx, rc);
+		}
 		rc = ccg_run_global(ctx, include, o->norm, o->elem_size, o->byteScale, D, &Dn, &ginc);
 		if(rc) die_gpu(ctx, rc);
 	}
@@ -727,6 +749,10 @@ static void make_matrix(DistOpts *o) {
 		if(strcmp(o->noutputfilename, o->outputfilename) == 0) noutfile = outfile;
 		else noutfile = open_out(o->noutputfilename);
 	}
+	if(o->diffilename) {
+		if(strcmp(o->diffilename, o->outputfilename) == 0) g_diffile = outfile;
+		else g_diffile = open_out(o->diffilename);
+	}
 	int informat;
 	if(o->flag & 16) informat = '>';
 	else if(o->numFile) {
@@ -755,6 +781,7 @@ static void make_matrix(DistOpts *o) {
 		fprintf(stderr, "Invalid argument combination.\n");
 		exit(1);
 	}
+	if(g_diffile && g_diffile != outfile && g_diffile != stdout) fclose(g_diffile);
 	if(outfile != stdout) fclose(outfile);
 	else fflush(stdout);
 	if(noutfile && noutfile != outfile && noutfile != stdout) fclose(noutfile);
@@ -771,7 +798,7 @@ static int help_message(FILE *out) {
 		{'S', "separator", "Separator", "\\t"},
 		{'x', "print_precision", "Floating point print precision", "9"},
 		{'y', "methylation_motifs", "Mask methylation motifs from <file> (not on the GPU path)", "False/None"},
-		{'V', "nucleotide_variations", "Output nucleotide variations (not on the GPU path)", "False/None"},
+		{'V', "nucleotide_variations", "Output nucleotide variations", "False/None"},
 		{'r', "reference", "Target reference", "None"},
 		{'a', "add", "Add file to existing matrix", ""},
 		{'E', "min_depth", "Minimum depth", "15"},
@@ -901,9 +928,11 @@ int main_dist(int argc, char **argv) {
 	if(dist_mat_parse_method(&o)) die_invalid(o.method_err);
 	if(!o.numFile && o.targetTemplate) o.numFile = 1;
 
-	if(o.diffilename || o.methfilename) {
+	if(o.methfilename || (o.diffilename && (o.proxi || o.addfilename))) {
 		fprintf(stderr, "%s is not available on the GPU path of dist (use the CPU ccphylo for it).\n",
-		        o.diffilename ? "-V / --nucleotide_variations" : "-y / --methylation_motifs");
+		        o.methfilename ? "-y / --methylation_motifs" :
+		        o.proxi ? "-V / --nucleotide_variations together with -P / --proximity" :
+		                  "-V / --nucleotide_variations together with -a / --add");
 		return 1;
 	}
 	if(o.addfilename && o.filenames) return add_to_matrix(&o);

@@ -202,6 +202,18 @@ int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include,
 int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned minLength, double minCov,
                 double *D, double *N, int *cols);
 
+/* -V / --nucleotide_variations: what fsaCmpThreadOut prints into `diffile` while it compares --
+ * fsacmpairint (fsacmp.c:685-737, pair != 0) or fsacmprint (:646-683, shared mask), one
+ * "(i, j)\t<base_i><label><base_j>" line per variant (printDiff :635-644).  fn is called once
+ * per compared pair that has variants, rows ascending and columns ascending within a row (the
+ * order of the reference run with -t 1): sample_i > sample_j are slot numbers,
+ * variants[k] = label << 4 | code_i << 2 | code_j (codes 0..3 = ACGT; label is the reference's
+ * running position counter, see csrc/k_variants.cu).  A non-zero return of fn stops the listing.
+ * Pair mode: a pair-mode store as ccg_run_pair takes it.  Shared-mask mode: after
+ * ccg_build_global_mask and BEFORE ccg_run_global.  Not with -P. */
+typedef int (*ccg_variant_fn)(void *user, int sample_i, int sample_j, const uint64_t *variants, size_t count);
+int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *include, ccg_variant_fn fn, void *user);
+
 /* Raw integer results of the last pair-mode run for included samples:
  * mismatch counts and inclusion counts as u32, same packed layout.  HOST
  * buffers; either may be NULL. */

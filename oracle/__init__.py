@@ -60,6 +60,8 @@ def lib():
         L.orc_fsa_cmp_pair_proxi.restype = C.c_int
         L.orc_fsa_cmp_pair_proxi.argtypes = [C.c_int, C.c_int, _u64p, C.c_long, _u8p, _u32p, C.c_uint, C.c_uint,
                                              C.c_double, C.c_uint, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_list_variants.restype = C.c_long
+        L.orc_list_variants.argtypes = [_u64p, _u64p, _u32p, C.c_int, C.c_void_p, C.c_long]
         L.orc_mask_count.restype = C.c_int
         L.orc_mask_count.argtypes = [_u32p, C.c_int]
         L.orc_raw_pair_matrix.restype = None
@@ -230,6 +232,20 @@ def fsa_cmp_row(seqs, masks, row, length, norm=0, min_length=1, min_cov=0.5):
     return D, N
 
 
+def list_variants(seq_i, seq_j, mask, length):
+    """-V: [(label, code_i, code_j), ...] of one pair under `mask`, as fsacmpairint / fsacmprint print them."""
+    seq_i, seq_j, mask = np.ascontiguousarray(seq_i), np.ascontiguousarray(seq_j), np.ascontiguousarray(mask)
+    k = lib().orc_list_variants(seq_i, seq_j, mask, length, None, 0)
+    out = np.zeros(max(k, 1), dtype=np.uint64)
+    lib().orc_list_variants(seq_i, seq_j, mask, length, out.ctypes.data, k)
+    return [(int(v >> 4), int((v >> 2) & 3), int(v & 3)) for v in out[:k]]
+
+
+def variant_text(si, sj, variants):
+    """printDiff (fsacmp.c:635-644)"""
+    return "".join("(%d, %d)\t%c%d%c\n" % (si, sj, "ACGT"[a], pos, "ACGT"[b]) for pos, a, b in variants)
+
+
 def raw_pair_matrix(seqs, masks, length, nthreads=8):
     n, W = seqs.shape
     mism = np.zeros(max(cells(n), 1), dtype=np.uint32)
@@ -283,6 +299,8 @@ def ref():
         R.refshim_and_known.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint]
         R.refshim_inc_pos.restype = None
         R.refshim_inc_pos.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint, C.c_uint]
+        R.refshim_variants.restype = C.c_uint64
+        R.refshim_variants.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _u64p, _u32p, C.c_int, C.c_char_p, C.c_long]
         R.refshim_pair.restype = C.c_uint64
         R.refshim_pair.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint]
         R.refshim_fsa_cmp.restype = C.c_int
@@ -325,6 +343,20 @@ def ref_pair(seq_i, seq_j, inc_i, inc_j, length, proxi=0):
     r = ref().refshim_pair(pad(seq_i, np.uint64), pad(seq_j, np.uint64), pad(inc_i, np.uint32), pad(inc_j, np.uint32),
                            length, proxi)
     return int(r >> 32), int(r & 0xFFFFFFFF)
+
+
+def ref_variants(pair, si, sj, seq_i, seq_j, mask, length):
+    """the text the reference's fsacmpairint (pair) / fsacmprint prints for one pair, and its return value"""
+    W = words(length)
+
+    def pad(a, dt):
+        b = np.zeros(W + 2, dtype=dt)
+        b[:W] = a
+        return b
+    buf = C.create_string_buffer(64 * (length + 1))
+    r = ref().refshim_variants(1 if pair else 0, si, sj, pad(seq_i, np.uint64), pad(seq_j, np.uint64), pad(mask, np.uint32),
+                               length, buf, len(buf))
+    return buf.value.decode(), int(r)
 
 
 def ref_fsa_cmp(seqs, masks, include, length, pair=True, tnum=1, norm=0, min_length=1, min_cov=0.5, proxi=0,

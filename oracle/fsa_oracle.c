@@ -145,6 +145,39 @@ uint32_t orc_masked_mism(const uint64_t *seq_i, const uint64_t *seq_j,
 }
 
 /* ------------------------------------------------------------------ */
+/* -V variant listing                                                  */
+/* ------------------------------------------------------------------ */
+/* (reference fsacmp.c:646-683 fsacmprint, :685-737 fsacmpairint, printDiff :635-644)
+ * The reference walks a word only when the mask word is non-zero and the two packed words differ (anywhere,
+ * masked or not); it then reads lanes from the LEAST significant end -- lane k is base 31 - k of the word --
+ * while labelling them pos, pos + 1, ... from a counter that starts at 1, and it stops at the highest set mask
+ * bit, so the counter advances by (index of that bit + 1) for a walked word and by 32 for every other word.
+ * The printed positions are therefore not alignment coordinates; they are reproduced as
+ * they are. */
+long orc_list_variants(const uint64_t *seq_i, const uint64_t *seq_j, const uint32_t *mask, int len,
+                       uint64_t *out, long cap) {
+	int w, W = orc_words(len);
+	unsigned label = 1;
+	long count = 0;
+
+	for(w = 0; w < W; ++w) {
+		const uint32_t inc = mask[w];
+		if(inc && seq_i[w] != seq_j[w]) {
+			int k;
+			for(k = 0; k < 32 && (inc >> k) != 0; ++k) {
+				const unsigned ci = (unsigned) (seq_i[w] >> (2 * k)) & 3, cj = (unsigned) (seq_j[w] >> (2 * k)) & 3;
+				if(((inc >> k) & 1) && ci != cj) {
+					if(out && count < cap) out[count] = ((uint64_t) (label + (unsigned) k) << 4) | (ci << 2) | cj;
+					++count;
+				}
+			}
+			label += (unsigned) k;
+		} else label += 32;
+	}
+	return count;
+}
+
+/* ------------------------------------------------------------------ */
 /* -P proximity masking                                                */
 /* ------------------------------------------------------------------ */
 static inline void clear_range(uint32_t *mask, long lo, long hi, int len) {

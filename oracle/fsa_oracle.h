@@ -67,6 +67,12 @@ void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j,
                            const uint32_t *inc_i, const uint32_t *inc_j, int len,
                            unsigned proxi, uint32_t *mism, uint32_t *ninc);
 
+/* fsacmp.c:646-683 fsacmprint / :685-737 fsacmpairint (-V): the variants of one pair under `mask` (pair mode: the
+ * pair's mask; shared-mask mode: the global mask) in the order and with the position labels the reference
+ * prints.  out[k] = label << 4 | code_i << 2 | code_j; returns how many there are (out may be NULL / cap 0). */
+long orc_list_variants(const uint64_t *seq_i, const uint64_t *seq_j, const uint32_t *mask, int len,
+                       uint64_t *out, long cap);
+
 /* fsacmp.c:552-585 fsacmp: mismatches under one shared mask. */
 uint32_t orc_masked_mism(const uint64_t *seq_i, const uint64_t *seq_j,
                          const uint32_t *mask, int len);

@@ -84,6 +84,27 @@ uint64_t refshim_pair(uint64_t *seq_i, uint64_t *seq_j, uint32_t *inc_i,
 	return r;
 }
 
+/* -V: the lines fsacmpairint (pair != 0, fsacmp.c:685) / fsacmprint (fsacmp.c:646) print for one pair under `mask`,
+ * as text into buf (capacity cap, 0-terminated); returns the function's own return value. */
+#define _GNU_SOURCE
+#include <stdio.h>
+FILE *open_memstream(char **ptr, size_t *sizeloc);
+uint64_t refshim_variants(int pair, int si, int sj, uint64_t *seq_i, uint64_t *seq_j, uint32_t *mask, int len, char *buf,
+                          long cap) {
+	char *text = 0;
+	size_t size = 0;
+	FILE *f = open_memstream(&text, &size);
+	uint64_t r;
+	if(pair) r = fsacmpairint(f, si, sj, (long unsigned *) seq_i, (long unsigned *) seq_j, mask, len);
+	else r = fsacmprint(f, si, sj, (long unsigned *) seq_i, (long unsigned *) seq_j, mask, len);
+	fclose(f);
+	if((long) size >= cap) size = (size_t) cap - 1;
+	memcpy(buf, text, size);
+	buf[size] = 0;
+	free(text);
+	return r;
+}
+
 /* The drop-in boundary itself: fsaCmpThreadOut (fsacmpthrd.c:76), called the
  * way cdist.c:181 / :184 call it.  seqs is n x wstride u64, masks n x wstride
  * u32 (pair) or 1 x wstride (global).  D / N receive Dn(Dn-1)/2 packed cells

@@ -172,3 +172,26 @@ def test_pair_mode_with_proximity_matches_reference(built, elem, scale, proxi):
         assert dnr == dno
         assert np.array_equal(Dr.view(np.uint8), Do.view(np.uint8))
         assert np.array_equal(Nr.view(np.uint8), No.view(np.uint8))
+
+
+# ---------------------------------------------------------------------------------------------
+# -V variant listing (fsacmp.c:635-737)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("length", [1, 31, 32, 33, 64, 97, 1500, 4099])
+def test_variant_listing_matches_reference(built, length):
+    codes = synth.make_codes(5, length, seed=length, snp=0.05, nrun=0.05, lower=0.03, gap=0.01)
+    seqs, masks, _ = oracle.encode_samples(codes)
+    gmask = oracle.global_mask(codes, np.ones(5, np.uint8))
+    total = 0
+    for i in range(1, 5):
+        for j in range(i):
+            pm = masks[i] & masks[j]
+            text, r = oracle.ref_variants(True, i, j, seqs[i], seqs[j], pm, length)
+            got = oracle.list_variants(seqs[i], seqs[j], pm, length)
+            assert oracle.variant_text(i, j, got) == text
+            assert (r >> 32) == len(got)
+            total += len(got)
+            text, r = oracle.ref_variants(False, i, j, seqs[i], seqs[j], gmask, length)
+            got = oracle.list_variants(seqs[i], seqs[j], gmask, length)
+            assert oracle.variant_text(i, j, got) == text and r == len(got)
+    assert total > 0 or length < 31
