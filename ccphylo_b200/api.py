@@ -28,7 +28,7 @@ EXPORTS = [
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
-    "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants",
+    "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs",
 ]
 
 MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "ln", "nl1", "nl2",
@@ -97,6 +97,8 @@ def load():
     L.ccg_put_samples_packed_dev.argtypes = [vp, i, i, vp, vp, C.c_long]
     L.ccg_put_sample_codes.argtypes = [vp, i, vp]
     L.ccg_get_inc_counts.argtypes = [vp, vp]
+    L.ccg_set_motifs.argtypes = [vp, i, vp, vp]
+    L.ccg_mask_motifs.argtypes = [vp, i, i, vp]
     L.ccg_set_proximity.argtypes = [vp, u, i]
     L.ccg_sample_proximity.argtypes = [vp, i, i, i, vp]
     L.ccg_run_pair.argtypes = [vp, vp, u, u, d, i, d, vp, vp, C.POINTER(i)]
@@ -254,6 +256,20 @@ class Context:
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         assert codes.size == self.len
         self._ck(self._L.ccg_put_sample_codes(self._h, idx, codes.ctypes.data))
+
+    def set_motifs(self, motifs):
+        """-y: motifs = [[set | 16 * methylated, ...], ...] as getMethMotifs builds them (motif, reverse complement, ...)."""
+        lens = np.array([len(m) for m in motifs], dtype=np.int32)
+        sets = np.array([v for m in motifs for v in m], dtype=np.uint8)
+        self._ck(self._L.ccg_set_motifs(self._h, len(motifs), lens.ctypes.data if len(motifs) else None,
+                                        sets.ctypes.data if len(motifs) else None))
+
+    def mask_motifs(self, first=0, count=None):
+        """maskMotifs (meth.c:141) on slots [first, first+count) -> their included counts afterwards."""
+        count = self.n - first if count is None else count
+        out = np.zeros(max(count, 1), dtype=np.uint32)
+        self._ck(self._L.ccg_mask_motifs(self._h, first, count, out.ctypes.data))
+        return out[:count]
 
     def sample_proximity(self, first=0, count=None, apply=True):
         """getIncPosPtr(includes[i], seq, seq, proxi) of cdist.c:91 on slots [first, first+count) -> their counts."""

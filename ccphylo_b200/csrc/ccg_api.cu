@@ -143,6 +143,8 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	free_problem(ctx);
 	ccg_mat_free(ctx);
 	cudaFree(ctx->d_stage);
+	cudaFree(ctx->d_motif_lens);
+	cudaFree(ctx->d_motif_sets);
 	cudaFree(ctx->d_acc);
 	cudaFree(ctx->d_tickets);
 	cudaFree(ctx->d_tiles);
@@ -605,6 +607,53 @@ extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include,
 	 * still see where two samples differ outside the mask, which decides the reference's position labels */
 	ctx->global_applied = 1;
 	ctx->global_pending = 1;
+	return CCG_OK;
+}
+
+/* -y: the motif list of getMethMotifs (methparse.c:268) */
+extern "C" int ccg_set_motifs(ccg_ctx *ctx, int nmotifs, const int *lens, const unsigned char *sets) {
+	if(!ctx || nmotifs < 0 || (nmotifs && (!lens || !sets))) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(ctx->d_motif_lens); ctx->d_motif_lens = 0;
+	cudaFree(ctx->d_motif_sets); ctx->d_motif_sets = 0;
+	ctx->motif_n = ctx->motif_nsets = 0;
+	if(nmotifs == 0) return CCG_OK;
+	int total = 0;
+	for(int m = 0; m < nmotifs; ++m) {
+		if(lens[m] < 1 || lens[m] > 32) {
+			set_err(ctx, "motif %d has %d positions: 1 .. 32 are supported", m, lens[m]);
+			return CCG_ERR_UNSUPPORTED;
+		}
+		total += lens[m];
+	}
+	if((size_t) nmotifs * sizeof(int) + (size_t) total > 40000) {
+		set_err(ctx, "%d motifs with %d positions do not fit the kernel's shared memory", nmotifs, total);
+		return CCG_ERR_UNSUPPORTED;
+	}
+	CK(ctx, cudaMalloc(&ctx->d_motif_lens, (size_t) nmotifs * sizeof(int)));
+	CK(ctx, cudaMalloc(&ctx->d_motif_sets, (size_t) total));
+	CK(ctx, cudaMemcpy(ctx->d_motif_lens, lens, (size_t) nmotifs * sizeof(int), cudaMemcpyHostToDevice));
+	CK(ctx, cudaMemcpy(ctx->d_motif_sets, sets, (size_t) total, cudaMemcpyHostToDevice));
+	ctx->motif_n = nmotifs;
+	ctx->motif_nsets = total;
+	return CCG_OK;
+}
+
+/* maskMotifs (meth.c:141) on the uploaded slots [first, first + count) */
+extern "C" int ccg_mask_motifs(ccg_ctx *ctx, int first, int count, unsigned *inc_out) {
+	if(!ctx || !ctx->d_planes || !ctx->pair_mode || first < 0 || count < 0 || first + count > ctx->n) return CCG_ERR_ARG;
+	if(count == 0) return CCG_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	if(ctx->motif_n && ctx->words > 0) {
+		int rc = ensure_stage(ctx, (size_t) count * sizeof(unsigned) + 64);
+		if(rc) return rc;
+		unsigned *d_removed = (unsigned *) ctx->d_stage;
+		CK(ctx, cudaMemsetAsync(d_removed, 0, (size_t) count * sizeof(unsigned), ctx->stream));
+		CK(ctx, ccg_launch_motif_mask(ctx, first, count, d_removed));
+	}
+	if(inc_out) CK(ctx, cudaMemcpyAsync(inc_out, ctx->d_inc + first, (size_t) count * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	return CCG_OK;
 }
 

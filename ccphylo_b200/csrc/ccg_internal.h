@@ -109,6 +109,9 @@ struct ccg_ctx {
 	int use_i8;                     /* CCG_I8=1: int8 operands (kind::i8) instead of the default e2m1 panel (kind::mxf4) */
 	int dbg_kslices, dbg_serial, dbg_nolock, dbg_umma1;   /* CCG_KSLICES / CCG_EXPAND_SERIAL / CCG_NOLOCK / CCG_UMMA1 overrides (experiments only) */
 
+	int motif_n, motif_nsets;       /* -y: motifs (with their reverse complements) set by ccg_set_motifs */
+	int *d_motif_lens;
+	unsigned char *d_motif_sets;
 	int row_slot1;                  /* ccg_run_row: 1 + the slot whose row is being computed, 0 otherwise */
 	unsigned proxi;                 /* -P: minimum distance between SNPs (0 = no proximity masking), ccg_set_proximity */
 	int proxi_snp_only;             /* events of the per-sample builder: 0 getIncPos, 1 getIncPosInsig / getIncPosInsigPrune */
@@ -229,6 +232,9 @@ cudaError_t ccg_launch_sample_proxi(ccg_ctx *ctx, int vs_ref, int ref_slot, cons
                                     unsigned *d_cleared);
 cudaError_t ccg_launch_count_mask(ccg_ctx *ctx, unsigned *d_count);
 cudaError_t ccg_launch_pair_proxi(ccg_ctx *ctx, const ProxiParams &p);
+
+/* k_motif.cu */
+cudaError_t ccg_launch_motif_mask(ccg_ctx *ctx, int first, int count, unsigned *d_removed);
 
 /* k_variants.cu */
 cudaError_t ccg_launch_variants(ccg_ctx *ctx, const VariantParams &p, int write, int shared_mask);

@@ -15,7 +15,8 @@
  *     shared-mask variant in ccg_build_global_mask;
  *   - -V (variant listing) comes from the device as well (ccg_list_variants, same labels as the reference);
  *     -a appends one row to an existing matrix (ccg_run_row / ccg_mat_run_row);
- *   - -y (motif masking) is refused, and so are -V with -P or -a, and -a with -P.
+ *   - -y masks methylation motifs on the device right after each upload (ccg_mask_motifs);
+ *   - refused: the combinations -V with -P, -a or -y; -y with -P; -a with -P.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -28,6 +29,7 @@
 #include "cmdline.h"
 #include "dist_opts.h"
 #include "fsa_reader.h"
+#include "motifs.h"
 #include "ordered_pool.h"
 #include "phy_writer.h"
 
@@ -131,25 +133,39 @@ static void parse_one(int job, void *state, void *user) {
 	fsa_close(fr);
 }
 
+/* -y: motifs loaded by make_matrix (dist.c:127-131); n == 0 without -y */
+static MotifList g_motifs;
+
+/* one sample into its slot: the device packs it, builds its mask and -- with -y -- takes the methylation sites
+ * of every motif match out of it (maskMotifs, cdist.c:90,109,137) */
+static void upload_sample(ccg_ctx *ctx, int slot, const ByteBuf *codes, unsigned *inc) {
+	int rc = ccg_put_sample_codes(ctx, slot, codes->data);
+	/* the staging copy is asynchronous and the parser's buffer is about to be reused */
+	if(!rc) rc = ccg_sync(ctx);
+	if(!rc && (g_motifs.n || inc)) rc = ccg_mask_motifs(ctx, slot, 1, inc);
+	if(rc) die_gpu(ctx, rc);
+}
+
 /* The count the inclusion test of cdist.c:91-100 / :138-147 looks at, for a candidate whose codes are in r.
- * Without -P it is the number of known bases, which the parser thread has counted.  With -P and the event
- * definition of getIncPos (fsacmp.c:181: not -f 8 / -f 32) the bases between two unknown positions at most
- * proxi apart go as well; the device applies (pair mode) or just counts (the shared-mask reference candidate,
- * whose ranges ccg_build_global_mask clears later) that on the freshly uploaded sample.
+ * Plain: the number of known bases, which the parser thread has counted.  With -y the methylation sites of the
+ * motif matches are gone from it, and with -P and the event definition of getIncPos (fsacmp.c:181: not -f 8 /
+ * -f 32) so are the bases between two unknown positions at most proxi apart; the device applies (pair mode) or
+ * just counts (the shared-mask reference candidate, whose ranges ccg_build_global_mask clears later) that on the
+ * freshly uploaded sample.  Later shared-mask samples are gated on their known bases alone (cdist.c:102).
  * *uploaded tells the caller that slot already holds the sample. */
 static unsigned candidate_count(const DistOpts *o, ccg_ctx *ctx, int slot, const ByteBuf *codes, unsigned known, int len,
                                 int pair, int is_ref_candidate, int *uploaded) {
 	*uploaded = 0;
-	if(!o->proxi || (o->flag & (8 | 32)) || len <= 0) return known;
-	if(!pair && !is_ref_candidate) return known;       /* cdist.c:102: len - unknowns */
-	int rc = ccg_put_sample_codes(ctx, slot, codes->data);
-	if(rc) die_gpu(ctx, rc);
-	rc = ccg_sync(ctx);
-	if(rc) die_gpu(ctx, rc);
+	const int proxi_counts = o->proxi && !(o->flag & (8 | 32));
+	if((!proxi_counts && !g_motifs.n) || len <= 0) return known;
+	if(!pair && !is_ref_candidate) return known;
 	unsigned inc = 0;
-	rc = ccg_sample_proximity(ctx, slot, 1, pair, &inc);
-	if(rc) die_gpu(ctx, rc);
+	upload_sample(ctx, slot, codes, &inc);
 	*uploaded = 1;
+	if(proxi_counts) {
+		int rc = ccg_sample_proximity(ctx, slot, 1, pair, &inc);
+		if(rc) die_gpu(ctx, rc);
+	}
 	return inc;
 }
 
@@ -238,6 +254,7 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	int len = 0, have_ref = 0, included = n;
 	const int pair = (o->flag & 2) != 0;
 	rc = ccg_set_proximity(ctx, o->proxi, (o->flag & (8 | 32)) != 0);
+	if(!rc && g_motifs.n) rc = ccg_set_motifs(ctx, g_motifs.n, g_motifs.lens, g_motifs.sets);
 	if(rc) die_gpu(ctx, rc);
 
 	for(int i = 0; i < n; ++i) {
@@ -288,13 +305,7 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 				} else {
 					fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", path, (int) inc, len);
 					have_ref = 1;
-					if(len > 0 && !uploaded) {
-						rc = ccg_put_sample_codes(ctx, i, r->codes.data);
-						if(rc) die_gpu(ctx, rc);
-						/* the staging copy is asynchronous and the ring slot is about to be reused */
-						rc = ccg_sync(ctx);
-						if(rc) die_gpu(ctx, rc);
-					}
+					if(len > 0 && !uploaded) upload_sample(ctx, i, &r->codes, 0);
 				}
 			}
 		}
@@ -409,6 +420,7 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	int rc = ccg_init(&ctx, -1);
 	if(rc) die_gpu(0, rc);
 	rc = ccg_set_proximity(ctx, o->proxi, (o->flag & (8 | 32)) != 0);
+	if(!rc && g_motifs.n) rc = ccg_set_motifs(ctx, g_motifs.n, g_motifs.lens, g_motifs.sets);
 	if(rc) die_gpu(ctx, rc);
 	char **names = calloc((size_t) (nrec ? nrec : 1), sizeof(char *));
 	if(!names) die_errno();
@@ -461,12 +473,7 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 			have_ref = 1;
 			names[n] = strdup(name);
 			if(!names[n]) die_errno();
-			if(len > 0 && !uploaded) {
-				rc = ccg_put_sample_codes(ctx, n, r->codes.data);
-				if(rc) die_gpu(ctx, rc);
-				rc = ccg_sync(ctx);
-				if(rc) die_gpu(ctx, rc);
-			}
+			if(len > 0 && !uploaded) upload_sample(ctx, n, &r->codes, 0);
 			++n;
 		}
 		if(parallel) pool_release(pool, job);
@@ -749,6 +756,7 @@ static void make_matrix(DistOpts *o) {
 		if(strcmp(o->noutputfilename, o->outputfilename) == 0) noutfile = outfile;
 		else noutfile = open_out(o->noutputfilename);
 	}
+	if(o->methfilename && motifs_load(o->methfilename, &g_motifs)) exit(1);
 	if(o->diffilename) {
 		if(strcmp(o->diffilename, o->outputfilename) == 0) g_diffile = outfile;
 		else g_diffile = open_out(o->diffilename);
@@ -797,7 +805,7 @@ static int help_message(FILE *out) {
 		{'n', "nucleotide_numbers", "Output number of nucleotides included", "False/None"},
 		{'S', "separator", "Separator", "\\t"},
 		{'x', "print_precision", "Floating point print precision", "9"},
-		{'y', "methylation_motifs", "Mask methylation motifs from <file> (not on the GPU path)", "False/None"},
+		{'y', "methylation_motifs", "Mask methylation motifs from <file>", "False/None"},
 		{'V', "nucleotide_variations", "Output nucleotide variations", "False/None"},
 		{'r', "reference", "Target reference", "None"},
 		{'a', "add", "Add file to existing matrix", ""},
@@ -928,9 +936,10 @@ int main_dist(int argc, char **argv) {
 	if(dist_mat_parse_method(&o)) die_invalid(o.method_err);
 	if(!o.numFile && o.targetTemplate) o.numFile = 1;
 
-	if(o.methfilename || (o.diffilename && (o.proxi || o.addfilename))) {
+	if((o.methfilename && (o.proxi || o.diffilename)) || (o.diffilename && (o.proxi || o.addfilename))) {
 		fprintf(stderr, "%s is not available on the GPU path of dist (use the CPU ccphylo for it).\n",
-		        o.methfilename ? "-y / --methylation_motifs" :
+		        o.methfilename ? (o.proxi ? "-y / --methylation_motifs together with -P / --proximity" :
+		                                    "-y / --methylation_motifs together with -V / --nucleotide_variations") :
 		        o.proxi ? "-V / --nucleotide_variations together with -P / --proximity" :
 		                  "-V / --nucleotide_variations together with -a / --add");
 		return 1;

@@ -159,6 +159,19 @@ int ccg_set_proximity(ccg_ctx *ctx, unsigned proxi, int snp_events_only);
  * inc_out[k] (may be NULL) receives getNpos of slot first+k's mask after the masking. */
 int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int apply, unsigned *inc_out);
 
+/* -y / --methylation_motifs: the motif list getMethMotifs (methparse.c:268-296) builds -- every
+ * motif of the file followed by its reverse complement (as strrcMeth :83-103 produces it).  Motif
+ * m has lens[m] (1 .. 32) positions whose codes follow each other in `sets`: bits 0..3 = the
+ * bases A, C, G, T the position's IUPAC letter accepts, bit 4 = methylation site (an upper-case
+ * letter).  Host pointers, copied.  nmotifs = 0 removes the list. */
+int ccg_set_motifs(ccg_ctx *ctx, int nmotifs, const int *lens, const unsigned char *sets);
+
+/* maskMotifs (meth.c:141-159, called cdist.c:90,109,137) for the uploaded slots
+ * [first, first+count) of a pair-mode store, once, right after their upload: wherever a motif
+ * matches the sample's packed sequence (unknown bases read as A) the methylation sites leave the
+ * sample's mask.  inc_out[k] (may be NULL) receives getNpos of slot first+k afterwards. */
+int ccg_mask_motifs(ccg_ctx *ctx, int first, int count, unsigned *inc_out);
+
 /* Per-slot included-position counts (getNpos of each sample's own mask,
  * fsacmp.c:487; cdist.c:91).  out has n entries. */
 int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out);

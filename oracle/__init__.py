@@ -60,6 +60,8 @@ def lib():
         L.orc_fsa_cmp_pair_proxi.restype = C.c_int
         L.orc_fsa_cmp_pair_proxi.argtypes = [C.c_int, C.c_int, _u64p, C.c_long, _u8p, _u32p, C.c_uint, C.c_uint,
                                              C.c_double, C.c_uint, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_mask_motifs.restype = C.c_long
+        L.orc_mask_motifs.argtypes = [_u64p, _u32p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_list_variants.restype = C.c_long
         L.orc_list_variants.argtypes = [_u64p, _u64p, _u32p, C.c_int, C.c_void_p, C.c_long]
         L.orc_mask_count.restype = C.c_int
@@ -232,6 +234,69 @@ def fsa_cmp_row(seqs, masks, row, length, norm=0, min_length=1, min_cov=0.5):
     return D, N
 
 
+_IUPAC = {"a": 1, "c": 2, "g": 4, "t": 8, "u": 8, "r": 5, "y": 10, "s": 6, "w": 9, "k": 12, "m": 3, "b": 14, "d": 13, "h": 11,
+          "v": 7, "x": 15, "n": 15}
+
+
+def parse_motifs(text, as_built=False):
+    """methparse.c:27-81,105-175,268-296: FASTA-like motif file -> [(sets, ...)], each motif followed by its reverse
+    complement; lower case = plain position, upper case = methylation site (bit 4); anything else is dropped.
+
+    as_built: qseq2methMotif pads the alternative words of a position that has fewer bases than the motif's most
+    ambiguous one with `bases[*seq & 31]` (methparse.c:231-236); for an upper-case letter that index is >= 16 and
+    runs past the 16-entry array -- undefined behaviour.  In the binary built here (gcc -O3, oracle/Makefile) the
+    32-entry `nums` follows `bases` on the stack, so the padding base is popcount(set): such a position also
+    accepts the base whose code equals the number of bases its letter stands for.  as_built=True reproduces that
+    (pinned in tests/test_oracle_vs_reference.py); the default is the evident intention, which is also what the
+    CUDA path implements."""
+    motifs, cur = [], None
+    lines = text.split("\n")
+    for k, line in enumerate(lines):
+        if line.startswith(">") and (cur is None or True):
+            if cur:
+                motifs.append(cur)
+            cur = []
+            continue
+        if cur is None:
+            cur = []
+        for ch in line:
+            if ch.lower() in _IUPAC and ch not in "-.":
+                cur.append(_IUPAC[ch.lower()] | (16 if ch.isupper() else 0))
+    if cur:
+        motifs.append(cur)
+    out = []
+    for m in motifs:
+        rc = []
+        for v in reversed(m):
+            s = v & 15
+            comp = ((s & 1) << 3) | ((s & 2) << 1) | ((s & 4) >> 1) | ((s & 8) >> 3)
+            rc.append(comp | (v & 16))
+        if len(m) & 1:
+            # strrcMeth (methparse.c:83-103) swaps and complements pairs from both ends, then "complements the
+            # middle" through a pointer that still stands on the last LEFT element: that one is complemented a
+            # second time (back to the letter it was swapped with) and the middle letter is never complemented.
+            # (A one-letter motif makes it write in front of the buffer: not restated.)
+            mid = len(m) >> 1
+            rc[mid] = m[mid]
+            if mid >= 1:
+                rc[mid - 1] = m[len(m) - mid]
+        for mm in (m, rc):
+            if as_built:
+                num = max(bin(v & 15).count("1") for v in mm)
+                mm = [v | (1 << bin(v & 15).count("1")) if (v & 16) and bin(v & 15).count("1") < num else v for v in mm]
+            out.append(mm)
+    return out
+
+
+def mask_motifs(seq, mask, length, motifs):
+    """maskMotifs (meth.c:141) in place on `mask`; returns the number of matches"""
+    lens = np.array([len(m) for m in motifs], dtype=np.int32)
+    sets = np.array([v for m in motifs for v in m], dtype=np.uint8)
+    if length == 0 or len(motifs) == 0:
+        return 0
+    return lib().orc_mask_motifs(np.ascontiguousarray(seq), mask, length, len(motifs), lens.ctypes.data, sets.ctypes.data)
+
+
 def list_variants(seq_i, seq_j, mask, length):
     """-V: [(label, code_i, code_j), ...] of one pair under `mask`, as fsacmpairint / fsacmprint print them."""
     seq_i, seq_j, mask = np.ascontiguousarray(seq_i), np.ascontiguousarray(seq_j), np.ascontiguousarray(mask)
@@ -299,6 +364,8 @@ def ref():
         R.refshim_and_known.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint]
         R.refshim_inc_pos.restype = None
         R.refshim_inc_pos.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint, C.c_uint]
+        R.refshim_mask_motifs.restype = C.c_int
+        R.refshim_mask_motifs.argtypes = [C.c_char_p, _u64p, _u32p, C.c_int]
         R.refshim_variants.restype = C.c_uint64
         R.refshim_variants.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _u64p, _u32p, C.c_int, C.c_char_p, C.c_long]
         R.refshim_pair.restype = C.c_uint64
@@ -343,6 +410,14 @@ def ref_pair(seq_i, seq_j, inc_i, inc_j, length, proxi=0):
     r = ref().refshim_pair(pad(seq_i, np.uint64), pad(seq_j, np.uint64), pad(inc_i, np.uint32), pad(inc_j, np.uint32),
                            length, proxi)
     return int(r >> 32), int(r & 0xFFFFFFFF)
+
+
+def ref_mask_motifs(motif_path, seq, mask, length):
+    """the reference's getMethMotifs + maskMotifs on one packed sequence; mask (W + 2 words) is updated in place"""
+    W = words(length)
+    s = np.zeros(W + 2, dtype=np.uint64)
+    s[:W] = seq
+    return ref().refshim_mask_motifs(motif_path.encode(), s, mask, length)
 
 
 def ref_variants(pair, si, sj, seq_i, seq_j, mask, length):

@@ -145,6 +145,39 @@ uint32_t orc_masked_mism(const uint64_t *seq_i, const uint64_t *seq_j,
 }
 
 /* ------------------------------------------------------------------ */
+/* -y methylation motif masking                                        */
+/* ------------------------------------------------------------------ */
+/* (reference meth.c:52-159: matchMotif32 compares a window with up to four alternative words per motif, i.e.
+ * position k matches when the sequence base is one of the bases the motif's IUPAC letter stands for; matchMotif
+ * tries every start 0 .. len - motif length; maskMotif clears the upper-case positions of the motif.  Motifs of
+ * more than 32 positions shift by a negative count there (meth.c:99) and are not restated.) */
+long orc_mask_motifs(const uint64_t *seq, uint32_t *mask, int len, int nmotifs, const int *lens,
+                     const unsigned char *sets) {
+	long found = 0;
+	int m;
+
+	for(m = 0; m < nmotifs; sets += lens[m], ++m) {
+		const int L = lens[m];
+		long p;
+		for(p = 0; p + L <= len; ++p) {
+			int k, ok = 1;
+			for(k = 0; k < L && ok; ++k) {
+				const long q = p + k;
+				const unsigned code = (unsigned) (seq[q >> 5] >> (62 - 2 * (q & 31))) & 3;
+				ok = (sets[k] >> code) & 1;
+			}
+			if(!ok) continue;
+			++found;
+			for(k = 0; k < L; ++k) {
+				const long q = p + k;
+				if(sets[k] & 16) mask[q >> 5] &= ~(1u << (31 - (q & 31)));
+			}
+		}
+	}
+	return found;
+}
+
+/* ------------------------------------------------------------------ */
 /* -V variant listing                                                  */
 /* ------------------------------------------------------------------ */
 /* (reference fsacmp.c:646-683 fsacmprint, :685-737 fsacmpairint, printDiff :635-644)

@@ -67,6 +67,14 @@ void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j,
                            const uint32_t *inc_i, const uint32_t *inc_j, int len,
                            unsigned proxi, uint32_t *mism, uint32_t *ninc);
 
+/* meth.c:141-159 maskMotifs (-y) with the motif list of methparse.c:268 getMethMotifs: nmotifs motifs (the file's
+ * motifs and their reverse complements), motif m has lens[m] <= 32 positions whose codes follow each other in
+ * `sets`: bits 0..3 = the bases A, C, G, T the position accepts, bit 4 = methylation site.  Wherever a motif
+ * matches the PACKED sequence (unknown bases read as A, qseqs.c:60) the mask bits of its methylation sites are
+ * cleared.  Returns the number of matches (meth.c:153). */
+long orc_mask_motifs(const uint64_t *seq, uint32_t *mask, int len, int nmotifs, const int *lens,
+                     const unsigned char *sets);
+
 /* fsacmp.c:646-683 fsacmprint / :685-737 fsacmpairint (-V): the variants of one pair under `mask` (pair mode: the
  * pair's mask; shared-mask mode: the global mask) in the order and with the position labels the reference
  * prints.  out[k] = label << 4 | code_i << 2 | code_j; returns how many there are (out may be NULL / cap 0). */

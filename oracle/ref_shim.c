@@ -84,6 +84,25 @@ uint64_t refshim_pair(uint64_t *seq_i, uint64_t *seq_j, uint32_t *inc_i,
 	return r;
 }
 
+/* -y: getMethMotifs (methparse.c:268) on the motif file, then maskMotifs (meth.c:141) on one packed sequence */
+#include "filebuff.h"
+#include "meth.h"
+#include "methparse.h"
+int refshim_mask_motifs(char *motif_path, uint64_t *seq, uint32_t *mask, int len) {
+	FileBuff *infile = setFileBuff(1048576);
+	Qseqs *qseq = setQseqs(1024);
+	MethMotif *motif;
+	int n;
+	openAndDetermine(infile, motif_path);
+	motif = getMethMotifs(infile, qseq);
+	closeFileBuff(infile);
+	n = maskMotifs((long unsigned *) seq, mask, len, motif);
+	destroyMethMotifs(motif);
+	destroyQseqs(qseq);
+	destroyFileBuff(infile);
+	return n;
+}
+
 /* -V: the lines fsacmpairint (pair != 0, fsacmp.c:685) / fsacmprint (fsacmp.c:646) print for one pair under `mask`,
  * as text into buf (capacity cap, 0-terminated); returns the function's own return value. */
 #define _GNU_SOURCE

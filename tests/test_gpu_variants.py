@@ -49,7 +49,9 @@ def test_pair_mode_lists(ctx, n, length):
 
 @pytest.mark.parametrize("n,length", [(4, 97), (30, 5003), (260, 2000)])
 def test_shared_mask_lists(ctx, n, length):
-    codes = synth.make_codes(n, length, seed=n + length, snp=0.03, nrun=0.004, lower=0.02, gap=0.01)
+    rare = n > 100           # many samples: keep the shared mask from running empty
+    codes = synth.make_codes(n, length, seed=n + length, snp=0.03, nrun=0.0002 if rare else 0.004,
+                             lower=0.0002 if rare else 0.02, gap=0.0001 if rare else 0.01)
     seqs, masks, inc = oracle.encode_samples(codes)
     include = np.ones(n, np.uint8)
     if n > 5:

@@ -52,7 +52,7 @@ def test_option_scanner_dialect(built, tmp_path):
     a = tmp_path / "a.fsa"
     a.write_text(">ref\nACGT\n")
     p = run("-pf3", "-s", "-W", "100", "-rref", "-i", str(a), str(a), "-P", "2", "-y", "m.txt")
-    assert p.returncode == 1 and "-y / --methylation_motifs is not available on the GPU path" in p.stderr
+    assert p.returncode == 1 and "-y / --methylation_motifs together with -P / --proximity is not available on the GPU path" in p.stderr
     p = run("-r", "ref", "-a", "x", "-P", "3", str(a), str(a))
     assert p.returncode == 1 and "-a / --add together with -P" in p.stderr
     # -a reads the existing matrix before it needs the device: a multi-matrix file is refused as the reference does

@@ -195,3 +195,40 @@ def test_variant_listing_matches_reference(built, length):
             got = oracle.list_variants(seqs[i], seqs[j], gmask, length)
             assert oracle.variant_text(i, j, got) == text and r == len(got)
     assert total > 0 or length < 31
+
+
+# ---------------------------------------------------------------------------------------------
+# -y methylation motif masking (meth.c:52-159, methparse.c:27-296)
+# ---------------------------------------------------------------------------------------------
+MOTIF_FILES = [">dam\ngAtc\n", ">dam\ngAtc\n>dcm\ncCwgg\n>x\nrgATcnny\n", "gatC\n>multi line\ncC\nwg\ng\n>odd chars\nGA-NT.C\n",
+               ">long\nacgtacgtAcgtacgtacgtacgTacgtacgt\n>three\ngAn\n>iupac\nRYSWKMBDHVN\n"]
+
+
+@pytest.mark.parametrize("which", range(len(MOTIF_FILES)))
+def test_motif_masking_matches_reference(built, tmp_path, which):
+    path = str(tmp_path / "motifs.fsa")
+    with open(path, "w") as f:
+        f.write(MOTIF_FILES[which])
+    # all but the first file hold motifs on which the reference reads past an array (see oracle.parse_motifs):
+    # as_built reproduces what this container's build of it does; on the first file both readings agree
+    motifs = oracle.parse_motifs(MOTIF_FILES[which], as_built=True)
+    assert motifs and all(len(m) <= 32 for m in motifs)
+    assert (motifs == oracle.parse_motifs(MOTIF_FILES[which])) == (which == 0)
+    hits = 0
+    for length in (1, 4, 31, 32, 33, 64, 65, 700, 4099):
+        codes = synth.make_codes(3, length, seed=length + which, snp=0.05, nrun=0.05, lower=0.03, gap=0.01)
+        if length >= 700:
+            codes[1, 100:132] = np.tile([0, 1, 2, 3], 8)            # the 32-mer of the last file
+        seqs, masks, _ = oracle.encode_samples(codes)
+        for s in range(3):
+            W = oracle.words(length)
+            want = np.zeros(W + 2, np.uint32)
+            want[:W] = oracle.full_mask(length)
+            n_ref = oracle.ref_mask_motifs(path, seqs[s], want, length)
+            got = oracle.full_mask(length).copy()
+            n = oracle.mask_motifs(seqs[s], got, length, motifs)
+            assert n == n_ref, (length, s)
+            assert np.array_equal(got, want[:W]), (length, s)
+            assert want[W] == 0 and want[W + 1] == 0
+            hits += n
+    assert hits > 0
