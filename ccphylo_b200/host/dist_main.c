@@ -480,6 +480,14 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	}
 	if(parallel) pool_finish(pool);
 	else fsa_close(fr);
+	if(n == 0) {
+		/* no record was kept: the reference shrinks its arrays to zero bytes, takes realloc's NULL for a failure and
+		 * leaves through ERROR() with errno still 0 (cdist.c:323-329) -- this line, exit code 0, empty outputs */
+		fprintf(stderr, "Error: %d (%s)\n", 0, strerror(0));
+		fflush(outfile);
+		if(noutfile) fflush(noutfile);
+		exit(0);
+	}
 	/* excluded records were dropped: the n kept samples occupy slots 0..n-1 */
 	unsigned char *include = malloc((size_t) (nrec ? nrec : 1));
 	if(!include) die_errno();
