@@ -130,18 +130,38 @@ k_pairdist_proxi(const uint32_t *__restrict__ planes, int n_pad, int chunks, uns
 	for(int a = 0; a < PX_ROWS; ++a) proxi_pair_init(st[a]);
 
 	const uint4 *P = reinterpret_cast<const uint4 *>(planes);
+	/* The walk is one dependent chain per pair, so the loads of chunk c + 1 are issued before chunk c is worked on
+	 * (register double buffer): without that every iteration waits a full memory latency. */
+	uint4 jn[3], in_[PX_ROWS][3];
+#pragma unroll
+	for(int q = 0; q < 3; ++q) {
+		jn[q] = __ldg(P + (size_t) q * n_pad + j);
+#pragma unroll
+		for(int a = 0; a < PX_ROWS; ++a) in_[a][q] = __ldg(P + (size_t) q * n_pad + i[a]);
+	}
 #pragma unroll 1
 	for(int c = 0; c < chunks; ++c) {
-		const size_t row = (size_t) c * 3;
-		const uint4 jh = __ldg(P + (row + 0) * n_pad + j);
-		const uint4 jl = __ldg(P + (row + 1) * n_pad + j);
-		const uint4 jm = __ldg(P + (row + 2) * n_pad + j);
+		uint4 jc[3], ic[PX_ROWS][3];
+#pragma unroll
+		for(int q = 0; q < 3; ++q) {
+			jc[q] = jn[q];
+#pragma unroll
+			for(int a = 0; a < PX_ROWS; ++a) ic[a][q] = in_[a][q];
+		}
+		if(c + 1 < chunks) {
+			const size_t row = (size_t) (c + 1) * 3;
+#pragma unroll
+			for(int q = 0; q < 3; ++q) {
+				jn[q] = __ldg(P + (row + q) * n_pad + j);
+#pragma unroll
+				for(int a = 0; a < PX_ROWS; ++a) in_[a][q] = __ldg(P + (row + q) * n_pad + i[a]);
+			}
+		}
+		const uint4 jh = jc[0], jl = jc[1], jm = jc[2];
 #pragma unroll
 		for(int a = 0; a < PX_ROWS; ++a) {
 			if(!active[a]) continue;
-			const uint4 ih = __ldg(P + (row + 0) * n_pad + i[a]);
-			const uint4 il = __ldg(P + (row + 1) * n_pad + i[a]);
-			const uint4 im = __ldg(P + (row + 2) * n_pad + i[a]);
+			const uint4 ih = ic[a][0], il = ic[a][1], im = ic[a][2];
 			const int p0 = c * CCG_CHUNK_BASES;
 #define CCG_PX_WORD(f, q)                                                                  \
 	{                                                                                      \
