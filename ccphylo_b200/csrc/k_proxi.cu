@@ -163,14 +163,9 @@ k_pairdist_proxi(const uint32_t *__restrict__ planes, int n_pad, int chunks, uns
 			if(!active[a]) continue;
 			const uint4 ih = ic[a][0], il = ic[a][1], im = ic[a][2];
 			const int p0 = c * CCG_CHUNK_BASES;
-#define CCG_PX_WORD(f, q)                                                                  \
-	{                                                                                      \
-		const uint32_t m = im.f & jm.f;                                                    \
-		const uint32_t d = ((il.f ^ jl.f) | (ih.f ^ jh.f)) & m;                            \
-		proxi_pair_word(st[a], p0 + 32 * q, d, m, proxi);                                  \
-	}
-			CCG_PX_WORD(x, 0) CCG_PX_WORD(y, 1) CCG_PX_WORD(z, 2) CCG_PX_WORD(w, 3)
-#undef CCG_PX_WORD
+			const uint32_t m0 = im.x & jm.x, m1 = im.y & jm.y, m2 = im.z & jm.z, m3 = im.w & jm.w;
+			proxi_pair_chunk(st[a], p0, ((il.x ^ jl.x) | (ih.x ^ jh.x)) & m0, ((il.y ^ jl.y) | (ih.y ^ jh.y)) & m1,
+			                 ((il.z ^ jl.z) | (ih.z ^ jh.z)) & m2, ((il.w ^ jl.w) | (ih.w ^ jh.w)) & m3, m0, m1, m2, m3, proxi);
 		}
 	}
 

@@ -108,6 +108,23 @@ static int check_pairs(int n, int len, unsigned proxi, unsigned variant_for_mask
 			}
 			unsigned got_m, got_n;
 			proxi_pair_finish(st, &got_m, &got_n);
+			/* the chunked form the kernel uses: four words per call, the tail padded with empty words */
+			ProxiPairState sc;
+			proxi_pair_init(sc);
+			for(int w = 0; w < W; w += 4) {
+				uint32_t mm[4] = {0, 0, 0, 0}, dd[4] = {0, 0, 0, 0};
+				for(int q = 0; q < 4 && w + q < W; ++q) {
+					mm[q] = pl[i].m[w + q] & pl[j].m[w + q];
+					dd[q] = ((pl[i].l[w + q] ^ pl[j].l[w + q]) | (pl[i].h[w + q] ^ pl[j].h[w + q])) & mm[q];
+				}
+				proxi_pair_chunk(sc, w * 32, dd[0], dd[1], dd[2], dd[3], mm[0], mm[1], mm[2], mm[3], proxi);
+			}
+			unsigned chunk_m, chunk_n;
+			proxi_pair_finish(sc, &chunk_m, &chunk_n);
+			if(chunk_m != got_m || chunk_n != got_n) {
+				printf("pair len=%d proxi=%u (%d,%d): chunked %u/%u, word by word %u/%u\n", len, proxi, i, j, chunk_m, chunk_n, got_m, got_n);
+				return 1;
+			}
 			++cases;
 			if(got_m != want_m || got_n != want_n) {
 				printf("pair len=%d proxi=%u (%d,%d): got %u/%u want %u/%u\n", len, proxi, i, j, got_m, got_n, want_m, want_n);

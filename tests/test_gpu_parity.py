@@ -258,10 +258,17 @@ def test_empty_and_degenerate_inputs(ctx):
     # nothing included
     D, N, dn, _ = api.fsa_cmp_thread_out(seqs, np.zeros(3, np.uint8), masks, 100, pair=True, ctx=ctx)
     assert dn == 0 and len(D) == 0
-    # proximity masking is not a GPU feature: loud refusal, never a silent fallback
-    with pytest.raises(api.CcgError) as e:
-        api.fsa_cmp_thread_out(seqs, np.ones(3, np.uint8), masks, 100, pair=True, proxi=3, ctx=ctx)
-    assert e.value.code == 5
+    # an unsupported combination is a loud refusal, never a silent fallback: a row against an existing matrix
+    # (-a) with proximity masking (-P)
+    ctx.set_problem(3, 100, pair=True)
+    ctx.put_samples_packed(seqs, masks)
+    ctx.set_proximity(3)
+    try:
+        with pytest.raises(api.CcgError) as e:
+            ctx.run_row(2)
+        assert e.value.code == 5
+    finally:
+        ctx.set_proximity(0)
 
 
 def test_temporary_context_path(built):
