@@ -1401,10 +1401,6 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
                            int *cols_out) {
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !D || row_slot < 0 || row_slot >= ctx->n || !ctx->present[row_slot])
 		return CCG_ERR_ARG;
-	if(ctx->proxi) {
-		set_err(ctx, "a row against an existing matrix (-a) with proximity masking (-P) is not available on the GPU path");
-		return CCG_ERR_UNSUPPORTED;
-	}
 	if(ctx->world > 1) {
 		set_err(ctx, "ccg_run_row runs on one device");
 		return CCG_ERR_UNSUPPORTED;
@@ -1429,6 +1425,54 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
 			return CCG_ERR_NOMEM;
 		}
 		ctx->out_bytes = bytes;
+	}
+	if(ctx->proxi && ctx->words > 0) {
+		/* -P: the pair's mask is the new sample's own mask after ITS builder (fsacmpthrd.c:627-628), then the
+		 * per-sample builder again against the column sample (:545-546) -- k_row_proxi.  The new sample's planes are
+		 * set aside as uploaded (the events are defined on the codes), masked in place for the run, and put back. */
+		for(int i = 0; i < ctx->n_pad; ++i) ctx->h_rank[i] = i < ctx->n && use[i] ? 1 : -1;
+		int r = 0;
+		for(int i = 0; i < ctx->n; ++i)
+			if(use[i]) ctx->h_rank[i] = r++;
+		free(use);
+		EpilogueParams ep;
+		memset(&ep, 0, sizeof(ep));
+		ep.elem_size = 8;
+		ep.norm = norm;
+		ep.byteScale = 1.0;
+		ep.D = ctx->d_out_D;
+		ep.N = ctx->d_out_N;
+		ep.rank = ctx->d_rank;
+		ep.row_plus1 = ctx->h_rank[row_slot] + 1;
+		if(minLength < minCov * ctx->len) minLength = (unsigned) (minCov * ctx->len);
+		ep.minLength = minLength;
+		ep.nFactor = 1.0;
+		void *d_raw = 0;
+		unsigned char *d_use = 0;
+		unsigned *d_clr = 0;
+		int first_used = -1;
+		int rc = stage_use_flags(ctx, 0, row_slot, row_slot + 1, &d_use, &d_clr, (size_t) ctx->n_pad, &first_used);
+		if(rc) return rc;
+		CK(ctx, cudaMalloc(&d_raw, (size_t) ctx->chunks * 3 * 16));
+		cudaError_t e = cudaMemcpyAsync(ctx->d_rank, ctx->h_rank, (size_t) ctx->n_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+		if(e == cudaSuccess) e = ccg_launch_row_planes(ctx, row_slot, d_raw, 0);
+		if(e == cudaSuccess && !ctx->proxi_snp_only) e = ccg_launch_sample_proxi(ctx, 0, 0, d_use, 1, d_clr);
+		if(e == cudaSuccess) e = cudaEventRecord(ctx->ev0, ctx->stream);
+		if(e == cudaSuccess) e = ccg_launch_row_proxi(ctx, row_slot, d_raw, ep);
+		if(e == cudaSuccess) e = cudaEventRecord(ctx->ev1, ctx->stream);
+		if(e == cudaSuccess) e = ccg_launch_row_planes(ctx, row_slot, d_raw, 1);
+		if(e == cudaSuccess) e = cudaMemcpyAsync(D, ctx->d_out_D, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+		if(e == cudaSuccess && N) e = cudaMemcpyAsync(N, ctx->d_out_N, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+		if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		cudaFree(d_raw);
+		if(e != cudaSuccess) {
+			set_err(ctx, "row run with proximity masking failed: %s", cudaGetErrorString(e));
+			return CCG_ERR_CUDA;
+		}
+		ctx->ev_valid = 1;
+		ctx->last_Dn = 0;
+		snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_row_proxi cols=%d proxi=%u", cols, ctx->proxi);
+		return CCG_OK;
 	}
 	const int win_on = ctx->win_on;
 	int win[4];

@@ -232,6 +232,8 @@ cudaError_t ccg_launch_sample_proxi(ccg_ctx *ctx, int vs_ref, int ref_slot, cons
                                     unsigned *d_cleared);
 cudaError_t ccg_launch_count_mask(ccg_ctx *ctx, unsigned *d_count);
 cudaError_t ccg_launch_pair_proxi(ccg_ctx *ctx, const ProxiParams &p);
+cudaError_t ccg_launch_row_planes(ccg_ctx *ctx, int slot, void *d_buf, int restore);
+cudaError_t ccg_launch_row_proxi(ccg_ctx *ctx, int row_slot, const void *d_rowraw, const EpilogueParams &ep);
 
 /* k_motif.cu */
 cudaError_t ccg_launch_motif_mask(ccg_ctx *ctx, int first, int count, unsigned *d_removed);

@@ -182,7 +182,68 @@ k_pairdist_proxi(const uint32_t *__restrict__ planes, int n_pad, int chunks, uns
 	}
 }
 
+/* -a with -P: one thread per column sample walks the alignment against the new sample (proxi_row_word).  rowraw holds
+ * the new sample's planes as uploaded ([chunk][h, l, m]); its mask plane in the store has been through the
+ * per-sample builder by now (fsacmpthrd.c:627-628). */
+__global__ void __launch_bounds__(128)
+k_row_proxi(const uint32_t *__restrict__ planes, int n_pad, int chunks, long long len, unsigned proxi, int snp_only,
+            const uint4 *__restrict__ rowraw, int row_slot, EpilogueParams ep) {
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if(j >= row_slot || ep.rank[j] < 0) return;
+	const uint4 *P = reinterpret_cast<const uint4 *>(planes);
+	ProxiRowState st;
+	proxi_row_init(st);
+#pragma unroll 1
+	for(int c = 0; c < chunks; ++c) {
+		const size_t row = (size_t) c * 3;
+		const uint4 jh = __ldg(P + (row + 0) * n_pad + j), jl = __ldg(P + (row + 1) * n_pad + j), jm = __ldg(P + (row + 2) * n_pad + j);
+		const uint4 rh = __ldg(rowraw + row), rl = __ldg(rowraw + row + 1), rm = __ldg(rowraw + row + 2);
+		const uint4 own = __ldg(P + (row + 2) * n_pad + row_slot);
+		const long long p0 = (long long) c * CCG_CHUNK_BASES;
+#define CCG_ROW_WORD(f, q)                                                                                        \
+	{                                                                                                             \
+		const uint32_t valid = proxi_valid_bits(len, p0 + 32 * q);                                                \
+		const uint32_t ev = proxi_events(1, snp_only, jm.f, jh.f, jl.f, rm.f, rh.f, rl.f, valid);                  \
+		const uint32_t m = own.f & jm.f;                                                                          \
+		const uint32_t d = ((rh.f ^ jh.f) | (rl.f ^ jl.f)) & m;                                                   \
+		proxi_row_word(st, p0 + 32 * q, ev, m, d, proxi);                                                         \
+	}
+		CCG_ROW_WORD(x, 0) CCG_ROW_WORD(y, 1) CCG_ROW_WORD(z, 2) CCG_ROW_WORD(w, 3)
+#undef CCG_ROW_WORD
+	}
+	unsigned mism, ninc;
+	proxi_row_finish(st, &mism, &ninc);
+	ccg_write_cell(ep, row_slot, j, mism, ninc);
+}
+
+/* the three plane words of every chunk of one slot <-> a compact [chunk][3] buffer */
+__global__ void __launch_bounds__(256)
+k_row_planes(uint32_t *planes, int n_pad, int chunks, int slot, uint4 *buf, int restore) {
+	uint4 *P = reinterpret_cast<uint4 *>(planes);
+	for(long long e = blockIdx.x * (long long) blockDim.x + threadIdx.x; e < (long long) chunks * 3; e += (long long) gridDim.x * blockDim.x) {
+		if(restore) P[e * n_pad + slot] = buf[e];
+		else buf[e] = P[e * n_pad + slot];
+	}
+}
+
 } // namespace
+
+cudaError_t ccg_launch_row_planes(ccg_ctx *ctx, int slot, void *d_buf, int restore) {
+	int blocks = (ctx->chunks * 3 + 255) / 256;
+	if(blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+	k_row_planes<<<blocks, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks, slot, (uint4 *) d_buf, restore);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t ccg_launch_row_proxi(ccg_ctx *ctx, int row_slot, const void *d_rowraw, const EpilogueParams &ep) {
+	if(row_slot <= 0) return cudaSuccess;
+	k_row_proxi<<<(unsigned) ((row_slot + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks, (long long) ctx->len,
+	                                                                        ctx->proxi, ctx->proxi_snp_only, (const uint4 *) d_rowraw,
+	                                                                        row_slot, ep);
+	ctx->launches++;
+	return cudaGetLastError();
+}
 
 cudaError_t ccg_launch_sample_proxi(ccg_ctx *ctx, int vs_ref, int ref_slot, const unsigned char *d_use, int apply,
                                     unsigned *d_cleared) {

@@ -165,6 +165,62 @@ CCG_HD void proxi_pair_finish(const ProxiPairState &st, unsigned *mism, unsigned
 }
 
 /* ------------------------------------------------------------------------------------------
+ * one row against an existing matrix (-a with -P)
+ * ------------------------------------------------------------------------------------------ */
+/* cmpFsaRowThrd (fsacmpthrd.c:543-556): the pair's mask starts as the new sample's own mask, then goes through
+ * the PER-SAMPLE builder against the column sample -- getIncPosPtr(includeseq, seq, ref, proxi), not maskProxi --
+ * and fsacmpair counts under it.  So an event at most proxi after the previous event removes everything from
+ * the previous event to this one, both inclusive; what is wanted here are the counts of what is removed. */
+struct ProxiRowState {
+	long long last;          /* position of the last event, -1 = none */
+	unsigned pend_inc, pend_snp;   /* included positions / SNPs strictly after `last` seen so far */
+	unsigned last_inc, last_snp;   /* `last` itself is included / a SNP and not yet removed */
+	unsigned cleared_inc, cleared_snp, total_inc, total_snp;
+};
+
+CCG_HD void proxi_row_init(ProxiRowState &st) {
+	st.last = -1;
+	st.pend_inc = st.pend_snp = st.last_inc = st.last_snp = 0;
+	st.cleared_inc = st.cleared_snp = st.total_inc = st.total_snp = 0;
+}
+
+/* ev = event bits of the word (proxi_events), m = included positions before the pair's proximity masking,
+ * d = SNPs among them; words ascending, p0 = position of the word's first base */
+CCG_HD void proxi_row_word(ProxiRowState &st, long long p0, uint32_t ev, uint32_t m, uint32_t d, unsigned proxi) {
+	st.total_inc += (unsigned) ccg_popc32(m);
+	st.total_snp += (unsigned) ccg_popc32(d);
+	uint32_t rest = 0xFFFFFFFFu;                 /* bases of this word not yet looked at */
+	while(ev) {
+		const int b = ccg_first_bit(ev);
+		const uint32_t bit = 0x80000000u >> b;
+		ev &= ~bit;
+		const uint32_t before = rest & ~(bit | (bit - 1u));
+		st.pend_inc += (unsigned) ccg_popc32(m & before);
+		st.pend_snp += (unsigned) ccg_popc32(d & before);
+		rest = bit - 1u;
+		const long long p = p0 + b;
+		const unsigned inc_p = (m & bit) ? 1u : 0u, snp_p = (d & bit) ? 1u : 0u;
+		if(st.last >= 0 && (unsigned long long) (p - st.last) <= proxi) {
+			st.cleared_inc += st.pend_inc + st.last_inc + inc_p;
+			st.cleared_snp += st.pend_snp + st.last_snp + snp_p;
+			st.last_inc = st.last_snp = 0;
+		} else {
+			st.last_inc = inc_p;
+			st.last_snp = snp_p;
+		}
+		st.pend_inc = st.pend_snp = 0;
+		st.last = p;
+	}
+	st.pend_inc += (unsigned) ccg_popc32(m & rest);
+	st.pend_snp += (unsigned) ccg_popc32(d & rest);
+}
+
+CCG_HD void proxi_row_finish(const ProxiRowState &st, unsigned *mism, unsigned *ninc) {
+	*mism = st.total_snp - st.cleared_snp;
+	*ninc = st.total_inc - st.cleared_inc;
+}
+
+/* ------------------------------------------------------------------------------------------
  * per sample
  * ------------------------------------------------------------------------------------------ */
 /* Event bits of one word.  vs_ref == 0: the sample against itself (pair mode, cdist.c:91): its

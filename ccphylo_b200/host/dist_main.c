@@ -16,7 +16,7 @@
  *   - -V (variant listing) comes from the device as well (ccg_list_variants, same labels as the reference);
  *     -a appends one row to an existing matrix (ccg_run_row / ccg_mat_run_row);
  *   - -y masks methylation motifs on the device right after each upload (ccg_mask_motifs);
- *   - refused: the combinations -V with -P, -a or -y; -y with -P; -a with -P.
+ *   - refused: the combinations -V with -P, -a or -y; -y with -P.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -639,23 +639,31 @@ static int add_fasta_row(const DistOpts *o, const PhyNames *phy, double *D, doub
 	const int len = (int) added.codes.len;
 	unsigned minLength = o->minLength;
 	if(minLength < o->minCov * len) minLength = (unsigned) (o->minCov * len);
-	if(added.known < minLength) {
+	ccg_ctx *ctx = 0;
+	int rc = ccg_init(&ctx, -1);
+	if(rc) die_gpu(0, rc);
+	rc = ccg_set_proximity(ctx, o->proxi, (o->flag & (8 | 32)) != 0);
+	if(!rc) rc = ccg_set_problem(ctx, n + 1, len, 1);
+	if(rc) die_gpu(ctx, rc);
+	/* the new sample's own count (fsacmpthrd.c:627-629): with -P and getIncPos' events the bases between close
+	 * unknown positions do not count; ccg_run_row applies that masking itself, here it is only counted */
+	unsigned inc = added.known;
+	if(len > 0) {
+		rc = ccg_put_sample_codes(ctx, n, added.codes.data);
+		if(!rc) rc = ccg_sync(ctx);
+		if(!rc && o->proxi && !(o->flag & (8 | 32))) rc = ccg_sample_proximity(ctx, n, 1, 0, &inc);
+		if(rc) die_gpu(ctx, rc);
+	}
+	if(inc < minLength) {
 		fprintf(stderr, "Template (\"%s\") did not exceed threshold for inclusion:\t%s\n", o->targetTemplate, addname);
+		ccg_destroy(ctx);
 		return 1;
 	}
 	int threads = o->threads < 1 ? 1 : o->threads;
 	if(n < threads) fprintf(stderr, "Adjustning number of nodes to %d, to conform with the matrix size.\n", (threads = n));
-	if(n < 1) return 0;
-
-	ccg_ctx *ctx = 0;
-	int rc = ccg_init(&ctx, -1);
-	if(rc) die_gpu(0, rc);
-	rc = ccg_set_problem(ctx, n + 1, len, 1);
-	if(rc) die_gpu(ctx, rc);
-	if(len > 0) {
-		rc = ccg_put_sample_codes(ctx, n, added.codes.data);
-		if(!rc) rc = ccg_sync(ctx);
-		if(rc) die_gpu(ctx, rc);
+	if(n < 1) {
+		ccg_destroy(ctx);
+		return 0;
 	}
 	/* the samples of the existing matrix, parsed by the host threads, into the slots below */
 	DistOpts old = *o;
@@ -711,10 +719,6 @@ static int add_fasta_row(const DistOpts *o, const PhyNames *phy, double *D, doub
 }
 
 static int add_to_matrix(const DistOpts *o) {
-	if(o->proxi) {
-		fprintf(stderr, "-a / --add together with -P / --proximity is not available on the GPU path of dist (use the CPU ccphylo for it).\n");
-		return 1;
-	}
 	/* directory of the first input file: the names of the matrix are looked up there (dist.c:344-356) */
 	char *dir = strdup(o->filenames[0]);
 	if(!dir) die_errno();

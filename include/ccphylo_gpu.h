@@ -211,7 +211,10 @@ int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include,
  * in the reference; N may be NULL) receive the cell against the k-th uploaded slot below
  * row_slot: N = positions known in both, D = norm ? mismatches * norm / N : mismatches, and
  * D = -1, N = 0 where N < max(minLength, minCov * len) (the caller prints the reference's
- * "No sufficient overlap with sample" line for those).  *cols receives the number of cells. */
+ * "No sufficient overlap with sample" line for those).  *cols receives the number of cells.
+ * With ccg_set_proximity(proxi > 0) the pair's mask is what cmpFsaRowThrd builds (:545-546): the
+ * new sample's own mask after its builder, put through getIncPosPtr(…, seq, ref, proxi) against the
+ * column sample; the new sample is uploaded as it is (no ccg_sample_proximity on its slot). */
 int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned minLength, double minCov,
                 double *D, double *N, int *cols);
 

@@ -188,6 +188,51 @@ static int check_samples(int len, unsigned proxi, int variant, int seg_words) {
 	return 0;
 }
 
+/* -a with -P: the row state machine against getIncPos on the pair's mask + plain counting */
+static int check_rows(int len, unsigned proxi, int variant) {
+	const int W = orc_words(len);
+	std::vector<unsigned char> base((size_t) len), add, col;
+	for(int p = 0; p < len; ++p) base[p] = (unsigned char) (rnd() & 3);
+	make_sample(base, add, 0.03, 0.02);
+	make_sample(base, col, 0.03, 0.02);
+	std::vector<uint64_t> qa((size_t) W + 1), qc((size_t) W + 1);
+	std::vector<uint32_t> ka((size_t) W + 1), kc((size_t) W + 1), own((size_t) W + 1);
+	orc_pack(add.data(), len, qa.data());
+	orc_pack(col.data(), len, qc.data());
+	orc_known_mask(add.data(), len, ka.data());
+	orc_known_mask(col.data(), len, kc.data());
+	/* includeadd: the new sample's own builder (fsacmpthrd.c:627-628) */
+	own = ka;
+	orc_inc_pos(own.data(), add.data(), add.data(), len, proxi, variant);
+	/* oracle: copy, getIncPosPtr(copy, col, add, proxi), fsacmpair */
+	std::vector<uint32_t> pm = own;
+	orc_inc_pos(pm.data(), col.data(), add.data(), len, proxi, variant);
+	std::vector<uint32_t> ones((size_t) W + 1, 0xFFFFFFFFu);
+	uint32_t want_m = 0, want_n = 0;
+	orc_pair_counts(qa.data(), qc.data(), pm.data(), ones.data(), len, &want_m, &want_n);
+	/* device scheme: raw planes of both for the events, the new sample's masked mask for the counts */
+	Planes pa, pc;
+	to_planes(qa.data(), ka.data(), W, pa);
+	to_planes(qc.data(), kc.data(), W, pc);
+	ProxiRowState st;
+	proxi_row_init(st);
+	for(int w = 0; w < W; ++w) {
+		const uint32_t valid = proxi_valid_bits(len, (long long) w * 32);
+		const uint32_t ev = proxi_events(1, variant, pc.m[w], pc.h[w], pc.l[w], pa.m[w], pa.h[w], pa.l[w], valid);
+		const uint32_t m = own[w] & pc.m[w];
+		const uint32_t d = ((pa.h[w] ^ pc.h[w]) | (pa.l[w] ^ pc.l[w])) & m;
+		proxi_row_word(st, (long long) w * 32, ev, m, d, proxi);
+	}
+	unsigned got_m, got_n;
+	proxi_row_finish(st, &got_m, &got_n);
+	++cases;
+	if(got_m != want_m || got_n != want_n) {
+		printf("row len=%d proxi=%u variant=%d: got %u/%u want %u/%u\n", len, proxi, variant, got_m, got_n, want_m, want_n);
+		return 1;
+	}
+	return 0;
+}
+
 int main(int argc, char **argv) {
 	rng_state = 0x9E3779B97F4A7C15ull ^ (uint64_t) (argc > 1 ? atoll(argv[1]) : 1) * 0x100000001B3ull;
 	static const unsigned proxis[] = {1, 2, 3, 5, 8, 31, 32, 33, 63, 64, 65, 100, 1000, 100000};
@@ -196,6 +241,8 @@ int main(int argc, char **argv) {
 		for(unsigned li = 0; li < sizeof(lens) / sizeof(*lens); ++li) {
 			for(unsigned variant = 0; variant < 2; ++variant) {
 				if(check_pairs(5, lens[li], proxis[pi], variant)) return 1;
+				for(int rep = 0; rep < 6; ++rep)
+					if(check_rows(lens[li], proxis[pi], (int) variant)) return 1;
 				for(int seg = 1; seg <= 64; seg *= 4)
 					if(check_samples(lens[li], proxis[pi], (int) variant, seg)) return 1;
 			}

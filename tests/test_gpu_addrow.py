@@ -52,6 +52,45 @@ def test_fasta_row_against_the_oracle(ctx, n, length, kernel):
         ctx.set_kernel(api.KERNEL_AUTO)
 
 
+@pytest.mark.parametrize("snp_only", [False, True])
+@pytest.mark.parametrize("proxi", [1, 6, 33, 400])
+@pytest.mark.parametrize("n,length", [(3, 97), (40, 4099), (300, 9000 + 1)])
+def test_fasta_row_with_proximity_against_the_oracle(ctx, n, length, proxi, snp_only):
+    """-a with -P: the pair's mask is the new sample's own mask put through the per-sample builder against each
+    column sample (not maskProxi)"""
+    variant = 1 if snp_only else 0
+    codes = synth.make_codes(n + 1, length, seed=n + length + proxi, snp=0.02, nrun=0.01, lower=0.01, gap=0.005)
+    if n > 3:
+        codes[2, : length - length // 4] = 4
+    seqs, masks, inc = oracle.encode_samples(codes)                                   # columns: known positions
+    own = oracle.full_mask(length).copy()
+    oracle.inc_pos(own, codes[n], codes[n], proxi, variant)                           # includeadd
+    masks_o = masks.copy()
+    masks_o[n] = own
+    ctx.set_proximity(proxi, snp_only)
+    try:
+        ctx.set_problem(n + 1, length, pair=True)
+        for i in range(n + 1):
+            ctx.put_sample_codes(i, codes[i])
+            ctx.sync()
+        before = ctx.inc_counts().copy()
+        for norm in (0, 1000):
+            D, N = ctx.run_row(n, norm=norm, min_length=1, min_cov=0.5)
+            Do, No = oracle.fsa_cmp_row(seqs, masks_o, n, length, norm=norm, min_length=1, min_cov=0.5, proxi=proxi,
+                                        variant=variant, codes=codes)
+            assert np.array_equal(D.view(np.uint8), Do.view(np.uint8))
+            assert np.array_equal(N.view(np.uint8), No.view(np.uint8))
+        assert "k_row_proxi" in ctx.last_kernel
+        # the new sample's planes were put back as uploaded
+        assert np.array_equal(ctx.inc_counts(), before)
+    finally:
+        ctx.set_proximity(0)
+    plain, _ = oracle.fsa_cmp_row(seqs, masks, n, length, norm=1000, min_length=1, min_cov=0.5)
+    assert proxi < 6 or not np.array_equal(plain, Do)
+    D0, N0 = ctx.run_row(n, norm=1000, min_length=1, min_cov=0.5)
+    assert np.array_equal(D0, plain)
+
+
 @pytest.mark.parametrize("method", ["cos", "chi2", "bc", "z", "l1", "nl2"])
 def test_mat_row_against_the_oracle(ctx, method):
     from test_gpu_mat import random_counts, close
@@ -74,8 +113,9 @@ def _run(cmd, cwd):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
-@pytest.mark.parametrize("args", [["-f", "3"], ["-f", "3", "-W", "1000000"], ["-f", "2", "-W", "1000"], ["-f", "11", "-x", "4"]],
-                         ids=["relaxed", "normalised", "strict-names", "insig-precision"])
+@pytest.mark.parametrize("args", [["-f", "3"], ["-f", "3", "-W", "1000000"], ["-f", "2", "-W", "1000"], ["-f", "11", "-x", "4"],
+                                  ["-f", "3", "-P", "9", "-W", "1000"], ["-f", "35", "-P", "50"]],
+                         ids=["relaxed", "normalised", "strict-names", "insig-precision", "proximity", "proximity-prune"])
 def test_cli_add_fasta_row_against_the_reference_binary(built, tmp_path, args):
     """matrix of n samples by the reference, then -a with one more sample by the reference and by this driver on
     copies of the same files: both must leave the same bytes in the .phy and the .num"""

@@ -2,6 +2,8 @@
 oracle/_ref/libccphylo_ref.so (reference objects + oracle/ref_shim.c): the real
 get2BitTable / qseq2nibble / initIncPos / getIncPos / getNpos / maskProxi / fsacmpair and
 the real fsaCmpThreadOut fan-out with cmpairFsaThrd / cmpFsaThrd.  Bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -232,3 +234,39 @@ def test_motif_masking_matches_reference(built, tmp_path, which):
             assert want[W] == 0 and want[W + 1] == 0
             hits += n
     assert hits > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# -a: one row against an existing matrix (cmpFsaRowThrd fsacmpthrd.c:482-580), through the reference binary
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flag,proxi", [(3, 0), (3, 9), (3, 200), (35, 50), (11, 4)])
+def test_row_restatement_matches_reference_binary(built, tmp_path, flag, proxi):
+    import subprocess
+    ref_bin = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ccphylo")
+    n, length = 7, 6000 + 11
+    rows = synth.make_ascii(n + 1, length, seed=flag + proxi, snp=0.01, nrun=0.02)
+    rows[3, : length - 2000] = ord("N")
+    td = str(tmp_path)
+    for i in range(n + 1):
+        synth.write_fasta(os.path.join(td, f"s{i}.fsa"), rows[i], header="ref", width=60)
+    files = [os.path.join(td, f"s{i}.fsa") for i in range(n)]
+    common = ["-f", str(flag), "-P", str(proxi), "-W", "1000"]
+    p = subprocess.run([ref_bin, "dist", "-r", "ref", "-C", "0.0", "-i"] + files + common + ["-o", "m.phy", "-n", "m.num"],
+                       cwd=td, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    p = subprocess.run([ref_bin, "dist", "-r", "ref", "-a", os.path.join(td, f"s{n}.fsa"), "-i", files[0]] + common +
+                       ["-o", "m.phy", "-n", "m.num"], cwd=td, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    want_d = [float(x) for x in open(os.path.join(td, "m.phy")).read().splitlines()[-1].split("\t")[1:]]
+    want_n = [float(x) for x in open(os.path.join(td, "m.num")).read().splitlines()[-1].split("\t")[1:]]
+    codes = np.stack([oracle.translate(rows[i].tobytes(), flag) for i in range(n + 1)])
+    variant = oracle.variant_of(flag)
+    seqs, masks, _ = oracle.encode_samples(codes)
+    own = oracle.full_mask(length).copy()
+    oracle.inc_pos(own, codes[n], codes[n], proxi, variant)
+    masks[n] = own
+    D, N = oracle.fsa_cmp_row(seqs, masks, n, length, norm=1000, min_length=1, min_cov=0.5, proxi=proxi, variant=variant,
+                              codes=codes)
+    assert len(want_d) == n and want_d[3] == -1
+    assert np.array_equal(N, np.array(want_n))
+    assert np.all(np.abs(D - np.array(want_d)) <= 0.5000001e-9 + 1e-12 * np.abs(D))
