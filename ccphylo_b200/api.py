@@ -28,7 +28,7 @@ EXPORTS = [
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
-    "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs",
+    "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs", "ccg_list_variants_row",
 ]
 
 MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "ln", "nl1", "nl2",
@@ -107,6 +107,7 @@ def load():
     L.ccg_run_global_dev.argtypes = [vp, vp, u, i, d, vp, C.POINTER(i), C.POINTER(u)]
     L.ccg_get_raw_counts.argtypes = [vp, vp, vp]
     L.ccg_list_variants.argtypes = [vp, i, vp, VARIANT_FN, vp]
+    L.ccg_list_variants_row.argtypes = [vp, i, VARIANT_FN, vp]
     L.ccg_run_row.argtypes = [vp, i, u, u, d, vp, vp, C.POINTER(i)]
     L.ccg_fsa_cmp_thread_out.argtypes = [vp, i, vp, vp, i, d, i, i, vp, vp, vp, u, u, d, u, C.POINTER(i), C.POINTER(u)]
     L.ccg_host_alloc.restype = vp
@@ -328,13 +329,17 @@ class Context:
                                      N.ctypes.data if want_n else None, C.byref(cols)))
         return D[:cols.value], (N[:cols.value] if want_n else None)
 
-    def list_variants(self, pair=True, include=None):
-        """-V: {(sample_i, sample_j): [(label, code_i, code_j), ...]} in the order the callback delivers them."""
+    def list_variants(self, pair=True, include=None, row=None):
+        """-V: [((sample_i, sample_j), [(label, code_i, code_j), ...]), ...] in the order the callback delivers them;
+        row = slot restricts the listing to that sample against the slots below it (-V with -a)."""
         out = []
 
         def take(user, si, sj, ptr, count):
             out.append(((si, sj), [(int(ptr[k] >> 4), int((ptr[k] >> 2) & 3), int(ptr[k] & 3)) for k in range(count)]))
             return 0
+        if row is not None:
+            self._ck(self._L.ccg_list_variants_row(self._h, row, VARIANT_FN(take), None))
+            return out
         inc = None if include is None else np.ascontiguousarray(include, dtype=np.uint8)
         self._ck(self._L.ccg_list_variants(self._h, 1 if pair else 0, None if inc is None else inc.ctypes.data,
                                            VARIANT_FN(take), None))

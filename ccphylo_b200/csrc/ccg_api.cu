@@ -1496,7 +1496,7 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
 }
 
 /* -V: fsacmpairint (fsacmp.c:685) / fsacmprint (:646) for every compared pair, see k_variants.cu */
-extern "C" int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *include, ccg_variant_fn fn, void *user) {
+static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *include, int last_row_only, ccg_variant_fn fn, void *user) {
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !fn) return CCG_ERR_ARG;
 	if(ctx->proxi || ctx->world > 1) {
 		set_err(ctx, "variant listing (-V) is not available together with %s", ctx->proxi ? "proximity masking (-P)" : "a rank partition");
@@ -1516,6 +1516,7 @@ extern "C" int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *in
 		if(ctx->present[i] && ctx->have[i >> 7] && (!include || include[i])) slot_of[Dn++] = i;
 	if(Dn < 2) { free(slot_of); return CCG_OK; }
 	const long long cells = (long long) Dn * (Dn - 1) / 2;
+	const long long cells_lo = last_row_only ? (long long) (Dn - 1) * (Dn - 2) / 2 : 0;
 	const int BATCH = 1 << 18;                       /* cells per count pass */
 	const size_t CAP = (size_t) 1 << 24;             /* entries per write pass (128 MiB) */
 	int *d_slot = 0;
@@ -1531,7 +1532,7 @@ extern "C" int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *in
 	h_off = (unsigned long long *) malloc((size_t) (BATCH + 1) * sizeof(unsigned long long));
 	if(e == cudaSuccess && (!h_counts || !h_off)) rc = CCG_ERR_NOMEM;
 	if(e == cudaSuccess && !rc) e = cudaMemcpyAsync(d_slot, slot_of, (size_t) Dn * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-	for(long long c0 = 0; c0 < cells && e == cudaSuccess && !rc; c0 += BATCH) {
+	for(long long c0 = cells_lo; c0 < cells && e == cudaSuccess && !rc; c0 += BATCH) {
 		const int nb = (int) (cells - c0 < BATCH ? cells - c0 : BATCH);
 		VariantParams p;
 		memset(&p, 0, sizeof(p));
@@ -1593,6 +1594,21 @@ extern "C" int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *in
 	free(h_counts);
 	free(h_off);
 	free(slot_of);
+	return rc;
+}
+
+extern "C" int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *include, ccg_variant_fn fn, void *user) {
+	return list_variants_impl(ctx, pair, include, 0, fn, user);
+}
+
+/* -V with -a: fsacmpairint(diffile, n, j, addL, seqL, ...) of cmpFsaRowThrd (fsacmpthrd.c:552-553) */
+extern "C" int ccg_list_variants_row(ccg_ctx *ctx, int row_slot, ccg_variant_fn fn, void *user) {
+	if(!ctx || !ctx->d_planes || row_slot < 0 || row_slot >= ctx->n || !ctx->present[row_slot]) return CCG_ERR_ARG;
+	unsigned char *use = (unsigned char *) calloc((size_t) ctx->n, 1);
+	if(!use) return CCG_ERR_NOMEM;
+	for(int j = 0; j <= row_slot; ++j) use[j] = ctx->present[j];
+	int rc = list_variants_impl(ctx, 1, use, 1, fn, user);
+	free(use);
 	return rc;
 }
 

@@ -16,7 +16,7 @@
  *   - -V (variant listing) comes from the device as well (ccg_list_variants, same labels as the reference);
  *     -a appends one row to an existing matrix (ccg_run_row / ccg_mat_run_row);
  *   - -y masks methylation motifs on the device right after each upload (ccg_mask_motifs);
- *   - refused: the combinations -V with -P, -a or -y; -y with -P.
+ *   - refused: the combinations -V with -P or -y; -y with -P (-a ignores -y, as the reference does).
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -701,6 +701,18 @@ static int add_fasta_row(const DistOpts *o, const PhyNames *phy, double *D, doub
 	pool_finish(pool);
 	for(int k = 0; k < window; ++k) bytebuf_free(&slots[k].codes);
 	free(slots);
+	if(len > 0 && o->diffilename) {
+		/* ltdFsaRowThrd appends to the variant file (fsacmpthrd.c:632-637) */
+		FILE *diffile = strcmp(o->diffilename, "-") == 0 ? stdout : fopen(o->diffilename, "ab");
+		if(!diffile) {
+			fprintf(stderr, "Filename:\t%s\n", o->diffilename);
+			die_errno();
+		}
+		rc = ccg_list_variants_row(ctx, n, print_variants, diffile);
+		if(rc) die_gpu(ctx, rc);
+		if(diffile != stdout) fclose(diffile);
+		else fflush(stdout);
+	}
 	if(len > 0) {
 		int cols = 0;
 		rc = ccg_run_row(ctx, n, o->norm, minLength, o->minCov, D, N, &cols);
@@ -948,12 +960,11 @@ int main_dist(int argc, char **argv) {
 	if(dist_mat_parse_method(&o)) die_invalid(o.method_err);
 	if(!o.numFile && o.targetTemplate) o.numFile = 1;
 
-	if((o.methfilename && (o.proxi || o.diffilename)) || (o.diffilename && (o.proxi || o.addfilename))) {
+	if((o.methfilename && !o.addfilename && (o.proxi || o.diffilename)) || (o.diffilename && o.proxi)) {
 		fprintf(stderr, "%s is not available on the GPU path of dist (use the CPU ccphylo for it).\n",
-		        o.methfilename ? (o.proxi ? "-y / --methylation_motifs together with -P / --proximity" :
+		        (o.methfilename && !o.addfilename) ? (o.proxi ? "-y / --methylation_motifs together with -P / --proximity" :
 		                                    "-y / --methylation_motifs together with -V / --nucleotide_variations") :
-		        o.proxi ? "-V / --nucleotide_variations together with -P / --proximity" :
-		                  "-V / --nucleotide_variations together with -a / --add");
+		                                   "-V / --nucleotide_variations together with -P / --proximity");
 		return 1;
 	}
 	if(o.addfilename && o.filenames) return add_to_matrix(&o);

@@ -229,6 +229,9 @@ int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned minLength, d
  * ccg_build_global_mask and BEFORE ccg_run_global.  Not with -P. */
 typedef int (*ccg_variant_fn)(void *user, int sample_i, int sample_j, const uint64_t *variants, size_t count);
 int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *include, ccg_variant_fn fn, void *user);
+/* The same for the row of ccg_run_row (-V with -a: fsacmpairint(diffile, n, j, ...) in cmpFsaRowThrd,
+ * fsacmpthrd.c:552-553): the pairs (row_slot, j) of the uploaded slots j below row_slot. */
+int ccg_list_variants_row(ccg_ctx *ctx, int row_slot, ccg_variant_fn fn, void *user);
 
 /* Raw integer results of the last pair-mode run for included samples:
  * mismatch counts and inclusion counts as u32, same packed layout.  HOST

@@ -44,6 +44,10 @@ def test_fasta_row_against_the_oracle(ctx, n, length, kernel):
             assert np.array_equal(N.view(np.uint8), No.view(np.uint8))
         if n > 3:
             assert D[2] == -1.0 and N[2] == 0.0
+        # -V with -a: the row's variant lists
+        got = ctx.list_variants(row=n)
+        want = [((n, j), v) for j in range(n) for v in [oracle.list_variants(seqs[n], seqs[j], masks[n] & masks[j], length)] if v]
+        assert got == want
         # the full matrix still comes out right on the same store afterwards (the row mode leaves no state behind)
         Df, Nf, dn = ctx.run_pair(norm=1000, min_length=1, min_cov=0.5)
         Dw, Nw, dnw = oracle.fsa_cmp_pair(seqs, masks, np.ones(n + 1, np.uint8), length, norm=1000, min_length=1, min_cov=0.5)
@@ -144,6 +148,29 @@ def test_cli_add_fasta_row_against_the_reference_binary(built, tmp_path, args):
         outs[tag] = (open(os.path.join(d, "m.phy")).read(), open(os.path.join(d, "m.num")).read(),
                      sorted(p.stderr.replace(d + "/", "").splitlines()))
     assert outs["reference"][0].startswith("%10d\n" % (n + 1)) and "\t-1" in outs["reference"][0].splitlines()[-1]
+    assert outs["driver"] == outs["reference"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
+def test_cli_add_row_with_variant_file_against_the_reference_binary(built, tmp_path):
+    """-a with -V: the new row's variant lists are appended to the file (fsacmpthrd.c:632-637, :552-553)"""
+    n, length = 6, 8000 + 3
+    rows = synth.make_ascii(n + 1, length, seed=33, snp=0.01, nrun=0.01)
+    outs = {}
+    for tag, exe in (("reference", REF_BIN), ("driver", BIN)):
+        d = tmp_path / tag
+        d.mkdir()
+        d = str(d)
+        for i in range(n + 1):
+            synth.write_fasta(os.path.join(d, f"s{i}.fsa"), rows[i], header="ref", width=60)
+        files = [os.path.join(d, f"s{i}.fsa") for i in range(n)]
+        p = _run([REF_BIN, "dist", "-r", "ref", "-f", "3", "-t", "1", "-V", "v.txt", "-i"] + files + ["-o", "m.phy", "-n", "m.num"], d)
+        assert p.returncode == 0, p.stderr
+        p = _run([exe, "dist", "-r", "ref", "-f", "3", "-t", "1", "-V", "v.txt", "-a", os.path.join(d, f"s{n}.fsa"), "-i", files[0],
+                  "-o", "m.phy", "-n", "m.num"], d)
+        assert p.returncode == 0, p.stderr
+        outs[tag] = (open(os.path.join(d, "v.txt")).read(), open(os.path.join(d, "m.phy")).read(), open(os.path.join(d, "m.num")).read())
+    assert ("(%d, 0)\t" % n) in outs["reference"][0] and outs["reference"][0].startswith("(1, 0)\t")
     assert outs["driver"] == outs["reference"]
 
 
