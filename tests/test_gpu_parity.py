@@ -258,14 +258,14 @@ def test_empty_and_degenerate_inputs(ctx):
     # nothing included
     D, N, dn, _ = api.fsa_cmp_thread_out(seqs, np.zeros(3, np.uint8), masks, 100, pair=True, ctx=ctx)
     assert dn == 0 and len(D) == 0
-    # an unsupported combination is a loud refusal, never a silent fallback: a row against an existing matrix
-    # (-a) with proximity masking (-P)
+    # an unsupported combination is a loud refusal, never a silent fallback: variant lists (-V) with proximity
+    # masking (-P)
     ctx.set_problem(3, 100, pair=True)
     ctx.put_samples_packed(seqs, masks)
     ctx.set_proximity(3)
     try:
         with pytest.raises(api.CcgError) as e:
-            ctx.run_row(2)
+            ctx.list_variants(pair=True)
         assert e.value.code == 5
     finally:
         ctx.set_proximity(0)
