@@ -1522,12 +1522,11 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 	int *d_slot = 0;
 	unsigned *d_counts = 0, *h_counts = 0;
 	unsigned long long *d_off = 0, *h_off = 0, *d_ent = 0, *h_ent = 0;
+	size_t ent_cap = 0;
 	int rc = CCG_OK;
 	cudaError_t e = cudaMalloc(&d_slot, (size_t) Dn * sizeof(int));
 	if(e == cudaSuccess) e = cudaMalloc(&d_counts, (size_t) BATCH * sizeof(unsigned));
 	if(e == cudaSuccess) e = cudaMalloc(&d_off, (size_t) (BATCH + 1) * sizeof(unsigned long long));
-	if(e == cudaSuccess) e = cudaMalloc(&d_ent, CAP * sizeof(unsigned long long));
-	if(e == cudaSuccess) e = cudaMallocHost(&h_ent, CAP * sizeof(unsigned long long));
 	h_counts = (unsigned *) malloc((size_t) BATCH * sizeof(unsigned));
 	h_off = (unsigned long long *) malloc((size_t) (BATCH + 1) * sizeof(unsigned long long));
 	if(e == cudaSuccess && (!h_counts || !h_off)) rc = CCG_ERR_NOMEM;
@@ -1546,6 +1545,18 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 		if(e != cudaSuccess) break;
 		h_off[0] = 0;
 		for(int k = 0; k < nb; ++k) h_off[k + 1] = h_off[k] + h_counts[k];
+		/* the entry buffers grow to what a batch needs, up to CAP entries (most listings are small) */
+		size_t want = h_off[nb] < CAP ? (size_t) h_off[nb] : CAP;
+		for(int k = 0; k < nb; ++k)
+			if(h_counts[k] > want) want = h_counts[k] < CAP ? h_counts[k] : CAP;
+		if(want > ent_cap) {
+			cudaFree(d_ent); d_ent = 0;
+			cudaFreeHost(h_ent); h_ent = 0;
+			ent_cap = want < 65536 ? 65536 : want;
+			e = cudaMalloc(&d_ent, ent_cap * sizeof(unsigned long long));
+			if(e == cudaSuccess) e = cudaMallocHost(&h_ent, ent_cap * sizeof(unsigned long long));
+			if(e != cudaSuccess) break;
+		}
 		e = cudaMemcpyAsync(d_off, h_off, (size_t) (nb + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream);
 		/* write passes over runs of cells whose lists fit the entry buffer */
 		int k0 = 0;
