@@ -335,7 +335,9 @@ class Context:
         out = []
 
         def take(user, si, sj, ptr, count):
-            out.append(((si, sj), [(int(ptr[k] >> 4), int((ptr[k] >> 2) & 3), int(ptr[k] & 3)) for k in range(count)]))
+            v = np.ctypeslib.as_array(ptr, shape=(count,))
+            out.append(((si, sj), list(zip((v >> np.uint64(4)).tolist(), ((v >> np.uint64(2)) & np.uint64(3)).tolist(),
+                                           (v & np.uint64(3)).tolist()))))
             return 0
         if row is not None:
             self._ck(self._L.ccg_list_variants_row(self._h, row, VARIANT_FN(take), None))

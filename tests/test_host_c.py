@@ -31,6 +31,38 @@ def test_proximity_arithmetic_of_the_kernels_on_the_host(built, tmp_path):
         assert p.returncode == 0 and p.stdout.startswith("OK "), p.stdout + p.stderr
 
 
+def test_motif_file_parser_matches_the_oracle(built, tmp_path):
+    """host/motifs.c (the driver's -y parser: IUPAC sets, methylation sites, the reference's reverse complement of
+    odd-length motifs, its as-built padding of ambiguity letters and CCPHYLO_MOTIF_STRICT) against oracle.parse_motifs,
+    which tests/test_oracle_vs_reference.py pins to the reference's getMethMotifs + maskMotifs"""
+    import oracle
+    exe = str(tmp_path / "motifs_test")
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "motifs_test.c"),
+                    os.path.join(HOST, "motifs.c"), os.path.join(HOST, "fsa_reader.c"), "-lz"], check=True)
+    files = [">dam\ngAtc\n", ">dam\ngAtc\n>dcm\ncCwgg\n>x\nrgATcnny\n", "gatC\n>multi line\ncC\nwg\ng\n>odd chars\nGA-NT.C\r\n",
+             ">long\nacgtacgtAcgtacgtacgtacgTacgtacgt\n>three\ngAn\n>iupac\nRYSWKMBDHVN\n>u\nUu\n>empty\n>x\nXx\n"]
+    for k, text in enumerate(files):
+        path = str(tmp_path / f"m{k}.fsa")
+        with open(path, "w") as f:
+            f.write(text)
+        for strict in (False, True):
+            env = dict(os.environ)
+            env.pop("CCPHYLO_MOTIF_STRICT", None)
+            if strict:
+                env["CCPHYLO_MOTIF_STRICT"] = "1"
+            p = subprocess.run([exe, path], capture_output=True, text=True, env=env)
+            assert p.returncode == 0, p.stderr
+            got = [[int(x) for x in line.split()] for line in p.stdout.splitlines()]
+            assert got == oracle.parse_motifs(text, as_built=not strict), (k, strict)
+    path = str(tmp_path / "toolong.fsa")
+    with open(path, "w") as f:
+        f.write(">m\n" + "acgt" * 8 + "a\n")
+    p = subprocess.run([exe, path], capture_output=True, text=True)
+    assert p.returncode == 1 and "more than 32 positions" in p.stderr
+    p = subprocess.run([exe, str(tmp_path / "missing.fsa")], capture_output=True, text=True)
+    assert p.returncode == 1 and "Filename:" in p.stderr
+
+
 def test_option_scanner_dialect(built, tmp_path):
     def run(*args):
         return subprocess.run([BIN, "dist"] + list(args), capture_output=True, text=True, cwd=str(tmp_path))
