@@ -44,7 +44,8 @@ OrderedPool *pool_start(int njobs, int nthreads, int window, void *states, unsig
 	if(!p) return 0;
 	if(nthreads < 1) nthreads = 1;
 	if(nthreads > njobs) nthreads = njobs > 0 ? njobs : 1;
-	if(window < nthreads) window = nthreads;
+	if(window < 1) window = 1;
+	if(nthreads > window) nthreads = window;      /* the caller's state array has `window` slots: never index past it */
 	p->njobs = njobs;
 	p->nthreads = nthreads;
 	p->window = window;

@@ -63,6 +63,108 @@ def test_motif_file_parser_matches_the_oracle(built, tmp_path):
     assert p.returncode == 1 and "Filename:" in p.stderr
 
 
+def test_ordered_parse_pool(tmp_path):
+    """host/ordered_pool.c: results in job order, slots not reused before release, look-ahead bounded by the window,
+    more threads than window slots or jobs"""
+    exe = str(tmp_path / "ordered_pool_test")
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "ordered_pool_test.c"),
+                    os.path.join(HOST, "ordered_pool.c"), "-lpthread"], check=True)
+    for args in (("300", "8", "10"), ("50", "16", "3"), ("5", "8", "10"), ("100", "1", "1"), ("64", "4", "4")):
+        p = subprocess.run([exe] + list(args), capture_output=True, text=True, timeout=60)
+        assert p.returncode == 0 and p.stdout.strip() == "OK", (args, p.stdout)
+
+
+def _readers_exe(tmp_path):
+    exe = str(tmp_path / "readers_test")
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "readers_test.c"),
+                    os.path.join(HOST, "fsa_reader.c"), os.path.join(HOST, "mat_reader.c"), "-lz"], check=True)
+    return exe
+
+
+def test_fasta_reader_matches_the_oracle_translation(built, tmp_path):
+    """host/fsa_reader.c (gzip-transparent buffer, header / sequence scanning of seqparse.c:128-248, the byte -> code
+    table of fsacmp.c:32-91 for every -f variant) against oracle.translate, itself pinned to the reference's table"""
+    import gzip
+    import numpy as np
+    import oracle
+    exe = _readers_exe(tmp_path)
+    rng = np.random.default_rng(4)
+    alphabet = np.frombuffer(b"ACGTacgtNn-RYKMSWBDHVryUuXx*. 1\r", dtype=np.uint8)
+    records = []
+    for k in range(6):
+        n = [0, 1, 59, 60, 61, 5000][k]
+        seq = alphabet[rng.integers(0, len(alphabet), size=n)].tobytes().replace(b">", b"A")
+        records.append((b"rec%d some text \t " % k if k % 2 else b"rec%d" % k, seq))
+    text = b""
+    for hdr, seq in records:
+        text += b">" + hdr + b"\n"
+        for s0 in range(0, len(seq), 60):
+            text += seq[s0:s0 + 60] + b"\n"
+    text += b">last header without sequence"
+    plain = str(tmp_path / "a.fsa")
+    with open(plain, "wb") as f:
+        f.write(text)
+    with gzip.open(plain + ".gz", "wb") as f:
+        f.write(text)
+    for flag in (1, 9, 33, 41):
+        outs = []
+        for path in (plain, plain + ".gz"):
+            p = subprocess.run([exe, "fsa", str(flag), path], capture_output=True)
+            assert p.returncode == 0
+            outs.append(p.stdout)
+        lines = outs[0].split(b"\n")
+        assert lines[0] == b"first=62 plain=1" and outs[1].split(b"\n")[0] == b"first=62 plain=0"
+        assert outs[0].split(b"\n")[1:] == outs[1].split(b"\n")[1:]
+        k = 1
+        offset = 0
+        for hdr, seq in records:
+            name, at = lines[k].rsplit(b" @", 1)
+            assert name == b">" + hdr.rstrip() and int(at) == offset
+            want = oracle.translate(seq.replace(b"\n", b""), flag)
+            assert lines[k + 1] == bytes(want + ord("0")), (flag, hdr)
+            k += 2
+            offset += 1 + len(hdr) + 1 + len(seq) + (len(seq) + 59) // 60
+        # a header that runs into the end of the file is no record (FileBuffgetFsaHeader returns 0, seqparse.c:128-160)
+        assert lines[k:] == [b""]
+
+
+def test_mat_reader_matches_a_plain_parse(built, tmp_path):
+    """host/mat_reader.c against helpers.parse_mat (the storage order and totals of matparse.c:213-259): template
+    selection among several, insertion rows dropped, gz input, a template that is absent"""
+    import gzip
+    import numpy as np
+    import helpers
+    exe = _readers_exe(tmp_path)
+    rng = np.random.default_rng(7)
+    blocks = []
+    for name, rows in (("other template", 40), ("tmpl", 300), ("tail", 5)):
+        ref = "".join("ACGT-"[k] for k in rng.integers(0, 5, size=rows))
+        counts = rng.integers(0, 70, size=(rows, 6))
+        counts[rng.random(rows) < 0.1] = 0
+        blocks.append((name, ref, counts))
+    text = "".join(helpers.mat_text(nm, ref, c) for nm, ref, c in blocks)
+    path = str(tmp_path / "s.mat")
+    with open(path, "w") as f:
+        f.write(text)
+    with gzip.open(path + ".gz", "wt") as f:
+        f.write(text)
+    for target in ("tmpl", "other template", "tail", "absent"):
+        for min_depth in (1, 15):
+            for q in (path, path + ".gz"):
+                p = subprocess.run([exe, "mat", str(min_depth), q, target], capture_output=True, text=True)
+                assert p.returncode == 0
+                lines = p.stdout.splitlines()
+                want = helpers.parse_mat(text, target)
+                if want is None:
+                    assert lines == ["status=0"]
+                    continue
+                counts, totals = want
+                assert lines[0] == "status=1"
+                assert lines[1] == "%d %d" % (len(totals), int((totals >= min_depth).sum()))
+                got = np.array([[int(x) for x in ln.split()] for ln in lines[2:]], dtype=np.int64).reshape(-1, 7)
+                assert np.array_equal(got[:, :6], counts.astype(np.int64)) and np.array_equal(got[:, 6], totals.astype(np.int64))
+
+
 def test_option_scanner_dialect(built, tmp_path):
     def run(*args):
         return subprocess.run([BIN, "dist"] + list(args), capture_output=True, text=True, cwd=str(tmp_path))
