@@ -372,6 +372,10 @@ def ref():
         R.refshim_and_known.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint]
         R.refshim_inc_pos.restype = None
         R.refshim_inc_pos.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint, C.c_uint]
+        R.refshim_phy_names.restype = C.c_int
+        R.refshim_phy_names.argtypes = [C.c_char_p, C.c_char_p, C.c_char, C.c_char_p, C.c_long]
+        R.refshim_phy_update.restype = None
+        R.refshim_phy_update.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.c_uint, C.c_int]
         R.refshim_mask_motifs.restype = C.c_int
         R.refshim_mask_motifs.argtypes = [C.c_char_p, _u64p, _u32p, C.c_int]
         R.refshim_variants.restype = C.c_uint64
@@ -418,6 +422,20 @@ def ref_pair(seq_i, seq_j, inc_i, inc_j, length, proxi=0):
     r = ref().refshim_pair(pad(seq_i, np.uint64), pad(seq_j, np.uint64), pad(inc_i, np.uint32), pad(inc_j, np.uint32),
                            length, proxi)
     return int(r >> 32), int(r & 0xFFFFFFFF)
+
+
+def ref_phy_names(phy_path, directory, sep="\t"):
+    """getSizePhy + getFilenamesPhy of the reference -> (n or error code, [names])"""
+    buf = C.create_string_buffer(1 << 20)
+    n = ref().refshim_phy_names(phy_path.encode(), directory.encode(), sep.encode(), buf, len(buf))
+    return n, buf.value.decode().split("\n")[:-1]
+
+
+def ref_phy_update(phy_path, n, name, row, flag=1, precision=9):
+    """printphyUpdate of the reference on the file"""
+    row = np.ascontiguousarray(row, dtype=np.float64)
+    ref().refshim_phy_update(phy_path.encode(), n, C.create_string_buffer(name.encode()), row.ctypes.data_as(C.POINTER(C.c_double)),
+                             flag, precision)
 
 
 def ref_mask_motifs(motif_path, seq, mask, length):

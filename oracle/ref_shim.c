@@ -84,6 +84,40 @@ uint64_t refshim_pair(uint64_t *seq_i, uint64_t *seq_j, uint32_t *inc_i,
 	return r;
 }
 
+/* -a: getSizePhy + getFilenamesPhy (phy.c:509-650) on an existing Phylip file: the names (prefixed with dir) joined
+ * by '\n' into buf; returns n, -1 if the names cannot be read, -2 if bytes are left behind the n rows (dist.c:366) */
+#include "phy.h"
+int refshim_phy_names(char *phyname, char *dir, char sep, char *buf, long cap) {
+	FileBuff *infile = setFileBuff(1048576);
+	Qseqs **names;
+	int n, i, left;
+	long used = 0;
+	openAndDetermine(infile, phyname);
+	n = getSizePhy(infile);
+	names = getFilenamesPhy(dir, n, infile, sep);
+	if(!names) return -1;
+	left = infile->bytes;
+	buf[0] = 0;
+	for(i = 0; i < n; ++i) {
+		long l = (long) strlen((char *) names[i]->seq);
+		if(used + l + 2 > cap) break;
+		memcpy(buf + used, names[i]->seq, (size_t) l);
+		used += l;
+		buf[used++] = '\n';
+		buf[used] = 0;
+	}
+	closeFileBuff(infile);
+	return left ? -2 : n;
+}
+
+/* -a: printphyUpdate (phy.c:201-250) after setPrecisionPhy */
+void refshim_phy_update(char *phyname, int n, char *name, double *row, unsigned flag, int precision) {
+	FILE *f = fopen(phyname, "rb+");
+	setPrecisionPhy(precision);
+	printphyUpdate(f, n, name, row, flag);
+	fclose(f);
+}
+
 /* -y: getMethMotifs (methparse.c:268) on the motif file, then maskMotifs (meth.c:141) on one packed sequence */
 #include "filebuff.h"
 #include "meth.h"

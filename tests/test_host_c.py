@@ -63,6 +63,54 @@ def test_motif_file_parser_matches_the_oracle(built, tmp_path):
     assert p.returncode == 1 and "Filename:" in p.stderr
 
 
+def test_phylip_update_matches_the_reference(built, tmp_path):
+    """host/phy_update.c (-a: names of the existing matrix, row append) against the reference's own getSizePhy /
+    getFilenamesPhy / printphyUpdate called in-process: relaxed and strict names, a comment line (which both
+    overwrite with the new count), quoted names, precision, a second matrix in the file"""
+    import shutil
+    import numpy as np
+    import oracle
+    if not oracle.have_ref():
+        import pytest
+        pytest.skip("oracle/_ref was not built (needs /root/reference)")
+    exe = str(tmp_path / "phy_update_test")
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "phy_update_test.c"),
+                    os.path.join(HOST, "phy_update.c"), os.path.join(HOST, "fsa_reader.c"), "-lz"], check=True)
+    relaxed = "%10d\nsample_a.fsa\ns_b\t12\nanother name.fsa\t3.500000000\t-1\n" % 3
+    strict = "%10d\n%-10.10s\n%-10.10s\t12\n%-10.10s\t3\t4\n" % (3, "s0.fsa", "a_long_name_cut", "x")
+    comment = "#tmpl\n" + relaxed
+    two = relaxed + relaxed
+    cases = {"relaxed": relaxed, "strict": strict, "comment": comment, "two": two, "one": "%10d\nonly\n" % 1}
+    for tag, text in cases.items():
+        path = str(tmp_path / (tag + ".phy"))
+        with open(path, "w") as f:
+            f.write(text)
+        n_ref, names_ref = oracle.ref_phy_names(path, "dir/sub/")
+        p = subprocess.run([exe, "names", path, "dir/sub/", "\t"], capture_output=True, text=True)
+        assert p.returncode == 0
+        lines = p.stdout.splitlines()
+        if tag == "two":
+            assert n_ref == -2 and lines == ["-1"] and p.stderr == "Cannot update a multi distance phylip file.\n"
+            continue
+        if tag == "one":
+            assert n_ref == -1 and lines == ["0"] and p.stderr == "Malformatted phylip file, name on row: 1\n"
+            continue
+        assert lines[0] == "1" and n_ref == len(lines) - 1
+        assert lines[1:] == names_ref, tag
+        # append a row with both
+        n = n_ref + 1
+        row = np.array([0.0, 17.0, 2.123456789123, -1.0][: n - 1])
+        for flag, precision, name in ((1, 9, "path/to/new sample.fsa"), (0, 4, "'quoted_and_long_name.fsa'"), (1, 2, '"q.fsa"')):
+            a, b = str(tmp_path / "a.phy"), str(tmp_path / "b.phy")
+            shutil.copy(path, a)
+            shutil.copy(path, b)
+            oracle.ref_phy_update(a, n, name, row, flag, precision)
+            p = subprocess.run([exe, "append", b, str(n), name, str(flag), str(precision)] + [repr(float(x)) for x in row],
+                               capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+            assert open(a, "rb").read() == open(b, "rb").read(), (tag, flag, precision, name)
+
+
 def test_ordered_parse_pool(tmp_path):
     """host/ordered_pool.c: results in job order, slots not reused before release, look-ahead bounded by the window,
     more threads than window slots or jobs"""
