@@ -786,7 +786,7 @@ extern "C" int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out) {
  * (tile, K slice) items; with `slots` items in flight the last wave is only partly filled, and at 820 tiles on 74
  * CTA pairs (10 k samples, one GPU) an unsplit run idles 7.7 % of the machine in it.  The smallest split that fills
  * the waves to 99 % is taken (measured there: GEMM 304 -> 282 ms with 6 slices), else the best one found. */
-static int choose_split(long long slots, long long ntiles, int iters_total, int min_iters, int max_split) {
+static int choose_split(long long slots, long long ntiles, int iters_total, int min_iters, int max_split, int even_tail = 1) {
 	int best = 1;
 	double best_util = -1.0;
 	for(int k = 1; k <= max_split; ++k) {
@@ -794,10 +794,12 @@ static int choose_split(long long slots, long long ntiles, int iters_total, int 
 		long long items = ntiles * k;
 		long long waves = (items + slots - 1) / slots;
 		double util = (double) items / (double) (waves * slots);
-		if(util > best_util + 0.005) { best_util = util; best = k; }
+		if(util > best_util + (even_tail ? 0.005 : 0.02)) { best_util = util; best = k; }
 		if(util >= 0.99) break;
-		/* plenty of waves already: a few more slices are enough to even out the tail */
-		if(items >= 8 * slots && k >= 16) break;
+		/* plenty of waves already: a few more slices are enough to even out the tail.  Not when the run is fed from
+		 * the host slab by slab (even_tail == 0): there the GEMM hides behind the PCIe upload and more slices only
+		 * add accumulator traffic. */
+		if(items >= 8 * slots && (!even_tail || k >= 16)) break;
 	}
 	return best;
 }
@@ -1157,7 +1159,8 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 			p.ntiles = (int) (2 * cnt);
 			p.tiles = ctx->d_tiles + cnt;
 		}
-		p.kslices = choose_split((long long) (p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx)), (long long) p.ntiles, nu, fp4 ? 8 : 16, 512);
+		p.kslices = choose_split((long long) (p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx)), (long long) p.ntiles, nu, fp4 ? 8 : 16, 512,
+		                        ctx->feed_seqs ? 0 : 1);
 		/* f32 accumulators: an S item adds at most 3 * 256 per chunk pair and must stay below 2^24 */
 		if(fp4 && (nu + p.kslices - 1) / p.kslices > 20000) p.kslices = (nu + 19999) / 20000;
 		p.chunks_per_slice = (nu + p.kslices - 1) / p.kslices;
