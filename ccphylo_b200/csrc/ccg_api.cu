@@ -1491,6 +1491,7 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
 		ctx->row_slot1 = row_slot + 1;
 		rc = run_common(ctx, 0, use, norm, minLength, minCov, 8, 1.0, ctx->d_out_D, ctx->d_out_N, &Dn);
 		ctx->row_slot1 = 0;
+		ctx->last_Dn = 0;               /* one tile stripe only: nothing for ccg_get_raw_counts to gather */
 	}
 	ctx->win_on = win_on;
 	memcpy(ctx->win, win, sizeof(win));
