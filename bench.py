@@ -9,9 +9,12 @@ encode (reference packed words -> device bit planes) + all-vs-all compare + fuse
 (packed lower-triangular D and N as doubles).  Workload: the configuration BASELINE.json's
 metric is quoted on -- 10,000 samples x 5 Mbp, pair mode, -n (configs[2]; it fits one B200:
 19 GB of bit planes, the int8 operand panel is processed in K slabs).  The job is the same
-at every N ("strong"): the lower-triangular macro tiles are cut into N contiguous runs of a
-Z-order curve, one per rank, with no data-path collective.  `--scaling weak` instead grows
-the sample count with sqrt(N) so the pairs per GPU stay fixed.
+at every N ("strong").  At N > 1 the ALIGNMENT axis is cut (K split): every GPU holds 1/N of
+the bases of every sample, runs all macro tiles on its slice, and the int32 partial sums are
+added by the GPU that owns a matrix row, through peer pointers over NVLink, inside its
+epilogue kernel (ccphylo_b200/csrc/ccg_group.cu).  `--scaling weak` instead grows the sample
+count with sqrt(N).  `--workload ring|mat` measures BASELINE configs[3] / configs[4]
+(bench_workloads.py).
 
 `value`  : inputs resident in HBM (reference packed format) when the timed region starts.
 `e2e`    : the same metric through the reference-facing C-ABI call with HOST buffers
@@ -196,19 +199,44 @@ def reference_arm(args, rank, world):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def parity_sample_ids(n, count=128, seed=12345):
+    """Sample slots for the parity check, stratified over the 256-sample row blocks so that the pairs among them
+    fall into EVERY macro tile of the lower triangle (>= 2 samples per block when count allows it)."""
+    rng = np.random.default_rng(seed)
+    blocks = (n + 255) // 256
+    per = max(2, count // blocks)
+    ids = []
+    for b in range(blocks):
+        lo, hi = b * 256, min(n, b * 256 + 256)
+        k = min(per, hi - lo)
+        ids.extend(rng.choice(np.arange(lo, hi), size=k, replace=False).tolist())
+    return np.array(sorted(ids), dtype=np.int64)
+
+
+def packed_index(ids):
+    """Packed lower-triangular cell of every pair (a > b) among `ids`, in the order of a matrix over just those samples."""
+    r, c = np.tril_indices(len(ids), -1)
+    hi, lo = ids[r], ids[c]
+    return hi * (hi - 1) // 2 + lo, hi
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--samples", type=int, default=BASE_SAMPLES, help="samples (at N=1 when --scaling weak)")
+    ap.add_argument("--workload", default="fasta", choices=["fasta", "ring", "mat"],
+                    help="fasta: BASELINE configs[2], the metric's own configuration (default); ring: configs[3]; mat: configs[4]")
+    ap.add_argument("--samples", type=int, default=None, help="samples (at N=1 when --scaling weak)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--length", type=int, default=LENGTH)
+    ap.add_argument("--length", type=int, default=None)
     ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "umma", "fused"])
+    ap.add_argument("--method", default="cos", help="--workload mat: the -d method")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--parity-samples", type=int, default=128)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,6 +245,13 @@ def main():
     if world != args.gpus and world > 1:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}")
 
+    if args.workload != "fasta":
+        import bench_workloads
+        return bench_workloads.main(args, rank, world, local_rank, emit, log, ClockSampler, measured_peaks)
+    if args.samples is None:
+        args.samples = BASE_SAMPLES
+    if args.length is None:
+        args.length = LENGTH
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
@@ -238,12 +273,19 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
+    # ---- the workload: n samples x `length` bp; at N > 1 the ALIGNMENT is cut (K split): rank r holds the bases
+    # [b_r, b_r+1) of every sample and synthesises just that slice (the alignment is the concatenation) ----
     n, length = samples_for(world, args.samples, args.scaling), args.length
-    W = api.words(length)
+    slices = api.group_slices(length, world)
+    b0, b1 = slices[rank], slices[rank + 1]
+    len_r = b1 - b0
+    if len_r < 256:
+        raise SystemExit(f"bench.py: {length} bp cannot be cut into {world} slices of at least 256 bp")
+    W = api.words(len_r)
     t_gen = time.time()
-    seqs_t, masks_t = synth.make_packed_torch(n, length, seed=2, device=dev)
+    seqs_t, masks_t = synth.make_packed_torch(n, len_r, seed=2 + 1000 * rank, device=dev)
     torch.cuda.synchronize()
-    log(f"[rank {rank}] generated {n} x {length} bp in {time.time() - t_gen:.1f}s")
+    log(f"[rank {rank}] generated {n} x {len_r} bp (bases {b0}..{b1} of {length}) in {time.time() - t_gen:.1f}s")
 
     ctx = api.Context(local_rank)
     # a real (non-default) stream: the library launches on it and the torch events below see the work
@@ -254,12 +296,18 @@ def main():
     use_umma = args.kernel in ("auto", "umma", "fused")   # AUTO resolves to a tensor kernel at bench sizes
     ctx.set_kernel({"auto": api.KERNEL_AUTO, "popc": api.KERNEL_POPC, "umma": api.KERNEL_UMMA,
                     "fused": api.KERNEL_FUSED}[args.kernel])
-    ctx.set_partition(rank, world)
-    ctx.set_problem(n, length, pair=True)
+    if world > 1:
+        # K-split group, one process per GPU: exchange the CUDA IPC handles of the accumulator windows
+        handle = ctx.group_export(n)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        ctx.group_join(rank, world, handles)
+        ctx.group_set_alignment(length)
+    ctx.set_problem(n, len_r, pair=True)
     ncell = api.cells(n)
     d_D = torch.zeros(ncell, dtype=torch.float64, device=dev)
     d_N = torch.zeros(ncell, dtype=torch.float64, device=dev)
-    my_cells = api.partition_cells(n, rank, world)
+    row_lo, row_hi = api.group_rows(n, rank, world)
     total_basecmp = float(ncell) * length
 
     def step():
@@ -280,18 +328,14 @@ def main():
     time.sleep(0.3)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
     t0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
-        # per-launch device time of the compare kernel: CUDA events recorded by the library on
-        # the same stream around that launch (read after the region, see below)
     ev1.record(stream)
     barrier()
     t1 = time.time()
     ms_total = ev0.elapsed_time(ev1)
-    kms.append(ctx.last_compare_ms())
     clocks = sampler.stop(t0, t1)
     launches = ctx.launches - launches0
     if world > 1:
@@ -318,12 +362,12 @@ def main():
             kern_ms.append(ctx.last_compare_ms())
     kern_ms = float(np.mean(kern_ms))
     compare_ms = float(np.mean(compare_ms))
+    barrier()
     peaks, peaks_src = measured_peaks()
     int8_2x_bf16 = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-    # the tensor pipe's own int8 rate on this GPU under this box's power cap: a loads-free loop of the
-    # kernel's MMA shape (tcgen05 kind::i8, cta_group::2, 256x256x32), run about as long as the GEMM phase
-    # (sustained) and for a few ms (burst).  MEASURED_PEAKS.json only holds bf16, and 2 x that figure
-    # under-states what kind::i8 delivers here (the GEMM itself exceeds it), so it is reported beside.
+    # the tensor pipe's own rate on this GPU under this box's power cap: a loads-free loop of the kernel's MMA kind
+    # and shape (tcgen05, cta_group::2, 256x256), run about as long as the GEMM phase (sustained) and for a few ms
+    # (burst).  MEASURED_PEAKS.json only holds bf16; 4 x / 2 x that figure is reported beside.
     i8_burst = i8_sustained = fp4_burst = fp4_sustained = None
     fp4_inexact = None
     is_fp4 = "mxf4" in ctx.last_kernel
@@ -338,130 +382,112 @@ def main():
             raise SystemExit("bench.py: the kind::mxf4 accumulators are not exact on this device -- number withheld")
     own_peak = fp4_sustained if is_fp4 else i8_sustained
     pipe_peak = own_peak if (own_peak and own_peak > 0) else int8_2x_bf16
-    int8_peak = pipe_peak
-    my_basecmp = float(my_cells) * length
-    # algorithmic work of this rank's launch: every owned macro tile is a full 128 x 256 block of
-    # the contraction only for the tensor kernel's own accounting; the roofline uses the USEFUL
-    # pairwise base comparisons (cells of the strict lower triangle) x 8 int8 ops
+    # algorithmic work of this rank's GEMM launches: the USEFUL pairwise base comparisons (cells of the strict lower
+    # triangle) x the bases of this rank's slice x 8 tensor ops
+    my_basecmp = float(ncell) * len_r
     achieved = OPS_PER_BASECMP * my_basecmp / (kern_ms * 1e-3) / 1e12
+    step_frac = OPS_PER_BASECMP * total_basecmp / (ms_step * 1e-3) / 1e12 / (world * pipe_peak)
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this workload
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_umma2_mxf4_10k_traffic.json" if "mxf4" in ctx.last_kernel
-                         else "r01_umma2_10k_traffic.json")
-    if use_umma and world == 1 and os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        if tj["samples"] == n and tj["length"] == length and tj["kernel"] in ctx.last_kernel and \
-                tj.get("operands", "i8") == ("mxf4" if is_fp4 else "i8"):
-            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
-            # the capture cut the K axis into more launches than this run: scale to this run's launches per step
-            nslabs_now = int(ctx.last_kernel.split("slabs=")[1]) if "slabs=" in ctx.last_kernel else 1
-            traffic = traffic * tj.get("launches_per_step_in_capture", nslabs_now) / max(nslabs_now, 1)
+    tnote = None
+    for tname in ("r02_umma2_mxf4_10k_traffic.json", "r01_umma2_mxf4_10k_traffic.json") if is_fp4 else ("r01_umma2_10k_traffic.json",):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if use_umma and world == 1 and os.path.exists(tpath) and traffic is None:
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj["samples"] == n and tj["length"] == length and tj["kernel"] in ctx.last_kernel and \
+                    tj.get("operands", "i8") == ("mxf4" if is_fp4 else "i8"):
+                traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+                # a capture that cut the K axis into more launches than this run: scale to this run's launches per step
+                nslabs_now = int(ctx.last_kernel.split("slabs=")[1].split()[0]) if "slabs=" in ctx.last_kernel else 1
+                traffic = traffic * tj.get("launches_per_step_in_capture", nslabs_now) / max(nslabs_now, 1)
+                tnote = f"DRAM bytes per GEMM launch from the committed ncu --set full capture profiles/{tname}"
     roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": int8_peak,
+        "bound": "tensor", "achieved": achieved, "peak": pipe_peak,
         "unit": "TOP/s (e2m1 x e2m1 -> f32, kind::mxf4)" if is_fp4 else "TOP/s (int8)",
-        "frac": achieved / int8_peak, "traffic": traffic,
-        "traffic_note": "DRAM bytes per GEMM launch from the committed ncu --set full capture of this workload" if traffic else None,
+        "frac": achieved / pipe_peak, "traffic": traffic, "traffic_note": tnote,
         "kernel": ctx.last_kernel,
         "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms_step,
         "compare_phase_ms": compare_ms,
         "expand_ms": float(np.mean(expand_ms)) if expand_ms else None,
+        "step_frac_all_gpus": step_frac,
+        "step_frac_note": "8 ops x all base comparisons / (step time x n_gpus x peak): the whole step, every GPU, against the pipe",
         "peak_source": ("own loads-free tcgen05 microbenchmark of the kernel's MMA kind and shape "
                         "(ccg_measure_fp4_peak / ccg_measure_i8_peak), sustained: run as long as the GEMM phase, same "
                         "power cap" if own_peak and own_peak > 0 else
                         f"2 x bf16_tflops_sustained of {peaks_src} MEASURED_PEAKS.json"),
         "peak_fp4_burst": fp4_burst, "peak_fp4_sustained": fp4_sustained, "fp4_inexact_elements_at_1.6e7": fp4_inexact,
         "peak_i8_burst": i8_burst, "peak_i8_sustained": i8_sustained,
-        "peak_2x_bf16_sustained": int8_2x_bf16, "frac_of_2x_bf16_sustained": achieved / int8_2x_bf16,
+        "peak_2x_bf16_sustained": int8_2x_bf16, "frac_of_4x_bf16_sustained": achieved / (2 * int8_2x_bf16),
         "peaks_file": peaks_src,
         "algorithmic": f"{OPS_PER_BASECMP} tensor ops (4 MACs) per pairwise base comparison (K=4L contraction), "
-                       f"useful cells only (strict lower triangle)",
+                       f"useful cells only (strict lower triangle); rank 0's launches cover {len_r} of {length} bases",
     }
 
-    # ---- parity spot check (outside the timed region): a few cells against the oracle ----
+    # ---- parity (outside the timed region): >= 1000 cells spread over EVERY macro tile (and, at N > 1, over every
+    # rank's rows) against the oracle on the same samples.  The rows of those samples are gathered on rank 0. ----
+    ids = parity_sample_ids(n, args.parity_samples)
+    idx_t = torch.from_numpy(ids).to(dev)
+    sub_s = seqs_t[idx_t].cpu().numpy().view(np.uint64)
+    sub_m = masks_t[idx_t].cpu().numpy().view(np.uint32)
+    cell_idx, cell_row = packed_index(ids)
+    own = (cell_row >= row_lo) & (cell_row < row_hi)
+    cidx_t = torch.from_numpy(cell_idx).to(dev)
+    own_t = torch.from_numpy(own).to(dev)
+    gD = torch.where(own_t, d_D[cidx_t], torch.zeros((), dtype=torch.float64, device=dev))
+    gN = torch.where(own_t, d_N[cidx_t], torch.zeros((), dtype=torch.float64, device=dev))
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (sub_s, sub_m))
+        dist.all_reduce(gD)
+        dist.all_reduce(gN)
+        sub_s = np.concatenate([p[0] for p in parts], axis=1)
+        sub_m = np.concatenate([p[1] for p in parts], axis=1)
     parity = None
-    cpu_baseline = None
     if rank == 0:
         import oracle
-        ns = min(n, 64)
-        hs = seqs_t[:ns].cpu().numpy().view(np.uint64)
-        hm = masks_t[:ns].cpu().numpy().view(np.uint32)
-        Do, No, _ = oracle.fsa_cmp_pair(hs, hm, np.ones(ns, np.uint8), length)
-        Dg = d_D[:api.cells(ns)].cpu().numpy()
-        Ng = d_N[:api.cells(ns)].cpu().numpy()
-        if world == 1:
-            parity = bool(np.array_equal(Dg, Do) and np.array_equal(Ng, No))
-        else:                                   # rank 0 owns only some of these cells
-            own = Ng != 0
-            parity = bool(np.array_equal(Dg[own], Do[own]) and np.array_equal(Ng[own], No[own]))
+        assert sub_s.shape[1] == api.words(length), (sub_s.shape, api.words(length))
+        Do, No, _ = oracle.fsa_cmp_pair(sub_s, sub_m, np.ones(len(ids), np.uint8), length)
+        parity = bool(np.array_equal(gD.cpu().numpy(), Do) and np.array_equal(gN.cpu().numpy(), No))
+        tiles_hit = len({(int(a) // 256, int(b) // 256) for a, b in zip(cell_row, ids[np.tril_indices(len(ids), -1)[1]])})
         if not parity:
             raise SystemExit("bench.py: GPU result differs from the oracle -- number withheld")
 
-    # ---- e2e: host buffers through the reference-facing C-ABI ----
-    # N <= 2: the one-call drop-in ccg_fsa_cmp_thread_out (host row pointers in, host matrices out; the library
-    #        streams the rows its tiles need K slab by K slab under the GEMM).
-    # N >= 4: every rank uploads only ITS shard of the samples (n/N rows: the PCIe links work in parallel instead
-    #        of every rank pulling the rows of its tiles through the same host memory), the packed rows are
-    #        all-gathered over NVLink (NCCL: the one real exchange step of this path), then ccg_put_samples_packed_dev
-    #        + ccg_run_pair with host matrices out.
+    # ---- e2e: host buffers through the reference-facing C-ABI: ONE call per rank at every N.
+    # ccg_fsa_cmp_thread_out(host row pointers in, host matrices out).  At N > 1 the rank's context is a member of
+    # the K-split group: its rows are its slice of the alignment (pinned host memory), the library streams them
+    # slab by slab under the GEMM, synchronises with the peers on the device, and copies the span of cells it owns
+    # into the host matrices. ----
     e2e = None
     if not args.no_e2e:
         L = api.load()
         import ctypes as C
         row_s, row_m = W * 8, W * 4
-        # measured on the 8-GPU box (profiles/): with 2 ranks the per-rank K-slab streaming (upload hidden under
-        # the GEMM) wins (417 vs 522 ms); from 4 ranks on the ranks' tile regions overlap in the rows they need,
-        # the shared host memory becomes the bottleneck (550-577 ms) and the sharded upload + all-gather wins
-        sharded = world >= 4 and n % world == 0
-        n_host = n // world if sharded else n
-        r0 = rank * n_host if sharded else 0
-        hs_ptr = L.ccg_host_alloc(n_host * row_s)
-        hm_ptr = L.ccg_host_alloc(n_host * row_m)
+        hs_ptr = L.ccg_host_alloc(n * row_s)
+        hm_ptr = L.ccg_host_alloc(n * row_m)
         hD_ptr = L.ccg_host_alloc(max(ncell, 1) * 8)
         hN_ptr = L.ccg_host_alloc(max(ncell, 1) * 8)
         if not (hs_ptr and hm_ptr and hD_ptr and hN_ptr):
             raise SystemExit("bench.py: pinned host allocation failed")
-        hs = np.ctypeslib.as_array(C.cast(hs_ptr, C.POINTER(C.c_uint64)), shape=(n_host, W))
-        hm = np.ctypeslib.as_array(C.cast(hm_ptr, C.POINTER(C.c_uint32)), shape=(n_host, W))
+        hs = np.ctypeslib.as_array(C.cast(hs_ptr, C.POINTER(C.c_uint64)), shape=(n, W))
+        hm = np.ctypeslib.as_array(C.cast(hm_ptr, C.POINTER(C.c_uint32)), shape=(n, W))
         hs_t = torch.from_numpy(hs.view(np.int64))
         hm_t = torch.from_numpy(hm.view(np.int32))
-        hs_t.copy_(seqs_t[r0:r0 + n_host])                      # device -> pinned host, no pageable intermediate
-        hm_t.copy_(masks_t[r0:r0 + n_host])
+        hs_t.copy_(seqs_t)                      # device -> pinned host, no pageable intermediate
+        hm_t.copy_(masks_t)
         torch.cuda.synchronize()
         include = np.ones(n, dtype=np.uint8)
         dn, ginc = C.c_int(0), C.c_uint(0)
-        if not sharded:
-            sp = (C.c_void_p * n)(*[hs_ptr + k * row_s for k in range(n)])
-            mp = (C.c_void_p * n)(*[hm_ptr + k * row_m for k in range(n)])
+        sp = (C.c_void_p * n)(*[hs_ptr + k * row_s for k in range(n)])
+        mp = (C.c_void_p * n)(*[hm_ptr + k * row_m for k in range(n)])
 
-            def e2e_step():
-                rc = L.ccg_fsa_cmp_thread_out(ctx._h, 1, hD_ptr, hN_ptr, 8, 1.0, n, length, sp, include.ctypes.data, mp,
-                                              0, 1, 0.5, 0, C.byref(dn), C.byref(ginc))
-                if rc:
-                    raise SystemExit("ccg_fsa_cmp_thread_out failed: " + L.ccg_last_error(ctx._h).decode())
-            call = "ccg_fsa_cmp_thread_out(ctx, pair=1, host rows in pinned memory, host D/N out)"
-            h2d = int(n * (row_s + row_m))
-        else:
-            # the gather lands in the buffers the device-resident arm used (same contents)
-            seqs_t.zero_()
-            masks_t.zero_()
-            C.memset(hD_ptr, 0, max(ncell, 1) * 8)              # cells of other ranks stay zero
-            C.memset(hN_ptr, 0, max(ncell, 1) * 8)
-
-            def e2e_step():
-                seqs_t[r0:r0 + n_host].copy_(hs_t, non_blocking=True)
-                masks_t[r0:r0 + n_host].copy_(hm_t, non_blocking=True)
-                dist.all_gather_into_tensor(seqs_t, seqs_t[r0:r0 + n_host])
-                dist.all_gather_into_tensor(masks_t, masks_t[r0:r0 + n_host])
-                ctx.set_problem(n, length, pair=True)
-                ctx.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
-                # the epilogue writes this rank's cells straight into the pinned host matrices (mapped memory):
-                # a rank owns 1/N of the cells, a device-to-host copy of the whole matrix would move N times that
-                ctx.run_pair_dev(hD_ptr, hN_ptr, norm=0, min_length=1, min_cov=0.5, elem_size=8)
-                ctx.sync()
-            call = (f"per rank: H2D of its {n_host}-sample shard (pinned rows) -> NCCL all-gather of the packed rows over "
-                    f"NVLink -> ccg_put_samples_packed_dev + ccg_run_pair_dev writing the rank's cells into pinned host D/N")
-            h2d = int(n * (row_s + row_m))                          # summed over the ranks: every row crosses PCIe once
+        def e2e_step():
+            rc = L.ccg_fsa_cmp_thread_out(ctx._h, 1, hD_ptr, hN_ptr, 8, 1.0, n, len_r, sp, include.ctypes.data, mp,
+                                          0, 1, 0.5, 0, C.byref(dn), C.byref(ginc))
+            if rc:
+                raise SystemExit("ccg_fsa_cmp_thread_out failed: " + L.ccg_last_error(ctx._h).decode())
+        call = "ccg_fsa_cmp_thread_out(ctx, pair=1, host rows in pinned memory, host D/N out)" + \
+               (f", one call per rank on its slice of the alignment (K-split group of {world})" if world > 1 else "")
 
         for _ in range(2):
             e2e_step()
@@ -479,20 +505,24 @@ def main():
             e_ms = float(tt.item())
         hD = np.ctypeslib.as_array(C.cast(hD_ptr, C.POINTER(C.c_double)), shape=(max(ncell, 1),))
         hN = np.ctypeslib.as_array(C.cast(hN_ptr, C.POINTER(C.c_double)), shape=(max(ncell, 1),))
-        if rank == 0:
-            # the host-path result must equal the device-path result (rank 0's own cells when partitioned)
-            dD = d_D.cpu().numpy()
-            own = np.ones(ncell, bool) if world == 1 else (hN[:ncell] != 0)
-            if not np.array_equal(hD[:ncell][own], dD[own]) or (world > 1 and not own.any()):
-                raise SystemExit("bench.py: host-path result differs from the device-path result")
+        # the host-path result must equal the device-path result on the span of cells this rank owns
+        _, _, c_lo, c_hi = ctx.group_last_span() if world > 1 else (0, n, 0, ncell)
+        same = bool(np.array_equal(hD[c_lo:c_hi], d_D[c_lo:c_hi].cpu().numpy()) and
+                    np.array_equal(hN[c_lo:c_hi], d_N[c_lo:c_hi].cpu().numpy()) and c_hi > c_lo)
+        if world > 1:
+            st = torch.tensor([1 if same else 0, c_hi - c_lo], device=dev, dtype=torch.int64)
+            dist.all_reduce(st)
+            same = int(st[0].item()) == world and int(st[1].item()) == ncell      # the spans tile the triangle
+        if not same:
+            raise SystemExit("bench.py: host-path result differs from the device-path result")
         e2e = {"value": total_basecmp / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(2 * ncell * 8) * (1 if sharded else world),
-               "steps": e_steps,
-               "call": call}
+               "h2d_bytes_per_step": int(n * (api.words(length) * 12)), "d2h_bytes_per_step": int(2 * ncell * 8),
+               "steps": e_steps, "call": call, "matches_device_path": same}
         for p in (hs_ptr, hm_ptr, hD_ptr, hN_ptr):
             L.ccg_host_free(p)
 
     # ---- cpu baseline: the unmodified reference on this box's host cores (rank 0, N=1 only) ----
+    cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         ns_cap = min(n, 64 + 8 * cores)
@@ -521,13 +551,17 @@ def main():
                                                              if args.scaling == "strong" else
                                                              "sample count grown with sqrt(N)"),
                        "samples": n, "length": length, "pairs": ncell,
-                       "partition": f"lower-triangular 128x256 macro tiles, Z-order curve cut into {world} cost-balanced run(s), "
-                                    f"no collective",
-                       "l2": "inputs (%.2f GB of planes) larger than the 126 MB L2; no explicit flush" %
+                       "partition": ("one GPU" if world == 1 else
+                                     f"K split: each of the {world} GPUs holds 1/{world} of the alignment of every sample and runs all "
+                                     f"macro tiles on it; int32 partial sums reduced by the owner of a matrix row through peer "
+                                     f"pointers over NVLink inside the epilogue kernel (no NCCL collective on the data path)"),
+                       "l2": "inputs (%.2f GB of planes per GPU) larger than the 126 MB L2; no explicit flush" %
                              (n * W * 12 / 1e9),
                        "step": "encode (packed words -> bit planes) + compare + fused epilogue"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "parity_vs_oracle": parity,
+            "parity_cells_checked": int(len(cell_idx)), "parity_tiles_hit": int(tiles_hit),
+            "parity_tiles_total": int(((n + 255) // 256) * ((n + 255) // 256 + 1) // 2),
         }
         emit(line)
     ctx.close()

@@ -29,7 +29,10 @@ EXPORTS = [
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
     "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs", "ccg_list_variants_row",
+    "ccg_init_multi", "ccg_init_multi_devices", "ccg_multi_gpus", "ccg_group_export", "ccg_group_join", "ccg_group_leave",
+    "ccg_group_set_alignment", "ccg_group_rows", "ccg_group_last_span",
 ]
+GROUP_HANDLE_BYTES = 128
 
 MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "l1", "l2", "linf", "ln", "nl1", "nl2",
                "nlinf", "nln"]          # CCG_MAT_* ids, include/ccphylo_gpu.h
@@ -127,6 +130,15 @@ def load():
     L.ccg_mat_run.argtypes = [vp, vp, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, i, C.c_double,
                               vp, vp, vp, vp]
     L.ccg_mat_run_row.argtypes = [vp, i, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, vp, vp, vp]
+    L.ccg_init_multi.argtypes = [C.POINTER(vp), i]
+    L.ccg_init_multi_devices.argtypes = [C.POINTER(vp), i, vp]
+    L.ccg_multi_gpus.argtypes = [vp, C.POINTER(i)]
+    L.ccg_group_export.argtypes = [vp, i, vp]
+    L.ccg_group_join.argtypes = [vp, i, i, vp]
+    L.ccg_group_leave.argtypes = [vp]
+    L.ccg_group_set_alignment.argtypes = [vp, ll, u]
+    L.ccg_group_rows.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+    L.ccg_group_last_span.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(ll), C.POINTER(ll)]
     L.ccg_measure_fp4_peak.restype = C.c_double
     L.ccg_measure_fp4_peak.argtypes = [vp, C.c_double, C.c_double, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     L.ccg_measure_i8_peak.restype = C.c_double
@@ -150,6 +162,21 @@ def partition_tiles(n, rank, world):
     return list(zip(ti[:k].tolist(), tj[:k].tolist()))
 
 
+def group_rows(n, rank, world):
+    """Sample slots [lo, hi) whose matrix rows member `rank` of a K-split group of `world` finalises (host only)."""
+    lo, hi = C.c_int(0), C.c_int(0)
+    rc = load().ccg_group_rows(n, rank, world, C.byref(lo), C.byref(hi))
+    if rc:
+        raise CcgError(rc, "ccg_group_rows")
+    return lo.value, hi.value
+
+
+def group_slices(length, world):
+    """First base of every member's slice of the alignment (multiples of 256) plus the end: what ccg_init_multi
+    uses, and what one-process-per-GPU callers should use so that the slices partition the alignment."""
+    return [length if g == world else (length * g // world) // 256 * 256 for g in range(world + 1)]
+
+
 def words(length):
     return (length >> 5) + (1 if length & 31 else 0)
 
@@ -171,14 +198,50 @@ def _row_ptrs(arr2d, skip=None):
 class Context:
     """One GPU context (one per process / GPU), wrapping ``ccg_ctx``."""
 
-    def __init__(self, device=-1):
+    def __init__(self, device=-1, multi=None):
+        """device: CUDA device of a single-GPU context.  multi = N (0 = all visible) or a list of device ids makes
+        an in-process multi-GPU context (ccg_init_multi / ccg_init_multi_devices) instead."""
         self._L = load()
         self._h = C.c_void_p()
-        rc = self._L.ccg_init(C.byref(self._h), device)
+        if multi is None:
+            rc = self._L.ccg_init(C.byref(self._h), device)
+        elif isinstance(multi, int):
+            rc = self._L.ccg_init_multi(C.byref(self._h), multi)
+        else:
+            devs = np.ascontiguousarray(multi, dtype=np.int32)
+            rc = self._L.ccg_init_multi_devices(C.byref(self._h), len(devs), devs.ctypes.data)
         if rc:
             raise CcgError(rc, self._L.ccg_last_error(None).decode())
         self.n = self.len = 0
         self.pair = True
+
+    # ---- multi-GPU ----
+    def multi_gpus(self):
+        """(member GPUs, members working on the current problem)"""
+        a = C.c_int(1)
+        return self._L.ccg_multi_gpus(self._h, C.byref(a)), a.value
+
+    def group_export(self, max_samples):
+        buf = (C.c_char * GROUP_HANDLE_BYTES)()
+        self._ck(self._L.ccg_group_export(self._h, max_samples, buf))
+        return bytes(buf)
+
+    def group_join(self, rank, world, handles):
+        blob = b"".join(handles)
+        assert len(blob) == world * GROUP_HANDLE_BYTES
+        self._ck(self._L.ccg_group_join(self._h, rank, world, blob))
+
+    def group_leave(self):
+        self._ck(self._L.ccg_group_leave(self._h))
+
+    def group_set_alignment(self, total_len, global_inc=0):
+        self._ck(self._L.ccg_group_set_alignment(self._h, total_len, global_inc))
+
+    def group_last_span(self):
+        """(row_lo, row_hi, cell_lo, cell_hi) of the last run of this group member."""
+        a, b, c, d = C.c_int(0), C.c_int(0), C.c_longlong(0), C.c_longlong(0)
+        self._ck(self._L.ccg_group_last_span(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
 
     def _ck(self, rc):
         if rc:

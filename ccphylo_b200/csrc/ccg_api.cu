@@ -28,6 +28,13 @@ static void set_err(ccg_ctx *ctx, const char *fmt, ...) {
 	va_end(ap);
 }
 
+void ccg_set_err(ccg_ctx *ctx, const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(ctx ? ctx->err : g_init_err, 512, fmt, ap);
+	va_end(ap);
+}
+
 #define CK(ctx, call)                                                                              \
 	do {                                                                                           \
 		cudaError_t e__ = (call);                                                                  \
@@ -65,7 +72,12 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 		return CCG_ERR_NO_DEVICE;
 	}
 	cudaDeviceProp prop;
-	if(cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+	memset(&prop, 0, sizeof(prop));
+	if(cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+		set_err(0, "cudaGetDeviceProperties(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+		return CCG_ERR_NO_DEVICE;
+	}
+	if(prop.major != 10) {
 		set_err(0, "device %d is compute capability %d.%d; this library is built for sm_100a only", device, prop.major,
 		        prop.minor);
 		return CCG_ERR_NO_DEVICE;
@@ -81,20 +93,29 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 		free(ctx);
 		return CCG_ERR_CUDA;
 	}
-	for(int k = 0; k < 4; ++k) cudaEventCreate(&ctx->ev_phase[k]);
-	cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
-	for(int k = 0; k < 2; ++k) {
-		cudaStreamCreateWithFlags(&ctx->copy_stream[k], cudaStreamNonBlocking);
-		cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming);
-	}
-	cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming);
-	cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
-	cudaEventCreateWithFlags(&ctx->ev_launch, cudaEventDisableTiming);
-	for(int k = 0; k < 2; ++k) {
-		cudaEventCreateWithFlags(&ctx->ev_x[k], cudaEventDisableTiming);
-		cudaEventCreateWithFlags(&ctx->ev_g[k], cudaEventDisableTiming);
-	}
 	ctx->stream = ctx->own_stream;
+	{
+		/* the fork / join ordering of run_umma rests on these: a failed creation must not degrade to stream 0 */
+		cudaError_t e = cudaSuccess;
+		for(int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaEventCreate(&ctx->ev_phase[k]);
+		if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+		for(int k = 0; k < 2 && e == cudaSuccess; ++k) {
+			e = cudaStreamCreateWithFlags(&ctx->copy_stream[k], cudaStreamNonBlocking);
+			if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming);
+			if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_x[k], cudaEventDisableTiming);
+			if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_g[k], cudaEventDisableTiming);
+		}
+		if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming);
+		if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+		if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_launch, cudaEventDisableTiming);
+		if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_switch, cudaEventDisableTiming);
+		if(e != cudaSuccess) {
+			set_err(0, "creating the context's streams / events failed: %s", cudaGetErrorString(e));
+			cudaGetLastError();
+			ccg_destroy(ctx);
+			return CCG_ERR_CUDA;
+		}
+	}
 	{
 		/* stream memory operations: let the aux stream wait until the GEMM CTAs are resident */
 		void *fn = 0;
@@ -138,8 +159,11 @@ static void free_problem(ccg_ctx *ctx) {
 
 extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	if(!ctx) return;
+	if(ctx->multi) ccg_multi_destroy(ctx);
 	cudaSetDevice(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
+	if(ctx->stream) cudaStreamSynchronize(ctx->stream);
+	ccg_group_release(ctx);
+	cudaFree(ctx->grp_own_win);
 	free_problem(ctx);
 	ccg_mat_free(ctx);
 	cudaFree(ctx->d_stage);
@@ -152,39 +176,61 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	cudaFree(ctx->d_resident);
 	cudaFree(ctx->d_out_D);
 	cudaFree(ctx->d_out_N);
-	cudaEventDestroy(ctx->ev0);
-	cudaEventDestroy(ctx->ev1);
-	for(int k = 0; k < 4; ++k) cudaEventDestroy(ctx->ev_phase[k]);
-	cudaEventDestroy(ctx->ev_fork);
-	cudaEventDestroy(ctx->ev_launch);
-	for(int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_x[k]); cudaEventDestroy(ctx->ev_g[k]); }
-	cudaStreamSynchronize(ctx->aux_stream);
-	cudaStreamDestroy(ctx->aux_stream);
+	/* a context whose creation failed half way holds null handles */
+	if(ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if(ctx->ev1) cudaEventDestroy(ctx->ev1);
+	for(int k = 0; k < 4; ++k) if(ctx->ev_phase[k]) cudaEventDestroy(ctx->ev_phase[k]);
+	if(ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+	if(ctx->ev_launch) cudaEventDestroy(ctx->ev_launch);
+	if(ctx->ev_switch) cudaEventDestroy(ctx->ev_switch);
 	for(int k = 0; k < 2; ++k) {
-		cudaStreamSynchronize(ctx->copy_stream[k]);
-		cudaStreamDestroy(ctx->copy_stream[k]);
-		cudaEventDestroy(ctx->ev_up[k]);
+		if(ctx->ev_x[k]) cudaEventDestroy(ctx->ev_x[k]);
+		if(ctx->ev_g[k]) cudaEventDestroy(ctx->ev_g[k]);
+	}
+	if(ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+	for(int k = 0; k < 2; ++k) {
+		if(ctx->copy_stream[k]) { cudaStreamSynchronize(ctx->copy_stream[k]); cudaStreamDestroy(ctx->copy_stream[k]); }
+		if(ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
 		cudaFree(ctx->d_stage2[k]);
 	}
-	cudaEventDestroy(ctx->ev_main);
-	cudaStreamDestroy(ctx->own_stream);
+	if(ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+	if(ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+	cudaGetLastError();
 	free(ctx);
 }
 
 extern "C" int ccg_set_stream(ccg_ctx *ctx, void *cuda_stream) {
 	if(!ctx) return CCG_ERR_ARG;
-	ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+	if(ctx->multi) {
+		if(!cuda_stream) return CCG_OK;
+		set_err(ctx, "a multi-GPU context launches on its members' own streams");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	cudaStream_t next = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+	if(next != ctx->stream) {
+		/* work still queued on the old stream (e.g. the clearing of a fresh sample store by ccg_set_problem) must
+		 * be finished before anything launched on the new one touches the same buffers */
+		CK(ctx, cudaSetDevice(ctx->device));
+		CK(ctx, cudaEventRecord(ctx->ev_switch, ctx->stream));
+		CK(ctx, cudaStreamWaitEvent(next, ctx->ev_switch, 0));
+		ctx->stream = next;
+	}
 	return CCG_OK;
 }
 
 extern "C" int ccg_set_kernel(ccg_ctx *ctx, int kernel) {
 	if(!ctx || kernel < CCG_KERNEL_AUTO || kernel > CCG_KERNEL_FUSED) return CCG_ERR_ARG;
+	if(ctx->multi) return ccg_multi_set_kernel(ctx, kernel);
 	ctx->kernel_choice = kernel;
 	return CCG_OK;
 }
 
 extern "C" int ccg_set_proximity(ccg_ctx *ctx, unsigned proxi, int snp_events_only) {
 	if(!ctx) return CCG_ERR_ARG;
+	if(ctx->multi) {
+		ccg_multi_note_special(ctx, 1, proxi != 0);
+		return ccg_set_proximity(ccg_multi_member(ctx, 0), proxi, snp_events_only);
+	}
 	ctx->proxi = proxi;
 	ctx->proxi_snp_only = snp_events_only ? 1 : 0;
 	return CCG_OK;
@@ -192,6 +238,11 @@ extern "C" int ccg_set_proximity(ccg_ctx *ctx, unsigned proxi, int snp_events_on
 
 extern "C" int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes) {
 	if(!ctx) return CCG_ERR_ARG;
+	if(ctx->multi) {
+		int rc = CCG_OK;
+		for(int g = 0; ccg_multi_member(ctx, g) && !rc; ++g) rc = ccg_set_scratch_limit(ccg_multi_member(ctx, g), bytes);
+		return rc;
+	}
 	if(ctx->x_budget != bytes && ctx->d_X) {
 		/* re-size the operand panel on the next run */
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -206,12 +257,14 @@ extern "C" int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes) {
 
 extern "C" int ccg_sync(ccg_ctx *ctx) {
 	if(!ctx) return CCG_ERR_ARG;
+	if(ctx->multi) return ccg_multi_sync(ctx);
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	return CCG_OK;
 }
 
 extern "C" int ccg_set_tile_window(ccg_ctx *ctx, int row_lo, int row_hi, int col_lo, int col_hi) {
 	if(!ctx) return CCG_ERR_ARG;
+	CCG_MULTI_SOLO(ctx, "a tile window", ccg_set_tile_window(m0, row_lo, row_hi, col_lo, col_hi));
 	if(row_lo < 0) {
 		ctx->win_on = 0;
 	} else {
@@ -228,6 +281,11 @@ extern "C" int ccg_set_tile_window(ccg_ctx *ctx, int row_lo, int row_hi, int col
 
 extern "C" int ccg_set_partition(ccg_ctx *ctx, int rank, int world) {
 	if(!ctx || world < 1 || rank < 0 || rank >= world) return CCG_ERR_ARG;
+	CCG_MULTI_SOLO(ctx, "a tile partition", ccg_set_partition(m0, rank, world));
+	if(world > 1 && ctx->grp_world > 1) {
+		set_err(ctx, "a context is either a member of a K-split group or a rank of a tile partition, not both");
+		return CCG_ERR_ARG;
+	}
 	ctx->rank = rank;
 	ctx->world = world;
 	update_need(ctx);
@@ -449,6 +507,7 @@ static int make_x_tmap(ccg_ctx *ctx) {
 
 extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	if(!ctx || n < 0 || len < 0) return CCG_ERR_ARG;
+	if(ctx->multi) return ccg_multi_set_problem(ctx, n, len, pair_mode);
 	CK(ctx, cudaSetDevice(ctx->device));
 	const int words = (len >> 5) + ((len & 31) ? 1 : 0);
 	int chunks = (words + CCG_CHUNK_WORDS - 1) / CCG_CHUNK_WORDS;
@@ -522,6 +581,7 @@ static int ensure_stage(ccg_ctx *ctx, size_t bytes) {
 }
 
 extern "C" int ccg_put_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
+	if(ctx && ctx->multi && mask) return ccg_multi_put_global_mask(ctx, mask, 0);
 	if(!ctx || !ctx->d_planes || ctx->pair_mode || !mask) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
 	CK(ctx, cudaMemcpyAsync(ctx->d_gmask, mask, (size_t) ctx->words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -532,6 +592,7 @@ extern "C" int ccg_put_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
 }
 
 extern "C" int ccg_apply_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
+	if(ctx && ctx->multi && mask) return ccg_multi_put_global_mask(ctx, mask, 1);
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !mask) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
 	if(!ctx->d_gmask) CK(ctx, cudaMalloc(&ctx->d_gmask, (size_t) (ctx->words + 1) * sizeof(uint32_t)));
@@ -572,6 +633,7 @@ static int stage_use_flags(ccg_ctx *ctx, const unsigned char *include, int lo, i
 }
 
 extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include, unsigned *global_inc) {
+	if(ctx && ctx->multi) return ccg_multi_build_global_mask(ctx, include, global_inc);
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode) return CCG_ERR_ARG;
 	if(ctx->world > 1) {
 		set_err(ctx, "ccg_build_global_mask needs every sample on this device (partitioned contexts hold only their row blocks)");
@@ -613,6 +675,10 @@ extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include,
 /* -y: the motif list of getMethMotifs (methparse.c:268) */
 extern "C" int ccg_set_motifs(ccg_ctx *ctx, int nmotifs, const int *lens, const unsigned char *sets) {
 	if(!ctx || nmotifs < 0 || (nmotifs && (!lens || !sets))) return CCG_ERR_ARG;
+	if(ctx->multi) {
+		ccg_multi_note_special(ctx, 2, nmotifs != 0);
+		return ccg_multi_forwarded(ctx, ccg_set_motifs(ccg_multi_member(ctx, 0), nmotifs, lens, sets));
+	}
 	CK(ctx, cudaSetDevice(ctx->device));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	cudaFree(ctx->d_motif_lens); ctx->d_motif_lens = 0;
@@ -642,6 +708,7 @@ extern "C" int ccg_set_motifs(ccg_ctx *ctx, int nmotifs, const int *lens, const 
 
 /* maskMotifs (meth.c:141) on the uploaded slots [first, first + count) */
 extern "C" int ccg_mask_motifs(ccg_ctx *ctx, int first, int count, unsigned *inc_out) {
+	CCG_MULTI_SOLO(ctx, "motif masking (-y)", ccg_mask_motifs(m0, first, count, inc_out));
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || first < 0 || count < 0 || first + count > ctx->n) return CCG_ERR_ARG;
 	if(count == 0) return CCG_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
@@ -658,6 +725,7 @@ extern "C" int ccg_mask_motifs(ccg_ctx *ctx, int first, int count, unsigned *inc
 }
 
 extern "C" int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int apply, unsigned *inc_out) {
+	CCG_MULTI_SOLO(ctx, "proximity masking (-P)", ccg_sample_proximity(m0, first, count, apply, inc_out));
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || first < 0 || count < 0 || first + count > ctx->n) return CCG_ERR_ARG;
 	if(count == 0) return CCG_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
@@ -699,6 +767,7 @@ extern "C" int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int appl
 
 extern "C" int ccg_put_samples_packed(ccg_ctx *ctx, int first, int count, const uint64_t *const *seqs,
                                       const uint32_t *const *includes) {
+	if(ctx && ctx->multi && seqs) return ccg_multi_put_samples_packed(ctx, first, count, seqs, includes);
 	if(!ctx || !ctx->d_planes || first < 0 || count < 0 || first + count > ctx->n || !seqs) return CCG_ERR_ARG;
 	if(ctx->pair_mode && !includes) return CCG_ERR_ARG;
 	if(count == 0 || ctx->words == 0) return CCG_OK;
@@ -737,6 +806,7 @@ extern "C" int ccg_put_samples_packed(ccg_ctx *ctx, int first, int count, const 
 
 extern "C" int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count, const uint64_t *d_seqs,
                                           const uint32_t *d_masks, long wstride) {
+	CCG_MULTI_SOLO(ctx, "an upload from device memory", ccg_put_samples_packed_dev(m0, first, count, d_seqs, d_masks, wstride));
 	if(!ctx || !ctx->d_planes || first < 0 || count < 0 || first + count > ctx->n || !d_seqs || wstride < ctx->words)
 		return CCG_ERR_ARG;
 	if(ctx->pair_mode && !d_masks) return CCG_ERR_ARG;
@@ -761,6 +831,7 @@ extern "C" int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count, co
 }
 
 extern "C" int ccg_put_sample_codes(ccg_ctx *ctx, int idx, const unsigned char *codes) {
+	if(ctx && ctx->multi && codes) return ccg_multi_put_sample_codes(ctx, idx, codes);
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || idx < 0 || idx >= ctx->n || !codes) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
 	size_t stride = ((size_t) ctx->len + 15) & ~(size_t) 15;
@@ -775,6 +846,7 @@ extern "C" int ccg_put_sample_codes(ccg_ctx *ctx, int idx, const unsigned char *
 }
 
 extern "C" int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out) {
+	if(ctx && ctx->multi && out) return ccg_multi_get_inc_counts(ctx, out);
 	if(!ctx || !ctx->d_inc || !out) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
 	CK(ctx, cudaMemcpyAsync(out, ctx->d_inc, (size_t) ctx->n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1027,20 +1099,30 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	ctx->last_kernel_kind = CCG_KERNEL_UMMA;
 	if(cnt == 0) return CCG_OK;
 
-	/* dense int32 accumulators S and I */
+	/* dense int32 accumulators S and I: the context's own, or -- member of a K-split group -- the buffer of this
+	 * run inside the window the peers can read (ccg_group.cu) */
 	size_t c_bytes = (size_t) 2 * ctx->n_pad * ctx->n_pad * sizeof(int);
-	if(ctx->c_bytes < c_bytes) {
-		CK(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(ctx->d_C);
-		ctx->d_C = 0;
-		ctx->c_bytes = 0;
-		if(cudaMalloc(&ctx->d_C, c_bytes) != cudaSuccess) {
-			set_err(ctx, "cudaMalloc of %zu bytes for the int32 accumulators failed", c_bytes);
-			return CCG_ERR_NOMEM;
+	const bool group = ctx->grp_world > 1;
+	int *acc_S = 0, *acc_I = 0;
+	if(group) {
+		rc = ccg_group_accumulators(ctx, &acc_S, &acc_I);
+		if(rc) return rc;
+	} else {
+		if(ctx->c_bytes < c_bytes) {
+			CK(ctx, cudaStreamSynchronize(ctx->stream));
+			cudaFree(ctx->d_C);
+			ctx->d_C = 0;
+			ctx->c_bytes = 0;
+			if(cudaMalloc(&ctx->d_C, c_bytes) != cudaSuccess) {
+				set_err(ctx, "cudaMalloc of %zu bytes for the int32 accumulators failed", c_bytes);
+				return CCG_ERR_NOMEM;
+			}
+			ctx->c_bytes = c_bytes;
 		}
-		ctx->c_bytes = c_bytes;
+		acc_S = ctx->d_C;
+		acc_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
 	}
-	CK(ctx, cudaMemsetAsync(ctx->d_C, 0, c_bytes, ctx->stream));
+	CK(ctx, cudaMemsetAsync(acc_S, 0, c_bytes, ctx->stream));
 
 	/* e2m1 operands on kind::mxf4 (2.27x the kind::i8 pipe rate, exact for these sums) unless CCG_I8=1 */
 	const bool fp4 = !ctx->use_i8 && !ctx->dbg_umma1;
@@ -1122,8 +1204,8 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	memset(&p, 0, sizeof(p));
 	p.ntiles = (int) cnt;
 	p.tiles = ctx->d_tiles;
-	p.C_S = ctx->d_C;
-	p.C_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
+	p.C_S = acc_S;
+	p.C_I = acc_I;
 	p.ldc = ctx->n_pad;
 	p.fp4 = fp4 ? 1 : 0;
 	p.no_mask_items = (fp4 && !ctx->pair_mode) ? 1 : 0;   /* two-plane store: k_finalize_umma uses the constant */
@@ -1161,13 +1243,11 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		}
 		p.kslices = choose_split((long long) (p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx)), (long long) p.ntiles, nu, fp4 ? 8 : 16, 512,
 		                        ctx->feed_seqs ? 0 : 1);
-		/* f32 accumulators: an S item adds at most 3 * 256 per chunk pair and must stay below 2^24 */
-		if(fp4 && (nu + p.kslices - 1) / p.kslices > 20000) p.kslices = (nu + 19999) / 20000;
+		if(ctx->dbg_kslices > 0) p.kslices = ctx->dbg_kslices;
+		/* f32 accumulators: an S item adds at most 3 * 256 per chunk pair and must stay below 2^24 (applied after
+		 * the experiment override as well: exactness is not a tuning knob) */
+		if(fp4 && (nu + p.kslices - 1) / p.kslices > CCG_FP4_MAX_PAIRS) p.kslices = (nu + CCG_FP4_MAX_PAIRS - 1) / CCG_FP4_MAX_PAIRS;
 		p.chunks_per_slice = (nu + p.kslices - 1) / p.kslices;
-		if(ctx->dbg_kslices > 0) {
-			p.kslices = ctx->dbg_kslices;
-			p.chunks_per_slice = (nu + p.kslices - 1) / p.kslices;
-		}
 		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nu) --p.kslices;
 		if(ctx->feed_seqs) {
 			rc = feed_slab(ctx, chunk0, nch);
@@ -1206,11 +1286,15 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	ctx->last_i_const = i_const;
 	p.ntiles = (int) cnt;
 	p.tiles = ctx->d_tiles;
-	CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, i_const));
+	if(group) {
+		/* barrier with the peers, then the reduce-scatter over NVLink fused with the epilogue of this member's rows */
+		rc = ccg_group_finalize(ctx, ep, i_const);
+		if(rc) return rc;
+	} else CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, i_const));
 	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 	ctx->ev_valid = 1;
-	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_umma%s tiles=%d kslices=%d slabs=%d",
-	         ctx->dbg_umma1 ? "" : (fp4 ? "2<mxf4>" : "2<i8>"), p.ntiles, p.kslices, nslabs);
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_umma%s tiles=%d kslices=%d slabs=%d%s",
+	         ctx->dbg_umma1 ? "" : (fp4 ? "2<mxf4>" : "2<i8>"), p.ntiles, p.kslices, nslabs, group ? " +k_finalize_group" : "");
 	return CCG_OK;
 }
 
@@ -1275,6 +1359,17 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 		return CCG_ERR_ARG;
 	}
 	CK(ctx, cudaSetDevice(ctx->device));
+	const bool group = ctx->grp_world > 1;
+	if(group) {
+		if(ctx->proxi || ctx->row_slot1 || ctx->world > 1 || ctx->win_on) {
+			set_err(ctx, "a member of a K-split group runs plain all-vs-all comparisons only (no -P, row run, tile partition or window)");
+			return CCG_ERR_UNSUPPORTED;
+		}
+		if(ctx->grp_total_len < ctx->len || (mode == 1 && !ctx->grp_global_inc && ctx->global_inc)) {
+			set_err(ctx, "K-split group: ccg_group_set_alignment(total length%s) must precede the run", mode == 1 ? ", inclusion count of the whole global mask" : "");
+			return CCG_ERR_ARG;
+		}
+	}
 	if(mode == 1 && ctx->global_pending) {
 		CK(ctx, ccg_launch_apply_global_mask(ctx));
 		ctx->global_pending = 0;
@@ -1313,13 +1408,14 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	if(ctx->row_slot1) ep.row_plus1 = ctx->h_rank[ctx->row_slot1 - 1] + 1;
 	if(mode == 0) {
 		/* fsacmpthrd.c:292: minLength = minLength < minCov * len ? minCov * len : minLength */
-		if(minLength < minCov * ctx->len) minLength = (unsigned) (minCov * ctx->len);
+		const long long gate_len = group ? ctx->grp_total_len : (long long) ctx->len;       /* the whole alignment */
+		if(minLength < minCov * gate_len) minLength = (unsigned) (minCov * gate_len);
 		ep.minLength = minLength;
 		ep.nFactor = 1.0;
 	} else {
 		/* fsacmpthrd.c:171-176 */
 		double nFactor = 1.0;
-		if(norm) { nFactor = norm; nFactor /= (int) ctx->global_inc; }
+		if(norm) { nFactor = norm; nFactor /= (int) (group ? ctx->grp_global_inc : ctx->global_inc); }
 		ep.nFactor = nFactor;
 	}
 	/* AUTO: the tensor-core kernel wins once there is enough work to fill the machine */
@@ -1335,7 +1431,16 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	int kind = ctx->kernel_choice;
 	if(kind == CCG_KERNEL_AUTO)
 		kind = (Dn >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
-	if(ctx->feed_seqs) kind = CCG_KERNEL_UMMA;      /* the caller streams host rows into the tensor path's K slabs */
+	if(ctx->feed_seqs || group) kind = CCG_KERNEL_UMMA;      /* the caller streams host rows into the tensor path's K slabs */
+	/* int32 sums of the tensor path: |S| <= 3 (len + 255) must stay below 2^31; the u32 counters of the POPC path
+	 * hold any alignment an int length can describe */
+	if(kind != CCG_KERNEL_POPC && 3.0 * ((double) ctx->len + 256.0) >= 2147483648.0) {
+		if(ctx->kernel_choice != CCG_KERNEL_AUTO || ctx->feed_seqs || group) {
+			set_err(ctx, "alignment of %d bases: the tensor path's int32 sums hold 3 x length only up to 715 Mbp", ctx->len);
+			return CCG_ERR_UNSUPPORTED;
+		}
+		kind = CCG_KERNEL_POPC;
+	}
 	if(kind == CCG_KERNEL_FUSED) return run_fused(ctx, ep);
 	return kind == CCG_KERNEL_UMMA ? run_umma(ctx, ep) : run_popc(ctx, ep);
 }
@@ -1370,7 +1475,15 @@ static int run_to_host(ccg_ctx *ctx, int mode, const unsigned char *include, uns
 	                    N ? ctx->d_out_N : 0, &Dn);
 	if(rc) return rc;
 	if(Dn_out) *Dn_out = Dn;
-	if(Dn > 1) {
+	if(Dn > 1 && ctx->grp_world > 1) {
+		/* a member of a K-split group owns a contiguous run of matrix rows = one span of the packed triangle; the
+		 * members write disjoint spans of the same host matrices */
+		const size_t lo = (size_t) ctx->grp_span[0] * elem_size, bytes_own = (size_t) (ctx->grp_span[1] - ctx->grp_span[0]) * elem_size;
+		if(bytes_own) {
+			CK(ctx, cudaMemcpyAsync((char *) D + lo, (char *) ctx->d_out_D + lo, bytes_own, cudaMemcpyDeviceToHost, ctx->stream));
+			if(N) CK(ctx, cudaMemcpyAsync((char *) N + lo, (char *) ctx->d_out_N + lo, bytes_own, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+	} else if(Dn > 1) {
 		size_t cells = (size_t) Dn * (Dn - 1) / 2;
 		CK(ctx, cudaMemcpyAsync(D, ctx->d_out_D, cells * elem_size, cudaMemcpyDeviceToHost, ctx->stream));
 		if(N) CK(ctx, cudaMemcpyAsync(N, ctx->d_out_N, cells * elem_size, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1381,25 +1494,29 @@ static int run_to_host(ccg_ctx *ctx, int mode, const unsigned char *include, uns
 
 extern "C" int ccg_run_pair(ccg_ctx *ctx, const unsigned char *include, unsigned norm, unsigned minLength, double minCov,
                             int elem_size, double byteScale, void *D, void *N, int *Dn) {
+	if(ctx && ctx->multi) return ccg_multi_run(ctx, 1, include, norm, minLength, minCov, elem_size, byteScale, D, N, Dn, 0);
 	return run_to_host(ctx, 0, include, norm, minLength, minCov, elem_size, byteScale, D, N, Dn);
 }
 
 extern "C" int ccg_run_global(ccg_ctx *ctx, const unsigned char *include, unsigned norm, int elem_size, double byteScale,
                               void *D, int *Dn, unsigned *global_inc) {
-	if(ctx && global_inc) *global_inc = ctx->global_inc;
+	if(ctx && ctx->multi) return ccg_multi_run(ctx, 0, include, norm, 0, 0.0, elem_size, byteScale, D, 0, Dn, global_inc);
+	if(ctx && global_inc) *global_inc = ctx->grp_world > 1 ? ctx->grp_global_inc : ctx->global_inc;
 	return run_to_host(ctx, 1, include, norm, 0, 0.0, elem_size, byteScale, D, 0, Dn);
 }
 
 extern "C" int ccg_run_pair_dev(ccg_ctx *ctx, const unsigned char *include, unsigned norm, unsigned minLength,
                                 double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn) {
 	if(!d_D) return CCG_ERR_ARG;
+	CCG_MULTI_SOLO(ctx, "a run into device buffers", ccg_run_pair_dev(m0, include, norm, minLength, minCov, elem_size, byteScale, d_D, d_N, Dn));
 	return run_common(ctx, 0, include, norm, minLength, minCov, elem_size, byteScale, d_D, d_N, Dn);
 }
 
 extern "C" int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include, unsigned norm, int elem_size,
                                   double byteScale, void *d_D, int *Dn, unsigned *global_inc) {
 	if(!d_D) return CCG_ERR_ARG;
-	if(ctx && global_inc) *global_inc = ctx->global_inc;
+	CCG_MULTI_SOLO(ctx, "a run into device buffers", ccg_run_global_dev(m0, include, norm, elem_size, byteScale, d_D, Dn, global_inc));
+	if(ctx && global_inc) *global_inc = ctx->grp_world > 1 ? ctx->grp_global_inc : ctx->global_inc;
 	return run_common(ctx, 1, include, norm, 0, 0.0, elem_size, byteScale, d_D, 0, Dn);
 }
 
@@ -1407,6 +1524,7 @@ extern "C" int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include, un
  * The pair kernels run on the macro-tile row that holds the slot; the epilogue keeps that one row. */
 extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned minLength, double minCov, double *D, double *N,
                            int *cols_out) {
+	CCG_MULTI_SOLO(ctx, "a row run (-a)", ccg_run_row(m0, row_slot, norm, minLength, minCov, D, N, cols_out));
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !D || row_slot < 0 || row_slot >= ctx->n || !ctx->present[row_slot])
 		return CCG_ERR_ARG;
 	if(ctx->world > 1) {
@@ -1507,7 +1625,7 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
 /* -V: fsacmpairint (fsacmp.c:685) / fsacmprint (:646) for every compared pair, see k_variants.cu */
 static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *include, int last_row_only, ccg_variant_fn fn, void *user) {
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !fn) return CCG_ERR_ARG;
-	if(ctx->proxi || ctx->world > 1) {
+	if(ctx->proxi || ctx->world > 1 || ctx->grp_world > 1) {
 		set_err(ctx, "variant listing (-V) is not available together with %s", ctx->proxi ? "proximity masking (-P)" : "a rank partition");
 		return CCG_ERR_UNSUPPORTED;
 	}
@@ -1618,11 +1736,13 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 }
 
 extern "C" int ccg_list_variants(ccg_ctx *ctx, int pair, const unsigned char *include, ccg_variant_fn fn, void *user) {
+	CCG_MULTI_SOLO(ctx, "variant listing (-V)", ccg_list_variants(m0, pair, include, fn, user));
 	return list_variants_impl(ctx, pair, include, 0, fn, user);
 }
 
 /* -V with -a: fsacmpairint(diffile, n, j, addL, seqL, ...) of cmpFsaRowThrd (fsacmpthrd.c:552-553) */
 extern "C" int ccg_list_variants_row(ccg_ctx *ctx, int row_slot, ccg_variant_fn fn, void *user) {
+	CCG_MULTI_SOLO(ctx, "variant listing (-V)", ccg_list_variants_row(m0, row_slot, fn, user));
 	if(!ctx || !ctx->d_planes || row_slot < 0 || row_slot >= ctx->n || !ctx->present[row_slot]) return CCG_ERR_ARG;
 	unsigned char *use = (unsigned char *) calloc((size_t) ctx->n, 1);
 	if(!use) return CCG_ERR_NOMEM;
@@ -1633,7 +1753,12 @@ extern "C" int ccg_list_variants_row(ccg_ctx *ctx, int row_slot, ccg_variant_fn 
 }
 
 extern "C" int ccg_get_raw_counts(ccg_ctx *ctx, uint32_t *mism, uint32_t *ninc) {
+	CCG_MULTI_SOLO(ctx, "ccg_get_raw_counts", ccg_get_raw_counts(m0, mism, ninc));
 	if(!ctx || !ctx->d_planes) return CCG_ERR_ARG;
+	if(ctx->grp_world > 1) {
+		set_err(ctx, "ccg_get_raw_counts: a member of a K-split group holds partial sums only");
+		return CCG_ERR_UNSUPPORTED;
+	}
 	int Dn = ctx->last_Dn;
 	if(Dn < 2) return CCG_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
@@ -1663,6 +1788,9 @@ extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, 
                                       const uint32_t *const *includes, unsigned norm, unsigned minLength, double minCov,
                                       unsigned proxi, int *Dn, unsigned *global_inc) {
 	if(!seqs || !includes || n < 0) return CCG_ERR_ARG;
+	if(ctx && ctx->multi)
+		return ccg_multi_fsa_cmp_thread_out(ctx, pair, D, N, elem_size, byteScale, n, len, seqs, include, includes, norm, minLength,
+		                                    minCov, proxi, Dn, global_inc);
 	ccg_ctx *own = 0;
 	int rc;
 	if(!ctx) {
@@ -1697,7 +1825,9 @@ extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, 
 		 * the PCIe upload of slab s+1 hides behind the GEMM of slab s (run_umma / feed_slab) */
 		int kind = ctx->kernel_choice;
 		if(kind == CCG_KERNEL_AUTO) kind = (ninc >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
-		if(kind == CCG_KERNEL_UMMA && !ctx->proxi && ctx->stream_min_chunks > 0 && ctx->chunks >= ctx->stream_min_chunks) {
+		if(ctx->grp_world > 1) kind = CCG_KERNEL_UMMA;
+		if(kind == CCG_KERNEL_UMMA && !ctx->proxi && ctx->stream_min_chunks > 0 && ctx->chunks >= ctx->stream_min_chunks &&
+		   3.0 * ((double) len + 256.0) < 2147483648.0) {
 			for(int i = 0; i < n; ++i) {
 				if(!srow[i]) continue;
 				ctx->present[i] = 1;
@@ -1744,11 +1874,18 @@ extern "C" void ccg_host_free(void *p) {
 	if(p) cudaFreeHost(p);
 }
 
-extern "C" long long ccg_launch_count(const ccg_ctx *ctx) { return ctx ? ctx->launches : 0; }
-extern "C" const char *ccg_last_kernel(const ccg_ctx *ctx) { return ctx ? ctx->last_kernel : ""; }
+extern "C" long long ccg_launch_count(const ccg_ctx *ctx) {
+	if(ctx && ctx->multi) return ccg_multi_launch_count(ctx);
+	return ctx ? ctx->launches : 0;
+}
+extern "C" const char *ccg_last_kernel(const ccg_ctx *ctx) {
+	if(ctx && ctx->multi) return ccg_multi_last_kernel(ctx);
+	return ctx ? ctx->last_kernel : "";
+}
 
 extern "C" float ccg_last_phase_ms(ccg_ctx *ctx, int phase) {
 	float ms = -1.0f;
+	if(ctx && ctx->multi) return ccg_last_phase_ms(ccg_multi_member(ctx, 0), phase);
 	if(!ctx || !ctx->phase_valid || phase < 0 || phase > 1) return ms;
 	if(ctx->last_kernel_kind == CCG_KERNEL_POPC || (ctx->last_kernel_kind == CCG_KERNEL_FUSED && phase == 0)) return ms;
 	if(cudaEventSynchronize(ctx->ev_phase[2 * phase + 1]) != cudaSuccess) return -1.0f;
@@ -1758,6 +1895,7 @@ extern "C" float ccg_last_phase_ms(ccg_ctx *ctx, int phase) {
 
 extern "C" float ccg_last_compare_ms(ccg_ctx *ctx) {
 	float ms = -1.0f;
+	if(ctx && ctx->multi) return ccg_multi_last_compare_ms(ctx);
 	if(!ctx || !ctx->ev_valid) return ms;
 	if(cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;
 	if(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0f;

@@ -1,0 +1,707 @@
+/*
+ * ccg_group.cu -- the multi-GPU side of the C-ABI: the K-split group and the in-process multi-GPU context.
+ *
+ * The reference's fan-out is one C call that hands pairs to `tnum` threads sharing the heap
+ * (fsaCmpThreadOut fsacmpthrd.c:76-106, pair loop of cmpairFsaThrd :261-480).  Across GPUs the unit that is
+ * handed out here is not the pair but the ALIGNMENT AXIS: member g of a group of `world` GPUs owns the bases
+ * [b_g, b_g+1) of EVERY sample, runs the whole lower triangle on that slice with the ordinary tensor-core pair
+ * kernel, and the int32 partial sums S and I of the members are added up -- integer split-K is exact and
+ * order-independent -- by the member that OWNS a matrix row, inside its epilogue kernel, reading the peers'
+ * accumulators through peer-mapped pointers over NVLink (k_finalize_group: reduce-scatter fused with the
+ * epilogue).  What that buys over the tile partition (ccg_set_partition): every member repacks / expands exactly
+ * 1/world of the operands (a tile partition touches O(n / sqrt(world)) row blocks for 1/world of the tiles),
+ * every member runs the same tile list (no tile imbalance), host rows reach the members as `world` parallel
+ * uploads of disjoint word ranges, and there is no all-gather.
+ *
+ * Synchronisation is one device-side flag barrier per run (k_group_barrier: system-scope release / acquire on a
+ * flag word per peer in every member's window) between "my accumulators are complete" and "I read everybody's".
+ * The accumulators are double-buffered, so the barrier of run k also orders the zeroing of a buffer in run k+1
+ * after every peer's reads of it in run k-1.
+ *
+ * Members may live in one process (ccg_init_multi: one host thread per device, peer access enabled) or in one
+ * process per GPU (ccg_group_export / ccg_group_join: CUDA IPC handles exchanged by the caller, e.g. through
+ * torch.distributed in bench.py).
+ */
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <unistd.h>
+
+#include <thread>
+#include <vector>
+
+#include "ccg_internal.h"
+#include "epilogue.cuh"
+
+#define CKG(ctx, call)                                                                                 \
+	do {                                                                                               \
+		cudaError_t e__ = (call);                                                                      \
+		if(e__ != cudaSuccess) {                                                                       \
+			ccg_set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+			return CCG_ERR_CUDA;                                                                       \
+		}                                                                                              \
+	} while(0)
+
+namespace {
+
+struct GroupHandle {                /* what ccg_group_export writes into the caller's CCG_GROUP_HANDLE_BYTES */
+	unsigned magic;
+	int pid;
+	int device;
+	int npad_max;
+	unsigned long long ptr;
+	unsigned long long bytes;
+	cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(GroupHandle) <= CCG_GROUP_HANDLE_BYTES, "handle does not fit");
+constexpr unsigned GROUP_MAGIC = 0x43434747u;
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+	unsigned v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+/* Thread t talks to member t: everything this member's stream did before the barrier (its accumulator sums) is
+ * released to t, and the kernel ends only once every member has announced the same epoch to this member.  A
+ * member that never arrives (a failed peer) traps after 30 s instead of hanging the GPU. */
+__global__ void k_group_barrier(GroupBarrierParams q) {
+	const int t = threadIdx.x;
+	if(t >= q.world) return;
+	__threadfence_system();
+	q.hdr[t]->iconst_from[q.buf][q.rank] = q.i_const;
+	st_release_sys(&q.hdr[t]->arrive[q.rank], q.epoch);
+	const unsigned *mine = &q.hdr[q.rank]->arrive[t];
+	const unsigned long long t0 = global_ns();
+	while((int) (ld_acquire_sys(mine) - q.epoch) < 0) {
+		__nanosleep(200);
+		if(global_ns() - t0 > 30000000000ull) __trap();
+	}
+}
+
+__device__ __forceinline__ int4 ld_cg_int4(const int *p) { return __ldcg(reinterpret_cast<const int4 *>(p)); }
+
+/* Reduce-scatter fused with the epilogue: the owner of rows [row_lo, row_hi) adds the members' partial sums of
+ * those rows -- 128-bit loads, its own from HBM, the peers' over NVLink (L1 bypassed: the data belongs to another
+ * GPU's L2) -- and applies mismatch = (3I - S) / 4 and the reference epilogue (fsacmpthrd.c:419-475 / :247-255). */
+__global__ void __launch_bounds__(256)
+k_finalize_group(const GroupFinalizeParams q, const EpilogueParams ep) {
+	int i_const = 0;
+	if(!q.pair_mode)
+		for(int p = 0; p < q.world; ++p) i_const += q.own->iconst_from[q.buf][p];
+	for(int i = q.row_lo + (int) blockIdx.x; i < q.row_hi; i += (int) gridDim.x) {
+		if(i >= q.n) break;
+		const size_t off = (size_t) i * q.ldc;
+		for(int j4 = 4 * (int) threadIdx.x; j4 < i; j4 += 4 * (int) blockDim.x) {
+			int4 S = make_int4(0, 0, 0, 0), I = make_int4(0, 0, 0, 0);
+#pragma unroll 4
+			for(int p = 0; p < q.world; ++p) {
+				const int4 s = ld_cg_int4(q.C[p] + off + j4);
+				S.x += s.x; S.y += s.y; S.z += s.z; S.w += s.w;
+				if(q.pair_mode) {
+					const int4 v = ld_cg_int4(q.C[p] + q.plane + off + j4);
+					I.x += v.x; I.y += v.y; I.z += v.z; I.w += v.w;
+				}
+			}
+			const int Sv[4] = {S.x, S.y, S.z, S.w};
+			const int Iv[4] = {I.x, I.y, I.z, I.w};
+#pragma unroll
+			for(int e = 0; e < 4; ++e) {
+				const int j = j4 + e;
+				if(j >= i) break;
+				const int inc = q.pair_mode ? Iv[e] : i_const;
+				const unsigned mism = (unsigned) ((3 * (long long) inc - Sv[e]) >> 2);
+				ccg_write_cell(ep, i, j, mism, (unsigned) inc);
+			}
+		}
+	}
+}
+
+} // namespace
+
+/* ---- row ownership (pure host arithmetic) ----
+ * Member r finalises the matrix rows (sample slots) [bounds[r], bounds[r+1]): contiguous, so its cells are ONE
+ * contiguous span of the packed triangle (one device-to-host copy per matrix), cut so that every member gets
+ * about the same number of cells; boundaries are multiples of 8 rows. */
+static void group_row_bounds(int n, int world, int *bounds) {
+	const double total = n > 1 ? (double) n * (n - 1) / 2.0 : 0.0;
+	bounds[0] = 0;
+	for(int r = 1; r < world; ++r) {
+		const double target = total * r / world;
+		long long b = (long long) ceil((1.0 + sqrt(1.0 + 8.0 * target)) / 2.0);
+		b = (b + 7) / 8 * 8;
+		if(b < bounds[r - 1]) b = bounds[r - 1];
+		if(b > n) b = n;
+		bounds[r] = (int) b;
+	}
+	bounds[world] = n;
+}
+
+extern "C" int ccg_group_rows(int n, int rank, int world, int *row_lo, int *row_hi) {
+	if(n < 0 || world < 1 || world > CCG_GROUP_MAX || rank < 0 || rank >= world) return CCG_ERR_ARG;
+	int bounds[CCG_GROUP_MAX + 1];
+	group_row_bounds(n, world, bounds);
+	if(row_lo) *row_lo = bounds[rank];
+	if(row_hi) *row_hi = bounds[rank + 1];
+	return CCG_OK;
+}
+
+/* ---- membership ---- */
+void ccg_group_release(ccg_ctx *ctx) {
+	if(!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for(int p = 0; p < CCG_GROUP_MAX; ++p) {
+		if(ctx->grp_opened[p] && ctx->grp_win[p]) cudaIpcCloseMemHandle(ctx->grp_win[p]);
+		ctx->grp_opened[p] = 0;
+		ctx->grp_win[p] = 0;
+	}
+	ctx->grp_world = 0;
+	ctx->grp_rank = 0;
+	cudaGetLastError();
+}
+
+extern "C" int ccg_group_leave(ccg_ctx *ctx) {
+	if(!ctx) return CCG_ERR_ARG;
+	ccg_group_release(ctx);
+	return CCG_OK;
+}
+
+extern "C" int ccg_group_export(ccg_ctx *ctx, int max_samples, void *handle) {
+	if(!ctx || !handle || max_samples < 1) return CCG_ERR_ARG;
+	CKG(ctx, cudaSetDevice(ctx->device));
+	ccg_group_release(ctx);
+	const int npad = (max_samples + CCG_SLOT_PAD - 1) / CCG_SLOT_PAD * CCG_SLOT_PAD;
+	const size_t bytes = CCG_GROUP_HDR_BYTES + (size_t) 2 * 2 * npad * npad * sizeof(int);
+	if(!ctx->grp_own_win || ctx->grp_win_bytes < bytes) {
+		cudaFree(ctx->grp_own_win);
+		ctx->grp_own_win = 0;
+		ctx->grp_win_bytes = 0;
+		if(cudaMalloc(&ctx->grp_own_win, bytes) != cudaSuccess) {
+			ccg_set_err(ctx, "cudaMalloc of %zu bytes for the group window (accumulators of %d samples) failed: %s", bytes,
+			            max_samples, cudaGetErrorString(cudaGetLastError()));
+			return CCG_ERR_NOMEM;
+		}
+		ctx->grp_win_bytes = bytes;
+		ctx->grp_npad_max = npad;
+	}
+	/* flags start at zero before any peer can know this window */
+	CKG(ctx, cudaMemset(ctx->grp_own_win, 0, CCG_GROUP_HDR_BYTES));
+	ctx->grp_epoch = 0;
+	ctx->grp_buf = 0;
+	GroupHandle h;
+	memset(&h, 0, sizeof(h));
+	h.magic = GROUP_MAGIC;
+	h.pid = (int) getpid();
+	h.device = ctx->device;
+	h.npad_max = ctx->grp_npad_max;
+	h.ptr = (unsigned long long) (uintptr_t) ctx->grp_own_win;
+	h.bytes = ctx->grp_win_bytes;
+	if(cudaIpcGetMemHandle(&h.ipc, ctx->grp_own_win) != cudaSuccess) {
+		/* fine for members of one process (they use the pointer); a cross-process join will fail loudly */
+		cudaGetLastError();
+		memset(&h.ipc, 0, sizeof(h.ipc));
+	}
+	memset(handle, 0, CCG_GROUP_HANDLE_BYTES);
+	memcpy(handle, &h, sizeof(h));
+	return CCG_OK;
+}
+
+extern "C" int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *handles) {
+	if(!ctx || !handles || world < 1 || world > CCG_GROUP_MAX || rank < 0 || rank >= world) return CCG_ERR_ARG;
+	if(!ctx->grp_own_win) {
+		ccg_set_err(ctx, "ccg_group_join before ccg_group_export");
+		return CCG_ERR_ARG;
+	}
+	if(ctx->world > 1) {
+		ccg_set_err(ctx, "a context is either a member of a K-split group or a rank of a tile partition, not both");
+		return CCG_ERR_ARG;
+	}
+	CKG(ctx, cudaSetDevice(ctx->device));
+	for(int p = 0; p < CCG_GROUP_MAX; ++p) {
+		if(ctx->grp_opened[p] && ctx->grp_win[p]) cudaIpcCloseMemHandle(ctx->grp_win[p]);
+		ctx->grp_opened[p] = 0;
+		ctx->grp_win[p] = 0;
+	}
+	const int me = (int) getpid();
+	int npad_min = ctx->grp_npad_max;
+	for(int p = 0; p < world; ++p) {
+		GroupHandle h;
+		memcpy(&h, (const char *) handles + (size_t) p * CCG_GROUP_HANDLE_BYTES, sizeof(h));
+		if(h.magic != GROUP_MAGIC) {
+			ccg_set_err(ctx, "handle %d of the group is not a ccg_group_export handle", p);
+			return CCG_ERR_ARG;
+		}
+		if(h.npad_max < npad_min) npad_min = h.npad_max;
+		if(p == rank) {
+			if(h.pid != me || (void *) (uintptr_t) h.ptr != ctx->grp_own_win) {
+				ccg_set_err(ctx, "handle %d is not this context's own export", p);
+				return CCG_ERR_ARG;
+			}
+			ctx->grp_win[p] = ctx->grp_own_win;
+		} else if(h.pid == me) {
+			/* member of the same process: its pointer is valid here once peer access is on */
+			if(h.device != ctx->device) {
+				int can = 0;
+				CKG(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
+				if(!can) {
+					ccg_set_err(ctx, "device %d cannot access device %d: no peer path for the K-split group", ctx->device, h.device);
+					return CCG_ERR_UNSUPPORTED;
+				}
+				cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+				if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+					ccg_set_err(ctx, "cudaDeviceEnablePeerAccess(%d) failed: %s", h.device, cudaGetErrorString(e));
+					return CCG_ERR_CUDA;
+				}
+				cudaGetLastError();
+			}
+			ctx->grp_win[p] = (void *) (uintptr_t) h.ptr;
+		} else {
+			void *q = 0;
+			cudaError_t e = cudaIpcOpenMemHandle(&q, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+			if(e != cudaSuccess) {
+				ccg_set_err(ctx, "cudaIpcOpenMemHandle of member %d's window failed: %s", p, cudaGetErrorString(e));
+				cudaGetLastError();
+				return CCG_ERR_CUDA;
+			}
+			ctx->grp_win[p] = q;
+			ctx->grp_opened[p] = 1;
+		}
+	}
+	ctx->grp_npad_max = npad_min < ctx->grp_npad_max ? npad_min : ctx->grp_npad_max;
+	ctx->grp_rank = rank;
+	ctx->grp_world = world;
+	ctx->grp_total_len = 0;
+	ctx->grp_global_inc = 0;
+	return CCG_OK;
+}
+
+extern "C" int ccg_group_set_alignment(ccg_ctx *ctx, long long total_len, unsigned global_inc) {
+	if(!ctx || total_len < 0) return CCG_ERR_ARG;
+	ctx->grp_total_len = total_len;
+	ctx->grp_global_inc = global_inc;
+	return CCG_OK;
+}
+
+extern "C" int ccg_group_last_span(const ccg_ctx *ctx, int *row_lo, int *row_hi, long long *cell_lo, long long *cell_hi) {
+	if(!ctx) return CCG_ERR_ARG;
+	if(row_lo) *row_lo = ctx->grp_rows[0];
+	if(row_hi) *row_hi = ctx->grp_rows[1];
+	if(cell_lo) *cell_lo = ctx->grp_span[0];
+	if(cell_hi) *cell_hi = ctx->grp_span[1];
+	return CCG_OK;
+}
+
+/* the accumulator buffer of this run inside the member's own window */
+int ccg_group_accumulators(ccg_ctx *ctx, int **C_S, int **C_I) {
+	if(ctx->n_pad > ctx->grp_npad_max) {
+		ccg_set_err(ctx, "the group window was exported for %d sample slots, the problem has %d", ctx->grp_npad_max, ctx->n_pad);
+		return CCG_ERR_ARG;
+	}
+	const size_t plane = (size_t) ctx->n_pad * ctx->n_pad;
+	const size_t buf_ints = (size_t) 2 * ctx->grp_npad_max * ctx->grp_npad_max;
+	int *base = (int *) ((char *) ctx->grp_own_win + CCG_GROUP_HDR_BYTES) + (size_t) ctx->grp_buf * buf_ints;
+	*C_S = base;
+	*C_I = base + plane;
+	return CCG_OK;
+}
+
+/* after the member's GEMM: barrier with the peers, then reduce + epilogue of the rows this member owns */
+int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const) {
+	const int world = ctx->grp_world, rank = ctx->grp_rank;
+	GroupBarrierParams b;
+	memset(&b, 0, sizeof(b));
+	for(int p = 0; p < world; ++p) b.hdr[p] = (GroupHeader *) ctx->grp_win[p];
+	b.rank = rank;
+	b.world = world;
+	b.buf = ctx->grp_buf;
+	b.i_const = i_const;
+	b.epoch = ++ctx->grp_epoch;
+	k_group_barrier<<<1, 32, 0, ctx->stream>>>(b);
+	ctx->launches++;
+	CKG(ctx, cudaGetLastError());
+
+	int bounds[CCG_GROUP_MAX + 1];
+	group_row_bounds(ctx->n, world, bounds);
+	GroupFinalizeParams q;
+	memset(&q, 0, sizeof(q));
+	const size_t buf_ints = (size_t) 2 * ctx->grp_npad_max * ctx->grp_npad_max;
+	for(int p = 0; p < world; ++p)
+		q.C[p] = (const int *) ((const char *) ctx->grp_win[p] + CCG_GROUP_HDR_BYTES) + (size_t) ctx->grp_buf * buf_ints;
+	q.own = (const GroupHeader *) ctx->grp_win[rank];
+	q.plane = (size_t) ctx->n_pad * ctx->n_pad;
+	q.world = world;
+	q.ldc = ctx->n_pad;
+	q.n = ctx->n;
+	q.pair_mode = ctx->pair_mode;            /* a three-plane store carries the inclusion counts in the I plane */
+	q.buf = ctx->grp_buf;
+	q.row_lo = bounds[rank];
+	q.row_hi = bounds[rank + 1];
+	/* the packed span of those rows over the included samples */
+	long long r_lo = ctx->last_Dn, r_hi = ctx->last_Dn;
+	for(int i = q.row_lo; i < ctx->n; ++i)
+		if(ctx->h_rank[i] >= 0) { r_lo = ctx->h_rank[i]; break; }
+	for(int i = q.row_hi; i < ctx->n; ++i)
+		if(ctx->h_rank[i] >= 0) { r_hi = ctx->h_rank[i]; break; }
+	ctx->grp_rows[0] = q.row_lo;
+	ctx->grp_rows[1] = q.row_hi;
+	ctx->grp_span[0] = r_lo * (r_lo - 1) / 2;
+	ctx->grp_span[1] = r_hi * (r_hi - 1) / 2;
+	const int rows = q.row_hi - q.row_lo;
+	if(rows > 0) {
+		int grid = rows < 8 * ctx->sm_count ? rows : 8 * ctx->sm_count;
+		k_finalize_group<<<grid, 256, 0, ctx->stream>>>(q, ep);
+		ctx->launches++;
+		CKG(ctx, cudaGetLastError());
+	}
+	ctx->grp_buf ^= 1;
+	return CCG_OK;
+}
+
+/* ====================================================================================================
+ * In-process multi-GPU context (ccg_init_multi): one leader handle, one member context per device.
+ * The leader takes the same calls as a single-device context; for a problem that is worth splitting
+ * (tensor path, long alignment, no -P / -y) the members form a K-split group and every heavy call runs
+ * on one host thread per member, otherwise member 0 works alone.  This is the fan-out the reference
+ * does with pthreads inside fsaCmpThreadOut (fsacmpthrd.c:76-106), one level up.
+ * ==================================================================================================== */
+struct ccg_multi {
+	int n;                                 /* member contexts */
+	ccg_ctx *member[CCG_GROUP_MAX];
+	int joined;                            /* members currently joined as a group of this many (0 = not joined) */
+	int joined_samples;                    /* sample slots the members' windows were exported for */
+	int active;                            /* members working on the current problem: 1 = member 0 alone */
+	int samples, len, pair;
+	int base0[CCG_GROUP_MAX + 1];          /* first base of every member's slice (multiples of 256) */
+	int special;                           /* -P or -y set: those runs stay on one device */
+	int kernel_choice;
+	int force;                             /* CCG_MULTI_FORCE=1: split whatever the size (tests) */
+	char last_kernel[160];
+};
+
+template <class F>
+static int multi_parallel(ccg_multi *m, int count, F f) {
+	std::vector<int> rcs((size_t) count, CCG_OK);
+	std::vector<std::thread> th;
+	for(int g = 1; g < count; ++g) th.emplace_back([&, g]() { rcs[(size_t) g] = f(g); });
+	rcs[0] = f(0);
+	for(auto &t : th) t.join();
+	for(int g = 0; g < count; ++g)
+		if(rcs[(size_t) g]) return rcs[(size_t) g] | (g << 8);
+	return CCG_OK;
+}
+
+static int multi_fail(ccg_ctx *lead, int packed) {
+	const int g = packed >> 8, rc = packed & 0xFF;
+	if(rc) ccg_set_err(lead, "gpu %d (device %d): %s", g, lead->multi->member[g]->device, lead->multi->member[g]->err);
+	return rc;
+}
+
+static int multi_unsupported(ccg_ctx *lead, const char *what) {
+	ccg_set_err(lead, "%s runs on one device: not available while the problem is split over %d GPUs", what, lead->multi->active);
+	return CCG_ERR_UNSUPPORTED;
+}
+
+extern "C" int ccg_init_multi_devices(ccg_ctx **out, int ngpus, const int *devices) {
+	if(!out || ngpus < 1 || ngpus > CCG_GROUP_MAX || !devices) return CCG_ERR_ARG;
+	*out = 0;
+	ccg_ctx *lead = 0;
+	int rc = ccg_init(&lead, devices[0]);
+	if(rc) return rc;
+	ccg_multi *m = (ccg_multi *) calloc(1, sizeof(ccg_multi));
+	if(!m) { ccg_destroy(lead); return CCG_ERR_NOMEM; }
+	m->n = ngpus;
+	m->active = 1;
+	m->force = getenv("CCG_MULTI_FORCE") ? atoi(getenv("CCG_MULTI_FORCE")) : 0;
+	for(int g = 0; g < ngpus && !rc; ++g) rc = ccg_init(&m->member[g], devices[g]);
+	if(rc) {
+		for(int g = 0; g < ngpus; ++g) ccg_destroy(m->member[g]);
+		free(m);
+		ccg_destroy(lead);
+		return rc;
+	}
+	lead->multi = m;
+	*out = lead;
+	return CCG_OK;
+}
+
+extern "C" int ccg_init_multi(ccg_ctx **out, int ngpus) {
+	int count = 0;
+	if(!out) return CCG_ERR_ARG;
+	if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+		cudaGetLastError();
+		ccg_set_err(0, "no CUDA device visible");
+		return CCG_ERR_NO_DEVICE;
+	}
+	if(ngpus <= 0 || ngpus > count) ngpus = count;
+	if(ngpus > CCG_GROUP_MAX) ngpus = CCG_GROUP_MAX;
+	int devices[CCG_GROUP_MAX];
+	for(int g = 0; g < ngpus; ++g) devices[g] = g;
+	return ccg_init_multi_devices(out, ngpus, devices);
+}
+
+extern "C" int ccg_multi_gpus(const ccg_ctx *ctx, int *active) {
+	if(!ctx || !ctx->multi) { if(active) *active = 1; return 1; }
+	if(active) *active = ctx->multi->active;
+	return ctx->multi->n;
+}
+
+void ccg_multi_destroy(ccg_ctx *lead) {
+	ccg_multi *m = lead->multi;
+	if(!m) return;
+	for(int g = 0; g < m->n; ++g) ccg_destroy(m->member[g]);
+	free(m);
+	lead->multi = 0;
+}
+
+/* (re)joins the first `active` members as a group able to hold `samples` slots */
+static int multi_join(ccg_ctx *lead, int active, int samples) {
+	ccg_multi *m = lead->multi;
+	if(m->joined == active && m->joined_samples >= samples) return CCG_OK;
+	for(int g = 0; g < m->n; ++g) ccg_group_leave(m->member[g]);
+	m->joined = 0;
+	if(active < 2) return CCG_OK;
+	std::vector<char> handles((size_t) active * CCG_GROUP_HANDLE_BYTES);
+	for(int g = 0; g < active; ++g) {
+		int rc = ccg_group_export(m->member[g], samples, handles.data() + (size_t) g * CCG_GROUP_HANDLE_BYTES);
+		if(rc) return multi_fail(lead, rc | (g << 8));
+	}
+	for(int g = 0; g < active; ++g) {
+		int rc = ccg_group_join(m->member[g], g, active, handles.data());
+		if(rc) return multi_fail(lead, rc | (g << 8));
+	}
+	m->joined = active;
+	m->joined_samples = samples;
+	return CCG_OK;
+}
+
+/* how many members a problem is split over: the tensor path on a long alignment, nothing that has to see a whole
+ * sample at once (-P walks the alignment sequentially, a motif may straddle a slice boundary) */
+static int multi_choose_active(const ccg_multi *m, int n, int len) {
+	if(m->n < 2 || m->special || len < 512) return 1;
+	if(m->kernel_choice == CCG_KERNEL_POPC || m->kernel_choice == CCG_KERNEL_FUSED) return 1;
+	int a = m->n;
+	if(m->force) {
+		while(a > 1 && len / a < 256) --a;
+		return a;
+	}
+	if(n < 512) return 1;
+	while(a > 1 && len / a < 128 * 1024) --a;
+	return a;
+}
+
+int ccg_multi_set_problem(ccg_ctx *lead, int n, int len, int pair_mode) {
+	ccg_multi *m = lead->multi;
+	const int active = multi_choose_active(m, n, len);
+	int rc = multi_join(lead, active, n > 0 ? n : 1);
+	if(rc) return rc;
+	m->active = active;
+	m->samples = n;
+	m->len = len;
+	m->pair = pair_mode ? 1 : 0;
+	lead->n = n;
+	lead->len = len;
+	lead->pair_mode = m->pair;
+	for(int g = 0; g <= active; ++g) m->base0[g] = g == active ? len : (int) ((long long) len * g / active / 256 * 256);
+	for(int g = 0; g < active; ++g) {
+		ccg_set_kernel(m->member[g], active > 1 ? CCG_KERNEL_UMMA : m->kernel_choice);
+		rc = ccg_set_problem(m->member[g], n, m->base0[g + 1] - m->base0[g], pair_mode);
+		if(rc) return multi_fail(lead, rc | (g << 8));
+		if(active > 1) ccg_group_set_alignment(m->member[g], len, 0);
+	}
+	return CCG_OK;
+}
+
+int ccg_multi_set_kernel(ccg_ctx *lead, int kernel) {
+	ccg_multi *m = lead->multi;
+	m->kernel_choice = kernel;
+	for(int g = 0; g < m->n; ++g) ccg_set_kernel(m->member[g], kernel);
+	return CCG_OK;
+}
+
+int ccg_multi_sync(ccg_ctx *lead) {
+	ccg_multi *m = lead->multi;
+	for(int g = 0; g < m->n; ++g) {
+		int rc = ccg_sync(m->member[g]);
+		if(rc) return multi_fail(lead, rc | (g << 8));
+	}
+	return CCG_OK;
+}
+
+void ccg_multi_note_special(ccg_ctx *lead, int bit, int on) {
+	if(on) lead->multi->special |= bit;
+	else lead->multi->special &= ~bit;
+}
+ccg_ctx *ccg_multi_solo(ccg_ctx *lead, const char *what, int *rc) {
+	ccg_multi *m = lead->multi;
+	if(m->active > 1) { *rc = multi_unsupported(lead, what); return 0; }
+	*rc = CCG_OK;
+	return m->member[0];
+}
+/* copies member 0's message up after a forwarded call failed */
+int ccg_multi_forwarded(ccg_ctx *lead, int rc) { return rc ? multi_fail(lead, rc) : CCG_OK; }
+
+int ccg_multi_put_global_mask(ccg_ctx *lead, const uint32_t *mask, int apply) {
+	ccg_multi *m = lead->multi;
+	unsigned inc = 0;
+	const int words = (m->len >> 5) + ((m->len & 31) ? 1 : 0);
+	for(int w = 0; w < words; ++w) inc += (unsigned) __builtin_popcount(mask[w]);
+	for(int g = 0; g < m->active; ++g) {
+		const uint32_t *part = mask + m->base0[g] / 32;
+		int rc = apply ? ccg_apply_global_mask(m->member[g], part) : ccg_put_global_mask(m->member[g], part);
+		if(rc) return multi_fail(lead, rc | (g << 8));
+		if(m->active > 1) ccg_group_set_alignment(m->member[g], m->len, inc);
+	}
+	lead->global_inc = inc;
+	return CCG_OK;
+}
+
+int ccg_multi_build_global_mask(ccg_ctx *lead, const unsigned char *include, unsigned *global_inc) {
+	ccg_multi *m = lead->multi;
+	unsigned inc = 0;
+	for(int g = 0; g < m->active; ++g) {
+		unsigned part = 0;
+		int rc = ccg_build_global_mask(m->member[g], include, &part);
+		if(rc) return multi_fail(lead, rc | (g << 8));
+		inc += part;
+	}
+	if(m->active > 1)
+		for(int g = 0; g < m->active; ++g) ccg_group_set_alignment(m->member[g], m->len, inc);
+	lead->global_inc = inc;
+	if(global_inc) *global_inc = inc;
+	return CCG_OK;
+}
+
+int ccg_multi_put_samples_packed(ccg_ctx *lead, int first, int count, const uint64_t *const *seqs, const uint32_t *const *includes) {
+	ccg_multi *m = lead->multi;
+	if(m->active == 1) return ccg_multi_forwarded(lead, ccg_put_samples_packed(m->member[0], first, count, seqs, includes));
+	if(count <= 0) return CCG_OK;
+	int rc = multi_parallel(m, m->active, [&](int g) -> int {
+		const size_t w0 = (size_t) m->base0[g] / 32;
+		std::vector<const uint64_t *> s((size_t) count);
+		std::vector<const uint32_t *> k((size_t) count);
+		for(int i = 0; i < count; ++i) {
+			s[(size_t) i] = seqs[i] ? seqs[i] + w0 : 0;
+			k[(size_t) i] = (includes && includes[i]) ? includes[i] + w0 : 0;
+		}
+		int r = ccg_put_samples_packed(m->member[g], first, count, s.data(), includes ? k.data() : 0);
+		/* the row pointer arrays die here: the copies must have been issued AND staged */
+		if(!r) r = ccg_sync(m->member[g]);
+		return r;
+	});
+	return rc ? multi_fail(lead, rc) : CCG_OK;
+}
+
+int ccg_multi_put_sample_codes(ccg_ctx *lead, int idx, const unsigned char *codes) {
+	ccg_multi *m = lead->multi;
+	for(int g = 0; g < m->active; ++g) {
+		int rc = ccg_put_sample_codes(m->member[g], idx, codes + m->base0[g]);
+		if(rc) return multi_fail(lead, rc | (g << 8));
+	}
+	return CCG_OK;
+}
+
+int ccg_multi_get_inc_counts(ccg_ctx *lead, unsigned *out) {
+	ccg_multi *m = lead->multi;
+	const int n = m->samples;
+	std::vector<unsigned> part((size_t) (n ? n : 1));
+	for(int i = 0; i < n; ++i) out[i] = 0;
+	for(int g = 0; g < m->active; ++g) {
+		int rc = ccg_get_inc_counts(m->member[g], part.data());
+		if(rc) return multi_fail(lead, rc | (g << 8));
+		for(int i = 0; i < n; ++i) out[i] += part[(size_t) i];
+	}
+	return CCG_OK;
+}
+
+static void multi_note_kernel(ccg_ctx *lead) {
+	ccg_multi *m = lead->multi;
+	if(m->active > 1) snprintf(m->last_kernel, sizeof(m->last_kernel), "%s x %d gpus (K split)", ccg_last_kernel(m->member[0]), m->active);
+	else snprintf(m->last_kernel, sizeof(m->last_kernel), "%s", ccg_last_kernel(m->member[0]));
+}
+
+int ccg_multi_run(ccg_ctx *lead, int pair, const unsigned char *include, unsigned norm, unsigned minLength, double minCov,
+                  int elem_size, double byteScale, void *D, void *N, int *Dn, unsigned *global_inc) {
+	ccg_multi *m = lead->multi;
+	if(global_inc) *global_inc = lead->global_inc;
+	std::vector<int> dn((size_t) m->active, 0);
+	int rc = multi_parallel(m, m->active, [&](int g) -> int {
+		unsigned gi = 0;
+		return pair ? ccg_run_pair(m->member[g], include, norm, minLength, minCov, elem_size, byteScale, D, N, &dn[(size_t) g])
+		            : ccg_run_global(m->member[g], include, norm, elem_size, byteScale, D, &dn[(size_t) g], &gi);
+	});
+	if(rc) return multi_fail(lead, rc);
+	if(Dn) *Dn = dn[0];
+	if(m->active == 1 && global_inc) *global_inc = m->member[0]->global_inc;
+	multi_note_kernel(lead);
+	return CCG_OK;
+}
+
+int ccg_multi_fsa_cmp_thread_out(ccg_ctx *lead, int pair, void *D, void *N, int elem_size, double byteScale, int n, int len,
+                                 const uint64_t *const *seqs, const unsigned char *include, const uint32_t *const *includes,
+                                 unsigned norm, unsigned minLength, double minCov, unsigned proxi, int *Dn, unsigned *global_inc) {
+	ccg_multi *m = lead->multi;
+	const int special = m->special;
+	if(proxi && pair) m->special = 1;
+	int rc = ccg_multi_set_problem(lead, n, len, pair);
+	m->special = special;
+	if(rc) return rc;
+	if(m->active == 1) {
+		rc = ccg_fsa_cmp_thread_out(m->member[0], pair, D, N, elem_size, byteScale, n, len, seqs, include, includes, norm, minLength,
+		                            minCov, proxi, Dn, global_inc);
+		multi_note_kernel(lead);
+		return ccg_multi_forwarded(lead, rc);
+	}
+	unsigned ginc = 0;
+	if(!pair) {
+		const int words = (len >> 5) + ((len & 31) ? 1 : 0);
+		for(int w = 0; w < words; ++w) ginc += (unsigned) __builtin_popcount(includes[0][w]);
+	}
+	std::vector<int> dn((size_t) m->active, 0);
+	rc = multi_parallel(m, m->active, [&](int g) -> int {
+		const size_t w0 = (size_t) m->base0[g] / 32;
+		std::vector<const uint64_t *> s((size_t) (n ? n : 1));
+		std::vector<const uint32_t *> k((size_t) (n ? n : 1));
+		for(int i = 0; i < n; ++i) {
+			s[(size_t) i] = seqs[i] ? seqs[i] + w0 : 0;
+			k[(size_t) i] = pair ? (includes[i] ? includes[i] + w0 : 0) : includes[0] + w0;
+		}
+		if(!pair) k[0] = includes[0] + w0;
+		ccg_group_set_alignment(m->member[g], len, ginc);
+		unsigned gi = 0;
+		return ccg_fsa_cmp_thread_out(m->member[g], pair, D, N, elem_size, byteScale, n, m->base0[g + 1] - m->base0[g], s.data(),
+		                              include, k.data(), norm, minLength, minCov, 0, &dn[(size_t) g], &gi);
+	});
+	if(rc) return multi_fail(lead, rc);
+	if(Dn) *Dn = dn[0];
+	if(global_inc) *global_inc = ginc;
+	lead->global_inc = ginc;
+	multi_note_kernel(lead);
+	return CCG_OK;
+}
+
+long long ccg_multi_launch_count(const ccg_ctx *lead) {
+	long long k = 0;
+	for(int g = 0; g < lead->multi->n; ++g) k += ccg_launch_count(lead->multi->member[g]);
+	return k;
+}
+const char *ccg_multi_last_kernel(const ccg_ctx *lead) { return lead->multi->last_kernel; }
+float ccg_multi_last_compare_ms(ccg_ctx *lead) {
+	float ms = -1.0f;
+	for(int g = 0; g < lead->multi->active; ++g) {
+		const float v = ccg_last_compare_ms(lead->multi->member[g]);
+		if(v > ms) ms = v;
+	}
+	return ms;
+}
+ccg_ctx *ccg_multi_member(ccg_ctx *lead, int g) { return (lead->multi && g >= 0 && g < lead->multi->n) ? lead->multi->member[g] : 0; }

@@ -37,6 +37,7 @@
 #define CCG_UMMA_BM 256      /* macro tile rows    (tcgen05 M = 256 over a CTA pair: 2 x 128 TMEM lanes) */
 #define CCG_UMMA_BN 256      /* macro tile columns (tcgen05 N) */
 #define CCG_SLOT_PAD 256     /* slots are padded to a multiple of this */
+#define CCG_FP4_MAX_PAIRS 20000   /* chunk pairs per kind::mxf4 work item: 3 * 256 * 20000 < 2^24, every partial sum exact in f32 */
 
 struct EpilogueParams {
 	int mode;              /* 0 pair (fsacmpthrd.c:419-475), 1 global (fsacmpthrd.c:247-255) */
@@ -96,12 +97,40 @@ struct UmmaParams {
 	int single;            /* tiles are 128 x 256 and run on the single-CTA kernel (CCG_UMMA1=1, experiments) */
 };
 
+/* ---- K-split group: every member GPU owns a slice of the alignment (all samples, 1/world of the bases), runs
+ * the whole lower triangle on it, and the members' int32 partial sums are added up by the OWNER of a matrix row
+ * through peer-mapped pointers (NVLink), fused with the epilogue -- ccg_group.cu ---- */
+#define CCG_GROUP_MAX 16
+#define CCG_GROUP_HDR_BYTES 4096
+
+struct GroupHeader {                        /* start of every member's peer window */
+	unsigned arrive[CCG_GROUP_MAX];         /* arrive[p]: last barrier epoch member p announced to this member */
+	int iconst_from[2][CCG_GROUP_MAX];      /* shared-mask mode: member p's constant inclusion count, per C buffer */
+};
+
+struct GroupBarrierParams {
+	GroupHeader *hdr[CCG_GROUP_MAX];
+	int rank, world, buf, i_const;
+	unsigned epoch;
+};
+
+struct GroupFinalizeParams {
+	const int *C[CCG_GROUP_MAX];            /* every member's current accumulator buffer: S plane, I plane behind it */
+	const GroupHeader *own;
+	size_t plane;                           /* ints per plane (n_pad * ldc) */
+	int world, ldc, n, pair_mode, buf;
+	int row_lo, row_hi;                     /* sample slots (matrix rows) this member finalises */
+};
+
+struct ccg_multi;
+
 struct ccg_ctx {
 	int device;
 	int sm_count;
 	cudaStream_t own_stream, stream;
 	cudaStream_t aux_stream;   /* operand expansion of slab s+1 runs here, under the GEMM of slab s */
 	cudaEvent_t ev_fork, ev_launch, ev_x[2], ev_g[2];
+	cudaEvent_t ev_switch;     /* ccg_set_stream: orders the new stream after the work queued on the old one */
 	int kernel_choice;
 	int rank, world;
 	int win_on, win[4];            /* macro-tile window [tm_lo, tm_hi) x [tn_lo, tn_hi), ccg_set_tile_window */
@@ -191,6 +220,21 @@ struct ccg_ctx {
 	unsigned *mat_part_rows, *mat_rows;
 	size_t mat_part_cap;
 
+	/* K-split group membership (grp_world > 1), ccg_group.cu */
+	int grp_world, grp_rank;
+	void *grp_win[CCG_GROUP_MAX];          /* peer windows: header + 2 accumulator buffers; [grp_rank] is this member's own */
+	unsigned char grp_opened[CCG_GROUP_MAX];   /* mapped with cudaIpcOpenMemHandle (closed on leave) */
+	void *grp_own_win;                     /* this context's exported window (cudaMalloc) */
+	size_t grp_win_bytes;
+	int grp_npad_max;                      /* slots the window's accumulators were sized for */
+	unsigned grp_epoch;                    /* barriers passed so far */
+	int grp_buf;                           /* accumulator buffer of the next run (the two are used in turn) */
+	long long grp_total_len;               /* length of the whole alignment: the minCov gate (fsacmpthrd.c:292) */
+	unsigned grp_global_inc;               /* shared-mask mode: getNpos of the whole global mask */
+	long long grp_span[2];                 /* packed cells [lo, hi) the last run of this member wrote */
+	int grp_rows[2];                       /* sample slots [lo, hi) it finalised */
+	struct ccg_multi *multi;               /* leader of an in-process multi-GPU context (ccg_init_multi) */
+
 	cudaEvent_t ev0, ev1;
 	int ev_valid;
 	cudaEvent_t ev_phase[4];   /* tensor-core path, first slab: expand begin/end, GEMM begin/end */
@@ -243,6 +287,42 @@ cudaError_t ccg_launch_variants(ccg_ctx *ctx, const VariantParams &p, int write,
 
 /* k_matdist.cu */
 void ccg_mat_free(ccg_ctx *ctx);
+
+/* ccg_group.cu */
+void ccg_set_err(ccg_ctx *ctx, const char *fmt, ...);
+void ccg_group_release(ccg_ctx *ctx);
+int ccg_group_accumulators(ccg_ctx *ctx, int **C_S, int **C_I);
+int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const);
+void ccg_multi_destroy(ccg_ctx *ctx);
+int ccg_multi_set_problem(ccg_ctx *lead, int n, int len, int pair_mode);
+int ccg_multi_set_kernel(ccg_ctx *lead, int kernel);
+int ccg_multi_sync(ccg_ctx *lead);
+void ccg_multi_note_special(ccg_ctx *lead, int bit, int on);
+ccg_ctx *ccg_multi_solo(ccg_ctx *lead, const char *what, int *rc);
+int ccg_multi_forwarded(ccg_ctx *lead, int rc);
+int ccg_multi_put_global_mask(ccg_ctx *lead, const uint32_t *mask, int apply);
+int ccg_multi_build_global_mask(ccg_ctx *lead, const unsigned char *include, unsigned *global_inc);
+int ccg_multi_put_samples_packed(ccg_ctx *lead, int first, int count, const uint64_t *const *seqs, const uint32_t *const *includes);
+int ccg_multi_put_sample_codes(ccg_ctx *lead, int idx, const unsigned char *codes);
+int ccg_multi_get_inc_counts(ccg_ctx *lead, unsigned *out);
+int ccg_multi_run(ccg_ctx *lead, int pair, const unsigned char *include, unsigned norm, unsigned minLength, double minCov,
+                  int elem_size, double byteScale, void *D, void *N, int *Dn, unsigned *global_inc);
+int ccg_multi_fsa_cmp_thread_out(ccg_ctx *lead, int pair, void *D, void *N, int elem_size, double byteScale, int n, int len,
+                                 const uint64_t *const *seqs, const unsigned char *include, const uint32_t *const *includes,
+                                 unsigned norm, unsigned minLength, double minCov, unsigned proxi, int *Dn, unsigned *global_inc);
+long long ccg_multi_launch_count(const ccg_ctx *lead);
+const char *ccg_multi_last_kernel(const ccg_ctx *lead);
+float ccg_multi_last_compare_ms(ccg_ctx *lead);
+ccg_ctx *ccg_multi_member(ccg_ctx *lead, int g);
+
+/* a call that only one device can take: forwarded to member 0 of a multi-GPU context unless the problem is split */
+#define CCG_MULTI_SOLO(ctx, what, call)                      \
+	if((ctx) && (ctx)->multi) {                              \
+		int rc__ = 0;                                        \
+		ccg_ctx *m0 = ccg_multi_solo((ctx), what, &rc__);    \
+		if(!m0) return rc__;                                 \
+		return ccg_multi_forwarded((ctx), (call));           \
+	}
 
 /* k_pairdist_fused.cu */
 cudaError_t ccg_launch_fused(ccg_ctx *ctx, const UmmaParams &p);

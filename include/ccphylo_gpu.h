@@ -53,7 +53,8 @@ enum {
 enum {
 	CCG_KERNEL_AUTO = 0,
 	CCG_KERNEL_POPC = 1,     /* bit-sliced LOP3+POPC path on the INT pipe */
-	CCG_KERNEL_UMMA = 2,     /* int8 contraction on tcgen05 tensor cores, operands expanded to an HBM panel */
+	CCG_KERNEL_UMMA = 2,     /* contraction on tcgen05 tensor cores (CTA pairs; e2m1 operands on kind::mxf4, or int8 on kind::i8
+	                          * with CCG_I8=1), operands expanded to an HBM panel */
 	CCG_KERNEL_FUSED = 3     /* same contraction, operands expanded from the bit planes inside the CTA */
 };
 
@@ -67,16 +68,58 @@ int ccg_init(ccg_ctx **ctx, int device);
 void ccg_destroy(ccg_ctx *ctx);
 
 /* Launch everything on the caller's cudaStream_t (NULL = the context's own
- * stream).  Lets a host that already owns a stream order and time the work. */
+ * stream).  Lets a host that already owns a stream order and time the work.
+ * The new stream is ordered after everything still queued on the old one. */
 int ccg_set_stream(ccg_ctx *ctx, void *cuda_stream);
 int ccg_set_kernel(ccg_ctx *ctx, int kernel);
 /* Block until all work queued by this context has finished. */
 int ccg_sync(ccg_ctx *ctx);
 
-/* This context computes only the lower-triangular tile blocks dealt to `rank`
- * of `world` (one process per GPU, no data-path collective).  Cells of other
- * ranks are left untouched in device outputs and read back as zero in host
- * outputs.  Default rank 0 of 1. */
+/* ---------------------------------------------------------------------------
+ * Multi-GPU.  The reference's fan-out is one C call that spreads the pair loop over `tnum` threads
+ * (fsaCmpThreadOut fsacmpthrd.c:76-106).  Here the same call spreads over the GPUs of one box by cutting
+ * the ALIGNMENT axis ("K split"): member g of `world` GPUs holds the bases [b_g, b_g+1) of every sample
+ * (b_g multiples of 256), runs the whole lower triangle on its slice, and the int32 partial sums are
+ * added by the member that owns a matrix row -- over NVLink, fused with the epilogue.  Integer split
+ * sums are exact, so the result is bit-identical to a single-GPU run.
+ *
+ * In one process: ccg_init_multi returns ONE handle that takes the calls below like a single-device
+ * context (ccg_set_problem .. ccg_put_sample_codes / ccg_put_samples_packed / ccg_put_global_mask ..
+ * ccg_run_pair / ccg_run_global, ccg_fsa_cmp_thread_out, ccg_get_inc_counts, ccg_build_global_mask).
+ * A problem worth splitting (tensor path, >= 128 kbp per GPU, no -P / -y) runs on all members, one
+ * host thread per device; anything else runs on member 0 alone; calls that need a whole sample on one
+ * device (-P, -y, -V, -a, device-pointer uploads) return CCG_ERR_UNSUPPORTED while a problem is split.
+ * ngpus <= 0: every visible device.  ccg_multi_gpus returns the member count, *active the number
+ * working on the current problem. */
+int ccg_init_multi(ccg_ctx **ctx, int ngpus);
+int ccg_init_multi_devices(ccg_ctx **ctx, int ngpus, const int *devices);   /* devices may repeat (tests on one GPU) */
+int ccg_multi_gpus(const ccg_ctx *ctx, int *active);
+
+/* One process per GPU (torchrun, MPI): every rank creates its context with ccg_init, exports a handle
+ * to the peer window that holds its accumulators (sized for max_samples sample slots), the ranks
+ * exchange the CCG_GROUP_HANDLE_BYTES blobs (any host channel), and every rank joins with all of them
+ * in rank order.  From then on the context's problem is THIS RANK'S SLICE of the alignment:
+ * ccg_set_problem(n, slice length) and the put / run calls work on the slice, every rank passes the
+ * same include[] and epilogue arguments, the run calls synchronise the ranks on the device, and a rank
+ * writes only the cells of the matrix rows it owns: ccg_group_rows(n, rank, world) in sample slots,
+ * ccg_group_last_span in packed cells (one contiguous span; host outputs outside it are left untouched).
+ * ccg_group_set_alignment: the length of the WHOLE alignment (the minCov gate, fsacmpthrd.c:292) and,
+ * for shared-mask runs, getNpos of the whole global mask (fsacmpthrd.c:164-176); call it before a run.
+ * Not available on such a context: -P, ccg_run_row, ccg_list_variants, ccg_get_raw_counts,
+ * ccg_set_partition, ccg_set_tile_window.  A rank that never reaches the run makes the others fail
+ * after 30 s (CCG_ERR_CUDA). */
+#define CCG_GROUP_HANDLE_BYTES 128
+int ccg_group_export(ccg_ctx *ctx, int max_samples, void *handle);
+int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *handles);
+int ccg_group_leave(ccg_ctx *ctx);
+int ccg_group_set_alignment(ccg_ctx *ctx, long long total_len, unsigned global_inc);
+int ccg_group_rows(int n, int rank, int world, int *row_lo, int *row_hi);     /* pure host arithmetic */
+int ccg_group_last_span(const ccg_ctx *ctx, int *row_lo, int *row_hi, long long *cell_lo, long long *cell_hi);
+
+/* The older deal, kept for the sample-shard ring: this context computes only the lower-triangular
+ * tile blocks dealt to `rank` of `world` (one process per GPU, no data-path collective).  Cells of
+ * other ranks are left untouched in device outputs and read back as zero in host outputs.
+ * Default rank 0 of 1. */
 int ccg_set_partition(ccg_ctx *ctx, int rank, int world);
 /* Restrict the run to the cells with row_lo <= i < row_hi and col_lo <= j < col_hi (sample slot
  * indices; row_lo and col_lo must be multiples of ccg_tile_rows() / ccg_tile_cols(); the window
@@ -88,8 +131,9 @@ int ccg_set_tile_window(ccg_ctx *ctx, int row_lo, int row_hi, int col_lo, int co
 
 /* Pure host helpers (no device needed) describing that deal: the lower
  * triangle is cut into macro tiles of ccg_tile_rows() x ccg_tile_cols()
- * samples, enumerated row-major over (tm, tn <= tm/2); the tile with index id
- * belongs to rank id % world.
+ * samples (tm, tn <= tm), ordered along a Z-order curve that is cut into
+ * `world` contiguous runs of equal estimated cost (tiles + the row blocks
+ * they read); rank r owns run r.
  * ccg_partition_cells: number of (r,c) cells of an n-sample matrix owned by
  * `rank`.  ccg_partition_tiles: writes up to `cap` owned tiles to tm[] / tn[]
  * and returns how many the rank owns. */
@@ -125,7 +169,10 @@ int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include, unsigned *
 /* Upload samples [first, first+count) in the reference's packed format from
  * HOST memory; seqs[k] / includes[k] are row pointers exactly as the
  * reference holds them (dist.c:143-154).  includes may be NULL in
- * shared-mask mode.  A NULL row pointer leaves that slot empty (excluded). */
+ * shared-mask mode.  A NULL row pointer leaves that slot empty (excluded).
+ * Source buffers of ALL host-pointer ccg_put_* calls: pageable rows are staged
+ * before the call returns; rows in pinned memory (ccg_host_alloc) are read
+ * asynchronously and must stay untouched until ccg_sync or a run call returns. */
 int ccg_put_samples_packed(ccg_ctx *ctx, int first, int count,
                            const uint64_t *const *seqs,
                            const uint32_t *const *includes);

@@ -250,3 +250,47 @@ def test_streamed_host_rows_match_resident_upload(built, monkeypatch, pair, cont
             assert dn == dno == n - 2 and ginc == ginco
             assert np.array_equal(_bits(D), _bits(Do))
         assert "slabs=" in c.last_kernel and int(c.last_kernel.split("slabs=")[1]) > 1
+
+
+# ---- the f32 accumulators of kind::mxf4 at their exactness bound ----
+# An S work item adds 3 per matching base: identical, fully known samples drive every accumulator element to
+# 3 x (bases of the K slice), the largest magnitude the path can produce.  The host keeps a slice at or below
+# CCG_FP4_MAX_PAIRS = 20,000 chunk pairs (5.12 Mbp): 3 * 256 * 20000 = 15,360,000 < 2^24.  The guard must hold
+# when the experiment knob CCG_KSLICES asks for fewer slices, and on the automatic path for longer genomes.
+@pytest.mark.parametrize("length,kslices_env,min_slices", [(5_120_000, "1", 1), (5_120_000 + 256, "1", 2), (12_000_000, None, 3)],
+                         ids=["5.12Mbp-one-slice-at-the-bound", "one-pair-over-forces-two-slices", "12Mbp-auto"])
+def test_mxf4_exact_at_the_accumulator_bound(built, length, kslices_env, min_slices):
+    import os
+    n = 40
+    rng = np.random.default_rng(length % 1009)
+    row = rng.integers(0, 4, size=length, dtype=np.uint8)
+    codes = np.broadcast_to(row, (n, length)).copy()
+    codes[1, ::7] = (codes[1, ::7] + 1) & 3            # one sample that differs in every 7th base
+    codes[2, 1000:2000] = 4                            # one with unknown bases
+    seqs, masks, inc = oracle.encode_samples(codes)
+    del codes
+    if kslices_env is not None:
+        os.environ["CCG_KSLICES"] = kslices_env
+    try:
+        c = api.Context()
+    finally:
+        os.environ.pop("CCG_KSLICES", None)
+    try:
+        c.set_kernel(api.KERNEL_UMMA)
+        c.set_problem(n, length, pair=True)
+        c.put_samples_packed(seqs, masks)
+        D, N, dn = c.run_pair(min_length=0, min_cov=0.0)
+        kern = c.last_kernel
+        assert "mxf4" in kern
+        ks = int(kern.split("kslices=")[1].split()[0])
+        slabs = int(kern.split("slabs=")[1].split()[0])
+        assert ks * slabs >= min_slices, kern
+        pairs_per_item = -(-(-(-length // 256)) // (ks * slabs))
+        assert pairs_per_item <= 20000, kern
+    finally:
+        c.close()
+    mo, no = oracle.raw_pair_matrix(seqs, masks, length)
+    assert dn == n
+    assert np.array_equal(N, no.astype(np.float64))
+    assert np.array_equal(D, mo.astype(np.float64))
+    assert (mo == 0).sum() >= (n - 2) * (n - 3) // 2 and no.max() == length

@@ -112,3 +112,60 @@ def test_ring_schedule_visits_every_shard_pair_once(world):
         assert parts[0][0] == 0 and sum(p[1] for p in parts) == 512, (key, parts)
         assert all(a[0] + a[1] == b[0] for a, b in zip(parts, parts[1:])), (key, parts)
     assert ring.shard_size(100000, 8) == 12544 and ring.shard_size(1000, 4) == 256
+
+
+# ---- K-split group: host arithmetic of the row ownership and of the alignment slices, on gloo ranks ----
+def _group_worker(rank, world, port, n, length, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ccphylo_b200 import api
+
+    lo, hi = api.group_rows(n, rank, world)
+    rows = torch.zeros(n, dtype=torch.int64)
+    rows[lo:hi] += 1
+    cells = torch.tensor([hi * (hi - 1) // 2 - lo * (lo - 1) // 2 if hi > lo else 0], dtype=torch.int64)
+    sl = api.group_slices(length, world)
+    bases = torch.zeros(length, dtype=torch.int64)
+    bases[sl[rank]:sl[rank + 1]] += 1
+    worst = torch.tensor([float(cells.item())])
+    dist.all_reduce(rows)
+    dist.all_reduce(cells)
+    dist.all_reduce(bases)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        out.put((rows.tolist(), int(cells.item()), bases.min().item(), bases.max().item(), float(worst.item()), sl))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,length", [(2, 1000, 5000), (2, 10000, 5_000_000), (3, 257, 77777)])
+def test_group_rows_and_slices_partition_the_job(built, world, n, length):
+    from ccphylo_b200 import api
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_group_worker, args=(r, world, port, n, length, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    rows, cells, bmin, bmax, worst, sl = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(v == 1 for v in rows)                       # every matrix row has exactly one owner
+    assert cells == api.cells(n)                           # the owners' packed spans tile the triangle
+    assert bmin == 1 and bmax == 1                         # every base of the alignment is in exactly one slice
+    assert all(b % 256 == 0 for b in sl[:-1]) and sl[-1] == length
+    assert worst <= api.cells(n) / world * 1.15 + 8 * n    # cut for equal cells (boundaries are multiples of 8 rows)
+
+
+def test_group_rows_edge_cases(built):
+    from ccphylo_b200 import api
+
+    for n in (0, 1, 2, 7, 8, 9, 255, 256, 10000, 100000):
+        for world in (1, 2, 5, 8, 16):
+            b = [api.group_rows(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(lo <= hi for lo, hi in b)
+    assert api.group_slices(5_000_000, 8)[1] == 624896 and api.group_slices(1000, 3) == [0, 256, 512, 1000]
