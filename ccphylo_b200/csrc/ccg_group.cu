@@ -29,6 +29,9 @@
 #include <math.h>
 #include <unistd.h>
 
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -128,6 +131,38 @@ k_finalize_group(const GroupFinalizeParams q, const EpilogueParams ep) {
 }
 
 } // namespace
+
+/* Members that share one process meet on the host before they launch the device barrier: everything a member
+ * allocates or frees for the run (cudaFree waits for the whole device) has then happened, so -- also when several
+ * members sit on ONE device, as in the single-GPU tests -- no member can block in the driver behind a peer's
+ * spinning barrier kernel that is waiting for it. */
+struct HostBarrier {
+	std::mutex m;
+	std::condition_variable cv;
+	int count = 0, waiting = 0;
+	unsigned gen = 0;
+	bool broken = false;
+};
+
+static int host_barrier_wait(HostBarrier *b) {
+	std::unique_lock<std::mutex> lk(b->m);
+	if(b->broken) return 1;
+	const unsigned g = b->gen;
+	if(++b->waiting >= b->count) {
+		b->waiting = 0;
+		++b->gen;
+		b->cv.notify_all();
+		return 0;
+	}
+	const bool ok = b->cv.wait_for(lk, std::chrono::seconds(120), [&] { return b->gen != g || b->broken; });
+	return (!ok || b->broken) ? 1 : 0;
+}
+
+static void host_barrier_break(HostBarrier *b) {
+	std::lock_guard<std::mutex> lk(b->m);
+	b->broken = true;
+	b->cv.notify_all();
+}
 
 /* ---- row ownership (pure host arithmetic) ----
  * Member r finalises the matrix rows (sample slots) [bounds[r], bounds[r+1]): contiguous, so its cells are ONE
@@ -319,6 +354,10 @@ int ccg_group_accumulators(ccg_ctx *ctx, int **C_S, int **C_I) {
 /* after the member's GEMM: barrier with the peers, then reduce + epilogue of the rows this member owns */
 int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const) {
 	const int world = ctx->grp_world, rank = ctx->grp_rank;
+	if(ctx->grp_host_barrier && host_barrier_wait((HostBarrier *) ctx->grp_host_barrier)) {
+		ccg_set_err(ctx, "another GPU of the group failed before the run reached the reduction");
+		return CCG_ERR_CUDA;
+	}
 	GroupBarrierParams b;
 	memset(&b, 0, sizeof(b));
 	for(int p = 0; p < world; ++p) b.hdr[p] = (GroupHeader *) ctx->grp_win[p];
@@ -387,15 +426,22 @@ struct ccg_multi {
 	int kernel_choice;
 	int force;                             /* CCG_MULTI_FORCE=1: split whatever the size (tests) */
 	char last_kernel[160];
+	HostBarrier *rendezvous;
 };
 
 template <class F>
 static int multi_parallel(ccg_multi *m, int count, F f) {
 	std::vector<int> rcs((size_t) count, CCG_OK);
 	std::vector<std::thread> th;
-	for(int g = 1; g < count; ++g) th.emplace_back([&, g]() { rcs[(size_t) g] = f(g); });
-	rcs[0] = f(0);
+	auto run = [&](int g) {
+		rcs[(size_t) g] = f(g);
+		if(rcs[(size_t) g]) host_barrier_break(m->rendezvous);       /* nobody waits for a member that gave up */
+	};
+	for(int g = 1; g < count; ++g) th.emplace_back([&, g]() { run(g); });
+	run(0);
 	for(auto &t : th) t.join();
+	m->rendezvous->broken = false;
+	m->rendezvous->waiting = 0;
 	for(int g = 0; g < count; ++g)
 		if(rcs[(size_t) g]) return rcs[(size_t) g] | (g << 8);
 	return CCG_OK;
@@ -422,10 +468,12 @@ extern "C" int ccg_init_multi_devices(ccg_ctx **out, int ngpus, const int *devic
 	if(!m) { ccg_destroy(lead); return CCG_ERR_NOMEM; }
 	m->n = ngpus;
 	m->active = 1;
+	m->rendezvous = new HostBarrier();
 	m->force = getenv("CCG_MULTI_FORCE") ? atoi(getenv("CCG_MULTI_FORCE")) : 0;
 	for(int g = 0; g < ngpus && !rc; ++g) rc = ccg_init(&m->member[g], devices[g]);
 	if(rc) {
 		for(int g = 0; g < ngpus; ++g) ccg_destroy(m->member[g]);
+		delete m->rendezvous;
 		free(m);
 		ccg_destroy(lead);
 		return rc;
@@ -460,6 +508,7 @@ void ccg_multi_destroy(ccg_ctx *lead) {
 	ccg_multi *m = lead->multi;
 	if(!m) return;
 	for(int g = 0; g < m->n; ++g) ccg_destroy(m->member[g]);
+	delete m->rendezvous;
 	free(m);
 	lead->multi = 0;
 }
@@ -468,7 +517,10 @@ void ccg_multi_destroy(ccg_ctx *lead) {
 static int multi_join(ccg_ctx *lead, int active, int samples) {
 	ccg_multi *m = lead->multi;
 	if(m->joined == active && m->joined_samples >= samples) return CCG_OK;
-	for(int g = 0; g < m->n; ++g) ccg_group_leave(m->member[g]);
+	for(int g = 0; g < m->n; ++g) {
+		ccg_group_leave(m->member[g]);
+		m->member[g]->grp_host_barrier = 0;
+	}
 	m->joined = 0;
 	if(active < 2) return CCG_OK;
 	std::vector<char> handles((size_t) active * CCG_GROUP_HANDLE_BYTES);
@@ -480,6 +532,9 @@ static int multi_join(ccg_ctx *lead, int active, int samples) {
 		int rc = ccg_group_join(m->member[g], g, active, handles.data());
 		if(rc) return multi_fail(lead, rc | (g << 8));
 	}
+	m->rendezvous->count = active;
+	m->rendezvous->waiting = 0;
+	for(int g = 0; g < active; ++g) m->member[g]->grp_host_barrier = m->rendezvous;
 	m->joined = active;
 	m->joined_samples = samples;
 	return CCG_OK;

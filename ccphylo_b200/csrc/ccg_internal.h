@@ -234,6 +234,7 @@ struct ccg_ctx {
 	long long grp_span[2];                 /* packed cells [lo, hi) the last run of this member wrote */
 	int grp_rows[2];                       /* sample slots [lo, hi) it finalised */
 	struct ccg_multi *multi;               /* leader of an in-process multi-GPU context (ccg_init_multi) */
+	void *grp_host_barrier;                /* members of one process: host rendezvous before the device barrier (ccg_group.cu) */
 
 	cudaEvent_t ev0, ev1;
 	int ev_valid;
