@@ -307,7 +307,7 @@ def main():
     ncell = api.cells(n)
     d_D = torch.zeros(ncell, dtype=torch.float64, device=dev)
     d_N = torch.zeros(ncell, dtype=torch.float64, device=dev)
-    row_lo, row_hi = api.group_rows(n, rank, world)
+    row_blk = api.group_row_block()                      # matrix rows are owned in blocks, dealt round-robin over the ranks
     total_basecmp = float(ncell) * length
 
     def step():
@@ -431,7 +431,7 @@ def main():
     sub_s = seqs_t[idx_t].cpu().numpy().view(np.uint64)
     sub_m = masks_t[idx_t].cpu().numpy().view(np.uint32)
     cell_idx, cell_row = packed_index(ids)
-    own = (cell_row >= row_lo) & (cell_row < row_hi)
+    own = (cell_row // row_blk) % world == rank
     cidx_t = torch.from_numpy(cell_idx).to(dev)
     own_t = torch.from_numpy(own).to(dev)
     gD = torch.where(own_t, d_D[cidx_t], torch.zeros((), dtype=torch.float64, device=dev))
@@ -505,14 +505,19 @@ def main():
             e_ms = float(tt.item())
         hD = np.ctypeslib.as_array(C.cast(hD_ptr, C.POINTER(C.c_double)), shape=(max(ncell, 1),))
         hN = np.ctypeslib.as_array(C.cast(hN_ptr, C.POINTER(C.c_double)), shape=(max(ncell, 1),))
-        # the host-path result must equal the device-path result on the span of cells this rank owns
-        _, _, c_lo, c_hi = ctx.group_last_span() if world > 1 else (0, n, 0, ncell)
-        same = bool(np.array_equal(hD[c_lo:c_hi], d_D[c_lo:c_hi].cpu().numpy()) and
-                    np.array_equal(hN[c_lo:c_hi], d_N[c_lo:c_hi].cpu().numpy()) and c_hi > c_lo)
+        # the host-path result must equal the device-path result on the cells of the row blocks this rank owns
+        same, owned = True, 0
+        dD, dN = d_D.cpu().numpy(), d_N.cpu().numpy()
+        for lo, hi in api.group_owned_blocks(n, rank, world):
+            c_lo, c_hi = lo * (lo - 1) // 2, hi * (hi - 1) // 2
+            same = same and bool(np.array_equal(hD[c_lo:c_hi], dD[c_lo:c_hi]) and np.array_equal(hN[c_lo:c_hi], dN[c_lo:c_hi]))
+            owned += c_hi - c_lo
+        del dD, dN
+        same = same and owned == api.group_cells(n, rank, world) and owned > 0
         if world > 1:
-            st = torch.tensor([1 if same else 0, c_hi - c_lo], device=dev, dtype=torch.int64)
+            st = torch.tensor([1 if same else 0, owned], device=dev, dtype=torch.int64)
             dist.all_reduce(st)
-            same = int(st[0].item()) == world and int(st[1].item()) == ncell      # the spans tile the triangle
+            same = int(st[0].item()) == world and int(st[1].item()) == ncell      # the owned blocks tile the triangle
         if not same:
             raise SystemExit("bench.py: host-path result differs from the device-path result")
         e2e = {"value": total_basecmp / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms,

@@ -30,7 +30,7 @@ EXPORTS = [
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
     "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs", "ccg_list_variants_row",
     "ccg_init_multi", "ccg_init_multi_devices", "ccg_multi_gpus", "ccg_group_export", "ccg_group_join", "ccg_group_leave",
-    "ccg_group_set_alignment", "ccg_group_rows", "ccg_group_last_span",
+    "ccg_group_set_alignment", "ccg_group_set_output", "ccg_group_row_block", "ccg_group_row_owner", "ccg_group_cells",
 ]
 GROUP_HANDLE_BYTES = 128
 
@@ -137,8 +137,11 @@ def load():
     L.ccg_group_join.argtypes = [vp, i, i, vp]
     L.ccg_group_leave.argtypes = [vp]
     L.ccg_group_set_alignment.argtypes = [vp, ll, u]
-    L.ccg_group_rows.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
-    L.ccg_group_last_span.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(ll), C.POINTER(ll)]
+    L.ccg_group_set_output.argtypes = [vp, i]
+    L.ccg_group_row_block.argtypes = []
+    L.ccg_group_row_owner.argtypes = [i, i]
+    L.ccg_group_cells.restype = ll
+    L.ccg_group_cells.argtypes = [i, i, i]
     L.ccg_measure_fp4_peak.restype = C.c_double
     L.ccg_measure_fp4_peak.argtypes = [vp, C.c_double, C.c_double, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     L.ccg_measure_i8_peak.restype = C.c_double
@@ -162,13 +165,20 @@ def partition_tiles(n, rank, world):
     return list(zip(ti[:k].tolist(), tj[:k].tolist()))
 
 
-def group_rows(n, rank, world):
-    """Sample slots [lo, hi) whose matrix rows member `rank` of a K-split group of `world` finalises (host only)."""
-    lo, hi = C.c_int(0), C.c_int(0)
-    rc = load().ccg_group_rows(n, rank, world, C.byref(lo), C.byref(hi))
-    if rc:
-        raise CcgError(rc, "ccg_group_rows")
-    return lo.value, hi.value
+def group_row_block():
+    """Matrix rows are owned in blocks of this many rows, dealt round-robin over the members of a K-split group."""
+    return load().ccg_group_row_block()
+
+
+def group_owned_blocks(n, rank, world):
+    """[(row_lo, row_hi)] of the row blocks of an n-sample matrix that member `rank` of `world` finalises (host only)."""
+    blk = group_row_block()
+    return [(b * blk, min(n, b * blk + blk)) for b in range(rank, (n + blk - 1) // blk, world)]
+
+
+def group_cells(n, rank, world):
+    """Packed cells of an n-sample triangle (all samples included) that member `rank` owns."""
+    return load().ccg_group_cells(n, rank, world)
 
 
 def group_slices(length, world):
@@ -234,14 +244,12 @@ class Context:
     def group_leave(self):
         self._ck(self._L.ccg_group_leave(self._h))
 
+    def group_set_output(self, compact):
+        self._ck(self._L.ccg_group_set_output(self._h, 1 if compact else 0))
+
     def group_set_alignment(self, total_len, global_inc=0):
         self._ck(self._L.ccg_group_set_alignment(self._h, total_len, global_inc))
 
-    def group_last_span(self):
-        """(row_lo, row_hi, cell_lo, cell_hi) of the last run of this group member."""
-        a, b, c, d = C.c_int(0), C.c_int(0), C.c_longlong(0), C.c_longlong(0)
-        self._ck(self._L.ccg_group_last_span(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return a.value, b.value, c.value, d.value
 
     def _ck(self, rc):
         if rc:

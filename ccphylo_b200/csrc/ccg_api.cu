@@ -164,6 +164,8 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	if(ctx->stream) cudaStreamSynchronize(ctx->stream);
 	ccg_group_release(ctx);
 	cudaFree(ctx->grp_own_win);
+	cudaFree(ctx->d_row_base);
+	free(ctx->h_row_base);
 	free_problem(ctx);
 	ccg_mat_free(ctx);
 	cudaFree(ctx->d_stage);
@@ -1091,9 +1093,61 @@ static int upload_macro_tiles(ccg_ctx *ctx, size_t *cnt_out) {
 	return rc;
 }
 
+/* The operand panel, sized once per problem geometry (cudaMemGetInfo / cudaMalloc are far too slow per run): the
+ * whole K axis in one buffer when it fits, else two slab buffers so that the expansion of slab s+1 runs under the
+ * GEMM of slab s. */
+static int ensure_panel(ccg_ctx *ctx, bool fp4) {
+	int rc;
+	if(ctx->d_X) return CCG_OK;
+	size_t free_b = 0, total_b = 0;
+	CK(ctx, cudaMemGetInfo(&free_b, &total_b));
+	/* default: up to 70 % of what is free (the planes, accumulators and outputs are already allocated) */
+	size_t budget = ctx->x_budget ? ctx->x_budget : free_b / 10 * 7;
+	if(budget > free_b - free_b / 8) budget = free_b - free_b / 8;
+	const size_t per_chunk = (size_t) ctx->n_pad * (fp4 ? 256 : 512);
+	long long fit = (long long) (budget / per_chunk);        /* chunks one buffer could hold */
+	int want_slabs = 1;
+	if(fit < ctx->chunks) {
+		fit = (long long) (budget / (2 * per_chunk));         /* two buffers */
+		if(fit < 1) {
+			set_err(ctx, "not enough device memory for the operand panel (%d slots)", ctx->n_pad);
+			return CCG_ERR_NOMEM;
+		}
+		want_slabs = (int) ((ctx->chunks + fit - 1) / fit);
+	}
+	/* measured (profiles/): running the expansion under the GEMM does not pay on one GPU (both
+	 * are limited by HBM traffic and issue slots: 13.2 ms overlapped vs 12.3 ms back to back at
+	 * 1000 x 5 Mbp), so the panel is cut only when it does not fit; then the two buffers keep
+	 * the tensor pipe busy while the next slab is produced */
+	fit = (ctx->chunks + want_slabs - 1) / want_slabs;              /* equal slabs */
+	if(fp4) fit = (fit + 1) & ~1LL;                                  /* whole chunk pairs */
+	const int nbuf = want_slabs > 1 ? 2 : 1;
+	ctx->x_buf_bytes = (size_t) fit * per_chunk;
+	size_t x_bytes = ctx->x_buf_bytes * nbuf;
+	if(cudaMalloc(&ctx->d_X, x_bytes) != cudaSuccess) {
+		ctx->d_X = 0;
+		set_err(ctx, "cudaMalloc of %zu bytes for the operand panel failed", x_bytes);
+		return CCG_ERR_NOMEM;
+	}
+	ctx->x_bytes = x_bytes;
+	ctx->x_chunks = (int) fit;
+	rc = make_x_tmap(ctx);
+	if(rc) return rc;
+	return CCG_OK;
+}
+
+static int run_umma_windows(ccg_ctx *ctx, const EpilogueParams &ep, int win_rows);
+
 static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	size_t cnt = 0;
-	int rc = upload_macro_tiles(ctx, &cnt);
+	int rc;
+	const bool group = ctx->grp_world > 1;
+	if(group) {
+		/* accumulators larger than the peer window: windows of macro-tile rows, one after the other */
+		const int win_rows = ccg_group_window_rows(ctx);
+		if(win_rows > 0 && win_rows < ctx->n_pad) return run_umma_windows(ctx, ep, win_rows);
+	}
+	rc = upload_macro_tiles(ctx, &cnt);
 	if(rc) return rc;
 	ctx->last_ntiles = (int) cnt;
 	ctx->last_kernel_kind = CCG_KERNEL_UMMA;
@@ -1102,10 +1156,10 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	/* dense int32 accumulators S and I: the context's own, or -- member of a K-split group -- the buffer of this
 	 * run inside the window the peers can read (ccg_group.cu) */
 	size_t c_bytes = (size_t) 2 * ctx->n_pad * ctx->n_pad * sizeof(int);
-	const bool group = ctx->grp_world > 1;
 	int *acc_S = 0, *acc_I = 0;
+	void *acc_clear = 0;
 	if(group) {
-		rc = ccg_group_accumulators(ctx, &acc_S, &acc_I);
+		rc = ccg_group_accumulators(ctx, 0, &acc_S, &acc_I, &acc_clear, &c_bytes);
 		if(rc) return rc;
 	} else {
 		if(ctx->c_bytes < c_bytes) {
@@ -1121,50 +1175,17 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		}
 		acc_S = ctx->d_C;
 		acc_I = ctx->d_C + (size_t) ctx->n_pad * ctx->n_pad;
+		acc_clear = ctx->d_C;
 	}
-	CK(ctx, cudaMemsetAsync(acc_S, 0, c_bytes, ctx->stream));
+	CK(ctx, cudaMemsetAsync(acc_clear, 0, c_bytes, ctx->stream));
 
 	/* e2m1 operands on kind::mxf4 (2.27x the kind::i8 pipe rate, exact for these sums) unless CCG_I8=1 */
 	const bool fp4 = !ctx->use_i8 && !ctx->dbg_umma1;
 	/* operand panel: the K axis is cut into slabs; two slab buffers so that the expansion of
 	 * slab s+1 (aux stream, HBM-write bound) runs under the GEMM of slab s (tensor bound).
 	 * Sized once per problem geometry (cudaMemGetInfo / cudaMalloc are far too slow per run). */
-	if(!ctx->d_X) {
-		size_t free_b = 0, total_b = 0;
-		CK(ctx, cudaMemGetInfo(&free_b, &total_b));
-		/* default: up to 70 % of what is free (the planes, accumulators and outputs are already allocated) */
-		size_t budget = ctx->x_budget ? ctx->x_budget : free_b / 10 * 7;
-		if(budget > free_b - free_b / 8) budget = free_b - free_b / 8;
-		const size_t per_chunk = (size_t) ctx->n_pad * (fp4 ? 256 : 512);
-		long long fit = (long long) (budget / per_chunk);        /* chunks one buffer could hold */
-		int want_slabs = 1;
-		if(fit < ctx->chunks) {
-			fit = (long long) (budget / (2 * per_chunk));         /* two buffers */
-			if(fit < 1) {
-				set_err(ctx, "not enough device memory for the operand panel (%d slots)", ctx->n_pad);
-				return CCG_ERR_NOMEM;
-			}
-			want_slabs = (int) ((ctx->chunks + fit - 1) / fit);
-		}
-		/* measured (profiles/): running the expansion under the GEMM does not pay on one GPU (both
-		 * are limited by HBM traffic and issue slots: 13.2 ms overlapped vs 12.3 ms back to back at
-		 * 1000 x 5 Mbp), so the panel is cut only when it does not fit; then the two buffers keep
-		 * the tensor pipe busy while the next slab is produced */
-		fit = (ctx->chunks + want_slabs - 1) / want_slabs;              /* equal slabs */
-		if(fp4) fit = (fit + 1) & ~1LL;                                  /* whole chunk pairs */
-		const int nbuf = want_slabs > 1 ? 2 : 1;
-		ctx->x_buf_bytes = (size_t) fit * per_chunk;
-		size_t x_bytes = ctx->x_buf_bytes * nbuf;
-		if(cudaMalloc(&ctx->d_X, x_bytes) != cudaSuccess) {
-			ctx->d_X = 0;
-			set_err(ctx, "cudaMalloc of %zu bytes for the operand panel failed", x_bytes);
-			return CCG_ERR_NOMEM;
-		}
-		ctx->x_bytes = x_bytes;
-		ctx->x_chunks = (int) fit;
-		rc = make_x_tmap(ctx);
-		if(rc) return rc;
-	}
+	rc = ensure_panel(ctx, fp4);
+	if(rc) return rc;
 	long long slab = ctx->x_chunks;
 	/* a rank of a partitioned run spends a larger share of its step expanding (it reads O(n / sqrt(world)) rows
 	 * for 1 / world of the tiles): cut the K axis so that the expansion of slab s+1 runs under the GEMM of slab s.
@@ -1181,8 +1202,9 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		 * slab's upload is the only one not hidden behind a GEMM) */
 		const int feed_slabs = ctx->dbg_feed_slabs > 0 ? ctx->dbg_feed_slabs : 16;
 		long long want = (ctx->chunks + feed_slabs - 1) / feed_slabs;
-		if(want < ctx->stream_min_chunks / 2) want = ctx->stream_min_chunks / 2;
-		if(want < 16) want = 16;
+		/* the GEMM of the LAST slab is the tail nothing hides: a short alignment (a member's slice of a K-split group)
+		 * is cut finer -- down to 512 chunks, where a slab's GEMM is still ~1 ms of full waves */
+		if(want < 512) want = 512;
 		const long long cap = ctx->x_bytes >= 2 * ctx->x_buf_bytes ? ctx->x_chunks : ctx->x_chunks / 2;
 		if(want < slab && cap >= 1) slab = want < cap ? want : cap;
 		if(fp4 && (slab & 1)) slab = slab > 1 ? slab - 1 : 2;
@@ -1288,13 +1310,95 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 	p.tiles = ctx->d_tiles;
 	if(group) {
 		/* barrier with the peers, then the reduce-scatter over NVLink fused with the epilogue of this member's rows */
-		rc = ccg_group_finalize(ctx, ep, i_const);
+		rc = ccg_group_finalize(ctx, ep, i_const, 0, ctx->n_pad);
 		if(rc) return rc;
 	} else CK(ctx, ccg_launch_finalize_umma(ctx, p, ep, i_const));
 	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
 	ctx->ev_valid = 1;
 	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_umma%s tiles=%d kslices=%d slabs=%d%s",
 	         ctx->dbg_umma1 ? "" : (fp4 ? "2<mxf4>" : "2<i8>"), p.ntiles, p.kslices, nslabs, group ? " +k_finalize_group" : "");
+	return CCG_OK;
+}
+
+/* K-split group whose n x n accumulators exceed the peer window (BASELINE configs[3]: 100,000 samples): the member's
+ * whole slice of every sample is expanded once, then the lower triangle is run in windows of whole macro-tile rows;
+ * each window is accumulated into one of the two window buffers, reduced over the members and finalised
+ * (ccg_group_finalize) while the next window's GEMM is already queued behind it.  The sequence shards never move. */
+static int run_umma_windows(ccg_ctx *ctx, const EpilogueParams &ep, int win_rows) {
+	if(ctx->use_i8 || ctx->dbg_umma1 || ctx->feed_seqs) {
+		set_err(ctx, "a windowed K-split run uses the e2m1 panel kernel on samples already on the device");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	const int nwin = (ctx->n_pad + win_rows - 1) / win_rows;
+	const int tiles_per_win = win_rows / CCG_UMMA_BM;
+	std::vector<int2> tiles;
+	for_each_ctx_tile(ctx, [&](int tm, int tn) {
+		int2 t;
+		t.x = tm;
+		t.y = tn;
+		tiles.push_back(t);
+	});
+	ctx->last_ntiles = (int) tiles.size();
+	ctx->last_kernel_kind = CCG_KERNEL_UMMA;
+	if(tiles.empty()) return CCG_OK;
+	/* window by window, Z-order inside a window (neighbouring CTA pairs share operand rows in L2) */
+	std::stable_sort(tiles.begin(), tiles.end(), [&](const int2 &a, const int2 &b) { return a.x / tiles_per_win < b.x / tiles_per_win; });
+	std::vector<size_t> start((size_t) nwin + 1, tiles.size());
+	for(size_t k = tiles.size(); k-- > 0;) start[(size_t) (tiles[k].x / tiles_per_win)] = k;
+	for(int w = nwin - 1; w >= 0; --w)
+		if(start[(size_t) w] > start[(size_t) w + 1]) start[(size_t) w] = start[(size_t) w + 1];
+	int rc = ensure_tiles(ctx, tiles.data(), tiles.size());
+	if(rc) return rc;
+	rc = ensure_panel(ctx, true);
+	if(rc) return rc;
+	if(ctx->x_chunks < ctx->chunks) {
+		set_err(ctx, "windowed K-split run: the operand panel of this GPU's slice (%d slots x %d chunks) must fit the device in one "
+		        "piece; use more GPUs", ctx->n_pad, ctx->chunks);
+		return CCG_ERR_NOMEM;
+	}
+	const int nu = (ctx->chunks + 1) / 2;                       /* chunk pairs */
+	const int i_const = nu * 2 * CCG_CHUNK_BASES;
+	ctx->last_i_const = i_const;
+	CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev_phase[0], ctx->stream));
+	CK(ctx, ccg_launch_expand_fp4(ctx, ctx->stream, ctx->d_X, 0, nu, 0));
+	CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->stream));
+	CK(ctx, cudaEventRecord(ctx->ev_phase[2], ctx->stream));
+	UmmaParams p;
+	memset(&p, 0, sizeof(p));
+	p.ldc = ctx->n_pad;
+	p.fp4 = 1;
+	p.no_mask_items = ctx->pair_mode ? 0 : 1;
+	p.slab_chunks = nu;
+	p.row_base = 0;
+	int kslices_seen = 0;
+	for(int w = 0; w < nwin; ++w) {
+		const int row0 = w * win_rows, row1 = row0 + win_rows < ctx->n_pad ? row0 + win_rows : ctx->n_pad;
+		const size_t ntl = start[(size_t) w + 1] - start[(size_t) w];
+		if(ntl == 0) continue;                                  /* rows past the last sample: the same on every member */
+		void *clear = 0;
+		size_t bytes = 0;
+		rc = ccg_group_accumulators(ctx, row0, &p.C_S, &p.C_I, &clear, &bytes);
+		if(rc) return rc;
+		CK(ctx, cudaMemsetAsync(clear, 0, bytes, ctx->stream));
+		p.tiles = ctx->d_tiles + start[(size_t) w];
+		p.ntiles = (int) ntl;
+		p.kslices = choose_split((long long) ccg_umma_pair_slots(ctx), (long long) ntl, nu, 8, 512, 1);
+		if(ctx->dbg_kslices > 0) p.kslices = ctx->dbg_kslices;
+		if((nu + p.kslices - 1) / p.kslices > CCG_FP4_MAX_PAIRS) p.kslices = (nu + CCG_FP4_MAX_PAIRS - 1) / CCG_FP4_MAX_PAIRS;
+		p.chunks_per_slice = (nu + p.kslices - 1) / p.kslices;
+		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nu) --p.kslices;
+		if(p.kslices > kslices_seen) kslices_seen = p.kslices;
+		CK(ctx, ccg_launch_umma(ctx, p));
+		rc = ccg_group_finalize(ctx, ep, i_const, row0, row1);
+		if(rc) return rc;
+	}
+	CK(ctx, cudaEventRecord(ctx->ev_phase[3], ctx->stream));
+	ctx->phase_valid = 1;
+	CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+	ctx->ev_valid = 1;
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_pairdist_umma2<mxf4> tiles=%d kslices=%d slabs=1 windows=%d +k_finalize_group",
+	         (int) tiles.size(), kslices_seen, nwin);
 	return CCG_OK;
 }
 
@@ -1350,6 +1454,16 @@ static int run_fused(ccg_ctx *ctx, const EpilogueParams &ep) {
 	return CCG_OK;
 }
 
+/* compaction map: included samples in input order (fsacmpthrd.c:305-329) */
+static int compute_ranks(ccg_ctx *ctx, const unsigned char *include) {
+	int Dn = 0;
+	for(int i = 0; i < ctx->n_pad; ++i) {
+		int inc = i < ctx->n && ctx->present[i] && (!include || include[i]);
+		ctx->h_rank[i] = inc ? Dn++ : -1;
+	}
+	return Dn;
+}
+
 static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
                       double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn_out) {
 	if(!ctx || !ctx->d_planes) return CCG_ERR_ARG;
@@ -1375,12 +1489,7 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 		ctx->global_pending = 0;
 	}
 
-	/* compaction map: included samples in input order (fsacmpthrd.c:305-329) */
-	int Dn = 0;
-	for(int i = 0; i < ctx->n_pad; ++i) {
-		int inc = i < ctx->n && ctx->present[i] && (!include || include[i]);
-		ctx->h_rank[i] = inc ? Dn++ : -1;
-	}
+	const int Dn = compute_ranks(ctx, include);
 	ctx->last_Dn = Dn;
 	if(Dn_out) *Dn_out = Dn;
 	ctx->last_ntiles = 0;
@@ -1405,6 +1514,7 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	ep.D = d_D;
 	ep.N = mode == 0 ? d_N : 0;
 	ep.rank = ctx->d_rank;
+	ep.row_base = ctx->ep_row_base;
 	if(ctx->row_slot1) ep.row_plus1 = ctx->h_rank[ctx->row_slot1 - 1] + 1;
 	if(mode == 0) {
 		/* fsacmpthrd.c:292: minLength = minLength < minCov * len ? minCov * len : minLength */
@@ -1445,10 +1555,107 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	return kind == CCG_KERNEL_UMMA ? run_umma(ctx, ep) : run_popc(ctx, ep);
 }
 
+/* Host matrices of a K-split member: the member owns the row blocks b with b % world == rank, its device result
+ * buffers hold just those rows back to back (row_base[r] = offset of compact row r), and every owned block is one
+ * contiguous run of cells of the packed host matrix -- one copy per block and matrix.  The members of a group write
+ * disjoint cells of the same host matrices. */
+/* K-split member: row_base[r] = offset of compact row r in a buffer that holds just the rows this member owns,
+ * back to back (h_row_base on the host, d_row_base for the epilogue).  Needs the rank map of this include[]. */
+static int group_row_bases(ccg_ctx *ctx, const unsigned char *include, long long *owned_cells) {
+	const int world = ctx->grp_world, rank = ctx->grp_rank;
+	if(ctx->row_base_cap < (size_t) ctx->n_pad) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_row_base); ctx->d_row_base = 0;
+		free(ctx->h_row_base); ctx->h_row_base = 0;
+		ctx->row_base_cap = 0;
+		ctx->h_row_base = (long long *) malloc((size_t) ctx->n_pad * sizeof(long long));
+		if(!ctx->h_row_base) return CCG_ERR_NOMEM;
+		CK(ctx, cudaMalloc(&ctx->d_row_base, (size_t) ctx->n_pad * sizeof(long long)));
+		ctx->row_base_cap = (size_t) ctx->n_pad;
+	}
+	const int Dn = compute_ranks(ctx, include);
+	long long off = 0;
+	for(int i = 0; i < ctx->n; ++i) {
+		const int r = ctx->h_rank[i];
+		if(r < 0) continue;
+		if((i / CCG_GROUP_ROW_BLOCK) % world == rank) { ctx->h_row_base[r] = off; off += r; }
+		else ctx->h_row_base[r] = -1;
+	}
+	if(Dn > 0)
+		CK(ctx, cudaMemcpyAsync(ctx->d_row_base, ctx->h_row_base, (size_t) Dn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+	if(owned_cells) *owned_cells = off;
+	return CCG_OK;
+}
+
+/* Host matrices of a K-split member: the member owns the row blocks b with b % world == rank, its device result
+ * buffers hold just those rows back to back, and every owned block is one contiguous run of cells of the packed
+ * host matrix -- one copy per block and matrix; the members of a group write disjoint cells of the same host
+ * matrices.  With ccg_group_set_output(compact) the host buffers hold only the owned rows as well: one copy. */
+static int run_to_host_group(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
+                             double minCov, int elem_size, double byteScale, void *D, void *N, int *Dn_out) {
+	const int world = ctx->grp_world, rank = ctx->grp_rank;
+	const long long own_max = ccg_group_cells(ctx->n, rank, world);
+	const size_t bytes = (size_t) (own_max > 0 ? own_max : 1) * 8;
+	if(ctx->out_bytes < bytes || !ctx->d_out_D) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_out_D); ctx->d_out_D = 0;
+		cudaFree(ctx->d_out_N); ctx->d_out_N = 0;
+		ctx->out_bytes = 0;
+		if(cudaMalloc(&ctx->d_out_D, bytes) != cudaSuccess || cudaMalloc(&ctx->d_out_N, bytes) != cudaSuccess) {
+			set_err(ctx, "cudaMalloc of 2 x %zu result bytes failed", bytes);
+			return CCG_ERR_NOMEM;
+		}
+		ctx->out_bytes = bytes;
+	}
+	long long owned = 0;
+	int rc = group_row_bases(ctx, include, &owned);
+	if(rc) return rc;
+	ctx->ep_row_base = ctx->d_row_base;
+	int Dn = 0;
+	rc = run_common(ctx, mode, include, norm, minLength, minCov, elem_size, byteScale, ctx->d_out_D, N ? ctx->d_out_N : 0, &Dn);
+	ctx->ep_row_base = 0;
+	if(rc) return rc;
+	if(Dn_out) *Dn_out = Dn;
+	if(Dn > 1 && ctx->grp_compact && owned > 0) {
+		CK(ctx, cudaMemcpyAsync(D, ctx->d_out_D, (size_t) owned * elem_size, cudaMemcpyDeviceToHost, ctx->stream));
+		if(N) CK(ctx, cudaMemcpyAsync(N, ctx->d_out_N, (size_t) owned * elem_size, cudaMemcpyDeviceToHost, ctx->stream));
+	} else if(Dn > 1) {
+		for(int b = rank; (long long) b * CCG_GROUP_ROW_BLOCK < ctx->n; b += world) {
+			const int i0 = b * CCG_GROUP_ROW_BLOCK, i1 = i0 + CCG_GROUP_ROW_BLOCK < ctx->n ? i0 + CCG_GROUP_ROW_BLOCK : ctx->n;
+			long long r0 = -1, r1 = -1;                           /* compact rows of the block: consecutive */
+			for(int i = i0; i < i1; ++i)
+				if(ctx->h_rank[i] >= 0) { if(r0 < 0) r0 = ctx->h_rank[i]; r1 = ctx->h_rank[i] + 1; }
+			if(r0 < 0) continue;
+			const size_t lo = (size_t) (r0 * (r0 - 1) / 2) * elem_size, len = (size_t) (r1 * (r1 - 1) / 2 - r0 * (r0 - 1) / 2) * elem_size;
+			const size_t src = (size_t) ctx->h_row_base[r0] * elem_size;
+			if(!len) continue;
+			CK(ctx, cudaMemcpyAsync((char *) D + lo, (char *) ctx->d_out_D + src, len, cudaMemcpyDeviceToHost, ctx->stream));
+			if(N) CK(ctx, cudaMemcpyAsync((char *) N + lo, (char *) ctx->d_out_N + src, len, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+	}
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return CCG_OK;
+}
+
+/* device-resident run of a K-split member with compact outputs (ccg_group_set_output) */
+static int run_dev_group_compact(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
+                                 double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn) {
+	if(!ctx->d_planes) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	int rc = group_row_bases(ctx, include, 0);
+	if(rc) return rc;
+	ctx->ep_row_base = ctx->d_row_base;
+	rc = run_common(ctx, mode, include, norm, minLength, minCov, elem_size, byteScale, d_D, d_N, Dn);
+	ctx->ep_row_base = 0;
+	return rc;
+}
+
 static int run_to_host(ccg_ctx *ctx, int mode, const unsigned char *include, unsigned norm, unsigned minLength,
                        double minCov, int elem_size, double byteScale, void *D, void *N, int *Dn_out) {
 	if(!ctx || !D) return CCG_ERR_ARG;
+	if(!ctx->d_planes || (elem_size != 8 && elem_size != 4 && elem_size != 2 && elem_size != 1)) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
+	if(ctx->grp_world > 1) return run_to_host_group(ctx, mode, include, norm, minLength, minCov, elem_size, byteScale, D, N, Dn_out);
 	/* worst case Dn = n */
 	size_t max_cells = ctx->n > 1 ? (size_t) ctx->n * (ctx->n - 1) / 2 : 0;
 	size_t bytes = max_cells * 8;
@@ -1475,15 +1682,7 @@ static int run_to_host(ccg_ctx *ctx, int mode, const unsigned char *include, uns
 	                    N ? ctx->d_out_N : 0, &Dn);
 	if(rc) return rc;
 	if(Dn_out) *Dn_out = Dn;
-	if(Dn > 1 && ctx->grp_world > 1) {
-		/* a member of a K-split group owns a contiguous run of matrix rows = one span of the packed triangle; the
-		 * members write disjoint spans of the same host matrices */
-		const size_t lo = (size_t) ctx->grp_span[0] * elem_size, bytes_own = (size_t) (ctx->grp_span[1] - ctx->grp_span[0]) * elem_size;
-		if(bytes_own) {
-			CK(ctx, cudaMemcpyAsync((char *) D + lo, (char *) ctx->d_out_D + lo, bytes_own, cudaMemcpyDeviceToHost, ctx->stream));
-			if(N) CK(ctx, cudaMemcpyAsync((char *) N + lo, (char *) ctx->d_out_N + lo, bytes_own, cudaMemcpyDeviceToHost, ctx->stream));
-		}
-	} else if(Dn > 1) {
+	if(Dn > 1) {
 		size_t cells = (size_t) Dn * (Dn - 1) / 2;
 		CK(ctx, cudaMemcpyAsync(D, ctx->d_out_D, cells * elem_size, cudaMemcpyDeviceToHost, ctx->stream));
 		if(N) CK(ctx, cudaMemcpyAsync(N, ctx->d_out_N, cells * elem_size, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1509,6 +1708,8 @@ extern "C" int ccg_run_pair_dev(ccg_ctx *ctx, const unsigned char *include, unsi
                                 double minCov, int elem_size, double byteScale, void *d_D, void *d_N, int *Dn) {
 	if(!d_D) return CCG_ERR_ARG;
 	CCG_MULTI_SOLO(ctx, "a run into device buffers", ccg_run_pair_dev(m0, include, norm, minLength, minCov, elem_size, byteScale, d_D, d_N, Dn));
+	if(ctx && ctx->grp_world > 1 && ctx->grp_compact)
+		return run_dev_group_compact(ctx, 0, include, norm, minLength, minCov, elem_size, byteScale, d_D, d_N, Dn);
 	return run_common(ctx, 0, include, norm, minLength, minCov, elem_size, byteScale, d_D, d_N, Dn);
 }
 
@@ -1517,6 +1718,8 @@ extern "C" int ccg_run_global_dev(ccg_ctx *ctx, const unsigned char *include, un
 	if(!d_D) return CCG_ERR_ARG;
 	CCG_MULTI_SOLO(ctx, "a run into device buffers", ccg_run_global_dev(m0, include, norm, elem_size, byteScale, d_D, Dn, global_inc));
 	if(ctx && global_inc) *global_inc = ctx->grp_world > 1 ? ctx->grp_global_inc : ctx->global_inc;
+	if(ctx && ctx->grp_world > 1 && ctx->grp_compact)
+		return run_dev_group_compact(ctx, 1, include, norm, 0, 0.0, elem_size, byteScale, d_D, 0, Dn);
 	return run_common(ctx, 1, include, norm, 0, 0.0, elem_size, byteScale, d_D, 0, Dn);
 }
 
@@ -1827,7 +2030,8 @@ extern "C" int ccg_fsa_cmp_thread_out(ccg_ctx *ctx, int pair, void *D, void *N, 
 		if(kind == CCG_KERNEL_AUTO) kind = (ninc >= 192 && ctx->chunks >= 64) ? CCG_KERNEL_UMMA : CCG_KERNEL_POPC;
 		if(ctx->grp_world > 1) kind = CCG_KERNEL_UMMA;
 		if(kind == CCG_KERNEL_UMMA && !ctx->proxi && ctx->stream_min_chunks > 0 && ctx->chunks >= ctx->stream_min_chunks &&
-		   3.0 * ((double) len + 256.0) < 2147483648.0) {
+		   3.0 * ((double) len + 256.0) < 2147483648.0 &&
+		   !(ctx->grp_world > 1 && ccg_group_window_rows(ctx) < ctx->n_pad)) {      /* windowed group runs expand the whole slice first */
 			for(int i = 0; i < n; ++i) {
 				if(!srow[i]) continue;
 				ctx->present[i] = 1;

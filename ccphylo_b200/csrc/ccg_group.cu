@@ -94,9 +94,11 @@ __global__ void k_group_barrier(GroupBarrierParams q) {
 
 __device__ __forceinline__ int4 ld_cg_int4(const int *p) { return __ldcg(reinterpret_cast<const int4 *>(p)); }
 
-/* Reduce-scatter fused with the epilogue: the owner of rows [row_lo, row_hi) adds the members' partial sums of
- * those rows -- 128-bit loads, its own from HBM, the peers' over NVLink (L1 bypassed: the data belongs to another
- * GPU's L2) -- and applies mismatch = (3I - S) / 4 and the reference epilogue (fsacmpthrd.c:419-475 / :247-255). */
+/* Reduce-scatter fused with the epilogue: matrix rows are owned in blocks of CCG_GROUP_ROW_BLOCK rows dealt
+ * round-robin (row block b belongs to member b % world).  The owner adds the members' partial sums of its rows --
+ * 128-bit loads, its own from HBM, the peers' over NVLink (L1 bypassed: the data belongs to another GPU's L2) --
+ * and applies mismatch = (3I - S) / 4 and the reference epilogue (fsacmpthrd.c:419-475 / :247-255).
+ * q.C[p] are biased pointers: element (i, j) of the matrix is at C[p][i * ldc + j] for the rows of this window. */
 __global__ void __launch_bounds__(256)
 k_finalize_group(const GroupFinalizeParams q, const EpilogueParams ep) {
 	int i_const = 0;
@@ -104,7 +106,8 @@ k_finalize_group(const GroupFinalizeParams q, const EpilogueParams ep) {
 		for(int p = 0; p < q.world; ++p) i_const += q.own->iconst_from[q.buf][p];
 	for(int i = q.row_lo + (int) blockIdx.x; i < q.row_hi; i += (int) gridDim.x) {
 		if(i >= q.n) break;
-		const size_t off = (size_t) i * q.ldc;
+		if((i / CCG_GROUP_ROW_BLOCK) % q.world != q.rank) continue;
+		const long long off = (long long) i * q.ldc;
 		for(int j4 = 4 * (int) threadIdx.x; j4 < i; j4 += 4 * (int) blockDim.x) {
 			int4 S = make_int4(0, 0, 0, 0), I = make_int4(0, 0, 0, 0);
 #pragma unroll 4
@@ -165,30 +168,27 @@ static void host_barrier_break(HostBarrier *b) {
 }
 
 /* ---- row ownership (pure host arithmetic) ----
- * Member r finalises the matrix rows (sample slots) [bounds[r], bounds[r+1]): contiguous, so its cells are ONE
- * contiguous span of the packed triangle (one device-to-host copy per matrix), cut so that every member gets
- * about the same number of cells; boundaries are multiples of 8 rows. */
-static void group_row_bounds(int n, int world, int *bounds) {
-	const double total = n > 1 ? (double) n * (n - 1) / 2.0 : 0.0;
-	bounds[0] = 0;
-	for(int r = 1; r < world; ++r) {
-		const double target = total * r / world;
-		long long b = (long long) ceil((1.0 + sqrt(1.0 + 8.0 * target)) / 2.0);
-		b = (b + 7) / 8 * 8;
-		if(b < bounds[r - 1]) b = bounds[r - 1];
-		if(b > n) b = n;
-		bounds[r] = (int) b;
-	}
-	bounds[world] = n;
+ * Matrix rows (sample slots) are owned in blocks of CCG_GROUP_ROW_BLOCK = 64 rows dealt round-robin: row i belongs
+ * to member (i / 64) % world.  Every window of rows is thereby spread over all members (the NVLink reads of the
+ * reduction run on every link at once) and a member's share of the cells is within a block row of 1 / world. */
+extern "C" int ccg_group_row_block(void) { return CCG_GROUP_ROW_BLOCK; }
+
+extern "C" int ccg_group_row_owner(int row, int world) {
+	if(row < 0 || world < 1) return -1;
+	return (row / CCG_GROUP_ROW_BLOCK) % world;
 }
 
-extern "C" int ccg_group_rows(int n, int rank, int world, int *row_lo, int *row_hi) {
-	if(n < 0 || world < 1 || world > CCG_GROUP_MAX || rank < 0 || rank >= world) return CCG_ERR_ARG;
-	int bounds[CCG_GROUP_MAX + 1];
-	group_row_bounds(n, world, bounds);
-	if(row_lo) *row_lo = bounds[rank];
-	if(row_hi) *row_hi = bounds[rank + 1];
-	return CCG_OK;
+/* cells of the packed triangle over n samples (all included) that member `rank` owns */
+extern "C" long long ccg_group_cells(int n, int rank, int world) {
+	if(n < 0 || world < 1 || rank < 0 || rank >= world) return -1;
+	long long cells = 0;
+	for(int b = rank; (long long) b * CCG_GROUP_ROW_BLOCK < n; b += world) {
+		const long long lo = (long long) b * CCG_GROUP_ROW_BLOCK;
+		long long hi = lo + CCG_GROUP_ROW_BLOCK;
+		if(hi > n) hi = n;
+		cells += hi * (hi - 1) / 2 - lo * (lo - 1) / 2;
+	}
+	return cells;
 }
 
 /* ---- membership ---- */
@@ -217,7 +217,15 @@ extern "C" int ccg_group_export(ccg_ctx *ctx, int max_samples, void *handle) {
 	CKG(ctx, cudaSetDevice(ctx->device));
 	ccg_group_release(ctx);
 	const int npad = (max_samples + CCG_SLOT_PAD - 1) / CCG_SLOT_PAD * CCG_SLOT_PAD;
-	const size_t bytes = CCG_GROUP_HDR_BYTES + (size_t) 2 * 2 * npad * npad * sizeof(int);
+	/* two accumulator buffers of two int32 planes.  Up to 8 GiB they hold the whole n_pad x n_pad matrix; a larger
+	 * problem is run in windows of whole macro-tile rows that fit (CCG_GROUP_WINDOW_BYTES: test hook) */
+	size_t budget = (size_t) 8 << 30;
+	if(getenv("CCG_GROUP_WINDOW_BYTES")) budget = (size_t) atoll(getenv("CCG_GROUP_WINDOW_BYTES"));
+	const size_t one_tile_row = (size_t) 2 * 2 * CCG_UMMA_BM * npad * sizeof(int);
+	size_t acc = (size_t) 2 * 2 * npad * npad * sizeof(int);
+	if(acc > budget) acc = budget / one_tile_row * one_tile_row;
+	if(acc < one_tile_row) acc = one_tile_row;
+	const size_t bytes = CCG_GROUP_HDR_BYTES + acc;
 	if(!ctx->grp_own_win || ctx->grp_win_bytes < bytes) {
 		cudaFree(ctx->grp_own_win);
 		ctx->grp_own_win = 0;
@@ -270,6 +278,7 @@ extern "C" int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *han
 	}
 	const int me = (int) getpid();
 	int npad_min = ctx->grp_npad_max;
+	size_t bytes_min = ctx->grp_win_bytes;
 	for(int p = 0; p < world; ++p) {
 		GroupHandle h;
 		memcpy(&h, (const char *) handles + (size_t) p * CCG_GROUP_HANDLE_BYTES, sizeof(h));
@@ -278,6 +287,7 @@ extern "C" int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *han
 			return CCG_ERR_ARG;
 		}
 		if(h.npad_max < npad_min) npad_min = h.npad_max;
+		if(h.bytes < bytes_min) bytes_min = (size_t) h.bytes;
 		if(p == rank) {
 			if(h.pid != me || (void *) (uintptr_t) h.ptr != ctx->grp_own_win) {
 				ccg_set_err(ctx, "handle %d is not this context's own export", p);
@@ -314,6 +324,7 @@ extern "C" int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *han
 		}
 	}
 	ctx->grp_npad_max = npad_min < ctx->grp_npad_max ? npad_min : ctx->grp_npad_max;
+	ctx->grp_acc_bytes = bytes_min - CCG_GROUP_HDR_BYTES;      /* every member lays its buffers out the same way */
 	ctx->grp_rank = rank;
 	ctx->grp_world = world;
 	ctx->grp_total_len = 0;
@@ -328,31 +339,42 @@ extern "C" int ccg_group_set_alignment(ccg_ctx *ctx, long long total_len, unsign
 	return CCG_OK;
 }
 
-extern "C" int ccg_group_last_span(const ccg_ctx *ctx, int *row_lo, int *row_hi, long long *cell_lo, long long *cell_hi) {
+extern "C" int ccg_group_set_output(ccg_ctx *ctx, int compact) {
 	if(!ctx) return CCG_ERR_ARG;
-	if(row_lo) *row_lo = ctx->grp_rows[0];
-	if(row_hi) *row_hi = ctx->grp_rows[1];
-	if(cell_lo) *cell_lo = ctx->grp_span[0];
-	if(cell_hi) *cell_hi = ctx->grp_span[1];
+	ctx->grp_compact = compact ? 1 : 0;
 	return CCG_OK;
 }
 
-/* the accumulator buffer of this run inside the member's own window */
-int ccg_group_accumulators(ccg_ctx *ctx, int **C_S, int **C_I) {
-	if(ctx->n_pad > ctx->grp_npad_max) {
-		ccg_set_err(ctx, "the group window was exported for %d sample slots, the problem has %d", ctx->grp_npad_max, ctx->n_pad);
+/* rows (a multiple of the macro-tile height) one accumulator buffer holds for the current problem */
+int ccg_group_window_rows(ccg_ctx *ctx) {
+	if(ctx->n_pad > ctx->grp_npad_max) return 0;
+	const size_t per_row = (size_t) 2 * 2 * ctx->n_pad * sizeof(int);          /* 2 buffers x 2 planes */
+	long long rows = (long long) (ctx->grp_acc_bytes / per_row) / CCG_UMMA_BM * CCG_UMMA_BM;
+	if(rows > ctx->n_pad) rows = ctx->n_pad;
+	return (int) rows;
+}
+
+/* The accumulator buffer of this run / window inside the member's own window, biased so that the kernels address
+ * matrix row i as C[i * n_pad + j] for the rows [row0, row0 + window rows); *bytes = what to clear at *clear. */
+int ccg_group_accumulators(ccg_ctx *ctx, int row0, int **C_S, int **C_I, void **clear, size_t *bytes) {
+	const int rows = ccg_group_window_rows(ctx);
+	if(rows < CCG_UMMA_BM) {
+		ccg_set_err(ctx, "the group window (%zu accumulator bytes, exported for %d sample slots) cannot hold one macro-tile row of "
+		            "%d slots", ctx->grp_acc_bytes, ctx->grp_npad_max, ctx->n_pad);
 		return CCG_ERR_ARG;
 	}
-	const size_t plane = (size_t) ctx->n_pad * ctx->n_pad;
-	const size_t buf_ints = (size_t) 2 * ctx->grp_npad_max * ctx->grp_npad_max;
-	int *base = (int *) ((char *) ctx->grp_own_win + CCG_GROUP_HDR_BYTES) + (size_t) ctx->grp_buf * buf_ints;
-	*C_S = base;
-	*C_I = base + plane;
+	const size_t plane = (size_t) rows * ctx->n_pad;
+	int *base = (int *) ((char *) ctx->grp_own_win + CCG_GROUP_HDR_BYTES) + (size_t) ctx->grp_buf * 2 * plane;
+	*C_S = base - (long long) row0 * ctx->n_pad;
+	*C_I = *C_S + plane;
+	*clear = base;
+	*bytes = 2 * plane * sizeof(int);
 	return CCG_OK;
 }
 
-/* after the member's GEMM: barrier with the peers, then reduce + epilogue of the rows this member owns */
-int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const) {
+/* after the member's GEMM of the rows [row0, row1): barrier with the peers, then reduce + epilogue of the rows of
+ * that window this member owns */
+int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const, int row0, int row1) {
 	const int world = ctx->grp_world, rank = ctx->grp_rank;
 	if(ctx->grp_host_barrier && host_barrier_wait((HostBarrier *) ctx->grp_host_barrier)) {
 		ccg_set_err(ctx, "another GPU of the group failed before the run reached the reduction");
@@ -369,39 +391,46 @@ int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const) {
 	k_group_barrier<<<1, 32, 0, ctx->stream>>>(b);
 	ctx->launches++;
 	CKG(ctx, cudaGetLastError());
+	/* ... and once more after it: a host call that blocks until this stream has drained (a copy into pageable host
+	 * memory, say) may hold the driver while it waits; by then every member's barrier kernel must be in its queue */
+	if(ctx->grp_host_barrier && host_barrier_wait((HostBarrier *) ctx->grp_host_barrier)) {
+		ccg_set_err(ctx, "another GPU of the group failed before the run reached the reduction");
+		return CCG_ERR_CUDA;
+	}
+	if(getenv("CCG_DEBUG")) {
+		cudaError_t e = cudaStreamSynchronize(ctx->stream);
+		fprintf(stderr, "[ccg group] rank %d/%d epoch %u buf %d rows [%d,%d) n %d n_pad %d winrows %d acc_bytes %zu: barrier %s\n", rank, world,
+		        b.epoch, b.buf, row0, row1, ctx->n, ctx->n_pad, ccg_group_window_rows(ctx), ctx->grp_acc_bytes, cudaGetErrorString(e));
+	}
 
-	int bounds[CCG_GROUP_MAX + 1];
-	group_row_bounds(ctx->n, world, bounds);
+	const int rows_cap = ccg_group_window_rows(ctx);
+	const size_t plane = (size_t) rows_cap * ctx->n_pad;
 	GroupFinalizeParams q;
 	memset(&q, 0, sizeof(q));
-	const size_t buf_ints = (size_t) 2 * ctx->grp_npad_max * ctx->grp_npad_max;
 	for(int p = 0; p < world; ++p)
-		q.C[p] = (const int *) ((const char *) ctx->grp_win[p] + CCG_GROUP_HDR_BYTES) + (size_t) ctx->grp_buf * buf_ints;
+		q.C[p] = (const int *) ((const char *) ctx->grp_win[p] + CCG_GROUP_HDR_BYTES) + (size_t) ctx->grp_buf * 2 * plane -
+		         (long long) row0 * ctx->n_pad;
 	q.own = (const GroupHeader *) ctx->grp_win[rank];
-	q.plane = (size_t) ctx->n_pad * ctx->n_pad;
+	q.plane = plane;
 	q.world = world;
+	q.rank = rank;
 	q.ldc = ctx->n_pad;
 	q.n = ctx->n;
 	q.pair_mode = ctx->pair_mode;            /* a three-plane store carries the inclusion counts in the I plane */
 	q.buf = ctx->grp_buf;
-	q.row_lo = bounds[rank];
-	q.row_hi = bounds[rank + 1];
-	/* the packed span of those rows over the included samples */
-	long long r_lo = ctx->last_Dn, r_hi = ctx->last_Dn;
-	for(int i = q.row_lo; i < ctx->n; ++i)
-		if(ctx->h_rank[i] >= 0) { r_lo = ctx->h_rank[i]; break; }
-	for(int i = q.row_hi; i < ctx->n; ++i)
-		if(ctx->h_rank[i] >= 0) { r_hi = ctx->h_rank[i]; break; }
-	ctx->grp_rows[0] = q.row_lo;
-	ctx->grp_rows[1] = q.row_hi;
-	ctx->grp_span[0] = r_lo * (r_lo - 1) / 2;
-	ctx->grp_span[1] = r_hi * (r_hi - 1) / 2;
+	q.row_lo = row0;
+	q.row_hi = row1 < ctx->n ? row1 : ctx->n;
 	const int rows = q.row_hi - q.row_lo;
 	if(rows > 0) {
 		int grid = rows < 8 * ctx->sm_count ? rows : 8 * ctx->sm_count;
 		k_finalize_group<<<grid, 256, 0, ctx->stream>>>(q, ep);
 		ctx->launches++;
 		CKG(ctx, cudaGetLastError());
+		if(getenv("CCG_DEBUG")) {
+			cudaError_t e = cudaStreamSynchronize(ctx->stream);
+			fprintf(stderr, "[ccg group] rank %d finalize grid %d plane %zu row_base %p D %p: %s\n", rank, grid, q.plane, (const void *) ep.row_base,
+			        ep.D, cudaGetErrorString(e));
+		}
 	}
 	ctx->grp_buf ^= 1;
 	return CCG_OK;
@@ -486,6 +515,16 @@ extern "C" int ccg_init_multi_devices(ccg_ctx **out, int ngpus, const int *devic
 extern "C" int ccg_init_multi(ccg_ctx **out, int ngpus) {
 	int count = 0;
 	if(!out) return CCG_ERR_ARG;
+	if(getenv("CCG_MULTI_DEVICES")) {
+		/* test hook: an explicit member -> device list, ids may repeat ("0,0,0": three members on one GPU) */
+		int devices[CCG_GROUP_MAX], k = 0;
+		for(const char *p = getenv("CCG_MULTI_DEVICES"); *p && k < CCG_GROUP_MAX;) {
+			devices[k++] = atoi(p);
+			while(*p && *p != ',') ++p;
+			if(*p == ',') ++p;
+		}
+		if(k > 0) return ccg_init_multi_devices(out, (ngpus > 0 && ngpus < k) ? ngpus : k, devices);
+	}
 	if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
 		cudaGetLastError();
 		ccg_set_err(0, "no CUDA device visible");
@@ -493,6 +532,7 @@ extern "C" int ccg_init_multi(ccg_ctx **out, int ngpus) {
 	}
 	if(ngpus <= 0 || ngpus > count) ngpus = count;
 	if(ngpus > CCG_GROUP_MAX) ngpus = CCG_GROUP_MAX;
+	if(ngpus == 1) return ccg_init(out, 0);       /* one device: a plain context, nothing to fan out */
 	int devices[CCG_GROUP_MAX];
 	for(int g = 0; g < ngpus; ++g) devices[g] = g;
 	return ccg_init_multi_devices(out, ngpus, devices);

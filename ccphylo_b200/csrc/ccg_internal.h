@@ -49,6 +49,8 @@ struct EpilogueParams {
 	void *D;               /* device, packed over included samples */
 	void *N;               /* device or NULL */
 	const int *rank;       /* slot -> compact index, -1 = excluded */
+	const long long *row_base;   /* NULL: cell = r (r - 1) / 2 + c.  Else cell = row_base[r] + c (a K-split member's compact
+	                              * buffer of the rows it owns) */
 	int row_plus1;         /* 0 = the packed triangle.  r + 1: only the cells of compact row r are written, cell = column, and
 	                        * a cell that fails the gate gets N = 0 (cmpFsaRowThrd fsacmpthrd.c:560-570; doubles only) */
 };
@@ -102,6 +104,7 @@ struct UmmaParams {
  * through peer-mapped pointers (NVLink), fused with the epilogue -- ccg_group.cu ---- */
 #define CCG_GROUP_MAX 16
 #define CCG_GROUP_HDR_BYTES 4096
+#define CCG_GROUP_ROW_BLOCK 64              /* matrix rows are owned in blocks of this many, dealt round-robin */
 
 struct GroupHeader {                        /* start of every member's peer window */
 	unsigned arrive[CCG_GROUP_MAX];         /* arrive[p]: last barrier epoch member p announced to this member */
@@ -117,9 +120,9 @@ struct GroupBarrierParams {
 struct GroupFinalizeParams {
 	const int *C[CCG_GROUP_MAX];            /* every member's current accumulator buffer: S plane, I plane behind it */
 	const GroupHeader *own;
-	size_t plane;                           /* ints per plane (n_pad * ldc) */
-	int world, ldc, n, pair_mode, buf;
-	int row_lo, row_hi;                     /* sample slots (matrix rows) this member finalises */
+	size_t plane;                           /* ints per plane (window rows * ldc) */
+	int world, rank, ldc, n, pair_mode, buf;
+	int row_lo, row_hi;                     /* rows of this window; the member finalises those it owns */
 };
 
 struct ccg_multi;
@@ -231,8 +234,11 @@ struct ccg_ctx {
 	int grp_buf;                           /* accumulator buffer of the next run (the two are used in turn) */
 	long long grp_total_len;               /* length of the whole alignment: the minCov gate (fsacmpthrd.c:292) */
 	unsigned grp_global_inc;               /* shared-mask mode: getNpos of the whole global mask */
-	long long grp_span[2];                 /* packed cells [lo, hi) the last run of this member wrote */
-	int grp_rows[2];                       /* sample slots [lo, hi) it finalised */
+	size_t grp_acc_bytes;                  /* accumulator bytes of a window (the smallest of the members' exports) */
+	long long *d_row_base, *h_row_base;    /* group runs into host matrices: compact offset of every owned row */
+	size_t row_base_cap;
+	int grp_compact;                       /* ccg_group_set_output: D / N of the run calls hold only this member's rows */
+	const long long *ep_row_base;          /* what the next run's epilogue uses as EpilogueParams::row_base */
 	struct ccg_multi *multi;               /* leader of an in-process multi-GPU context (ccg_init_multi) */
 	void *grp_host_barrier;                /* members of one process: host rendezvous before the device barrier (ccg_group.cu) */
 
@@ -291,9 +297,11 @@ void ccg_mat_free(ccg_ctx *ctx);
 
 /* ccg_group.cu */
 void ccg_set_err(ccg_ctx *ctx, const char *fmt, ...);
+extern "C" long long ccg_group_cells(int n, int rank, int world);
 void ccg_group_release(ccg_ctx *ctx);
-int ccg_group_accumulators(ccg_ctx *ctx, int **C_S, int **C_I);
-int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const);
+int ccg_group_window_rows(ccg_ctx *ctx);
+int ccg_group_accumulators(ccg_ctx *ctx, int row0, int **C_S, int **C_I, void **clear, size_t *bytes);
+int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const, int row0, int row1);
 void ccg_multi_destroy(ccg_ctx *ctx);
 int ccg_multi_set_problem(ccg_ctx *lead, int n, int len, int pair_mode);
 int ccg_multi_set_kernel(ccg_ctx *lead, int kernel);

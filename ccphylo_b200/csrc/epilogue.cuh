@@ -32,7 +32,7 @@ __device__ __forceinline__ void ccg_write_cell(const EpilogueParams &ep, int slo
 	int r = ep.rank[slot_i];
 	int c = ep.rank[slot_j];
 	if(r < 0 || c < 0) return;
-	long long cell = (long long) r * (r - 1) / 2 + c;
+	long long cell = ep.row_base ? ep.row_base[r] + c : (long long) r * (r - 1) / 2 + c;
 	if(ep.row_plus1) {
 		if(r + 1 != ep.row_plus1) return;
 		cell = c;

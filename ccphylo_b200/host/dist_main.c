@@ -173,6 +173,21 @@ static unsigned candidate_count(const DistOpts *o, ccg_ctx *ctx, int slot, const
 /* -V: where fsaCmpThreadOut's `diffile` lines go (dist.c:85-95); NULL without -V */
 static FILE *g_diffile = 0;
 
+/* The device context of a FASTA run.  The reference spreads the pair loop over -t threads inside fsaCmpThreadOut
+ * (fsacmpthrd.c:76-106); here the same calls spread over every visible GPU: ccg_init_multi returns one handle, the
+ * library cuts the alignment between the GPUs when the job is worth it and works on one device otherwise.
+ * -P, -y and -V need a whole sample on one device, so those runs open a single-device context.
+ * CCPHYLO_GPUS=N limits the number of GPUs (1 = single device). */
+static ccg_ctx *open_fasta_context(const DistOpts *o) {
+	ccg_ctx *ctx = 0;
+	const char *env = getenv("CCPHYLO_GPUS");
+	const int want = env ? atoi(env) : 0;
+	const int plain = !o->proxi && !g_motifs.n && !g_diffile;
+	int rc = (plain && want != 1) ? ccg_init_multi(&ctx, want) : ccg_init(&ctx, -1);
+	if(rc) die_gpu(0, rc);
+	return ctx;
+}
+
 /* printDiff (fsacmp.c:635-644) for one pair's list from ccg_list_variants */
 static int print_variants(void *user, int sample_i, int sample_j, const uint64_t *variants, size_t count) {
 	FILE *f = (FILE *) user;
@@ -218,6 +233,11 @@ static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, un
 		if(rc) die_gpu(ctx, rc);
 	}
 	stat_line("  compare (device, incl. result copy)", t_cmp);
+	if(getenv("CCPHYLO_GPU_STATS")) {
+		int active = 1;
+		const int gpus = ccg_multi_gpus(ctx, &active);
+		fprintf(stderr, "# gpu-stats\t%d of %d GPU(s)\t%s\n", active, gpus, ccg_last_kernel(ctx));
+	}
 	if(Dn > 1) {
 		phy_write_mt(outfile, D, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision, o->threads);
 		if(N) phy_write_mt(n_into_out ? outfile : noutfile, N, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision, o->threads);
@@ -242,10 +262,9 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	OrderedPool *pool = pool_start(n, nthreads, window, slots, sizeof(Parsed), parse_one, &fj);
 	if(!pool) die_errno();
 
-	ccg_ctx *ctx = 0;
 	double t0 = now_s();
-	int rc = ccg_init(&ctx, -1);
-	if(rc) die_gpu(0, rc);
+	ccg_ctx *ctx = open_fasta_context(o);
+	int rc;
 	stat_line("device context", t0);
 	t0 = now_s();
 	unsigned char *include = malloc((size_t) n);
@@ -417,10 +436,8 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 		if(!fr) die_errno();
 	}
 
-	ccg_ctx *ctx = 0;
-	int rc = ccg_init(&ctx, -1);
-	if(rc) die_gpu(0, rc);
-	rc = ccg_set_proximity(ctx, o->proxi, (o->flag & (8 | 32)) != 0);
+	ccg_ctx *ctx = open_fasta_context(o);
+	int rc = ccg_set_proximity(ctx, o->proxi, (o->flag & (8 | 32)) != 0);
 	if(!rc && g_motifs.n) rc = ccg_set_motifs(ctx, g_motifs.n, g_motifs.lens, g_motifs.sets);
 	if(rc) die_gpu(ctx, rc);
 	char **names = calloc((size_t) (nrec ? nrec : 1), sizeof(char *));

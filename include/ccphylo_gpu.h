@@ -101,8 +101,11 @@ int ccg_multi_gpus(const ccg_ctx *ctx, int *active);
  * in rank order.  From then on the context's problem is THIS RANK'S SLICE of the alignment:
  * ccg_set_problem(n, slice length) and the put / run calls work on the slice, every rank passes the
  * same include[] and epilogue arguments, the run calls synchronise the ranks on the device, and a rank
- * writes only the cells of the matrix rows it owns: ccg_group_rows(n, rank, world) in sample slots,
- * ccg_group_last_span in packed cells (one contiguous span; host outputs outside it are left untouched).
+ * writes only the cells of the matrix rows it owns (ccg_group_row_owner; host and device outputs outside
+ * them are left untouched).  The int32 partial sums live in a peer-readable window of at most 8 GiB per
+ * rank: a sample set whose n x n accumulators exceed it (BASELINE configs[3]: 100,000 samples) is run in
+ * windows of whole macro-tile rows, each reduced and finalised before the next one starts, so the sequence
+ * shards never move between the GPUs.
  * ccg_group_set_alignment: the length of the WHOLE alignment (the minCov gate, fsacmpthrd.c:292) and,
  * for shared-mask runs, getNpos of the whole global mask (fsacmpthrd.c:164-176); call it before a run.
  * Not available on such a context: -P, ccg_run_row, ccg_list_variants, ccg_get_raw_counts,
@@ -113,8 +116,16 @@ int ccg_group_export(ccg_ctx *ctx, int max_samples, void *handle);
 int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *handles);
 int ccg_group_leave(ccg_ctx *ctx);
 int ccg_group_set_alignment(ccg_ctx *ctx, long long total_len, unsigned global_inc);
-int ccg_group_rows(int n, int rank, int world, int *row_lo, int *row_hi);     /* pure host arithmetic */
-int ccg_group_last_span(const ccg_ctx *ctx, int *row_lo, int *row_hi, long long *cell_lo, long long *cell_hi);
+/* compact != 0: the D / N buffers of the run calls (host or device) hold ONLY this rank's cells -- the rows of
+ * its row blocks over the included samples, back to back: compact row r of an owned block starts where the
+ * previous owned included row ended and has r cells.  For sample sets whose full matrices are too large to
+ * exist once per rank (100,000 samples: 40 GB per matrix).  Default 0: full-size buffers, packed addressing. */
+int ccg_group_set_output(ccg_ctx *ctx, int compact);
+/* pure host arithmetic: rows are owned in blocks of ccg_group_row_block() = 64, row i by rank (i / 64) % world;
+ * ccg_group_cells = packed cells of an n-sample triangle (all included) a rank owns */
+int ccg_group_row_block(void);
+int ccg_group_row_owner(int row, int world);
+long long ccg_group_cells(int n, int rank, int world);
 
 /* The older deal, kept for the sample-shard ring: this context computes only the lower-triangular
  * tile blocks dealt to `rank` of `world` (one process per GPU, no data-path collective).  Cells of

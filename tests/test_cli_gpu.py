@@ -279,3 +279,39 @@ def test_mat_golden(built, tmp_path, case):
     assert sorted(p.stderr.replace(td + "/", "").splitlines()) == sorted(case["stderr"].splitlines())
     # the comment lines of -f 4 come through as well
     assert [l for l in open(phy).read().splitlines() if l.startswith("#")] == [l for l in case["phy"].splitlines() if l.startswith("#")]
+
+
+# ---- multi-GPU: `ccphylo-b200 dist` opens ccg_init_multi for plain FASTA runs; the output must not depend on the
+# number of GPUs.  CCG_MULTI_DEVICES puts the members on the devices that exist (all on GPU 0 on a 1-GPU box). ----
+@pytest.mark.parametrize("flag", ["3", "1"], ids=["pair", "shared-mask"])
+def test_msa_on_several_gpus_is_byte_identical_to_one(built, tmp_path, flag):
+    import torch
+    from ccphylo_b200 import synth
+
+    td = str(tmp_path)
+    n, length = 230, 9000 + 7
+    rows = synth.make_ascii(n, length, seed=42, snp=0.01, nrun=0.02)
+    rows[17, :] = ord("N")                                        # an excluded record
+    path = os.path.join(td, "msa.fsa")
+    with open(path, "wb") as f:
+        for k in range(n):
+            f.write(b">smp%d\n" % k)
+            for s in range(0, length, 70):
+                f.write(rows[k, s:s + 70].tobytes() + b"\n")
+    outs = {}
+    ngpu = max(torch.cuda.device_count(), 1)
+    for members in (1, 2, 5):
+        env = dict(os.environ, CCPHYLO_GPUS=str(members), CCG_MULTI_FORCE="1", CCPHYLO_GPU_STATS="1",
+                   CCG_MULTI_DEVICES=",".join(str(g % ngpu) for g in range(members)))
+        phy, num = os.path.join(td, f"o{members}.phy"), os.path.join(td, f"o{members}.num")
+        p = subprocess.run([BIN, "dist", "-i", path, "-f", flag, "-W", "1000000", "-o", phy, "-n", num, "-t", "4"], capture_output=True,
+                           text=True, cwd=td, timeout=300, env=env)
+        assert p.returncode == 0, p.stderr[-2000:]
+        stats = [ln for ln in p.stderr.splitlines() if ln.startswith("# gpu-stats") and "GPU(s)" in ln]
+        assert stats and (f"{members} of {members} GPU(s)" in stats[0] if members > 1 else "1 of 1 GPU(s)" in stats[0]), p.stderr
+        if members > 1:
+            assert "K split" in stats[0] and "k_finalize_group" in stats[0]
+        text = "\n".join(ln for ln in p.stderr.splitlines() if not ln.startswith("# gpu-stats"))
+        outs[members] = (open(phy).read(), open(num).read(), text)
+    assert outs[1][0].count("\n") >= n and "# Excluded:\tsmp17" in outs[1][2]
+    assert outs[2] == outs[1] and outs[5] == outs[1]

@@ -148,6 +148,37 @@ def test_group_repeated_runs_alternate_the_accumulator_buffers(multi):
         assert np.array_equal(N, no.astype(np.float64)) and np.array_equal(D, mo.astype(np.float64))
 
 
+@pytest.mark.parametrize("members,n,length,tile_rows", [(3, 700, 3000, 1), (2, 1100, 2600, 2), (4, 513, 5000 + 3, 1)])
+@pytest.mark.parametrize("pair", [True, False], ids=["pair", "shared-mask"])
+def test_group_windows_of_macro_tile_rows(built, monkeypatch, members, n, length, tile_rows, pair):
+    # BASELINE configs[3] in small: the n x n accumulators do not fit the peer window, so the triangle is run in
+    # windows of `tile_rows` macro-tile rows, each reduced over the members and finalised before its buffer is reused
+    n_pad = (n + 255) // 256 * 256
+    monkeypatch.setenv("CCG_MULTI_FORCE", "1")
+    monkeypatch.setenv("CCG_GROUP_WINDOW_BYTES", str(tile_rows * 2 * 2 * 256 * n_pad * 4))
+    codes, seqs, masks, inc = _set(n, length, seed=n + length, nrun=0.02)
+    codes[5, :] = 4
+    seqs, masks, inc = oracle.encode_samples(codes)
+    include = (inc >= length // 2).astype(np.uint8)
+    c = api.Context(multi=_devices(members))
+    try:
+        if pair:
+            D, N, dn, _ = api.fsa_cmp_thread_out(seqs, include, masks, length, pair=True, norm=1000000, min_length=1, min_cov=0.5, ctx=c)
+            Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=1000000, min_length=1, min_cov=0.5)
+            assert np.array_equal(N, No)
+        else:
+            gmask = oracle.global_mask(codes, include)
+            D, _, dn, ginc = api.fsa_cmp_thread_out(seqs, include, gmask.reshape(1, -1), length, pair=False, norm=1000, ctx=c)
+            Do, dno, ginco = oracle.fsa_cmp_global(seqs, gmask, include, length, norm=1000)
+            assert ginc == ginco
+        kern = c.last_kernel
+        assert f"windows={n_pad // (256 * tile_rows) + (1 if n_pad % (256 * tile_rows) else 0)}" in kern, kern
+        assert dn == dno == n - 1
+        assert np.array_equal(D.view(np.uint64), Do.view(np.uint64))
+    finally:
+        c.close()
+
+
 def test_small_or_special_problems_stay_on_one_member(built):
     c = api.Context(multi=_devices(2))
     try:

@@ -121,10 +121,15 @@ def _group_worker(rank, world, port, n, length, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from ccphylo_b200 import api
 
-    lo, hi = api.group_rows(n, rank, world)
+    L = api.load()
     rows = torch.zeros(n, dtype=torch.int64)
-    rows[lo:hi] += 1
-    cells = torch.tensor([hi * (hi - 1) // 2 - lo * (lo - 1) // 2 if hi > lo else 0], dtype=torch.int64)
+    cells = 0
+    for lo, hi in api.group_owned_blocks(n, rank, world):
+        rows[lo:hi] += 1
+        cells += hi * (hi - 1) // 2 - lo * (lo - 1) // 2
+        assert all(L.ccg_group_row_owner(i, world) == rank for i in (lo, hi - 1))
+    assert cells == api.group_cells(n, rank, world)
+    cells = torch.tensor([cells], dtype=torch.int64)
     sl = api.group_slices(length, world)
     bases = torch.zeros(length, dtype=torch.int64)
     bases[sl[rank]:sl[rank + 1]] += 1
@@ -154,18 +159,20 @@ def test_group_rows_and_slices_partition_the_job(built, world, n, length):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(v == 1 for v in rows)                       # every matrix row has exactly one owner
-    assert cells == api.cells(n)                           # the owners' packed spans tile the triangle
+    assert cells == api.cells(n)                           # the owners' cells tile the triangle
     assert bmin == 1 and bmax == 1                         # every base of the alignment is in exactly one slice
     assert all(b % 256 == 0 for b in sl[:-1]) and sl[-1] == length
-    assert worst <= api.cells(n) / world * 1.15 + 8 * n    # cut for equal cells (boundaries are multiples of 8 rows)
+    assert worst <= api.cells(n) / world + 64 * n          # round-robin blocks of 64 rows: within a block row of equal
 
 
-def test_group_rows_edge_cases(built):
+def test_group_ownership_edge_cases(built):
     from ccphylo_b200 import api
 
-    for n in (0, 1, 2, 7, 8, 9, 255, 256, 10000, 100000):
+    assert api.group_row_block() == 64
+    for n in (0, 1, 2, 63, 64, 65, 255, 10000, 100000):
         for world in (1, 2, 5, 8, 16):
-            b = [api.group_rows(n, r, world) for r in range(world)]
-            assert b[0][0] == 0 and b[-1][1] == n
-            assert all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(lo <= hi for lo, hi in b)
+            blocks = sorted(b for r in range(world) for b in api.group_owned_blocks(n, r, world))
+            assert sum(hi - lo for lo, hi in blocks) == n
+            assert all(x[1] == y[0] for x, y in zip(blocks, blocks[1:]))
+            assert sum(api.group_cells(n, r, world) for r in range(world)) == api.cells(n)
     assert api.group_slices(5_000_000, 8)[1] == 624896 and api.group_slices(1000, 3) == [0, 256, 512, 1000]
