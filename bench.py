@@ -424,6 +424,10 @@ def main():
                        f"useful cells only (strict lower triangle); rank 0's launches cover {len_r} of {length} bases",
     }
 
+    if rank == 0:
+        log(f"[rank 0] device-resident: {ms_step:.2f} ms/step, value {value:.4g} {UNIT}, kernel {kern_ms:.2f} ms, "
+            f"frac {achieved / pipe_peak:.3f}, {ctx.last_kernel}")
+
     # ---- parity (outside the timed region): >= 1000 cells spread over EVERY macro tile (and, at N > 1, over every
     # rank's rows) against the oracle on the same samples.  The rows of those samples are gathered on rank 0. ----
     ids = parity_sample_ids(n, args.parity_samples)
@@ -489,6 +493,7 @@ def main():
         call = "ccg_fsa_cmp_thread_out(ctx, pair=1, host rows in pinned memory, host D/N out)" + \
                (f", one call per rank on its slice of the alignment (K-split group of {world})" if world > 1 else "")
 
+        barrier()                 # the ranks leave the host allocations at different times: start the first call together
         for _ in range(2):
             e2e_step()
         barrier()

@@ -791,14 +791,34 @@ extern "C" int ccg_put_samples_packed(ccg_ctx *ctx, int first, int count, const 
 		if(!seqs[k] || (ctx->pair_mode && !includes[k])) { ++k; continue; }
 		if(!ctx->need[(first + k) >> 7]) { ctx->present[first + k] = 1; ++k; continue; }
 		int run = 0;
+		/* rows at one distance from each other (one host allocation, as dist.c:143-154 makes them) cross PCIe as ONE
+		 * strided copy per staging batch instead of one call per row */
+		bool uniform = true;
+		ptrdiff_t ds = 0, dm = 0;
 		while(k + run < count && (size_t) run < batch && seqs[k + run] && (!ctx->pair_mode || includes[k + run]) &&
 		      ctx->need[(first + k + run) >> 7]) {
 			ctx->have[(first + k + run) >> 7] = 1;
-			CK(ctx, cudaMemcpyAsync(d_seq + (size_t) run * W, seqs[k + run], W * 8, cudaMemcpyHostToDevice, ctx->stream));
-			if(ctx->pair_mode)
-				CK(ctx, cudaMemcpyAsync(d_msk + (size_t) run * W, includes[k + run], W * 4, cudaMemcpyHostToDevice, ctx->stream));
 			ctx->present[first + k + run] = 1;
+			if(run == 1) {
+				ds = (const char *) seqs[k + 1] - (const char *) seqs[k];
+				dm = ctx->pair_mode ? (const char *) includes[k + 1] - (const char *) includes[k] : 0;
+				if(ds < (ptrdiff_t) (W * 8) || (ctx->pair_mode && dm < (ptrdiff_t) (W * 4))) uniform = false;
+			} else if(run > 1) {
+				if((const char *) seqs[k + run] - (const char *) seqs[k + run - 1] != ds) uniform = false;
+				if(ctx->pair_mode && (const char *) includes[k + run] - (const char *) includes[k + run - 1] != dm) uniform = false;
+			}
 			++run;
+		}
+		if(uniform && run > 1) {
+			CK(ctx, cudaMemcpy2DAsync(d_seq, W * 8, seqs[k], (size_t) ds, W * 8, (size_t) run, cudaMemcpyHostToDevice, ctx->stream));
+			if(ctx->pair_mode)
+				CK(ctx, cudaMemcpy2DAsync(d_msk, W * 4, includes[k], (size_t) dm, W * 4, (size_t) run, cudaMemcpyHostToDevice, ctx->stream));
+		} else {
+			for(int r = 0; r < run; ++r) {
+				CK(ctx, cudaMemcpyAsync(d_seq + (size_t) r * W, seqs[k + r], W * 8, cudaMemcpyHostToDevice, ctx->stream));
+				if(ctx->pair_mode)
+					CK(ctx, cudaMemcpyAsync(d_msk + (size_t) r * W, includes[k + r], W * 4, cudaMemcpyHostToDevice, ctx->stream));
+			}
 		}
 		CK(ctx, ccg_launch_repack(ctx, first + k, run, d_seq, d_msk, (long) W));
 		k += run;

@@ -77,7 +77,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 /* Thread t talks to member t: everything this member's stream did before the barrier (its accumulator sums) is
  * released to t, and the kernel ends only once every member has announced the same epoch to this member.  A
- * member that never arrives (a failed peer) traps after 30 s instead of hanging the GPU. */
+ * member that never arrives (a failed peer) traps after q.timeout_ns (120 s, CCG_GROUP_TIMEOUT_S) instead of
+ * hanging the GPU. */
 __global__ void k_group_barrier(GroupBarrierParams q) {
 	const int t = threadIdx.x;
 	if(t >= q.world) return;
@@ -88,7 +89,7 @@ __global__ void k_group_barrier(GroupBarrierParams q) {
 	const unsigned long long t0 = global_ns();
 	while((int) (ld_acquire_sys(mine) - q.epoch) < 0) {
 		__nanosleep(200);
-		if(global_ns() - t0 > 30000000000ull) __trap();
+		if(global_ns() - t0 > q.timeout_ns) __trap();
 	}
 }
 
@@ -388,6 +389,7 @@ int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const, int 
 	b.buf = ctx->grp_buf;
 	b.i_const = i_const;
 	b.epoch = ++ctx->grp_epoch;
+	b.timeout_ns = (unsigned long long) (getenv("CCG_GROUP_TIMEOUT_S") ? atof(getenv("CCG_GROUP_TIMEOUT_S")) : 120.0) * 1000000000ull;
 	k_group_barrier<<<1, 32, 0, ctx->stream>>>(b);
 	ctx->launches++;
 	CKG(ctx, cudaGetLastError());

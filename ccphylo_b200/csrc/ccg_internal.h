@@ -115,6 +115,7 @@ struct GroupBarrierParams {
 	GroupHeader *hdr[CCG_GROUP_MAX];
 	int rank, world, buf, i_const;
 	unsigned epoch;
+	unsigned long long timeout_ns;
 };
 
 struct GroupFinalizeParams {

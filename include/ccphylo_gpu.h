@@ -110,7 +110,7 @@ int ccg_multi_gpus(const ccg_ctx *ctx, int *active);
  * for shared-mask runs, getNpos of the whole global mask (fsacmpthrd.c:164-176); call it before a run.
  * Not available on such a context: -P, ccg_run_row, ccg_list_variants, ccg_get_raw_counts,
  * ccg_set_partition, ccg_set_tile_window.  A rank that never reaches the run makes the others fail
- * after 30 s (CCG_ERR_CUDA). */
+ * after 120 s (CCG_GROUP_TIMEOUT_S; CCG_ERR_CUDA): start the runs of all ranks together. */
 #define CCG_GROUP_HANDLE_BYTES 128
 int ccg_group_export(ccg_ctx *ctx, int max_samples, void *handle);
 int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *handles);
