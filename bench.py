@@ -166,6 +166,7 @@ def make_host_workload(n, length, seed):
     """Synthetic workload on the host (numpy) for the reference arm when no GPU generated it."""
     import oracle
     from ccphylo_b200 import synth
+    import synth_torch  # noqa: E402
 
     codes = synth.make_codes(n, length, seed=seed)
     return oracle.encode_samples(codes)[:2]
@@ -263,6 +264,7 @@ def main():
     import torch.distributed as dist
 
     from ccphylo_b200 import api, synth
+    import synth_torch  # noqa: E402
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
@@ -283,7 +285,7 @@ def main():
         raise SystemExit(f"bench.py: {length} bp cannot be cut into {world} slices of at least 256 bp")
     W = api.words(len_r)
     t_gen = time.time()
-    seqs_t, masks_t = synth.make_packed_torch(n, len_r, seed=2 + 1000 * rank, device=dev)
+    seqs_t, masks_t = synth_torch.make_packed_torch(n, len_r, seed=2 + 1000 * rank, device=dev)
     torch.cuda.synchronize()
     log(f"[rank {rank}] generated {n} x {len_r} bp (bases {b0}..{b1} of {length}) in {time.time() - t_gen:.1f}s")
 

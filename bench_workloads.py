@@ -51,6 +51,7 @@ def ring_main(args, rank, world, local_rank, emit, log, ClockSampler, measured_p
 
     import bench
     from ccphylo_b200 import api, synth
+    import synth_torch  # noqa: E402
 
     if args.impl == "reference":
         if rank == 0:
@@ -74,7 +75,7 @@ def ring_main(args, rank, world, local_rank, emit, log, ClockSampler, measured_p
     len_r = b1 - b0
     W = api.words(len_r)
     t_gen = time.time()
-    seqs_t, masks_t = synth.make_packed_torch(n, len_r, seed=4 + 1000 * rank, device=dev)
+    seqs_t, masks_t = synth_torch.make_packed_torch(n, len_r, seed=4 + 1000 * rank, device=dev)
     torch.cuda.synchronize()
     log(f"[rank {rank}] generated {n} x {len_r} bp (bases {b0}..{b1} of {length}) in {time.time() - t_gen:.1f}s")
 

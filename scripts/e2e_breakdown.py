@@ -12,12 +12,13 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from ccphylo_b200 import api, synth  # noqa: E402
+import synth_torch  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 length = 5_000_000
 dev = torch.device("cuda", 0)
 W = api.words(length)
-seqs_t, masks_t = synth.make_packed_torch(n, length, seed=2, device=dev)
+seqs_t, masks_t = synth_torch.make_packed_torch(n, length, seed=2, device=dev)
 L = api.load()
 hs_ptr = L.ccg_host_alloc(n * W * 8)
 hm_ptr = L.ccg_host_alloc(n * W * 4)

@@ -14,6 +14,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from ccphylo_b200 import api, synth  # noqa: E402
+import synth_torch  # noqa: E402
 
 DAM_DCM = [[4, 17, 8, 2], [4, 1, 24, 2], [2, 18, 9, 4, 4], [2, 4, 9, 20, 4]]      # gAtc, gaTc, cCwgg, cgwGg
 
@@ -27,7 +28,7 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     n, L = a.samples, a.length
-    seqs, masks = synth.make_packed_torch(n, L, seed=2, device=dev)
+    seqs, masks = synth_torch.make_packed_torch(n, L, seed=2, device=dev)
     ctx = api.Context(0)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)

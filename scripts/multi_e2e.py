@@ -27,6 +27,7 @@ def main():
     args = ap.parse_args()
     import torch
     from ccphylo_b200 import api, synth
+    import synth_torch  # noqa: E402
 
     n, length = args.samples, args.length
     W = api.words(length)
@@ -42,7 +43,7 @@ def main():
     blk = 1000
     for k in range(0, n, blk):                                   # generate on the GPU block by block, park on the host
         m = min(blk, n - k)
-        s, mk = synth.make_packed_torch(m, length, seed=2 + k, device=dev)
+        s, mk = synth_torch.make_packed_torch(m, length, seed=2 + k, device=dev)
         torch.from_numpy(hs[k:k + m].view(np.int64)).copy_(s)
         torch.from_numpy(hm[k:k + m].view(np.int32)).copy_(mk)
     torch.cuda.synchronize()

@@ -12,6 +12,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from ccphylo_b200 import api, synth  # noqa: E402
+import synth_torch  # noqa: E402
 
 
 def main():
@@ -24,7 +25,7 @@ def main():
     ap.add_argument("--proxi", type=int, default=0, help="-P: run k_pairdist_proxi instead of the plain compare")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
-    seqs, masks = synth.make_packed_torch(a.samples, a.length, seed=2, device=dev)
+    seqs, masks = synth_torch.make_packed_torch(a.samples, a.length, seed=2, device=dev)
     ctx = api.Context(0)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)

@@ -1,4 +1,9 @@
-"""Sample-shard ring for sets whose bit planes do not fit one GPU's HBM (BASELINE configs[3]:
+"""HARNESS, not product: the NCCL sample-shard ring of round 1, kept to compare against the library's own answer to
+sets larger than one GPU (sequence shards + row windows, ccphylo_b200/csrc/ccg_group.cu; bench.py --workload ring:
+2.17 s per 100,000 x 2.9 Mbp step on 8 B200 against 4.99 s for this ring).  It drives the C-ABI block by block
+(ccg_set_tile_window) and moves the shards with torch.distributed.
+
+Sample-shard ring for sets whose bit planes do not fit one GPU's HBM (BASELINE configs[3]:
 100,000 samples x 2.9 Mbp = 109 GB of planes).
 
 Every rank owns one shard of S consecutive samples (S a multiple of the macro-tile edge).  The
@@ -19,7 +24,11 @@ test drives; the schedule, the slot placement and the block extraction are the s
 """
 import numpy as np
 
-from . import api
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ccphylo_b200 import api  # noqa: E402
 
 
 def shard_size(n, world, edge=256):

@@ -18,7 +18,10 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from ccphylo_b200 import api, ring, synth  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ring  # noqa: E402
+from ccphylo_b200 import api, synth  # noqa: E402
+import synth_torch  # noqa: E402
 
 _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
@@ -41,7 +44,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     # every rank generates ITS shard only (seeded by the rank): no rank ever holds the whole set
-    seqs, masks = synth.make_packed_torch(S, L, seed=1000 + rank, device=dev, snp=0.01 if a.check else synth.SNP_RATE)
+    seqs, masks = synth_torch.make_packed_torch(S, L, seed=1000 + rank, device=dev, snp=0.01 if a.check else synth.SNP_RATE)
     st = ring.RankState(rank, world, S, L, seqs, masks, dev)
     st.ctx.set_stream(stream.cuda_stream)
     pinned = {}

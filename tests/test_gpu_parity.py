@@ -9,6 +9,7 @@ import pytest
 import helpers
 import oracle
 from ccphylo_b200 import api, synth
+import synth_torch  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -210,7 +211,7 @@ def test_size_independent_properties_large(ctx):
 
     n, length = 512, 1_000_000
     half = (length // 2 // 32) * 32
-    seqs_t, masks_t = synth.make_packed_torch(n, length, seed=9, device="cuda")
+    seqs_t, masks_t = synth_torch.make_packed_torch(n, length, seed=9, device="cuda")
     W = seqs_t.shape[1]
 
     def run(s_t, m_t, L):

@@ -7,7 +7,10 @@ import pytest
 import torch
 
 import oracle
-from ccphylo_b200 import api, ring, synth
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+import ring  # noqa: E402  (scripts/ring.py: the NCCL sample-shard ring harness)
+from ccphylo_b200 import api, synth  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 

@@ -8,6 +8,7 @@ import pytest
 import helpers
 import oracle
 from ccphylo_b200 import api, synth
+import synth_torch  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -160,7 +161,7 @@ def test_umma_equals_popc_on_device(built):
     import torch
 
     n, length = 700, 400_000
-    seqs_t, masks_t = synth.make_packed_torch(n, length, seed=5, device="cuda")
+    seqs_t, masks_t = synth_torch.make_packed_torch(n, length, seed=5, device="cuda")
     torch.cuda.synchronize()
     out = {}
     for kind in (api.KERNEL_POPC, api.KERNEL_UMMA, api.KERNEL_FUSED):

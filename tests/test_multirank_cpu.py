@@ -68,7 +68,9 @@ def _ring_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from ccphylo_b200 import ring
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import ring
 
     tr = ring.NcclTransport(rank, world)            # the transport only needs torch.distributed P2P
     cur = torch.full((4,), float(rank))
@@ -88,7 +90,9 @@ def _ring_worker(rank, world, port, out):
 
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_ring_schedule_visits_every_shard_pair_once(world):
-    from ccphylo_b200 import ring
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import ring
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
