@@ -30,7 +30,7 @@ EXPORTS = [
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
     "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs", "ccg_list_variants_row",
     "ccg_init_multi", "ccg_init_multi_devices", "ccg_multi_gpus", "ccg_group_export", "ccg_group_join", "ccg_group_leave",
-    "ccg_group_set_alignment", "ccg_group_set_output", "ccg_group_row_block", "ccg_group_row_owner", "ccg_group_cells",
+    "ccg_mat_run_partial", "ccg_mat_finalize_host", "ccg_group_set_alignment", "ccg_group_set_output", "ccg_group_row_block", "ccg_group_row_owner", "ccg_group_cells",
 ]
 GROUP_HANDLE_BYTES = 128
 
@@ -129,6 +129,8 @@ def load():
     L.ccg_mat_put_sample.argtypes = [vp, i, vp, vp, i]
     L.ccg_mat_run.argtypes = [vp, vp, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, i, C.c_double,
                               vp, vp, vp, vp]
+    L.ccg_mat_run_partial.argtypes = [vp, vp, i, C.c_uint, C.c_double, C.c_uint, vp, vp, vp]
+    L.ccg_mat_finalize_host.argtypes = [i, vp, vp, vp, vp, C.c_uint, C.c_uint, C.c_double, i, C.c_double, vp, vp, vp, vp]
     L.ccg_mat_run_row.argtypes = [vp, i, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, vp, vp, vp]
     L.ccg_init_multi.argtypes = [C.POINTER(vp), i]
     L.ccg_init_multi_devices.argtypes = [C.POINTER(vp), i, vp]

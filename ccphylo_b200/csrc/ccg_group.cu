@@ -458,6 +458,10 @@ struct ccg_multi {
 	int force;                             /* CCG_MULTI_FORCE=1: split whatever the size (tests) */
 	char last_kernel[160];
 	HostBarrier *rendezvous;
+	/* count matrices (.mat): the position axis is cut the same way */
+	int mat_active, mat_n, mat_max_len;
+	int mat_base0[CCG_GROUP_MAX + 1];
+	int *mat_lens;                         /* whole length of every slot */
 };
 
 template <class F>
@@ -551,6 +555,7 @@ void ccg_multi_destroy(ccg_ctx *lead) {
 	if(!m) return;
 	for(int g = 0; g < m->n; ++g) ccg_destroy(m->member[g]);
 	delete m->rendezvous;
+	free(m->mat_lens);
 	free(m);
 	lead->multi = 0;
 }
@@ -802,3 +807,84 @@ float ccg_multi_last_compare_ms(ccg_ctx *lead) {
 	return ms;
 }
 ccg_ctx *ccg_multi_member(ccg_ctx *lead, int g) { return (lead->multi && g >= 0 && g < lead->multi->n) ? lead->multi->member[g] : 0; }
+
+/* ---- count matrices on a multi-GPU context: member g holds the positions [mat_base0[g], mat_base0[g + 1]) of every
+ * sample and returns its raw per-pair sums; the leader adds them in member order (a fixed order: the result does not
+ * depend on timing) and finishes on the host with the reference's own arithmetic (ccg_mat_finalize_host) ---- */
+extern "C" int ccg_mat_run_partial(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha,
+                                   unsigned minDepth, double *dist, uint32_t *rows, int *Dn_out);
+extern "C" int ccg_mat_finalize_host(int n, const unsigned char *include, const int *lens, const double *dist, const uint32_t *rows,
+                                     unsigned norm, unsigned minLength, double minCov, int elem_size, double byteScale, void *D, void *N,
+                                     uint32_t *rows_inc, int *Dn_out);
+
+ccg_ctx *ccg_multi_mat_solo(ccg_ctx *lead) { return lead->multi->member[0]; }
+
+int ccg_multi_mat_set_problem(ccg_ctx *lead, int n, int max_len) {
+	ccg_multi *m = lead->multi;
+	int a = m->n;
+	if(m->force) { while(a > 1 && max_len / a < 64) --a; }
+	else { if(n < 64) a = 1; while(a > 1 && max_len / a < 65536) --a; }
+	m->mat_active = a;
+	m->mat_n = n;
+	m->mat_max_len = max_len;
+	free(m->mat_lens);
+	m->mat_lens = (int *) calloc((size_t) (n ? n : 1), sizeof(int));
+	if(!m->mat_lens) return CCG_ERR_NOMEM;
+	for(int g = 0; g <= a; ++g) m->mat_base0[g] = g == a ? max_len : (int) ((long long) max_len * g / a / 32 * 32);
+	for(int g = 0; g < m->n; ++g) {
+		/* members outside the split give their store back */
+		int rc = g < a ? ccg_mat_set_problem(m->member[g], n, m->mat_base0[g + 1] - m->mat_base0[g]) : ccg_mat_set_problem(m->member[g], 0, 0);
+		if(rc) return multi_fail(lead, rc | (g << 8));
+	}
+	return CCG_OK;
+}
+
+int ccg_multi_mat_put_sample(ccg_ctx *lead, int idx, const uint16_t *counts6, const uint32_t *totals, int len) {
+	ccg_multi *m = lead->multi;
+	if(idx < 0 || idx >= m->mat_n || len < 0 || len > m->mat_max_len) return CCG_ERR_ARG;
+	m->mat_lens[idx] = len;
+	for(int g = 0; g < m->mat_active; ++g) {
+		const int p0 = m->mat_base0[g], p1 = m->mat_base0[g + 1];
+		const int part = len <= p0 ? 0 : (len < p1 ? len : p1) - p0;
+		int rc = ccg_mat_put_sample(m->member[g], idx, counts6 + (size_t) p0 * 6, totals ? totals + p0 : 0, part);
+		/* the member's pinned staging buffer is filled by this thread: the next put waits for the upload itself */
+		if(rc) return multi_fail(lead, rc | (g << 8));
+	}
+	return CCG_OK;
+}
+
+int ccg_multi_mat_run(ccg_ctx *lead, const unsigned char *include, int method, unsigned order, double alpha, unsigned norm,
+                      unsigned minDepth, unsigned minLength, double minCov, int elem_size, double byteScale, void *D, void *N, int *Dn_out,
+                      uint32_t *rows_inc) {
+	ccg_multi *m = lead->multi;
+	if(!m->mat_lens) return CCG_ERR_ARG;
+	if(m->mat_active == 1) {
+		int rc = ccg_mat_run(m->member[0], include, method, order, alpha, norm, minDepth, minLength, minCov, elem_size, byteScale, D, N, Dn_out,
+		                     rows_inc);
+		multi_note_kernel(lead);
+		return ccg_multi_forwarded(lead, rc);
+	}
+	int Dn = 0;
+	for(int i = 0; i < m->mat_n; ++i) Dn += (!include || include[i]) ? 1 : 0;
+	if(Dn_out) *Dn_out = Dn;
+	if(Dn < 2) return CCG_OK;
+	const size_t cells = (size_t) Dn * (Dn - 1) / 2;
+	const int a = m->mat_active;
+	std::vector<std::vector<double>> dist((size_t) a);
+	std::vector<std::vector<uint32_t>> rows((size_t) a);
+	int rc = multi_parallel(m, a, [&](int g) -> int {
+		dist[(size_t) g].assign(cells, 0.0);
+		rows[(size_t) g].assign(cells, 0u);
+		int dn = 0;
+		return ccg_mat_run_partial(m->member[g], include, method, order, alpha, minDepth, dist[(size_t) g].data(), rows[(size_t) g].data(), &dn);
+	});
+	if(rc) return multi_fail(lead, rc);
+	for(int g = 1; g < a; ++g)
+		for(size_t c = 0; c < cells; ++c) {
+			dist[0][c] += dist[(size_t) g][c];
+			rows[0][c] += rows[(size_t) g][c];
+		}
+	snprintf(m->last_kernel, sizeof(m->last_kernel), "%s x %d gpus (position split)", ccg_last_kernel(m->member[0]), a);
+	return ccg_mat_finalize_host(m->mat_n, include, m->mat_lens, dist[0].data(), rows[0].data(), norm, minLength, minCov, elem_size, byteScale,
+	                             D, N, rows_inc, 0);
+}

@@ -213,13 +213,13 @@ struct ccg_ctx {
 	int tmap_valid;
 
 	/* count-matrix (.mat) path, k_matdist.cu */
-	void *mat_counts;          /* [mat_npad][mat_lpad] 16-byte records */
-	void *mat_norms;           /* [mat_npad][mat_lpad] doubles: sqrt of the squared count-vector length (cos) */
+	void *mat_counts;          /* [mat_npad][3][mat_lpad] u32: A|C<<16, G|T<<16, -|N<<16 */
+	void *mat_tot_over;        /* [mat_npad][mat_lpad] u32 row totals of samples with counts above 65,535, else NULL */
 	int *mat_lens, *mat_hlens; /* device / host: rows per slot */
 	int *mat_rank;
 	int mat_n, mat_npad;
 	long long mat_lpad;
-	void *mat_stage;           /* pinned staging for one sample */
+	void *mat_stage;           /* device staging for one sample in the upload format (len x 6 u16) */
 	double *mat_part_dist;
 	unsigned *mat_part_rows, *mat_rows;
 	size_t mat_part_cap;
@@ -324,6 +324,12 @@ long long ccg_multi_launch_count(const ccg_ctx *lead);
 const char *ccg_multi_last_kernel(const ccg_ctx *lead);
 float ccg_multi_last_compare_ms(ccg_ctx *lead);
 ccg_ctx *ccg_multi_member(ccg_ctx *lead, int g);
+int ccg_multi_mat_set_problem(ccg_ctx *lead, int n, int max_len);
+int ccg_multi_mat_put_sample(ccg_ctx *lead, int idx, const uint16_t *counts6, const uint32_t *totals, int len);
+int ccg_multi_mat_run(ccg_ctx *lead, const unsigned char *include, int method, unsigned order, double alpha, unsigned norm,
+                      unsigned minDepth, unsigned minLength, double minCov, int elem_size, double byteScale, void *D, void *N, int *Dn_out,
+                      uint32_t *rows_inc);
+ccg_ctx *ccg_multi_mat_solo(ccg_ctx *lead);
 
 /* a call that only one device can take: forwarded to member 0 of a multi-GPU context unless the problem is split */
 #define CCG_MULTI_SOLO(ctx, what, call)                      \

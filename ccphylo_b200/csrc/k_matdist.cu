@@ -8,10 +8,13 @@
  * reference re-opens, inflates and re-parses sample j's file for every cell (i, j); here every
  * sample's template is parsed once on the host and kept resident in HBM.
  *
- * Device layout: counts[slot][position] = 16-byte record {A, C, G, T, -, N as u16; total as u32}
- * (the order the reference stores them in, matparse.c:254-259) plus norms[slot][position] = the
- * double sqrt(sum of squared counts) that `cos` needs, positions zero-padded to a multiple of 64.
- * Insertion rows (reference base '-') are dropped by the host parser.
+ * Device layout (12 bytes per position and sample -- the payload of the reference's record, matparse.c:254-259;
+ * 2,000 samples x 5 Mbp = 120 GB fit one B200):
+ *     counts[slot][plane][position] u32,  plane 0 = A | C << 16,  1 = G | T << 16,  2 = '-' | N << 16
+ * positions zero-padded to a multiple of 32.  The row total (the reference's 32-bit field) and, for `cos`, the
+ * double sqrt(sum of squared counts) are recomputed when a CTA stages a block of positions in shared memory: once
+ * per sample and position of the tile instead of once per pair.  Insertion rows (reference base '-') are dropped by
+ * the host parser.
  *
  * Per pair (i > j), over the positions p < len_j of the earlier sample (the one the reference
  * streams):   if(minDepth <= tot_j[p]) { ++nNucs;
@@ -19,15 +22,19 @@
  * Gate: rowsInc < minLength || rowsInc < minCov * len_j  ->  D = -1, N = 0 ("No sufficient
  * overlap"); else D = norm ? dist / rowsInc * norm : dist, N = rowsInc.
  *
- * Work item = (16 x 16 tile of sample pairs, slice of positions).  A CTA stages 64 positions of
- * its 16 + 16 samples in shared memory (coalesced 16-byte loads along the position axis), every
- * thread owns one pair and walks the positions in order; the per-slice partial sums are written
- * to a [slice][tile][256] buffer and added in slice order by k_matdist_finalize, so the result
- * is deterministic (it differs from the reference's strictly sequential fp64 sum only by
- * rounding: the parity bar for this path is 1e-6 relative, counts are exact).
- * Roofline: CUDA-core FP64 + INT (sqrt / divide per position pair); HBM traffic is
- * 2 x 16 B x 16 samples per 256 position pairs.  -fmad=false (csrc/Makefile) keeps nvcc from
- * contracting the reference's multiply-then-add sequences.
+ * Work item = (32 x 32 tile of sample pairs, slice of positions).  A CTA of 256 threads stages 32 positions of
+ * its 32 + 32 samples in shared memory (coalesced loads along the position axis); every thread owns a 2 x 2 block
+ * of pairs (rows li, li + 16; columns lj, lj + 16), so every record it reads from shared memory serves two pairs,
+ * and walks the positions in order; the per-slice partial sums go to a [slice][tile][1024] buffer and are added in
+ * slice order by k_matdist_finalize, so the result is deterministic (it differs from the reference's strictly
+ * sequential fp64 sum only by rounding: the parity bar for this path is 1e-6 relative, counts are exact).
+ * Roofline: CUDA-core FP64 (one divide per position pair for `cos`) + INT; HBM traffic is 2 x 12 B x 32 samples
+ * per 1024 position pairs, i.e. negligible.  -fmad=false (csrc/Makefile) keeps nvcc from contracting the
+ * reference's multiply-then-add sequences.
+ *
+ * Multi-GPU: the POSITION axis is cut (the same K split as the FASTA path): ccg_mat_run_partial returns a member's
+ * raw per-pair sums over its positions, ccg_mat_finalize_host adds nothing and gates / scales on the host -- the
+ * reference's own double arithmetic; a multi-GPU context (ccg_init_multi) does both behind ccg_mat_run.
  */
 #include <math.h>
 #include <stdio.h>
@@ -41,8 +48,9 @@
 
 namespace {
 
-constexpr int MT = 16;            /* tile edge in samples */
-constexpr int MP = 64;            /* positions per stage (2 x 16 x 65 x 16 B = 33 KB of static shared memory) */
+constexpr int MT = 32;            /* tile edge in samples */
+constexpr int TH = 16;            /* threads per tile edge: a thread owns rows li, li + TH and columns lj, lj + TH */
+constexpr int MP = 32;            /* positions per stage (2 x 32 x 33 x 16 B = 33 KB of static shared memory) */
 
 struct MatParams {
 	unsigned minDepth;
@@ -55,6 +63,7 @@ struct Rec {
 	int tot;
 };
 
+/* shared-memory record: the three packed count words + the row total computed at staging time */
 __device__ __forceinline__ Rec unpack(const uint4 v) {
 	Rec r;
 	r.c[0] = v.x & 0xFFFF; r.c[1] = v.x >> 16;
@@ -218,118 +227,174 @@ __device__ __forceinline__ double veccmp(const Rec &a, const Rec &b, const MatPa
 	}
 }
 
-/* cos: the two square roots of coscmp depend on one sample each, so they are taken once per sample and
- * position on the host (ccg_mat_put_sample) instead of once per pair: sqrt(c1) * sqrt(c2) and the division are
- * the same IEEE operations on the same values, i.e. every per-position term is still bit-identical to the
- * reference's, at less than half of the FP64 work. */
+/* one position of one pair: the gates of cmpMats (matcmp.c:470-481) around the per-position distance */
 template <int M>
-__global__ void __launch_bounds__(MT * MT)
-k_matdist(const uint4 *__restrict__ counts, const double *__restrict__ norms, long long lpad, const int2 *__restrict__ tiles,
-          int ntiles, int nslices, int pos_per_slice, const int *__restrict__ lens, MatParams mp, double *__restrict__ part_dist,
-          unsigned *__restrict__ part_rows) {
+__device__ __forceinline__ void pair_step(const Rec &a, const Rec &b, double sa, double sb, const MatParams &mp, double &dist, unsigned &rows) {
+	if(mp.minDepth <= (unsigned) b.tot && mp.minDepth <= (unsigned) a.tot) {
+		double d;
+		if(M == CCG_MAT_COS) {
+			/* coscmp matcmp.c:420.  sqrt(c1), sqrt(c2) depend on one sample each: taken once per sample and position
+			 * at staging time; the dot product is a sum of int products converted to double one by one in the reference
+			 * -- every partial sum an integer below 2^53, so the int64 sum converted once is the same double */
+			long long dot = 0;
+#pragma unroll
+			for(int k = 0; k < 5; ++k) dot += (long long) (a.c[k] * b.c[k]);
+			if(sa == 0 || sb == 0) d = -1;
+			else {
+				d = 1 - (double) dot / (sa * sb);
+				d = d < 0 ? 0 : d;
+			}
+		} else d = veccmp<M>(a, b, mp);
+		if(0 <= d) { dist += d; ++rows; }
+	}
+}
+
+template <int M>
+__global__ void __launch_bounds__(TH * TH)
+k_matdist(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ tot_over, long long lpad, const int2 *__restrict__ tiles, int ntiles, int nslices,
+          int pos_per_slice, const int *__restrict__ lens, MatParams mp, double *__restrict__ part_dist, unsigned *__restrict__ part_rows) {
 	__shared__ uint4 sA[MT][MP + 1], sB[MT][MP + 1];
 	extern __shared__ double s_norm[];                       /* cos only: [2][MT][MP + 1] */
 	double (*nA)[MP + 1] = reinterpret_cast<double (*)[MP + 1]>(s_norm);
 	double (*nB)[MP + 1] = reinterpret_cast<double (*)[MP + 1]>(s_norm + MT * (MP + 1));
 	const int tile = blockIdx.x % ntiles, ks = blockIdx.x / ntiles;
 	const int ti = tiles[tile].x, tj = tiles[tile].y;
-	const int li = threadIdx.x / MT, lj = threadIdx.x % MT;
-	const int si = ti * MT + li, sj = tj * MT + lj;          /* sample slots of this thread's pair (i = row, j = column) */
-	const int len_j = lens[sj];
+	const int li = threadIdx.x / TH, lj = threadIdx.x % TH;
+	/* the 2 x 2 pairs of this thread: q = 2 * (row half) + (column half) */
+	const int si0 = ti * MT + li, si1 = si0 + TH, sj0 = tj * MT + lj, sj1 = sj0 + TH;
+	const int len_j0 = lens[sj0], len_j1 = lens[sj1];
+	const bool on[4] = {sj0 < si0, sj1 < si0, sj0 < si1, sj1 < si1};
 	const long long p_begin = (long long) ks * pos_per_slice;
 	long long p_end = p_begin + pos_per_slice;
 	if(p_end > lpad) p_end = lpad;
-	double dist = 0;
-	unsigned rows = 0;
+	double dist[4] = {0, 0, 0, 0};
+	unsigned rows[4] = {0, 0, 0, 0};
 	for(long long p0 = p_begin; p0 < p_end; p0 += MP) {
 		__syncthreads();
-		for(int e = threadIdx.x; e < 2 * MT * MP; e += MT * MT) {
+		for(int e = threadIdx.x; e < 2 * MT * MP; e += TH * TH) {
 			const int which = e / (MT * MP), r = (e / MP) % MT, p = e % MP;
 			const int slot = (which ? tj : ti) * MT + r;
-			const uint4 v = counts[(size_t) slot * lpad + p0 + p];
+			const uint32_t *src = counts + (size_t) slot * 3 * lpad + p0 + p;
+			uint4 v;
+			v.x = src[0];
+			v.y = src[lpad];
+			v.z = src[2 * lpad];
+			v.w = (v.x & 0xFFFF) + (v.x >> 16) + (v.y & 0xFFFF) + (v.y >> 16) + (v.z & 0xFFFF) + (v.z >> 16);   /* the row total */
+			if(tot_over) {
+				/* a sample with a count above 65,535: the reference keeps 16 bits of the count but the whole depth in
+				 * the row total (matparse.c:246-258); such samples carry their totals in a side plane */
+				const uint32_t t = tot_over[(size_t) slot * lpad + p0 + p];
+				if(t != 0xFFFFFFFFu) v.w = t;
+			}
 			if(which) sB[r][p] = v; else sA[r][p] = v;
 			if(M == CCG_MAT_COS) {
-				const double nv = norms[(size_t) slot * lpad + p0 + p];
+				/* coscmp's c1: int products summed in an unsigned long (matcmp.c:426-437) */
+				const Rec c = unpack(v);
+				unsigned long long c1 = 0;
+#pragma unroll
+				for(int k = 0; k < 5; ++k) c1 += (unsigned long long) (long long) (c.c[k] * c.c[k]);
+				const double nv = sqrt((double) c1);
 				if(which) nB[r][p] = nv; else nA[r][p] = nv;
 			}
 		}
 		__syncthreads();
-		if(sj < si) {
+		if(on[2]) {                                          /* the lower-left pair of the block is the last one to drop out */
 #pragma unroll 2
 			for(int p = 0; p < MP; ++p) {
-				if(p0 + p >= len_j) break;
-				const Rec b = unpack(sB[lj][p]);
-				if(mp.minDepth <= (unsigned) b.tot) {
-					const Rec a = unpack(sA[li][p]);
-					if(mp.minDepth <= (unsigned) a.tot) {
-						double d;
-						if(M == CCG_MAT_COS) {
-							/* coscmp matcmp.c:420 with sqrt(c1), sqrt(c2) precomputed per sample */
-							const double sa = nA[li][p], sb = nB[lj][p];
-							double dot = 0;
-#pragma unroll
-							for(int k = 0; k < 5; ++k) dot += (double) (a.c[k] * b.c[k]);
-							if(sa == 0 || sb == 0) d = -1;
-							else {
-								d = 1 - dot / (sa * sb);
-								d = d < 0 ? 0 : d;
-							}
-						} else d = veccmp<M>(a, b, mp);
-						if(0 <= d) { dist += d; ++rows; }
-					}
-				}
+				const long long pos = p0 + p;
+				const bool in0 = pos < len_j0, in1 = pos < len_j1;
+				if(!in0 && !in1) break;
+				const Rec a0 = unpack(sA[li][p]), a1 = unpack(sA[li + TH][p]);
+				const Rec b0 = unpack(sB[lj][p]), b1 = unpack(sB[lj + TH][p]);
+				double na0 = 0, na1 = 0, nb0 = 0, nb1 = 0;
+				if(M == CCG_MAT_COS) { na0 = nA[li][p]; na1 = nA[li + TH][p]; nb0 = nB[lj][p]; nb1 = nB[lj + TH][p]; }
+				if(on[0] && in0) pair_step<M>(a0, b0, na0, nb0, mp, dist[0], rows[0]);
+				if(on[1] && in1) pair_step<M>(a0, b1, na0, nb1, mp, dist[1], rows[1]);
+				if(in0) pair_step<M>(a1, b0, na1, nb0, mp, dist[2], rows[2]);
+				if(on[3] && in1) pair_step<M>(a1, b1, na1, nb1, mp, dist[3], rows[3]);
 			}
 		}
 	}
-	const size_t o = ((size_t) ks * ntiles + tile) * (MT * MT) + threadIdx.x;
-	part_dist[o] = dist;
-	part_rows[o] = rows;
+	const size_t o = (((size_t) ks * ntiles + tile) * (TH * TH) + threadIdx.x) * 4;
+#pragma unroll
+	for(int q = 0; q < 4; ++q) {
+		part_dist[o + q] = dist[q];
+		part_rows[o + q] = rows[q];
+	}
 }
 
-/* adds the slices in order, applies the gates of cmpMats (matcmp.c:483-494) and writes the cells */
-__global__ void __launch_bounds__(MT * MT)
+/* the gates of cmpMats (matcmp.c:483-494) and the cell formats; shared by the device epilogue and the host one */
+__host__ __device__ __forceinline__ void mat_cell(double dist, unsigned rows, int len_i, int len_j, unsigned norm, unsigned minLength,
+                                                  double minCov, double *d_out, double *n_out, bool *ok_out) {
+	/* the streamed sample must not be longer than the loaded one (matcmp.c:466-468), and the overlap gate */
+	const bool ok = len_j <= len_i && !(rows < minLength || (double) rows < minCov * (double) len_j);
+	if(!ok) { *d_out = -1.0; *n_out = 0.0; }
+	else { *n_out = (double) rows; *d_out = norm ? dist / (double) rows * (double) norm : dist; }
+	*ok_out = ok;
+}
+
+/* adds the slices in order, applies the gates of cmpMats (matcmp.c:483-494) and writes the cells; with raw != 0 the
+ * sums themselves are written (ccg_mat_run_partial: a member of a position split) */
+__global__ void __launch_bounds__(TH * TH)
 k_matdist_finalize(const int2 *__restrict__ tiles, int ntiles, int nslices, const double *__restrict__ part_dist,
                    const unsigned *__restrict__ part_rows, const int *__restrict__ lens, const int *__restrict__ rank, int n,
                    unsigned norm, unsigned minLength, double minCov, int elem_size, double byteScale, void *D, void *N,
-                   unsigned *__restrict__ rows_out, int row_slot) {
+                   unsigned *__restrict__ rows_out, int row_slot, int raw) {
 	const int tile = blockIdx.x;
 	const int ti = tiles[tile].x, tj = tiles[tile].y;
-	const int si = ti * MT + threadIdx.x / MT, sj = tj * MT + threadIdx.x % MT;
-	if(si >= n || sj >= si) return;
-	const int r = rank[si], c = rank[sj];
-	if(r < 0 || c < 0) return;
-	double dist = 0;
-	unsigned rows = 0;
-	for(int ks = 0; ks < nslices; ++ks) {
-		const size_t o = ((size_t) ks * ntiles + tile) * (MT * MT) + threadIdx.x;
-		dist += part_dist[o];
-		rows += part_rows[o];
-	}
-	const int len_j = lens[sj], len_i = lens[si];
-	/* the streamed sample must not be longer than the loaded one (matcmp.c:466-468), and the overlap gate */
-	const bool ok = len_j <= len_i && !(rows < minLength || (double) rows < minCov * (double) len_j);
-	double d, nn;
-	if(!ok) { d = -1.0; nn = 0.0; }
-	else { nn = (double) rows; d = norm ? dist / (double) rows * (double) norm : dist; }
-	/* row_slot >= 0 (cmpMatRowThrd ltdmatrixthrd.c:111): only that sample's row, cell = column */
-	if(row_slot >= 0 && si != row_slot) return;
-	const long long cell = row_slot >= 0 ? (long long) c : (long long) r * (r - 1) / 2 + c;
-	if(rows_out) rows_out[cell] = ok ? rows : 0u;
-	if(elem_size == 8) {
-		((double *) D)[cell] = d;
-		if(N) ((double *) N)[cell] = nn;
-	} else if(elem_size == 4) {
-		((float *) D)[cell] = (float) d;
-		if(N) ((float *) N)[cell] = (float) nn;
-	} else {
-		/* dtouc(value, 0.5), bytescale.h:22 */
-		ccg_store_fixed(D, cell, elem_size, __dadd_rn(__dmul_rn(d, byteScale), 0.5));
-		if(N) ccg_store_fixed(N, cell, elem_size, __dadd_rn(__dmul_rn(nn, byteScale), 0.5));
+#pragma unroll 1
+	for(int q = 0; q < 4; ++q) {
+		const int si = ti * MT + threadIdx.x / TH + TH * (q >> 1), sj = tj * MT + threadIdx.x % TH + TH * (q & 1);
+		if(si >= n || sj >= si) continue;
+		const int r = rank[si], c = rank[sj];
+		if(r < 0 || c < 0) continue;
+		double dist = 0;
+		unsigned rows = 0;
+		for(int ks = 0; ks < nslices; ++ks) {
+			const size_t o = (((size_t) ks * ntiles + tile) * (TH * TH) + threadIdx.x) * 4 + q;
+			dist += part_dist[o];
+			rows += part_rows[o];
+		}
+		/* row_slot >= 0 (cmpMatRowThrd ltdmatrixthrd.c:111): only that sample's row, cell = column */
+		if(row_slot >= 0 && si != row_slot) continue;
+		const long long cell = row_slot >= 0 ? (long long) c : (long long) r * (r - 1) / 2 + c;
+		if(raw) {
+			((double *) D)[cell] = dist;
+			rows_out[cell] = rows;
+			continue;
+		}
+		double d, nn;
+		bool ok;
+		mat_cell(dist, rows, lens[si], lens[sj], norm, minLength, minCov, &d, &nn, &ok);
+		if(rows_out) rows_out[cell] = ok ? rows : 0u;
+		if(elem_size == 8) {
+			((double *) D)[cell] = d;
+			if(N) ((double *) N)[cell] = nn;
+		} else if(elem_size == 4) {
+			((float *) D)[cell] = (float) d;
+			if(N) ((float *) N)[cell] = (float) nn;
+		} else {
+			/* dtouc(value, 0.5), bytescale.h:22 */
+			ccg_store_fixed(D, cell, elem_size, __dadd_rn(__dmul_rn(d, byteScale), 0.5));
+			if(N) ccg_store_fixed(N, cell, elem_size, __dadd_rn(__dmul_rn(nn, byteScale), 0.5));
+		}
 	}
 }
 
-typedef void (*MatKernel)(const uint4 *, const double *, long long, const int2 *, int, int, int, const int *, MatParams, double *,
-                          unsigned *);
+/* upload format -> store: a position's six u16 counts are three u32 words (A|C<<16, G|T<<16, -|N<<16 on a little-endian
+ * host): de-interleave them into the three planes of the slot */
+__global__ void __launch_bounds__(256)
+k_mat_planes(const uint32_t *__restrict__ rows, int len, long long lpad, uint32_t *__restrict__ dst) {
+	for(long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x; p < lpad; p += (long long) gridDim.x * blockDim.x) {
+		uint32_t w0 = 0, w1 = 0, w2 = 0;
+		if(p < len) { w0 = rows[3 * p]; w1 = rows[3 * p + 1]; w2 = rows[3 * p + 2]; }
+		dst[p] = w0;
+		dst[lpad + p] = w1;
+		dst[2 * lpad + p] = w2;
+	}
+}
+
+typedef void (*MatKernel)(const uint32_t *, const uint32_t *, long long, const int2 *, int, int, int, const int *, MatParams, double *, unsigned *);
 
 MatKernel pick_kernel(int method) {
 	switch(method) {
@@ -368,13 +433,13 @@ MatKernel pick_kernel(int method) {
 
 void ccg_mat_free(ccg_ctx *ctx) {
 	cudaFree(ctx->mat_counts); ctx->mat_counts = 0;
-	cudaFree(ctx->mat_norms); ctx->mat_norms = 0;
+	cudaFree(ctx->mat_tot_over); ctx->mat_tot_over = 0;
 	cudaFree(ctx->mat_lens); ctx->mat_lens = 0;
 	cudaFree(ctx->mat_part_dist); ctx->mat_part_dist = 0;
 	cudaFree(ctx->mat_part_rows); ctx->mat_part_rows = 0;
 	cudaFree(ctx->mat_rows); ctx->mat_rows = 0;
 	cudaFree(ctx->mat_rank); ctx->mat_rank = 0;
-	cudaFreeHost(ctx->mat_stage); ctx->mat_stage = 0;
+	cudaFree(ctx->mat_stage); ctx->mat_stage = 0;
 	free(ctx->mat_hlens); ctx->mat_hlens = 0;
 	ctx->mat_part_cap = 0;
 	ctx->mat_n = 0;
@@ -383,6 +448,7 @@ void ccg_mat_free(ccg_ctx *ctx) {
 
 extern "C" int ccg_mat_set_problem(ccg_ctx *ctx, int n, int max_len) {
 	if(!ctx || n < 0 || max_len < 0) return CCG_ERR_ARG;
+	if(ctx->multi) return ccg_multi_mat_set_problem(ctx, n, max_len);
 	MCK(ctx, cudaSetDevice(ctx->device));
 	MCK(ctx, cudaStreamSynchronize(ctx->stream));
 	ccg_mat_free(ctx);
@@ -391,7 +457,7 @@ extern "C" int ccg_mat_set_problem(ccg_ctx *ctx, int n, int max_len) {
 	if(ctx->mat_npad == 0) ctx->mat_npad = MT;
 	ctx->mat_lpad = (((long long) max_len + MP - 1) / MP) * MP;
 	if(ctx->mat_lpad == 0) ctx->mat_lpad = MP;
-	const size_t bytes = (size_t) ctx->mat_npad * (size_t) ctx->mat_lpad * 16;
+	const size_t bytes = (size_t) ctx->mat_npad * (size_t) ctx->mat_lpad * 12;
 	if(cudaMalloc(&ctx->mat_counts, bytes) != cudaSuccess) {
 		snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc of %zu bytes for %d count matrices of %d positions failed: %s", bytes, n,
 		         max_len, cudaGetErrorString(cudaGetLastError()));
@@ -399,53 +465,56 @@ extern "C" int ccg_mat_set_problem(ccg_ctx *ctx, int n, int max_len) {
 		return CCG_ERR_NOMEM;
 	}
 	MCK(ctx, cudaMemsetAsync(ctx->mat_counts, 0, bytes, ctx->stream));
-	/* sqrt of the squared count-vector length per sample and position (cos) */
-	if(cudaMalloc(&ctx->mat_norms, bytes / 2) != cudaSuccess) {
-		snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc of %zu bytes for the count-vector norms failed", bytes / 2);
-		ctx->mat_norms = 0;
-		return CCG_ERR_NOMEM;
-	}
-	MCK(ctx, cudaMemsetAsync(ctx->mat_norms, 0, bytes / 2, ctx->stream));
 	MCK(ctx, cudaMalloc(&ctx->mat_lens, (size_t) ctx->mat_npad * sizeof(int)));
 	MCK(ctx, cudaMalloc(&ctx->mat_rank, (size_t) ctx->mat_npad * sizeof(int)));
 	ctx->mat_hlens = (int *) calloc((size_t) ctx->mat_npad, sizeof(int));
 	if(!ctx->mat_hlens) return CCG_ERR_NOMEM;
-	/* pinned staging for one sample */
-	if(cudaHostAlloc(&ctx->mat_stage, (size_t) ctx->mat_lpad * 24, cudaHostAllocDefault) != cudaSuccess) {
+	/* device staging for one sample in the upload format */
+	if(cudaMalloc(&ctx->mat_stage, (size_t) ctx->mat_lpad * 12) != cudaSuccess) {
 		ctx->mat_stage = 0;
-		snprintf(ctx->err, sizeof(ctx->err), "cudaHostAlloc of %lld staging bytes failed", ctx->mat_lpad * 16);
+		snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc of %lld staging bytes failed", ctx->mat_lpad * 12);
 		return CCG_ERR_NOMEM;
 	}
 	return CCG_OK;
 }
 
 extern "C" int ccg_mat_put_sample(ccg_ctx *ctx, int idx, const uint16_t *counts6, const uint32_t *totals, int len) {
+	if(ctx && ctx->multi) return ccg_multi_mat_put_sample(ctx, idx, counts6, totals, len);
 	if(!ctx || !ctx->mat_counts || idx < 0 || idx >= ctx->mat_n || len < 0 || len > ctx->mat_lpad || (len && !counts6)) return CCG_ERR_ARG;
 	MCK(ctx, cudaSetDevice(ctx->device));
-	/* the staging buffer is reused: wait for the previous upload */
-	MCK(ctx, cudaStreamSynchronize(ctx->stream));
-	uint16_t *st = (uint16_t *) ctx->mat_stage;
-	double *sn = (double *) ((char *) ctx->mat_stage + (size_t) ctx->mat_lpad * 16);
-	for(int p = 0; p < len; ++p) {
-		const uint16_t *c = counts6 + (size_t) p * 6;
-		uint16_t *o = st + (size_t) p * 8;
-		unsigned tot = totals ? totals[p] : (unsigned) c[0] + c[1] + c[2] + c[3] + c[4] + c[5];
-		o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = c[3]; o[4] = c[4]; o[5] = c[5];
-		memcpy(o + 6, &tot, 4);
-		/* coscmp's c1: int products summed in an unsigned long (matcmp.c:426-437) */
-		unsigned long long c1 = 0;
-		for(int k = 0; k < 5; ++k) c1 += (unsigned long long) (long long) ((int) c[k] * (int) c[k]);
-		sn[p] = sqrt((double) c1);
+	/* the (device) staging buffer is reused in stream order; a pageable source is staged before the copy call returns,
+	 * a pinned one must stay untouched until ccg_sync (include/ccphylo_gpu.h) */
+	/* the reference's 32-bit row total (matparse.c:254-259) is the sum of the six counts unless a count was truncated */
+	bool over = false;
+	if(totals)
+		for(int p = 0; p < len && !over; ++p) {
+			const uint16_t *c = counts6 + (size_t) p * 6;
+			over = totals[p] != (unsigned) c[0] + c[1] + c[2] + c[3] + c[4] + c[5];
+		}
+	const long long lp = ctx->mat_lpad;
+	uint32_t *dst = (uint32_t *) ctx->mat_counts + (size_t) idx * 3 * (size_t) lp;
+	if(len) MCK(ctx, cudaMemcpyAsync(ctx->mat_stage, counts6, (size_t) len * 12, cudaMemcpyHostToDevice, ctx->stream));
+	{
+		long long blocks = (lp + 255) / 256;
+		if(blocks > 8LL * ctx->sm_count) blocks = 8LL * ctx->sm_count;
+		k_mat_planes<<<(unsigned) blocks, 256, 0, ctx->stream>>>((const uint32_t *) ctx->mat_stage, len, lp, dst);
+		ctx->launches++;
+		MCK(ctx, cudaGetLastError());
 	}
-	uint4 *dst = (uint4 *) ctx->mat_counts + (size_t) idx * (size_t) ctx->mat_lpad;
-	double *dstn = (double *) ctx->mat_norms + (size_t) idx * (size_t) ctx->mat_lpad;
-	if(len) {
-		MCK(ctx, cudaMemcpyAsync(dst, st, (size_t) len * 16, cudaMemcpyHostToDevice, ctx->stream));
-		MCK(ctx, cudaMemcpyAsync(dstn, sn, (size_t) len * 8, cudaMemcpyHostToDevice, ctx->stream));
-	}
-	if(len < ctx->mat_lpad) {
-		MCK(ctx, cudaMemsetAsync(dst + len, 0, (size_t) (ctx->mat_lpad - len) * 16, ctx->stream));
-		MCK(ctx, cudaMemsetAsync(dstn + len, 0, (size_t) (ctx->mat_lpad - len) * 8, ctx->stream));
+	if(over || ctx->mat_tot_over) {
+		/* row totals that are not the sum of the stored (16-bit) counts: such a sample's totals go to the side plane,
+		 * 0xFFFFFFFF everywhere else means "the sum" */
+		if(!ctx->mat_tot_over) {
+			const size_t tb = (size_t) ctx->mat_npad * (size_t) lp * 4;
+			if(cudaMalloc(&ctx->mat_tot_over, tb) != cudaSuccess) {
+				ctx->mat_tot_over = 0;
+				snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc of %zu bytes for the row totals failed", tb);
+				return CCG_ERR_NOMEM;
+			}
+			MCK(ctx, cudaMemsetAsync(ctx->mat_tot_over, 0xFF, tb, ctx->stream));
+		}
+		MCK(ctx, cudaMemsetAsync((uint32_t *) ctx->mat_tot_over + (size_t) idx * lp, 0xFF, (size_t) lp * 4, ctx->stream));
+		if(over) MCK(ctx, cudaMemcpyAsync((uint32_t *) ctx->mat_tot_over + (size_t) idx * lp, totals, (size_t) len * 4, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	ctx->mat_hlens[idx] = len;
 	return CCG_OK;
@@ -453,8 +522,9 @@ extern "C" int ccg_mat_put_sample(ccg_ctx *ctx, int idx, const uint16_t *counts6
 
 static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha, unsigned norm,
                         unsigned minDepth, unsigned minLength, double minCov, int elem_size, double byteScale, void *D,
-                        void *N, int *Dn_out, uint32_t *rows_inc, int row_slot) {
+                        void *N, int *Dn_out, uint32_t *rows_inc, int row_slot, int raw = 0) {
 	if(!ctx || !ctx->mat_counts || !D) return CCG_ERR_ARG;
+	if(raw && (!rows_inc || elem_size != 8 || N)) return CCG_ERR_ARG;
 	if(elem_size != 8 && elem_size != 4 && elem_size != 2 && elem_size != 1) return CCG_ERR_ARG;
 	MatKernel kern = pick_kernel(method);
 	if(!kern) return CCG_ERR_ARG;
@@ -479,7 +549,7 @@ static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, 
 				any_i |= rank[(size_t) ti * MT + k] >= 0;
 				any_j |= rank[(size_t) tj * MT + k] >= 0;
 			}
-			/* one process per GPU: the 16 x 16 tiles are dealt round-robin (ccg_set_partition); cells of other
+			/* one process per GPU: the 32 x 32 tiles are dealt round-robin (ccg_set_partition); cells of other
 			 * ranks read back as zero */
 			if(any_i && any_j && (ctx->world <= 1 || (int) (ordinal++ % ctx->world) == ctx->rank)) tiles.push_back(make_int2(ti, tj));
 			else if(any_i && any_j) { /* another rank's tile */ }
@@ -539,16 +609,16 @@ static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, 
 		cudaEventRecord(ctx->ev0, ctx->stream);
 		const size_t dyn = method == CCG_MAT_COS ? (size_t) 2 * MT * (MP + 1) * sizeof(double) : 0;
 		if(dyn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
-		kern<<<(unsigned) ((long long) ntiles * nslices), MT * MT, dyn, ctx->stream>>>((const uint4 *) ctx->mat_counts,
-		                                                                              (const double *) ctx->mat_norms, ctx->mat_lpad, d_tiles,
+		kern<<<(unsigned) ((long long) ntiles * nslices), TH * TH, dyn, ctx->stream>>>((const uint32_t *) ctx->mat_counts,
+		                                                                              (const uint32_t *) ctx->mat_tot_over, ctx->mat_lpad, d_tiles,
 		                                                                              ntiles, nslices, pos_per_slice, ctx->mat_lens, mp,
 		                                                                              ctx->mat_part_dist, ctx->mat_part_rows);
 		cudaEventRecord(ctx->ev1, ctx->stream);
 		ctx->ev_valid = 1;
 		ctx->launches++;
-		k_matdist_finalize<<<ntiles, MT * MT, 0, ctx->stream>>>(d_tiles, ntiles, nslices, ctx->mat_part_dist, ctx->mat_part_rows,
+		k_matdist_finalize<<<ntiles, TH * TH, 0, ctx->stream>>>(d_tiles, ntiles, nslices, ctx->mat_part_dist, ctx->mat_part_rows,
 		                                                       ctx->mat_lens, ctx->mat_rank, n, norm, minLength, minCov, elem_size,
-		                                                       byteScale, d_D, d_N, d_rows, row_slot);
+		                                                       byteScale, d_D, d_N, d_rows, row_slot, raw);
 		ctx->launches++;
 		e = cudaGetLastError();
 	}
@@ -571,13 +641,76 @@ static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, 
 extern "C" int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha, unsigned norm,
                            unsigned minDepth, unsigned minLength, double minCov, int elem_size, double byteScale, void *D,
                            void *N, int *Dn_out, uint32_t *rows_inc) {
+	if(ctx && ctx->multi)
+		return ccg_multi_mat_run(ctx, include, method, order, alpha, norm, minDepth, minLength, minCov, elem_size, byteScale, D, N, Dn_out,
+		                         rows_inc);
 	return mat_run_impl(ctx, include, method, order, alpha, norm, minDepth, minLength, minCov, elem_size, byteScale, D, N, Dn_out,
 	                    rows_inc, -1);
 }
 
 /* cmpMatRowThrd (ltdmatrixthrd.c:111-181): the last uploaded sample against all the others */
+/* A member of a position split: the raw per-pair sums over THIS context's positions -- dist[cell] the fp64 sum of
+ * the per-position distances, rows[cell] the positions that counted (rowsInc of cmpMats, matcmp.c:470-481) -- packed
+ * over the included samples, no gate, no scaling.  The caller adds the members' sums and hands them to
+ * ccg_mat_finalize_host. */
+extern "C" int ccg_mat_run_partial(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha,
+                                   unsigned minDepth, double *dist, uint32_t *rows, int *Dn_out) {
+	if(ctx && ctx->multi) {
+		ccg_set_err(ctx, "ccg_mat_run_partial is the per-member call: use it on a single-device context");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	return mat_run_impl(ctx, include, method, order, alpha, 0, minDepth, 0, 0.0, 8, 1.0, dist, 0, Dn_out, rows, -1, 1);
+}
+
+static inline int host_cvttsd2si(double x) {
+	if(!(x > -2147483649.0 && x < 2147483648.0)) return (int) 0x80000000;
+	return (int) x;
+}
+
+/* The tail of cmpMats (matcmp.c:483-494) + the cell formats on the HOST, in the reference's own double arithmetic:
+ * dist / rows: the summed raw sums of all members; lens: the whole length of every sample slot. */
+extern "C" int ccg_mat_finalize_host(int n, const unsigned char *include, const int *lens, const double *dist, const uint32_t *rows,
+                                     unsigned norm, unsigned minLength, double minCov, int elem_size, double byteScale, void *D, void *N,
+                                     uint32_t *rows_inc, int *Dn_out) {
+	if(n < 0 || !lens || !dist || !rows || !D) return CCG_ERR_ARG;
+	if(elem_size != 8 && elem_size != 4 && elem_size != 2 && elem_size != 1) return CCG_ERR_ARG;
+	std::vector<int> slot;
+	for(int i = 0; i < n; ++i)
+		if(!include || include[i]) slot.push_back(i);
+	const int Dn = (int) slot.size();
+	if(Dn_out) *Dn_out = Dn;
+	long long cell = 0;
+	for(int r = 1; r < Dn; ++r)
+		for(int c = 0; c < r; ++c, ++cell) {
+			double d, nn;
+			bool ok;
+			mat_cell(dist[cell], rows[cell], lens[slot[(size_t) r]], lens[slot[(size_t) c]], norm, minLength, minCov, &d, &nn, &ok);
+			if(rows_inc) rows_inc[cell] = ok ? rows[cell] : 0u;
+			if(elem_size == 8) {
+				((double *) D)[cell] = d;
+				if(N) ((double *) N)[cell] = nn;
+			} else if(elem_size == 4) {
+				((float *) D)[cell] = (float) d;
+				if(N) ((float *) N)[cell] = (float) nn;
+			} else {
+				const int td = host_cvttsd2si(d * byteScale + 0.5), tn = host_cvttsd2si(nn * byteScale + 0.5);
+				if(elem_size == 2) {
+					((unsigned short *) D)[cell] = (unsigned short) td;
+					if(N) ((unsigned short *) N)[cell] = (unsigned short) tn;
+				} else {
+					((unsigned char *) D)[cell] = (unsigned char) td;
+					if(N) ((unsigned char *) N)[cell] = (unsigned char) tn;
+				}
+			}
+		}
+	return CCG_OK;
+}
+
 extern "C" int ccg_mat_run_row(ccg_ctx *ctx, int row_slot, int method, unsigned order, double alpha, unsigned norm,
                                unsigned minDepth, unsigned minLength, double minCov, double *D, double *N, uint32_t *rows_inc) {
+	if(ctx && ctx->multi)
+		return ccg_multi_forwarded(ctx, ccg_mat_run_row(ccg_multi_mat_solo(ctx), row_slot, method, order, alpha, norm, minDepth, minLength,
+		                                                minCov, D, N, rows_inc));
 	if(!ctx || !ctx->mat_counts || row_slot < 0 || row_slot >= ctx->mat_n) return CCG_ERR_ARG;
 	if(ctx->world > 1) return CCG_ERR_UNSUPPORTED;
 	/* columns are the slots below the row: everything above it stays out */

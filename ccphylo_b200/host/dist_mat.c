@@ -283,11 +283,20 @@ int dist_mat_add_row(const DistOpts *o, int n, char **paths, double *D, double *
 	return 0;
 }
 
+/* every visible GPU (the library cuts the position axis between them when the matrices are long enough);
+ * CCPHYLO_GPUS=N limits the number, 1 = a single-device context */
+static ccg_ctx *open_mat_context(void) {
+	ccg_ctx *ctx = 0;
+	const char *env = getenv("CCPHYLO_GPUS");
+	const int want = env ? atoi(env) : 0;
+	int rc = want == 1 ? ccg_init(&ctx, -1) : ccg_init_multi(&ctx, want);
+	if(rc) die_gpu(0, rc);
+	return ctx;
+}
+
 void dist_mat_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 	const int n = (int) o->numFile;
-	ccg_ctx *ctx = 0;
-	int rc = ccg_init(&ctx, -1);
-	if(rc) die_gpu(0, rc);
+	ccg_ctx *ctx = open_mat_context();
 	unsigned char *include = calloc((size_t) n, 1);
 	if(!include) die_errno();
 	one_template(o, ctx, n, o->filenames, 0, o->targetTemplate, include, outfile, noutfile, 1);
@@ -350,9 +359,7 @@ void dist_mat_union(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 		fprintf(stderr, "Union input with FASTA consensus files (-f 16) is not available on the GPU path.\n");
 		exit(1);
 	}
-	ccg_ctx *ctx = 0;
-	int rc = ccg_init(&ctx, -1);
-	if(rc) die_gpu(0, rc);
+	ccg_ctx *ctx = open_mat_context();
 	unsigned char *want = malloc((size_t) n), *include = malloc((size_t) n);
 	if(!want || !include) die_errno();
 	while(fsa_read_line(fr, &line)) {

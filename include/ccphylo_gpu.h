@@ -341,7 +341,9 @@ enum {
  * not '-': insertion rows are dropped by the caller, as stripMat matcmp.c:27 intends). */
 int ccg_mat_set_problem(ccg_ctx *ctx, int n, int max_len);
 /* counts6: len x 6 u16 in the reference's order A, C, G, T, -, N (matparse.c:254-259);
- * totals: len x u32 row totals, or NULL to sum the six counts.  Host pointers. */
+ * totals: len x u32 row totals, or NULL to sum the six counts.  Host pointers.  The device keeps the 12 bytes of
+ * counts per position; the totals of a sample whose totals are NOT the sum of its (16-bit) counts -- a depth above
+ * 65,535, which the reference truncates in the count but not in the total -- go to a side plane. */
 int ccg_mat_put_sample(ccg_ctx *ctx, int idx, const uint16_t *counts6, const uint32_t *totals, int len);
 /* All pairs of the samples with include[i] != 0 (NULL = all slots).  method is a CCG_MAT_* id,
  * order the n of l<n> / nl<n>, alpha the -l level of `z`.  D, N (N may be NULL): HOST buffers of
@@ -351,6 +353,18 @@ int ccg_mat_put_sample(ccg_ctx *ctx, int idx, const uint16_t *counts6, const uin
 int ccg_mat_run(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha,
                 unsigned norm, unsigned minDepth, unsigned minLength, double minCov, int elem_size,
                 double byteScale, void *D, void *N, int *Dn, uint32_t *rows_inc);
+
+/* Position split over several GPUs (the K split of the FASTA path; a multi-GPU context does this behind ccg_mat_run).
+ * A member context holds the positions [p_g, p_g+1) of every sample (ccg_mat_set_problem / ccg_mat_put_sample with the
+ * slice lengths).  ccg_mat_run_partial returns its raw per-pair sums, packed over the included samples: dist[cell] the
+ * fp64 sum of the per-position distances, rows[cell] the positions that counted (rowsInc, matcmp.c:470-481).  The
+ * caller adds the members' sums and finishes with ccg_mat_finalize_host (pure host code, no device): the tail of
+ * cmpMats (matcmp.c:483-494) and the cell formats, lens[] = the whole length of every sample slot. */
+int ccg_mat_run_partial(ccg_ctx *ctx, const unsigned char *include, int method, unsigned order, double alpha,
+                        unsigned minDepth, double *dist, uint32_t *rows, int *Dn);
+int ccg_mat_finalize_host(int n, const unsigned char *include, const int *lens, const double *dist, const uint32_t *rows,
+                          unsigned norm, unsigned minLength, double minCov, int elem_size, double byteScale, void *D, void *N,
+                          uint32_t *rows_inc, int *Dn);
 
 /* One row against an existing matrix (-a on .mat input): replaces matCmpThreadOut(tnum,
  * &cmpMatRowThrd, ...) (ltdmatrixthrd.c:605, worker :111-181).  The new sample sits in slot

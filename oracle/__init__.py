@@ -91,6 +91,17 @@ MAT_METHODS = ["cos", "z", "chi2", "nchi2", "c", "nc", "p", "np", "bc", "nbc", "
                "nlinf", "nln"]
 
 
+def write_mat(path, name, refbases, counts6):
+    """one sample's KMA .mat text file (bench / test infrastructure for runs of the reference binary)"""
+    L = lib()
+    L.orc_write_mat.restype = C.c_int
+    L.orc_write_mat.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_long]
+    refbases = np.ascontiguousarray(refbases, dtype=np.uint8)
+    counts6 = np.ascontiguousarray(counts6, dtype=np.uint16)
+    if L.orc_write_mat(path.encode(), name.encode(), refbases.ctypes.data, counts6.ctypes.data, counts6.shape[0]) != 0:
+        raise OSError(f"cannot write {path}")
+
+
 def mat_method(name):
     """'-d' name -> (method id, order) with the reference's precedence (dist.c:738-786)."""
     if name in MAT_METHODS and name not in ("ln", "nln"):

@@ -228,3 +228,19 @@ int orc_mat_matrix(int method, unsigned order, double alpha, int n, long lmax, c
 	}
 	return Dn;
 }
+
+/* Test / bench infrastructure: writes one KMA count matrix (.mat, plain text) for the reference binary to read --
+ * "#name", then per position "ref\tA\tC\tG\tT\tN\t-" (the file order; counts6 holds A,C,G,T,-,N), then a blank line. */
+#include <stdio.h>
+int orc_write_mat(const char *path, const char *name, const unsigned char *refbases, const uint16_t *counts6, long len) {
+	FILE *f = fopen(path, "w");
+	long p;
+	if(!f) return -1;
+	fprintf(f, "#%s\n", name);
+	for(p = 0; p < len; ++p) {
+		const uint16_t *c = counts6 + 6 * p;
+		fprintf(f, "%c\t%u\t%u\t%u\t%u\t%u\t%u\n", "ACGT"[refbases[p] & 3], c[0], c[1], c[2], c[3], c[5], c[4]);
+	}
+	fputc('\n', f);
+	return fclose(f);
+}

@@ -148,3 +148,87 @@ def test_rank_partition_covers_every_cell_once(built):
             hits += (N != 0)
     assert np.array_equal(Nsum, No) and hits.max() == 1
     assert close(Dsum, Do)
+
+
+# ---- the 12-byte store: totals recomputed on the device, a side plane for depths above 65,535 ----
+def test_row_totals_that_are_not_the_sum_of_the_stored_counts(ctx):
+    # the reference keeps 16 bits of a count but the whole depth in the row total (matparse.c:246-258): a depth of
+    # 70,000 is stored as 4,464 with total 70,000 + the rest.  Such samples carry their totals separately.
+    n, length = 9, 700
+    counts, totals = random_counts(n, length, seed=7)
+    lens = np.full(n, length, np.int32)
+    totals[3, 100:140] += 65536                              # what a count of 65,536 + c leaves behind
+    totals[6, ::50] += 3 * 65536
+    ctx.mat_set_problem(n, length)
+    for i in range(n):
+        ctx.mat_put_sample(i, counts[i], totals[i])
+    for method in ("cos", "nchi2", "bc"):
+        D, N, dn, rows = ctx.mat_run(None, method=method, min_depth=30)
+        Do, No, dno = oracle.mat_matrix(counts, totals, lens, None, method=method, min_depth=30)
+        assert np.array_equal(N, No) and close(D, Do), method
+    # putting an ordinary sample into the slot again removes the override
+    totals[3] = counts[3].astype(np.uint32).sum(axis=1)
+    ctx.mat_put_sample(3, counts[3], totals[3])
+    D, N, dn, rows = ctx.mat_run(None, method="nchi2", min_depth=30)
+    Do, No, dno = oracle.mat_matrix(counts, totals, lens, None, method="nchi2", min_depth=30)
+    assert np.array_equal(N, No) and close(D, Do)
+
+
+# ---- position split over several GPUs (members on the devices that exist; all on GPU 0 on a 1-GPU box) ----
+@pytest.mark.parametrize("members", [2, 3])
+@pytest.mark.parametrize("method", ["cos", "chi2", "nl2"])
+def test_position_split_over_members(built, monkeypatch, members, method):
+    import torch
+    ngpu = max(torch.cuda.device_count(), 1)
+    monkeypatch.setenv("CCG_MULTI_FORCE", "1")
+    n, length = 70, 3000 + 7
+    counts, totals = random_counts(n, length, seed=31 + members)
+    lens = np.full(n, length, np.int32)
+    lens[5], lens[40] = 1500, 2999                          # shorter instances of the template: some members hold none of 5's tail
+    include = np.ones(n, np.uint8)
+    include[11] = 0
+    c = api.Context(multi=[g % ngpu for g in range(members)])
+    try:
+        c.mat_set_problem(n, length)
+        for i in range(n):
+            c.mat_put_sample(i, counts[i, :lens[i]], totals[i, :lens[i]])
+        for kw in (dict(norm=0), dict(norm=1000, min_depth=20, min_cov=0.4)):
+            D, N, dn, rows = c.mat_run(include, method=method, **kw)
+            cz = counts.copy()
+            for i in range(n):
+                cz[i, lens[i]:] = 0
+            Do, No, dno = oracle.mat_matrix(cz, cz.astype(np.uint32).sum(axis=2).astype(np.uint32), lens, include, method=method, **kw)
+            assert dn == dno == n - 1
+            assert np.array_equal(N, No) and np.array_equal(rows, No.astype(np.uint32))
+            assert close(D, Do)
+        assert "position split" in c.last_kernel and c.multi_gpus()[0] == members
+    finally:
+        c.close()
+
+
+def test_partial_sums_and_host_epilogue(ctx):
+    # what a rank of a one-process-per-GPU position split does: raw sums from the device, the tail of cmpMats on the host
+    import ctypes as C
+    n, length = 33, 1200
+    counts, totals = random_counts(n, length, seed=3, low=0.2)
+    lens = np.full(n, length, np.int32)
+    include = np.ones(n, np.uint8)
+    include[0] = 0
+    ctx.mat_set_problem(n, length)
+    for i in range(n):
+        ctx.mat_put_sample(i, counts[i], totals[i])
+    L = api.load()
+    cells = api.cells(n - 1)
+    for elem, scale in ((8, 1.0), (4, 1.0), (2, 100.0)):
+        D, N, dn, rows = ctx.mat_run(include, method="cos", norm=1000, min_cov=0.6, elem_size=elem, byte_scale=scale)
+        dist = np.zeros(cells, np.float64)
+        rr = np.zeros(cells, np.uint32)
+        dnp = C.c_int(0)
+        mid, order = api.mat_method("cos")
+        assert L.ccg_mat_run_partial(ctx._h, include.ctypes.data, mid, order, 0.05, 15, dist.ctypes.data, rr.ctypes.data, C.byref(dnp)) == 0
+        D2 = np.zeros(cells, api.ELEM_DTYPE[elem])
+        N2 = np.zeros(cells, api.ELEM_DTYPE[elem])
+        r2 = np.zeros(cells, np.uint32)
+        assert L.ccg_mat_finalize_host(n, include.ctypes.data, lens.ctypes.data, dist.ctypes.data, rr.ctypes.data, 1000, 1, 0.6, elem, scale,
+                                       D2.ctypes.data, N2.ctypes.data, r2.ctypes.data, None) == 0
+        assert dnp.value == dn and np.array_equal(D2.view(np.uint8), D.view(np.uint8)) and np.array_equal(N2, N) and np.array_equal(r2, rows)
