@@ -127,6 +127,7 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 		if(cudaMalloc(&ctx->d_resident, sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); ctx->d_resident = 0; }
 	}
 	/* tuning knobs for experiments (scripts/one_step.py); unset in normal use */
+	ctx->watchdog_cycles = getenv("CCG_WATCHDOG_S") ? (long long) (atof(getenv("CCG_WATCHDOG_S")) * 2.0e9) : 4000000000LL;
 	if(getenv("CCG_KSLICES")) ctx->dbg_kslices = atoi(getenv("CCG_KSLICES"));
 	if(getenv("CCG_EXPAND_SERIAL")) ctx->dbg_serial = atoi(getenv("CCG_EXPAND_SERIAL"));
 	if(getenv("CCG_NOLOCK")) ctx->dbg_nolock = atoi(getenv("CCG_NOLOCK"));
@@ -528,6 +529,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 		ctx->global_inc = 0;
 		ctx->global_applied = 0;
 		ctx->global_pending = 0;
+		ctx->remask_pending = 0;
 		ctx->last_Dn = 0;
 		ctx->last_ntiles = 0;
 		return CCG_OK;
@@ -564,6 +566,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	update_need(ctx);
 	ctx->global_applied = 0;
 	ctx->global_pending = 0;
+	ctx->remask_pending = 0;
 	ctx->global_inc = 0;
 	return make_planes_tmap(ctx);
 }
@@ -1504,6 +1507,11 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 			return CCG_ERR_ARG;
 		}
 	}
+	if(ctx->remask_pending) {
+		/* -y: the code planes still hold the bases of the methylation sites (k_motif.cu) */
+		CK(ctx, ccg_launch_remask_all(ctx));
+		ctx->remask_pending = 0;
+	}
 	if(mode == 1 && ctx->global_pending) {
 		CK(ctx, ccg_launch_apply_global_mask(ctx));
 		ctx->global_pending = 0;
@@ -1774,6 +1782,10 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
 			return CCG_ERR_NOMEM;
 		}
 		ctx->out_bytes = bytes;
+	}
+	if(ctx->remask_pending) {
+		CK(ctx, ccg_launch_remask_all(ctx));
+		ctx->remask_pending = 0;
 	}
 	if(ctx->proxi && ctx->words > 0) {
 		/* -P: the pair's mask is the new sample's own mask after ITS builder (fsacmpthrd.c:627-628), then the

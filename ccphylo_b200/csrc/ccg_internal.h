@@ -97,6 +97,7 @@ struct UmmaParams {
 	int no_mask_items;     /* e2m1 panel, shared-mask mode: the inclusion count is a constant, no I items */
 	int fp4;               /* e2m1 panel (kind::mxf4): slab_chunks / chunks_per_slice count chunk PAIRS, S and I are separate items */
 	int single;            /* tiles are 128 x 256 and run on the single-CTA kernel (CCG_UMMA1=1, experiments) */
+	long long watchdog;    /* cycles an mbarrier wait may take before the kernel traps; 0 = no limit (set by ccg_launch_umma) */
 };
 
 /* ---- K-split group: every member GPU owns a slice of the alignment (all samples, 1/world of the bases), runs
@@ -140,11 +141,13 @@ struct ccg_ctx {
 	int win_on, win[4];            /* macro-tile window [tm_lo, tm_hi) x [tn_lo, tn_hi), ccg_set_tile_window */
 	int min_slabs;                  /* cut the K axis into at least this many slabs (expansion overlapped with the GEMM) */
 	int use_i8;                     /* CCG_I8=1: int8 operands (kind::i8) instead of the default e2m1 panel (kind::mxf4) */
+	long long watchdog_cycles;      /* CCG_WATCHDOG_S (default 2 s at 2 GHz; 0 = off, for profiler replays) */
 	int dbg_kslices, dbg_serial, dbg_nolock, dbg_umma1;   /* CCG_KSLICES / CCG_EXPAND_SERIAL / CCG_NOLOCK / CCG_UMMA1 overrides (experiments only) */
 
 	int motif_n, motif_nsets;       /* -y: motifs (with their reverse complements) set by ccg_set_motifs */
 	int *d_motif_lens;
 	unsigned char *d_motif_sets;
+	int remask_pending;             /* -y: mask planes changed by ccg_mask_motifs, code planes not yet re-masked (done before a run) */
 	int row_slot1;                  /* ccg_run_row: 1 + the slot whose row is being computed, 0 otherwise */
 	unsigned proxi;                 /* -P: minimum distance between SNPs (0 = no proximity masking), ccg_set_proximity */
 	int proxi_snp_only;             /* events of the per-sample builder: 0 getIncPos, 1 getIncPosInsig / getIncPosInsigPrune */
@@ -289,6 +292,7 @@ cudaError_t ccg_launch_row_proxi(ccg_ctx *ctx, int row_slot, const void *d_rowra
 
 /* k_motif.cu */
 cudaError_t ccg_launch_motif_mask(ccg_ctx *ctx, int first, int count, unsigned *d_removed);
+cudaError_t ccg_launch_remask_all(ccg_ctx *ctx);
 
 /* k_variants.cu */
 cudaError_t ccg_launch_variants(ccg_ctx *ctx, const VariantParams &p, int write, int shared_mask);

@@ -11,7 +11,7 @@
  * and the bits to clear are OR over the upper-case positions k of (starts >> k), which run over into the next
  * word.  One thread owns one 16-byte plane word (4 x 32 bases) of one sample: it evaluates the five 32-base words
  * whose matches can reach into it and rewrites its word of the MASK plane only; the code planes, which every
- * neighbour is reading, are re-masked by a second, element-wise kernel.  Lanes of a warp are neighbouring samples
+ * neighbour is reading, are re-masked later by an element-wise kernel (k_remask_all, before the first run).  Lanes of a warp are neighbouring samples
  * (coalesced 512 B rows).  HBM-bound: 3 x 32 B read + 16 B written per sample and 128 bases.
  */
 #include "ccg_internal.h"
@@ -105,23 +105,28 @@ k_motif_mask(uint32_t *planes, int n_pad, int chunks, long long len, int first, 
 	if(gone_all) atomicAdd(removed + s, gone_all);
 }
 
-/* code planes &= mask plane, included counts -= removed */
+/* included counts -= removed.  The CODE planes keep the bases of the methylation sites for now: the reference changes
+ * only the inclusion mask (maskMotif meth.c:127-139), and what still looks at the sequences afterwards -- the variant
+ * listing of -V (fsacmpairint / fsacmprint compare whole packed words) -- must see them unchanged.  The compare
+ * kernels want code planes that are zero wherever the mask is: k_remask_all does that right before the first run. */
 __global__ void __launch_bounds__(128)
-k_motif_remask(uint32_t *planes, int n_pad, int chunks, int first, int count, const unsigned *__restrict__ removed,
-               unsigned *__restrict__ inc) {
-	const int s = blockIdx.x * 32 + threadIdx.x;
-	if(s >= count || removed[s] == 0) return;
-	const int slot = first + s;
+k_motif_counts(int first, int count, const unsigned *__restrict__ removed, unsigned *__restrict__ inc) {
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if(s < count && removed[s]) inc[first + s] -= removed[s];
+}
+
+__global__ void __launch_bounds__(256)
+k_remask_all(uint32_t *planes, int n_pad, int chunks) {
 	uint4 *P = reinterpret_cast<uint4 *>(planes);
-	for(int ch = blockIdx.y * blockDim.y + threadIdx.y; ch < chunks; ch += gridDim.y * blockDim.y) {
+	const long long total = (long long) chunks * n_pad;
+	for(long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
+		const long long ch = e / n_pad, slot = e % n_pad;
 		const size_t row = (size_t) ch * 3;
 		const uint4 m = P[(row + 2) * n_pad + slot];
 		uint4 h = P[(row + 0) * n_pad + slot], l = P[(row + 1) * n_pad + slot];
-		h.x &= m.x; h.y &= m.y; h.z &= m.z; h.w &= m.w;
-		l.x &= m.x; l.y &= m.y; l.z &= m.z; l.w &= m.w;
-		P[(row + 0) * n_pad + slot] = h;
-		P[(row + 1) * n_pad + slot] = l;
-		if(ch == 0) inc[slot] -= removed[s];
+		const uint4 h2 = make_uint4(h.x & m.x, h.y & m.y, h.z & m.z, h.w & m.w), l2 = make_uint4(l.x & m.x, l.y & m.y, l.z & m.z, l.w & m.w);
+		if(h2.x != h.x || h2.y != h.y || h2.z != h.z || h2.w != h.w) P[(row + 0) * n_pad + slot] = h2;
+		if(l2.x != l.x || l2.y != l.y || l2.z != l.z || l2.w != l.w) P[(row + 1) * n_pad + slot] = l2;
 	}
 }
 
@@ -138,7 +143,16 @@ cudaError_t ccg_launch_motif_mask(ccg_ctx *ctx, int first, int count, unsigned *
 	ctx->launches++;
 	cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return e;
-	k_motif_remask<<<grid, block, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks, first, count, d_removed, ctx->d_inc);
+	k_motif_counts<<<(unsigned) ((count + 127) / 128), 128, 0, ctx->stream>>>(first, count, d_removed, ctx->d_inc);
+	ctx->launches++;
+	ctx->remask_pending = 1;
+	return cudaGetLastError();
+}
+
+/* code planes &= mask plane over the whole (three-plane) store: before the first run after ccg_mask_motifs */
+cudaError_t ccg_launch_remask_all(ccg_ctx *ctx) {
+	if(ctx->nplanes != 3 || ctx->words == 0) return cudaSuccess;
+	k_remask_all<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks);
 	ctx->launches++;
 	return cudaGetLastError();
 }

@@ -67,14 +67,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, unsigned parity) {
 	    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 	return ok != 0;
 }
-/* bounded wait: a lost completion traps (reported as a CUDA error) instead of hanging the GPU */
-__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
+/* bounded wait: a lost completion traps (reported as a CUDA error) instead of hanging the GPU.  limit = cycles
+ * (UmmaParams::watchdog: ~2 s by default, far beyond any legitimate wait in these kernels; 0 = wait for ever, which
+ * is what a profiler's kernel replay needs -- CCG_WATCHDOG_S=0) */
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity, long long limit) {
 	if(mbar_try_wait(bar, parity)) return;
 	const long long t0 = clock64();
 	unsigned spins = 0;
 	while(!mbar_try_wait(bar, parity)) {
-		/* watchdog: ~2 s at 2 GHz, far beyond any legitimate wait in these kernels */
-		if((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+		if((++spins & 1023u) == 0 && limit > 0 && clock64() - t0 > limit) __trap();
 	}
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
@@ -313,7 +314,7 @@ k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 						}
 					}
 					const int s = it % STAGES;
-					if(it >= STAGES) mbar_wait(bar_empty + 8 * s, ((it / STAGES) - 1) & 1);
+					if(it >= STAGES) mbar_wait(bar_empty + 8 * s, ((it / STAGES) - 1) & 1, p.watchdog);
 					const uint32_t dst = base + s * STAGE_BYTES;
 					const uint32_t bar = bar_full + 8 * s;
 					/* row coordinate of the 128-row box of row block rb, k-block kabs in the blocked panel */
@@ -341,13 +342,13 @@ k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 				if(nchunk < 0) nchunk = 0;
 				const int nkb = nchunk * 4;
 				if(round > 0) {
-					mbar_wait(bar_tfree, (round - 1) & 1);           /* the previous item's accumulators were read */
+					mbar_wait(bar_tfree, (round - 1) & 1, p.watchdog);           /* the previous item's accumulators were read */
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				}
 				uint32_t usedS = 0, usedI = 0;
 				for(int kb = 0; kb < nkb; ++kb, ++it) {
 					const int s = it % STAGES;
-					mbar_wait(bar_full + 8 * s, (it / STAGES) & 1);
+					mbar_wait(bar_full + 8 * s, (it / STAGES) & 1, p.watchdog);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 					const uint32_t a0 = base + s * STAGE_BYTES;
 					const uint64_t adesc = make_desc(a0);
@@ -375,7 +376,7 @@ k_pairdist_umma(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 			const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
 			const int nleft = p.slab_chunks - ks * p.chunks_per_slice;
 			const int row = tm * BM + quarter * 32 + lane;
-			mbar_wait(bar_accum, round & 1);
+			mbar_wait(bar_accum, round & 1, p.watchdog);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			if(nleft > 0) {
 				int *cS = p.C_S + (size_t) row * p.ldc + tn * BN;
@@ -547,7 +548,7 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 						}
 					}
 					const int s = it % STAGES2;
-					if(it >= STAGES2) mbar_wait(bar_empty + 8 * s, ((it / STAGES2) - 1) & 1);
+					if(it >= STAGES2) mbar_wait(bar_empty + 8 * s, ((it / STAGES2) - 1) & 1, p.watchdog);
 					const uint32_t dst = base + s * STAGE2_BYTES;
 					const uint32_t bar = (bar_full + 8 * s) & PEER_MASK;      /* the leader's barrier */
 					/* k-block of this stage inside the slab: 4 per chunk (pair), channel-minor */
@@ -574,13 +575,13 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 				if(nchunk < 0) nchunk = 0;
 				const int nkb = FP4 ? (which ? nchunk : 3 * nchunk) : nchunk * 4;
 				if(round > 0) {
-					mbar_wait(bar_tfree, (round - 1) & 1);
+					mbar_wait(bar_tfree, (round - 1) & 1, p.watchdog);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				}
 				uint32_t usedS = 0, usedI = 0;
 				for(int kb = 0; kb < nkb; ++kb, ++it) {
 					const int s = it % STAGES2;
-					mbar_wait(bar_full + 8 * s, (it / STAGES2) & 1);
+					mbar_wait(bar_full + 8 * s, (it / STAGES2) & 1, p.watchdog);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 					const uint32_t a0 = base + s * STAGE2_BYTES;
 					const uint64_t adesc = make_desc(a0);
@@ -618,7 +619,7 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 			const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
 			const int nleft = p.slab_chunks - ks * p.chunks_per_slice;
 			const int row = tm * BMT + (int) cta_rank * 128 + quarter * 32 + lane;
-			mbar_wait(bar_accum, round & 1);
+			mbar_wait(bar_accum, round & 1, p.watchdog);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			if(nleft > 0) {
 				int *cS = p.C_S + (size_t) row * p.ldc + tn * BN;
@@ -788,6 +789,7 @@ cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p_in) {
 	e = cudaFuncSetAttribute(k_pairdist_umma2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
 	if(e != cudaSuccess) return e;
 	UmmaParams p = p_in;
+	p.watchdog = ctx->watchdog_cycles;
 	const long long items = (long long) p.ntiles * p.kslices * ((p.fp4 && !p.no_mask_items) ? 2 : 1);
 	if(items <= 0) return cudaSuccess;
 	const int slots = p.single ? ctx->sm_count : ccg_umma_pair_slots(ctx);   /* CTAs or CTA pairs */

@@ -16,7 +16,7 @@
  *   - -V (variant listing) comes from the device as well (ccg_list_variants, same labels as the reference);
  *     -a appends one row to an existing matrix (ccg_run_row / ccg_mat_run_row);
  *   - -y masks methylation motifs on the device right after each upload (ccg_mask_motifs);
- *   - refused: the combinations -V with -P or -y; -y with -P (-a ignores -y, as the reference does).
+ *   - refused: -V with -P; -y with -P in shared-mask mode (-a ignores -y, as the reference does).
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -139,11 +139,15 @@ static MotifList g_motifs;
 
 /* one sample into its slot: the device packs it, builds its mask and -- with -y -- takes the methylation sites
  * of every motif match out of it (maskMotifs, cdist.c:90,109,137) */
-static void upload_sample(ccg_ctx *ctx, int slot, const ByteBuf *codes, unsigned *inc) {
+static void upload_sample(ccg_ctx *ctx, int slot, const ByteBuf *codes, unsigned *inc, int proxi_apply) {
 	int rc = ccg_put_sample_codes(ctx, slot, codes->data);
 	/* the staging copy is asynchronous and the parser's buffer is about to be reused */
 	if(!rc) rc = ccg_sync(ctx);
-	if(!rc && (g_motifs.n || inc)) rc = ccg_mask_motifs(ctx, slot, 1, inc);
+	/* -P in pair mode: getIncPosPtr(includes[i], seq, seq, proxi) (cdist.c:91) only CLEARS mask bits, and which ones
+	 * depends on the sequence alone -- so it commutes with maskMotifs (cdist.c:90), and it runs first here because the
+	 * device finds the unknown positions in the still pristine mask */
+	if(!rc && proxi_apply) rc = ccg_sample_proximity(ctx, slot, 1, 1, inc);
+	if(!rc && (g_motifs.n || (inc && !proxi_apply))) rc = ccg_mask_motifs(ctx, slot, 1, inc);
 	if(rc) die_gpu(ctx, rc);
 }
 
@@ -161,10 +165,11 @@ static unsigned candidate_count(const DistOpts *o, ccg_ctx *ctx, int slot, const
 	if((!proxi_counts && !g_motifs.n) || len <= 0) return known;
 	if(!pair && !is_ref_candidate) return known;
 	unsigned inc = 0;
-	upload_sample(ctx, slot, codes, &inc);
+	upload_sample(ctx, slot, codes, &inc, proxi_counts && pair);
 	*uploaded = 1;
-	if(proxi_counts) {
-		int rc = ccg_sample_proximity(ctx, slot, 1, pair, &inc);
+	if(proxi_counts && !pair) {
+		/* the shared-mask reference candidate: its ranges are only counted here, ccg_build_global_mask clears them */
+		int rc = ccg_sample_proximity(ctx, slot, 1, 0, &inc);
 		if(rc) die_gpu(ctx, rc);
 	}
 	return inc;
@@ -325,7 +330,7 @@ static void dist_fasta_files(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 				} else {
 					fprintf(stderr, "# Included:\t%s\t( %d / %d )\n", path, (int) inc, len);
 					have_ref = 1;
-					if(len > 0 && !uploaded) upload_sample(ctx, i, &r->codes, 0);
+					if(len > 0 && !uploaded) upload_sample(ctx, i, &r->codes, 0, 0);
 				}
 			}
 		}
@@ -491,7 +496,7 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 			have_ref = 1;
 			names[n] = strdup(name);
 			if(!names[n]) die_errno();
-			if(len > 0 && !uploaded) upload_sample(ctx, n, &r->codes, 0);
+			if(len > 0 && !uploaded) upload_sample(ctx, n, &r->codes, 0, 0);
 			++n;
 		}
 		if(parallel) pool_release(pool, job);
@@ -879,11 +884,13 @@ int main_dist(int argc, char **argv) {
 	if(dist_mat_parse_method(&o)) die_invalid(o.method_err);
 	if(!o.numFile && o.targetTemplate) o.numFile = 1;
 
-	if((o.methfilename && !o.addfilename && (o.proxi || o.diffilename)) || (o.diffilename && o.proxi)) {
+	/* -y with -P: in pair mode (-f bit 2) the two maskings commute and both run on the device; the shared mask of the
+	 * default mode is built from per-sample masks there, where a motif site would read as an unknown base */
+	if((o.methfilename && !o.addfilename && o.proxi && !(o.flag & 2)) || (o.diffilename && o.proxi)) {
 		fprintf(stderr, "%s is not available on the GPU path of dist (use the CPU ccphylo for it).\n",
-		        (o.methfilename && !o.addfilename) ? (o.proxi ? "-y / --methylation_motifs together with -P / --proximity" :
-		                                    "-y / --methylation_motifs together with -V / --nucleotide_variations") :
-		                                   "-V / --nucleotide_variations together with -P / --proximity");
+		        (o.methfilename && !o.addfilename && o.proxi && !(o.flag & 2)) ?
+		        "-y / --methylation_motifs together with -P / --proximity without pairwise inclusion (-f 2)" :
+		        "-V / --nucleotide_variations together with -P / --proximity");
 		return 1;
 	}
 	if(o.addfilename && o.filenames) return add_to_matrix(&o);

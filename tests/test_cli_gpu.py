@@ -315,3 +315,48 @@ def test_msa_on_several_gpus_is_byte_identical_to_one(built, tmp_path, flag):
         outs[members] = (open(phy).read(), open(num).read(), text)
     assert outs[1][0].count("\n") >= n and "# Excluded:\tsmp17" in outs[1][2]
     assert outs[2] == outs[1] and outs[5] == outs[1]
+
+
+# ---- the pipe the north star names: ccphylo union | ccphylo dist | ccphylo tree, with OUR dist in the middle ----
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ccphylo")
+NEWICK_C9 = "((a.mat.gz:0.003971940,d.mat.gz:1.000283475):0.991239454,c.mat.gz:0.965967545,b.mat.gz:0.011964387);"
+
+
+def _write_c8_inputs(td):
+    """SURVEY App. C #8 / #9: four KMA count matrices of template `tmpl` (reference (ACGT)x5) and their .res files"""
+    ref = "ACGT" * 5
+    spec = {"a": (30, {}), "b": (40, {3: "A"}), "c": (25, {3: "A", 10: "T", 11: "N"}), "d": (20, {0: "-", 5: "C"})}
+    hdr = ("#Template\tScore\tExpected\tTemplate_length\tTemplate_Identity\tTemplate_Coverage\tQuery_Identity\tQuery_Coverage\t"
+           "Depth\tq_value\tp_value\n")
+    for name, (depth, variants) in spec.items():
+        rows = []
+        for p, r in enumerate(ref):
+            b = variants.get(p, r)
+            c = [0] * 6
+            c["ACGTN-".index(b)] = depth
+            if b in "ACGT":
+                c[("ACGT".index(b) + 1) % 4] += p % 3
+            rows.append(r + "\t" + "\t".join(map(str, c)))
+        with gzip.open(os.path.join(td, name + ".mat.gz"), "wt") as f:
+            f.write("#tmpl\n" + "\n".join(rows) + "\n\n")
+        with open(os.path.join(td, name + ".res"), "w") as f:
+            f.write(hdr + "tmpl\t1000\t10\t20\t100.00\t100.00\t100.00\t100.00\t%d.00\t500.00\t1.0e-26\n" % depth)
+    return [name + ".res" for name in spec]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
+def test_union_dist_tree_pipe_with_the_gpu_dist_in_the_middle(built, tmp_path):
+    td = str(tmp_path)
+    res = _write_c8_inputs(td)
+    union = subprocess.run([REF_BIN, "union", "-i"] + res, capture_output=True, cwd=td, timeout=60)
+    assert union.returncode == 0 and union.stdout.startswith(b"4\ta.res")
+    trees = {}
+    for who, binary in (("reference", REF_BIN), ("gpu", BIN)):
+        dist = subprocess.run([binary, "dist", "-f", "5"], input=union.stdout, capture_output=True, cwd=td, timeout=300)
+        assert dist.returncode == 0, dist.stderr.decode()[-1000:]
+        tree = subprocess.run([REF_BIN, "tree"], input=dist.stdout, capture_output=True, cwd=td, timeout=60)
+        assert tree.returncode == 0, tree.stderr.decode()[-1000:]
+        trees[who] = (dist.stdout.decode(), tree.stdout.decode())
+    assert trees["reference"][1].strip() == ">tmpl" + NEWICK_C9           # SURVEY App. C #9
+    assert trees["gpu"][1] == trees["reference"][1]                       # the same Newick through our dist
+    assert trees["gpu"][0] == trees["reference"][0]                       # and the same Phylip text in between

@@ -109,3 +109,66 @@ def test_cli_motif_masking_against_the_reference_binary(built, tmp_path, msa, fl
     plain = _run([REF_BIN, "dist", "-f", flag, "-W", "1000", "-o", os.path.join(td, "plain.phy")] + inputs, td)
     assert open(os.path.join(td, "plain.phy")).read() != outs["reference"][0] or plain.stderr != outs["reference"][2]
     assert outs["driver"] == outs["reference"]
+
+
+# ---- -y together with -V and with -P: the reference runs them, so does the driver ----
+def _inputs(td, msa, rows):
+    n, length = rows.shape
+    if msa:
+        path = os.path.join(td, "aln.fsa")
+        with open(path, "wb") as f:
+            for i in range(n):
+                f.write(b">s%d\n" % i)
+                for s0 in range(0, length, 60):
+                    f.write(rows[i, s0:s0 + 60].tobytes() + b"\n")
+        return ["-i", path]
+    files = []
+    for i in range(n):
+        fp = os.path.join(td, f"s{i:02d}.fsa")
+        synth.write_fasta(fp, rows[i], header="ref", width=60)
+        files.append(fp)
+    return ["-r", "ref", "-i"] + files
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
+@pytest.mark.parametrize("flag", ["3", "1"], ids=["pair", "shared-mask"])
+@pytest.mark.parametrize("msa", [False, True], ids=["files", "msa"])
+def test_cli_motifs_with_variant_listing(built, tmp_path, msa, flag):
+    # maskMotifs changes the inclusion masks only; fsacmpairint / fsacmprint then compare the UNCHANGED packed words
+    # (fsacmp.c:646-737): the device keeps the code planes untouched until the listing is done
+    td = str(tmp_path)
+    n, length = 9, 6000 + 11
+    rows = synth.make_ascii(n, length, seed=17, snp=0.01, nrun=0.004)
+    mot = os.path.join(td, "motifs.fsa")
+    with open(mot, "w") as f:
+        f.write(CLI_FILES[0])
+    inputs = _inputs(td, msa, rows)
+    outs = {}
+    for tag, exe in (("reference", REF_BIN), ("driver", BIN)):
+        phy, num, var = (os.path.join(td, tag + ext) for ext in (".phy", ".num", ".var"))
+        p = _run([exe, "dist", "-f", flag, "-y", mot, "-V", var, "-W", "1000", "-t", "1", "-o", phy, "-n", num] + inputs, td)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[tag] = (open(phy).read(), open(num).read(), open(var).read(), p.stderr)
+    assert len(outs["reference"][2]) > 100
+    assert outs["driver"] == outs["reference"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
+@pytest.mark.parametrize("flag,proxi", [("3", "7"), ("3", "40"), ("11", "12"), ("35", "9")])
+@pytest.mark.parametrize("msa", [False, True], ids=["files", "msa"])
+def test_cli_motifs_with_proximity_in_pair_mode(built, tmp_path, msa, flag, proxi):
+    # cdist.c:90-91: maskMotifs, then getIncPosPtr(includes[i], seq, seq, proxi); both only clear mask bits
+    td = str(tmp_path)
+    n, length = 9, 6000 + 11
+    rows = synth.make_ascii(n, length, seed=23, snp=0.02, nrun=0.01, gap=0.004)
+    mot = os.path.join(td, "motifs.fsa")
+    with open(mot, "w") as f:
+        f.write(CLI_FILES[0])
+    inputs = _inputs(td, msa, rows)
+    outs = {}
+    for tag, exe in (("reference", REF_BIN), ("driver", BIN)):
+        phy, num = os.path.join(td, tag + ".phy"), os.path.join(td, tag + ".num")
+        p = _run([exe, "dist", "-f", flag, "-y", mot, "-P", proxi, "-W", "1000", "-t", "2", "-o", phy, "-n", num] + inputs, td)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[tag] = (open(phy).read(), open(num).read(), p.stderr)
+    assert outs["driver"] == outs["reference"]
