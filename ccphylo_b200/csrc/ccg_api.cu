@@ -1227,7 +1227,9 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		long long want = (ctx->chunks + feed_slabs - 1) / feed_slabs;
 		/* the GEMM of the LAST slab is the tail nothing hides: a short alignment (a member's slice of a K-split group)
 		 * is cut finer -- down to 512 chunks, where a slab's GEMM is still ~1 ms of full waves */
-		if(want < 512) want = 512;
+		long long floor_chunks = ctx->stream_min_chunks / 2 < 512 ? ctx->stream_min_chunks / 2 : 512;
+		if(floor_chunks < 16) floor_chunks = 16;
+		if(want < floor_chunks) want = floor_chunks;
 		const long long cap = ctx->x_bytes >= 2 * ctx->x_buf_bytes ? ctx->x_chunks : ctx->x_chunks / 2;
 		if(want < slab && cap >= 1) slab = want < cap ? want : cap;
 		if(fp4 && (slab & 1)) slab = slab > 1 ? slab - 1 : 2;

@@ -85,6 +85,7 @@ __global__ void k_group_barrier(GroupBarrierParams q) {
 	__threadfence_system();
 	q.hdr[t]->iconst_from[q.buf][q.rank] = q.i_const;
 	st_release_sys(&q.hdr[t]->arrive[q.rank], q.epoch);
+	if(!q.spin) return;             /* members sharing one device meet on the host instead (ccg_group_finalize) */
 	const unsigned *mine = &q.hdr[q.rank]->arrive[t];
 	const unsigned long long t0 = global_ns();
 	while((int) (ld_acquire_sys(mine) - q.epoch) < 0) {
@@ -278,6 +279,7 @@ extern "C" int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *han
 		ctx->grp_win[p] = 0;
 	}
 	const int me = (int) getpid();
+	ctx->grp_same_device = 0;
 	int npad_min = ctx->grp_npad_max;
 	size_t bytes_min = ctx->grp_win_bytes;
 	for(int p = 0; p < world; ++p) {
@@ -324,6 +326,29 @@ extern "C" int ccg_group_join(ccg_ctx *ctx, int rank, int world, const void *han
 			ctx->grp_opened[p] = 1;
 		}
 	}
+	/* two members on one device (single-GPU tests): then EVERY member of the group synchronises on the host */
+	for(int p = 0; p < world; ++p)
+		for(int q = p + 1; q < world; ++q) {
+			GroupHandle a, b;
+			memcpy(&a, (const char *) handles + (size_t) p * CCG_GROUP_HANDLE_BYTES, sizeof(a));
+			memcpy(&b, (const char *) handles + (size_t) q * CCG_GROUP_HANDLE_BYTES, sizeof(b));
+			if(a.pid == b.pid && a.device == b.device) {
+				if(a.pid != me) {
+					ccg_set_err(ctx, "members %d and %d of the group share a device of another process", p, q);
+					return CCG_ERR_UNSUPPORTED;
+				}
+				ctx->grp_same_device = 1;
+			}
+		}
+	if(ctx->grp_same_device)
+		for(int p = 0; p < world; ++p) {
+			GroupHandle a;
+			memcpy(&a, (const char *) handles + (size_t) p * CCG_GROUP_HANDLE_BYTES, sizeof(a));
+			if(a.pid != me) {
+				ccg_set_err(ctx, "a group with two members on one device must live in one process");
+				return CCG_ERR_UNSUPPORTED;
+			}
+		}
 	ctx->grp_npad_max = npad_min < ctx->grp_npad_max ? npad_min : ctx->grp_npad_max;
 	ctx->grp_acc_bytes = bytes_min - CCG_GROUP_HDR_BYTES;      /* every member lays its buffers out the same way */
 	ctx->grp_rank = rank;
@@ -389,10 +414,15 @@ int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const, int 
 	b.buf = ctx->grp_buf;
 	b.i_const = i_const;
 	b.epoch = ++ctx->grp_epoch;
+	b.spin = ctx->grp_same_device ? 0 : 1;
 	b.timeout_ns = (unsigned long long) (getenv("CCG_GROUP_TIMEOUT_S") ? atof(getenv("CCG_GROUP_TIMEOUT_S")) : 120.0) * 1000000000ull;
 	k_group_barrier<<<1, 32, 0, ctx->stream>>>(b);
 	ctx->launches++;
 	CKG(ctx, cudaGetLastError());
+	/* Members that share ONE device (the single-GPU tests) must not wait for each other in spinning kernels -- nothing
+	 * guarantees that two kernels of one device run at the same time: there the kernel above only publishes, every
+	 * member drains its own stream, and the barrier is the host rendezvous below. */
+	if(ctx->grp_same_device) CKG(ctx, cudaStreamSynchronize(ctx->stream));
 	/* ... and once more after it: a host call that blocks until this stream has drained (a copy into pageable host
 	 * memory, say) may hold the driver while it waits; by then every member's barrier kernel must be in its queue */
 	if(ctx->grp_host_barrier && host_barrier_wait((HostBarrier *) ctx->grp_host_barrier)) {

@@ -116,6 +116,7 @@ struct GroupBarrierParams {
 	GroupHeader *hdr[CCG_GROUP_MAX];
 	int rank, world, buf, i_const;
 	unsigned epoch;
+	int spin;                               /* 0: publish only (members on one device synchronise on the host) */
 	unsigned long long timeout_ns;
 };
 
@@ -244,6 +245,7 @@ struct ccg_ctx {
 	int grp_compact;                       /* ccg_group_set_output: D / N of the run calls hold only this member's rows */
 	const long long *ep_row_base;          /* what the next run's epilogue uses as EpilogueParams::row_base */
 	struct ccg_multi *multi;               /* leader of an in-process multi-GPU context (ccg_init_multi) */
+	int grp_same_device;                   /* another member of this process sits on the same device: host-side barrier */
 	void *grp_host_barrier;                /* members of one process: host rendezvous before the device barrier (ccg_group.cu) */
 
 	cudaEvent_t ev0, ev1;
