@@ -238,6 +238,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--parity-samples", type=int, default=128)
+    ap.add_argument("--copy-rows", action="store_true", help="device-resident arm: ccg_put_samples_packed_dev (copy into the "
+                    "bit-plane store) instead of lending the rows")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -313,7 +315,12 @@ def main():
     total_basecmp = float(ncell) * length
 
     def step():
-        ctx.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
+        # the packed rows stay where they are in HBM: the library is lent them and expands its operands straight from
+        # the reference's words (ccg_put_samples_packed_dev_borrowed); --copy-rows takes the copying upload instead
+        if args.copy_rows:
+            ctx.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
+        else:
+            ctx.put_samples_packed_dev_borrowed(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
         ctx.run_pair_dev(d_D.data_ptr(), d_N.data_ptr(), norm=0, min_length=1, min_cov=0.5, elem_size=8)
 
     def barrier():
@@ -569,7 +576,9 @@ def main():
                                      f"pointers over NVLink inside the epilogue kernel (no NCCL collective on the data path)"),
                        "l2": "inputs (%.2f GB of planes per GPU) larger than the 126 MB L2; no explicit flush" %
                              (n * W * 12 / 1e9),
-                       "step": "encode (packed words -> bit planes) + compare + fused epilogue"},
+                       "step": ("encode (packed words -> bit planes) + operand expansion + compare + epilogue" if args.copy_rows else
+                                "operand expansion straight from the resident packed words (rows lent to the library) + compare + "
+                                "epilogue")},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "parity_vs_oracle": parity,
             "parity_cells_checked": int(len(cell_idx)), "parity_tiles_hit": int(tiles_hit),

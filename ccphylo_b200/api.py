@@ -24,7 +24,7 @@ EXPORTS = [
     "ccg_set_partition", "ccg_set_tile_window", "ccg_tile_rows", "ccg_tile_cols", "ccg_partition_cells", "ccg_partition_tiles",
     "ccg_set_scratch_limit", "ccg_set_problem", "ccg_put_global_mask", "ccg_apply_global_mask", "ccg_build_global_mask",
     "ccg_put_samples_packed",
-    "ccg_put_samples_packed_dev", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
+    "ccg_put_samples_packed_dev", "ccg_put_samples_packed_dev_borrowed", "ccg_put_sample_codes", "ccg_get_inc_counts", "ccg_run_pair", "ccg_run_global",
     "ccg_run_pair_dev", "ccg_run_global_dev", "ccg_get_raw_counts", "ccg_fsa_cmp_thread_out", "ccg_host_alloc",
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
@@ -98,6 +98,7 @@ def load():
     L.ccg_build_global_mask.argtypes = [vp, vp, vp]
     L.ccg_put_samples_packed.argtypes = [vp, i, i, vp, vp]
     L.ccg_put_samples_packed_dev.argtypes = [vp, i, i, vp, vp, C.c_long]
+    L.ccg_put_samples_packed_dev_borrowed.argtypes = [vp, i, i, vp, vp, C.c_long]
     L.ccg_put_sample_codes.argtypes = [vp, i, vp]
     L.ccg_get_inc_counts.argtypes = [vp, vp]
     L.ccg_set_motifs.argtypes = [vp, i, vp, vp]
@@ -325,6 +326,10 @@ class Context:
 
     def put_samples_packed_dev(self, d_seqs_ptr, d_masks_ptr, count, wstride, first=0):
         self._ck(self._L.ccg_put_samples_packed_dev(self._h, first, count, d_seqs_ptr, d_masks_ptr, wstride))
+
+    def put_samples_packed_dev_borrowed(self, d_seqs_ptr, d_masks_ptr, count, wstride, first=0):
+        """the rows are lent, not copied: keep them valid and unchanged until the run has finished"""
+        self._ck(self._L.ccg_put_samples_packed_dev_borrowed(self._h, first, count, d_seqs_ptr, d_masks_ptr, wstride))
 
     def put_sample_codes(self, idx, codes):
         codes = np.ascontiguousarray(codes, dtype=np.uint8)

@@ -20,6 +20,12 @@
 
 static char g_init_err[512] = "";
 static void update_need(ccg_ctx *ctx);
+static int materialize_borrowed(ccg_ctx *ctx);
+#define NEED_PLANES(ctx)                          \
+	do {                                          \
+		int rc__ = materialize_borrowed(ctx);     \
+		if(rc__) return rc__;                     \
+	} while(0)
 
 static void set_err(ccg_ctx *ctx, const char *fmt, ...) {
 	va_list ap;
@@ -530,6 +536,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 		ctx->global_applied = 0;
 		ctx->global_pending = 0;
 		ctx->remask_pending = 0;
+		ctx->bor_pending = 0;
 		ctx->last_Dn = 0;
 		ctx->last_ntiles = 0;
 		return CCG_OK;
@@ -567,6 +574,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	ctx->global_applied = 0;
 	ctx->global_pending = 0;
 	ctx->remask_pending = 0;
+	ctx->bor_pending = 0;
 	ctx->global_inc = 0;
 	return make_planes_tmap(ctx);
 }
@@ -600,6 +608,7 @@ extern "C" int ccg_apply_global_mask(ccg_ctx *ctx, const uint32_t *mask) {
 	if(ctx && ctx->multi && mask) return ccg_multi_put_global_mask(ctx, mask, 1);
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !mask) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
+	NEED_PLANES(ctx);
 	if(!ctx->d_gmask) CK(ctx, cudaMalloc(&ctx->d_gmask, (size_t) (ctx->words + 1) * sizeof(uint32_t)));
 	CK(ctx, cudaMemcpyAsync(ctx->d_gmask, mask, (size_t) ctx->words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 	unsigned inc = 0;
@@ -645,6 +654,7 @@ extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include,
 		return CCG_ERR_UNSUPPORTED;
 	}
 	CK(ctx, cudaSetDevice(ctx->device));
+	NEED_PLANES(ctx);
 	if(!ctx->d_gmask) CK(ctx, cudaMalloc(&ctx->d_gmask, (size_t) (ctx->words + 1) * sizeof(uint32_t)));
 	unsigned char *d_use = 0;
 	unsigned *d_cnt = 0;
@@ -717,6 +727,7 @@ extern "C" int ccg_mask_motifs(ccg_ctx *ctx, int first, int count, unsigned *inc
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || first < 0 || count < 0 || first + count > ctx->n) return CCG_ERR_ARG;
 	if(count == 0) return CCG_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
+	NEED_PLANES(ctx);
 	if(ctx->motif_n && ctx->words > 0) {
 		int rc = ensure_stage(ctx, (size_t) count * sizeof(unsigned) + 64);
 		if(rc) return rc;
@@ -734,6 +745,7 @@ extern "C" int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int appl
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || first < 0 || count < 0 || first + count > ctx->n) return CCG_ERR_ARG;
 	if(count == 0) return CCG_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
+	NEED_PLANES(ctx);
 	unsigned *h = (unsigned *) malloc((size_t) count * 2 * sizeof(unsigned));
 	if(!h) return CCG_ERR_NOMEM;
 	unsigned *h_inc = h, *h_clr = h + count;
@@ -855,6 +867,37 @@ extern "C" int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count, co
 	return CCG_OK;
 }
 
+/* builds the plane store of the lent rows when something other than the tensor path's expansion needs it */
+static int materialize_borrowed(ccg_ctx *ctx) {
+	if(!ctx->bor_pending) return CCG_OK;
+	ctx->bor_pending = 0;
+	return ccg_put_samples_packed_dev(ctx, ctx->bor_first, ctx->bor_count, ctx->bor_seqs, ctx->bor_masks, ctx->bor_wstride);
+}
+
+/* Same as ccg_put_samples_packed_dev, but the rows are LENT: they must stay valid and unchanged until the run that
+ * uses them has finished (ccg_sync), and the library reads them during that run. */
+extern "C" int ccg_put_samples_packed_dev_borrowed(ccg_ctx *ctx, int first, int count, const uint64_t *d_seqs,
+                                                   const uint32_t *d_masks, long wstride) {
+	CCG_MULTI_SOLO(ctx, "an upload from device memory", ccg_put_samples_packed_dev_borrowed(m0, first, count, d_seqs, d_masks, wstride));
+	if(!ctx || !ctx->d_planes || first < 0 || count < 0 || first + count > ctx->n || !d_seqs || wstride < ctx->words)
+		return CCG_ERR_ARG;
+	if(ctx->pair_mode && !d_masks) return CCG_ERR_ARG;
+	int rc = materialize_borrowed(ctx);            /* one lent range at a time */
+	if(rc || count == 0) return rc;
+	/* only the e2m1 tensor path reads lent rows; everything else goes through the planes right away */
+	if(ctx->use_i8 || ctx->dbg_umma1 || ctx->proxi || ctx->motif_n || ctx->world > 1 || ctx->win_on)
+		return ccg_put_samples_packed_dev(ctx, first, count, d_seqs, d_masks, wstride);
+	memset(ctx->present + first, 1, (size_t) count);
+	for(int b = first >> 7; b <= (first + count - 1) >> 7; ++b) ctx->have[b] = 1;
+	ctx->bor_seqs = d_seqs;
+	ctx->bor_masks = ctx->pair_mode ? d_masks : 0;
+	ctx->bor_wstride = wstride;
+	ctx->bor_first = first;
+	ctx->bor_count = count;
+	ctx->bor_pending = 1;
+	return CCG_OK;
+}
+
 extern "C" int ccg_put_sample_codes(ccg_ctx *ctx, int idx, const unsigned char *codes) {
 	if(ctx && ctx->multi && codes) return ccg_multi_put_sample_codes(ctx, idx, codes);
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || idx < 0 || idx >= ctx->n || !codes) return CCG_ERR_ARG;
@@ -874,6 +917,7 @@ extern "C" int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out) {
 	if(ctx && ctx->multi && out) return ccg_multi_get_inc_counts(ctx, out);
 	if(!ctx || !ctx->d_inc || !out) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
+	NEED_PLANES(ctx);                          /* the per-sample counts come out of the plane build */
 	CK(ctx, cudaMemcpyAsync(out, ctx->d_inc, (size_t) ctx->n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	return CCG_OK;
@@ -1562,6 +1606,7 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 	/* measured on B200 (profiles/): the tensor kernel runs the contraction ~5x faster than the
 	 * XU-pipe-bound POPC kernel but pays a fixed operand-expansion pass; small problems stay on POPC */
 	if(mode == 0 && ctx->proxi) {
+		NEED_PLANES(ctx);
 		if(ctx->feed_seqs) {
 			set_err(ctx, "internal: host rows cannot be streamed into a run with proximity masking");
 			return CCG_ERR_ARG;
@@ -1580,6 +1625,10 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 			return CCG_ERR_UNSUPPORTED;
 		}
 		kind = CCG_KERNEL_POPC;
+	}
+	if(ctx->bor_pending && !(kind == CCG_KERNEL_UMMA && !ctx->use_i8 && !ctx->dbg_umma1 && !ctx->feed_seqs)) {
+		int rc = materialize_borrowed(ctx);
+		if(rc) return rc;
 	}
 	if(kind == CCG_KERNEL_FUSED) return run_fused(ctx, ep);
 	return kind == CCG_KERNEL_UMMA ? run_umma(ctx, ep) : run_popc(ctx, ep);
@@ -1765,6 +1814,7 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
 		return CCG_ERR_UNSUPPORTED;
 	}
 	CK(ctx, cudaSetDevice(ctx->device));
+	NEED_PLANES(ctx);
 	unsigned char *use = (unsigned char *) calloc((size_t) ctx->n, 1);
 	if(!use) return CCG_ERR_NOMEM;
 	int cols = 0;
@@ -1872,6 +1922,7 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 		return CCG_ERR_ARG;
 	}
 	CK(ctx, cudaSetDevice(ctx->device));
+	NEED_PLANES(ctx);
 	const int n = ctx->n;
 	int *slot_of = (int *) malloc((size_t) (n ? n : 1) * sizeof(int));
 	if(!slot_of) return CCG_ERR_NOMEM;

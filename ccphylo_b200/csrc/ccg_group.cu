@@ -402,6 +402,10 @@ int ccg_group_accumulators(ccg_ctx *ctx, int row0, int **C_S, int **C_I, void **
  * that window this member owns */
 int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const, int row0, int row1) {
 	const int world = ctx->grp_world, rank = ctx->grp_rank;
+	if(ctx->grp_same_device && !ctx->grp_host_barrier) {
+		ccg_set_err(ctx, "members of a group that share a device run through ccg_init_multi_devices (they synchronise on the host)");
+		return CCG_ERR_UNSUPPORTED;
+	}
 	if(ctx->grp_host_barrier && host_barrier_wait((HostBarrier *) ctx->grp_host_barrier)) {
 		ccg_set_err(ctx, "another GPU of the group failed before the run reached the reduction");
 		return CCG_ERR_CUDA;

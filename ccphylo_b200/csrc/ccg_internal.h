@@ -167,6 +167,13 @@ struct ccg_ctx {
 	unsigned char *need;       /* host [n_pad/128]: row block touched by a macro tile this rank owns */
 	unsigned char *have;       /* host [n_pad/128]: row block whose present slots were really uploaded */
 
+	/* rows lent by the caller (ccg_put_samples_packed_dev_borrowed): read straight by the tensor path's expansion;
+	 * the plane store of those slots is built only when something else needs it (materialize_borrowed) */
+	const uint64_t *bor_seqs;
+	const uint32_t *bor_masks;
+	long bor_wstride;
+	int bor_first, bor_count, bor_pending;
+
 	void *d_stage;             /* staging for host rows */
 	size_t stage_bytes;
 

@@ -180,9 +180,31 @@ __device__ __forceinline__ uint32_t spread8(uint32_t x) {      /* bit k of the b
 	x = (x | (x << 3)) & 0x11111111u;
 	return x;
 }
+/* keep the even bits of x (bit 2k -> bit k): the low / high code bit of every base of a packed reference word */
+__device__ __forceinline__ uint32_t even_bits(uint64_t x) {
+	x &= 0x5555555555555555ull;
+	x = (x | (x >> 1)) & 0x3333333333333333ull;
+	x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+	x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+	x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+	x = (x | (x >> 16));
+	return (uint32_t) x;
+}
+
+/* where the expansion reads a sample from: the plane store, or -- for the slots [first, first + count) of rows the
+ * caller lent us (ccg_put_samples_packed_dev_borrowed) -- straight from the reference's packed words, which saves
+ * the 12 + 12 bytes per word of the plane store round trip (k_repack_packed) on the tensor path */
+struct PackedSource {
+	const uint64_t *seqs;          /* NULL: everything comes from the planes */
+	const uint32_t *masks;         /* NULL: shared-mask mode, gmask below */
+	const uint32_t *gmask;
+	long wstride;
+	int first, count, words;
+};
+
 __global__ void __launch_bounds__(256)
 k_expand_fp4(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunks_total, int slot0, int slots, int chunk0,
-             int npairs, int8_t *__restrict__ X, size_t nkb) {
+             int npairs, int8_t *__restrict__ X, size_t nkb, const PackedSource src) {
 	const long long total = (long long) slots * npairs * 8;           /* 2 chunks x 4 words per pair */
 	for(long long gid = (long long) blockIdx.x * blockDim.x + threadIdx.x; gid < total;
 	    gid += (long long) gridDim.x * blockDim.x) {
@@ -192,7 +214,17 @@ k_expand_fp4(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int ch
 		const int kp = (int) (item / slots);
 		const int chunk = chunk0 + 2 * kp + (sub >> 2), q = sub & 3;
 		uint32_t h = 0, l = 0, m = nplanes == 3 ? 0u : 0xFFFFFFFFu;
-		if(chunk < chunks_total) {
+		if(src.seqs && slot >= src.first && slot < src.first + src.count) {
+			const long w = (long) chunk * CCG_CHUNK_WORDS + q;
+			if(w < src.words) {
+				const size_t at = (size_t) (slot - src.first) * src.wstride + w;
+				const uint64_t x = __ldg(src.seqs + at);
+				const uint32_t mk = src.masks ? __ldg(src.masks + at) : __ldg(src.gmask + w);
+				h = even_bits(x >> 1) & mk;
+				l = even_bits(x) & mk;
+				if(nplanes == 3) m = mk;
+			}
+		} else if(chunk < chunks_total) {
 			const size_t prow = (size_t) chunk * nplanes;
 			h = planes[((prow + 0) * n_pad + slot) * 4 + q];
 			l = planes[((prow + 1) * n_pad + slot) * 4 + q];
@@ -720,8 +752,19 @@ cudaError_t ccg_launch_expand_fp4(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, 
 		if(items > 0) {
 			long long blocks = (items * 8 + 255) / 256;
 			if(bounded && blocks > 6LL * ctx->sm_count) blocks = 6LL * ctx->sm_count;
+			PackedSource src;
+			memset(&src, 0, sizeof(src));
+			if(ctx->bor_pending) {
+				src.seqs = ctx->bor_seqs;
+				src.masks = ctx->bor_masks;
+				src.gmask = ctx->d_gmask;
+				src.wstride = ctx->bor_wstride;
+				src.first = ctx->bor_first;
+				src.count = ctx->bor_count;
+				src.words = ctx->words;
+			}
 			k_expand_fp4<<<(unsigned) blocks, 256, 0, stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, ctx->chunks, slot0, slots, chunk0,
-			                                                   npairs, X, (size_t) npairs * 4);
+			                                                   npairs, X, (size_t) npairs * 4, src);
 			ctx->launches++;
 		}
 		b = e;

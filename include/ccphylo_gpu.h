@@ -194,6 +194,15 @@ int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count,
                                const uint64_t *d_seqs, const uint32_t *d_masks,
                                long wstride);
 
+/* Same, but the rows are LENT instead of copied: they must stay valid and unchanged until the run that uses them
+ * has finished (ccg_sync or a host-output run call), and the library reads them during that run.  The tensor path
+ * then expands its operands straight from the packed words and skips building the bit-plane store (12 B read +
+ * 12 B written per 32 bases and sample); any call that needs the planes (-P, -y, -V, the POPC kernel, the
+ * per-sample counts) builds them from the lent rows first.  One lent range at a time. */
+int ccg_put_samples_packed_dev_borrowed(ccg_ctx *ctx, int first, int count,
+                                        const uint64_t *d_seqs, const uint32_t *d_masks,
+                                        long wstride);
+
 /* Upload one sample as translated codes 0..4 (len bytes, host); the device
  * performs qseq2nibble (qseqs.c:60), initIncPos + getIncPos(seq, seq, 0)
  * (fsacmp.c:164,181) and getNpos (:487).  Pair mode only. */

@@ -295,3 +295,48 @@ def test_mxf4_exact_at_the_accumulator_bound(built, length, kslices_env, min_sli
     assert np.array_equal(N, no.astype(np.float64))
     assert np.array_equal(D, mo.astype(np.float64))
     assert (mo == 0).sum() >= (n - 2) * (n - 3) // 2 and no.max() == length
+
+
+# ---- rows LENT to the library: the tensor path expands straight from the reference's packed words ----
+@pytest.mark.parametrize("n,length", [(300, 128 * 70 + 5), (513, 20000 + 17), (260, 255)])
+@pytest.mark.parametrize("pair", [True, False], ids=["pair", "shared-mask"])
+def test_lent_rows_expand_without_the_plane_store(built, n, length, pair):
+    import torch
+
+    codes, seqs, masks, inc = _set(n, length, seed=n + length, nrun=0.004 if not pair else 0.05)
+    include = np.ones(n, np.uint8)
+    include[[3, n - 1]] = 0
+    gmask = oracle.global_mask(codes, include)
+    d_seqs = torch.from_numpy(seqs.view(np.int64)).cuda()
+    d_masks = torch.from_numpy(masks.view(np.int32)).cuda()
+    torch.cuda.synchronize()
+    with api.Context() as c:
+        c.set_kernel(api.KERNEL_UMMA)
+        c.set_problem(n, length, pair=pair)
+        if not pair:
+            c.put_global_mask(gmask)
+        c.put_samples_packed_dev_borrowed(d_seqs.data_ptr(), d_masks.data_ptr() if pair else None, n, d_seqs.stride(0))
+        launches0 = c.launches
+        if pair:
+            D, N, dn = c.run_pair(include=include, norm=1000)
+            Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=1000)
+            assert np.array_equal(_bits(N), _bits(No))
+        else:
+            D, dn, ginc = c.run_global(include=include, norm=1000)
+            Do, dno, ginco = oracle.fsa_cmp_global(seqs, gmask, include, length, norm=1000)
+            assert ginc == ginco
+        assert dn == dno == n - 2 and np.array_equal(_bits(D), _bits(Do))
+        assert "mxf4" in c.last_kernel
+        # no k_repack launch: expansion(s) + GEMM + finalize only
+        assert c.launches - launches0 <= 4
+        if pair:
+            # something that needs the planes builds them from the lent rows: per-sample counts, then the POPC kernel
+            assert np.array_equal(c.inc_counts(), inc)
+            c.set_kernel(api.KERNEL_POPC)
+            D2, N2, dn2 = c.run_pair(include=include, norm=1000)
+            assert np.array_equal(_bits(D2), _bits(Do)) and np.array_equal(_bits(N2), _bits(No))
+            # and a fresh loan after that is read directly again
+            c.set_kernel(api.KERNEL_UMMA)
+            c.put_samples_packed_dev_borrowed(d_seqs.data_ptr(), d_masks.data_ptr(), n, d_seqs.stride(0))
+            D3, N3, dn3 = c.run_pair(include=include, norm=1000)
+            assert np.array_equal(_bits(D3), _bits(Do)) and np.array_equal(_bits(N3), _bits(No))
