@@ -100,7 +100,7 @@ def ring_main(args, rank, world, local_rank, emit, log, ClockSampler, measured_p
     total_basecmp = float(ncell) * length
 
     def step():
-        ctx.put_samples_packed_dev(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))
+        ctx.put_samples_packed_dev_borrowed(seqs_t.data_ptr(), masks_t.data_ptr(), n, seqs_t.stride(0))   # rows lent, read in place
         ctx.run_pair_dev(d_D.data_ptr(), d_N.data_ptr(), norm=0, min_length=1, min_cov=0.5, elem_size=8)
 
     def barrier():
@@ -268,7 +268,7 @@ def ring_main(args, rank, world, local_rank, emit, log, ClockSampler, measured_p
                                      f"macro-tile rows, int32 partial sums reduced by the row owners through peer pointers over NVLink "
                                      f"inside the epilogue kernel; no shard ever moves" if world > 1 else "one GPU"),
                        "l2": "inputs far larger than the 126 MB L2; no explicit flush",
-                       "step": "encode (packed words -> bit planes) + operand expansion + windows of (GEMM, peer reduce + epilogue)"},
+                       "step": "operand expansion straight from the resident packed words + windows of (GEMM, peer reduce + epilogue)"},
             "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
             "parity_vs_oracle": parity, "parity_cells_checked": int(len(hi)), "parity_samples": int(len(ids)),
         })

@@ -134,7 +134,8 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 	}
 	/* tuning knobs for experiments (scripts/one_step.py); unset in normal use */
 	ctx->watchdog_cycles = getenv("CCG_WATCHDOG_S") ? (long long) (atof(getenv("CCG_WATCHDOG_S")) * 2.0e9) : 4000000000LL;
-	if(getenv("CCG_KSLICES")) ctx->dbg_kslices = atoi(getenv("CCG_KSLICES"));
+	if(getenv("CCG_NOTHIN")) ctx->dbg_nothin = atoi(getenv("CCG_NOTHIN"));
+if(getenv("CCG_KSLICES")) ctx->dbg_kslices = atoi(getenv("CCG_KSLICES"));
 	if(getenv("CCG_EXPAND_SERIAL")) ctx->dbg_serial = atoi(getenv("CCG_EXPAND_SERIAL"));
 	if(getenv("CCG_NOLOCK")) ctx->dbg_nolock = atoi(getenv("CCG_NOLOCK"));
 	if(getenv("CCG_UMMA1")) ctx->dbg_umma1 = atoi(getenv("CCG_UMMA1"));
@@ -152,7 +153,7 @@ static void free_problem(ccg_ctx *ctx) {
 	cudaFree(ctx->d_gmask); ctx->d_gmask = 0;
 	cudaFree(ctx->d_inc); ctx->d_inc = 0;
 	cudaFree(ctx->d_rank); ctx->d_rank = 0;
-	cudaFree(ctx->d_X); ctx->d_X = 0; ctx->x_bytes = 0;
+	cudaFree(ctx->d_X); ctx->d_X = 0; ctx->x_bytes = 0; ctx->tmap_thin_valid = 0;
 	cudaFree(ctx->d_C); ctx->d_C = 0; ctx->c_bytes = 0;
 	free(ctx->present); ctx->present = 0;
 	free(ctx->need); ctx->need = 0;
@@ -259,6 +260,7 @@ extern "C" int ccg_set_scratch_limit(ccg_ctx *ctx, size_t bytes) {
 		ctx->d_X = 0;
 		ctx->x_bytes = 0;
 		ctx->x_chunks = 0;
+		ctx->tmap_thin_valid = 0;
 	}
 	ctx->x_budget = bytes;
 	return CCG_OK;
@@ -512,6 +514,25 @@ static int make_x_tmap(ccg_ctx *ctx) {
 		return CCG_ERR_CUDA;
 	}
 	return CCG_OK;
+}
+
+/* the panel again, with a box of `rows` rows: what one CTA stages as its half of a thin item's B operand */
+cudaError_t ccg_make_thin_tmap(ccg_ctx *ctx, int rows) {
+	EncodeTiledFn enc;
+	if(get_encoder(ctx, &enc)) return cudaErrorUnknown;
+	cuuint64_t gdim[2] = {128, (cuuint64_t) (ctx->x_bytes / 128)};
+	cuuint64_t gstride[1] = {128};
+	cuuint32_t box[2] = {128, (cuuint32_t) rows};
+	cuuint32_t estr[2] = {1, 1};
+	CUresult r = enc(&ctx->tmap_thin, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ctx->d_X, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(r != CUDA_SUCCESS) {
+		set_err(ctx, "cuTensorMapEncodeTiled(X, thin box of %d rows) failed with CUresult %d", rows, (int) r);
+		return cudaErrorUnknown;
+	}
+	ctx->tmap_thin_rows = rows;
+	ctx->tmap_thin_valid = 1;
+	return cudaSuccess;
 }
 
 extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
@@ -1198,6 +1219,7 @@ static int ensure_panel(ccg_ctx *ctx, bool fp4) {
 	}
 	ctx->x_bytes = x_bytes;
 	ctx->x_chunks = (int) fit;
+	ctx->tmap_thin_valid = 0;
 	rc = make_x_tmap(ctx);
 	if(rc) return rc;
 	return CCG_OK;

@@ -97,6 +97,7 @@ struct UmmaParams {
 	int no_mask_items;     /* e2m1 panel, shared-mask mode: the inclusion count is a constant, no I items */
 	int fp4;               /* e2m1 panel (kind::mxf4): slab_chunks / chunks_per_slice count chunk PAIRS, S and I are separate items */
 	int single;            /* tiles are 128 x 256 and run on the single-CTA kernel (CCG_UMMA1=1, experiments) */
+	int thin_tm, thin_n, thin_valid;   /* thin items (k_pairdist_umma2): tile row, MMA N, valid rows; thin_tm < 0 = none */
 	long long watchdog;    /* cycles an mbarrier wait may take before the kernel traps; 0 = no limit (set by ccg_launch_umma) */
 };
 
@@ -221,6 +222,8 @@ struct ccg_ctx {
 	CUtensorMap tmap;          /* planes as a 4-D tensor, box [4 chunks][planes][64 slots][4] (POPC kernel) */
 	CUtensorMap tmap_pl;       /* same tensor, box [1 chunk][planes][128 slots][4] (fused tensor kernel) */
 	CUtensorMap tmap_x;        /* operand panel as a 2-D tensor */
+	CUtensorMap tmap_thin;     /* same tensor, box of tmap_thin_rows rows: a CTA's half of the B operand of a thin item */
+	int tmap_thin_rows, tmap_thin_valid, dbg_nothin;
 	int tmap_valid;
 
 	/* count-matrix (.mat) path, k_matdist.cu */
@@ -288,6 +291,7 @@ cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int 
 cudaError_t ccg_launch_expand_fp4(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int npairs, int bounded);
 cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
 int ccg_umma_pair_slots(ccg_ctx *ctx);
+cudaError_t ccg_make_thin_tmap(ccg_ctx *ctx, int rows);
 cudaError_t ccg_launch_finalize_umma(ccg_ctx *ctx, const UmmaParams &p, const EpilogueParams &ep, int i_const);
 cudaError_t ccg_launch_gather_raw_dense(ccg_ctx *ctx, int i_const, uint32_t *d_mism, uint32_t *d_ninc);
 

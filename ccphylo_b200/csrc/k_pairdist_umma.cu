@@ -473,12 +473,17 @@ __device__ __forceinline__ void umma2_i8(uint32_t tmem_d, uint64_t adesc, uint64
  * Block-scaled instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptorBlockScaled):
  * a/b_format E2M1 (1) @7/@10, K-major, n_dim @17, scale_format UE8M0 (1) @23, m_dim @24, K = 64. */
 constexpr uint32_t IDESC_MXF4 = (1u << 7) | (1u << 10) | ((uint32_t) (BN >> 3) << 17) | (1u << 23) | ((uint32_t) (256 >> 4) << 24);
-__device__ __forceinline__ void umma2_mxf4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t sfa, uint32_t sfb) {
+/* the same descriptor for an N of n columns (a multiple of 16): thin items, see k_pairdist_umma2 */
+__device__ __forceinline__ uint32_t idesc_mxf4(int n) {
+	return (1u << 7) | (1u << 10) | ((uint32_t) (n >> 3) << 17) | (1u << 23) | ((uint32_t) (256 >> 4) << 24);
+}
+__device__ __forceinline__ void umma2_mxf4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t sfa, uint32_t sfb,
+                                           uint32_t idesc) {
 	asm volatile(
 	    "{\n\t.reg .pred p;\n\t"
 	    "setp.ne.b32 p, %4, 0;\n\t"
 	    "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
-	    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC_MXF4), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
+	    ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
 }
 __device__ __forceinline__ void umma2_commit(uint32_t bar) {
 	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -495,9 +500,17 @@ __device__ __forceinline__ void cluster_sync_all() {
  * PAIRS (one 128-byte channel row = 256 bases).  Exactness: every product is -1, 0 or +1, the pipe adds exact
  * partial sums into f32 (measured: scripts/fp4_probe.py), so an item is exact while 3 * 256 * pairs < 2^24 --
  * the host keeps the slices below 20,000 pairs. */
+/* THIN items (FP4 only).  The last macro-tile row of a sample count that is not a multiple of 256 holds only
+ * v = n - 256 tm valid rows (16 of 256 at n = 10,000: 4.8 % of all MMA work would be padding).  When v is small
+ * (p.thin_n = v rounded up to 16, p.thin_tm = that tile row) the off-diagonal tiles of that row are computed
+ * TRANSPOSED: the 256 samples of the column block are the M side (A operand, one row block per CTA as usual), the v
+ * valid samples of the row block are the N side -- CTA r of the pair stages rows [r N/2, r N/2 + N/2) of that row
+ * block as its half of B through a tensor map whose box is N/2 rows (tmap_thin) -- and the MMA runs with N = thin_n.
+ * TMEM lane = column sample j, TMEM column e = row sample 256 tm + e, so the epilogue adds into C[256 tm + e][j]:
+ * the same cells, just reached from the other side (and with the 32 lanes of a warp on 32 consecutive ints). */
 template <bool FP4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
+k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_thin, const UmmaParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t raw = smem_u32(smem_raw);
 	const uint32_t base = (raw + 1023u) & ~1023u;
@@ -566,7 +579,11 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 				if(nchunk < 0) nchunk = 0;
 				const int nkb = FP4 ? (which ? nchunk : 3 * nchunk) : nchunk * 4;   /* stages of this item */
 				const long long g0 = (long long) round * p.epochs_per_item;
-				const int rbA = 2 * tm + (int) cta_rank, rbB = 2 * tn + (int) cta_rank;
+				const bool thin = FP4 && tm == p.thin_tm && tn < tm;
+				const int rbA = thin ? 2 * tn + (int) cta_rank : 2 * tm + (int) cta_rank;
+				const int rbB = thin ? 2 * tm : 2 * tn + (int) cta_rank;
+				const int b_off = thin ? (int) cta_rank * (p.thin_n >> 1) : 0;      /* first row of this CTA's half of B */
+				const unsigned stage_tx = thin ? (unsigned) (2 * (A_BYTES + (p.thin_n >> 1) * BK)) : (unsigned) (2 * STAGE2_BYTES);
 				for(int kb = 0; kb < nkb; ++kb, ++it) {
 					if(p.sync && cta_rank == 0 && (kb % LOCK_E) == 0) {
 						const long long g = g0 + kb / LOCK_E;
@@ -585,9 +602,9 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 					const uint32_t bar = (bar_full + 8 * s) & PEER_MASK;      /* the leader's barrier */
 					/* k-block of this stage inside the slab: 4 per chunk (pair), channel-minor */
 					const int kabs = FP4 ? (which ? (c_begin + kb) * 4 + 3 : (c_begin + kb / 3) * 4 + kb % 3) : c_begin * 4 + kb;
-					if(cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE2_BYTES);
+					if(cta_rank == 0) mbar_expect_tx(bar_full + 8 * s, stage_tx);
 					tma_load_2d_pair(dst, &tmap, bar, 0, p.row_base + (rbA * nkb_slab + kabs) * 128);
-					tma_load_2d_pair(dst + A_BYTES, &tmap, bar, 0, p.row_base + (rbB * nkb_slab + kabs) * 128);
+					tma_load_2d_pair(dst + A_BYTES, thin ? &tmap_thin : &tmap, bar, 0, p.row_base + (rbB * nkb_slab + kabs) * 128 + b_off);
 				}
 				if(p.sync && cta_rank == 0)
 					for(int e = (nkb + LOCK_E - 1) / LOCK_E; e < p.epochs_per_item; ++e) lockstep_arrive(p.sync, g0 + e);
@@ -599,13 +616,15 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 			unsigned it = 0;
 			int round = 0;
 			for(int w = cid; w < items; w += G, ++round) {
-				const int q = w / p.ntiles;
+				const int tile = w % p.ntiles, q = w / p.ntiles;
 				const int ks = FP4 ? q % p.kslices : q, which = FP4 ? q / p.kslices : 0;   /* all S items first, then the I items */
 				const int c_begin = ks * p.chunks_per_slice;
 				int nchunk = p.slab_chunks - c_begin;
 				if(nchunk > p.chunks_per_slice) nchunk = p.chunks_per_slice;
 				if(nchunk < 0) nchunk = 0;
 				const int nkb = FP4 ? (which ? nchunk : 3 * nchunk) : nchunk * 4;
+				const bool thin = FP4 && p.tiles[tile].x == p.thin_tm && p.tiles[tile].y < p.tiles[tile].x;
+				const uint32_t idesc = thin ? idesc_mxf4(p.thin_n) : IDESC_MXF4;
 				if(round > 0) {
 					mbar_wait(bar_tfree, (round - 1) & 1, p.watchdog);
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -621,7 +640,7 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 					if(FP4) {
 #pragma unroll
 						for(int k = 0; k < BK / 32; ++k) {               /* 32 bytes = 64 e2m1 = one MMA K */
-							umma2_mxf4(tmem, adesc + 2 * k, bdesc + 2 * k, usedS, tmem + 256, tmem + 264);
+							umma2_mxf4(tmem, adesc + 2 * k, bdesc + 2 * k, usedS, tmem + 256, tmem + 264, idesc);
 							usedS = 1;
 						}
 					} else {
@@ -651,9 +670,23 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
 			const int tm = p.tiles[tile].x, tn = p.tiles[tile].y;
 			const int nleft = p.slab_chunks - ks * p.chunks_per_slice;
 			const int row = tm * BMT + (int) cta_rank * 128 + quarter * 32 + lane;
+			const bool thin = FP4 && tm == p.thin_tm && tn < tm;
 			mbar_wait(bar_accum, round & 1, p.watchdog);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-			if(nleft > 0) {
+			if(nleft > 0 && thin) {
+				/* transposed item: this thread's TMEM lane is column sample j, TMEM column e is row sample 256 tm + e */
+				const int j = tn * BN + (int) cta_rank * 128 + quarter * 32 + lane;
+				int *c = (which ? p.C_I : p.C_S) + (size_t) (tm * BMT) * p.ldc + j;
+				for(int cb = 0; cb * 32 < p.thin_n; ++cb) {
+					uint32_t r[32];
+					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + cb * 32, r);
+			#pragma unroll
+					for(int e = 0; e < 32; ++e) {
+						const int v = __float2int_rn(__uint_as_float(r[e]));
+						if(cb * 32 + e < p.thin_valid && v) atomicAdd(c + (size_t) (cb * 32 + e) * p.ldc, v);
+					}
+				}
+			} else if(nleft > 0) {
 				int *cS = p.C_S + (size_t) row * p.ldc + tn * BN;
 				int *cI = p.C_I + (size_t) row * p.ldc + tn * BN;
 				const int jlim = row - tn * BN;
@@ -855,9 +888,23 @@ cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p_in) {
 		p.sync = ctx->d_sync;
 	}
 	ctx->last_gemm_ctas = p.single ? grid : 2 * grid;
+	/* thin items: the last macro-tile row when it holds few valid samples (see k_pairdist_umma2) */
+	p.thin_tm = -1;
+	p.thin_n = p.thin_valid = 0;
+	const int v = ctx->n % BMT;
+	if(p.fp4 && !p.single && v > 0 && v <= 96 && ctx->n > BMT && !ctx->dbg_nothin) {
+		const int tn_thin = (v + 15) / 16 * 16;
+		if(ctx->tmap_thin_rows != tn_thin / 2 || !ctx->tmap_thin_valid) {
+			cudaError_t et = ccg_make_thin_tmap(ctx, tn_thin / 2);
+			if(et != cudaSuccess) return et;
+		}
+		p.thin_tm = ctx->n / BMT;
+		p.thin_n = tn_thin;
+		p.thin_valid = v;
+	}
 	if(p.single) k_pairdist_umma<<<(unsigned) grid, THREADS, smem1, ctx->stream>>>(ctx->tmap_x, p);
-	else if(p.fp4) k_pairdist_umma2<true><<<(unsigned) (2 * grid), THREADS, smem2, ctx->stream>>>(ctx->tmap_x, p);
-	else k_pairdist_umma2<false><<<(unsigned) (2 * grid), THREADS, smem2, ctx->stream>>>(ctx->tmap_x, p);
+	else if(p.fp4) k_pairdist_umma2<true><<<(unsigned) (2 * grid), THREADS, smem2, ctx->stream>>>(ctx->tmap_x, p.thin_tm >= 0 ? ctx->tmap_thin : ctx->tmap_x, p);
+	else k_pairdist_umma2<false><<<(unsigned) (2 * grid), THREADS, smem2, ctx->stream>>>(ctx->tmap_x, ctx->tmap_x, p);
 	ctx->launches++;
 	return cudaGetLastError();
 }
