@@ -780,7 +780,8 @@ extern "C" int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int appl
 		int first_used = -1;
 		int rc = stage_use_flags(ctx, 0, first, first + count, &d_use, &d_clr, (size_t) ctx->n_pad, &first_used);
 		if(rc) { free(h); return rc; }
-		e = ccg_launch_sample_proxi(ctx, 0, 0, d_use, apply ? 1 : 0, d_clr);
+		e = ccg_launch_sample_proxi(ctx, 0, 0, d_use, apply ? 2 : 0, d_clr);
+		if(apply) ctx->remask_pending = 1;          /* mask plane only: the code planes follow before the first run */
 		if(e == cudaSuccess)
 			e = cudaMemcpyAsync(h_clr, d_clr + first, (size_t) count * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
 	}
@@ -903,7 +904,10 @@ extern "C" int ccg_put_samples_packed_dev_borrowed(ccg_ctx *ctx, int first, int 
 	if(!ctx || !ctx->d_planes || first < 0 || count < 0 || first + count > ctx->n || !d_seqs || wstride < ctx->words)
 		return CCG_ERR_ARG;
 	if(ctx->pair_mode && !d_masks) return CCG_ERR_ARG;
-	int rc = materialize_borrowed(ctx);            /* one lent range at a time */
+	/* one lent range at a time: an earlier loan that the new one does not replace slot for slot gets its planes now */
+	int rc = CCG_OK;
+	if(ctx->bor_pending && count > 0 && first <= ctx->bor_first && first + count >= ctx->bor_first + ctx->bor_count) ctx->bor_pending = 0;
+	else rc = materialize_borrowed(ctx);
 	if(rc || count == 0) return rc;
 	/* only the e2m1 tensor path reads lent rows; everything else goes through the planes right away */
 	if(ctx->use_i8 || ctx->dbg_umma1 || ctx->proxi || ctx->motif_n || ctx->world > 1 || ctx->win_on)

@@ -55,8 +55,12 @@ struct SelfSink {
 		if(!(old & bits)) return;
 		if(apply) {
 			old = atomicAnd(m, ~bits);
-			atomicAnd(planes + plane_index(n_pad, w, 0, slot), ~bits);
-			atomicAnd(planes + plane_index(n_pad, w, 1, slot), ~bits);
+			/* apply == 2: the mask plane only -- the code planes keep the bases (a motif scan may still follow, and
+			 * the reference's maskMotifs reads the unchanged sequence); k_remask_all clears them before the first run */
+			if(apply == 1) {
+				atomicAnd(planes + plane_index(n_pad, w, 0, slot), ~bits);
+				atomicAnd(planes + plane_index(n_pad, w, 1, slot), ~bits);
+			}
 		}
 		cleared += (unsigned) __popc(old & bits);
 	}
