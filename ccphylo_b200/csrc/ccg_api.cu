@@ -21,9 +21,11 @@
 static char g_init_err[512] = "";
 static void update_need(ccg_ctx *ctx);
 static int materialize_borrowed(ccg_ctx *ctx);
+static int planes_usable(ccg_ctx *ctx);
 #define NEED_PLANES(ctx)                          \
 	do {                                          \
 		int rc__ = materialize_borrowed(ctx);     \
+		if(!rc__) rc__ = planes_usable(ctx);      \
 		if(rc__) return rc__;                     \
 	} while(0)
 
@@ -135,13 +137,14 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 	/* tuning knobs for experiments (scripts/one_step.py); unset in normal use */
 	ctx->watchdog_cycles = getenv("CCG_WATCHDOG_S") ? (long long) (atof(getenv("CCG_WATCHDOG_S")) * 2.0e9) : 4000000000LL;
 	if(getenv("CCG_NOTHIN")) ctx->dbg_nothin = atoi(getenv("CCG_NOTHIN"));
-if(getenv("CCG_KSLICES")) ctx->dbg_kslices = atoi(getenv("CCG_KSLICES"));
+	if(getenv("CCG_KSLICES")) ctx->dbg_kslices = atoi(getenv("CCG_KSLICES"));
 	if(getenv("CCG_EXPAND_SERIAL")) ctx->dbg_serial = atoi(getenv("CCG_EXPAND_SERIAL"));
 	if(getenv("CCG_NOLOCK")) ctx->dbg_nolock = atoi(getenv("CCG_NOLOCK"));
 	if(getenv("CCG_UMMA1")) ctx->dbg_umma1 = atoi(getenv("CCG_UMMA1"));
 	if(getenv("CCG_I8")) ctx->use_i8 = atoi(getenv("CCG_I8"));
 	ctx->min_slabs = getenv("CCG_MIN_SLABS") ? atoi(getenv("CCG_MIN_SLABS")) : 0;     /* 0 = automatic */
 	if(getenv("CCG_FEED_SLABS")) ctx->dbg_feed_slabs = atoi(getenv("CCG_FEED_SLABS"));
+	if(getenv("CCG_FEED_PLANES")) ctx->dbg_feed_planes = atoi(getenv("CCG_FEED_PLANES"));
 	/* host rows are streamed K slab by K slab from this alignment length on (0 = never) */
 	ctx->stream_min_chunks = getenv("CCG_STREAM_MIN_CHUNKS") ? atoi(getenv("CCG_STREAM_MIN_CHUNKS")) : 4096;
 	*out = ctx;
@@ -173,6 +176,7 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	ccg_group_release(ctx);
 	cudaFree(ctx->grp_own_win);
 	cudaFree(ctx->d_row_base);
+	cudaFree(ctx->d_unfed);
 	free(ctx->h_row_base);
 	free_problem(ctx);
 	ccg_mat_free(ctx);
@@ -558,6 +562,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 		ctx->global_pending = 0;
 		ctx->remask_pending = 0;
 		ctx->bor_pending = 0;
+		ctx->planes_stale = 0;
 		ctx->last_Dn = 0;
 		ctx->last_ntiles = 0;
 		return CCG_OK;
@@ -596,6 +601,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	ctx->global_pending = 0;
 	ctx->remask_pending = 0;
 	ctx->bor_pending = 0;
+	ctx->planes_stale = 0;
 	ctx->global_inc = 0;
 	return make_planes_tmap(ctx);
 }
@@ -889,6 +895,15 @@ extern "C" int ccg_put_samples_packed_dev(ccg_ctx *ctx, int first, int count, co
 	return CCG_OK;
 }
 
+/* ccg_fsa_cmp_thread_out on a long alignment streams the host rows straight into the operand panel: afterwards the
+ * context holds results and per-sample counts, but no bit-plane store of that sample set */
+static int planes_usable(ccg_ctx *ctx) {
+	if(!ctx->planes_stale) return CCG_OK;
+	set_err(ctx, "the samples of the last ccg_fsa_cmp_thread_out call were streamed through the operand panel and left no sample "
+	        "store on the device: declare the problem again (ccg_set_problem) and upload them with ccg_put_*");
+	return CCG_ERR_ARG;
+}
+
 /* builds the plane store of the lent rows when something other than the tensor path's expansion needs it */
 static int materialize_borrowed(ccg_ctx *ctx) {
 	if(!ctx->bor_pending) return CCG_OK;
@@ -942,7 +957,10 @@ extern "C" int ccg_get_inc_counts(ccg_ctx *ctx, unsigned *out) {
 	if(ctx && ctx->multi && out) return ccg_multi_get_inc_counts(ctx, out);
 	if(!ctx || !ctx->d_inc || !out) return CCG_ERR_ARG;
 	CK(ctx, cudaSetDevice(ctx->device));
-	NEED_PLANES(ctx);                          /* the per-sample counts come out of the plane build */
+	{
+		int rc = materialize_borrowed(ctx);    /* the per-sample counts come out of the plane build (or of a streamed run) */
+		if(rc) return rc;
+	}
 	CK(ctx, cudaMemcpyAsync(out, ctx->d_inc, (size_t) ctx->n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	return CCG_OK;
@@ -1095,7 +1113,9 @@ static int run_popc(ccg_ctx *ctx, const EpilogueParams &ep) {
  * Uploads the words of chunks [chunk0, chunk0 + nch) of every needed row (copy stream) and
  * repacks them into the plane store; ev_up fires when the slab's planes are complete.  Rows at
  * a uniform distance (one host allocation) go as 2-D copies, others row by row. */
-static int feed_slab(ccg_ctx *ctx, int chunk0, int nch) {
+/* X != NULL (e2m1 panel): the staged words are expanded straight into the slab's panel buffer X (npairs chunk pairs) by
+ * the copy stream itself -- no plane store, no separate expansion pass competing with the GEMM for the SMs. */
+static int feed_slab(ccg_ctx *ctx, int chunk0, int nch, int8_t *X, int npairs) {
 	const int w0 = chunk0 * CCG_CHUNK_WORDS;
 	int nw = nch * CCG_CHUNK_WORDS;
 	if(nw > ctx->words - w0) nw = ctx->words - w0;
@@ -1153,11 +1173,13 @@ static int feed_slab(ccg_ctx *ctx, int chunk0, int nch) {
 						CK(ctx, cudaMemcpyAsync(d_msk + (size_t) r * pw, masks[k + r] + w0, (size_t) nw * 4, cudaMemcpyHostToDevice, cs));
 				}
 			}
-			CK(ctx, ccg_launch_repack_direct(ctx, cs, k, run, d_seq, d_msk, (long) pw, chunk0, nch));
+			if(X) CK(ctx, ccg_launch_expand_rows(ctx, cs, X, k, run, d_seq, d_msk, (long) pw, chunk0, npairs));
+			else CK(ctx, ccg_launch_repack_direct(ctx, cs, k, run, d_seq, d_msk, (long) pw, chunk0, nch));
 			k += run;
 			q ^= 1;
 		}
 	}
+	if(X && ctx->n_unfed) CK(ctx, ccg_launch_zero_panel_rows(ctx, ctx->copy_stream[0], X, ctx->d_unfed, ctx->n_unfed, npairs));
 	for(int q = 0; q < 2; ++q) CK(ctx, cudaEventRecord(ctx->ev_up[q], ctx->copy_stream[q]));
 	return CCG_OK;
 }
@@ -1336,6 +1358,30 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		CK(ctx, cudaEventRecord(ctx->ev_main, ctx->stream));
 		for(int q = 0; q < 2; ++q) CK(ctx, cudaStreamWaitEvent(ctx->copy_stream[q], ctx->ev_main, 0));
 	}
+	/* host rows streamed into the e2m1 panel: expanded by the copy streams, no plane store (CCG_FEED_PLANES=1: old path) */
+	const bool direct_feed = ctx->feed_seqs && fp4 && !ctx->dbg_feed_planes;
+	if(direct_feed) {
+		std::vector<int> unfed;
+		for(int b = 0; b < ctx->n_pad / 128; ++b) {
+			if(!ctx->need[b]) continue;
+			for(int k = b * 128; k < (b + 1) * 128; ++k)
+				if(k >= ctx->n || !ctx->feed_seqs[k] || (ctx->feed_masks && !ctx->feed_masks[k])) unfed.push_back(k);
+		}
+		ctx->n_unfed = (int) unfed.size();
+		if(ctx->unfed_cap < unfed.size()) {
+			CK(ctx, cudaStreamSynchronize(ctx->stream));
+			cudaFree(ctx->d_unfed);
+			ctx->d_unfed = 0;
+			ctx->unfed_cap = 0;
+			CK(ctx, cudaMalloc(&ctx->d_unfed, unfed.size() * sizeof(int)));
+			ctx->unfed_cap = unfed.size();
+		}
+		if(!unfed.empty()) {
+			CK(ctx, cudaMemcpyAsync(ctx->d_unfed, unfed.data(), unfed.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+			CK(ctx, cudaStreamSynchronize(ctx->stream));                 /* the host list dies with this block */
+		}
+		ctx->planes_stale = 1;
+	}
 	const bool gate = ctx->fn_wait_value && ctx->d_resident && nslabs > 1;
 	if(gate) CK(ctx, cudaMemsetAsync(ctx->d_resident, 0, sizeof(unsigned), ctx->stream));
 	p.resident = gate ? ctx->d_resident : 0;
@@ -1366,26 +1412,34 @@ static int run_umma(ccg_ctx *ctx, const EpilogueParams &ep) {
 		if(fp4 && (nu + p.kslices - 1) / p.kslices > CCG_FP4_MAX_PAIRS) p.kslices = (nu + CCG_FP4_MAX_PAIRS - 1) / CCG_FP4_MAX_PAIRS;
 		p.chunks_per_slice = (nu + p.kslices - 1) / p.kslices;
 		while(p.kslices > 1 && (long long) (p.kslices - 1) * p.chunks_per_slice >= nu) --p.kslices;
+		/* who writes the slab's panel: the aux stream (expansion from the plane store) or -- host rows streamed into the
+		 * e2m1 panel -- the two copy streams themselves, right behind their uploads */
+		cudaStream_t writers[2] = {ctx->aux_stream, 0};
+		int nwriters = 1;
+		if(direct_feed) { writers[0] = ctx->copy_stream[0]; writers[1] = ctx->copy_stream[1]; nwriters = 2; }
+		for(int wq = 0; wq < nwriters; ++wq) {
+			/* buffer b is free once the GEMM of slab s-2 has read it */
+			if(s >= 2) CK(ctx, cudaStreamWaitEvent(writers[wq], ctx->ev_g[b], 0));
+			if(ctx->dbg_serial && s >= 1) CK(ctx, cudaStreamWaitEvent(writers[wq], ctx->ev_g[b ^ 1], 0));
+			if(gate && s >= 1) {
+				typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+				/* ev_launch: the GEMM of slab s-1 has been handed to the device queue */
+				CK(ctx, cudaStreamWaitEvent(writers[wq], ctx->ev_launch, 0));
+				CUresult r = ((WaitValueFn) ctx->fn_wait_value)((CUstream) writers[wq], (CUdeviceptr) ctx->d_resident,
+				                                                resident_target, CU_STREAM_WAIT_VALUE_GEQ);
+				if(r != CUDA_SUCCESS) {
+					set_err(ctx, "cuStreamWaitValue32 failed with CUresult %d", (int) r);
+					return CCG_ERR_CUDA;
+				}
+			}
+		}
 		if(ctx->feed_seqs) {
-			rc = feed_slab(ctx, chunk0, nch);
+			rc = feed_slab(ctx, chunk0, nch, direct_feed ? ctx->d_X + buf_off[b] : 0, nu);
 			if(rc) return rc;
 			for(int q = 0; q < 2; ++q) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_up[q], 0));
 		}
-		/* buffer b is free once the GEMM of slab s-2 has read it */
-		if(s >= 2) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b], 0));
-		if(ctx->dbg_serial && s >= 1) CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_g[b ^ 1], 0));
-		if(gate && s >= 1) {
-			typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-			/* ev_launch: the GEMM of slab s-1 has been handed to the device queue */
-			CK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_launch, 0));
-			CUresult r = ((WaitValueFn) ctx->fn_wait_value)((CUstream) ctx->aux_stream, (CUdeviceptr) ctx->d_resident,
-			                                                resident_target, CU_STREAM_WAIT_VALUE_GEQ);
-			if(r != CUDA_SUCCESS) {
-				set_err(ctx, "cuStreamWaitValue32 failed with CUresult %d", (int) r);
-				return CCG_ERR_CUDA;
-			}
-		}
-		if(fp4) CK(ctx, ccg_launch_expand_fp4(ctx, ctx->aux_stream, ctx->d_X + buf_off[b], chunk0, nu, nslabs > 1 && !ctx->dbg_serial));
+		if(direct_feed) { /* the panel of this slab is complete once both copy streams are through (ev_up, waited for above) */ }
+		else if(fp4) CK(ctx, ccg_launch_expand_fp4(ctx, ctx->aux_stream, ctx->d_X + buf_off[b], chunk0, nu, nslabs > 1 && !ctx->dbg_serial));
 		else CK(ctx, ccg_launch_expand(ctx, ctx->aux_stream, ctx->d_X + buf_off[b], chunk0, nch, nslabs > 1 && !ctx->dbg_serial));
 		CK(ctx, cudaEventRecord(ctx->ev_x[b], ctx->aux_stream));
 		if(s == nslabs - 1) CK(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->aux_stream));
@@ -1589,6 +1643,10 @@ static int run_common(ccg_ctx *ctx, int mode, const unsigned char *include, unsi
 		ctx->global_pending = 0;
 	}
 
+	if(ctx->planes_stale && !ctx->feed_seqs) {
+		int rc = planes_usable(ctx);
+		if(rc) return rc;
+	}
 	const int Dn = compute_ranks(ctx, include);
 	ctx->last_Dn = Dn;
 	if(Dn_out) *Dn_out = Dn;

@@ -174,6 +174,10 @@ struct ccg_ctx {
 	const uint32_t *bor_masks;
 	long bor_wstride;
 	int bor_first, bor_count, bor_pending;
+	int planes_stale;          /* the last run streamed host rows straight into the operand panel: the plane store was not built */
+	int *d_unfed;              /* streamed runs: slots of read row blocks that no batch writes (their panel rows are zeroed) */
+	int n_unfed;
+	size_t unfed_cap;
 
 	void *d_stage;             /* staging for host rows */
 	size_t stage_bytes;
@@ -182,6 +186,7 @@ struct ccg_ctx {
 	 * s+1 cross PCIe on copy_stream while the GEMM of slab s runs */
 	int stream_min_chunks;                 /* stream when the alignment has at least this many chunks (0 = never) */
 	int dbg_feed_slabs;                    /* CCG_FEED_SLABS override (experiments) */
+	int dbg_feed_planes;                   /* CCG_FEED_PLANES=1: streamed rows go through the plane store (the older path) */
 	cudaStream_t copy_stream[2];
 	cudaEvent_t ev_up[2], ev_main;
 	const uint64_t *const *feed_seqs;      /* host row pointers, or NULL when nothing is being streamed */
@@ -289,6 +294,9 @@ int ccg_popc_kc(void);
 /* k_pairdist_umma.cu */
 cudaError_t ccg_launch_expand(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int nchunks, int bounded);
 cudaError_t ccg_launch_expand_fp4(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int chunk0, int npairs, int bounded);
+cudaError_t ccg_launch_expand_rows(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int first, int count, const uint64_t *d_seqs,
+                                   const uint32_t *d_masks, long wstride, int chunk0, int npairs);
+cudaError_t ccg_launch_zero_panel_rows(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, const int *d_slots, int nslots, int npairs);
 cudaError_t ccg_launch_umma(ccg_ctx *ctx, const UmmaParams &p);
 int ccg_umma_pair_slots(ccg_ctx *ctx);
 cudaError_t ccg_make_thin_tmap(ccg_ctx *ctx, int rows);

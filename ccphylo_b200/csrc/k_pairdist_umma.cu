@@ -251,6 +251,74 @@ k_expand_fp4(const uint32_t *__restrict__ planes, int n_pad, int nplanes, int ch
 	}
 }
 
+/* The same expansion for host rows that are being STREAMED in K slabs (feed_slab in ccg_api.cu): the batch of rows a
+ * copy stream has just staged on the device -- the words of one slab, reference packed format -- goes straight into
+ * the slab's panel; the bit-plane store is not built at all on this path.  One thread per (row, word of a chunk
+ * pair) walks the slab's chunk pairs: 8 neighbouring threads read 64 contiguous bytes of a row and write 128
+ * contiguous bytes of every channel row, and a thread's popcounts add up to one atomic for the per-sample counts
+ * (getNpos, fsacmp.c:487).  gmask (shared-mask mode, masks == NULL) points at the slab's first word. */
+__global__ void __launch_bounds__(256)
+k_expand_fp4_rows(const uint64_t *__restrict__ seqs, const uint32_t *__restrict__ masks, const uint32_t *__restrict__ gmask, long wstride,
+                  int nvalid, int first, int count, int npairs, int pairs_per_block, int nplanes, int8_t *__restrict__ X, size_t nkb,
+                  unsigned *__restrict__ inc) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int s = t >> 3, sub = t & 7;
+	if(s >= count) return;
+	const int slot = first + s;
+	const int kp0 = blockIdx.y * pairs_per_block;
+	int kp1 = kp0 + pairs_per_block;
+	if(kp1 > npairs) kp1 = npairs;
+	const uint64_t *srow = seqs + (size_t) s * wstride;
+	const uint32_t *mrow = masks ? masks + (size_t) s * wstride : gmask;
+	unsigned known = 0;
+	for(int kp = kp0; kp < kp1; ++kp) {
+		const int w = kp * 8 + sub;
+		uint64_t x = 0;
+		uint32_t mk = 0;
+		if(w < nvalid) { x = __ldg(srow + w); mk = __ldg(mrow + w); }
+		uint32_t h = __brev(even_bits(x >> 1) & mk), l = __brev(even_bits(x) & mk);
+		const uint32_t m = __brev(nplanes == 3 ? mk : 0xFFFFFFFFu);
+		known += (unsigned) __popc(mk);
+		uint32_t c0[4], c1[4], c2[4], c3[4];
+#pragma unroll
+		for(int g = 0; g < 4; ++g) {
+			const uint32_t one = spread8((m >> (8 * g)) & 0xFFu) << 1;
+			const uint32_t sh = spread8((h >> (8 * g)) & 0xFFu) << 3;
+			const uint32_t sl = spread8((l >> (8 * g)) & 0xFFu) << 3;
+			c0[g] = one | sh;
+			c1[g] = one | sl;
+			c2[g] = one | (sh ^ sl);
+			c3[g] = one;
+		}
+		const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) kp * 4) * 128 + (slot & 127);
+		uint4 *dst = reinterpret_cast<uint4 *>(X + tile_row * 128 + sub * 16);
+		__stcs(dst + 0 * 1024, make_uint4(c0[0], c0[1], c0[2], c0[3]));
+		__stcs(dst + 1 * 1024, make_uint4(c1[0], c1[1], c1[2], c1[3]));
+		__stcs(dst + 2 * 1024, make_uint4(c2[0], c2[1], c2[2], c2[3]));
+		__stcs(dst + 3 * 1024, make_uint4(c3[0], c3[1], c3[2], c3[3]));
+	}
+	if(masks) {
+		known += __shfl_xor_sync(0xffffffffu, known, 4);
+		known += __shfl_xor_sync(0xffffffffu, known, 2);
+		known += __shfl_xor_sync(0xffffffffu, known, 1);
+		if(sub == 0 && known) atomicAdd(inc + slot, known);
+	}
+}
+
+/* rows of the slab's panel that no streamed batch wrote (empty or excluded slots of a row block that is read): zeros */
+__global__ void __launch_bounds__(256)
+k_zero_panel_rows(const int *__restrict__ slots, int nslots, int npairs, int8_t *__restrict__ X, size_t nkb) {
+	const long long total = (long long) nslots * npairs * 4 * 8;          /* 16-byte pieces */
+	for(long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long) gridDim.x * blockDim.x) {
+		const int piece = (int) (e & 7), ch = (int) ((e >> 3) & 3);
+		const long long rest = e >> 5;
+		const int slot = slots[rest % nslots];
+		const long long kp = rest / nslots;
+		const size_t tile_row = ((size_t) (slot >> 7) * nkb + (size_t) kp * 4 + ch) * 128 + (slot & 127);
+		reinterpret_cast<uint4 *>(X + tile_row * 128)[piece] = make_uint4(0, 0, 0, 0);
+	}
+}
+
 /* ------------------------------------------------------------------ */
 /* the GEMM                                                            */
 /* ------------------------------------------------------------------ */
@@ -673,17 +741,28 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 			const bool thin = FP4 && tm == p.thin_tm && tn < tm;
 			mbar_wait(bar_accum, round & 1, p.watchdog);
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-			if(nleft > 0 && thin) {
-				/* transposed item: this thread's TMEM lane is column sample j, TMEM column e is row sample 256 tm + e */
+			if(nleft > 0 && FP4) {
+				/* One loop for both item shapes (a second copy of it costs 140 registers, which the kernels that run
+				 * beside this one -- operand expansion, slab uploads -- then lack).  Ordinary item: TMEM lane = matrix row,
+				 * TMEM column e = matrix column tn * 256 + e, consecutive ints, only columns below the row are needed.
+				 * Thin (transposed) item: TMEM lane = column sample j, TMEM column e = row sample 256 tm + e, so the
+				 * 32 values of a thread are one matrix column: stride ldc, the first thin_valid of them exist. */
 				const int j = tn * BN + (int) cta_rank * 128 + quarter * 32 + lane;
-				int *c = (which ? p.C_I : p.C_S) + (size_t) (tm * BMT) * p.ldc + j;
-				for(int cb = 0; cb * 32 < p.thin_n; ++cb) {
+				int *cp = (which ? p.C_I : p.C_S) + (thin ? (size_t) (tm * BMT) * p.ldc + j : (size_t) row * p.ldc + tn * BN);
+				const int stride = thin ? p.ldc : 1;
+				const int lim = thin ? p.thin_valid : row - tn * BN;
+				const int ncol = thin ? p.thin_n : BN;
+#pragma unroll 1
+				for(int cb = 0; cb * 32 < ncol; ++cb) {
+					if(__all_sync(0xffffffffu, cb * 32 >= lim)) break;
 					uint32_t r[32];
 					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + cb * 32, r);
-			#pragma unroll
+					const int left = lim - cb * 32;
+#pragma unroll
 					for(int e = 0; e < 32; ++e) {
-						const int v = __float2int_rn(__uint_as_float(r[e]));
-						if(cb * 32 + e < p.thin_valid && v) atomicAdd(c + (size_t) (cb * 32 + e) * p.ldc, v);
+						const int v = __float2int_rn(__uint_as_float(r[e]));       /* exact integers in f32 */
+						if(e < left && v) atomicAdd(cp, v);
+						cp += stride;
 					}
 				}
 			} else if(nleft > 0) {
@@ -695,23 +774,13 @@ k_pairdist_umma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 					if(__all_sync(0xffffffffu, cb * 32 >= jlim)) break;
 					uint32_t r[32];
 					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + cb * 32, r);
-					if(FP4) {
-						/* exact integers in f32 */
-						int *c = which ? cI : cS;
 #pragma unroll
-						for(int e = 0; e < 32; ++e) {
-							const int v = __float2int_rn(__uint_as_float(r[e]));
-							if(cb * 32 + e < jlim && v) atomicAdd(c + cb * 32 + e, v);
-						}
-					} else {
+					for(int e = 0; e < 32; ++e)
+						if(cb * 32 + e < jlim && r[e]) atomicAdd(cS + cb * 32 + e, (int) r[e]);
+					tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + BN + cb * 32, r);
 #pragma unroll
-						for(int e = 0; e < 32; ++e)
-							if(cb * 32 + e < jlim && r[e]) atomicAdd(cS + cb * 32 + e, (int) r[e]);
-						tmem_ld32(tmem + ((uint32_t) (quarter * 32) << 16) + BN + cb * 32, r);
-#pragma unroll
-						for(int e = 0; e < 32; ++e)
-							if(cb * 32 + e < jlim && r[e]) atomicAdd(cI + cb * 32 + e, (int) r[e]);
-					}
+					for(int e = 0; e < 32; ++e)
+						if(cb * 32 + e < jlim && r[e]) atomicAdd(cI + cb * 32 + e, (int) r[e]);
 				}
 			}
 			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -802,6 +871,32 @@ cudaError_t ccg_launch_expand_fp4(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, 
 		}
 		b = e;
 	}
+	return cudaGetLastError();
+}
+
+/* streamed batch of rows [first, first + count) (words of the slab that starts at chunk0) -> the slab's panel */
+cudaError_t ccg_launch_expand_rows(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, int first, int count, const uint64_t *d_seqs,
+                                   const uint32_t *d_masks, long wstride, int chunk0, int npairs) {
+	if(count <= 0 || npairs <= 0) return cudaSuccess;
+	int nvalid = ctx->words - chunk0 * CCG_CHUNK_WORDS;
+	if(nvalid > npairs * 8) nvalid = npairs * 8;
+	if(nvalid < 0) nvalid = 0;
+	/* a few hundred pairs per thread: enough blocks to keep the copy stream's share of the SMs busy beside the GEMM */
+	int per = 256;
+	if(per > npairs) per = npairs;
+	dim3 grid((unsigned) (((long long) count * 8 + 255) / 256), (unsigned) ((npairs + per - 1) / per));
+	k_expand_fp4_rows<<<grid, 256, 0, stream>>>(d_seqs, d_masks, ctx->d_gmask ? ctx->d_gmask + (size_t) chunk0 * CCG_CHUNK_WORDS : 0, wstride, nvalid,
+	                                            first, count, npairs, per, ctx->nplanes, X, (size_t) npairs * 4, ctx->d_inc);
+	ctx->launches++;
+	return cudaGetLastError();
+}
+
+cudaError_t ccg_launch_zero_panel_rows(ccg_ctx *ctx, cudaStream_t stream, int8_t *X, const int *d_slots, int nslots, int npairs) {
+	if(nslots <= 0 || npairs <= 0) return cudaSuccess;
+	long long blocks = ((long long) nslots * npairs * 32 + 255) / 256;
+	if(blocks > 2LL * ctx->sm_count) blocks = 2LL * ctx->sm_count;
+	k_zero_panel_rows<<<(unsigned) blocks, 256, 0, stream>>>(d_slots, nslots, npairs, X, (size_t) npairs * 4);
+	ctx->launches++;
 	return cudaGetLastError();
 }
 
