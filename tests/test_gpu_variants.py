@@ -122,3 +122,29 @@ def test_cli_variant_file_against_the_reference_binary(built, tmp_path, msa, fla
         outs[tag] += (open(both).read(),)
     assert outs["reference"][0].count("\n") > 100
     assert outs["driver"] == outs["reference"]
+
+
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(REF_GPU)), reason="oracle/_ref was not built (needs /root/reference)")
+@pytest.mark.parametrize("flag", ["3", "11", "1"])
+def test_reference_bound_to_the_library_lists_variants_on_the_device(built, tmp_path, flag):
+    # the UNMODIFIED reference linked against libccphylo_gpu.so through integration/fsacmpgpu.c: -V in pair mode comes
+    # from ccg_list_variants (in shared-mask mode the stub leaves it on the reference's own code); same bytes either way
+    td = str(tmp_path)
+    n, length = 10, 7000 + 5
+    rows = synth.make_ascii(n, length, seed=int(flag) + 90, snp=0.01, nrun=0.01)
+    files = []
+    for i in range(n):
+        fp = os.path.join(td, f"s{i:02d}.fsa")
+        synth.write_fasta(fp, rows[i], header="ref", width=60)
+        files.append(fp)
+    outs = {}
+    for tag, exe in (("reference", REF_BIN), ("bound", REF_GPU)):
+        phy, num, var = (os.path.join(td, tag + e) for e in (".phy", ".num", ".var"))
+        p = _run([exe, "dist", "-f", flag, "-t", "1", "-V", var, "-o", phy, "-n", num, "-r", "ref", "-i"] + files, td)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[tag] = (open(var).read(), open(phy).read(), open(num).read(), p.stderr)
+    assert outs["reference"][0].count("\n") > 50
+    assert outs["bound"] == outs["reference"]
