@@ -233,8 +233,8 @@ def test_option_scanner_dialect(built, tmp_path):
     # files the run then stops at the device (this container has none) or at the refused option
     a = tmp_path / "a.fsa"
     a.write_text(">ref\nACGT\n")
-    p = run("-pf3", "-s", "-W", "100", "-rref", "-i", str(a), str(a), "-P", "2", "-y", "m.txt")
-    assert p.returncode == 1 and "-y / --methylation_motifs together with -P / --proximity is not available on the GPU path" in p.stderr
+    p = run("-pf1", "-s", "-W", "100", "-rref", "-i", str(a), str(a), "-P", "2", "-y", "m.txt")
+    assert p.returncode == 1 and "-y / --methylation_motifs together with -P / --proximity without pairwise inclusion (-f 2) is not available on the GPU path" in p.stderr
     p = run("-r", "ref", "-a", "x", "-V", "v.txt", "-P", "2", str(a), str(a))
     assert p.returncode == 1 and "-V / --nucleotide_variations together with -P / --proximity" in p.stderr
     # -a reads the existing matrix before it needs the device: a multi-matrix file is refused as the reference does
