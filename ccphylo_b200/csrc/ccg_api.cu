@@ -561,6 +561,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 		ctx->global_applied = 0;
 		ctx->global_pending = 0;
 		ctx->remask_pending = 0;
+		ctx->codes_upload_masked = 0;
 		ctx->bor_pending = 0;
 		ctx->planes_stale = 0;
 		ctx->last_Dn = 0;
@@ -600,6 +601,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	ctx->global_applied = 0;
 	ctx->global_pending = 0;
 	ctx->remask_pending = 0;
+	ctx->codes_upload_masked = 0;
 	ctx->bor_pending = 0;
 	ctx->planes_stale = 0;
 	ctx->global_inc = 0;
@@ -1996,8 +1998,20 @@ extern "C" int ccg_run_row(ccg_ctx *ctx, int row_slot, unsigned norm, unsigned m
 /* -V: fsacmpairint (fsacmp.c:685) / fsacmprint (:646) for every compared pair, see k_variants.cu */
 static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *include, int last_row_only, ccg_variant_fn fn, void *user) {
 	if(!ctx || !ctx->d_planes || !ctx->pair_mode || !fn) return CCG_ERR_ARG;
-	if(ctx->proxi || ctx->world > 1 || ctx->grp_world > 1) {
-		set_err(ctx, "variant listing (-V) is not available together with %s", ctx->proxi ? "proximity masking (-P)" : "a rank partition");
+	if(ctx->world > 1 || ctx->grp_world > 1) {
+		set_err(ctx, "variant listing (-V) is not available together with a rank partition");
+		return CCG_ERR_UNSUPPORTED;
+	}
+	/* -P: in pair mode the reference lists under maskProxi's mask (fsacmpthrd.c:410-414), built per batch below; in
+	 * shared-mask mode the proximity ranges are part of the global mask already (cdist.c:111).  The row form (-a) would
+	 * need the per-sample builder against every column sample (fsacmpthrd.c:545-553) as a mask: not built. */
+	const int pair_proxi = pair && ctx->proxi && ctx->words > 0;
+	if(pair_proxi && ctx->codes_upload_masked) {
+		set_err(ctx, "variant listing (-V) with proximity masking (-P): call ccg_set_proximity before the packed rows are uploaded");
+		return CCG_ERR_ARG;
+	}
+	if(pair_proxi && last_row_only) {
+		set_err(ctx, "variant listing (-V) of an added row (-a) is not available together with proximity masking (-P)");
 		return CCG_ERR_UNSUPPORTED;
 	}
 	if(pair ? ctx->global_applied : !ctx->global_pending) {
@@ -2016,8 +2030,27 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 	if(Dn < 2) { free(slot_of); return CCG_OK; }
 	const long long cells = (long long) Dn * (Dn - 1) / 2;
 	const long long cells_lo = last_row_only ? (long long) (Dn - 1) * (Dn - 2) / 2 : 0;
-	const int BATCH = 1 << 18;                       /* cells per count pass */
+	int BATCH = 1 << 18;                             /* cells per count pass */
 	const size_t CAP = (size_t) 1 << 24;             /* entries per write pass (128 MiB) */
+	uint32_t *d_pmask = 0;
+	if(pair_proxi) {
+		/* one mask column of `words` words per cell of a batch: at most 1 GiB (or half of what is free) of scratch */
+		size_t free_b = 0, total_b = 0;
+		CK(ctx, cudaMemGetInfo(&free_b, &total_b));
+		size_t budget = (size_t) 1 << 30;
+		if(budget > free_b / 2) budget = free_b / 2;
+		long long fit = (long long) (budget / ((size_t) ctx->words * 4));
+		fit &= ~127LL;
+		if(fit < 128) fit = 128;
+		if(fit < BATCH) BATCH = (int) fit;
+		if(cells - cells_lo < BATCH) BATCH = (int) (((cells - cells_lo) + 127) & ~127LL);
+		if(cudaMalloc(&d_pmask, (size_t) BATCH * (size_t) ctx->words * 4) != cudaSuccess) {
+			cudaGetLastError();
+			set_err(ctx, "cudaMalloc of %zu bytes for the per-pair proximity masks failed", (size_t) BATCH * (size_t) ctx->words * 4);
+			free(slot_of);
+			return CCG_ERR_NOMEM;
+		}
+	}
 	int *d_slot = 0;
 	unsigned *d_counts = 0, *h_counts = 0;
 	unsigned long long *d_off = 0, *h_off = 0, *d_ent = 0, *h_ent = 0;
@@ -2038,7 +2071,10 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 		p.cell0 = c0;
 		p.slot_of_rank = d_slot;
 		p.counts = d_counts;
-		e = ccg_launch_variants(ctx, p, 0, !pair);
+		p.pair_mask = d_pmask;
+		p.pair_mask_stride = BATCH;
+		if(d_pmask) e = ccg_launch_pair_proxi_mask(ctx, p);
+		if(e == cudaSuccess) e = ccg_launch_variants(ctx, p, 0, !pair);
 		if(e == cudaSuccess) e = cudaMemcpyAsync(h_counts, d_counts, (size_t) nb * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
 		if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 		if(e != cudaSuccess) break;
@@ -2073,6 +2109,7 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 				p.cell0 = c0 + k0;
 				p.offsets = d_off + k0;
 				p.entries = d_ent;
+				p.pair_mask = d_pmask ? d_pmask + k0 : 0;
 				e = ccg_launch_variants(ctx, p, 1, !pair);
 				if(e == cudaSuccess) e = cudaMemcpyAsync(h_ent, d_ent, nent * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
 				if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -2096,6 +2133,7 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 		set_err(ctx, "variant listing failed: %s", cudaGetErrorString(e));
 		rc = CCG_ERR_CUDA;
 	}
+	cudaFree(d_pmask);
 	cudaFree(d_slot);
 	cudaFree(d_counts);
 	cudaFree(d_off);

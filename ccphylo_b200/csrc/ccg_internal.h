@@ -80,6 +80,8 @@ struct VariantParams {
 	unsigned *counts;                   /* count pass: variants per cell */
 	const unsigned long long *offsets;  /* write pass: running offsets of the batch's cells (offsets[0] = base) */
 	unsigned long long *entries;        /* write pass: label << 4 | code_i << 2 | code_j */
+	uint32_t *pair_mask;                /* -V with -P: the batch's per-pair masks, [word][cell of the batch] (0 = none) */
+	long long pair_mask_stride;         /* cells per word row of pair_mask */
 };
 
 struct UmmaParams {
@@ -149,6 +151,8 @@ struct ccg_ctx {
 	int motif_n, motif_nsets;       /* -y: motifs (with their reverse complements) set by ccg_set_motifs */
 	int *d_motif_lens;
 	unsigned char *d_motif_sets;
+	int codes_upload_masked;        /* a packed upload ANDed the code planes with the rows' masks (no -P set at the time): a
+	                                 * -V listing under -P would not see the words the reference compares */
 	int remask_pending;             /* -y: mask planes changed by ccg_mask_motifs, code planes not yet re-masked (done before a run) */
 	int row_slot1;                  /* ccg_run_row: 1 + the slot whose row is being computed, 0 otherwise */
 	unsigned proxi;                 /* -P: minimum distance between SNPs (0 = no proximity masking), ccg_set_proximity */
@@ -317,6 +321,7 @@ cudaError_t ccg_launch_remask_all(ccg_ctx *ctx);
 
 /* k_variants.cu */
 cudaError_t ccg_launch_variants(ccg_ctx *ctx, const VariantParams &p, int write, int shared_mask);
+cudaError_t ccg_launch_pair_proxi_mask(ccg_ctx *ctx, const VariantParams &p);
 
 /* k_matdist.cu */
 void ccg_mat_free(ccg_ctx *ctx);

@@ -42,7 +42,7 @@ __device__ __forceinline__ void store_chunk(uint32_t *planes, int n_pad, int npl
 __global__ void __launch_bounds__(256)
 k_repack_packed(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunk0, int nch, int words, int first, int count,
                 const uint64_t *__restrict__ seqs, const uint32_t *__restrict__ masks,
-                const uint32_t *__restrict__ gmask, long wstride, unsigned *__restrict__ inc) {
+                const uint32_t *__restrict__ gmask, long wstride, unsigned *__restrict__ inc, int keep_codes) {
 	__shared__ uint4 tile[3][16][33];                  /* [plane][chunk][sample], padded against bank conflicts */
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int cl = lane & 15;
@@ -64,8 +64,11 @@ k_repack_packed(uint32_t *__restrict__ planes, int n_pad, int nplanes, int chunk
 					const uint64_t x = __ldg(srow + w);
 					const uint32_t mk = __ldg(mrow + w);
 					m[q] = mk;
-					h[q] = compress_even(x >> 1) & mk;
-					l[q] = compress_even(x) & mk;
+					/* keep_codes: the rows' masks were narrowed by the caller (-P / -y on the host) and a variant listing
+					 * will compare whole words as the reference does; k_remask_all clears the codes before the first run */
+					const uint32_t cm = keep_codes ? 0xFFFFFFFFu : mk;
+					h[q] = compress_even(x >> 1) & cm;
+					l[q] = compress_even(x) & cm;
 					known += __popc(mk);
 				}
 			}
@@ -305,8 +308,12 @@ cudaError_t ccg_launch_repack_range(ccg_ctx *ctx, cudaStream_t stream, int first
                                     const uint32_t *d_masks, long wstride, int chunk0, int nch) {
 	if(count <= 0 || nch <= 0) return cudaSuccess;
 	dim3 grid((unsigned) ((nch + 15) / 16), (unsigned) ((count + 31) / 32));
+	/* with -P set, a pair-mode upload keeps the code bits of the positions its mask leaves out (see the kernel) */
+	const int keep = d_masks && ctx->nplanes == 3 && ctx->proxi != 0;
+	if(keep) ctx->remask_pending = 1;
+	else if(d_masks) ctx->codes_upload_masked = 1;
 	k_repack_packed<<<grid, 256, 0, stream>>>(ctx->d_planes, ctx->n_pad, ctx->nplanes, chunk0, nch, ctx->words, first, count,
-	                                         d_seqs, d_masks, ctx->d_gmask, wstride, ctx->d_inc);
+	                                         d_seqs, d_masks, ctx->d_gmask, wstride, ctx->d_inc, keep);
 	ctx->launches++;
 	return cudaGetLastError();
 }

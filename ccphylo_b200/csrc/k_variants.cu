@@ -14,8 +14,14 @@
  * word is "walked" when its mask word is non-zero and the two packed words differ anywhere; in a walked word lane
  * k (counted from the LEAST significant end: base 31 - k of the word, plane / mask bit k) is labelled counter + k
  * and the counter then advances by (index of the highest set mask bit + 1); any other word advances it by 32.
+ *
+ * With -P (pair mode) the reference walks the pair's proximity mask instead (maskProxi, then fsacmpairint on its
+ * output, fsacmpthrd.c:410-414), and the labels depend on every word of that mask: k_pair_proxi_mask builds it for a
+ * batch of cells into a scratch buffer [word][cell] (the walk of proxi_core.h: proxi_pair_mask_word), and both passes
+ * of k_variants read their mask words from there.
  */
 #include "ccg_internal.h"
+#include "proxi_core.h"
 
 namespace {
 
@@ -46,7 +52,14 @@ k_variants(const uint32_t *__restrict__ planes, int n_pad, int chunks, int words
 		const uint4 ih = __ldg(P + (row + 0) * n_pad + i), il = __ldg(P + (row + 1) * n_pad + i);
 		const uint4 jh = __ldg(P + (row + 0) * n_pad + j), jl = __ldg(P + (row + 1) * n_pad + j);
 		uint4 m;
-		if(gmask) {
+		if(p.pair_mask) {
+			const uint32_t *pm = p.pair_mask + (size_t) ch * CCG_CHUNK_WORDS * p.pair_mask_stride + t;
+			const int w0 = ch * CCG_CHUNK_WORDS;
+			m.x = w0 < words ? pm[0] : 0u;
+			m.y = w0 + 1 < words ? pm[p.pair_mask_stride] : 0u;
+			m.z = w0 + 2 < words ? pm[2 * p.pair_mask_stride] : 0u;
+			m.w = w0 + 3 < words ? pm[3 * p.pair_mask_stride] : 0u;
+		} else if(gmask) {
 			const int w0 = ch * CCG_CHUNK_WORDS;
 			m.x = w0 < words ? __ldg(gmask + w0) : 0u;
 			m.y = w0 + 1 < words ? __ldg(gmask + w0 + 1) : 0u;
@@ -80,7 +93,62 @@ k_variants(const uint32_t *__restrict__ planes, int n_pad, int chunks, int words
 	if(!WRITE) p.counts[t] = count;
 }
 
+/* -V with -P: maskProxi's output for every cell of the batch.  One thread per cell: first the unmasked pair mask
+ * inc_i & inc_j goes into the cell's column of the scratch buffer (coalesced over the cells), then the pair is walked
+ * once more and every two neighbouring SNPs at most proxi apart clear their range in it.  The walk never reaches
+ * beyond the word after the current one, and all words are in place before it starts. */
+struct PairMaskSink {
+	uint32_t *col;                      /* pair_mask + t */
+	long long stride;
+	__device__ __forceinline__ void clear(long long w, uint32_t bits) {
+		uint32_t *m = col + (size_t) w * stride;
+		const uint32_t old = *m;
+		if(old & bits) *m = old & ~bits;
+	}
+};
+
+__global__ void __launch_bounds__(128)
+k_pair_proxi_mask(const uint32_t *__restrict__ planes, int n_pad, int chunks, int words, unsigned proxi, VariantParams p) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= p.ncells) return;
+	int r, c;
+	cell_to_pair(p.cell0 + t, r, c);
+	const int i = p.slot_of_rank[r], j = p.slot_of_rank[c];
+	const uint4 *P = reinterpret_cast<const uint4 *>(planes);
+	PairMaskSink sink = {p.pair_mask + t, p.pair_mask_stride};
+#pragma unroll 1
+	for(int ch = 0; ch < chunks; ++ch) {
+		const size_t row = (size_t) ch * 3;
+		const uint4 im = __ldg(P + (row + 2) * n_pad + i), jm = __ldg(P + (row + 2) * n_pad + j);
+		const int w0 = ch * CCG_CHUNK_WORDS;
+		if(w0 < words) sink.col[(size_t) w0 * sink.stride] = im.x & jm.x;
+		if(w0 + 1 < words) sink.col[(size_t) (w0 + 1) * sink.stride] = im.y & jm.y;
+		if(w0 + 2 < words) sink.col[(size_t) (w0 + 2) * sink.stride] = im.z & jm.z;
+		if(w0 + 3 < words) sink.col[(size_t) (w0 + 3) * sink.stride] = im.w & jm.w;
+	}
+	long long last = -1;
+#pragma unroll 1
+	for(int ch = 0; ch < chunks; ++ch) {
+		const size_t row = (size_t) ch * 3;
+		const uint4 ih = __ldg(P + (row + 0) * n_pad + i), il = __ldg(P + (row + 1) * n_pad + i), im = __ldg(P + (row + 2) * n_pad + i);
+		const uint4 jh = __ldg(P + (row + 0) * n_pad + j), jl = __ldg(P + (row + 1) * n_pad + j), jm = __ldg(P + (row + 2) * n_pad + j);
+		const long long w0 = (long long) ch * CCG_CHUNK_WORDS;
+		proxi_pair_mask_word(last, w0, ((ih.x ^ jh.x) | (il.x ^ jl.x)) & im.x & jm.x, words, proxi, sink);
+		proxi_pair_mask_word(last, w0 + 1, ((ih.y ^ jh.y) | (il.y ^ jl.y)) & im.y & jm.y, words, proxi, sink);
+		proxi_pair_mask_word(last, w0 + 2, ((ih.z ^ jh.z) | (il.z ^ jl.z)) & im.z & jm.z, words, proxi, sink);
+		proxi_pair_mask_word(last, w0 + 3, ((ih.w ^ jh.w) | (il.w ^ jl.w)) & im.w & jm.w, words, proxi, sink);
+	}
+}
+
 } // namespace
+
+cudaError_t ccg_launch_pair_proxi_mask(ccg_ctx *ctx, const VariantParams &p) {
+	if(p.ncells <= 0 || ctx->words == 0) return cudaSuccess;
+	k_pair_proxi_mask<<<(unsigned) ((p.ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks, ctx->words,
+	                                                                               ctx->proxi, p);
+	ctx->launches++;
+	return cudaGetLastError();
+}
 
 cudaError_t ccg_launch_variants(ccg_ctx *ctx, const VariantParams &p, int write, int shared_mask) {
 	if(p.ncells <= 0) return cudaSuccess;

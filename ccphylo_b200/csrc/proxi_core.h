@@ -164,6 +164,30 @@ CCG_HD void proxi_pair_finish(const ProxiPairState &st, unsigned *mism, unsigned
 	*ninc = st.total - cleared;
 }
 
+/* -V with -P: the pair's mask itself (maskProxi's `include`, which fsacmpairint then walks, fsacmpthrd.c:410-414).
+ * One word of the pair per call, words ascending; d = SNP bits of word w under the unmasked pair mask, `last` = position
+ * of the last SNP so far (-1 = none), W = words of the alignment.  For two neighbouring SNPs last < p at most proxi apart
+ * the positions last + 1 .. p + 1 go: sink.clear(word, bits) is asked for words <= w + 1 (p + 1 may be the first base of
+ * the next word), so the caller has words 0 .. w + 1 of the mask in place before the call. */
+template <class Sink>
+CCG_HD void proxi_pair_mask_word(long long &last, long long w, uint32_t d, long long W, unsigned proxi, Sink &sink) {
+	while(d) {
+		const int b = ccg_first_bit(d);
+		d &= ~(0x80000000u >> b);
+		const long long p = w * 32 + b;
+		if(last >= 0 && (unsigned long long) (p - last) <= proxi) {
+			const long long lo = last + 1, hi = p + 1;
+			for(long long x = lo >> 5; x <= (hi >> 5) && x < W; ++x) {
+				uint32_t bits = 0xFFFFFFFFu;
+				if(x == (lo >> 5)) bits &= 0xFFFFFFFFu >> (int) (lo & 31);           /* bases lo % 32 .. 31 */
+				if(x == (hi >> 5)) bits &= 0xFFFFFFFFu << (31 - (int) (hi & 31));    /* bases 0 .. hi % 32 */
+				sink.clear(x, bits);
+			}
+		}
+		last = p;
+	}
+}
+
 /* ------------------------------------------------------------------------------------------
  * one row against an existing matrix (-a with -P)
  * ------------------------------------------------------------------------------------------ */

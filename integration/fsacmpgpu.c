@@ -41,17 +41,19 @@ void fsaCmpGpuOut(int tnum, void *(*func)(void *), Matrix *D, Matrix *N, int n, 
 	void *Ncells = (pair && N) ? cells(N, &elem) : 0;
 	ccg_ctx *ctx = 0;
 
-	if(diffile && (!pair || proxi)) {
-		/* -V in shared-mask mode walks the UNMASKED sequences beside the global mask (fsacmprint fsacmp.c:646), and
-		 * with -P it walks the per-pair proximity mask: both stay on the reference's own code.  (ccphylo-b200 dist
-		 * builds the shared mask on the device and lists those variants there: host/dist_main.c.) */
+	if(diffile && !pair) {
+		/* -V in shared-mask mode walks the UNMASKED sequences beside the global mask (fsacmprint fsacmp.c:646): that
+		 * stays on the reference's own code.  (ccphylo-b200 dist builds the shared mask on the device and lists those
+		 * variants there: host/dist_main.c.) */
 		fsaCmpThreadOut(tnum, func, D, N, n, len, seqs, include, includes, norm, minLength,
 		                minCov, diffile, targetTemplate, ref, filenames, proxi);
 		return;
 	}
 	if(diffile) {
-		/* -V, pair mode: fsacmpairint's lines (fsacmp.c:685-737) come from ccg_list_variants, in the order of a -t 1 run */
+		/* -V, pair mode: fsacmpairint's lines (fsacmp.c:685-737) come from ccg_list_variants, in the order of a -t 1 run;
+		 * with -P under maskProxi's per-pair mask (fsacmpthrd.c:410-414) */
 		if((rc = ccg_init(&ctx, -1))) die(0, rc);
+		if((rc = ccg_set_proximity(ctx, proxi, 0))) die(ctx, rc);
 		if((rc = ccg_set_problem(ctx, n, len, 1))) die(ctx, rc);
 		{
 			const uint64_t **s = malloc((size_t) (n ? n : 1) * sizeof(*s));

@@ -57,6 +57,8 @@ def lib():
         L.orc_pair_counts_proxi.restype = None
         L.orc_pair_counts_proxi.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint, C.POINTER(C.c_uint32),
                                             C.POINTER(C.c_uint32)]
+        L.orc_mask_proxi.restype = None
+        L.orc_mask_proxi.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint, _u32p]
         L.orc_fsa_cmp_pair_proxi.restype = C.c_int
         L.orc_fsa_cmp_pair_proxi.argtypes = [C.c_int, C.c_int, _u64p, C.c_long, _u8p, _u32p, C.c_uint, C.c_uint,
                                              C.c_double, C.c_uint, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
@@ -227,6 +229,14 @@ def pair_counts_proxi(seq_i, seq_j, inc_i, inc_j, length, proxi):
     return m.value, n.value
 
 
+def pair_mask_proxi(seq_i, seq_j, inc_i, inc_j, length, proxi):
+    """maskProxi: the pair's mask the counts (and the -V walk, fsacmpthrd.c:410-414) are taken under"""
+    out = np.zeros(max(words(length), 1), dtype=np.uint32)
+    lib().orc_mask_proxi(np.ascontiguousarray(seq_i), np.ascontiguousarray(seq_j), np.ascontiguousarray(inc_i),
+                         np.ascontiguousarray(inc_j), length, proxi, out)
+    return out[:words(length)]
+
+
 def fsa_cmp_row(seqs, masks, row, length, norm=0, min_length=1, min_cov=0.5, proxi=0, variant=0, codes=None):
     """cmpFsaRowThrd (fsacmpthrd.c:482-580): sample `row` against samples 0..row-1.  The pair mask is the new
     sample's own mask (includeadd, built :627-628 with its own builder) put through the per-sample builder against
@@ -391,6 +401,8 @@ def ref():
         R.refshim_mask_motifs.argtypes = [C.c_char_p, _u64p, _u32p, C.c_int]
         R.refshim_variants.restype = C.c_uint64
         R.refshim_variants.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _u64p, _u32p, C.c_int, C.c_char_p, C.c_long]
+        R.refshim_mask_proxi.restype = None
+        R.refshim_mask_proxi.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint, _u32p]
         R.refshim_pair.restype = C.c_uint64
         R.refshim_pair.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint]
         R.refshim_fsa_cmp.restype = C.c_int
@@ -433,6 +445,20 @@ def ref_pair(seq_i, seq_j, inc_i, inc_j, length, proxi=0):
     r = ref().refshim_pair(pad(seq_i, np.uint64), pad(seq_j, np.uint64), pad(inc_i, np.uint32), pad(inc_j, np.uint32),
                            length, proxi)
     return int(r >> 32), int(r & 0xFFFFFFFF)
+
+
+def ref_mask_proxi(seq_i, seq_j, inc_i, inc_j, length, proxi):
+    """maskProxi of the reference -> the pair's mask"""
+    W = words(length)
+
+    def pad(a, dt):
+        b = np.zeros(W + 2, dtype=dt)
+        b[:W] = a
+        return b
+    out = np.zeros(W + 2, dtype=np.uint32)
+    ref().refshim_mask_proxi(pad(seq_i, np.uint64), pad(seq_j, np.uint64), pad(inc_i, np.uint32), pad(inc_j, np.uint32),
+                             length, proxi, out)
+    return out[:W]
 
 
 def ref_phy_names(phy_path, directory, sep="\t"):

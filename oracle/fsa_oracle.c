@@ -247,22 +247,18 @@ void orc_inc_pos(uint32_t *mask, const unsigned char *seq_codes, const unsigned 
  * inc = inc_i & inc_j; the SNPs of the pair are the included positions whose 2-bit codes differ.  The
  * reference walks them from the last to the first with a position counter that is one too high, so for
  * two neighbouring SNPs p < q with q - p <= proxi it clears p+1 .. q+1: q and everything between go, p
- * stays.  Counts are then taken under the cleared mask. */
-void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j, const uint32_t *inc_i,
-                           const uint32_t *inc_j, int len, unsigned proxi, uint32_t *mism, uint32_t *ninc) {
+ * stays.  Counts are then taken under the cleared mask (orc_pair_counts_proxi); -V walks the
+ * same mask (fsacmpthrd.c:410-414), so it is also handed out as it is (orc_mask_proxi, m = ceil(len/32) words). */
+void orc_mask_proxi(const uint64_t *seq_i, const uint64_t *seq_j, const uint32_t *inc_i, const uint32_t *inc_j, int len,
+                    unsigned proxi, uint32_t *m) {
 	int w, W = orc_words(len);
-	uint32_t *m, d = 0, n = 0;
 	long *snp, ns = 0, k;
 
-	if(!proxi) {
-		orc_pair_counts(seq_i, seq_j, inc_i, inc_j, len, mism, ninc);
-		return;
-	}
-	m = malloc((size_t) (W ? W : 1) * sizeof(uint32_t));
+	for(w = 0; w < W; ++w) m[w] = inc_i[w] & inc_j[w];
+	if(!proxi) return;
 	snp = malloc((size_t) (len ? len : 1) * sizeof(long));
 	for(w = 0; w < W; ++w) {
 		int b;
-		m[w] = inc_i[w] & inc_j[w];
 		for(b = 0; b < 32; ++b) {
 			if((m[w] >> (31 - b)) & 1) {
 				const unsigned ci = (unsigned) (seq_i[w] >> (62 - 2 * b)) & 3, cj = (unsigned) (seq_j[w] >> (62 - 2 * b)) & 3;
@@ -273,12 +269,25 @@ void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j, const u
 	for(k = 0; k + 1 < ns; ++k) {
 		if((unsigned long) (snp[k + 1] - snp[k]) <= proxi) clear_range(m, snp[k] + 1, snp[k + 1] + 1, len);
 	}
+	free(snp);
+}
+
+void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j, const uint32_t *inc_i,
+                           const uint32_t *inc_j, int len, unsigned proxi, uint32_t *mism, uint32_t *ninc) {
+	int w, W = orc_words(len);
+	uint32_t *m, d = 0, n = 0;
+
+	if(!proxi) {
+		orc_pair_counts(seq_i, seq_j, inc_i, inc_j, len, mism, ninc);
+		return;
+	}
+	m = malloc((size_t) (W ? W : 1) * sizeof(uint32_t));
+	orc_mask_proxi(seq_i, seq_j, inc_i, inc_j, len, proxi, m);
 	for(w = 0; w < W; ++w) {
 		n += (uint32_t) __builtin_popcount(m[w]);
 		d += lane_mism(seq_i[w], seq_j[w], m[w]);
 	}
 	free(m);
-	free(snp);
 	*mism = d;
 	*ninc = n;
 }

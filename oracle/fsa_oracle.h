@@ -62,6 +62,9 @@ void orc_pair_counts(const uint64_t *seq_i, const uint64_t *seq_j,
 void orc_inc_pos(uint32_t *mask, const unsigned char *seq_codes,
                  const unsigned char *ref_codes, int len, unsigned proxi, int variant);
 
+/* fsacmp.c:355-485 maskProxi with -P proxi: the pair's mask (ceil(len/32) words) */
+void orc_mask_proxi(const uint64_t *seq_i, const uint64_t *seq_j, const uint32_t *inc_i, const uint32_t *inc_j, int len,
+                    unsigned proxi, uint32_t *mask_out);
 /* fsacmp.c:355-485 maskProxi with -P proxi + fsacmp.c:587-633 fsacmpair. */
 void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j,
                            const uint32_t *inc_i, const uint32_t *inc_j, int len,

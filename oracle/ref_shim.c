@@ -84,6 +84,11 @@ uint64_t refshim_pair(uint64_t *seq_i, uint64_t *seq_j, uint32_t *inc_i,
 	return r;
 }
 
+/* maskProxi alone: the pair's mask into out (len / 32 + 1 words are written) */
+void refshim_mask_proxi(uint64_t *seq_i, uint64_t *seq_j, uint32_t *inc_i, uint32_t *inc_j, int len, unsigned proxi, uint32_t *out) {
+	maskProxi(out, inc_i, inc_j, (long unsigned *) seq_i, (long unsigned *) seq_j, (unsigned) len, proxi);
+}
+
 /* -a: getSizePhy + getFilenamesPhy (phy.c:509-650) on an existing Phylip file: the names (prefixed with dir) joined
  * by '\n' into buf; returns n, -1 if the names cannot be read, -2 if bytes are left behind the n rows (dist.c:366) */
 #include "phy.h"

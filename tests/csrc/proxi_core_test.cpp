@@ -130,6 +130,24 @@ static int check_pairs(int n, int len, unsigned proxi, unsigned variant_for_mask
 				printf("pair len=%d proxi=%u (%d,%d): got %u/%u want %u/%u\n", len, proxi, i, j, got_m, got_n, want_m, want_n);
 				return 1;
 			}
+			/* the mask itself, as k_pair_proxi_mask builds it for -V: word w + 1 is put in place before word w is scanned */
+			std::vector<uint32_t> want_mask((size_t) W + 1, 0), got_mask((size_t) W + 1, 0);
+			orc_mask_proxi(seq[i].data(), seq[j].data(), mask[i].data(), mask[j].data(), len, proxi, want_mask.data());
+			HostSink msink = {got_mask.data()};
+			long long last = -1;
+			if(W) got_mask[0] = pl[i].m[0] & pl[j].m[0];
+			for(int w = 0; w < W; ++w) {
+				if(w + 1 < W) got_mask[w + 1] = pl[i].m[w + 1] & pl[j].m[w + 1];
+				const uint32_t m = pl[i].m[w] & pl[j].m[w];
+				const uint32_t d = ((pl[i].l[w] ^ pl[j].l[w]) | (pl[i].h[w] ^ pl[j].h[w])) & m;
+				proxi_pair_mask_word(last, w, d, W, proxi, msink);
+			}
+			if(memcmp(want_mask.data(), got_mask.data(), (size_t) W * sizeof(uint32_t)) != 0) {
+				int w = 0;
+				while(want_mask[w] == got_mask[w]) ++w;
+				printf("pair mask len=%d proxi=%u (%d,%d): word %d got %08x want %08x\n", len, proxi, i, j, w, got_mask[w], want_mask[w]);
+				return 1;
+			}
 		}
 	}
 	return 0;

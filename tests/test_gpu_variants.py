@@ -47,6 +47,38 @@ def test_pair_mode_lists(ctx, n, length):
     assert int(mism.sum()) == sum(len(v) for _, v in got)
 
 
+@pytest.mark.parametrize("proxi", [1, 3, 33, 200, 100000])
+@pytest.mark.parametrize("n,length", [(2, 1), (3, 33), (9, 129), (40, 4099), (150, 3000)])
+def test_pair_mode_lists_with_proximity(ctx, n, length, proxi):
+    """-V with -P: fsacmpairint walks maskProxi's per-pair mask (fsacmpthrd.c:410-414); the labels depend on every word
+    of that mask"""
+    codes = synth.make_codes(n, length, seed=n * 11 + length + proxi, snp=0.04, nrun=0.03, lower=0.02, gap=0.01)
+    seqs, masks, inc = oracle.encode_samples(codes, proxi=proxi)
+    include = (inc > 0).astype(np.uint8) if length > 1 else np.ones(n, np.uint8)
+    ctx.set_proximity(proxi)
+    try:
+        ctx.set_problem(n, length, pair=True)
+        ctx.put_samples_packed(seqs, masks)
+        got = ctx.list_variants(pair=True, include=include)
+        want, cleared = [], 0
+        for i in range(1, n):
+            for j in range(i):
+                if include[i] and include[j]:
+                    pm = oracle.pair_mask_proxi(seqs[i], seqs[j], masks[i], masks[j], length, proxi)
+                    cleared += int(np.bitwise_count(pm ^ (masks[i] & masks[j])).sum())
+                    v = oracle.list_variants(seqs[i], seqs[j], pm, length)
+                    if v:
+                        want.append(((i, j), v))
+        assert got == want
+        assert cleared > 0 or length < 64
+        # the counts of the run on the same store agree with the lists
+        D, N, dn = ctx.run_pair(include, min_length=0, min_cov=0.0)
+        mism, _ = ctx.raw_counts(dn)
+        assert int(mism.sum()) == sum(len(v) for _, v in got)
+    finally:
+        ctx.set_proximity(0)
+
+
 @pytest.mark.parametrize("n,length", [(4, 97), (30, 5003), (260, 2000)])
 def test_shared_mask_lists(ctx, n, length):
     rare = n > 100           # many samples: keep the shared mask from running empty
@@ -85,12 +117,12 @@ def _run(cmd, cwd):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
-@pytest.mark.parametrize("flag", ["3", "1", "11"])
+@pytest.mark.parametrize("flag,proxi", [("3", 0), ("1", 0), ("11", 0), ("3", 5), ("3", 300), ("35", 40), ("1", 12), ("11", 9)])
 @pytest.mark.parametrize("msa", [False, True], ids=["files", "msa"])
-def test_cli_variant_file_against_the_reference_binary(built, tmp_path, msa, flag):
+def test_cli_variant_file_against_the_reference_binary(built, tmp_path, msa, flag, proxi):
     td = str(tmp_path)
     n, length = 12, 9000 + 3
-    rows = synth.make_ascii(n, length, seed=int(flag) + 40, snp=0.01, nrun=0.01)
+    rows = synth.make_ascii(n, length, seed=int(flag) + 40 + proxi, snp=0.01, nrun=0.01)
     if int(flag) & 2:
         rows[4, 30:] = ord("N")          # excluded sample: the listed sample numbers are file indices (files) / kept records (msa)
     if msa:
@@ -111,12 +143,13 @@ def test_cli_variant_file_against_the_reference_binary(built, tmp_path, msa, fla
     outs = {}
     for tag, exe in (("reference", REF_BIN), ("driver", BIN)):
         phy, num, var = (os.path.join(td, tag + e) for e in (".phy", ".num", ".var"))
-        p = _run([exe, "dist", "-f", flag, "-t", "1", "-V", var, "-o", phy, "-n", num] + inputs, td)
+        prox = ["-P", str(proxi)] if proxi else []
+        p = _run([exe, "dist", "-f", flag, "-t", "1", "-V", var, "-o", phy, "-n", num] + prox + inputs, td)
         assert p.returncode == 0, p.stderr[-2000:]
         outs[tag] = (open(var).read(), open(phy).read(), p.stderr)
         # variants and matrix into the same file: the lists come first
         both = os.path.join(td, tag + ".both")
-        p = _run([exe, "dist", "-f", flag, "-t", "1", "-V", both, "-o", both] + inputs, td)
+        p = _run([exe, "dist", "-f", flag, "-t", "1", "-V", both, "-o", both] + prox + inputs, td)
         # (the reference closes that FILE twice and aborts after everything has been written, dist.c:293-298)
         assert p.returncode == 0 or exe == REF_BIN, p.stderr[-2000:]
         outs[tag] += (open(both).read(),)
@@ -128,13 +161,13 @@ REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu")
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(REF_GPU)), reason="oracle/_ref was not built (needs /root/reference)")
-@pytest.mark.parametrize("flag", ["3", "11", "1"])
-def test_reference_bound_to_the_library_lists_variants_on_the_device(built, tmp_path, flag):
+@pytest.mark.parametrize("flag,proxi", [("3", 0), ("11", 0), ("1", 0), ("3", 6), ("35", 150), ("1", 6)])
+def test_reference_bound_to_the_library_lists_variants_on_the_device(built, tmp_path, flag, proxi):
     # the UNMODIFIED reference linked against libccphylo_gpu.so through integration/fsacmpgpu.c: -V in pair mode comes
     # from ccg_list_variants (in shared-mask mode the stub leaves it on the reference's own code); same bytes either way
     td = str(tmp_path)
     n, length = 10, 7000 + 5
-    rows = synth.make_ascii(n, length, seed=int(flag) + 90, snp=0.01, nrun=0.01)
+    rows = synth.make_ascii(n, length, seed=int(flag) + 90 + proxi, snp=0.01, nrun=0.01)
     files = []
     for i in range(n):
         fp = os.path.join(td, f"s{i:02d}.fsa")
@@ -143,7 +176,8 @@ def test_reference_bound_to_the_library_lists_variants_on_the_device(built, tmp_
     outs = {}
     for tag, exe in (("reference", REF_BIN), ("bound", REF_GPU)):
         phy, num, var = (os.path.join(td, tag + e) for e in (".phy", ".num", ".var"))
-        p = _run([exe, "dist", "-f", flag, "-t", "1", "-V", var, "-o", phy, "-n", num, "-r", "ref", "-i"] + files, td)
+        p = _run([exe, "dist", "-f", flag, "-t", "1", "-V", var, "-o", phy, "-n", num] + (["-P", str(proxi)] if proxi else [])
+                 + ["-r", "ref", "-i"] + files, td)
         assert p.returncode == 0, p.stderr[-2000:]
         outs[tag] = (open(var).read(), open(phy).read(), open(num).read(), p.stderr)
     assert outs["reference"][0].count("\n") > 50

@@ -176,6 +176,25 @@ def test_pair_mode_with_proximity_matches_reference(built, elem, scale, proxi):
         assert np.array_equal(Nr.view(np.uint8), No.view(np.uint8))
 
 
+@pytest.mark.parametrize("proxi", [1, 2, 3, 7, 31, 32, 33, 64, 200, 100000])
+def test_pair_mask_with_proximity_and_the_variants_under_it(built, proxi):
+    """-V with -P (fsacmpthrd.c:410-414): maskProxi's mask itself, word for word, and fsacmpairint's lines under it"""
+    cleared = 0
+    for length in (1, 31, 32, 33, 64, 95, 128, 129, 700, 4099):
+        codes = _proxi_set(5, length, seed=3 * proxi + length)
+        seqs, masks, _ = oracle.encode_samples(codes, proxi=proxi)
+        for i in range(1, 5):
+            for j in range(i):
+                want = oracle.ref_mask_proxi(seqs[i], seqs[j], masks[i], masks[j], length, proxi)
+                got = oracle.pair_mask_proxi(seqs[i], seqs[j], masks[i], masks[j], length, proxi)
+                assert np.array_equal(got, want), (length, i, j)
+                cleared += int(np.bitwise_count((masks[i] & masks[j]) ^ got).sum())
+                text, r = oracle.ref_variants(True, i, j, seqs[i], seqs[j], want, length)
+                lst = oracle.list_variants(seqs[i], seqs[j], got, length)
+                assert oracle.variant_text(i, j, lst) == text and (r >> 32) == len(lst)
+    assert cleared > 0
+
+
 # ---------------------------------------------------------------------------------------------
 # -V variant listing (fsacmp.c:635-737)
 # ---------------------------------------------------------------------------------------------
