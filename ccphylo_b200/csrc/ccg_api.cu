@@ -91,6 +91,7 @@ extern "C" int ccg_init(ccg_ctx **out, int device) {
 		return CCG_ERR_NO_DEVICE;
 	}
 	ccg_ctx *ctx = (ccg_ctx *) calloc(1, sizeof(ccg_ctx));
+	if(ctx) ctx->trim_len = -1;
 	if(!ctx) return CCG_ERR_NOMEM;
 	ctx->device = device;
 	ctx->sm_count = prop.multiProcessorCount;
@@ -180,6 +181,7 @@ extern "C" void ccg_destroy(ccg_ctx *ctx) {
 	free(ctx->h_row_base);
 	free_problem(ctx);
 	ccg_mat_free(ctx);
+	ccg_trim_free(ctx);
 	cudaFree(ctx->d_stage);
 	cudaFree(ctx->d_motif_lens);
 	cudaFree(ctx->d_motif_sets);

@@ -247,6 +247,14 @@ struct ccg_ctx {
 	unsigned *mat_part_rows, *mat_rows;
 	size_t mat_part_cap;
 
+	/* `trim` (k_trim.cu): translated code bytes of the current and of the reference sample, the (shared or own) mask,
+	 * the event words of the proximity pass, the columns where some sample differs from the first one */
+	unsigned char *trim_cur, *trim_ref;
+	uint32_t *trim_mask, *trim_events, *trim_columns, *trim_ones;
+	unsigned *trim_count;
+	int trim_len, trim_words, trim_has_ref;     /* trim_len < 0: no trim job */
+	unsigned trim_proxi;
+
 	/* K-split group membership (grp_world > 1), ccg_group.cu */
 	int grp_world, grp_rank;
 	void *grp_win[CCG_GROUP_MAX];          /* peer windows: header + 2 accumulator buffers; [grp_rank] is this member's own */
@@ -325,6 +333,7 @@ cudaError_t ccg_launch_pair_proxi_mask(ccg_ctx *ctx, const VariantParams &p);
 
 /* k_matdist.cu */
 void ccg_mat_free(ccg_ctx *ctx);
+void ccg_trim_free(ccg_ctx *ctx);
 
 /* ccg_group.cu */
 void ccg_set_err(ccg_ctx *ctx, const char *fmt, ...);

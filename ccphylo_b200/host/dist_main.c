@@ -901,10 +901,12 @@ int main_dist(int argc, char **argv) {
 	return 0;
 }
 
+int main_trim(int argc, char **argv);      /* trim_main.c */
+
 int main(int argc, char **argv) {
 	if(argc < 2 || strcmp(argv[1], "-h") == 0 || strcmp(argv[1], "--help") == 0) {
 		fprintf(argc < 2 ? stderr : stdout,
-		        "# ccphylo-b200 %s\n# usage: ccphylo-b200 dist [options]   (`ccphylo-b200 dist -h` lists them)\n", VERSION);
+		        "# ccphylo-b200 %s\n# usage: ccphylo-b200 dist|trim [options]   (`ccphylo-b200 dist -h`, `ccphylo-b200 trim -h` list them)\n", VERSION);
 		return argc < 2;
 	}
 	if(strcmp(argv[1], "-v") == 0 || strcmp(argv[1], "--version") == 0) {
@@ -912,6 +914,7 @@ int main(int argc, char **argv) {
 		return 0;
 	}
 	if(strcmp(argv[1], "dist") == 0) return main_dist(argc - 1, argv + 1);
-	fprintf(stderr, "Invalid tool specified: %s (this build provides `dist` only)\n", argv[1]);
+	if(strcmp(argv[1], "trim") == 0) return main_trim(argc - 1, argv + 1);
+	fprintf(stderr, "Invalid tool specified: %s (this build provides `dist` and `trim`)\n", argv[1]);
 	return 1;
 }

@@ -383,6 +383,39 @@ int ccg_mat_run_row(ccg_ctx *ctx, int row_slot, int method, unsigned order, doub
                     unsigned minDepth, unsigned minLength, double minCov, double *D, double *N,
                     uint32_t *rows_inc);
 
+/* ---------------------------------------------------------------------------------------------
+ * `ccphylo trim` (fsaTrim, trim.c:77-260): the inclusion masks of the trimmed alignment.  trim has no pairwise stage;
+ * what it computes per sample is the mask work the `dist` front end also does, on trim's own alphabet: the translated
+ * code bytes of getIupacBitTable (fsacmp.c:93-162; 0-3 bases, 4 unknown, 5 gap, 6-15 ambiguity letters, +16 = soft-masked
+ * input) or of get2BitTable (flag 4).  One job at a time per context:
+ *
+ *   ccg_set_motifs(ctx, ...)                      optional, before ccg_trim_begin (-y)
+ *   ccg_trim_begin(ctx, len, proxi)               buffers for samples of len positions, -P proxi
+ *   ccg_trim_sample(ctx, codes, nibbles, 0, 0, &inc)
+ *        a sample on its own mask: initIncPos + maskMotifs + getIncPos(includes, seq, seq, proxi) + getNpos
+ *        (trim.c:197-203; the pairwise flag sends every sample this way).  codes: len translated bytes (host);
+ *        nibbles: the reference's packed words of the sample (qseq2nibble qseqs.c:60, ceil(len/32) u64), needed only
+ *        when motifs are set; *inc receives getNpos of the mask.
+ *   ccg_trim_keep_reference(ctx)                  the sample just processed becomes `ref` (trim.c:213-216): its stored
+ *                                                 bytes (soft flags stripped) are what later samples are compared with,
+ *                                                 its mask is the shared mask from here on
+ *   ccg_trim_sample(ctx, codes, nibbles, 1, builder, 0)
+ *        a later sample narrows the shared mask: maskMotifs + getIncPosPtr(includes, seq, ref, proxi) (trim.c:176-177);
+ *        builder 0 = getIncPos, 1 = getIncPosInsig (flag 8), 2 = getIncPosInsigPrune (flag 32).  Also notes the
+ *        columns where the sample's stored bytes differ from the reference sample's (pseudoAlnPrune fsacmp.c:504).
+ *   ccg_trim_get_mask(ctx, variable_columns_only, mask, &inc, &var)
+ *        the mask (ceil(len/32) words, bit 31-(p%32) of word p/32 = position p), *inc = getNpos of it, *var = the
+ *        number of its positions that also vary between samples; with variable_columns_only the returned mask is
+ *        restricted to those (flag 16).
+ *   ccg_trim_end(ctx)
+ * --------------------------------------------------------------------------------------------- */
+int ccg_trim_begin(ccg_ctx *ctx, int len, unsigned proxi);
+int ccg_trim_sample(ccg_ctx *ctx, const unsigned char *codes, const uint64_t *nibbles, int against_ref, int builder,
+                    unsigned *inc_out);
+int ccg_trim_keep_reference(ccg_ctx *ctx);
+int ccg_trim_get_mask(ccg_ctx *ctx, int variable_columns_only, uint32_t *mask_out, unsigned *inc_out, unsigned *var_out);
+int ccg_trim_end(ccg_ctx *ctx);
+
 /* Roofline denominator for the tensor-core kernel: runs a loads-free loop of the kernel's own
  * MMA shape (tcgen05 kind::i8, cta_group::2, 256 x 256 x 32, operands static in shared memory)
  * on every CTA pair for about target_ms and returns the rate in int8 TOP/s (2 ops per MAC);
