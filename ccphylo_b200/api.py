@@ -31,6 +31,7 @@ EXPORTS = [
     "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs", "ccg_list_variants_row",
     "ccg_init_multi", "ccg_init_multi_devices", "ccg_multi_gpus", "ccg_group_export", "ccg_group_join", "ccg_group_leave",
     "ccg_mat_run_partial", "ccg_mat_finalize_host", "ccg_group_set_alignment", "ccg_group_set_output", "ccg_group_row_block", "ccg_group_row_owner", "ccg_group_cells",
+    "ccg_trim_begin", "ccg_trim_sample", "ccg_trim_keep_reference", "ccg_trim_get_mask", "ccg_trim_end",
 ]
 GROUP_HANDLE_BYTES = 128
 
@@ -133,6 +134,11 @@ def load():
     L.ccg_mat_run_partial.argtypes = [vp, vp, i, C.c_uint, C.c_double, C.c_uint, vp, vp, vp]
     L.ccg_mat_finalize_host.argtypes = [i, vp, vp, vp, vp, C.c_uint, C.c_uint, C.c_double, i, C.c_double, vp, vp, vp, vp]
     L.ccg_mat_run_row.argtypes = [vp, i, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, vp, vp, vp]
+    L.ccg_trim_begin.argtypes = [vp, i, C.c_uint]
+    L.ccg_trim_sample.argtypes = [vp, vp, vp, i, i, vp]
+    L.ccg_trim_keep_reference.argtypes = [vp]
+    L.ccg_trim_get_mask.argtypes = [vp, i, vp, vp, vp]
+    L.ccg_trim_end.argtypes = [vp]
     L.ccg_init_multi.argtypes = [C.POINTER(vp), i]
     L.ccg_init_multi_devices.argtypes = [C.POINTER(vp), i, vp]
     L.ccg_multi_gpus.argtypes = [vp, C.POINTER(i)]
