@@ -52,8 +52,12 @@ __device__ __forceinline__ void ccg_write_cell(const EpilogueParams &ep, int slo
 		} else if(ep.elem_size == 4) {
 			float f;
 			if(!ok) f = -1.0f;
-			else if(ep.norm) f = __fdiv_rn(__ull2float_rn(scaled), __uint2float_rn(inc));
-			else f = __uint2float_rn(mism);
+			else if(ep.norm) {
+				f = __fdiv_rn(__ull2float_rn(scaled), __uint2float_rn(inc));
+				/* 0 / 0 (no included position and a zero threshold): the reference's SSE division gives the default NaN
+				 * with the sign bit set, which prints as "-nan"; CUDA's canonical float NaN is 0x7fffffff ("nan") */
+				if(f != f) f = __int_as_float((int) 0xFFC00000u);
+			} else f = __uint2float_rn(mism);
 			((float *) ep.D)[cell] = f;
 			if(ep.N) ((float *) ep.N)[cell] = __uint2float_rn(inc);
 		} else {

@@ -323,6 +323,122 @@ k_matdist(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ tot_
 	}
 }
 
+/* ------------------------------------------------------------------------------------------
+ * `cos` (the default -d, coscmp matcmp.c:420-446) has its own kernel: everything that depends on ONE sample and position
+ * is done once when a CTA stages the position -- the five counts unpacked to int, the depth gate and the "norm is zero"
+ * test folded into one flag, sqrt(c1) and its reciprocal -- so a position pair costs five integer multiply-adds, one
+ * int -> double conversion and a division that is done as the final Newton step of a division:
+ *     den = sa * sb  (as the reference rounds it);  y = (1/sa) * (1/sb);  q0 = dot * y;  r = fma(-den, q0, dot);
+ *     q = fma(r, y, q0)
+ * q is the quotient dot / den rounded from an error far below half an ulp (Markstein's correction step with a
+ * reciprocal good to ~2 ulp): it can differ from the correctly rounded quotient only when the exact value lies within
+ * ~2^-50 ulp of a rounding boundary, and the parity bar of this path is 1e-6 relative.  The int32 dot product is exact
+ * while no count of the stage exceeds 20,724 (5 * 20724^2 < 2^31); a stage with a larger count (the reference's int
+ * products wrap from 46,341 on, matcmp.c:429-437) takes the literal path: wrapped products summed in 64 bits and a real
+ * division.  Zero-padded positions have c1 = 0 and never count, so no length test is needed in the loop.
+ * ------------------------------------------------------------------------------------------ */
+constexpr int MPC = 16;           /* positions per stage of the cos kernel */
+constexpr int COS_FAST_MAX = 20724;
+
+struct CosStage {
+	int4 c03[2][MT][MPC + 1];     /* A C G T */
+	int2 c4ok[2][MT][MPC + 1];    /* '-', counts flag: minDepth <= total && c1 != 0 */
+	double2 nr[2][MT][MPC + 1];   /* sqrt(c1), 1 / sqrt(c1) */
+};
+
+__global__ void __launch_bounds__(TH * TH, 3)
+k_matdist_cos(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ tot_over, long long lpad, const int2 *__restrict__ tiles,
+              int ntiles, int nslices, int pos_per_slice, MatParams mp, double *__restrict__ part_dist, unsigned *__restrict__ part_rows) {
+	extern __shared__ __align__(16) unsigned char cos_smem[];
+	CosStage &st = *reinterpret_cast<CosStage *>(cos_smem);
+	const int tile = blockIdx.x % ntiles, ks = blockIdx.x / ntiles;
+	const int ti = tiles[tile].x, tj = tiles[tile].y;
+	const int li = threadIdx.x / TH, lj = threadIdx.x % TH;
+	const bool any_on = tj * MT + lj < ti * MT + li + TH;            /* sj0 < si1: the last pair of the block to drop out */
+	const long long p_begin = (long long) ks * pos_per_slice;
+	long long p_end = p_begin + pos_per_slice;
+	if(p_end > lpad) p_end = lpad;
+	double dist[4] = {0, 0, 0, 0};
+	unsigned rows[4] = {0, 0, 0, 0};
+	for(long long p0 = p_begin; p0 < p_end; p0 += MPC) {
+		__syncthreads();
+		int big = 0;
+		for(int e = threadIdx.x; e < 2 * MT * MPC; e += TH * TH) {
+			const int which = e / (MT * MPC), r = (e / MPC) % MT, p = e % MPC;
+			const int slot = (which ? tj : ti) * MT + r;
+			const uint32_t *src = counts + (size_t) slot * 3 * lpad + p0 + p;
+			const uint32_t x = src[0], y = src[lpad], z = src[2 * lpad];
+			const int c0 = x & 0xFFFF, c1 = x >> 16, c2 = y & 0xFFFF, c3 = y >> 16, c4 = z & 0xFFFF;
+			uint32_t tot = (uint32_t) (c0 + c1 + c2 + c3 + c4) + (z >> 16);
+			if(tot_over) {
+				const uint32_t t = tot_over[(size_t) slot * lpad + p0 + p];
+				if(t != 0xFFFFFFFFu) tot = t;
+			}
+			/* coscmp's c1: int products summed in an unsigned long (matcmp.c:426-437) */
+			const unsigned long long sq = (unsigned long long) (long long) (c0 * c0) + (unsigned long long) (long long) (c1 * c1) +
+			                              (unsigned long long) (long long) (c2 * c2) + (unsigned long long) (long long) (c3 * c3) +
+			                              (unsigned long long) (long long) (c4 * c4);
+			const double nv = sqrt((double) sq);
+			big |= (c0 | c1 | c2 | c3 | c4) > COS_FAST_MAX;          /* all five are below 2^16: the OR bounds the largest */
+			st.c03[which][r][p] = make_int4(c0, c1, c2, c3);
+			st.c4ok[which][r][p] = make_int2(c4, (mp.minDepth <= tot && sq != 0) ? 1 : 0);
+			st.nr[which][r][p] = make_double2(nv, sq ? 1.0 / nv : 0.0);
+		}
+		/* (the OR of the counts can exceed the limit while every count is below it: that only sends a stage down the
+		 * literal path more often than needed) */
+		big = __syncthreads_or(big);
+		if(!any_on) continue;
+		if(!big) {
+#pragma unroll 4
+			for(int p = 0; p < MPC; ++p) {
+				const int4 a0 = st.c03[0][li][p], a1 = st.c03[0][li + TH][p], b0 = st.c03[1][lj][p], b1 = st.c03[1][lj + TH][p];
+				const int2 a0x = st.c4ok[0][li][p], a1x = st.c4ok[0][li + TH][p], b0x = st.c4ok[1][lj][p], b1x = st.c4ok[1][lj + TH][p];
+				const double2 na0 = st.nr[0][li][p], na1 = st.nr[0][li + TH][p], nb0 = st.nr[1][lj][p], nb1 = st.nr[1][lj + TH][p];
+#define CCG_COS_PAIR(q, A, AX, NA, B, BX, NB)                                                            \
+	{                                                                                                    \
+		const int dot = A.x * B.x + A.y * B.y + A.z * B.z + A.w * B.w + AX.x * BX.x;                     \
+		const double dd = (double) dot, den = NA.x * NB.x, yy = NA.y * NB.y;                             \
+		const double q0 = dd * yy;                                                                       \
+		const double qq = fma(fma(-den, q0, dd), yy, q0);                                                \
+		double d = 1.0 - qq;                                                                             \
+		d = d < 0 ? 0 : d;                                                                               \
+		const int ok = AX.y & BX.y;                                                                      \
+		dist[q] += ok ? d : 0.0;                                                                         \
+		rows[q] += (unsigned) ok;                                                                        \
+	}
+				CCG_COS_PAIR(0, a0, a0x, na0, b0, b0x, nb0)
+				CCG_COS_PAIR(1, a0, a0x, na0, b1, b1x, nb1)
+				CCG_COS_PAIR(2, a1, a1x, na1, b0, b0x, nb0)
+				CCG_COS_PAIR(3, a1, a1x, na1, b1, b1x, nb1)
+#undef CCG_COS_PAIR
+			}
+		} else {
+#pragma unroll 1
+			for(int p = 0; p < MPC; ++p) {
+#pragma unroll
+				for(int q = 0; q < 4; ++q) {
+					const int ra = li + TH * (q >> 1), rb = lj + TH * (q & 1);
+					const int4 a = st.c03[0][ra][p], b = st.c03[1][rb][p];
+					const int2 ax = st.c4ok[0][ra][p], bx = st.c4ok[1][rb][p];
+					if(!(ax.y & bx.y)) continue;
+					const long long dot = (long long) (a.x * b.x) + (long long) (a.y * b.y) + (long long) (a.z * b.z) +
+					                      (long long) (a.w * b.w) + (long long) (ax.x * bx.x);
+					double d = 1 - (double) dot / (st.nr[0][ra][p].x * st.nr[1][rb][p].x);
+					d = d < 0 ? 0 : d;
+					dist[q] += d;
+					++rows[q];
+				}
+			}
+		}
+	}
+	const size_t o = (((size_t) ks * ntiles + tile) * (TH * TH) + threadIdx.x) * 4;
+#pragma unroll
+	for(int q = 0; q < 4; ++q) {
+		part_dist[o + q] = dist[q];
+		part_rows[o + q] = rows[q];
+	}
+}
+
 /* the gates of cmpMats (matcmp.c:483-494) and the cell formats; shared by the device epilogue and the host one */
 __host__ __device__ __forceinline__ void mat_cell(double dist, unsigned rows, int len_i, int len_j, unsigned norm, unsigned minLength,
                                                   double minCov, double *d_out, double *n_out, bool *ok_out) {
@@ -607,12 +723,19 @@ static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, 
 		mp.order = order;
 		mp.alpha = alpha;
 		cudaEventRecord(ctx->ev0, ctx->stream);
-		const size_t dyn = method == CCG_MAT_COS ? (size_t) 2 * MT * (MP + 1) * sizeof(double) : 0;
-		if(dyn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
-		kern<<<(unsigned) ((long long) ntiles * nslices), TH * TH, dyn, ctx->stream>>>((const uint32_t *) ctx->mat_counts,
-		                                                                              (const uint32_t *) ctx->mat_tot_over, ctx->mat_lpad, d_tiles,
-		                                                                              ntiles, nslices, pos_per_slice, ctx->mat_lens, mp,
-		                                                                              ctx->mat_part_dist, ctx->mat_part_rows);
+		if(method == CCG_MAT_COS && !getenv("CCG_MAT_GENERIC_COS")) {
+			cudaFuncSetAttribute(k_matdist_cos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CosStage));
+			k_matdist_cos<<<(unsigned) ((long long) ntiles * nslices), TH * TH, sizeof(CosStage), ctx->stream>>>(
+			    (const uint32_t *) ctx->mat_counts, (const uint32_t *) ctx->mat_tot_over, ctx->mat_lpad, d_tiles, ntiles, nslices,
+			    pos_per_slice, mp, ctx->mat_part_dist, ctx->mat_part_rows);
+		} else {
+			const size_t dyn = method == CCG_MAT_COS ? (size_t) 2 * MT * (MP + 1) * sizeof(double) : 0;
+			if(dyn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn);
+			kern<<<(unsigned) ((long long) ntiles * nslices), TH * TH, dyn, ctx->stream>>>((const uint32_t *) ctx->mat_counts,
+			                                                                              (const uint32_t *) ctx->mat_tot_over, ctx->mat_lpad, d_tiles,
+			                                                                              ntiles, nslices, pos_per_slice, ctx->mat_lens, mp,
+			                                                                              ctx->mat_part_dist, ctx->mat_part_rows);
+		}
 		cudaEventRecord(ctx->ev1, ctx->stream);
 		ctx->ev_valid = 1;
 		ctx->launches++;
@@ -630,7 +753,8 @@ static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, 
 		snprintf(ctx->err, sizeof(ctx->err), "count-matrix distance run failed: %s", cudaGetErrorString(e));
 		rc = CCG_ERR_CUDA;
 	}
-	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k_matdist<%d> tiles=%d slices=%d", method, ntiles, nslices);
+	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "%s<%d> tiles=%d slices=%d",
+	         method == CCG_MAT_COS && !getenv("CCG_MAT_GENERIC_COS") ? "k_matdist_cos" : "k_matdist", method, ntiles, nslices);
 	cudaFree(d_tiles);
 	cudaFree(d_D);
 	cudaFree(d_N);

@@ -193,12 +193,35 @@ static ccg_ctx *open_fasta_context(const DistOpts *o) {
 	return ctx;
 }
 
-/* printDiff (fsacmp.c:635-644) for one pair's list from ccg_list_variants */
+/* printDiff (fsacmp.c:635-644) for one pair's list from ccg_list_variants: "(%d, %d)\t%c%d%c\n" per variant.  A listing
+ * is millions of short lines, so they are put together by hand in a buffer (the pair's prefix once, the label's digits
+ * backwards) instead of going through fprintf one by one. */
 static int print_variants(void *user, int sample_i, int sample_j, const uint64_t *variants, size_t count) {
 	FILE *f = (FILE *) user;
-	for(size_t k = 0; k < count; ++k)
-		fprintf(f, "(%d, %d)\t%c%d%c\n", sample_i, sample_j, "ACGT"[(variants[k] >> 2) & 3], (int) (variants[k] >> 4),
-		        "ACGT"[variants[k] & 3]);
+	static char buf[1 << 16];
+	char prefix[48];
+	const int plen = snprintf(prefix, sizeof(prefix), "(%d, %d)\t", sample_i, sample_j);
+	size_t used = 0;
+	for(size_t k = 0; k < count; ++k) {
+		if(used + (size_t) plen + 32 > sizeof(buf)) {
+			if(fwrite(buf, 1, used, f) != used) return 1;
+			used = 0;
+		}
+		memcpy(buf + used, prefix, (size_t) plen);
+		used += (size_t) plen;
+		buf[used++] = "ACGT"[(variants[k] >> 2) & 3];
+		/* the reference prints the unsigned counter with %d */
+		int label = (int) (variants[k] >> 4);
+		char digits[12];
+		int nd = 0;
+		unsigned mag = label < 0 ? 0u - (unsigned) label : (unsigned) label;
+		do { digits[nd++] = (char) ('0' + mag % 10); mag /= 10; } while(mag);
+		if(label < 0) buf[used++] = '-';
+		while(nd) buf[used++] = digits[--nd];
+		buf[used++] = "ACGT"[variants[k] & 3];
+		buf[used++] = '\n';
+	}
+	if(used && fwrite(buf, 1, used, f) != used) return 1;
 	return 0;
 }
 

@@ -61,6 +61,35 @@ def test_all_methods_against_the_oracle(ctx, method):
     assert "k_matdist" in ctx.last_kernel
 
 
+def test_cos_kernel_deep_and_identical_samples(ctx):
+    # k_matdist_cos: stages whose counts stay below 20,725 take the int32 dot product and the two-fma division, deeper
+    # stages the literal path (64-bit sums, a real division); identical samples give distances of (almost) zero; counts
+    # stay below 46,341, where the reference's int products start to wrap (matcmp.c:429-437)
+    n, length = 70, 1500 + 7
+    counts, totals = random_counts(n, length, seed=99, depth=300)
+    rng = np.random.default_rng(5)
+    for i in range(0, n, 3):
+        s = int(rng.integers(0, length - 200))
+        counts[i, s:s + 150, :4] = rng.integers(15000, 46000, size=(150, 4)).astype(np.uint16)
+    counts[11] = counts[10]
+    counts[40] = counts[10]
+    counts[5, 300:330] = 0                                   # positions without a single read: c1 = 0, never counted
+    totals = counts.astype(np.uint32).sum(axis=2).astype(np.uint32)
+    lens = np.full(n, length, np.int32)
+    lens[7] = 900
+    counts[7, 900:] = 0
+    totals[7, 900:] = 0
+    ctx.mat_set_problem(n, length)
+    for i in range(n):
+        ctx.mat_put_sample(i, counts[i, :lens[i]], totals[i, :lens[i]])
+    for kw in (dict(min_depth=15), dict(min_depth=0, min_cov=0.0, norm=1000), dict(min_depth=100, min_cov=0.3)):
+        D, N, dn, rows = ctx.mat_run(None, method="cos", **kw)
+        Do, No, dno = oracle.mat_matrix(counts, totals, lens, None, method="cos", **kw)
+        assert dn == dno and np.array_equal(N, No), kw
+        assert close(D, Do), (kw, float(np.max(np.abs(D - Do))))
+    assert "k_matdist_cos" in ctx.last_kernel
+
+
 def test_depth_gate_overlap_gate_and_short_samples(ctx):
     n, length = 18, 900
     counts, totals = random_counts(n, length, seed=99, low=0.3)

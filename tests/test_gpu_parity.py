@@ -85,6 +85,25 @@ def test_pair_epilogue_all_cell_types(ctx, elem, scale, norm):
         np.testing.assert_allclose(D, Do, rtol=REL_TOL, atol=0.0)
 
 
+@pytest.mark.parametrize("elem", [8, 4])
+def test_zero_over_zero_cells_print_like_the_reference(ctx, elem):
+    # -L 0 -C 0 with a pair that shares no included position and a normalisation weight: the reference divides 0 by 0.
+    # Its NaN has the sign bit set in both cell types ("-nan" in the Phylip text); the epilogue writes the same bits.
+    n, length = 6, 700
+    codes = synth.make_codes(n, length, seed=31, snp=0.02, nrun=0.0)
+    codes[1, :400] = 4
+    codes[2, 400:] = 4
+    seqs, masks, inc = oracle.encode_samples(codes)
+    include = np.ones(n, dtype=np.uint8)
+    D, N, dn, _ = api.fsa_cmp_thread_out(seqs, include, masks, length, pair=True, norm=1000, min_length=0, min_cov=0.0,
+                                         elem_size=elem, ctx=ctx)
+    Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=1000, min_length=0, min_cov=0.0, elem_size=elem)
+    assert dn == dno == n
+    assert np.isnan(Do).sum() == 1 and np.signbit(Do[np.isnan(Do)]).all()
+    assert np.array_equal(_bits(D), _bits(Do))
+    assert np.array_equal(_bits(N), _bits(No))
+
+
 def test_pair_gate_writes_minus_one(ctx):
     n, length = 20, 2000
     codes = synth.make_codes(n, length, seed=5, snp=0.02, nrun=0.0)
