@@ -1,33 +1,35 @@
 /*
- * k_pairdist_umma.cu -- K2a: the all-vs-all compare as an int8 contraction on
- * the tcgen05 tensor cores (int32 accumulation in TMEM), plus the operand
- * expansion and the finalising epilogue.
+ * k_pairdist_umma.cu -- K2a: the all-vs-all compare as a dense contraction on the tcgen05 tensor cores, plus the
+ * operand expansion and the finalising epilogue.
  *
- * Replaces the same reference code as K2b: maskProxi (proxi == 0)
- * fsacmp.c:355-389, fsacmpair fsacmp.c:587-633, fsacmp fsacmp.c:552-585 and
- * the pair loop + epilogue of cmpairFsaThrd / cmpFsaThrd
+ * Replaces the same reference code as K2b (k_pairdist_popc.cu): maskProxi (proxi == 0) fsacmp.c:355-389, fsacmpair
+ * fsacmp.c:587-633, fsacmp fsacmp.c:552-585 and the pair loop + epilogue of cmpairFsaThrd / cmpFsaThrd
  * (fsacmpthrd.c:261-480 / :108-259).
  *
- * Algebra.  Per base every sample gets three
- * "tetrahedral" int8 channels and one mask channel:
+ * Algebra.  Per base every sample gets three "tetrahedral" channels and one mask
+ * channel:
  *     A=(+1,+1,+1) C=(+1,-1,-1) G=(-1,+1,-1) T=(-1,-1,+1)  unknown=(0,0,0), m = known ? 1 : 0
- * Over the three code channels  S(i,j) = sum t_i.t_j = 3*match - mismatch  on
- * jointly known positions, over the mask channel  I(i,j) = sum m_i*m_j = the
- * inclusion count.  Hence   mismatch = (3*I - S) / 4   exactly, in int32
- * (|S|, I <= 3L < 2^31).  K = 4L bytes: 8 int8 ops per pairwise base comparison.
+ * Over the three code channels  S(i,j) = sum t_i.t_j = 3*match - mismatch  on jointly known positions, over the mask
+ * channel  I(i,j) = sum m_i*m_j = the inclusion count.  Hence   mismatch = (3*I - S) / 4   exactly, in int32
+ * (|S|, I <= 3L < 2^31).  K = 4L elements: 8 tensor ops per pairwise base comparison.
  *
- * Operand panel X (HBM, built by k_expand from the bit planes):
- *     X[slot][chunk][channel 0..3][128 bases]  int8   (K-major rows)
- * one 128-byte channel row = one SWIZZLE_128B row = one pipeline stage.
- *
- * GEMM work item = (tile of 128 rows x 256 columns of the lower triangle,
- * K slice of chunks); the kernel is persistent (one CTA per SM looping over items) and the CTAs
- * of a round are throttled into lock-step so that shared operand rows are served by L2.  Warp 0 lane 0 issues TMA (A: 128x128 B, B: 2 x 128x128 B
- * per stage, 4 stages); warp 1 lane 0 issues tcgen05.mma kind::i8 M=128 N=256
- * K=32 (4 per stage) into two TMEM accumulators (S: channels 0-2, I: channel 3);
- * warps 2-5 drain TMEM with tcgen05.ld and RED.ADD the int32 partials into the
- * dense C buffers (split-K is exact for integers).  k_finalize applies
- * (3I-S)/4 and the reference epilogue.
+ * What is in this file:
+ *   k_expand_fp4 / k_expand_fp4_rows   operand panel X in e2m1 (two values per byte), from the bit planes or straight
+ *                         from the reference's packed words (rows lent by the caller / streamed host rows):
+ *                         X[slot/128][chunkpair*4+channel][slot%128][128 B], one 128-byte channel row = 256 bases,
+ *                         tile-blocked so that a 128-row x 128-byte TMA box is 16 KiB contiguous
+ *   k_expand              the same panel in int8 (one value per byte, 128 bases per channel row), CCG_I8=1
+ *   k_pairdist_umma2<FP4> THE kernel: persistent CTA pairs (cluster of 2, tcgen05 cta_group::2), work item = (256 x 256
+ *                         macro tile of the lower triangle, K slice); per CTA a 6-stage ring of 32 KiB (its 128 rows of
+ *                         A + its half of B, TMA SWIZZLE_128B, complete_tx on the leader's mbarrier); warp 0 = TMA
+ *                         producer, warp 1 of the leader = MMA issuer (kind::mxf4.block_scale M256 N256 K64 with all
+ *                         block scales 1.0 and f32 accumulators, or kind::i8 K32 with two s32 accumulators), warps 2-5
+ *                         of both CTAs = epilogue: tcgen05.ld, f32 -> s32, RED.ADD into the dense C_S / C_I (integer
+ *                         split-K is exact).  The CTAs of a round run in lock-step (epoch counters in global memory) so
+ *                         that the operand rows neighbouring tiles share are served by L2; "thin" items run the last,
+ *                         mostly empty macro-tile row transposed with a small MMA N (see the kernel).
+ *   k_pairdist_umma       the first, single-CTA int8 kernel (128 x 256 tiles, 4 stages), kept for CCG_UMMA1=1 experiments
+ *   k_finalize_umma       mismatch = (3I - S) / 4 and the reference epilogue (epilogue.cuh) over the packed cells
  */
 #include <string.h>
 

@@ -278,14 +278,21 @@ def test_empty_and_degenerate_inputs(ctx):
     # nothing included
     D, N, dn, _ = api.fsa_cmp_thread_out(seqs, np.zeros(3, np.uint8), masks, 100, pair=True, ctx=ctx)
     assert dn == 0 and len(D) == 0
-    # an unsupported combination is a loud refusal, never a silent fallback: variant lists (-V) with proximity
-    # masking (-P)
+    # a call order the device cannot serve is a loud refusal, never a silent fallback: variant lists (-V) under
+    # proximity masking (-P) compare the whole packed words, which a packed upload made BEFORE -P was set has already
+    # ANDed with the rows' masks
     ctx.set_problem(3, 100, pair=True)
     ctx.put_samples_packed(seqs, masks)
     ctx.set_proximity(3)
     try:
         with pytest.raises(api.CcgError) as e:
             ctx.list_variants(pair=True)
+        assert e.value.code == 3 and "ccg_set_proximity before" in str(e.value)
+        # and the row form (-a) under -P is not built
+        ctx.set_problem(3, 100, pair=True)
+        ctx.put_samples_packed(seqs, masks)
+        with pytest.raises(api.CcgError) as e:
+            ctx.list_variants(row=2)
         assert e.value.code == 5
     finally:
         ctx.set_proximity(0)
