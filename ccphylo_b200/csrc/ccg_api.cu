@@ -2005,16 +2005,13 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 		return CCG_ERR_UNSUPPORTED;
 	}
 	/* -P: in pair mode the reference lists under maskProxi's mask (fsacmpthrd.c:410-414), built per batch below; in
-	 * shared-mask mode the proximity ranges are part of the global mask already (cdist.c:111).  The row form (-a) would
-	 * need the per-sample builder against every column sample (fsacmpthrd.c:545-553) as a mask: not built. */
+	 * shared-mask mode the proximity ranges are part of the global mask already (cdist.c:111); the row form (-a) walks
+	 * the new sample's mask after the per-sample builder against each column sample (fsacmpthrd.c:545-553). */
 	const int pair_proxi = pair && ctx->proxi && ctx->words > 0;
+	const int row_proxi = pair_proxi && last_row_only;
 	if(pair_proxi && ctx->codes_upload_masked) {
 		set_err(ctx, "variant listing (-V) with proximity masking (-P): call ccg_set_proximity before the packed rows are uploaded");
 		return CCG_ERR_ARG;
-	}
-	if(pair_proxi && last_row_only) {
-		set_err(ctx, "variant listing (-V) of an added row (-a) is not available together with proximity masking (-P)");
-		return CCG_ERR_UNSUPPORTED;
 	}
 	if(pair ? ctx->global_applied : !ctx->global_pending) {
 		set_err(ctx, pair ? "variant listing in pair mode needs a store without a global mask"
@@ -2053,6 +2050,26 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 			return CCG_ERR_NOMEM;
 		}
 	}
+	/* row form under -P: the new sample's planes are set aside as uploaded, its own builder is applied to the store's
+	 * copy (as ccg_run_row does), and everything is put back at the end */
+	void *d_raw = 0;
+	const int row_slot = slot_of[Dn - 1];
+	if(row_proxi) {
+		unsigned char *d_use = 0;
+		unsigned *d_clr = 0;
+		int first_used = -1;
+		int rcu = stage_use_flags(ctx, 0, row_slot, row_slot + 1, &d_use, &d_clr, (size_t) ctx->n_pad, &first_used);
+		cudaError_t e0 = rcu ? cudaErrorUnknown : cudaMalloc(&d_raw, (size_t) ctx->chunks * 3 * 16);
+		if(e0 == cudaSuccess) e0 = ccg_launch_row_planes(ctx, row_slot, d_raw, 0);
+		if(e0 == cudaSuccess && !ctx->proxi_snp_only) e0 = ccg_launch_sample_proxi(ctx, 0, 0, d_use, 1, d_clr);
+		if(e0 != cudaSuccess) {
+			if(!rcu) set_err(ctx, "variant listing of a row with proximity masking failed: %s", cudaGetErrorString(e0));
+			cudaFree(d_raw);
+			cudaFree(d_pmask);
+			free(slot_of);
+			return rcu ? rcu : CCG_ERR_CUDA;
+		}
+	}
 	int *d_slot = 0;
 	unsigned *d_counts = 0, *h_counts = 0;
 	unsigned long long *d_off = 0, *h_off = 0, *d_ent = 0, *h_ent = 0;
@@ -2075,7 +2092,8 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 		p.counts = d_counts;
 		p.pair_mask = d_pmask;
 		p.pair_mask_stride = BATCH;
-		if(d_pmask) e = ccg_launch_pair_proxi_mask(ctx, p);
+		p.row_raw = (const uint4 *) d_raw;
+		if(d_pmask) e = row_proxi ? ccg_launch_row_proxi_mask(ctx, p, row_slot) : ccg_launch_pair_proxi_mask(ctx, p);
 		if(e == cudaSuccess) e = ccg_launch_variants(ctx, p, 0, !pair);
 		if(e == cudaSuccess) e = cudaMemcpyAsync(h_counts, d_counts, (size_t) nb * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
 		if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -2134,6 +2152,16 @@ static int list_variants_impl(ccg_ctx *ctx, int pair, const unsigned char *inclu
 	if(e != cudaSuccess) {
 		set_err(ctx, "variant listing failed: %s", cudaGetErrorString(e));
 		rc = CCG_ERR_CUDA;
+	}
+	if(d_raw) {
+		/* the new sample's planes go back as uploaded */
+		cudaError_t er = ccg_launch_row_planes(ctx, row_slot, d_raw, 1);
+		if(er == cudaSuccess) er = cudaStreamSynchronize(ctx->stream);
+		if(er != cudaSuccess && !rc) {
+			set_err(ctx, "variant listing of a row: restoring the planes failed: %s", cudaGetErrorString(er));
+			rc = CCG_ERR_CUDA;
+		}
+		cudaFree(d_raw);
 	}
 	cudaFree(d_pmask);
 	cudaFree(d_slot);

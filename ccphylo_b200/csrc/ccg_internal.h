@@ -82,6 +82,7 @@ struct VariantParams {
 	unsigned long long *entries;        /* write pass: label << 4 | code_i << 2 | code_j */
 	uint32_t *pair_mask;                /* -V with -P: the batch's per-pair masks, [word][cell of the batch] (0 = none) */
 	long long pair_mask_stride;         /* cells per word row of pair_mask */
+	const uint4 *row_raw;               /* -V with -a and -P: the row sample's planes as uploaded, [chunk][h, l, m] (0 = the store's) */
 };
 
 struct UmmaParams {
@@ -330,6 +331,7 @@ cudaError_t ccg_launch_remask_all(ccg_ctx *ctx);
 /* k_variants.cu */
 cudaError_t ccg_launch_variants(ccg_ctx *ctx, const VariantParams &p, int write, int shared_mask);
 cudaError_t ccg_launch_pair_proxi_mask(ccg_ctx *ctx, const VariantParams &p);
+cudaError_t ccg_launch_row_proxi_mask(ccg_ctx *ctx, const VariantParams &p, int row_slot);
 
 /* k_matdist.cu */
 void ccg_mat_free(ccg_ctx *ctx);

@@ -49,7 +49,9 @@ k_variants(const uint32_t *__restrict__ planes, int n_pad, int chunks, int words
 #pragma unroll 1
 	for(int ch = 0; ch < chunks; ++ch) {
 		const size_t row = (size_t) ch * 3;
-		const uint4 ih = __ldg(P + (row + 0) * n_pad + i), il = __ldg(P + (row + 1) * n_pad + i);
+		/* (the row sample of -a with -P: its codes as uploaded -- the store's copy is proximity-masked for the run) */
+		const uint4 ih = p.row_raw ? __ldg(p.row_raw + row) : __ldg(P + (row + 0) * n_pad + i);
+		const uint4 il = p.row_raw ? __ldg(p.row_raw + row + 1) : __ldg(P + (row + 1) * n_pad + i);
 		const uint4 jh = __ldg(P + (row + 0) * n_pad + j), jl = __ldg(P + (row + 1) * n_pad + j);
 		uint4 m;
 		if(p.pair_mask) {
@@ -140,7 +142,50 @@ k_pair_proxi_mask(const uint32_t *__restrict__ planes, int n_pad, int chunks, in
 	}
 }
 
+/* -V with -a and -P: the mask cmpFsaRowThrd walks for column sample j (fsacmpthrd.c:543-553) -- the new sample's own
+ * mask (already through its own builder, fsacmpthrd.c:627-628) restricted to j's known positions, then the per-sample
+ * builder of the new sample against j: everything between two events at most proxi apart goes, both ends included
+ * (proxi_scan_words).  Events are defined on the codes as uploaded: p.row_raw for the new sample. */
+struct RowMaskEvents {
+	const uint32_t *planes, *raw;
+	int n_pad, j, snp_only;
+	long long len;
+	__device__ __forceinline__ uint32_t operator()(long long w) const {
+		const size_t pj = ((size_t) (w >> 2) * 3 * n_pad + j) * 4 + (size_t) (w & 3), step = (size_t) n_pad * 4;
+		const size_t pr = (size_t) (w >> 2) * 12 + (size_t) (w & 3);
+		return proxi_events(1, snp_only, planes[pj + 2 * step], planes[pj], planes[pj + step], raw[pr + 8], raw[pr], raw[pr + 4],
+		                    proxi_valid_bits(len, w * 32));
+	}
+};
+
+__global__ void __launch_bounds__(128)
+k_row_proxi_mask(const uint32_t *__restrict__ planes, int n_pad, int words, long long len, unsigned proxi, int snp_only, int row_slot,
+                 VariantParams p) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= p.ncells) return;
+	int r, c;
+	cell_to_pair(p.cell0 + t, r, c);
+	const int j = p.slot_of_rank[c];
+	PairMaskSink sink = {p.pair_mask + t, p.pair_mask_stride};
+	const size_t step = (size_t) n_pad * 4;
+#pragma unroll 1
+	for(int w = 0; w < words; ++w) {
+		const size_t base = ((size_t) (w >> 2) * 3 * n_pad) * 4 + (size_t) (w & 3) + 2 * step;
+		sink.col[(size_t) w * sink.stride] = planes[base + (size_t) row_slot * 4] & planes[base + (size_t) j * 4];
+	}
+	RowMaskEvents ev = {planes, reinterpret_cast<const uint32_t *>(p.row_raw), n_pad, j, snp_only, len};
+	proxi_scan_words(-1, 0, words, proxi, ev, sink);
+}
+
 } // namespace
+
+cudaError_t ccg_launch_row_proxi_mask(ccg_ctx *ctx, const VariantParams &p, int row_slot) {
+	if(p.ncells <= 0 || ctx->words == 0) return cudaSuccess;
+	k_row_proxi_mask<<<(unsigned) ((p.ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->words, (long long) ctx->len,
+	                                                                              ctx->proxi, ctx->proxi_snp_only, row_slot, p);
+	ctx->launches++;
+	return cudaGetLastError();
+}
 
 cudaError_t ccg_launch_pair_proxi_mask(ccg_ctx *ctx, const VariantParams &p) {
 	if(p.ncells <= 0 || ctx->words == 0) return cudaSuccess;

@@ -16,7 +16,7 @@
  *   - -V (variant listing) comes from the device as well (ccg_list_variants, same labels as the reference);
  *     -a appends one row to an existing matrix (ccg_run_row / ccg_mat_run_row);
  *   - -y masks methylation motifs on the device right after each upload (ccg_mask_motifs);
- *   - refused: -V with -P and -a; -y with -P in shared-mask mode (-a ignores -y, as the reference does).
+ *   - refused: -y with -P in shared-mask mode (-a ignores -y, as the reference does).
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -908,15 +908,10 @@ int main_dist(int argc, char **argv) {
 	if(!o.numFile && o.targetTemplate) o.numFile = 1;
 
 	/* -y with -P: in pair mode (-f bit 2) the two maskings commute and both run on the device; the shared mask of the
-	 * default mode is built from per-sample masks there, where a motif site would read as an unknown base.
-	 * -V with -P lists under the per-pair proximity mask on the device (ccg_list_variants); only the row form of -a,
-	 * which would need the per-sample builder against every column sample as a mask, is left out. */
-	const int refuse_y = o.methfilename && !o.addfilename && o.proxi && !(o.flag & 2);
-	const int refuse_v = o.diffilename && o.proxi && o.addfilename;
-	if(refuse_y || refuse_v) {
-		fprintf(stderr, "%s is not available on the GPU path of dist (use the CPU ccphylo for it).\n",
-		        refuse_y ? "-y / --methylation_motifs together with -P / --proximity without pairwise inclusion (-f 2)" :
-		                   "-V / --nucleotide_variations together with -P / --proximity and -a / --add");
+	 * default mode is built from per-sample masks there, where a motif site would read as an unknown base */
+	if(o.methfilename && !o.addfilename && o.proxi && !(o.flag & 2)) {
+		fprintf(stderr, "-y / --methylation_motifs together with -P / --proximity without pairwise inclusion (-f 2) is not available "
+		                "on the GPU path of dist (use the CPU ccphylo for it).\n");
 		return 1;
 	}
 	if(o.addfilename && o.filenames) return add_to_matrix(&o);

@@ -221,8 +221,6 @@ def test_refused_options_and_errors(built, tmp_path):
     a = os.path.join(td, "a.fsa")
     with open(a, "w") as f:
         f.write(">ref\nACGT\n")
-    p = run([BIN, "dist", "-r", "ref", "-a", a, "-i", a, a, "-V", "v.txt", "-P", "3"], td)
-    assert p.returncode == 1 and "-V / --nucleotide_variations together with -P / --proximity and -a / --add is not available on the GPU path" in p.stderr
     p = run([BIN, "dist", "-r", "ref", "-f", "1", "-i", a, a, "-y", "m.txt", "-P", "3"], td)
     assert p.returncode == 1 and "without pairwise inclusion (-f 2) is not available on the GPU path" in p.stderr
     p = run([BIN, "dist", "-r", "ref", "-i", a, os.path.join(td, "missing.fsa")], td)

@@ -87,6 +87,19 @@ def test_fasta_row_with_proximity_against_the_oracle(ctx, n, length, proxi, snp_
         assert "k_row_proxi" in ctx.last_kernel
         # the new sample's planes were put back as uploaded
         assert np.array_equal(ctx.inc_counts(), before)
+        # -V with -a and -P: fsacmpairint walks the mask the builder leaves for each column sample (fsacmpthrd.c:545-553)
+        got = ctx.list_variants(row=n)
+        want = []
+        for j in range(n):
+            pm = own.copy()
+            oracle.inc_pos(pm, codes[j], codes[n], proxi, variant)
+            v = oracle.list_variants(seqs[n], seqs[j], pm, length)
+            if v:
+                want.append(((n, j), v))
+        assert got == want
+        assert np.array_equal(ctx.inc_counts(), before)
+        D2, N2 = ctx.run_row(n, norm=1000, min_length=1, min_cov=0.5)
+        assert np.array_equal(D2.view(np.uint8), Do.view(np.uint8))
     finally:
         ctx.set_proximity(0)
     plain, _ = oracle.fsa_cmp_row(seqs, masks, n, length, norm=1000, min_length=1, min_cov=0.5)
@@ -152,10 +165,12 @@ def test_cli_add_fasta_row_against_the_reference_binary(built, tmp_path, args):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
-def test_cli_add_row_with_variant_file_against_the_reference_binary(built, tmp_path):
-    """-a with -V: the new row's variant lists are appended to the file (fsacmpthrd.c:632-637, :552-553)"""
+@pytest.mark.parametrize("extra", [[], ["-P", "8"], ["-P", "120"]], ids=["plain", "P8", "P120"])
+def test_cli_add_row_with_variant_file_against_the_reference_binary(built, tmp_path, extra):
+    """-a with -V: the new row's variant lists are appended to the file (fsacmpthrd.c:632-637, :552-553); with -P under
+    the mask the per-sample builder leaves for each column sample"""
     n, length = 6, 8000 + 3
-    rows = synth.make_ascii(n + 1, length, seed=33, snp=0.01, nrun=0.01)
+    rows = synth.make_ascii(n + 1, length, seed=33 + len(extra) * 7, snp=0.01, nrun=0.01)
     outs = {}
     for tag, exe in (("reference", REF_BIN), ("driver", BIN)):
         d = tmp_path / tag
@@ -164,9 +179,9 @@ def test_cli_add_row_with_variant_file_against_the_reference_binary(built, tmp_p
         for i in range(n + 1):
             synth.write_fasta(os.path.join(d, f"s{i}.fsa"), rows[i], header="ref", width=60)
         files = [os.path.join(d, f"s{i}.fsa") for i in range(n)]
-        p = _run([REF_BIN, "dist", "-r", "ref", "-f", "3", "-t", "1", "-V", "v.txt", "-i"] + files + ["-o", "m.phy", "-n", "m.num"], d)
+        p = _run([REF_BIN, "dist", "-r", "ref", "-f", "3", "-t", "1", "-V", "v.txt"] + extra + ["-i"] + files + ["-o", "m.phy", "-n", "m.num"], d)
         assert p.returncode == 0, p.stderr
-        p = _run([exe, "dist", "-r", "ref", "-f", "3", "-t", "1", "-V", "v.txt", "-a", os.path.join(d, f"s{n}.fsa"), "-i", files[0],
+        p = _run([exe, "dist", "-r", "ref", "-f", "3", "-t", "1", "-V", "v.txt"] + extra + ["-a", os.path.join(d, f"s{n}.fsa"), "-i", files[0],
                   "-o", "m.phy", "-n", "m.num"], d)
         assert p.returncode == 0, p.stderr
         outs[tag] = (open(os.path.join(d, "v.txt")).read(), open(os.path.join(d, "m.phy")).read(), open(os.path.join(d, "m.num")).read())

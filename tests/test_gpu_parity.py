@@ -288,12 +288,6 @@ def test_empty_and_degenerate_inputs(ctx):
         with pytest.raises(api.CcgError) as e:
             ctx.list_variants(pair=True)
         assert e.value.code == 3 and "ccg_set_proximity before" in str(e.value)
-        # and the row form (-a) under -P is not built
-        ctx.set_problem(3, 100, pair=True)
-        ctx.put_samples_packed(seqs, masks)
-        with pytest.raises(api.CcgError) as e:
-            ctx.list_variants(row=2)
-        assert e.value.code == 5
     finally:
         ctx.set_proximity(0)
 

@@ -235,8 +235,6 @@ def test_option_scanner_dialect(built, tmp_path):
     a.write_text(">ref\nACGT\n")
     p = run("-pf1", "-s", "-W", "100", "-rref", "-i", str(a), str(a), "-P", "2", "-y", "m.txt")
     assert p.returncode == 1 and "-y / --methylation_motifs together with -P / --proximity without pairwise inclusion (-f 2) is not available on the GPU path" in p.stderr
-    p = run("-r", "ref", "-a", "x", "-V", "v.txt", "-P", "2", str(a), str(a))
-    assert p.returncode == 1 and "-V / --nucleotide_variations together with -P / --proximity and -a / --add" in p.stderr
     # -a reads the existing matrix before it needs the device: a multi-matrix file is refused as the reference does
     m = tmp_path / "m.phy"
     m.write_text("%10d\na.fsa\nb.fsa\t1\n%10d\na.fsa\nb.fsa\t2\n" % (2, 2))
