@@ -129,7 +129,12 @@ def mat_main(args, rank, world, local_rank, emit, log, ClockSampler, measured_pe
     len_r = p1 - p0
     t_gen = time.time()
     ref, samples = make_samples(length)
-    mine = [np.ascontiguousarray(s[p0:p1]) for s in samples]
+    # this rank's slice of every distinct sample in PINNED host memory: the e2e arm's uploads are real asynchronous
+    # copies (the contract's "from pinned host memory"), not staged through the driver's bounce buffer
+    mine = []
+    for s_ in samples:
+        t_ = torch.from_numpy(np.ascontiguousarray(s_[p0:p1])).pin_memory()
+        mine.append(t_.numpy())
     log(f"[rank {rank}] {DISTINCT} distinct samples x {length} positions generated in {time.time() - t_gen:.1f}s; slice {p0}..{p1}")
     L = api.load()
     ctx = api.Context(local_rank)
