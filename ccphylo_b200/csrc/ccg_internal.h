@@ -247,6 +247,8 @@ struct ccg_ctx {
 	double *mat_part_dist;
 	unsigned *mat_part_rows, *mat_rows;
 	size_t mat_part_cap;
+	void *mat_out_D, *mat_out_N, *mat_tiles;   /* device results and tile list of a run, kept and grown between runs */
+	size_t mat_cells_cap, mat_tiles_cap;
 
 	/* `trim` (k_trim.cu): translated code bytes of the current and of the reference sample, the (shared or own) mask,
 	 * the event words of the proximity pass, the columns where some sample differs from the first one */

@@ -342,8 +342,9 @@ constexpr int COS_FAST_MAX = 20724;
 
 struct CosStage {
 	int4 c03[2][MT][MPC + 1];     /* A C G T */
-	int2 c4ok[2][MT][MPC + 1];    /* '-', counts flag: minDepth <= total && c1 != 0 */
-	double2 nr[2][MT][MPC + 1];   /* sqrt(c1), 1 / sqrt(c1) */
+	int c4[2][MT][MPC + 1];       /* '-' */
+	double2 nr[2][MT][MPC + 1];   /* sqrt(c1), 1 / sqrt(c1); NaN, NaN when the position does not count for this sample */
+	unsigned ok[2][MT];           /* bit p: position p of the stage counts (minDepth <= total && c1 != 0) */
 };
 
 __global__ void __launch_bounds__(TH * TH, 3)
@@ -380,31 +381,44 @@ k_matdist_cos(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ 
 			                              (unsigned long long) (long long) (c4 * c4);
 			const double nv = sqrt((double) sq);
 			big |= (c0 | c1 | c2 | c3 | c4) > COS_FAST_MAX;          /* all five are below 2^16: the OR bounds the largest */
+			/* A position that does not count for this sample gets NaN norms: every pair it is part of then computes a NaN
+			 * distance, which fails the `d > 0` test below and adds nothing -- no flag in the inner loop.  The counted
+			 * positions (rowsInc) are the popcount of the AND of the two samples' bit masks, once per stage. */
+			const bool ok = mp.minDepth <= tot && sq != 0;
+			const double qnan = __longlong_as_double(0x7FF8000000000000LL);
 			st.c03[which][r][p] = make_int4(c0, c1, c2, c3);
-			st.c4ok[which][r][p] = make_int2(c4, (mp.minDepth <= tot && sq != 0) ? 1 : 0);
-			st.nr[which][r][p] = make_double2(nv, sq ? 1.0 / nv : 0.0);
+			st.c4[which][r][p] = c4;
+			/* the reciprocal only seeds the correction step of the division: rsqrt's 1 ulp is plenty */
+			st.nr[which][r][p] = ok ? make_double2(nv, rsqrt((double) sq)) : make_double2(qnan, qnan);
+			/* MPC = 16 consecutive lanes hold the 16 positions of one sample */
+			const unsigned bits = __ballot_sync(0xffffffffu, ok);
+			if(p == 0) st.ok[which][r] = (bits >> (threadIdx.x & 16)) & 0xFFFFu;
 		}
 		/* (the OR of the counts can exceed the limit while every count is below it: that only sends a stage down the
 		 * literal path more often than needed) */
 		big = __syncthreads_or(big);
 		if(!any_on) continue;
+		{
+			const unsigned ka0 = st.ok[0][li], ka1 = st.ok[0][li + TH], kb0 = st.ok[1][lj], kb1 = st.ok[1][lj + TH];
+			rows[0] += (unsigned) __popc(ka0 & kb0);
+			rows[1] += (unsigned) __popc(ka0 & kb1);
+			rows[2] += (unsigned) __popc(ka1 & kb0);
+			rows[3] += (unsigned) __popc(ka1 & kb1);
+		}
 		if(!big) {
 #pragma unroll 4
 			for(int p = 0; p < MPC; ++p) {
 				const int4 a0 = st.c03[0][li][p], a1 = st.c03[0][li + TH][p], b0 = st.c03[1][lj][p], b1 = st.c03[1][lj + TH][p];
-				const int2 a0x = st.c4ok[0][li][p], a1x = st.c4ok[0][li + TH][p], b0x = st.c4ok[1][lj][p], b1x = st.c4ok[1][lj + TH][p];
+				const int a0x = st.c4[0][li][p], a1x = st.c4[0][li + TH][p], b0x = st.c4[1][lj][p], b1x = st.c4[1][lj + TH][p];
 				const double2 na0 = st.nr[0][li][p], na1 = st.nr[0][li + TH][p], nb0 = st.nr[1][lj][p], nb1 = st.nr[1][lj + TH][p];
 #define CCG_COS_PAIR(q, A, AX, NA, B, BX, NB)                                                            \
 	{                                                                                                    \
-		const int dot = A.x * B.x + A.y * B.y + A.z * B.z + A.w * B.w + AX.x * BX.x;                     \
+		const int dot = A.x * B.x + A.y * B.y + A.z * B.z + A.w * B.w + AX * BX;                         \
 		const double dd = (double) dot, den = NA.x * NB.x, yy = NA.y * NB.y;                             \
 		const double q0 = dd * yy;                                                                       \
 		const double qq = fma(fma(-den, q0, dd), yy, q0);                                                \
-		double d = 1.0 - qq;                                                                             \
-		d = d < 0 ? 0 : d;                                                                               \
-		const int ok = AX.y & BX.y;                                                                      \
-		dist[q] += ok ? d : 0.0;                                                                         \
-		rows[q] += (unsigned) ok;                                                                        \
+		const double d = 1.0 - qq;                                                                       \
+		if(d > 0) dist[q] += d;                          /* the clamp; false for the NaN of a gated position */ \
 	}
 				CCG_COS_PAIR(0, a0, a0x, na0, b0, b0x, nb0)
 				CCG_COS_PAIR(1, a0, a0x, na0, b1, b1x, nb1)
@@ -418,15 +432,13 @@ k_matdist_cos(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ 
 #pragma unroll
 				for(int q = 0; q < 4; ++q) {
 					const int ra = li + TH * (q >> 1), rb = lj + TH * (q & 1);
+					if(!((st.ok[0][ra] & st.ok[1][rb]) >> p & 1u)) continue;
 					const int4 a = st.c03[0][ra][p], b = st.c03[1][rb][p];
-					const int2 ax = st.c4ok[0][ra][p], bx = st.c4ok[1][rb][p];
-					if(!(ax.y & bx.y)) continue;
 					const long long dot = (long long) (a.x * b.x) + (long long) (a.y * b.y) + (long long) (a.z * b.z) +
-					                      (long long) (a.w * b.w) + (long long) (ax.x * bx.x);
+					                      (long long) (a.w * b.w) + (long long) (st.c4[0][ra][p] * st.c4[1][rb][p]);
 					double d = 1 - (double) dot / (st.nr[0][ra][p].x * st.nr[1][rb][p].x);
 					d = d < 0 ? 0 : d;
 					dist[q] += d;
-					++rows[q];
 				}
 			}
 		}
@@ -554,6 +566,11 @@ void ccg_mat_free(ccg_ctx *ctx) {
 	cudaFree(ctx->mat_part_dist); ctx->mat_part_dist = 0;
 	cudaFree(ctx->mat_part_rows); ctx->mat_part_rows = 0;
 	cudaFree(ctx->mat_rows); ctx->mat_rows = 0;
+	cudaFree(ctx->mat_out_D); ctx->mat_out_D = 0;
+	cudaFree(ctx->mat_out_N); ctx->mat_out_N = 0;
+	cudaFree(ctx->mat_tiles); ctx->mat_tiles = 0;
+	ctx->mat_cells_cap = 0;
+	ctx->mat_tiles_cap = 0;
 	cudaFree(ctx->mat_rank); ctx->mat_rank = 0;
 	cudaFree(ctx->mat_stage); ctx->mat_stage = 0;
 	free(ctx->mat_hlens); ctx->mat_hlens = 0;
@@ -702,13 +719,34 @@ static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, 
 	}
 	int rc = CCG_OK;
 	const size_t cells = row_slot >= 0 ? (size_t) Dn - 1 : (size_t) Dn * (Dn - 1) / 2;
-	int2 *d_tiles = 0;
-	void *d_D = 0, *d_N = 0;
-	unsigned *d_rows = 0;
-	cudaError_t e = cudaMalloc(&d_tiles, (size_t) ntiles * sizeof(int2));
-	if(e == cudaSuccess) e = cudaMalloc(&d_D, cells * 8);
-	if(e == cudaSuccess && N) e = cudaMalloc(&d_N, cells * 8);
-	if(e == cudaSuccess && rows_inc) e = cudaMalloc(&d_rows, cells * 4);
+	/* tile list and device results: kept between runs and only grown (cudaMalloc / cudaFree per run cost up to
+	 * hundreds of milliseconds on some hosts) */
+	cudaError_t e = cudaSuccess;
+	if(ctx->mat_tiles_cap < (size_t) ntiles || ctx->mat_cells_cap < cells) {
+		e = cudaStreamSynchronize(ctx->stream);
+		if(e == cudaSuccess && ctx->mat_tiles_cap < (size_t) ntiles) {
+			cudaFree(ctx->mat_tiles);
+			ctx->mat_tiles = 0;
+			ctx->mat_tiles_cap = 0;
+			e = cudaMalloc(&ctx->mat_tiles, (size_t) ntiles * sizeof(int2));
+			if(e == cudaSuccess) ctx->mat_tiles_cap = (size_t) ntiles;
+		}
+		if(e == cudaSuccess && ctx->mat_cells_cap < cells) {
+			cudaFree(ctx->mat_out_D);
+			cudaFree(ctx->mat_out_N);
+			cudaFree(ctx->mat_rows);
+			ctx->mat_out_D = ctx->mat_out_N = 0;
+			ctx->mat_rows = 0;
+			ctx->mat_cells_cap = 0;
+			e = cudaMalloc(&ctx->mat_out_D, cells * 8);
+			if(e == cudaSuccess) e = cudaMalloc(&ctx->mat_out_N, cells * 8);
+			if(e == cudaSuccess) e = cudaMalloc(&ctx->mat_rows, cells * 4);
+			if(e == cudaSuccess) ctx->mat_cells_cap = cells;
+		}
+	}
+	int2 *d_tiles = (int2 *) ctx->mat_tiles;
+	void *d_D = ctx->mat_out_D, *d_N = N ? ctx->mat_out_N : 0;
+	unsigned *d_rows = rows_inc ? ctx->mat_rows : 0;
 	if(e == cudaSuccess && ctx->world > 1) {
 		e = cudaMemsetAsync(d_D, 0, cells * 8, ctx->stream);
 		if(e == cudaSuccess && d_N) e = cudaMemsetAsync(d_N, 0, cells * 8, ctx->stream);
@@ -755,10 +793,6 @@ static int mat_run_impl(ccg_ctx *ctx, const unsigned char *include, int method, 
 	}
 	snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "%s<%d> tiles=%d slices=%d",
 	         method == CCG_MAT_COS && !getenv("CCG_MAT_GENERIC_COS") ? "k_matdist_cos" : "k_matdist", method, ntiles, nslices);
-	cudaFree(d_tiles);
-	cudaFree(d_D);
-	cudaFree(d_N);
-	cudaFree(d_rows);
 	return rc;
 }
 
