@@ -24,6 +24,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include "ccphylo_gpu.h"
 #include "cmdline.h"
@@ -72,14 +74,54 @@ static FILE *open_out(const char *name) {
 /* ------------------------------------------------------------------------------------------
  * result matrices: packed lower triangle in pinned host memory
  * ------------------------------------------------------------------------------------------ */
-static void *alloc_cells(size_t n, int elem) {
-	size_t cells = n > 1 ? n * (n - 1) / 2 : 1;
-	void *p = ccg_host_alloc(cells * (size_t) elem);
+/* -H / --mmap (matrix.c:116-231 ltdMatrixMinit): the matrix lives in an unlinked temporary file that is mapped into
+ * memory, for sample sets whose matrices exceed the host's RAM.  The file goes where the reference's tmpF (tmp.c:27-76)
+ * puts it: -T dir/ -> dir/.kma-XXXXXX, -T prefix -> prefix.tmp<k>, no -T -> tmpfile(). */
+static FILE *tmp_file(const char *location) {
+	static int counter = 0;
+	if(!location || !*location) return tmpfile();
+	const size_t len = strlen(location);
+	char *name = malloc(len + 32);
+	if(!name) return 0;
+	FILE *f = 0;
+	if(location[len - 1] == '/') {
+		sprintf(name, "%s.kma-XXXXXX", location);
+		const int fd = mkstemp(name);
+		if(fd >= 0 && (f = fdopen(fd, "wb+"))) unlink(name);
+	} else {
+		sprintf(name, "%s.tmp%d", location, counter++);
+		if((f = fopen(name, "wb+"))) unlink(name);
+	}
+	free(name);
+	return f;
+}
+
+void *dist_alloc_cells(const DistOpts *o, size_t n, int elem) {
+	const size_t cells = n > 1 ? n * (n - 1) / 2 : 1, bytes = cells * (size_t) elem;
+	void *p;
+	if(o->mmap_matrix) {
+		FILE *f = tmp_file(o->tmpdir);
+		if(!f || ftruncate(fileno(f), (off_t) bytes)) die_errno();
+		p = mmap(0, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fileno(f), 0);
+		if(p == MAP_FAILED) {
+			fprintf(stderr, "MMAP failed:\n");
+			die_errno();
+		}
+		fclose(f);                               /* the mapping keeps the (unlinked) file alive */
+		return p;
+	}
+	p = ccg_host_alloc(bytes);
 	if(!p) {
-		fprintf(stderr, "Error: cannot allocate %zu bytes of pinned host memory\n", cells * (size_t) elem);
+		fprintf(stderr, "Error: cannot allocate %zu bytes of pinned host memory\n", bytes);
 		exit(1);
 	}
 	return p;
+}
+
+void dist_free_cells(const DistOpts *o, void *p, size_t n, int elem) {
+	if(!p) return;
+	if(o->mmap_matrix) munmap(p, (n > 1 ? n * (n - 1) / 2 : 1) * (size_t) elem);
+	else ccg_host_free(p);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -236,8 +278,8 @@ static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, un
 		fprintf(stderr, "All sequences were trimmed away.\n");
 		return 0;
 	}
-	void *D = alloc_cells((size_t) included, o->elem_size);
-	void *N = (pair && noutfile) ? alloc_cells((size_t) included, o->elem_size) : 0;
+	void *D = dist_alloc_cells(o, (size_t) included, o->elem_size);
+	void *N = (pair && noutfile) ? dist_alloc_cells(o, (size_t) included, o->elem_size) : 0;
 	int Dn = 0, rc;
 	const double t_cmp = now_s();
 	if(pair) {
@@ -270,8 +312,8 @@ static int compare_and_print(const DistOpts *o, ccg_ctx *ctx, int n, int len, un
 		phy_write_mt(outfile, D, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision, o->threads);
 		if(N) phy_write_mt(n_into_out ? outfile : noutfile, N, o->elem_size, o->byteScale, Dn, names, include, comment, o->flag, o->precision, o->threads);
 	}
-	ccg_host_free(D);
-	ccg_host_free(N);
+	dist_free_cells(o, D, (size_t) included, o->elem_size);
+	dist_free_cells(o, N, (size_t) included, o->elem_size);
 	return Dn;
 }
 
@@ -870,8 +912,8 @@ int main_dist(int argc, char **argv) {
 			case 'p': o.elem_size = 4; break;
 			case 's': o.elem_size = 2; o.byteScale = optscan_optional_double(&sc, o.byteScale); break;
 			case 'b': o.elem_size = 1; o.byteScale = optscan_optional_double(&sc, o.byteScale); break;
-			case 'H': break;
-			case 'T': (void) optscan_arg(&sc); break;
+			case 'H': o.mmap_matrix = 1; break;
+			case 'T': o.tmpdir = optscan_arg(&sc); break;
 			case 't': o.threads = (int) optscan_long(&sc); break;
 			case 'h': return help_message(stdout);
 			default:

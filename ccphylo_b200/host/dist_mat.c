@@ -171,8 +171,8 @@ static void one_template(const DistOpts *o, ccg_ctx *ctx, int n, char **filename
 	if(included < 2) return;                        /* nothing to print (dist.c:175: 1 < D->n) */
 
 	const size_t cells = (size_t) included * (included - 1) / 2;
-	void *D = ccg_host_alloc(cells * (size_t) o->elem_size);
-	void *N = ccg_host_alloc(cells * (size_t) o->elem_size);
+	void *D = dist_alloc_cells(o, (size_t) included, o->elem_size);
+	void *N = dist_alloc_cells(o, (size_t) included, o->elem_size);
 	uint32_t *rows = malloc(cells * sizeof(uint32_t));
 	if(!D || !N || !rows) die_errno();
 	int Dn = 0;
@@ -195,8 +195,8 @@ static void one_template(const DistOpts *o, ccg_ctx *ctx, int n, char **filename
 	if(noutfile) phy_write_mt(noutfile, N, o->elem_size, o->byteScale, Dn, filenames, include, target, o->flag, o->precision, o->threads);
 	free(slot_of);
 	free(rows);
-	ccg_host_free(D);
-	ccg_host_free(N);
+	dist_free_cells(o, D, (size_t) included, o->elem_size);
+	dist_free_cells(o, N, (size_t) included, o->elem_size);
 }
 
 /* ltdRowThrd (ltdmatrixthrd.c:564-611) + cmpMatRowThrd (:111-181) */

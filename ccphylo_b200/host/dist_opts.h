@@ -17,7 +17,14 @@ typedef struct {
 	unsigned flag, norm, minDepth, minLength, proxi;
 	int elem_size, precision, threads;
 	char sep;
+	int mmap_matrix;           /* -H: result matrices on the disk (matrix.c:116 ltdMatrixMinit) */
+	char *tmpdir;              /* -T: where their files go (tmp.c:27 tmpF) */
 } DistOpts;
+
+/* result matrices: packed lower triangle of n samples, elem bytes per cell -- pinned host memory, or with -H a
+ * mapping of an unlinked temporary file (dist_main.c) */
+void *dist_alloc_cells(const DistOpts *o, size_t n, int elem);
+void dist_free_cells(const DistOpts *o, void *p, size_t n, int elem);
 
 /* dist_mat.c: KMA .mat count-matrix inputs (ltdmatrixthrd.c:376, ltdmatrix.c:32) */
 void dist_mat_files(const DistOpts *o, FILE *outfile, FILE *noutfile);

@@ -216,6 +216,42 @@ def test_fasta_gz_input_stdout_and_long_options(built, tmp_path):
     assert p.stdout == case["phy"].replace("s0\n", "s0.gz\n").replace("s1\t", "s1.gz\t").replace("s2\t", "s2.gz\t").replace("s3\t", "s3.gz\t")
 
 
+def test_file_backed_matrices(built, tmp_path):
+    """-H / --mmap with and without -T (matrix.c:116 ltdMatrixMinit, tmp.c:27 tmpF): the matrices live in unlinked
+    temporary files; the output is the one of the in-memory run and nothing is left behind"""
+    case = next(c for c in CASES if c["name"] == "c1_pair_W")
+    td = str(tmp_path)
+    files = []
+    for nm, k in zip(case["names"], case["seq_ids"]):
+        path = os.path.join(td, nm)
+        with open(path, "w") as f:
+            f.write(">ref\n" + "\n".join(POOL[k][s:s + 60] for s in range(0, len(POOL[k]), 60)) + "\n")
+        files.append(path)
+    os.mkdir(os.path.join(td, "scratch"))
+    base = [BIN, "dist", "-r", "ref", "-f", "3", "-W", "1000000", "-n", "-"]
+    plain = run(base + ["-i"] + files, td)
+    assert plain.returncode == 0 and plain.stdout.startswith(case["phy"])
+    for extra in (["-H"], ["-H", "-T", "scratch/"], ["--mmap", "--tmp", "scratch/pre"], ["-p", "-H"], ["-b", "1", "-H", "-T", "scratch/"]):
+        a = run(base + extra + ["-i"] + files, td)
+        b = run(base + [x for x in extra if x not in ("-H", "--mmap")] + ["-i"] + files, td)
+        assert a.returncode == 0 and a.stdout == b.stdout and a.stderr == b.stderr, extra
+    assert os.listdir(os.path.join(td, "scratch")) == []
+    # .mat inputs go through the same allocation
+    G_ = helpers.load_golden("mat_dist.json")
+    mc = next(c for c in G_["cases"] if c["name"] == "rand_cos")
+    paths = []
+    for nm, k in zip(mc["names"], mc["text_ids"]):
+        path = os.path.join(td, nm)
+        with open(path, "w") as f:
+            f.write(G_["pool"][k])
+        paths.append(path)
+    cmd = [BIN, "dist", "-r", mc["template"], "-i"] + paths + mc["args"]
+    a = run(cmd + ["-H", "-T", "scratch/"], td)
+    b = run(cmd, td)
+    assert a.returncode == 0 and len(a.stdout) > 50 and a.stdout == b.stdout and a.stderr == b.stderr
+    assert os.listdir(os.path.join(td, "scratch")) == []
+
+
 def test_refused_options_and_errors(built, tmp_path):
     td = str(tmp_path)
     a = os.path.join(td, "a.fsa")
