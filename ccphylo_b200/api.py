@@ -31,7 +31,7 @@ EXPORTS = [
     "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs", "ccg_list_variants_row",
     "ccg_init_multi", "ccg_init_multi_devices", "ccg_multi_gpus", "ccg_group_export", "ccg_group_join", "ccg_group_leave",
     "ccg_mat_run_partial", "ccg_mat_finalize_host", "ccg_group_set_alignment", "ccg_group_set_output", "ccg_group_row_block", "ccg_group_row_owner", "ccg_group_cells",
-    "ccg_trim_begin", "ccg_trim_sample", "ccg_trim_keep_reference", "ccg_trim_get_mask", "ccg_trim_end",
+    "ccg_sample_count_masked", "ccg_trim_begin", "ccg_trim_sample", "ccg_trim_keep_reference", "ccg_trim_get_mask", "ccg_trim_end",
 ]
 GROUP_HANDLE_BYTES = 128
 
@@ -134,6 +134,7 @@ def load():
     L.ccg_mat_run_partial.argtypes = [vp, vp, i, C.c_uint, C.c_double, C.c_uint, vp, vp, vp]
     L.ccg_mat_finalize_host.argtypes = [i, vp, vp, vp, vp, C.c_uint, C.c_uint, C.c_double, i, C.c_double, vp, vp, vp, vp]
     L.ccg_mat_run_row.argtypes = [vp, i, i, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_double, vp, vp, vp]
+    L.ccg_sample_count_masked.argtypes = [vp, i, vp]
     L.ccg_trim_begin.argtypes = [vp, i, C.c_uint]
     L.ccg_trim_sample.argtypes = [vp, vp, vp, i, i, vp]
     L.ccg_trim_keep_reference.argtypes = [vp]
@@ -295,6 +296,12 @@ class Context:
 
     def sync(self):
         self._ck(self._L.ccg_sync(self._h))
+
+    def sample_count_masked(self, slot):
+        """getNpos of a shared-mask reference candidate after maskMotifs + getIncPosPtr(seq, seq, proxi); store unchanged"""
+        inc = C.c_uint(0)
+        self._ck(self._L.ccg_sample_count_masked(self._h, slot, C.byref(inc)))
+        return inc.value
 
     def set_proximity(self, proxi, snp_events_only=False):
         """-P proxi; snp_events_only selects the event definition of -f 8 / -f 32 (dist.c:802-806)."""

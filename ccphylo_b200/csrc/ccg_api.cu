@@ -563,6 +563,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 		ctx->global_applied = 0;
 		ctx->global_pending = 0;
 		ctx->remask_pending = 0;
+		ctx->motif_applied = 0;
 		ctx->codes_upload_masked = 0;
 		ctx->bor_pending = 0;
 		ctx->planes_stale = 0;
@@ -603,6 +604,7 @@ extern "C" int ccg_set_problem(ccg_ctx *ctx, int n, int len, int pair_mode) {
 	ctx->global_applied = 0;
 	ctx->global_pending = 0;
 	ctx->remask_pending = 0;
+	ctx->motif_applied = 0;
 	ctx->codes_upload_masked = 0;
 	ctx->bor_pending = 0;
 	ctx->planes_stale = 0;
@@ -687,13 +689,22 @@ extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include,
 	CK(ctx, cudaSetDevice(ctx->device));
 	NEED_PLANES(ctx);
 	if(!ctx->d_gmask) CK(ctx, cudaMalloc(&ctx->d_gmask, (size_t) (ctx->words + 1) * sizeof(uint32_t)));
+	/* -y together with -P: the events of the proximity pass are defined on the sequences (cdist.c:109-111: maskMotifs
+	 * only narrows the shared mask, getIncPosPtr then looks at the codes), so the motif sites must not be in the
+	 * samples' mask planes yet, where they would read as unknown bases.  The masking is done HERE, after the
+	 * proximity pass; a caller that has already run ccg_mask_motifs on this problem cannot be served. */
+	const int motifs_here = ctx->motif_n > 0 && !ctx->motif_applied && ctx->words > 0;
+	if(ctx->motif_n > 0 && ctx->motif_applied && ctx->proxi) {
+		set_err(ctx, "shared mask with -y and -P: leave the motif masking to ccg_build_global_mask (no ccg_mask_motifs before it)");
+		return CCG_ERR_UNSUPPORTED;
+	}
 	unsigned char *d_use = 0;
 	unsigned *d_cnt = 0;
 	int first = -1;
-	int rc = stage_use_flags(ctx, include, 0, ctx->n, &d_use, &d_cnt, 2, &first);
+	int rc = stage_use_flags(ctx, include, 0, ctx->n, &d_use, &d_cnt, 4 + (motifs_here ? (size_t) ctx->n_pad : 0), &first);
 	if(rc) return rc;
 	cudaError_t e = cudaMemsetAsync(ctx->d_gmask, 0, (size_t) (ctx->words + 1) * sizeof(uint32_t), ctx->stream);
-	if(e == cudaSuccess) e = ccg_launch_build_global_mask(ctx, d_use, d_cnt);
+	if(e == cudaSuccess) e = ccg_launch_build_global_mask(ctx, d_use, d_cnt, 0);
 	unsigned *d_final = d_cnt;
 	if(e == cudaSuccess && ctx->proxi && first >= 0) {
 		/* -P: every included sample also clears the runs between its close events against the first included
@@ -701,6 +712,13 @@ extern "C" int ccg_build_global_mask(ccg_ctx *ctx, const unsigned char *include,
 		e = ccg_launch_sample_proxi(ctx, 1, first, d_use, 0, 0);
 		if(e == cudaSuccess) e = ccg_launch_count_mask(ctx, d_cnt + 1);
 		d_final = d_cnt + 1;
+	}
+	if(e == cudaSuccess && motifs_here && first >= 0) {
+		/* maskMotifs (cdist.c:109,137) of every slot into its mask plane, then the planes ANDed into the mask */
+		e = ccg_launch_motif_mask(ctx, 0, ctx->n, d_cnt + 4);
+		if(e == cudaSuccess) e = ccg_launch_build_global_mask(ctx, d_use, d_cnt + 2, 1);
+		d_final = d_cnt + 2;
+		ctx->motif_applied = 1;
 	}
 	unsigned inc = 0;
 	if(e == cudaSuccess) e = cudaMemcpyAsync(&inc, d_final, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
@@ -765,6 +783,7 @@ extern "C" int ccg_mask_motifs(ccg_ctx *ctx, int first, int count, unsigned *inc
 		unsigned *d_removed = (unsigned *) ctx->d_stage;
 		CK(ctx, cudaMemsetAsync(d_removed, 0, (size_t) count * sizeof(unsigned), ctx->stream));
 		CK(ctx, ccg_launch_motif_mask(ctx, first, count, d_removed));
+		ctx->motif_applied = 1;
 	}
 	if(inc_out) CK(ctx, cudaMemcpyAsync(inc_out, ctx->d_inc + first, (size_t) count * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -811,6 +830,59 @@ extern "C" int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int appl
 		set_err(ctx, "per-sample proximity masking failed: %s", cudaGetErrorString(e));
 		return CCG_ERR_CUDA;
 	}
+	return CCG_OK;
+}
+
+/* The count the reference's inclusion test looks at for a shared-mask REFERENCE candidate under -y and -P (cdist.c:137-140:
+ * maskMotifs + getIncPosPtr(includes, seq, seq, proxi) + getNpos), without leaving a trace in the store: the candidate's
+ * planes are set aside, masked, counted and put back -- ccg_build_global_mask needs them as uploaded. */
+extern "C" int ccg_sample_count_masked(ccg_ctx *ctx, int slot, unsigned *inc_out) {
+	CCG_MULTI_SOLO(ctx, "motif / proximity masking (-y, -P)", ccg_sample_count_masked(m0, slot, inc_out));
+	if(!ctx || !ctx->d_planes || !ctx->pair_mode || slot < 0 || slot >= ctx->n || !inc_out) return CCG_ERR_ARG;
+	CK(ctx, cudaSetDevice(ctx->device));
+	NEED_PLANES(ctx);
+	unsigned inc0 = 0, clr = 0, inc1 = 0;
+	CK(ctx, cudaMemcpyAsync(&inc0, ctx->d_inc + slot, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	*inc_out = inc0;
+	if(ctx->words == 0) return CCG_OK;
+	const int remask0 = ctx->remask_pending;
+	void *d_raw = 0;
+	CK(ctx, cudaMalloc(&d_raw, (size_t) ctx->chunks * 3 * 16));
+	cudaError_t e = ccg_launch_row_planes(ctx, slot, d_raw, 0);
+	int rc = CCG_OK;
+	if(e == cudaSuccess && ctx->proxi && !ctx->proxi_snp_only) {
+		unsigned char *d_use = 0;
+		unsigned *d_clr = 0;
+		int first_used = -1;
+		rc = stage_use_flags(ctx, 0, slot, slot + 1, &d_use, &d_clr, (size_t) ctx->n_pad, &first_used);
+		if(!rc) {
+			e = ccg_launch_sample_proxi(ctx, 0, 0, d_use, 2, d_clr);
+			if(e == cudaSuccess) e = cudaMemcpyAsync(&clr, d_clr + slot, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+			if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		}
+	}
+	if(!rc && e == cudaSuccess && ctx->motif_n) {
+		rc = ensure_stage(ctx, sizeof(unsigned) + 64);
+		if(!rc) {
+			unsigned *d_removed = (unsigned *) ctx->d_stage;
+			e = cudaMemsetAsync(d_removed, 0, sizeof(unsigned), ctx->stream);
+			if(e == cudaSuccess) e = ccg_launch_motif_mask(ctx, slot, 1, d_removed);
+		}
+	}
+	if(!rc && e == cudaSuccess) e = cudaMemcpyAsync(&inc1, ctx->d_inc + slot, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+	/* back to the sample as uploaded */
+	cudaError_t er = ccg_launch_row_planes(ctx, slot, d_raw, 1);
+	if(er == cudaSuccess) er = cudaMemcpyAsync(ctx->d_inc + slot, &inc0, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream);
+	if(er == cudaSuccess) er = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d_raw);
+	ctx->remask_pending = remask0;
+	if(rc) return rc;
+	if(e != cudaSuccess || er != cudaSuccess) {
+		set_err(ctx, "counting a masked sample failed: %s", cudaGetErrorString(e != cudaSuccess ? e : er));
+		return CCG_ERR_CUDA;
+	}
+	*inc_out = inc1 - clr;
 	return CCG_OK;
 }
 

@@ -154,6 +154,7 @@ struct ccg_ctx {
 	unsigned char *d_motif_sets;
 	int codes_upload_masked;        /* a packed upload ANDed the code planes with the rows' masks (no -P set at the time): a
 	                                 * -V listing under -P would not see the words the reference compares */
+	int motif_applied;              /* ccg_mask_motifs has run on some slot of this problem */
 	int remask_pending;             /* -y: mask planes changed by ccg_mask_motifs, code planes not yet re-masked (done before a run) */
 	int row_slot1;                  /* ccg_run_row: 1 + the slot whose row is being computed, 0 otherwise */
 	unsigned proxi;                 /* -P: minimum distance between SNPs (0 = no proximity masking), ccg_set_proximity */
@@ -300,7 +301,7 @@ cudaError_t ccg_launch_encode_codes(ccg_ctx *ctx, int first, int count, const un
                                     long stride);
 cudaError_t ccg_launch_gather_raw(ccg_ctx *ctx, uint32_t *d_mism, uint32_t *d_ninc);
 cudaError_t ccg_launch_apply_global_mask(ccg_ctx *ctx);
-cudaError_t ccg_launch_build_global_mask(ccg_ctx *ctx, const unsigned char *d_use, unsigned *d_inc);
+cudaError_t ccg_launch_build_global_mask(ccg_ctx *ctx, const unsigned char *d_use, unsigned *d_inc, int and_into);
 
 /* k_pairdist_popc.cu */
 cudaError_t ccg_launch_popc(ccg_ctx *ctx, const PopcParams &p);

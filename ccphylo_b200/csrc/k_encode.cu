@@ -218,7 +218,7 @@ k_apply_global_mask(uint32_t *__restrict__ planes, int n_pad, int nplanes, int c
  * row of a chunk is n_pad x 16 contiguous bytes; lanes stride over the slots. */
 __global__ void __launch_bounds__(256)
 k_build_global_mask(const uint32_t *__restrict__ planes, int n_pad, int chunks, int words, const unsigned char *__restrict__ use,
-                    uint32_t *__restrict__ gmask, unsigned *__restrict__ inc) {
+                    uint32_t *__restrict__ gmask, unsigned *__restrict__ inc, int and_into) {
 	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if(warp >= chunks) return;
 	const uint4 *row = reinterpret_cast<const uint4 *>(planes) + ((size_t) warp * 3 + 2) * n_pad;
@@ -239,15 +239,20 @@ k_build_global_mask(const uint32_t *__restrict__ planes, int n_pad, int chunks, 
 		const uint32_t w[4] = {g.x, g.y, g.z, g.w};
 		unsigned known = 0;
 		for(int q = 0; q < 4; ++q)
-			if(warp * 4 + q < words) { gmask[warp * 4 + q] = w[q]; known += __popc(w[q]); }
+			if(warp * 4 + q < words) {
+				/* and_into: the mask already holds what earlier passes left (known-ness, proximity runs) */
+				const uint32_t v = and_into ? (w[q] & gmask[warp * 4 + q]) : w[q];
+				gmask[warp * 4 + q] = v;
+				known += __popc(v);
+			}
 		if(known) atomicAdd(inc, known);
 	}
 }
 
-cudaError_t ccg_launch_build_global_mask(ccg_ctx *ctx, const unsigned char *d_use, unsigned *d_inc) {
+cudaError_t ccg_launch_build_global_mask(ccg_ctx *ctx, const unsigned char *d_use, unsigned *d_inc, int and_into) {
 	const long long threads = (long long) ctx->chunks * 32;
 	k_build_global_mask<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_planes, ctx->n_pad, ctx->chunks, ctx->words,
-	                                                                                d_use, ctx->d_gmask, d_inc);
+	                                                                                d_use, ctx->d_gmask, d_inc, and_into);
 	ctx->launches++;
 	return cudaGetLastError();
 }

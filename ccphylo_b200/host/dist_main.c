@@ -16,7 +16,8 @@
  *   - -V (variant listing) comes from the device as well (ccg_list_variants, same labels as the reference);
  *     -a appends one row to an existing matrix (ccg_run_row / ccg_mat_run_row);
  *   - -y masks methylation motifs on the device right after each upload (ccg_mask_motifs);
- *   - refused: -y with -P in shared-mask mode (-a ignores -y, as the reference does).
+ *   - -y with -P in shared-mask mode: the motif sites go into the shared mask after the proximity pass
+ *     (ccg_build_global_mask); -a ignores -y, as the reference does.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -178,6 +179,9 @@ static void parse_one(int job, void *state, void *user) {
 
 /* -y: motifs loaded by make_matrix (dist.c:127-131); n == 0 without -y */
 static MotifList g_motifs;
+/* shared-mask mode with -y and -P: the motif sites stay out of the samples' own masks (they would read as unknown
+ * bases in the proximity pass); ccg_build_global_mask applies them after that pass */
+static int g_defer_motifs = 0;
 
 /* one sample into its slot: the device packs it, builds its mask and -- with -y -- takes the methylation sites
  * of every motif match out of it (maskMotifs, cdist.c:90,109,137) */
@@ -189,7 +193,9 @@ static void upload_sample(ccg_ctx *ctx, int slot, const ByteBuf *codes, unsigned
 	 * depends on the sequence alone -- so it commutes with maskMotifs (cdist.c:90), and it runs first here because the
 	 * device finds the unknown positions in the still pristine mask */
 	if(!rc && proxi_apply) rc = ccg_sample_proximity(ctx, slot, 1, 1, inc);
-	if(!rc && (g_motifs.n || (inc && !proxi_apply))) rc = ccg_mask_motifs(ctx, slot, 1, inc);
+	if(!rc && g_defer_motifs) {
+		if(inc) rc = ccg_sample_count_masked(ctx, slot, inc);
+	} else if(!rc && (g_motifs.n || (inc && !proxi_apply))) rc = ccg_mask_motifs(ctx, slot, 1, inc);
 	if(rc) die_gpu(ctx, rc);
 }
 
@@ -209,6 +215,7 @@ static unsigned candidate_count(const DistOpts *o, ccg_ctx *ctx, int slot, const
 	unsigned inc = 0;
 	upload_sample(ctx, slot, codes, &inc, proxi_counts && pair);
 	*uploaded = 1;
+	if(g_defer_motifs) return inc;               /* ccg_sample_count_masked has counted both maskings */
 	if(proxi_counts && !pair) {
 		/* the shared-mask reference candidate: its ranges are only counted here, ccg_build_global_mask clears them */
 		int rc = ccg_sample_proximity(ctx, slot, 1, 0, &inc);
@@ -949,13 +956,9 @@ int main_dist(int argc, char **argv) {
 	if(dist_mat_parse_method(&o)) die_invalid(o.method_err);
 	if(!o.numFile && o.targetTemplate) o.numFile = 1;
 
-	/* -y with -P: in pair mode (-f bit 2) the two maskings commute and both run on the device; the shared mask of the
-	 * default mode is built from per-sample masks there, where a motif site would read as an unknown base */
-	if(o.methfilename && !o.addfilename && o.proxi && !(o.flag & 2)) {
-		fprintf(stderr, "-y / --methylation_motifs together with -P / --proximity without pairwise inclusion (-f 2) is not available "
-		                "on the GPU path of dist (use the CPU ccphylo for it).\n");
-		return 1;
-	}
+	/* -y with -P: in pair mode (-f bit 2) both maskings run per sample (they commute); in shared-mask mode the motif
+	 * sites are applied to the shared mask after the proximity pass (ccg_build_global_mask) */
+	g_defer_motifs = o.methfilename && !o.addfilename && o.proxi && !(o.flag & 2);
 	if(o.addfilename && o.filenames) return add_to_matrix(&o);
 	make_matrix(&o);
 	return 0;

@@ -226,6 +226,14 @@ int ccg_set_proximity(ccg_ctx *ctx, unsigned proxi, int snp_events_only);
  * inc_out[k] (may be NULL) receives getNpos of slot first+k's mask after the masking. */
 int ccg_sample_proximity(ccg_ctx *ctx, int first, int count, int apply, unsigned *inc_out);
 
+/* Shared-mask mode with -y AND -P: the reference narrows the shared mask by the motif sites (maskMotifs cdist.c:109,137)
+ * and by the proximity runs, whose events are defined on the sequences (getIncPosPtr cdist.c:111,138).  The motif sites
+ * must therefore not be in the samples' own masks when ccg_build_global_mask runs its proximity pass: with motifs set
+ * and no ccg_mask_motifs call on the problem, ccg_build_global_mask applies the motif masking itself, after that pass.
+ * ccg_sample_count_masked returns what the reference's inclusion test sees for a REFERENCE candidate (cdist.c:137-140:
+ * getNpos after maskMotifs and getIncPosPtr(includes, seq, seq, proxi)) and leaves the store as it was. */
+int ccg_sample_count_masked(ccg_ctx *ctx, int slot, unsigned *inc_out);
+
 /* -y / --methylation_motifs: the motif list getMethMotifs (methparse.c:268-296) builds -- every
  * motif of the file followed by its reverse complement (as strrcMeth :83-103 produces it).  Motif
  * m has lens[m] (1 .. 32) positions whose codes follow each other in `sets`: bits 0..3 = the

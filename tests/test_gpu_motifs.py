@@ -154,10 +154,12 @@ def test_cli_motifs_with_variant_listing(built, tmp_path, msa, flag):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
-@pytest.mark.parametrize("flag,proxi", [("3", "7"), ("3", "40"), ("11", "12"), ("35", "9")])
+@pytest.mark.parametrize("flag,proxi", [("3", "7"), ("3", "40"), ("11", "12"), ("35", "9"), ("1", "7"), ("1", "60"), ("9", "12"), ("33", "9")])
 @pytest.mark.parametrize("msa", [False, True], ids=["files", "msa"])
-def test_cli_motifs_with_proximity_in_pair_mode(built, tmp_path, msa, flag, proxi):
-    # cdist.c:90-91: maskMotifs, then getIncPosPtr(includes[i], seq, seq, proxi); both only clear mask bits
+def test_cli_motifs_with_proximity(built, tmp_path, msa, flag, proxi):
+    # pair mode, cdist.c:90-91: maskMotifs, then getIncPosPtr(includes[i], seq, seq, proxi); both only clear mask bits.
+    # shared-mask mode, cdist.c:109-111 / :137-138: the motif sites narrow the shared mask, the proximity events are
+    # defined on the sequences -- ccg_build_global_mask applies the motifs after its proximity pass
     td = str(tmp_path)
     n, length = 9, 6000 + 11
     rows = synth.make_ascii(n, length, seed=23, snp=0.02, nrun=0.01, gap=0.004)
