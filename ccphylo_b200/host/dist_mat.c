@@ -188,7 +188,9 @@ static void one_template(const DistOpts *o, ccg_ctx *ctx, int n, char **filename
 	for(int r = 1; r < Dn; ++r)
 		for(int c = 0; c < r; ++c, ++k)
 			if(rows[k] == 0) {
-				if(threaded_msgs) fprintf(stderr, "No sufficient overlap between samples:\t%s\t%s\n", filenames[slot_of[r]], filenames[slot_of[c]]);
+				/* the threaded loop names the row sample by its COMPACT row number (filenames[pi], ltdmatrixthrd.c:320, pi counts
+				 * the included samples): with an excluded file in front that is another file's name; kept, the line is compared */
+				if(threaded_msgs) fprintf(stderr, "No sufficient overlap between samples:\t%s\t%s\n", filenames[r], filenames[slot_of[c]]);
 				else fprintf(stderr, "No sufficient overlap between samples:\t%s, %s\n", filenames[slot_of[r]], filenames[slot_of[c]]);
 			}
 	phy_write_mt(outfile, D, o->elem_size, o->byteScale, Dn, filenames, include, target, o->flag, o->precision, o->threads);
