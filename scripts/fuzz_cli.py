@@ -70,11 +70,13 @@ def make_motifs(rng):
     return "".join(out)
 
 
-def make_case(seed, idx):
+def make_case(seed, idx, big=False):
     rng = np.random.default_rng([seed, idx])
     tool = "trim" if rng.random() < 0.15 else "dist"
     n = int(rng.integers(2, 25))
     length = int(rng.choice(LENGTHS)) if rng.random() < 0.7 else int(rng.integers(1, 6000))
+    if big:                 # sizes at which the driver takes the tensor-core kernel (from 192 samples x 8192 bases on)
+        tool, n, length = "dist", int(rng.integers(192, 331)), int(rng.integers(8192, 20001))
     rows = make_rows(rng, n, length)
     pair = rng.random() < 0.7
     flag = (2 if pair else 0) | int(rng.choice([0, 1])) | int(rng.choice([0, 0, 4])) | int(rng.choice([0, 8])) | int(rng.choice([0, 0, 32]))
@@ -121,7 +123,7 @@ def make_case(seed, idx):
             args += ["-x", str(int(rng.integers(0, 13)))]
         if rng.random() < 0.1:
             args += ["-H"]
-        case["variants"] = bool(rng.random() < 0.3)
+        case["variants"] = bool(rng.random() < 0.3) and not big      # (a listing of 50,000 pairs is all print)
         case["out_stdout"] = bool(rng.random() < 0.15)
         case["num"] = str(rng.choice(["o.num", "o.num", "", "o.phy"]))
     threads = 1 if case["variants"] else int(rng.integers(1, 6))
@@ -378,6 +380,7 @@ def main():
     ap.add_argument("--budget-s", type=float, default=0.0, help="stop handing out cases after this many seconds")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "fuzz"))
     ap.add_argument("--self", dest="self_check", action="store_true")
+    ap.add_argument("--big", action="store_true", help="192 .. 330 samples x 8 .. 20 kbp: the tensor-core kernel behind the command line")
     ap.add_argument("--mat", action="store_true", help=".mat inputs (cells compared within 1e-6 relative) instead of FASTA")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
@@ -389,7 +392,7 @@ def main():
             return None
         if a.mat:
             return check_mat(make_mat_case(a.seed, i), a.out, a.self_check)
-        return check(make_case(a.seed, i), a.out, a.self_check)
+        return check(make_case(a.seed, i, a.big), a.out, a.self_check)
     with ThreadPoolExecutor(max_workers=a.workers) as ex:
         results = [r for r in ex.map(job, idxs) if r]
     bad = [r for r in results if r["verdict"] == "MISMATCH"]
@@ -398,7 +401,7 @@ def main():
                "known_divergence_3": sum(r["verdict"] == "known_divergence_3" for r in results), "nonzero_rc_both": sum(r["verdict"] == "ok" and r["rc"][0] != 0 for r in results),
                "seconds": round(time.time() - t0, 1), "self_check": a.self_check, "mismatches": bad,
                "ref_crashes": [r for r in results if r["verdict"] == "ref_crash"]}
-    with open(os.path.join(a.out, ("summary_mat_seed%d.json" if a.mat else "summary_seed%d.json") % a.seed), "w") as f:
+    with open(os.path.join(a.out, ("summary_mat_seed%d.json" if a.mat else "summary_big_seed%d.json" if a.big else "summary_seed%d.json") % a.seed), "w") as f:
         json.dump(summary, f, indent=1)
     print(json.dumps({k: v for k, v in summary.items() if k not in ("mismatches", "ref_crashes")}))
     for r in bad[:40]:

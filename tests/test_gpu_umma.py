@@ -340,3 +340,26 @@ def test_lent_rows_expand_without_the_plane_store(built, n, length, pair):
             c.put_samples_packed_dev_borrowed(d_seqs.data_ptr(), d_masks.data_ptr(), n, d_seqs.stride(0))
             D3, N3, dn3 = c.run_pair(include=include, norm=1000)
             assert np.array_equal(_bits(D3), _bits(Do)) and np.array_equal(_bits(N3), _bits(No))
+
+
+# ---- every extent of the last macro-tile row: thin (transposed, MMA N = 16 .. 96) up to 96 valid rows, full tiles above ----
+@pytest.mark.parametrize("v", [15, 16, 17, 31, 32, 33, 47, 48, 49, 64, 80, 81, 95, 96, 97, 128, 200, 255])
+def test_last_tile_row_extents(built, v):
+    n = (512 if v % 2 else 256) + v
+    length = 128 * 9 + 77
+    codes, seqs, masks, inc = _set(n, length, seed=1000 + v, snp=0.05, nrun=0.08)
+    include = np.ones(n, np.uint8)
+    include[[1, n - 2]] = 0
+    with api.Context() as c:
+        c.set_kernel(api.KERNEL_UMMA)
+        c.set_problem(n, length, pair=True)
+        c.put_samples_packed(seqs, masks)
+        D, N, dn = c.run_pair(min_length=0, min_cov=0.0)
+        assert "mxf4" in c.last_kernel and dn == n
+        mism, ninc = c.raw_counts(dn)
+        mo, no = oracle.raw_pair_matrix(seqs, masks, length)
+        assert np.array_equal(ninc, no) and np.array_equal(mism, mo)
+        D, N, dn = c.run_pair(include=include, norm=1000000)
+        Do, No, dno = oracle.fsa_cmp_pair(seqs, masks, include, length, norm=1000000)
+        assert dn == dno == n - 2
+        assert np.array_equal(_bits(D), _bits(Do)) and np.array_equal(_bits(N), _bits(No))
