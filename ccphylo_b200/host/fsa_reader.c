@@ -188,6 +188,19 @@ int fsa_read_codes(FsaReader *r, const unsigned char table[256], ByteBuf *codes)
 	}
 }
 
+const unsigned char *fsa_window(FsaReader *r, size_t *have) {
+	if(r->pos == r->avail && !refill(r)) {
+		*have = 0;
+		return 0;
+	}
+	*have = r->avail - r->pos;
+	return r->buf + r->pos;
+}
+
+void fsa_consume(FsaReader *r, size_t n) {
+	r->pos += n;
+}
+
 int fsa_read_line(FsaReader *r, ByteBuf *line) {
 	line->len = 0;
 	if(r->pos == r->avail && !refill(r)) return 0;

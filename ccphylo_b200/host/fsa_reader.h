@@ -46,6 +46,12 @@ int fsa_is_plain(FsaReader *r);
 /* continue reading at `offset` of the (decompressed) stream; 0 on success */
 int fsa_seek(FsaReader *r, long long offset);
 
+/* the unread bytes of the reader's buffer (refilled when empty; *have = 0 at end of file), for parsers that scan whole
+ * lines in place; fsa_consume marks the first n of them read.  A line cut by the end of the window is fetched whole
+ * with fsa_read_line. */
+const unsigned char *fsa_window(FsaReader *r, size_t *have);
+void fsa_consume(FsaReader *r, size_t n);
+
 /* next text line without its '\n' (0-terminated, len excludes the terminator); 0 at end of file */
 int fsa_read_line(FsaReader *r, ByteBuf *line);
 

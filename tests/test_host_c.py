@@ -185,9 +185,13 @@ def test_mat_reader_matches_a_plain_parse(built, tmp_path):
     exe = _readers_exe(tmp_path)
     rng = np.random.default_rng(7)
     blocks = []
-    for name, rows in (("other template", 40), ("tmpl", 300), ("tail", 5)):
+    # "big": more than the reader's 1 MiB window, so rows are cut by the window's end (in the plain and in the gz file
+    # at different rows), with 1 .. 5-digit counts; rows within 72 bytes of a window's end take the line-by-line parser
+    for name, rows in (("other template", 40), ("tmpl", 300), ("big", 150000), ("tail", 5)):
         ref = "".join("ACGT-"[k] for k in rng.integers(0, 5, size=rows))
         counts = rng.integers(0, 70, size=(rows, 6))
+        if name == "big":
+            counts = counts * rng.choice([1, 1, 10, 900], size=(rows, 1))
         counts[rng.random(rows) < 0.1] = 0
         blocks.append((name, ref, counts))
     text = "".join(helpers.mat_text(nm, ref, c) for nm, ref, c in blocks)
@@ -196,7 +200,7 @@ def test_mat_reader_matches_a_plain_parse(built, tmp_path):
         f.write(text)
     with gzip.open(path + ".gz", "wt") as f:
         f.write(text)
-    for target in ("tmpl", "other template", "tail", "absent"):
+    for target in ("tmpl", "other template", "big", "tail", "absent"):
         for min_depth in (1, 15):
             for q in (path, path + ".gz"):
                 p = subprocess.run([exe, "mat", str(min_depth), q, target], capture_output=True, text=True)
