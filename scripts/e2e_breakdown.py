@@ -42,7 +42,7 @@ torch.cuda.empty_cache()
 sp = (C.c_void_p * n)(*[hs_ptr + k * W * 8 for k in range(n)])
 mp = (C.c_void_p * n)(*[hm_ptr + k * W * 4 for k in range(n)])
 include = np.ones(n, dtype=np.uint8)
-for mode in ("stream", "stream4", "stream16"):
+for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("stream", "stream4", "stream16")):
     if mode == "nostream":
         os.environ["CCG_STREAM_MIN_CHUNKS"] = "0"
     if mode.startswith("stream") and mode != "stream":
