@@ -29,7 +29,7 @@ EXPORTS = [
     "ccg_host_free", "ccg_launch_count", "ccg_last_kernel", "ccg_last_compare_ms", "ccg_last_phase_ms",
     "ccg_measure_i8_peak", "ccg_measure_fp4_peak", "ccg_mat_set_problem", "ccg_mat_put_sample", "ccg_mat_run",
     "ccg_set_proximity", "ccg_sample_proximity", "ccg_run_row", "ccg_mat_run_row", "ccg_list_variants", "ccg_set_motifs", "ccg_mask_motifs", "ccg_list_variants_row",
-    "ccg_init_multi", "ccg_init_multi_devices", "ccg_multi_gpus", "ccg_group_export", "ccg_group_join", "ccg_group_leave",
+    "ccg_init_multi", "ccg_init_multi_devices", "ccg_multi_gpus", "ccg_multi_contexts", "ccg_group_export", "ccg_group_join", "ccg_group_leave",
     "ccg_mat_run_partial", "ccg_mat_finalize_host", "ccg_group_set_alignment", "ccg_group_set_output", "ccg_group_row_block", "ccg_group_row_owner", "ccg_group_cells",
     "ccg_sample_count_masked", "ccg_trim_begin", "ccg_trim_sample", "ccg_trim_keep_reference", "ccg_trim_get_mask", "ccg_trim_end",
 ]
@@ -143,6 +143,7 @@ def load():
     L.ccg_init_multi.argtypes = [C.POINTER(vp), i]
     L.ccg_init_multi_devices.argtypes = [C.POINTER(vp), i, vp]
     L.ccg_multi_gpus.argtypes = [vp, C.POINTER(i)]
+    L.ccg_multi_contexts.argtypes = [vp]
     L.ccg_group_export.argtypes = [vp, i, vp]
     L.ccg_group_join.argtypes = [vp, i, i, vp]
     L.ccg_group_leave.argtypes = [vp]
@@ -240,6 +241,10 @@ class Context:
         """(member GPUs, members working on the current problem)"""
         a = C.c_int(1)
         return self._L.ccg_multi_gpus(self._h, C.byref(a)), a.value
+
+    def multi_contexts(self):
+        """member device contexts started so far (member 0 at once, the others when a problem is first split)"""
+        return self._L.ccg_multi_contexts(self._h)
 
     def group_export(self, max_samples):
         buf = (C.c_char * GROUP_HANDLE_BYTES)()

@@ -480,7 +480,10 @@ int ccg_group_finalize(ccg_ctx *ctx, const EpilogueParams &ep, int i_const, int 
  * does with pthreads inside fsaCmpThreadOut (fsacmpthrd.c:76-106), one level up.
  * ==================================================================================================== */
 struct ccg_multi {
-	int n;                                 /* member contexts */
+	int n;                                 /* members (devices) this handle may use */
+	int created;                           /* member[0 .. created) exist: member 0 from the start, the others once a problem
+	                                        * is split (a small job on an 8-GPU box starts one device context, not eight) */
+	int device[CCG_GROUP_MAX];
 	ccg_ctx *member[CCG_GROUP_MAX];
 	int joined;                            /* members currently joined as a group of this many (0 = not joined) */
 	int joined_samples;                    /* sample slots the members' windows were exported for */
@@ -539,14 +542,15 @@ extern "C" int ccg_init_multi_devices(ccg_ctx **out, int ngpus, const int *devic
 	m->active = 1;
 	m->rendezvous = new HostBarrier();
 	m->force = getenv("CCG_MULTI_FORCE") ? atoi(getenv("CCG_MULTI_FORCE")) : 0;
-	for(int g = 0; g < ngpus && !rc; ++g) rc = ccg_init(&m->member[g], devices[g]);
+	for(int g = 0; g < ngpus; ++g) m->device[g] = devices[g];
+	rc = ccg_init(&m->member[0], devices[0]);
 	if(rc) {
-		for(int g = 0; g < ngpus; ++g) ccg_destroy(m->member[g]);
 		delete m->rendezvous;
 		free(m);
 		ccg_destroy(lead);
 		return rc;
 	}
+	m->created = 1;
 	lead->multi = m;
 	*out = lead;
 	return CCG_OK;
@@ -584,21 +588,54 @@ extern "C" int ccg_multi_gpus(const ccg_ctx *ctx, int *active) {
 	return ctx->multi->n;
 }
 
+extern "C" int ccg_multi_contexts(const ccg_ctx *ctx) { return (ctx && ctx->multi) ? ctx->multi->created : 1; }
+
 void ccg_multi_destroy(ccg_ctx *lead) {
 	ccg_multi *m = lead->multi;
 	if(!m) return;
-	for(int g = 0; g < m->n; ++g) ccg_destroy(m->member[g]);
+	for(int g = 0; g < m->created; ++g) ccg_destroy(m->member[g]);
 	delete m->rendezvous;
 	free(m->mat_lens);
 	free(m);
 	lead->multi = 0;
 }
 
+/* creates the member contexts [created, count), one host thread per device (a device context takes a few hundred
+ * milliseconds to start; eight in a row would be seconds) */
+static int multi_ensure(ccg_ctx *lead, int count) {
+	ccg_multi *m = lead->multi;
+	if(count > m->n) count = m->n;
+	if(count <= m->created) return CCG_OK;
+	const int first = m->created;
+	std::vector<int> rcs((size_t) count, CCG_OK);
+	std::vector<std::thread> th;
+	for(int g = first; g < count; ++g) th.emplace_back([&, g]() { rcs[(size_t) g] = ccg_init(&m->member[g], m->device[g]); });
+	for(auto &t : th) t.join();
+	int rc = CCG_OK;
+	for(int g = first; g < count; ++g)
+		if(rcs[(size_t) g] && !rc) {
+			rc = rcs[(size_t) g];
+			ccg_set_err(lead, "gpu %d (device %d): the device context could not be started (%s)", g, m->device[g], ccg_strerror(rc));
+		}
+	if(rc) {
+		for(int g = first; g < count; ++g) {
+			ccg_destroy(m->member[g]);
+			m->member[g] = 0;
+		}
+		return rc;
+	}
+	for(int g = first; g < count; ++g) ccg_set_kernel(m->member[g], m->kernel_choice);
+	m->created = count;
+	return CCG_OK;
+}
+
 /* (re)joins the first `active` members as a group able to hold `samples` slots */
 static int multi_join(ccg_ctx *lead, int active, int samples) {
 	ccg_multi *m = lead->multi;
+	int rc0 = multi_ensure(lead, active);
+	if(rc0) return rc0;
 	if(m->joined == active && m->joined_samples >= samples) return CCG_OK;
-	for(int g = 0; g < m->n; ++g) {
+	for(int g = 0; g < m->created; ++g) {
 		ccg_group_leave(m->member[g]);
 		m->member[g]->grp_host_barrier = 0;
 	}
@@ -661,13 +698,13 @@ int ccg_multi_set_problem(ccg_ctx *lead, int n, int len, int pair_mode) {
 int ccg_multi_set_kernel(ccg_ctx *lead, int kernel) {
 	ccg_multi *m = lead->multi;
 	m->kernel_choice = kernel;
-	for(int g = 0; g < m->n; ++g) ccg_set_kernel(m->member[g], kernel);
+	for(int g = 0; g < m->created; ++g) ccg_set_kernel(m->member[g], kernel);
 	return CCG_OK;
 }
 
 int ccg_multi_sync(ccg_ctx *lead) {
 	ccg_multi *m = lead->multi;
-	for(int g = 0; g < m->n; ++g) {
+	for(int g = 0; g < m->created; ++g) {
 		int rc = ccg_sync(m->member[g]);
 		if(rc) return multi_fail(lead, rc | (g << 8));
 	}
@@ -828,7 +865,7 @@ int ccg_multi_fsa_cmp_thread_out(ccg_ctx *lead, int pair, void *D, void *N, int 
 
 long long ccg_multi_launch_count(const ccg_ctx *lead) {
 	long long k = 0;
-	for(int g = 0; g < lead->multi->n; ++g) k += ccg_launch_count(lead->multi->member[g]);
+	for(int g = 0; g < lead->multi->created; ++g) k += ccg_launch_count(lead->multi->member[g]);
 	return k;
 }
 const char *ccg_multi_last_kernel(const ccg_ctx *lead) { return lead->multi->last_kernel; }
@@ -840,7 +877,10 @@ float ccg_multi_last_compare_ms(ccg_ctx *lead) {
 	}
 	return ms;
 }
-ccg_ctx *ccg_multi_member(ccg_ctx *lead, int g) { return (lead->multi && g >= 0 && g < lead->multi->n) ? lead->multi->member[g] : 0; }
+ccg_ctx *ccg_multi_member(ccg_ctx *lead, int g) {
+	if(!lead->multi || g < 0 || g >= lead->multi->n || multi_ensure(lead, g + 1)) return 0;
+	return lead->multi->member[g];
+}
 
 /* ---- count matrices on a multi-GPU context: member g holds the positions [mat_base0[g], mat_base0[g + 1]) of every
  * sample and returns its raw per-pair sums; the leader adds them in member order (a fixed order: the result does not
@@ -865,7 +905,9 @@ int ccg_multi_mat_set_problem(ccg_ctx *lead, int n, int max_len) {
 	m->mat_lens = (int *) calloc((size_t) (n ? n : 1), sizeof(int));
 	if(!m->mat_lens) return CCG_ERR_NOMEM;
 	for(int g = 0; g <= a; ++g) m->mat_base0[g] = g == a ? max_len : (int) ((long long) max_len * g / a / 32 * 32);
-	for(int g = 0; g < m->n; ++g) {
+	int rce = multi_ensure(lead, a);
+	if(rce) return rce;
+	for(int g = 0; g < m->created; ++g) {
 		/* members outside the split give their store back */
 		int rc = g < a ? ccg_mat_set_problem(m->member[g], n, m->mat_base0[g + 1] - m->mat_base0[g]) : ccg_mat_set_problem(m->member[g], 0, 0);
 		if(rc) return multi_fail(lead, rc | (g << 8));

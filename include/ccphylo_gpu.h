@@ -90,10 +90,13 @@ int ccg_sync(ccg_ctx *ctx);
  * host thread per device; anything else runs on member 0 alone; calls that need a whole sample on one
  * device (-P, -y, -V, -a, device-pointer uploads) return CCG_ERR_UNSUPPORTED while a problem is split.
  * ngpus <= 0: every visible device.  ccg_multi_gpus returns the member count, *active the number
- * working on the current problem. */
+ * working on the current problem.  Only member 0's device context is started by ccg_init_multi; the others start
+ * (in parallel) when the first problem is split, so a small job on an 8-GPU box pays for one context, as the
+ * reference's small jobs pay for no threads (fsacmpthrd.c:84-89).  ccg_multi_contexts: how many have been started. */
 int ccg_init_multi(ccg_ctx **ctx, int ngpus);
 int ccg_init_multi_devices(ccg_ctx **ctx, int ngpus, const int *devices);   /* devices may repeat (tests on one GPU) */
 int ccg_multi_gpus(const ccg_ctx *ctx, int *active);
+int ccg_multi_contexts(const ccg_ctx *ctx);
 
 /* One process per GPU (torchrun, MPI): every rank creates its context with ccg_init, exports a handle
  * to the peer window that holds its accumulators (sized for max_samples sample slots), the ranks

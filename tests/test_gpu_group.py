@@ -186,6 +186,7 @@ def test_small_or_special_problems_stay_on_one_member(built):
         codes, seqs, masks, inc = _set(n, length, seed=3)
         D, N, dn, _ = api.fsa_cmp_thread_out(seqs, np.ones(n, np.uint8), masks, length, pair=True, min_length=0, min_cov=0.0, ctx=c)
         assert c.multi_gpus() == (2, 1)
+        assert c.multi_contexts() == 1            # the second device's context was never started
         mo, no = oracle.raw_pair_matrix(seqs, masks, length)
         assert np.array_equal(N, no.astype(np.float64)) and np.array_equal(D, mo.astype(np.float64))
         # -P: sequential along the alignment -> member 0 alone, same result as a single-device context
@@ -195,6 +196,23 @@ def test_small_or_special_problems_stay_on_one_member(built):
             D2, N2, dn2, _ = api.fsa_cmp_thread_out(seqs, np.ones(n, np.uint8), masks, length, pair=True, min_length=0,
                                                     min_cov=0.0, proxi=5, ctx=s)
         assert np.array_equal(D1, D2) and np.array_equal(N1, N2)
+        assert c.multi_contexts() == 1
+        # a problem worth splitting starts the other member, and the handle goes back to one member afterwards
+        os.environ["CCG_MULTI_FORCE"] = "1"
+        try:
+            c2 = api.Context(multi=_devices(3))
+        finally:
+            del os.environ["CCG_MULTI_FORCE"]
+        try:
+            assert c2.multi_contexts() == 1
+            n, length = 40, 3000
+            codes, seqs, masks, inc = _set(n, length, seed=4)
+            D, N, dn, _ = api.fsa_cmp_thread_out(seqs, np.ones(n, np.uint8), masks, length, pair=True, min_length=0, min_cov=0.0, ctx=c2)
+            assert c2.multi_gpus() == (3, 3) and c2.multi_contexts() == 3
+            mo, no = oracle.raw_pair_matrix(seqs, masks, length)
+            assert np.array_equal(N, no.astype(np.float64)) and np.array_equal(D, mo.astype(np.float64))
+        finally:
+            c2.close()
     finally:
         c.close()
 
