@@ -15,10 +15,10 @@ import fuzz_cli  # noqa: E402
 needs_ref = pytest.mark.skipif(not os.path.exists(fuzz_cli.REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
 
 # (seed, index): a spread over dist / trim, files / MSA / gz, -P, -y, -V, cell types
-FASTA = [(1, k) for k in (0, 1, 2, 3, 5, 7, 8, 11, 13, 18, 37, 47)] + [(2, k) for k in (0, 3, 4, 9)]
+FASTA = [(1, k) for k in (0, 2, 3, 7, 11, 18, 37, 47)] + [(2, k) for k in (3, 9)]
 # seed 1 / 9, 12, 24, 42: an excluded file in front of a pair without sufficient overlap (the threaded loop names the row
 # sample by its compact row number, ltdmatrixthrd.c:320)
-MAT = [(1, k) for k in (0, 1, 3, 5, 9, 12, 24, 42)] + [(2, k) for k in (1, 2)]
+MAT = [(1, k) for k in (0, 3, 9, 12, 24, 42)] + [(2, 1)]
 
 
 @needs_ref
