@@ -20,4 +20,8 @@ void phy_write(FILE *out, const void *cells, int elem_size, double byteScale, in
 void phy_write_mt(FILE *out, const void *cells, int elem_size, double byteScale, int dn, char **names,
                   const unsigned char *include, const char *comment, unsigned flags, int precision, int threads);
 
+/* "%.*f" of one cell into dst (room for 48 bytes) without the C library, byte-identical to snprintf; returns the length,
+ * or 0 when the value is left to snprintf (non-finite, precision > 18, |d| >= 2^52, more than 19 digits) */
+size_t phy_format_fixed(char *dst, double d, int precision);
+
 #endif

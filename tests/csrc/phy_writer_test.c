@@ -1,5 +1,6 @@
 /* Host-side check of the Phylip writer: the multi-threaded writer must print byte for byte what a
  * plain per-cell fprintf loop in the reference's format (phy.c:59-123) prints, for every cell type. */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -19,7 +20,63 @@ static char *slurp(const char *path, size_t *len) {
 	return d;
 }
 
+/* phy_format_fixed against snprintf("%.*f"): ratios as the epilogue produces them, dyadic ties (exactly half a unit of
+ * the last printed digit), values next to a tie, tiny / huge / negative values, raw bit patterns; every precision 0 .. 18 */
+static uint64_t rng_state = 88172645463325252ull;
+static uint64_t rnd(void) {
+	rng_state ^= rng_state << 13;
+	rng_state ^= rng_state >> 7;
+	rng_state ^= rng_state << 17;
+	return rng_state;
+}
+
+static int check_fixed(double d, int precision, long *fallbacks) {
+	char a[512], b[64];
+	const int la = snprintf(a, sizeof(a), "%.*f", precision, d);
+	const size_t lb = phy_format_fixed(b, d, precision);
+	if(lb == 0) { ++*fallbacks; return 0; }
+	if((size_t) la != lb || memcmp(a, b, lb)) {
+		b[lb] = 0;
+		fprintf(stderr, "MISMATCH %.17g precision %d: snprintf '%s' phy_format_fixed '%s'\n", d, precision, a, b);
+		return 1;
+	}
+	return 0;
+}
+
+static int fixed_sweep(long rounds) {
+	long bad = 0, fallbacks = 0, total = 0;
+	for(long r = 0; r < rounds && bad < 10; ++r) {
+		const int p = (int) (rnd() % 19);
+		double v[12];
+		const uint64_t x = rnd(), y = rnd();
+		v[0] = (double) (x % 5000000) * 1000000.0 / (double) (1 + y % 5000000);       /* mismatches x norm / included */
+		v[1] = (double) (float) v[0];                                                  /* a float cell */
+		v[2] = (double) (x % 100000) / (double) (1 + y % 1000);
+		v[3] = ldexp((double) (2 * (x % 1000000) + 1), -1 - (int) (y % 40));           /* odd / 2^k: ties at some precision */
+		v[4] = nextafter(v[3], 0.0);
+		v[5] = nextafter(v[3], 1e300);
+		v[6] = -v[0];
+		v[7] = ldexp((double) (x >> 11), -(int) (y % 1100));                           /* down to subnormals */
+		v[8] = (double) (x % 1000) + 0.5;                                              /* p = 0 ties */
+		v[9] = (double) (x >> 20) / 1024.0;                                            /* up to 2^34, exact binary fractions */
+		memcpy(&v[10], &x, 8);                                                         /* any bit pattern */
+		v[11] = ((double) (x % 2000001) - 1000000.0) / 1e9;                            /* around zero: "-0.000000000" */
+		for(int k = 0; k < 12; ++k, ++total) bad += check_fixed(v[k], p, &fallbacks);
+	}
+	/* a few fixed points */
+	const double fixed[] = {0.5, 1.5, 2.5, 0.125, 0.375, 1e-10, -1e-10, 0.9999999995, 0.99999999949999, 999999.9999999995, 4503599627370495.5,
+	                        4503599627370496.0, 1e18, 9.223372036854e18, 5e-324, 1.7976931348623157e308, -0.0, 0.0};
+	for(size_t k = 0; k < sizeof(fixed) / sizeof(fixed[0]); ++k)
+		for(int p = 0; p <= 18; ++p, ++total) bad += check_fixed(fixed[k], p, &fallbacks);
+	/* out of range: left to snprintf */
+	char b[64];
+	if(phy_format_fixed(b, 1.5, 19) || phy_format_fixed(b, 1.5, -1) || phy_format_fixed(b, NAN, 9) || phy_format_fixed(b, INFINITY, 9)) ++bad;
+	printf("%s %ld values, %ld left to snprintf\n", bad ? "FAIL" : "OK", total, fallbacks);
+	return bad != 0 || fallbacks * 4 > total;
+}
+
 int main(int argc, char **argv) {
+	if(argc > 2 && strcmp(argv[1], "fixed") == 0) return fixed_sweep(atol(argv[2]));
 	const int n = argc > 1 ? atoi(argv[1]) : 700, dn = n - 3;
 	const char *dir = argc > 2 ? argv[2] : "/tmp";
 	char **names = malloc((size_t) n * sizeof(char *));

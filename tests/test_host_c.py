@@ -16,6 +16,9 @@ def test_threaded_phylip_writer_matches_per_cell_fprintf(tmp_path):
     for n in ("9", "1200"):
         p = subprocess.run([exe, n, str(tmp_path)], capture_output=True, text=True)
         assert p.returncode == 0 and p.stdout.strip() == "OK", p.stderr
+    # the writer's own "%.*f" (exact 128-bit arithmetic, ties to even) against snprintf: 7 million values, precision 0 .. 18
+    p = subprocess.run([exe, "fixed", "600000"], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.startswith("OK "), p.stdout + p.stderr
 
 
 def test_proximity_arithmetic_of_the_kernels_on_the_host(built, tmp_path):
