@@ -6,12 +6,14 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "ccphylo_b200", "host")
+# CCB_TEST_CFLAGS="-fsanitize=address,undefined -g": the same unit tests under the sanitizers
+EXTRA = os.environ.get("CCB_TEST_CFLAGS", "").split()
 BIN = os.path.join(ROOT, "ccphylo_b200", "bin", "ccphylo-b200")
 
 
 def test_threaded_phylip_writer_matches_per_cell_fprintf(tmp_path):
     exe = str(tmp_path / "phy_writer_test")
-    subprocess.run(["gcc", "-O2", "-std=gnu99", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "phy_writer_test.c"),
+    subprocess.run(["gcc", *EXTRA, "-O2", "-std=gnu99", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "phy_writer_test.c"),
                     os.path.join(HOST, "phy_writer.c"), "-lpthread", "-lm"], check=True)
     for n in ("9", "1200"):
         p = subprocess.run([exe, n, str(tmp_path)], capture_output=True, text=True)
@@ -26,7 +28,7 @@ def test_proximity_arithmetic_of_the_kernels_on_the_host(built, tmp_path):
     host and compared with the oracle's maskProxi / getIncPos* restatement"""
     exe = str(tmp_path / "proxi_core_test")
     odir = os.path.join(ROOT, "oracle")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-I", odir, "-I", os.path.join(ROOT, "ccphylo_b200", "csrc"), "-o", exe,
+    subprocess.run(["g++", *EXTRA, "-O2", "-std=c++17", "-Wall", "-I", odir, "-I", os.path.join(ROOT, "ccphylo_b200", "csrc"), "-o", exe,
                     os.path.join(ROOT, "tests", "csrc", "proxi_core_test.cpp"), "-L", odir, "-loracle",
                     "-Wl,-rpath," + odir], check=True)
     for seed in ("1", "2"):
@@ -40,7 +42,7 @@ def test_motif_file_parser_matches_the_oracle(built, tmp_path):
     which tests/test_oracle_vs_reference.py pins to the reference's getMethMotifs + maskMotifs"""
     import oracle
     exe = str(tmp_path / "motifs_test")
-    subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "motifs_test.c"),
+    subprocess.run(["gcc", *EXTRA, "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "motifs_test.c"),
                     os.path.join(HOST, "motifs.c"), os.path.join(HOST, "fsa_reader.c"), "-lz"], check=True)
     files = [">dam\ngAtc\n", ">dam\ngAtc\n>dcm\ncCwgg\n>x\nrgATcnny\n", "gatC\n>multi line\ncC\nwg\ng\n>odd chars\nGA-NT.C\r\n",
              ">long\nacgtacgtAcgtacgtacgtacgTacgtacgt\n>three\ngAn\n>iupac\nRYSWKMBDHVN\n>u\nUu\n>empty\n>x\nXx\n"]
@@ -77,7 +79,7 @@ def test_phylip_update_matches_the_reference(built, tmp_path):
         import pytest
         pytest.skip("oracle/_ref was not built (needs /root/reference)")
     exe = str(tmp_path / "phy_update_test")
-    subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "phy_update_test.c"),
+    subprocess.run(["gcc", *EXTRA, "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "phy_update_test.c"),
                     os.path.join(HOST, "phy_update.c"), os.path.join(HOST, "fsa_reader.c"), "-lz"], check=True)
     relaxed = "%10d\nsample_a.fsa\ns_b\t12\nanother name.fsa\t3.500000000\t-1\n" % 3
     strict = "%10d\n%-10.10s\n%-10.10s\t12\n%-10.10s\t3\t4\n" % (3, "s0.fsa", "a_long_name_cut", "x")
@@ -118,7 +120,7 @@ def test_ordered_parse_pool(tmp_path):
     """host/ordered_pool.c: results in job order, slots not reused before release, look-ahead bounded by the window,
     more threads than window slots or jobs"""
     exe = str(tmp_path / "ordered_pool_test")
-    subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "ordered_pool_test.c"),
+    subprocess.run(["gcc", *EXTRA, "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "ordered_pool_test.c"),
                     os.path.join(HOST, "ordered_pool.c"), "-lpthread"], check=True)
     for args in (("300", "8", "10"), ("50", "16", "3"), ("5", "8", "10"), ("100", "1", "1"), ("64", "4", "4")):
         p = subprocess.run([exe] + list(args), capture_output=True, text=True, timeout=60)
@@ -127,7 +129,7 @@ def test_ordered_parse_pool(tmp_path):
 
 def _readers_exe(tmp_path):
     exe = str(tmp_path / "readers_test")
-    subprocess.run(["gcc", "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "readers_test.c"),
+    subprocess.run(["gcc", *EXTRA, "-O2", "-std=gnu99", "-Wall", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "csrc", "readers_test.c"),
                     os.path.join(HOST, "fsa_reader.c"), os.path.join(HOST, "mat_reader.c"), "-lz"], check=True)
     return exe
 
