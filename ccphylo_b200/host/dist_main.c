@@ -917,14 +917,20 @@ int main_dist(int argc, char **argv) {
 			case 'D': o.method = 0; break;
 			case 'l': o.alpha = optscan_double(&sc); break;
 			case 'p': o.elem_size = 4; break;
-			case 's': o.elem_size = 2; o.byteScale = optscan_optional_double(&sc, o.byteScale); break;
+			case 's':
+				o.elem_size = 2;
+				if(!sc.name[1]) sc.name[0] = 'p';   /* the reference reports a bad value of the short form "at p" (dist.c:651-653) */
+				o.byteScale = optscan_optional_double(&sc, o.byteScale);
+				break;
 			case 'b': o.elem_size = 1; o.byteScale = optscan_optional_double(&sc, o.byteScale); break;
 			case 'H': o.mmap_matrix = 1; break;
 			case 'T': o.tmpdir = optscan_arg(&sc); break;
 			case 't': o.threads = (int) optscan_long(&sc); break;
 			case 'h': return help_message(stdout);
 			default:
-				snprintf(word, sizeof(word), "-%c", c);
+				/* a short option is named by its letter alone (the reference cuts the word behind it and prints from the
+				 * letter on, dist.c:671-672 / trim.c) */
+				snprintf(word, sizeof(word), "%c", c);
 				die_unknown(word);
 		}
 	}

@@ -363,7 +363,9 @@ int main_trim(int argc, char **argv) {
 			case 'F': flag_help = 1; break;
 			case 'h': return help_message(stdout);
 			default:
-				snprintf(word, sizeof(word), "-%c", c);
+				/* a short option is named by its letter alone (the reference cuts the word behind it and prints from the
+				 * letter on, dist.c:671-672 / trim.c) */
+				snprintf(word, sizeof(word), "%c", c);
 				die_unknown(word);
 		}
 	}

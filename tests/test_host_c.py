@@ -230,7 +230,8 @@ def test_option_scanner_dialect(built, tmp_path):
     assert "Relaxed Phylip" in run("-F").stdout and "Relaxed Phylip" in run("--flag_help").stdout
     assert "# cos:" in run("-D").stdout
     assert run("--bogus").stderr == 'Unknown argument or option: "--bogus"\n'
-    assert run("-Z").stderr == 'Unknown argument or option: "-Z"\n'
+    assert run("-Z").stderr == 'Unknown argument or option: "Z"\n'          # the letter alone, as the reference prints it
+    assert run("-pZq").stderr == 'Unknown argument or option: "Z"\n'
     assert run("-x").stderr == "Missing argument at x.\n"
     assert run("-x", "abc").stderr == "Invalid value parsed at x.\n"
     assert run("--print_precision=abc").stderr == "Invalid value parsed at print_precision.\n"
