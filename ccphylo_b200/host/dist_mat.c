@@ -187,7 +187,8 @@ static void one_template(const DistOpts *o, ccg_ctx *ctx, int n, char **filename
 	size_t k = 0;
 	for(int r = 1; r < Dn; ++r)
 		for(int c = 0; c < r; ++c, ++k)
-			if(rows[k] == 0) {
+			/* (with -L 0 -C 0 a pair without a single comparable position passes the gate: no line, the cell is 0/0) */
+			if(rows[k] == 0 && (o->minLength > 0 || o->minCov > 0)) {
 				/* the threaded loop names the row sample by its COMPACT row number (filenames[pi], ltdmatrixthrd.c:320, pi counts
 				 * the included samples): with an excluded file in front that is another file's name; kept, the line is compared */
 				if(threaded_msgs) fprintf(stderr, "No sufficient overlap between samples:\t%s\t%s\n", filenames[r], filenames[slot_of[c]]);
@@ -276,7 +277,7 @@ int dist_mat_add_row(const DistOpts *o, int n, char **paths, double *D, double *
 			N[j] = 0.0;
 			rows[j] = 0;
 		}
-		if(rows[j] == 0) fprintf(stderr, "No sufficient overlap with sample:\t%s\n", paths[j]);
+		if(rows[j] == 0 && (too_long[j] || o->minLength > 0 || o->minCov > 0)) fprintf(stderr, "No sufficient overlap with sample:\t%s\n", paths[j]);
 	}
 	free(rows);
 	free(too_long);

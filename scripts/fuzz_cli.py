@@ -327,6 +327,8 @@ def check_mat(case, keep_dir, self_check):
         if not cells_close(ref["phy"], drv["phy"], digits):
             diff.append("phy")
         verdict = "ok" if not diff else ("ref_crash" if ref["rc"] < 0 else "MISMATCH")
+        if b"unsupported by the CPU mock" in drv["stderr"]:
+            verdict = "unsupported"
         if verdict == "MISMATCH" and keep_dir:
             dst = os.path.join(keep_dir, "matcase%d" % case["idx"])
             shutil.rmtree(dst, ignore_errors=True)
@@ -349,6 +351,8 @@ def check(case, keep_dir, self_check):
         diff = [k for k in ref if ref[k] != drv[k]]
         # a reference that crashed (signal) or hung (20 s) proves nothing either way
         verdict = "ok" if not diff else ("ref_crash" if ref["rc"] < 0 else "MISMATCH")
+        if b"unsupported by the CPU mock" in drv["stderr"]:
+            verdict = "unsupported"
         # App. B #3: shared-mask mode with an excluded sample -- the reference compares the wrong pairs (the excluded
         # sample's words among them); the driver follows the intended semantics, documented in DESIGN.md
         if verdict == "MISMATCH" and case["tool"] == "dist" and not case["flag"] & 2 and b"# Excluded:" in ref["stderr"]:
@@ -380,9 +384,14 @@ def main():
     ap.add_argument("--budget-s", type=float, default=0.0, help="stop handing out cases after this many seconds")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "fuzz"))
     ap.add_argument("--self", dest="self_check", action="store_true")
+    ap.add_argument("--bin", default=None, help="the driver binary (default ccphylo_b200/bin/ccphylo-b200); tests/csrc/mock_ccg.c "
+                    "gives one that runs on the CPU")
     ap.add_argument("--big", action="store_true", help="192 .. 330 samples x 8 .. 20 kbp: the tensor-core kernel behind the command line")
     ap.add_argument("--mat", action="store_true", help=".mat inputs (cells compared within 1e-6 relative) instead of FASTA")
     a = ap.parse_args()
+    if a.bin:
+        global BIN
+        BIN = a.bin
     os.makedirs(a.out, exist_ok=True)
     idxs = [a.only] if a.only >= 0 else list(range(a.first, a.first + a.cases))
     t0 = time.time()
@@ -398,7 +407,8 @@ def main():
     bad = [r for r in results if r["verdict"] == "MISMATCH"]
     summary = {"seed": a.seed, "cases_run": len(results), "ok": sum(r["verdict"] == "ok" for r in results),
                "reference_crashed": sum(r["verdict"] == "ref_crash" for r in results), "mismatch": len(bad),
-               "known_divergence_3": sum(r["verdict"] == "known_divergence_3" for r in results), "nonzero_rc_both": sum(r["verdict"] == "ok" and r["rc"][0] != 0 for r in results),
+               "known_divergence_3": sum(r["verdict"] == "known_divergence_3" for r in results),
+               "unsupported_by_mock": sum(r["verdict"] == "unsupported" for r in results), "nonzero_rc_both": sum(r["verdict"] == "ok" and r["rc"][0] != 0 for r in results),
                "seconds": round(time.time() - t0, 1), "self_check": a.self_check, "mismatches": bad,
                "ref_crashes": [r for r in results if r["verdict"] == "ref_crash"]}
     with open(os.path.join(a.out, ("summary_mat_seed%d.json" if a.mat else "summary_big_seed%d.json" if a.big else "summary_seed%d.json") % a.seed), "w") as f:

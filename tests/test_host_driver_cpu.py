@@ -1,0 +1,61 @@
+"""The HOST driver end to end without a GPU: ccphylo_b200/host/*.c linked with tests/csrc/mock_ccg.c (the C-ABI answered
+by the oracle on the CPU -- test infrastructure, see its header) and compiled with -fsanitize=address,undefined, then
+driven by scripts/fuzz_cli.py's random command lines against the reference binary: option scanning, FASTA / MSA / gz /
+.mat parsing, the parser pool, gates and messages, -P / -y / -V plumbing, the Phylip writer and the file-backed matrices
+must print the reference's bytes and trip no sanitizer.  (What the mock does not stand in for -- trim, -a, shared-mask
+mode with -P / -y -- is reported as unsupported and skipped; those run on the GPU box, tests/test_cli_fuzz_gpu.py.)"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import fuzz_cli  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not os.path.exists(fuzz_cli.REF_BIN), reason="oracle/_ref/ccphylo was not built (needs /root/reference)")
+HOST = os.path.join(ROOT, "ccphylo_b200", "host")
+SRCS = ["dist_main.c", "trim_main.c", "dist_mat.c", "cmdline.c", "phy_writer.c", "fsa_reader.c", "mat_reader.c", "ordered_pool.c",
+        "motifs.c", "phy_update.c"]
+
+
+@pytest.fixture(scope="module")
+def mock_driver(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("mock") / "ccphylo-b200-mock")
+    cmd = ["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=gnu99", "-Wall",
+           "-Wno-unused-parameter", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle"), "-I", HOST, "-o", exe]
+    cmd += [os.path.join(HOST, s) for s in SRCS]
+    cmd += [os.path.join(ROOT, "tests", "csrc", "mock_ccg.c"), os.path.join(ROOT, "oracle", "fsa_oracle.c"),
+            os.path.join(ROOT, "oracle", "mat_oracle.c"), "-lz", "-lpthread", "-lm"]
+    subprocess.run(cmd, check=True)
+    old, fuzz_cli.BIN = fuzz_cli.BIN, exe
+    os.environ["ASAN_OPTIONS"] = "detect_leaks=0"          # the driver exits without freeing its tables, as the reference does
+    yield exe
+    fuzz_cli.BIN = old
+
+
+def test_fasta_command_lines_under_the_sanitizers(mock_driver, tmp_path):
+    ok = 0
+    for idx in range(160):
+        r = fuzz_cli.check(fuzz_cli.make_case(21, idx), str(tmp_path), False)
+        assert r["verdict"] in ("ok", "ref_crash", "known_divergence_3", "unsupported"), r
+        ok += r["verdict"] == "ok"
+    assert ok >= 80
+
+
+def test_mat_command_lines_under_the_sanitizers(mock_driver, tmp_path):
+    ok = 0
+    for idx in range(160):
+        r = fuzz_cli.check_mat(fuzz_cli.make_mat_case(21, idx), str(tmp_path), False)
+        assert r["verdict"] in ("ok", "ref_crash"), r
+        ok += r["verdict"] == "ok"
+    assert ok >= 150
+
+
+def test_no_overlap_line_only_when_a_gate_can_fail(mock_driver, tmp_path):
+    """-L 0 -C 0: a pair without one comparable position passes the gate (cell 0/0 = -nan, N = 0) and the reference prints no
+    'No sufficient overlap' line (found by this sweep: seed 5, cases 26 and 993)"""
+    for idx in (26, 993):
+        r = fuzz_cli.check_mat(fuzz_cli.make_mat_case(5, idx), str(tmp_path), False)
+        assert r["verdict"] == "ok", r
