@@ -7,8 +7,8 @@
  * ccphylo-b200-mock and lives in the test's temporary directory.
  *
  * Covered: `dist` on FASTA input -- pair mode with -P (per-sample builder, per-pair maskProxi), -y, -V; shared-mask mode
- * without -P / -y; `dist` on .mat input (every -d method).  Everything else (trim, -a, shared-mask -P / -y, device
- * pointers, groups) answers CCG_ERR_UNSUPPORTED.
+ * with -P or -y (not both); `dist` on .mat input (every -d method).  Everything else (trim, -a, shared-mask -P with -y,
+ * device pointers, groups) answers CCG_ERR_UNSUPPORTED.
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -179,13 +179,28 @@ int ccg_mask_motifs(ccg_ctx *c, int first, int count, unsigned *inc_out) {
 }
 
 int ccg_build_global_mask(ccg_ctx *c, const unsigned char *include, unsigned *global_inc) {
-	if(c->proxi || c->nmotifs) return unsupported(c, "shared-mask mode with -P or -y");
-	int any = 0;
-	for(int w = 0; w < c->words; ++w) c->gmask[w] = 0xFFFFFFFFu;
-	for(int i = 0; i < c->n; ++i) {
-		if(!c->present[i] || (include && !include[i])) continue;
-		any = 1;
-		for(int w = 0; w < c->words; ++w) c->gmask[w] &= c->masks[(size_t) i * c->words + w];
+	if(c->proxi && c->nmotifs) return unsupported(c, "shared-mask mode with -P and -y");
+	int any = 0, ref = -1;
+	if(c->proxi) {
+		/* cdist.c:86-112 with -P: initIncPos, then getIncPosPtr(includes[0], seq, ref, proxi) for every included sample,
+		 * ref = the first included one (the proximity events are defined on the sequences, not on the samples' masks) */
+		for(int p = 0; p < c->words * 32; ++p) {
+			if(p % 32 == 0) c->gmask[p / 32] = 0;
+			if(p < c->len) c->gmask[p / 32] |= 1u << (31 - p % 32);
+		}
+		for(int i = 0; i < c->n; ++i) {
+			if(!c->present[i] || (include && !include[i])) continue;
+			if(ref < 0) ref = i;
+			any = 1;
+			orc_inc_pos(c->gmask, c->codes[i], c->codes[ref], c->len, c->proxi, c->snp_only);
+		}
+	} else {
+		for(int w = 0; w < c->words; ++w) c->gmask[w] = 0xFFFFFFFFu;
+		for(int i = 0; i < c->n; ++i) {
+			if(!c->present[i] || (include && !include[i])) continue;
+			any = 1;
+			for(int w = 0; w < c->words; ++w) c->gmask[w] &= c->masks[(size_t) i * c->words + w];
+		}
 	}
 	if(!any) memset(c->gmask, 0, (size_t) c->words * 4);
 	c->have_gmask = 1;
