@@ -126,6 +126,12 @@ static void one_template(const DistOpts *o, ccg_ctx *ctx, int n, char **filename
 	/* the device store is sized by the first usable sample (all samples of a template have its rows) */
 	int have_problem = 0, rc, included = 0;
 	long max_len = 0;
+	/* The union twin (ltdMatrix_get, ltdmatrix.c:32) walks the rows from file 1 on and never loads file 0 as a row: that
+	 * sample meets its gate only when the first later sample that passes streams it as a column (cmpMats returns -2,
+	 * :157-158, include[0] = 0).  So its "did not exceed threshold" line comes at that moment -- and not at all when no
+	 * later sample passes. */
+	const int first_member = 0;
+	int first_line_due = 0;
 	for(int i = 0; i < n; ++i) {
 		MatParsed *r = (MatParsed *) pool_take(pool, i);
 		include[i] = 0;
@@ -142,8 +148,13 @@ static void one_template(const DistOpts *o, ccg_ctx *ctx, int n, char **filename
 		} else if(r->status == 0) {
 			fprintf(stderr, "Template (\"%s\") is not included in:\t%s\n", target, filenames[i]);
 		} else if(r->m.nNucs < o->minLength || r->m.nNucs < o->minCov * (double) r->m.len) {
-			fprintf(stderr, "Template (\"%s\") did not exceed threshold for inclusion:\t%s\n", target, filenames[i]);
+			if(!threaded_msgs && i == first_member) first_line_due = 1;
+			else fprintf(stderr, "Template (\"%s\") did not exceed threshold for inclusion:\t%s\n", target, filenames[i]);
 		} else {
+			if(first_line_due) {
+				fprintf(stderr, "Template (\"%s\") did not exceed threshold for inclusion:\t%s\n", target, filenames[first_member]);
+				first_line_due = 0;
+			}
 			if(!have_problem) {
 				max_len = (long) r->m.len;
 				rc = ccg_mat_set_problem(ctx, n, (int) max_len);

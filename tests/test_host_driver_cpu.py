@@ -53,6 +53,17 @@ def test_mat_command_lines_under_the_sanitizers(mock_driver, tmp_path):
     assert ok >= 150
 
 
+def test_union_command_lines_under_the_sanitizers(mock_driver, tmp_path):
+    """count matrices behind a union file: one block per template row over its own subset of the files; file 0's gate line
+    comes when the first later sample that passes streams it (ltdmatrix.c:157-158), not at all if none does"""
+    for idx in range(160):
+        r = fuzz_cli.check_mat(fuzz_cli.make_union_case(21, idx), str(tmp_path), False)
+        assert r["verdict"] in ("ok", "ref_crash"), r
+    for idx in (111, 120, 313, 523):                      # the cases that showed it
+        r = fuzz_cli.check_mat(fuzz_cli.make_union_case(1, idx), str(tmp_path), False)
+        assert r["verdict"] == "ok", r
+
+
 def test_no_overlap_line_only_when_a_gate_can_fail(mock_driver, tmp_path):
     """-L 0 -C 0: a pair without one comparable position passes the gate (cell 0/0 = -nan, N = 0) and the reference prints no
     'No sufficient overlap' line (found by this sweep: seed 5, cases 26 and 993)"""
