@@ -133,27 +133,57 @@ def make_case(seed, idx, big=False):
     return case
 
 
+NOISE = False        # --noise: FASTA layout variety (line widths, junk bytes the parsers drop, other records around the target)
+
+
+def _record(f, header, row, rng):
+    """one FASTA record; with NOISE: any line width, digits / blanks / '*' inside the lines (dropped by the parser,
+    seqparse.c:217-231), a missing final newline"""
+    f.write(b">" + header + b"\n")
+    if rng is None:
+        for s in range(0, len(row), 60):
+            f.write(row[s:s + 60].tobytes() + b"\n")
+        return
+    width = int(rng.choice([1, 7, 60, 61, 80, 1 << 30]))
+    junk = rng.random() < 0.4
+    body = []
+    for s in range(0, len(row), width):
+        line = row[s:s + width].tobytes()
+        if junk and len(line) > 2 and rng.random() < 0.3:
+            k = int(rng.integers(1, len(line)))
+            line = line[:k] + bytes(rng.choice(np.frombuffer(b" 0123456789*\t", dtype=np.uint8), size=int(rng.integers(1, 4)))) + line[k:]
+        body.append(line)
+    text = b"\n".join(body) + (b"" if rng.random() < 0.2 else b"\n")
+    f.write(text)
+    if not text.endswith(b"\n") :
+        return "open"
+    return None
+
+
 def write_inputs(case, d):
     rows, mode = case["rows"], case["mode"]
     opener = (lambda p: gzip.open(p, "wb")) if mode.endswith("_gz") else (lambda p: open(p, "wb"))
     ext = ".fsa.gz" if mode.endswith("_gz") else ".fsa"
-    width = 60
+    rng = np.random.default_rng([case["idx"], len(rows), 3]) if NOISE else None
     if mode.startswith("msa"):
         path = os.path.join(d, "aln" + ext)
         with opener(path) as f:
             for i, row in enumerate(rows):
-                f.write(b">s%d\n" % i)
-                for s in range(0, len(row), width):
-                    f.write(row[s:s + width].tobytes() + b"\n")
+                if _record(f, b"s%d" % i, row, rng) == "open" and i + 1 < len(rows):
+                    f.write(b"\n")
         inputs = ["-i", path]
     else:
         files = []
         for i, row in enumerate(rows):
             path = os.path.join(d, f"s{i:02d}{ext}")
             with opener(path) as f:
-                f.write(b">ref\n")
-                for s in range(0, len(row), width):
-                    f.write(row[s:s + width].tobytes() + b"\n")
+                if rng is not None and rng.random() < 0.3:            # another record in front of the target
+                    _record(f, b"other_contig", row[: max(1, len(row) // 3)][::-1].copy(), None)
+                state = _record(f, b"ref", row, rng)
+                if rng is not None and rng.random() < 0.3:            # and one behind it
+                    if state == "open":
+                        f.write(b"\n")
+                    _record(f, b"ref2", row[: max(1, len(row) // 2)].copy(), None)
             files.append(path)
         inputs = ["-r", "ref", "-i"] + files
     if case["motifs"]:
@@ -428,12 +458,16 @@ def main():
     ap.add_argument("--bin", default=None, help="the driver binary (default ccphylo_b200/bin/ccphylo-b200); tests/csrc/mock_ccg.c "
                     "gives one that runs on the CPU")
     ap.add_argument("--big", action="store_true", help="192 .. 330 samples x 8 .. 20 kbp: the tensor-core kernel behind the command line")
+    ap.add_argument("--noise", action="store_true", help="FASTA layout variety: line widths, junk bytes, records around the target")
     ap.add_argument("--union", action="store_true", help="with --mat: the count matrices behind a union file")
     ap.add_argument("--mat", action="store_true", help=".mat inputs (cells compared within 1e-6 relative) instead of FASTA")
     a = ap.parse_args()
     if a.bin:
         global BIN
         BIN = a.bin
+    if a.noise:
+        global NOISE
+        NOISE = True
     os.makedirs(a.out, exist_ok=True)
     idxs = [a.only] if a.only >= 0 else list(range(a.first, a.first + a.cases))
     t0 = time.time()
