@@ -445,6 +445,72 @@ def check(case, keep_dir, self_check):
         shutil.rmtree(base, ignore_errors=True)
 
 
+def check_add(seed, idx, keep_dir, self_check):
+    """-a: the reference builds the matrix of the first n - 1 files, then the last file is added to copies of it by the
+    reference and by the driver (add2Matrix dist.c:331-411): the .phy, the .num, the -V listing and sorted stderr must agree"""
+    case = make_case(seed, idx)
+    rng = np.random.default_rng([seed, idx, 5])
+    n = max(3, case["n"])
+    case["rows"] = (case["rows"] * 2)[:n]
+    args = [a for a in case["args"]]
+    for opt, has_value in (("-H", False), ("-x", True), ("-t", True)):
+        while opt in args:
+            k = args.index(opt)
+            del args[k:k + (2 if has_value else 1)]
+    for opt in ("-p", "-s", "-b"):                      # the added row is doubles (dist.c:386-391)
+        while opt in args:
+            k = args.index(opt)
+            del args[k:k + (2 if k + 1 < len(args) and not args[k + 1].startswith("-") else 1)]
+    flag = (case["flag"] | 2) & ~(4 | 16)
+    variants = bool(rng.random() < 0.3)
+    threads = 1 if variants else int(rng.integers(1, 4))
+    base = tempfile.mkdtemp(prefix="fuzza%d_" % idx)
+    try:
+        res = {}
+        for tag, exe in (("reference", REF_BIN), ("driver", REF_BIN if self_check else BIN)):
+            d = os.path.join(base, tag)
+            os.makedirs(d)
+            files = []
+            for i, row in enumerate(case["rows"]):
+                files.append(os.path.join(d, "s%02d.fsa" % i))
+                with open(files[-1], "wb") as f:
+                    _record(f, b"ref", row, None)
+            common = ["-r", "ref", "-f", str(flag)] + args + (["-V", "v.txt"] if variants else [])
+            p0 = subprocess.run([REF_BIN, "dist"] + common + ["-t", "1", "-i"] + files[:-1] + ["-o", "m.phy", "-n", "m.num"], capture_output=True,
+                                cwd=d, timeout=60)
+            if p0.returncode != 0 or not os.path.exists(os.path.join(d, "m.phy")) or os.path.getsize(os.path.join(d, "m.phy")) == 0:
+                return {"idx": idx, "verdict": "ref_crash" if p0.returncode < 0 else "no_matrix", "diff": [], "rc": [p0.returncode, 0], "what": "add"}
+            cmd = [exe, "dist"] + common + ["-t", str(threads), "-a", files[-1], "-i", files[0],
+                                            "-o", "m.phy", "-n", "m.num"]
+            try:
+                p = subprocess.run(cmd, capture_output=True, cwd=d, timeout=60)
+                rc, err = p.returncode, p.stderr
+            except subprocess.TimeoutExpired:
+                rc, err = -999, b"timeout"
+            rd = lambda q: open(os.path.join(d, q), "rb").read() if os.path.exists(os.path.join(d, q)) else None
+            junk = (b"Error: 11 (", b"Will continue with ")
+            lines = sorted(ln for ln in err.replace(d.encode() + b"/", b"").split(b"\n") if not ln.startswith(junk))
+            v = rd("v.txt")
+            res[tag] = {"rc": rc, "stderr": lines, "phy": rd("m.phy"), "num": rd("m.num"), "variants": sorted(v.split(b"\n")) if v else v, "cmd": cmd}
+        ref, drv = res["reference"], res["driver"]
+        diff = [k for k in ("rc", "stderr", "phy", "num", "variants") if ref[k] != drv[k]]
+        verdict = "ok" if not diff else ("ref_crash" if ref["rc"] < 0 else "MISMATCH")
+        if any(b"unsupported by the CPU mock" in ln for ln in drv["stderr"]):
+            verdict = "unsupported"
+        if verdict == "MISMATCH" and keep_dir:
+            dst = os.path.join(keep_dir, "addcase%d" % idx)
+            shutil.rmtree(dst, ignore_errors=True)
+            shutil.copytree(base, dst)
+            with open(os.path.join(dst, "case.json"), "w") as f:
+                json.dump({"idx": idx, "diff": diff, "reference_cmd": ref["cmd"], "driver_cmd": drv["cmd"], "reference_rc": ref["rc"],
+                           "driver_rc": drv["rc"], "reference_stderr": b"\n".join(ref["stderr"]).decode(errors="replace")[-2000:],
+                           "driver_stderr": b"\n".join(drv["stderr"]).decode(errors="replace")[-2000:]}, f, indent=1)
+        return {"idx": idx, "verdict": verdict, "diff": diff, "rc": [ref["rc"], drv["rc"]],
+                "what": "add n=%d L=%d -f %d %s%s" % (n, case["length"], flag, " ".join(args), " -V" if variants else "")}
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seed", type=int, default=1)
@@ -458,6 +524,7 @@ def main():
     ap.add_argument("--bin", default=None, help="the driver binary (default ccphylo_b200/bin/ccphylo-b200); tests/csrc/mock_ccg.c "
                     "gives one that runs on the CPU")
     ap.add_argument("--big", action="store_true", help="192 .. 330 samples x 8 .. 20 kbp: the tensor-core kernel behind the command line")
+    ap.add_argument("--add", action="store_true", help="-a: one more FASTA sample against a matrix the reference built")
     ap.add_argument("--noise", action="store_true", help="FASTA layout variety: line widths, junk bytes, records around the target")
     ap.add_argument("--union", action="store_true", help="with --mat: the count matrices behind a union file")
     ap.add_argument("--mat", action="store_true", help=".mat inputs (cells compared within 1e-6 relative) instead of FASTA")
@@ -475,6 +542,8 @@ def main():
     def job(i):
         if a.budget_s and time.time() - t0 > a.budget_s:
             return None
+        if a.add:
+            return check_add(a.seed, i, a.out, a.self_check)
         if a.mat:
             return check_mat(make_union_case(a.seed, i) if a.union else make_mat_case(a.seed, i), a.out, a.self_check)
         return check(make_case(a.seed, i, a.big), a.out, a.self_check)
@@ -487,7 +556,7 @@ def main():
                "unsupported_by_mock": sum(r["verdict"] == "unsupported" for r in results), "nonzero_rc_both": sum(r["verdict"] == "ok" and r["rc"][0] != 0 for r in results),
                "seconds": round(time.time() - t0, 1), "self_check": a.self_check, "mismatches": bad,
                "ref_crashes": [r for r in results if r["verdict"] == "ref_crash"]}
-    with open(os.path.join(a.out, ("summary_mat_seed%d.json" if a.mat else "summary_big_seed%d.json" if a.big else "summary_seed%d.json") % a.seed), "w") as f:
+    with open(os.path.join(a.out, ("summary_add_seed%d.json" if a.add else "summary_mat_seed%d.json" if a.mat else "summary_big_seed%d.json" if a.big else "summary_seed%d.json") % a.seed), "w") as f:
         json.dump(summary, f, indent=1)
     print(json.dumps({k: v for k, v in summary.items() if k not in ("mismatches", "ref_crashes")}))
     for r in bad[:40]:

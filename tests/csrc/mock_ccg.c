@@ -7,7 +7,7 @@
  * ccphylo-b200-mock and lives in the test's temporary directory.
  *
  * Covered: `dist` on FASTA input -- pair mode with -P (per-sample builder, per-pair maskProxi), -y, -V; shared-mask mode
- * with -P or -y (not both); `dist` on .mat input (every -d method).  Everything else (trim, -a, shared-mask -P with -y,
+ * with -P or -y (not both); `dist` on .mat input (every -d method).  -a on FASTA input.  Everything else (trim, -a on .mat input, shared-mask -P with -y,
  * device pointers, groups) answers CCG_ERR_UNSUPPORTED.
  */
 #include <stdint.h>
@@ -328,11 +328,75 @@ int ccg_mat_run(ccg_ctx *c, const unsigned char *include, int method, unsigned o
 	return CCG_OK;
 }
 
-/* ---- what the mock does not stand in for ---- */
-int ccg_run_row(ccg_ctx *c, int row_slot, unsigned norm, unsigned minLength, double minCov, double *D, double *N, int *cols) {
-	return unsupported(c, "-a");
+/* ---- -a: one row against the slots below it (cmpFsaRowThrd fsacmpthrd.c:482-580, as oracle.fsa_cmp_row restates it): the pair's
+ * mask is the new sample's own mask after its builder, put through the per-sample builder against the column sample ---- */
+static uint32_t *row_pair_mask(const ccg_ctx *c, int row, int j, const uint32_t *own) {
+	uint32_t *m = malloc((size_t) c->words * 4);
+	if(!m) return 0;
+	if(c->proxi) {
+		memcpy(m, own, (size_t) c->words * 4);
+		orc_inc_pos(m, c->codes[j], c->codes[row], c->len, c->proxi, c->snp_only);
+	} else
+		for(int w = 0; w < c->words; ++w) m[w] = own[w] & c->masks[(size_t) j * c->words + w];
+	return m;
 }
-int ccg_list_variants_row(ccg_ctx *c, int row_slot, ccg_variant_fn fn, void *user) { return unsupported(c, "-a with -V"); }
+
+static uint32_t *row_own_mask(const ccg_ctx *c, int row) {
+	uint32_t *own = malloc((size_t) c->words * 4);
+	if(!own) return 0;
+	memcpy(own, c->masks + (size_t) row * c->words, (size_t) c->words * 4);
+	if(c->proxi) orc_inc_pos(own, c->codes[row], c->codes[row], c->len, c->proxi, c->snp_only);
+	return own;
+}
+
+int ccg_run_row(ccg_ctx *c, int row_slot, unsigned norm, unsigned minLength, double minCov, double *D, double *N, int *cols) {
+	if(row_slot < 0 || row_slot >= c->n || !c->present[row_slot]) return CCG_ERR_ARG;
+	if(minLength < minCov * c->len) minLength = (unsigned) (minCov * c->len);
+	uint32_t *own = row_own_mask(c, row_slot), *ones = malloc((size_t) c->words * 4);
+	if(!own || !ones) { free(own); free(ones); return CCG_ERR_NOMEM; }
+	memset(ones, 0xFF, (size_t) c->words * 4);
+	int k = 0;
+	for(int j = 0; j < row_slot; ++j) {
+		if(!c->present[j]) continue;
+		uint32_t *m = row_pair_mask(c, row_slot, j, own), mism = 0, inc = 0;
+		if(!m) { free(own); free(ones); return CCG_ERR_NOMEM; }
+		orc_pair_counts(c->seqs + (size_t) row_slot * c->words, c->seqs + (size_t) j * c->words, m, ones, c->len, &mism, &inc);
+		free(m);
+		if(minLength <= inc) {
+			D[k] = norm ? (double) mism * (double) norm / (double) inc : (double) mism;
+			if(N) N[k] = inc;
+		} else {
+			D[k] = -1.0;
+			if(N) N[k] = 0.0;
+		}
+		++k;
+	}
+	free(own);
+	free(ones);
+	if(cols) *cols = k;
+	return CCG_OK;
+}
+
+int ccg_list_variants_row(ccg_ctx *c, int row_slot, ccg_variant_fn fn, void *user) {
+	if(row_slot < 0 || row_slot >= c->n || !c->present[row_slot]) return CCG_ERR_ARG;
+	uint32_t *own = row_own_mask(c, row_slot);
+	uint64_t *out = malloc(((size_t) c->len + 1) * 8);
+	if(!own || !out) { free(own); free(out); return CCG_ERR_NOMEM; }
+	for(int j = 0; j < row_slot; ++j) {
+		if(!c->present[j]) continue;
+		uint32_t *m = row_pair_mask(c, row_slot, j, own);
+		if(!m) break;
+		const long cnt = orc_list_variants(c->seqs + (size_t) row_slot * c->words, c->seqs + (size_t) j * c->words, m, c->len, out,
+		                                   (long) c->len + 1);
+		free(m);
+		if(cnt > 0 && fn(user, row_slot, j, out, (size_t) cnt)) break;
+	}
+	free(own);
+	free(out);
+	return CCG_OK;
+}
+
+/* ---- what the mock does not stand in for ---- */
 int ccg_mat_run_row(ccg_ctx *c, int row_slot, int method, unsigned order, double alpha, unsigned norm, unsigned minDepth,
                     unsigned minLength, double minCov, double *D, double *N, uint32_t *rows_inc) {
 	return unsupported(c, "-a on .mat input");

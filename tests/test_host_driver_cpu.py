@@ -2,8 +2,9 @@
 by the oracle on the CPU -- test infrastructure, see its header) and compiled with -fsanitize=address,undefined, then
 driven by scripts/fuzz_cli.py's random command lines against the reference binary: option scanning, FASTA / MSA / gz /
 .mat parsing, the parser pool, gates and messages, -P / -y / -V plumbing, the Phylip writer and the file-backed matrices
-must print the reference's bytes and trip no sanitizer.  (What the mock does not stand in for -- trim, -a, shared-mask
-mode with -P / -y -- is reported as unsupported and skipped; those run on the GPU box, tests/test_cli_fuzz_gpu.py.)"""
+must print the reference's bytes and trip no sanitizer.  (What the mock does not stand in for -- trim, -a on
+.mat input, shared-mask mode with -P and -y together -- is reported as unsupported and skipped; those run on the GPU box,
+tests/test_cli_fuzz_gpu.py, tests/test_gpu_trim.py, tests/test_gpu_addrow.py.)"""
 import os
 import subprocess
 import sys
@@ -62,6 +63,17 @@ def test_union_command_lines_under_the_sanitizers(mock_driver, tmp_path):
     for idx in (111, 120, 313, 523):                      # the cases that showed it
         r = fuzz_cli.check_mat(fuzz_cli.make_union_case(1, idx), str(tmp_path), False)
         assert r["verdict"] == "ok", r
+
+
+def test_add_row_command_lines_under_the_sanitizers(mock_driver, tmp_path):
+    """-a: the reference builds a matrix, then one more FASTA sample is added to copies of it by the reference and by the
+    driver (Phylip re-reading, name lookup, the row's gates, -P, -V appended to the listing)"""
+    ok = 0
+    for idx in range(120):
+        r = fuzz_cli.check_add(21, idx, str(tmp_path), False)
+        assert r["verdict"] in ("ok", "ref_crash", "no_matrix"), r
+        ok += r["verdict"] == "ok"
+    assert ok >= 90
 
 
 def test_no_overlap_line_only_when_a_gate_can_fail(mock_driver, tmp_path):
