@@ -319,6 +319,7 @@ def make_union_case(seed, idx):
         a[a.index("-L") + 1] = "1"
     case["mode"] = "union"
     case["union_rows"] = rows
+    case["stdin"] = bool(rng.random() < 0.4)          # `ccphylo union ... | ccphylo dist`: no -i, the union text on stdin
     return case
 
 
@@ -334,8 +335,9 @@ def run_mat(case, exe, d):
             union += t + "\t%d\t" % len(members) + "\t".join(str(k) for k in members) + "\n"
         with open(os.path.join(d, "in.union"), "w") as f:
             f.write(union)
-        cmd = [exe, "dist", "-i", os.path.join(d, "in.union")] + list(case["args"]) + ["-o", os.path.join(d, "o.phy"), "-n", os.path.join(d, "o.num")]
-        return cmd, _run_mat_cmd(cmd, d)
+        src = [] if case.get("stdin") else ["-i", os.path.join(d, "in.union")]
+        cmd = [exe, "dist"] + src + list(case["args"]) + ["-o", os.path.join(d, "o.phy"), "-n", os.path.join(d, "o.num")]
+        return cmd, _run_mat_cmd(cmd, d, os.path.join(d, "in.union") if case.get("stdin") else None)
     files = []
     for k, text in enumerate(case["texts"]):
         path = os.path.join(d, "%c.mat" % (ord("a") + k) + (".gz" if case["mode"] == "mat_gz" else ""))
@@ -349,9 +351,10 @@ def run_mat(case, exe, d):
     return cmd, _run_mat_cmd(cmd, d)
 
 
-def _run_mat_cmd(cmd, d):
+def _run_mat_cmd(cmd, d, stdin_path=None):
     try:
-        p = subprocess.run(cmd, capture_output=True, cwd=d, timeout=20)
+        with open(stdin_path or os.devnull, "rb") as fin:
+            p = subprocess.run(cmd, capture_output=True, cwd=d, timeout=20, stdin=fin)
         rc, out, err = p.returncode, p.stdout, p.stderr
     except subprocess.TimeoutExpired:
         rc, out, err = -999, b"", b"timeout"
