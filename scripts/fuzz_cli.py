@@ -514,6 +514,61 @@ def check_add(seed, idx, keep_dir, self_check):
         shutil.rmtree(base, ignore_errors=True)
 
 
+def check_add_mat(seed, idx, keep_dir, self_check):
+    """-a on .mat input: the reference builds the matrix of the first n - 1 count matrices, the last one is added to copies
+    of it by the reference and by the driver (ltdRow_get ltdmatrix.c:205); new row within 1e-6, old rows untouched"""
+    case = make_mat_case(seed, idx)
+    n = max(3, case["n"])
+    texts = (case["texts"] * 2)[:n]
+    args = list(case["args"])
+    for opt in ("-x", "-t"):
+        if opt in args:
+            k = args.index(opt)
+            del args[k:k + 2]
+    base = tempfile.mkdtemp(prefix="fuzzam%d_" % idx)
+    try:
+        res = {}
+        for tag, exe in (("reference", REF_BIN), ("driver", REF_BIN if self_check else BIN)):
+            d = os.path.join(base, tag)
+            os.makedirs(d)
+            files = []
+            for k, text in enumerate(texts):
+                files.append(os.path.join(d, "%c.mat" % (ord("a") + k)))
+                with open(files[-1], "w") as f:
+                    f.write(text)
+            p0 = subprocess.run([REF_BIN, "dist", "-r", "tmpl", "-t", "1", "-i"] + files[:-1] + args + ["-o", "m.phy", "-n", "m.num"],
+                                capture_output=True, cwd=d, timeout=60)
+            if p0.returncode != 0 or not os.path.exists(os.path.join(d, "m.phy")) or os.path.getsize(os.path.join(d, "m.phy")) == 0:
+                return {"idx": idx, "verdict": "ref_crash" if p0.returncode < 0 else "no_matrix", "diff": [], "rc": [p0.returncode, 0], "what": "add mat"}
+            cmd = [exe, "dist", "-r", "tmpl", "-t", "1", "-a", files[-1], "-i", files[0]] + args + ["-o", "m.phy", "-n", "m.num"]
+            try:
+                p = subprocess.run(cmd, capture_output=True, cwd=d, timeout=60)
+                rc, err = p.returncode, p.stderr
+            except subprocess.TimeoutExpired:
+                rc, err = -999, b"timeout"
+            rd = lambda q: open(os.path.join(d, q), "rb").read() if os.path.exists(os.path.join(d, q)) else None
+            res[tag] = {"rc": rc, "stderr": sorted(err.replace(d.encode() + b"/", b"").split(b"\n")), "phy": rd("m.phy"), "num": rd("m.num"), "cmd": cmd}
+        ref, drv = res["reference"], res["driver"]
+        diff = [k for k in ("rc", "stderr", "num") if ref[k] != drv[k]]
+        if not cells_close(ref["phy"], drv["phy"], 9):
+            diff.append("phy")
+        verdict = "ok" if not diff else ("ref_crash" if ref["rc"] < 0 else "MISMATCH")
+        if any(b"unsupported by the CPU mock" in ln for ln in drv["stderr"]):
+            verdict = "unsupported"
+        if verdict == "MISMATCH" and keep_dir:
+            dst = os.path.join(keep_dir, "addmatcase%d" % idx)
+            shutil.rmtree(dst, ignore_errors=True)
+            shutil.copytree(base, dst)
+            with open(os.path.join(dst, "case.json"), "w") as f:
+                json.dump({"idx": idx, "diff": diff, "reference_cmd": ref["cmd"], "driver_cmd": drv["cmd"], "reference_rc": ref["rc"],
+                           "driver_rc": drv["rc"], "reference_stderr": b"\n".join(ref["stderr"]).decode(errors="replace")[-2000:],
+                           "driver_stderr": b"\n".join(drv["stderr"]).decode(errors="replace")[-2000:]}, f, indent=1)
+        return {"idx": idx, "verdict": verdict, "diff": diff, "rc": [ref["rc"], drv["rc"]],
+                "what": "add mat n=%d L=%d %s" % (n, case["length"], " ".join(args))}
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seed", type=int, default=1)
@@ -546,7 +601,7 @@ def main():
         if a.budget_s and time.time() - t0 > a.budget_s:
             return None
         if a.add:
-            return check_add(a.seed, i, a.out, a.self_check)
+            return check_add_mat(a.seed, i, a.out, a.self_check) if a.mat else check_add(a.seed, i, a.out, a.self_check)
         if a.mat:
             return check_mat(make_union_case(a.seed, i) if a.union else make_mat_case(a.seed, i), a.out, a.self_check)
         return check(make_case(a.seed, i, a.big), a.out, a.self_check)
@@ -559,7 +614,7 @@ def main():
                "unsupported_by_mock": sum(r["verdict"] == "unsupported" for r in results), "nonzero_rc_both": sum(r["verdict"] == "ok" and r["rc"][0] != 0 for r in results),
                "seconds": round(time.time() - t0, 1), "self_check": a.self_check, "mismatches": bad,
                "ref_crashes": [r for r in results if r["verdict"] == "ref_crash"]}
-    with open(os.path.join(a.out, ("summary_add_seed%d.json" if a.add else "summary_mat_seed%d.json" if a.mat else "summary_big_seed%d.json" if a.big else "summary_seed%d.json") % a.seed), "w") as f:
+    with open(os.path.join(a.out, ("summary_add_mat_seed%d.json" if a.add and a.mat else "summary_add_seed%d.json" if a.add else "summary_mat_seed%d.json" if a.mat else "summary_big_seed%d.json" if a.big else "summary_seed%d.json") % a.seed), "w") as f:
         json.dump(summary, f, indent=1)
     print(json.dumps({k: v for k, v in summary.items() if k not in ("mismatches", "ref_crashes")}))
     for r in bad[:40]:

@@ -7,7 +7,7 @@
  * ccphylo-b200-mock and lives in the test's temporary directory.
  *
  * Covered: `dist` on FASTA input -- pair mode with -P (per-sample builder, per-pair maskProxi), -y, -V; shared-mask mode
- * with -P or -y (not both); `dist` on .mat input (every -d method).  -a on FASTA input.  Everything else (trim, -a on .mat input, shared-mask -P with -y,
+ * with -P or -y (not both); `dist` on .mat input (every -d method).  -a.  Everything else (trim, shared-mask -P with -y,
  * device pointers, groups) answers CCG_ERR_UNSUPPORTED.
  */
 #include <stdint.h>
@@ -18,6 +18,8 @@
 #include "ccphylo_gpu.h"
 #include "fsa_oracle.h"
 
+double orc_mat_pair(int method, unsigned order, double alpha, const uint16_t *ci, const uint32_t *ti, int len_i, const uint16_t *cj,
+                    const uint32_t *tj, int len_j, unsigned norm, unsigned minDepth, unsigned minLength, double minCov, unsigned *rows_inc);
 int orc_mat_matrix(int method, unsigned order, double alpha, int n, long lmax, const uint16_t *counts, const uint32_t *totals,
                    const int *lens, const unsigned char *include, unsigned norm, unsigned minDepth, unsigned minLength,
                    double minCov, double *D, double *N);
@@ -397,9 +399,24 @@ int ccg_list_variants_row(ccg_ctx *c, int row_slot, ccg_variant_fn fn, void *use
 }
 
 /* ---- what the mock does not stand in for ---- */
+/* -a on .mat input (cmpMatRowThrd ltdmatrixthrd.c:111-181): the new sample is the loaded one, every column sample is streamed */
 int ccg_mat_run_row(ccg_ctx *c, int row_slot, int method, unsigned order, double alpha, unsigned norm, unsigned minDepth,
                     unsigned minLength, double minCov, double *D, double *N, uint32_t *rows_inc) {
-	return unsupported(c, "-a on .mat input");
+	if(row_slot < 0 || row_slot >= c->mat_n || !c->mat_present[row_slot]) return CCG_ERR_ARG;
+	const size_t L = (size_t) c->mat_max;
+	for(int j = 0; j < row_slot; ++j) {
+		unsigned rows = 0;
+		double v = -1.0;
+		if(c->mat_present[j])
+			v = orc_mat_pair(method, order, alpha, c->mat_counts + 6 * L * row_slot, c->mat_totals + L * row_slot, c->mat_lens[row_slot],
+			                 c->mat_counts + 6 * L * j, c->mat_totals + L * j, c->mat_lens[j], norm, minDepth, minLength, minCov, &rows);
+		if(v == -2.0) return unsupported(c, "a column sample that fails its own gate (the caller checks that first)");
+		if(v == -1.0) rows = 0;
+		D[j] = v;
+		if(N) N[j] = rows;
+		if(rows_inc) rows_inc[j] = rows;
+	}
+	return CCG_OK;
 }
 int ccg_trim_begin(ccg_ctx *c, int len, unsigned proxi) { return unsupported(c, "trim"); }
 int ccg_trim_sample(ccg_ctx *c, const unsigned char *codes, const uint64_t *nibbles, int against_ref, int builder, unsigned *inc_out) {

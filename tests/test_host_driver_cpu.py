@@ -2,9 +2,9 @@
 by the oracle on the CPU -- test infrastructure, see its header) and compiled with -fsanitize=address,undefined, then
 driven by scripts/fuzz_cli.py's random command lines against the reference binary: option scanning, FASTA / MSA / gz /
 .mat parsing, the parser pool, gates and messages, -P / -y / -V plumbing, the Phylip writer and the file-backed matrices
-must print the reference's bytes and trip no sanitizer.  (What the mock does not stand in for -- trim, -a on
-.mat input, shared-mask mode with -P and -y together -- is reported as unsupported and skipped; those run on the GPU box,
-tests/test_cli_fuzz_gpu.py, tests/test_gpu_trim.py, tests/test_gpu_addrow.py.)"""
+must print the reference's bytes and trip no sanitizer.  (What the mock does not stand in for -- trim,
+shared-mask mode with -P and -y together -- is reported as unsupported and skipped; those run on the GPU box,
+tests/test_cli_fuzz_gpu.py, tests/test_gpu_trim.py.)"""
 import os
 import subprocess
 import sys
@@ -74,6 +74,16 @@ def test_add_row_command_lines_under_the_sanitizers(mock_driver, tmp_path):
         assert r["verdict"] in ("ok", "ref_crash", "no_matrix"), r
         ok += r["verdict"] == "ok"
     assert ok >= 90
+
+
+def test_add_mat_row_command_lines_under_the_sanitizers(mock_driver, tmp_path):
+    """-a on .mat input: one more count matrix against a matrix the reference built"""
+    ok = 0
+    for idx in range(100):
+        r = fuzz_cli.check_add_mat(21, idx, str(tmp_path), False)
+        assert r["verdict"] in ("ok", "ref_crash", "no_matrix"), r
+        ok += r["verdict"] == "ok"
+    assert ok >= 60
 
 
 def test_no_overlap_line_only_when_a_gate_can_fail(mock_driver, tmp_path):
