@@ -12,7 +12,7 @@ import helpers
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "ccphylo_b200", "bin", "ccphylo-b200")
+BIN = os.environ.get("CCPHYLO_TEST_BIN") or os.path.join(ROOT, "ccphylo_b200", "bin", "ccphylo-b200")   # (tests/csrc/mock_ccg.c gives a CPU driver)
 
 POOL, ALL_CASES = helpers.golden_cases()
 # every invocation pays a CUDA context start (~2 s): replay a representative third of the fixture here; the
@@ -51,7 +51,8 @@ def test_fasta_golden_byte_for_byte(built, tmp_path, case):
     assert p.stderr.replace(td + "/", "") == case["stderr"]
 
 
-REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu")
+# (with a CPU driver from tests/csrc/mock_ccg.c there is no device for the bound reference either)
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu" if not os.environ.get("CCPHYLO_TEST_BIN") else "ccphylo_gpu.absent")
 BOUND = [c for c in ALL_CASES if c["name"].startswith(("c1_pair", "c1_global", "c1_float", "c1_short_W", "c6_", "c7_",
                                                        "rand_L129_", "rand_L4100_pair"))]
 

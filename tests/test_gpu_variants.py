@@ -12,7 +12,7 @@ from ccphylo_b200 import api, synth
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "ccphylo_b200", "bin", "ccphylo-b200")
+BIN = os.environ.get("CCPHYLO_TEST_BIN") or os.path.join(ROOT, "ccphylo_b200", "bin", "ccphylo-b200")   # (tests/csrc/mock_ccg.c gives a CPU driver)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ccphylo")
 
 
@@ -157,7 +157,8 @@ def test_cli_variant_file_against_the_reference_binary(built, tmp_path, msa, fla
     assert outs["driver"] == outs["reference"]
 
 
-REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu")
+# (with a CPU driver from tests/csrc/mock_ccg.c there is no device for the bound reference either)
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu" if not os.environ.get("CCPHYLO_TEST_BIN") else "ccphylo_gpu.absent")
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(REF_GPU)), reason="oracle/_ref was not built (needs /root/reference)")

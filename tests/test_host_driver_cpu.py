@@ -92,3 +92,17 @@ def test_no_overlap_line_only_when_a_gate_can_fail(mock_driver, tmp_path):
     for idx in (26, 993):
         r = fuzz_cli.check_mat(fuzz_cli.make_mat_case(5, idx), str(tmp_path), False)
         assert r["verdict"] == "ok", r
+
+
+def test_the_gpu_box_cli_tests_on_the_cpu_driver(mock_driver):
+    """the command-line tests of the GPU suite (golden FASTA / .mat / union text, MSA plain and gz, -P, -y, -V, -a, -H,
+    long options, the union | dist | tree pipe) with the CPU driver in the place of ccphylo-b200: CCPHYLO_TEST_BIN"""
+    env = dict(os.environ, CCPHYLO_TEST_BIN=mock_driver, ASAN_OPTIONS="detect_leaks=0")
+    keep = ("(golden or cli or against_the_reference_binary or pipe or msa or option or file_backed or gz_input) and not bound "
+            "and not several_gpus and not config1 and not motifs_with_proximity")
+    p = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-k", keep, "-p", "no:cacheprovider",
+                        os.path.join(ROOT, "tests", "test_cli_gpu.py"), os.path.join(ROOT, "tests", "test_gpu_addrow.py"),
+                        os.path.join(ROOT, "tests", "test_gpu_motifs.py"), os.path.join(ROOT, "tests", "test_gpu_variants.py")],
+                       capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert " passed" in p.stdout and int(p.stdout.rsplit(" passed", 1)[0].split()[-1]) >= 100, p.stdout[-500:]
