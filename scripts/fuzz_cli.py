@@ -8,6 +8,11 @@ combinations nobody thought of.  Every case is reproducible from (seed, index): 
 `--self` compares the reference with itself (generator check on a box without a GPU).  Mismatching cases are
 written to <out>/case<K>/ with their inputs, both command lines and both outputs.
 
+Modes: default FASTA (`dist` / `trim`), --big (tensor-kernel sizes), --noise (FASTA layout variety), --mat (.mat files),
+--mat --union (union files, a third of them on stdin), --add / --add --mat (-a against a matrix the reference built).
+--bin PATH swaps the driver binary: tests/test_host_driver_cpu.py links host/*.c with tests/csrc/mock_ccg.c (the C-ABI
+answered by the oracle) so the same sweeps run on a box without a GPU, under the sanitizers.
+
 Known reference defects the generator stays away from: #3 shared-mask mode with excluded
 samples (only -C 0 -L 1 there), #8 a gzip file as first input without flag 16, #16 unmapped bytes.
 """
