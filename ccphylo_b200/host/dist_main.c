@@ -583,6 +583,14 @@ static void dist_fasta_msa(const DistOpts *o, FILE *outfile, FILE *noutfile) {
 		if(noutfile) fflush(noutfile);
 		exit(0);
 	}
+	if(n == 1 && o->mmap_matrix) {
+		/* one record kept and -H: the reference sizes its file-backed matrix for 0 cells, seeks to byte -1 of the
+		 * temporary file and leaves through ERROR() (matrix.c:150-155, cdist.c:333) */
+		errno = EINVAL;
+		fflush(outfile);
+		if(noutfile) fflush(noutfile);
+		die_errno();
+	}
 	/* excluded records were dropped: the n kept samples occupy slots 0..n-1 */
 	unsigned char *include = malloc((size_t) (nrec ? nrec : 1));
 	if(!include) die_errno();

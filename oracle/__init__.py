@@ -54,6 +54,8 @@ def lib():
         L.orc_and_known.argtypes = [_u32p, _u8p, _u8p, C.c_int]
         L.orc_inc_pos.restype = None
         L.orc_inc_pos.argtypes = [_u32p, _u8p, _u8p, C.c_int, C.c_uint, C.c_int]
+        L.orc_trim_pass.restype = None
+        L.orc_trim_pass.argtypes = [_u32p, _u8p, C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p]
         L.orc_pair_counts_proxi.restype = None
         L.orc_pair_counts_proxi.argtypes = [_u64p, _u64p, _u32p, _u32p, C.c_int, C.c_uint, C.POINTER(C.c_uint32),
                                             C.POINTER(C.c_uint32)]
@@ -172,6 +174,17 @@ def inc_pos(mask, seq_codes, ref_codes, proxi=0, variant=0):
     ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint8)
     if len(seq_codes):
         lib().orc_inc_pos(mask, seq_codes, ref_codes, len(seq_codes), proxi, variant)
+    return mask
+
+
+def trim_pass(mask, seq_codes, ref_codes=None, proxi=0, builder=0, columns=None):
+    """`ccphylo trim`: one sample's pass over `mask` on trim's alphabet (orc_trim_pass; in place).  seq_codes is modified
+    as the reference modifies it (soft flags stripped); ref_codes None = the sample against itself."""
+    assert seq_codes.dtype == np.uint8 and seq_codes.flags.c_contiguous
+    ref_ptr = None if ref_codes is None else np.ascontiguousarray(ref_codes, dtype=np.uint8).ctypes.data
+    col_ptr = None if columns is None else columns.ctypes.data
+    if len(seq_codes):
+        lib().orc_trim_pass(mask, seq_codes, ref_ptr, len(seq_codes), proxi, builder, col_ptr)
     return mask
 
 

@@ -243,6 +243,42 @@ void orc_inc_pos(uint32_t *mask, const unsigned char *seq_codes, const unsigned 
 	}
 }
 
+/* (reference fsacmp.c:181-353 on the code bytes of getIupacBitTable, as fsaTrim trim.c:77-260 calls them)
+ * Per position, c = the sample's byte, r = the reference sample's stored byte (its own pass stripped every soft flag):
+ *   getIncPos            event: c != r, c unknown or c soft;  cleared: c or r unknown, or c soft (then c &= 15 unless unknown)
+ *   getIncPosInsigPrune  cleared: c or r unknown, or c soft (c &= 15 as above) -- no event there;  otherwise event: c != r
+ *   getIncPosInsig       cleared: c or r unknown;  otherwise event: c != r (a soft c differs from the stripped r)
+ * The sample against itself is getIncPos with r = c: unknown and soft positions are cleared and are events, every
+ * soft flag goes.  Ranges as in orc_inc_pos. */
+void orc_trim_pass(uint32_t *mask, unsigned char *seq, const unsigned char *ref, int len, unsigned proxi, int builder,
+                   uint32_t *columns) {
+	long p, last = -1;
+
+	for(p = 0; p < len; ++p) {
+		const unsigned c = seq[p], r = ref ? ref[p] : (unsigned) (seq[p] & 15u);
+		const int unknown = c == 4 || r == 4, soft = (c & 16u) != 0;
+		int event, clear;
+		if(!ref || builder == 0) {
+			event = c != r || c == 4 || soft;
+			clear = unknown || soft;
+			if(!unknown && soft) seq[p] = (unsigned char) (c & 15u);
+		} else if(builder == 2) {
+			clear = unknown || soft;
+			event = !clear && c != r;
+			if(!unknown && soft) seq[p] = (unsigned char) (c & 15u);
+		} else {
+			clear = unknown;
+			event = !clear && c != r;
+		}
+		if(clear) mask[p >> 5] &= ~(1u << (31 - (p & 31)));
+		if(columns && ref && seq[p] != r) columns[p >> 5] |= 1u << (31 - (p & 31));
+		if(event) {
+			if(last >= 0 && (unsigned long) (p - last) <= proxi) clear_range(mask, last, p, len);
+			last = p;
+		}
+	}
+}
+
 /* (reference fsacmp.c:355-485 maskProxi with proxi > 0, then :587-633 fsacmpair)
  * inc = inc_i & inc_j; the SNPs of the pair are the included positions whose 2-bit codes differ.  The
  * reference walks them from the last to the first with a position counter that is one too high, so for

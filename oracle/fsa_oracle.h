@@ -70,6 +70,17 @@ void orc_pair_counts_proxi(const uint64_t *seq_i, const uint64_t *seq_j,
                            const uint32_t *inc_i, const uint32_t *inc_j, int len,
                            unsigned proxi, uint32_t *mism, uint32_t *ninc);
 
+/* `ccphylo trim` (fsaTrim trim.c:77-260): one sample's pass over an inclusion mask on trim's alphabet (getIupacBitTable
+ * fsacmp.c:93-162: 0-3 bases, 4 unknown, 5 gap, 6-15 ambiguity letters, +16 = soft-masked input).  ref == NULL: the sample
+ * against itself, getIncPos(includes, seq, seq, proxi) (trim.c:183,201).  Otherwise builder 0 = getIncPos (fsacmp.c:181),
+ * 1 = getIncPosInsig (:297, flag 8), 2 = getIncPosInsigPrune (:240, flag 32) against the reference sample's stored bytes.
+ * Clears unknown / soft-masked positions as the builder does, then everything from an event to the next one at most proxi
+ * later (both inclusive); strips the soft flag of `seq` where the reference strips it (the bytes trim prints and
+ * pseudoAlnPrune fsacmp.c:504 compares); ORs into `columns` (may be NULL) the positions where the stored byte differs
+ * from the reference sample's. */
+void orc_trim_pass(uint32_t *mask, unsigned char *seq, const unsigned char *ref, int len, unsigned proxi, int builder,
+                   uint32_t *columns);
+
 /* meth.c:141-159 maskMotifs (-y) with the motif list of methparse.c:268 getMethMotifs: nmotifs motifs (the file's
  * motifs and their reverse complements), motif m has lens[m] <= 32 positions whose codes follow each other in
  * `sets`: bits 0..3 = the bases A, C, G, T the position accepts, bit 4 = methylation site.  Wherever a motif

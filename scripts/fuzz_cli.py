@@ -436,6 +436,13 @@ def check(case, keep_dir, self_check):
         # sample's words among them); the driver follows the intended semantics, documented in DESIGN.md
         if verdict == "MISMATCH" and case["tool"] == "dist" and not case["flag"] & 2 and b"# Excluded:" in ref["stderr"]:
             verdict = "known_divergence_3"
+        # trim -f 8 without -f 1 / -f 4: the reference leaves the soft flag on the letters it prints and indexes past its
+        # 16-letter table (trim.c:40,50,60-64): bytes from beyond `bases`; the driver prints the letter (host/trim_main.c)
+        # (the same beside an unknown base of the reference sample whatever the flags say: only -f 1 / -f 4 have no soft letters)
+        if (verdict == "MISMATCH" and case["tool"] == "trim" and diff == ["trim"] and not case["flag"] & 5
+                and len(ref["trim"]) == len(drv["trim"])
+                and all(65 <= (y & ~32) <= 90 for x, y in zip(ref["trim"], drv["trim"]) if x != y)):
+            verdict = "known_trim_soft_letters"
         if verdict == "MISMATCH" and keep_dir:
             dst = os.path.join(keep_dir, "case%d" % case["idx"])
             shutil.rmtree(dst, ignore_errors=True)
@@ -616,7 +623,8 @@ def main():
     summary = {"seed": a.seed, "cases_run": len(results), "ok": sum(r["verdict"] == "ok" for r in results),
                "reference_crashed": sum(r["verdict"] == "ref_crash" for r in results), "mismatch": len(bad),
                "known_divergence_3": sum(r["verdict"] == "known_divergence_3" for r in results),
-               "unsupported_by_mock": sum(r["verdict"] == "unsupported" for r in results), "nonzero_rc_both": sum(r["verdict"] == "ok" and r["rc"][0] != 0 for r in results),
+               "unsupported_by_mock": sum(r["verdict"] == "unsupported" for r in results),
+               "known_trim_soft_letters": sum(r["verdict"] == "known_trim_soft_letters" for r in results), "nonzero_rc_both": sum(r["verdict"] == "ok" and r["rc"][0] != 0 for r in results),
                "seconds": round(time.time() - t0, 1), "self_check": a.self_check, "mismatches": bad,
                "ref_crashes": [r for r in results if r["verdict"] == "ref_crash"]}
     with open(os.path.join(a.out, ("summary_add_mat_seed%d.json" if a.add and a.mat else "summary_add_seed%d.json" if a.add else "summary_mat_seed%d.json" if a.mat else "summary_big_seed%d.json" if a.big else "summary_seed%d.json") % a.seed), "w") as f:

@@ -7,8 +7,8 @@
  * ccphylo-b200-mock and lives in the test's temporary directory.
  *
  * Covered: `dist` on FASTA input -- pair mode with -P (per-sample builder, per-pair maskProxi), -y, -V; shared-mask mode
- * with -P or -y (not both); `dist` on .mat input (every -d method).  -a.  Everything else (trim, shared-mask -P with -y,
- * device pointers, groups) answers CCG_ERR_UNSUPPORTED.
+ * with -P or -y (not both); `dist` on .mat input (every -d method); -a; `trim` (orc_trim_pass).  Everything else
+ * (shared-mask -P with -y, device pointers, groups) answers CCG_ERR_UNSUPPORTED.
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -43,6 +43,11 @@ struct ccg_ctx {
 	uint32_t *mat_totals;
 	int *mat_lens;
 	unsigned char *mat_present;
+	/* trim */
+	int t_len, t_words, t_has_ref;
+	unsigned t_proxi;
+	uint32_t *t_mask, *t_cols;
+	unsigned char *t_cur, *t_ref;
 	char err[256];
 };
 
@@ -91,6 +96,7 @@ void ccg_destroy(ccg_ctx *c) {
 	if(!c) return;
 	free_problem(c);
 	free_mat(c);
+	free(c->t_mask); free(c->t_cols); free(c->t_cur); free(c->t_ref);
 	free(c->mlens);
 	free(c->msets);
 	free(c);
@@ -418,12 +424,64 @@ int ccg_mat_run_row(ccg_ctx *c, int row_slot, int method, unsigned order, double
 	}
 	return CCG_OK;
 }
-int ccg_trim_begin(ccg_ctx *c, int len, unsigned proxi) { return unsupported(c, "trim"); }
+/* ---- trim: orc_trim_pass behind the ccg_trim_* calls (see include/ccphylo_gpu.h for the order of the calls) ---- */
+static void trim_free(ccg_ctx *c) {
+	free(c->t_mask); free(c->t_cols); free(c->t_cur); free(c->t_ref);
+	c->t_mask = c->t_cols = 0;
+	c->t_cur = c->t_ref = 0;
+	c->t_has_ref = 0;
+}
+
+int ccg_trim_begin(ccg_ctx *c, int len, unsigned proxi) {
+	trim_free(c);
+	c->t_len = len;
+	c->t_words = orc_words(len) > 0 ? orc_words(len) : 1;
+	c->t_proxi = proxi;
+	c->t_mask = calloc((size_t) c->t_words, 4);
+	c->t_cols = calloc((size_t) c->t_words, 4);
+	c->t_cur = calloc((size_t) len + 1, 1);
+	c->t_ref = calloc((size_t) len + 1, 1);
+	return (c->t_mask && c->t_cols && c->t_cur && c->t_ref) ? CCG_OK : CCG_ERR_NOMEM;
+}
+
 int ccg_trim_sample(ccg_ctx *c, const unsigned char *codes, const uint64_t *nibbles, int against_ref, int builder, unsigned *inc_out) {
-	return unsupported(c, "trim");
+	if(!c->t_mask || (against_ref && !c->t_has_ref) || builder < 0 || builder > 2) return CCG_ERR_ARG;
+	const int len = c->t_len, W = c->t_words;
+	if(len) memcpy(c->t_cur, codes, (size_t) len);
+	if(!against_ref)
+		for(int p = 0; p < W * 32; ++p) {                       /* initIncPos (fsacmp.c:164) */
+			if(p % 32 == 0) c->t_mask[p / 32] = 0;
+			if(p < len) c->t_mask[p / 32] |= 1u << (31 - p % 32);
+		}
+	orc_trim_pass(c->t_mask, c->t_cur, against_ref ? c->t_ref : 0, len, c->t_proxi, builder, against_ref ? c->t_cols : 0);
+	if(c->nmotifs && len) {
+		if(!nibbles) return CCG_ERR_ARG;
+		orc_mask_motifs(nibbles, c->t_mask, len, c->nmotifs, c->mlens, c->msets);
+	}
+	if(inc_out) *inc_out = (unsigned) orc_mask_count(c->t_mask, len);
+	return CCG_OK;
 }
-int ccg_trim_keep_reference(ccg_ctx *c) { return unsupported(c, "trim"); }
+
+int ccg_trim_keep_reference(ccg_ctx *c) {
+	if(!c->t_mask) return CCG_ERR_ARG;
+	for(int p = 0; p < c->t_len; ++p) c->t_ref[p] = (unsigned char) (c->t_cur[p] & 15u);
+	c->t_has_ref = 1;
+	return CCG_OK;
+}
+
 int ccg_trim_get_mask(ccg_ctx *c, int variable_columns_only, uint32_t *mask_out, unsigned *inc_out, unsigned *var_out) {
-	return unsupported(c, "trim");
+	if(!c->t_mask) return CCG_ERR_ARG;
+	unsigned var = 0;
+	for(int w = 0; w < orc_words(c->t_len); ++w) {
+		var += (unsigned) __builtin_popcount(c->t_mask[w] & c->t_cols[w]);
+		if(mask_out) mask_out[w] = variable_columns_only ? (c->t_mask[w] & c->t_cols[w]) : c->t_mask[w];
+	}
+	if(inc_out) *inc_out = (unsigned) orc_mask_count(c->t_mask, c->t_len);
+	if(var_out) *var_out = var;
+	return CCG_OK;
 }
-int ccg_trim_end(ccg_ctx *c) { return CCG_OK; }
+
+int ccg_trim_end(ccg_ctx *c) {
+	trim_free(c);
+	return CCG_OK;
+}

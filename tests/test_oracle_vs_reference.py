@@ -141,6 +141,44 @@ def test_per_sample_builders_with_proximity(built, flag, proxi):
             assert pad[len(want)] == 0
 
 
+@pytest.mark.parametrize("flag,builder", [(1, 0), (8, 1), (32, 2)], ids=["getIncPos", "getIncPosInsig", "getIncPosInsigPrune"])
+@pytest.mark.parametrize("proxi", [0, 1, 2, 5, 31, 33, 100, 5000])
+def test_trim_pass_on_the_iupac_alphabet(built, flag, builder, proxi):
+    """orc_trim_pass (what `trim` does per sample, on getIupacBitTable's codes: 0-3 bases, 4 unknown, 5 gap, 6-15
+    ambiguity letters, +16 soft-masked) against the reference's own getIncPos / getIncPosInsig / getIncPosInsigPrune:
+    the sample against itself, and a later sample against the stored reference sample (soft flags stripped)"""
+    rng = np.random.default_rng(flag * 1000 + proxi)
+    for length in (1, 31, 32, 64, 97, 1500):
+        base = rng.integers(0, 4, size=length).astype(np.uint8)
+
+        def sample():
+            c = base.copy()
+            sub = rng.random(length) < 0.05
+            c[sub] = rng.integers(0, 16, size=int(sub.sum()))                 # substitutions, unknowns, gaps, ambiguity letters
+            soft = (rng.random(length) < 0.05) & (c != 4)
+            c[soft] |= 16
+            if length:
+                c[-1] &= 3
+            return c
+
+        first, later = sample(), sample()
+        # the sample against itself (trim.c:201: always getIncPos)
+        want = np.zeros(oracle.words(length) + 1, np.uint32)
+        want[:-1] = oracle.full_mask(length)
+        oracle.ref_inc_pos(want, first, first, proxi, 1)
+        got = oracle.full_mask(length).copy()
+        stored = first.copy()
+        oracle.trim_pass(got, stored, None, proxi, 0)
+        assert np.array_equal(got, want[:-1]) and want[-1] == 0, (length, "self")
+        assert np.array_equal(stored, first & 15)
+        # a later sample against it, on the running mask (trim.c:176-177)
+        want2 = want.copy()
+        oracle.ref_inc_pos(want2, later, stored, proxi, flag)
+        got2 = got.copy()
+        oracle.trim_pass(got2, later.copy(), stored, proxi, builder)
+        assert np.array_equal(got2, want2[:-1]) and want2[-1] == 0, (length, "against the reference sample")
+
+
 @pytest.mark.parametrize("proxi", [1, 2, 3, 7, 31, 32, 33, 64, 200, 100000])
 def test_pair_counts_with_proximity(built, proxi):
     for length in (2, 33, 64, 96, 127, 1000, 3001):
