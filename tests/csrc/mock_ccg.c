@@ -155,10 +155,49 @@ int ccg_put_sample_codes(ccg_ctx *c, int idx, const unsigned char *codes) {
 	return CCG_OK;
 }
 
+/* packed rows as the reference holds them (the integration stub's way in); no code bytes: what needs them
+ * (ccg_sample_proximity, shared-mask -P) is not available on such a store */
+int ccg_put_samples_packed(ccg_ctx *c, int first, int count, const uint64_t *const *seqs, const uint32_t *const *includes) {
+	for(int k = 0; k < count; ++k) {
+		const int s = first + k;
+		if(s < 0 || s >= c->n) return CCG_ERR_ARG;
+		if(!seqs[k] || (c->pair && (!includes || !includes[k]))) { c->present[s] = 0; continue; }
+		memcpy(c->seqs + (size_t) s * c->words, seqs[k], (size_t) orc_words(c->len) * 8);
+		if(c->pair) memcpy(c->masks + (size_t) s * c->words, includes[k], (size_t) orc_words(c->len) * 4);
+		c->present[s] = 1;
+	}
+	return CCG_OK;
+}
+
+/* the one-call drop-in with fsaCmpThreadOut's argument list */
+int ccg_fsa_cmp_thread_out(ccg_ctx *c, int pair, void *D, void *N, int elem_size, double byteScale, int n, int len,
+                           const uint64_t *const *seqs, const unsigned char *include, const uint32_t *const *includes, unsigned norm,
+                           unsigned minLength, double minCov, unsigned proxi, int *Dn, unsigned *global_inc) {
+	int rc = ccg_set_proximity(c, proxi, 0);
+	if(!rc) rc = ccg_set_problem(c, n, len, 1);
+	if(rc) return rc;
+	const uint64_t **s = malloc((size_t) (n ? n : 1) * sizeof(*s));
+	const uint32_t **m = malloc((size_t) (n ? n : 1) * sizeof(*m));
+	if(!s || !m) { free(s); free(m); return CCG_ERR_NOMEM; }
+	for(int i = 0; i < n; ++i) {
+		const int in = !include || include[i];
+		s[i] = in ? seqs[i] : 0;
+		m[i] = in ? (pair ? includes[i] : includes[0]) : 0;
+	}
+	rc = ccg_put_samples_packed(c, 0, n, s, m);
+	free(s);
+	free(m);
+	if(rc) return rc;
+	if(pair) return ccg_run_pair(c, include, norm, minLength, minCov, elem_size, byteScale, D, N, Dn);
+	memcpy(c->gmask, includes[0], (size_t) orc_words(len) * 4);
+	c->have_gmask = 1;
+	return ccg_run_global(c, include, norm, elem_size, byteScale, D, Dn, global_inc);
+}
+
 int ccg_sample_proximity(ccg_ctx *c, int first, int count, int apply, unsigned *inc_out) {
 	for(int k = 0; k < count; ++k) {
 		const int s = first + k;
-		if(s < 0 || s >= c->n || !c->present[s]) return CCG_ERR_ARG;
+		if(s < 0 || s >= c->n || !c->present[s] || !c->codes[s]) return CCG_ERR_ARG;
 		uint32_t *m = c->masks + (size_t) s * c->words, *tmp = 0;
 		if(!apply) {
 			tmp = malloc((size_t) c->words * 4);

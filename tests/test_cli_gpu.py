@@ -52,7 +52,7 @@ def test_fasta_golden_byte_for_byte(built, tmp_path, case):
 
 
 # (with a CPU driver from tests/csrc/mock_ccg.c there is no device for the bound reference either)
-REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu" if not os.environ.get("CCPHYLO_TEST_BIN") else "ccphylo_gpu.absent")
+REF_GPU = os.environ.get("CCPHYLO_TEST_REF_GPU") or os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu" if not os.environ.get("CCPHYLO_TEST_BIN") else "ccphylo_gpu.absent")
 BOUND = [c for c in ALL_CASES if c["name"].startswith(("c1_pair", "c1_global", "c1_float", "c1_short_W", "c6_", "c7_",
                                                        "rand_L129_", "rand_L4100_pair"))]
 

@@ -158,7 +158,7 @@ def test_cli_variant_file_against_the_reference_binary(built, tmp_path, msa, fla
 
 
 # (with a CPU driver from tests/csrc/mock_ccg.c there is no device for the bound reference either)
-REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu" if not os.environ.get("CCPHYLO_TEST_BIN") else "ccphylo_gpu.absent")
+REF_GPU = os.environ.get("CCPHYLO_TEST_REF_GPU") or os.path.join(ROOT, "oracle", "_ref", "ccphylo_gpu" if not os.environ.get("CCPHYLO_TEST_BIN") else "ccphylo_gpu.absent")
 
 
 @pytest.mark.skipif(not (os.path.exists(REF_BIN) and os.path.exists(REF_GPU)), reason="oracle/_ref was not built (needs /root/reference)")
